@@ -1,0 +1,241 @@
+/* nvorbis_b200.h -- C ABI of the B200 Vorbis synthesis path.
+ *
+ * What this replaces in the reference (NVorbis, C#; file:line relative to NVorbis/):
+ *   the SYNTHESIS half of one audio packet, batched over K packets:
+ *     Residue0/1/2.WriteVectors  `res[o] += book[entry,dim]`   Residue0.cs:180-201, Residue1.cs:8-26, Residue2.cs:23-47
+ *     inverse channel coupling                                  Mapping.cs:137-182
+ *     Floor1.Apply (UnwrapPosts + RenderLineMulti)              Floor1.cs:186-341
+ *     Mdct.Reverse                                              Mdct.cs:13-21,65-535
+ *     window multiply                                           Mode.cs:159-166
+ *     OverlapBuffers / ClippingCopyBuffer / CopyBuffer          StreamDecoder.cs:391-415,532-541
+ *   i.e. everything IMode.Decode (Contracts/IMode.cs:8) does after the bits have been read, plus
+ *   the overlap/clip/interleave loop of StreamDecoder.Read (StreamDecoder.cs:320-389).
+ *
+ * What stays on the host (the caller): Ogg paging, header parsing, Huffman/codebook bit
+ * unpacking (Codebook.DecodeScalar, Floor1.Unpack, the class/entry reads of Residue0.Decode,
+ * Mode.GetPacketInfo) and the EOS trim (StreamDecoder.cs:429-437).  The host hands over, per
+ * packet, exactly the values those functions produce -- see nvb_frame / nvb_batch.
+ *
+ * All functions are cdecl, take plain pointers/sizes, never throw, and return an nvb_status.
+ * A context is single-threaded (like a reference StreamDecoder); several contexts may coexist.
+ */
+#ifndef NVORBIS_B200_H
+#define NVORBIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVB_ABI_VERSION 1
+
+#define NVB_MAX_CHANNELS   8     /* reference allows 255 (StreamDecoder.cs:186); larger -> NVB_ERR_UNSUPPORTED */
+#define NVB_MAX_POSTS      64    /* Floor1.Data.Posts = new int[64]            (Floor1.cs:12)   */
+#define NVB_MAX_CLASSES    64    /* residue classifications: 6 bits + 1         (Residue0.cs:41) */
+#define NVB_MAX_STAGES     8     /* cascade: 3 + 5 bits                          (Residue0.cs:48-56) */
+#define NVB_MAX_COUPLING   32    /* reference allows 256 steps (Mapping.cs:28); larger -> unsupported */
+
+typedef enum nvb_status {
+    NVB_OK = 0,
+    NVB_ERR_ARG = -1,          /* NULL / out-of-range argument (reference: ArgumentException family)     */
+    NVB_ERR_CUDA = -2,         /* CUDA runtime failure, see nvb_last_error()                             */
+    NVB_ERR_UNSUPPORTED = -3,  /* setup outside the supported envelope (see nvb_upload_setup)            */
+    NVB_ERR_NOMEM = -4,
+    NVB_ERR_STATE = -5,        /* call order (no setup uploaded, ...)  (reference: ObjectDisposedException) */
+    NVB_ERR_CAPACITY = -6,     /* pcm_out too small for the batch                                        */
+    NVB_ERR_DATA = -7          /* malformed batch (offsets out of range, ...) (reference: InvalidDataException) */
+} nvb_status;
+
+typedef struct nvb_ctx nvb_ctx;
+typedef struct nvb_dbatch nvb_dbatch;
+
+/* ---- setup (one per logical stream; built by the host from the setup header) ---------------- */
+
+/* Codebook VQ lookup (ICodebook this[entry,dim], Codebook.cs:322; table built by
+ * Codebook.InitLookupTable, Codebook.cs:222-283 -- the host computes the floats, the GPU gathers). */
+typedef struct nvb_codebook {
+    int32_t dims;          /* Codebook.Dimensions */
+    int32_t entries;       /* Codebook.Entries    */
+    int32_t map_type;      /* 0 = no lookup table */
+    int32_t reserved;
+    int64_t table_off;     /* index of [entry*dims + dim] floats inside nvb_setup.vq_floats; -1 if none */
+} nvb_codebook;
+
+/* Floor type 1 tables (Floor1.Init, Floor1.cs:30-133) */
+typedef struct nvb_floor1 {
+    int32_t n_posts;                    /* _xList.Length (<= 64)            */
+    int32_t multiplier;                 /* _multiplier (already +1)  :69-74 */
+    int32_t range;                      /* _range                    :71    */
+    int32_t reserved;
+    uint16_t x_list[NVB_MAX_POSTS];     /* _xList                    :78-90 */
+    uint8_t  l_neigh[NVB_MAX_POSTS];    /* _lNeigh                   :93-115 */
+    uint8_t  h_neigh[NVB_MAX_POSTS];    /* _hNeigh                          */
+    uint8_t  sort_idx[NVB_MAX_POSTS];   /* _sortIdx                  :118-132 */
+} nvb_floor1;
+
+typedef struct nvb_floor {
+    int32_t type;                       /* 1 = Floor1.  0 = Floor0: not yet accepted (NVB_ERR_UNSUPPORTED) */
+    int32_t reserved;
+    nvb_floor1 f1;
+} nvb_floor;
+
+/* Residue tables (Residue0.Init, Residue0.cs:35-117) */
+typedef struct nvb_residue {
+    int32_t type;                       /* 0, 1, 2 (Factory.cs:48-58) */
+    int32_t begin, end;                 /* _begin, _end               */
+    int32_t partition_size;             /* _partitionSize             */
+    int32_t classifications;            /* _classifications           */
+    int32_t max_stages;                 /* _maxStages                 */
+    int32_t cascade[NVB_MAX_CLASSES];   /* _cascade                   */
+    int16_t books[NVB_MAX_CLASSES][NVB_MAX_STAGES];  /* _books[class][stage] as codebook index, -1 = null */
+} nvb_residue;
+
+/* Mapping tables (Mapping.Init, Mapping.cs:16-93).  Only single-submap mappings are accepted: with
+ * more than one submap the reference forces every channel silent yet decodes each submap's residue
+ * over all channels (Mapping.cs:122-134) -- rejected with NVB_ERR_UNSUPPORTED instead of emulated. */
+typedef struct nvb_mapping {
+    int32_t n_coupling;
+    int32_t n_submaps;
+    uint8_t magnitude[NVB_MAX_COUPLING];   /* _couplingMangitude */
+    uint8_t angle[NVB_MAX_COUPLING];       /* _couplingAngle     */
+    int32_t floor;                         /* _submapFloor[0]   as index into nvb_setup.floors   */
+    int32_t residue;                       /* _submapResidue[0] as index into nvb_setup.residues */
+} nvb_mapping;
+
+typedef struct nvb_mode {               /* Mode.Init, Mode.cs:24-67 */
+    int32_t block_flag;                 /* _blockFlag: 1 = long (block_size[1]) */
+    int32_t mapping;
+} nvb_mode;
+
+typedef struct nvb_setup {
+    int32_t abi_version;                /* NVB_ABI_VERSION */
+    int32_t channels;                   /* StreamDecoder._channels */
+    int32_t sample_rate;
+    int32_t block_size[2];              /* _block0Size, _block1Size (StreamDecoder.cs:192-193) */
+    int32_t n_books, n_floors, n_residues, n_mappings, n_modes;
+    const nvb_codebook* books;
+    const float*        vq_floats;      /* concatenated lookup tables */
+    int64_t             n_vq_floats;
+    const nvb_floor*    floors;
+    const nvb_residue*  residues;
+    const nvb_mapping*  mappings;
+    const nvb_mode*     modes;
+    /* Optional host-computed tables.  Pass NULL to let the library compute them with the same
+     * float/double expression order as the reference (libm instead of System.Math).
+     *   window_slope[i]: block_size[i]/2 floats, the rising slope of Mode.CalcWindow (Mode.cs:80-85)
+     *   mdct_a/b/c/bitrev[i]: Mdct twiddles for block_size[i] (Mdct.cs:44-62): n/2, n/2, n/4 floats, n/8 u16 */
+    const float*    window_slope[2];
+    const float*    mdct_a[2];
+    const float*    mdct_b[2];
+    const float*    mdct_c[2];
+    const uint16_t* mdct_bitrev[2];
+} nvb_setup;
+
+/* ---- per-packet boundary record ------------------------------------------------------------ */
+
+enum { NVB_FRAME_OK = 0, NVB_FRAME_FAILED = 1 };
+
+/* One audio packet as seen by StreamDecoder.DecodeNextPacket (StreamDecoder.cs:465-530).
+ * status FAILED = DecodeNextPacket returned null (non-audio packet, IsShort, or no packet): the
+ * previous block's tail is drained un-overlapped (StreamDecoder.cs:352-356); no other field is read. */
+typedef struct nvb_frame {
+    uint8_t  status;        /* NVB_FRAME_OK / NVB_FRAME_FAILED */
+    uint8_t  mode;          /* index into setup.modes (StreamDecoder.cs:497) */
+    uint8_t  window;        /* Mode.GetPacketInfo windowIndex = prev?1:0 + next?2:0; 0 for short blocks (Mode.cs:135) */
+    uint8_t  res_decoded;   /* 1 if Residue.Decode ran (some channel live: Residue0.cs:125), else 0 */
+    uint32_t exec_mask;     /* bit c = IFloorData.ExecuteChannel of channel c after the ForceEnergy pass (Mapping.cs:111-119) */
+    int32_t  start;         /* packetStartIndex                                   (Mode.cs:137-140) */
+    int32_t  valid;         /* packetValidLength AFTER the EOS trim               (StreamDecoder.cs:429-437) */
+    int32_t  total;         /* packetTotalLength */
+    uint32_t classes_off;   /* into nvb_batch.classes: [stream][partition] u8, stream = channel (types 0/1) or 0 (type 2) */
+    uint32_t entries_off;   /* into nvb_batch.entries: VQ entry numbers in the order DecodeScalar returned them */
+    uint32_t entry_count;   /* entries decoded before the packet ended / failed ("use what we have", Residue0.cs:164-170).
+                               Residue type 0 adds a partition only when all of its entries were read
+                               (Residue0.cs:186-192): truncate entry_count to that partition boundary. */
+} nvb_frame;
+
+/* Floor payload: posts[frame][channel][nvb_post_stride()] int16; element 0 = PostCount (0 = floor
+ * unused or unpack failed, Floor1.cs:140,155-174), elements 1.. = raw Posts[] as unpacked (before
+ * UnwrapPosts).  nvb_post_stride() = 2 + max n_posts over the setup's floors, rounded up to even. */
+typedef struct nvb_batch {
+    int32_t          n_frames;
+    int32_t          reserved;
+    const nvb_frame* frames;
+    const int16_t*   posts;
+    const uint8_t*   classes;   int64_t n_classes;
+    const uint16_t*  entries;   int64_t n_entries;
+} nvb_batch;
+
+typedef struct nvb_result {
+    int64_t samples_per_channel;  /* PCM frames written (interleaved: samples_per_channel * channels floats) */
+    int32_t has_clipped;          /* StreamDecoder.HasClipped (Utils.ClipValue, Utils.cs:30-43) */
+    int32_t n_failed;             /* frames with status FAILED */
+    int32_t n_floor_range;        /* floor curve indices outside inverse_dB_table (reference: IndexOutOfRangeException); clamped */
+    int32_t n_inconsistent;       /* frames whose previous tail was longer than their own overlap region (clamped) */
+} nvb_result;
+
+/* nvb_run flags */
+enum {
+    NVB_RUN_DEFAULT   = 0,
+    NVB_RUN_EXACT     = 1,   /* stb-dataflow IMDCT without FMA contraction: bit-identical to the reference arithmetic */
+    NVB_RUN_NO_CLIP   = 2,   /* StreamDecoder.ClipSamples = false (CopyBuffer instead of ClippingCopyBuffer) */
+    NVB_RUN_CONTINUE  = 4    /* chain onto the previous batch of this context (keeps the overlap tail);
+                                without it the batch starts a stream: first block emits nothing (StreamDecoder.cs:446-450) */
+};
+
+/* ---- entry points ---------------------------------------------------------------------------- */
+
+int         nvb_abi_version(void);
+const char* nvb_strerror(int status);
+const char* nvb_last_error(nvb_ctx* ctx);           /* detail text of the last failure on this context */
+
+/* Creates a context on CUDA device `device`.  Fails with NVB_ERR_CUDA when no usable GPU exists:
+ * there is no CPU fallback. */
+int nvb_create(int device, nvb_ctx** out);
+int nvb_destroy(nvb_ctx* ctx);
+
+/* Uploads the immutable per-stream tables.  Replaces what StreamDecoder.LoadBooks leaves behind
+ * (StreamDecoder.cs:226-289).  NVB_ERR_UNSUPPORTED: channels > NVB_MAX_CHANNELS, Floor0,
+ * multi-submap mappings, > NVB_MAX_COUPLING steps, residue books with > 65536 entries. */
+int nvb_upload_setup(nvb_ctx* ctx, const nvb_setup* setup);
+
+/* Serialises the uploaded setup's device tables into one blob / installs such a blob, so that one
+ * rank can parse the headers and every other rank receives the tables with a single broadcast. */
+int nvb_setup_blob_size(nvb_ctx* ctx, size_t* bytes);
+int nvb_setup_blob_export(nvb_ctx* ctx, void* dst, size_t bytes);
+int nvb_setup_blob_import(nvb_ctx* ctx, const void* src, size_t bytes);
+
+int nvb_post_stride(nvb_ctx* ctx);
+
+/* ResetDecoder (StreamDecoder.cs:295-305): forget the overlap tail. */
+int nvb_reset(nvb_ctx* ctx);
+
+/* Host-buffer call: H2D of the batch, synthesis, D2H of interleaved PCM into pcm_out
+ * (capacity pcm_cap floats).  Equivalent to what K iterations of StreamDecoder.Read's packet
+ * loop leave in the caller's buffer. */
+int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap, nvb_result* res);
+
+/* Device-resident variant (pipelining / benchmarking): upload once, run many times.
+ * `stream` is a cudaStream_t (NULL = default stream); d_pcm is a device pointer with room for
+ * nvb_dbatch_samples()*channels floats.  nvb_dbatch_run only enqueues kernels. */
+int     nvb_dbatch_create(nvb_ctx* ctx, const nvb_batch* batch, int flags, nvb_dbatch** out);
+int64_t nvb_dbatch_samples(const nvb_dbatch* b);
+int     nvb_dbatch_run(nvb_ctx* ctx, nvb_dbatch* b, float* d_pcm, void* stream);
+int     nvb_dbatch_result(nvb_ctx* ctx, nvb_dbatch* b, void* stream, nvb_result* res);   /* synchronises `stream` */
+int     nvb_dbatch_destroy(nvb_ctx* ctx, nvb_dbatch* b);
+
+/* Stage entry points (same kernels, exposed for parity tests and for the roofline measurement):
+ *   nvb_dbatch_run_spectrum: residue + coupling + floor only; writes the dense spectrum
+ *     [frame][channel][N/2] (ok frames in order; per-frame float offsets via nvb_dbatch_spec_offsets).
+ *   nvb_dbatch_run_imdct: IMDCT + window + OLA + clip + interleave from a dense spectrum. */
+int     nvb_dbatch_run_spectrum(nvb_ctx* ctx, nvb_dbatch* b, float* d_spectrum, void* stream);
+int     nvb_dbatch_run_imdct(nvb_ctx* ctx, nvb_dbatch* b, const float* d_spectrum, float* d_pcm, void* stream);
+int64_t nvb_dbatch_spectrum_floats(const nvb_dbatch* b);
+int     nvb_dbatch_launches(const nvb_dbatch* b);   /* kernels enqueued by one nvb_dbatch_run */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVORBIS_B200_H */

@@ -1,0 +1,173 @@
+// nvb_fused_core.h -- lane-level arithmetic of the fused IMDCT + window + OLA + clip + interleave
+// kernel (nvb_fused.cu).  Written as phases of one warp: every phase is a function of
+// (lane, registers, shared memory) with a warp barrier between phases, so tests/cpu_shim.cpp can
+// replay a warp on the host lane by lane.
+//
+// IMDCT factorisation (M = N/2 coefficients, Q = N/4 complex points; reproduces what Mdct.Reverse
+// computes for N >= 256, i.e. y[i] = sum_k X[k] cos(2pi/N (i + 1/2 + N/4)(k + 1/2)), Mdct.cs:65-313):
+//   c[k] = (X[2k] + i X[M-1-2k]) * tw[k],   tw[k] = exp(-i pi (k + 1/8) / M)
+//   Cf   = FFT_Q(c);   D[n] = Cf[n] * tw[n];   u[2n] = Re D[n],  u[M-1-2n] = -Im D[n]
+//   y[i] = u[i+M/2] (i < M/2);  -u[3M/2-1-i] (M/2 <= i < 3M/2);  -u[i-3M/2] (i >= 3M/2)
+// This path may contract to FMA; it is held to <= 1e-5 max-abs against the oracle (the exact
+// path in nvb_kernels.cu is the bit-identical one).
+#pragma once
+#include "nvb_device_core.h"
+
+namespace nvb {
+
+struct cpx { float x, y; };
+NVB_HD cpx cmul(cpx a, cpx b) { cpx r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+NVB_HD cpx cadd(cpx a, cpx b) { cpx r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+NVB_HD cpx csub(cpx a, cpx b) { cpx r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+NVB_HD cpx cmul_mi(cpx a) { cpx r; r.x = a.y; r.y = -a.x; return r; }          // a * (-i)
+
+// 8-point forward DFT (W8 = exp(-2 pi i / 8)), in place, natural order in and out.
+NVB_HD void fft8(cpx* a) {
+    const float h = 0.70710678118654752440f;
+    cpx b0 = cadd(a[0], a[4]), b4 = csub(a[0], a[4]);
+    cpx b1 = cadd(a[1], a[5]), t5 = csub(a[1], a[5]);
+    cpx b2 = cadd(a[2], a[6]), t6 = csub(a[2], a[6]);
+    cpx b3 = cadd(a[3], a[7]), t7 = csub(a[3], a[7]);
+    cpx b5; b5.x = (t5.x + t5.y) * h; b5.y = (t5.y - t5.x) * h;                 // * (1 - i)/sqrt2
+    cpx b6 = cmul_mi(t6);                                                       // * (-i)
+    cpx b7; b7.x = (t7.y - t7.x) * h; b7.y = -(t7.x + t7.y) * h;                // * (-1 - i)/sqrt2
+    // even outputs: FFT4(b0..b3); odd outputs: FFT4(b4..b7)
+    cpx e0 = cadd(b0, b2), e1 = csub(b0, b2), e2 = cadd(b1, b3), e3 = cmul_mi(csub(b1, b3));
+    cpx o0 = cadd(b4, b6), o1 = csub(b4, b6), o2 = cadd(b5, b7), o3 = cmul_mi(csub(b5, b7));
+    a[0] = cadd(e0, e2); a[4] = csub(e0, e2); a[2] = cadd(e1, e3); a[6] = csub(e1, e3);
+    a[1] = cadd(o0, o2); a[5] = csub(o0, o2); a[3] = cadd(o1, o3); a[7] = csub(o1, o3);
+}
+
+constexpr int FUSED_SLOT_FLOATS = 1152;        // 8 rows * 72 float2 of exchange space >= 1024 floats of u
+constexpr int FUSED_LONG_N = 2048;
+constexpr int FUSED_SHORT_N = 256;
+
+// Registers of one lane while it transforms one long block: two radix-8 columns.
+struct LongRegs { cpx a[8]; cpx b[8]; };
+
+// ---- phase 1: load spectrum pairs, pre-twiddle, radix-8 over k2, twiddle W512^(r*m2), store ex1
+// spec2: the channel's spectrum as float2[512]; tw, w512: float2[512] tables; ex: float2[576].
+NVB_HD void long_phase1(int l, const float2* spec2, const float2* tw, const float2* w512, float2* ex) {
+    const int ra = l, rb = 63 - l;
+    float2 pa[8], pb[8];
+    #pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) { pa[k2] = spec2[64 * k2 + ra]; pb[k2] = spec2[64 * k2 + rb]; }
+    LongRegs R;
+    #pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) {
+        cpx ca, cb, t;
+        ca.x = pa[k2].x; ca.y = pb[7 - k2].y;          // X[2k] + i X[M-1-2k], k = 64 k2 + l
+        cb.x = pb[k2].x; cb.y = pa[7 - k2].y;          // k = 64 k2 + 63 - l
+        float2 wa = tw[64 * k2 + ra], wb = tw[64 * k2 + rb];
+        t.x = wa.x; t.y = wa.y; R.a[k2] = cmul(ca, t);
+        t.x = wb.x; t.y = wb.y; R.b[k2] = cmul(cb, t);
+    }
+    fft8(R.a); fft8(R.b);
+    #pragma unroll
+    for (int m2 = 0; m2 < 8; m2++) {
+        cpx va = R.a[m2], vb = R.b[m2];
+        if (m2 > 0) {
+            float2 wa = w512[(ra * m2) & 511], wb = w512[(rb * m2) & 511];
+            cpx t; t.x = wa.x; t.y = wa.y; va = cmul(va, t);
+            t.x = wb.x; t.y = wb.y; vb = cmul(vb, t);
+        }
+        ex[m2 * 72 + ra] = make_float2(va.x, va.y);
+        ex[m2 * 72 + rb] = make_float2(vb.x, vb.y);
+    }
+}
+
+// ---- phase 2: (a) gather the 8 k1 of (m2, k0) for two m2; (b) radix-8 over k1, twiddle W64^(k0*m1), store ex2
+NVB_HD void long_phase2_load(int l, const float2* ex, LongRegs& R) {
+    const int m2 = l >> 3, k0 = l & 7;
+    #pragma unroll
+    for (int k1 = 0; k1 < 8; k1++) {
+        float2 va = ex[m2 * 72 + 8 * k1 + k0], vb = ex[(m2 + 4) * 72 + 8 * k1 + k0];
+        R.a[k1].x = va.x; R.a[k1].y = va.y; R.b[k1].x = vb.x; R.b[k1].y = vb.y;
+    }
+}
+NVB_HD void long_phase2_store(int l, const float2* w512, float2* ex, LongRegs& R) {
+    const int m2 = l >> 3, k0 = l & 7;
+    fft8(R.a); fft8(R.b);
+    #pragma unroll
+    for (int m1 = 0; m1 < 8; m1++) {
+        cpx va = R.a[m1], vb = R.b[m1];
+        if (m1 > 0) {
+            float2 w = w512[(8 * k0 * m1) & 511];
+            cpx t; t.x = w.x; t.y = w.y; va = cmul(va, t); vb = cmul(vb, t);
+        }
+        ex[m2 * 72 + m1 * 9 + k0] = make_float2(va.x, va.y);
+        ex[(m2 + 4) * 72 + m1 * 9 + k0] = make_float2(vb.x, vb.y);
+    }
+}
+
+// ---- phase 3: (a) gather the 8 k0 of (m2, m1) and of (7-m2, 7-m1); (b) radix-8 over k0, post-twiddle,
+// write u as float2 pairs (u[2n], u[2n+1]) = (Re D[n], -Im D[511-n]).
+NVB_HD void long_phase3_load(int l, const float2* ex, LongRegs& R) {
+    const int m2 = l >> 3, m1 = l & 7;
+    #pragma unroll
+    for (int k0 = 0; k0 < 8; k0++) {
+        float2 va = ex[m2 * 72 + m1 * 9 + k0], vb = ex[(7 - m2) * 72 + (7 - m1) * 9 + k0];
+        R.a[k0].x = va.x; R.a[k0].y = va.y; R.b[k0].x = vb.x; R.b[k0].y = vb.y;
+    }
+}
+NVB_HD void long_phase3_store(int l, const float2* tw, float2* u2, LongRegs& R) {
+    const int m2 = l >> 3, m1 = l & 7;
+    fft8(R.a); fft8(R.b);
+    const int na0 = m2 + 8 * m1, nb0 = (7 - m2) + 8 * (7 - m1);
+    #pragma unroll
+    for (int m0 = 0; m0 < 8; m0++) {
+        float2 wa = tw[na0 + 64 * m0], wb = tw[nb0 + 64 * m0];
+        cpx t; t.x = wa.x; t.y = wa.y; R.a[m0] = cmul(R.a[m0], t);
+        t.x = wb.x; t.y = wb.y; R.b[m0] = cmul(R.b[m0], t);
+    }
+    #pragma unroll
+    for (int m0 = 0; m0 < 8; m0++) {
+        const int n = na0 + 64 * m0;                    // partner 511 - n = nb0 + 64 (7 - m0)
+        u2[n] = make_float2(R.a[m0].x, -R.b[7 - m0].y);
+        u2[511 - n] = make_float2(R.b[7 - m0].x, -R.a[m0].y);
+    }
+}
+
+// ---- short block (N = 256, Q = 64): lane holds points l and l+32.
+struct ShortRegs { cpx a, b; };
+NVB_HD void short_phase1(int l, const float* spec, const float2* tw64, const float2* w64, ShortRegs& R) {
+    cpx ca, cb, t;
+    ca.x = spec[2 * l]; ca.y = spec[127 - 2 * l];
+    cb.x = spec[2 * l + 64]; cb.y = spec[63 - 2 * l];
+    float2 w = tw64[l]; t.x = w.x; t.y = w.y; ca = cmul(ca, t);
+    w = tw64[l + 32]; t.x = w.x; t.y = w.y; cb = cmul(cb, t);
+    R.a = cadd(ca, cb);
+    w = w64[l]; t.x = w.x; t.y = w.y;
+    R.b = cmul(csub(ca, cb), t);
+}
+// One shuffle-DIF stage of the two 32-point FFTs (half-size s): own value v, partner's value p.
+NVB_HD cpx short_stage(int l, int s, cpx v, cpx p, const float2* w64) {
+    const int j = l & (s - 1);
+    if (l & s) {
+        float2 w = w64[(j * (32 / s)) & 63];            // W_{2s}^j = W64^(j*32/s)
+        cpx t; t.x = w.x; t.y = w.y;
+        return cmul(csub(p, v), t);
+    }
+    return cadd(v, p);
+}
+NVB_HD int brev5(int l) { return ((l & 1) << 4) | ((l & 2) << 2) | (l & 4) | ((l & 8) >> 2) | ((l & 16) >> 4); }
+NVB_HD void short_phase3_store(int l, const float2* tw64, float* u, const ShortRegs& R) {
+    const int m = brev5(l);
+    const int ne = 2 * m, no = 2 * m + 1;
+    float2 w = tw64[ne]; cpx t; t.x = w.x; t.y = w.y; cpx de = cmul(R.a, t);
+    w = tw64[no]; t.x = w.x; t.y = w.y; cpx dodd = cmul(R.b, t);
+    u[2 * ne] = de.x; u[127 - 2 * ne] = -de.y;
+    u[2 * no] = dodd.x; u[127 - 2 * no] = -dodd.y;
+}
+
+// ---- output side ------------------------------------------------------------------------------------
+// Un-windowed block value y[i] of a slot: u (executed channel) or the raw spectrum (Mapping.cs:192-196).
+NVB_HD float fused_y(const float* slot, bool exec, int N, int i) {
+    const int M = N >> 1, h = M >> 1;
+    if (!exec) return i < M ? slot[i] : 0.f;
+    if (i < h) return slot[i + h];
+    if (i < M + h) return -slot[M + h - 1 - i];
+    return -slot[i - M - h];
+}
+
+}  // namespace nvb

@@ -1,0 +1,94 @@
+// nvb_internal.h -- device-side table layout shared by the kernels and the C-ABI host code.
+// Not part of the public ABI (include/nvorbis_b200.h is).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include "../../include/nvorbis_b200.h"
+
+#if !defined(__CUDACC__)
+// host-only builds (tests/cpu_shim.cpp): the two CUDA vector types the tables use
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+
+namespace nvb {
+
+// ---- immutable per-stream tables, as they sit in ONE contiguous device allocation ("blob") ----
+struct DevBook    { int32_t dims, entries; int64_t off; };           // off: float index into vq, -1 = no table
+struct DevFloor1  { int32_t n_posts, mult, range, pad; uint16_t x[NVB_MAX_POSTS]; uint8_t lo[NVB_MAX_POSTS], hi[NVB_MAX_POSTS], sort[NVB_MAX_POSTS]; };
+struct DevResidue { int32_t type, begin, end, psize, nclass, stages; int32_t cascade[NVB_MAX_CLASSES]; int16_t books[NVB_MAX_CLASSES][NVB_MAX_STAGES]; };
+struct DevMapping { int32_t n_coupling, floor, residue, pad; uint8_t mag[NVB_MAX_COUPLING], ang[NVB_MAX_COUPLING]; };
+struct DevMode    { int32_t block_flag, mapping; };
+
+// Blob header: byte offsets of every section from the start of the blob.
+struct BlobHeader {
+    uint32_t magic;            // 'NVB1'
+    uint32_t abi;
+    uint64_t total_bytes;
+    int32_t channels, sample_rate, bs[2];
+    int32_t n_books, n_floors, n_residues, n_mappings, n_modes;
+    int32_t post_stride;       // int16 elements per (frame, channel) in nvb_batch.posts
+    int32_t max_items;         // max over modes of stages*partitions*streams (residue prefix table)
+    int32_t pad0;
+    uint64_t off_books, off_vq, off_floors, off_residues, off_mappings, off_modes;
+    uint64_t off_win_short;    // bs[0] floats
+    uint64_t off_win_long;     // 4 * bs[1] floats (window index = prev?1:0 + next?2:0)
+    uint64_t off_mdct_a[2], off_mdct_b[2], off_mdct_c[2], off_bitrev[2];   // reference twiddles (exact path)
+    uint64_t off_tw[2];        // fast path: float2[bs/4], exp(-i*pi*(k+1/8)/(bs/2))
+    uint64_t off_fft[2];       // fast path: float2[bs/4], exp(-2*pi*i*k/(bs/4))
+    uint64_t off_db;           // 256 floats
+    uint64_t n_vq;
+};
+
+// Resolved pointers handed to kernels by value.
+struct DevSetup {
+    int32_t channels, bs[2], post_stride, max_items;
+    const DevBook* books; const float* vq; int64_t n_vq;
+    const DevFloor1* floors; const DevResidue* residues; const DevMapping* mappings; const DevMode* modes;
+    const float* win_short; const float* win_long;
+    const float* A[2]; const float* B[2]; const float* C[2]; const uint16_t* bitrev[2];
+    const float2* tw[2]; const float2* fft[2];
+    const float* db;
+};
+
+// ---- per-frame plan built on the host from nvb_frame (ok frames only, in order) ----------------
+enum { PREV_NONE = -1, PREV_CARRY = -2 };
+struct DevFrame {
+    uint8_t  mode, window, res_decoded, kind;   // kind 0 = normal, 1 = emit the carried tail only (drain at batch start)
+    uint32_t exec_mask;
+    int32_t  n;                 // block size
+    int32_t  start;             // packetStartIndex: prev tail is added at [start, start+ola_len)
+    int32_t  out_begin, out_end;// emitted region of this block
+    int32_t  ola_len;
+    int32_t  prev;              // index of the previous DevFrame, PREV_NONE or PREV_CARRY
+    int32_t  prev_valid;        // where the tail starts inside the previous block
+    int32_t  api_index;         // index into nvb_batch.frames (posts are addressed with it)
+    int64_t  pcm_off;           // per-channel sample offset of out_begin in the PCM output
+    uint32_t classes_off, entries_off, entry_count;
+    uint32_t spec_off;          // float offset of this frame's [C][n/2] spectrum; its [C][n] block sits at 2*spec_off
+};
+
+struct Counters { int clipped, floor_range, bad_entry, pad; };
+
+// ---- launchers (nvb_kernels.cu) -----------------------------------------------------------------
+struct LaunchArgs {
+    DevSetup S;
+    const DevFrame* frames; int n_frames;      // device array
+    const int16_t* posts; const uint8_t* classes; const uint16_t* entries;
+    float* spectrum;            // [sum C*n/2]
+    float* blocks;              // [sum C*n]   (exact path scratch)
+    const float* carry_in;      // [C][bs1] previous batch's last block (or nullptr)
+    float* carry_out;           // [C][bs1] receives the batch's last block (or nullptr)
+    float* pcm;
+    Counters* counters;
+    int clip;
+};
+
+int launch_spectrum(const LaunchArgs& a, void* stream);
+int launch_imdct_exact(const LaunchArgs& a, void* stream);   // spectrum -> windowed blocks
+int launch_ola(const LaunchArgs& a, void* stream);           // blocks (+carry) -> interleaved PCM
+// Fused fast path: spectrum -> PCM for runs of frames; returns <0 if the batch shape is not covered.
+int launch_imdct_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream);
+bool fused_supported(const BlobHeader& h, const DevFrame* host_frames, int n_frames);
+
+}  // namespace nvb
