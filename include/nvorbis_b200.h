@@ -196,6 +196,12 @@ const char* nvb_last_error(nvb_ctx* ctx);           /* detail text of the last f
 int nvb_create(int device, nvb_ctx** out);
 int nvb_destroy(nvb_ctx* ctx);
 
+/* Page-locked host memory for batch inputs / PCM output (the P/Invoke host keeps its batch arrays in
+ * these so that the H2D/D2H copies of nvb_decode_batch run at full PCIe rate).  Any other host
+ * pointer is accepted by every call too, just slower. */
+int nvb_host_alloc(size_t bytes, void** out);
+int nvb_host_free(void* p);
+
 /* Uploads the immutable per-stream tables.  Replaces what StreamDecoder.LoadBooks leaves behind
  * (StreamDecoder.cs:226-289).  NVB_ERR_UNSUPPORTED: channels > NVB_MAX_CHANNELS, Floor0,
  * multi-submap mappings, > NVB_MAX_COUPLING steps, residue books with > 65536 entries. */
@@ -219,7 +225,9 @@ int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm
 
 /* Device-resident variant (pipelining / benchmarking): upload once, run many times.
  * `stream` is a cudaStream_t (NULL = default stream); d_pcm is a device pointer with room for
- * nvb_dbatch_samples()*channels floats.  nvb_dbatch_run only enqueues kernels. */
+ * nvb_dbatch_samples()*channels floats.  nvb_dbatch_run only enqueues kernels.  With
+ * NVB_RUN_CONTINUE the batch overlaps onto the tail left by the last nvb_decode_batch; running a
+ * dbatch never changes that tail. */
 int     nvb_dbatch_create(nvb_ctx* ctx, const nvb_batch* batch, int flags, nvb_dbatch** out);
 int64_t nvb_dbatch_samples(const nvb_dbatch* b);
 int     nvb_dbatch_run(nvb_ctx* ctx, nvb_dbatch* b, float* d_pcm, void* stream);

@@ -1,0 +1,374 @@
+// nvb_api.cu -- the C ABI of include/nvorbis_b200.h: contexts, setup upload, batch upload and launch.
+// Device memory, streams and copies only; the kernels are in nvb_kernels.cu / nvb_fused.cu and the
+// CUDA-free planning in nvb_host.cpp.  There is no CPU fallback: without a usable GPU nvb_create fails.
+#if !defined(NVB_CPU_SHIM)
+#include <cuda_runtime.h>
+#endif
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#include "nvb_host.h"
+
+using namespace nvb;
+
+struct nvb_ctx {
+    int device = 0;
+    std::string err;
+    bool has_setup = false;
+    std::vector<unsigned char> host_blob;
+    unsigned char* d_blob = nullptr;
+    BlobHeader H;
+    DevSetup S;
+    // overlap tail carried from one nvb_decode_batch to the next (StreamDecoder._prevPacketBuf)
+    CarryState carry;
+    float* d_carry[2] = {nullptr, nullptr};
+    int carry_cur = 0;
+    cudaStream_t stream = nullptr;
+    // reusable device staging of nvb_decode_batch
+    nvb_dbatch* staging = nullptr;
+    float* d_pcm = nullptr; size_t pcm_cap = 0;
+};
+
+struct nvb_dbatch {
+    Plan plan;
+    int flags = 0;
+    bool fused = false;
+    DevFrame* d_frames = nullptr; size_t cap_frames = 0;
+    int16_t* d_posts = nullptr;   size_t cap_posts = 0;
+    uint8_t* d_classes = nullptr; size_t cap_classes = 0;
+    uint16_t* d_entries = nullptr; size_t cap_entries = 0;
+    float* d_spectrum = nullptr;  size_t cap_spectrum = 0;
+    float* d_blocks = nullptr;    size_t cap_blocks = 0;
+    Counters* d_counters = nullptr;
+    int launches = 0;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(nvb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_err = msg;
+    return code;
+}
+int cuda_fail(nvb_ctx* ctx, cudaError_t e, const char* what) {
+    char tmp[256];
+    std::snprintf(tmp, sizeof tmp, "%s: %s", what, cudaGetErrorString(e));
+    return set_err(ctx, NVB_ERR_CUDA, tmp);
+}
+#define NVB_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail((ctx), e__, #call); } while (0)
+
+struct DeviceGuard {
+    int prev = -1; bool ok = false;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <class T> int grow(nvb_ctx* ctx, T*& p, size_t& cap, size_t need) {
+    if (need <= cap && p) return NVB_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t n = need ? need : 1;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e != cudaSuccess) { p = nullptr; cudaGetLastError(); return set_err(ctx, NVB_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    cap = n;
+    return NVB_OK;
+}
+
+void free_dbatch(nvb_dbatch* b) {
+    if (!b) return;
+    cudaFree(b->d_frames); cudaFree(b->d_posts); cudaFree(b->d_classes); cudaFree(b->d_entries);
+    cudaFree(b->d_spectrum); cudaFree(b->d_blocks); cudaFree(b->d_counters);
+    delete b;
+}
+
+int install_blob(nvb_ctx* ctx, std::vector<unsigned char>&& blob) {
+    DeviceGuard g(ctx->device);
+    unsigned char* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, blob.size());
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(ctx, NVB_ERR_NOMEM, std::string("cudaMalloc(blob): ") + cudaGetErrorString(e)); }
+    e = cudaMemcpy(d, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(ctx, e, "cudaMemcpy(blob)"); }
+    BlobHeader h; std::memcpy(&h, blob.data(), sizeof h);
+    float* carry[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++) {
+        e = cudaMalloc((void**)&carry[i], sizeof(float) * (size_t)h.channels * h.bs[1]);
+        if (e == cudaSuccess) e = cudaMemset(carry[i], 0, sizeof(float) * (size_t)h.channels * h.bs[1]);
+        if (e != cudaSuccess) { cudaFree(d); cudaFree(carry[0]); cudaFree(carry[1]); cudaGetLastError(); return set_err(ctx, NVB_ERR_NOMEM, "cudaMalloc(carry)"); }
+    }
+    if (ctx->d_blob) cudaFree(ctx->d_blob);
+    cudaFree(ctx->d_carry[0]); cudaFree(ctx->d_carry[1]);
+    ctx->d_blob = d; ctx->d_carry[0] = carry[0]; ctx->d_carry[1] = carry[1]; ctx->carry_cur = 0;
+    ctx->host_blob = std::move(blob);
+    ctx->H = h;
+    resolve_setup(ctx->d_blob, ctx->H, ctx->S);
+    ctx->carry = CarryState();
+    ctx->has_setup = true;
+    return NVB_OK;
+}
+
+// Uploads a batch into `b` (buffers grow as needed) and plans it.
+int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags, cudaStream_t st) {
+    std::string err;
+    int rc = plan_batch(ctx->host_blob.data(), batch, flags, ctx->carry, b->plan, err);
+    if (rc != NVB_OK) return set_err(ctx, rc, err);
+    b->flags = flags;
+    b->fused = !(flags & NVB_RUN_EXACT) && fused_supported(ctx->H, b->plan.frames.data(), (int)b->plan.frames.size());
+    const size_t nf = b->plan.frames.size();
+    const size_t n_posts = (size_t)batch->n_frames * ctx->H.channels * ctx->H.post_stride;
+    if ((rc = grow(ctx, b->d_frames, b->cap_frames, nf)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_posts, b->cap_posts, n_posts)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_classes, b->cap_classes, (size_t)batch->n_classes)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_entries, b->cap_entries, (size_t)batch->n_entries)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_spectrum, b->cap_spectrum, (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
+    if (!b->fused && (rc = grow(ctx, b->d_blocks, b->cap_blocks, 2 * (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
+    if (!b->d_counters) { size_t cap = 0; if ((rc = grow(ctx, b->d_counters, cap, 1)) != NVB_OK) return rc; }
+    if (nf) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_frames, b->plan.frames.data(), nf * sizeof(DevFrame), cudaMemcpyHostToDevice, st));
+    if (n_posts) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts, batch->posts, n_posts * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    if (batch->n_classes) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_classes, batch->classes, (size_t)batch->n_classes, cudaMemcpyHostToDevice, st));
+    if (batch->n_entries) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_entries, batch->entries, (size_t)batch->n_entries * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    return NVB_OK;
+}
+
+LaunchArgs make_args(nvb_ctx* ctx, nvb_dbatch* b, float* spectrum, float* d_pcm, bool save_carry) {
+    LaunchArgs a;
+    a.S = ctx->S;
+    a.frames = b->d_frames; a.n_frames = (int)b->plan.frames.size();
+    a.posts = b->d_posts; a.classes = b->d_classes; a.entries = b->d_entries;
+    a.spectrum = spectrum;
+    a.blocks = b->d_blocks;
+    a.carry_in = ctx->d_carry[ctx->carry_cur];
+    a.carry_out = save_carry ? ctx->d_carry[ctx->carry_cur ^ 1] : nullptr;
+    a.carry_frame = save_carry ? b->plan.last_ok : -1;
+    a.pcm = d_pcm;
+    a.counters = b->d_counters;
+    a.clip = (b->flags & NVB_RUN_NO_CLIP) ? 0 : 1;
+    return a;
+}
+
+// Enqueues the synthesis of an uploaded batch.  stage: 0 = all, 1 = spectrum only, 2 = IMDCT.. only.
+// `spectrum` = dense spectrum buffer written by stage 1 and read by stage 2 (nullptr: the batch's own).
+int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pcm, bool save_carry, cudaStream_t st) {
+    if (b->plan.frames.empty()) { b->launches = 0; return NVB_OK; }
+    LaunchArgs a = make_args(ctx, b, spectrum ? spectrum : b->d_spectrum, d_pcm, save_carry);
+    int launches = 0, r;
+    NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), st));
+    if (stage != 2) {
+        if ((r = launch_spectrum(a, st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_spectrum launch");
+        launches += r;
+    }
+    if (stage != 1) {
+        if (b->fused) {
+            if ((r = launch_imdct_fused(a, b->plan.frames.data(), st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_imdct_fused launch");
+            launches += r;
+        } else {
+            if ((r = launch_imdct_exact(a, st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_imdct_exact launch");
+            launches += r;
+            if ((r = launch_ola(a, st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_ola launch");
+            launches += r;
+            if (save_carry && b->plan.last_ok >= 0) {
+                const DevFrame& lf = b->plan.frames[(size_t)b->plan.last_ok];
+                NVB_CUDA(ctx, cudaMemcpy2DAsync(a.carry_out, sizeof(float) * ctx->H.bs[1], b->d_blocks + 2 * (size_t)lf.spec_off, sizeof(float) * lf.n,
+                                                sizeof(float) * lf.n, (size_t)ctx->H.channels, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+    }
+    b->launches = launches;
+    return NVB_OK;
+}
+
+int fetch_result(nvb_ctx* ctx, nvb_dbatch* b, cudaStream_t st, nvb_result* res) {
+    Counters c; std::memset(&c, 0, sizeof c);
+    if (!b->plan.frames.empty()) {
+        NVB_CUDA(ctx, cudaMemcpyAsync(&c, b->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
+    }
+    NVB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (res) {
+        res->samples_per_channel = b->plan.samples;
+        res->has_clipped = c.clipped ? 1 : 0;
+        res->n_failed = b->plan.n_failed;
+        res->n_floor_range = c.floor_range;
+        res->n_inconsistent = b->plan.n_inconsistent;
+    }
+    if (c.bad_entry) return set_err(ctx, NVB_ERR_DATA, "a VQ entry number is outside its codebook (Codebook.cs:322 would throw)");
+    return NVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nvb_abi_version(void) { return NVB_ABI_VERSION; }
+
+const char* nvb_strerror(int status) {
+    switch (status) {
+        case NVB_OK: return "ok";
+        case NVB_ERR_ARG: return "invalid argument";
+        case NVB_ERR_CUDA: return "CUDA failure";
+        case NVB_ERR_UNSUPPORTED: return "setup outside the supported envelope";
+        case NVB_ERR_NOMEM: return "out of memory";
+        case NVB_ERR_STATE: return "invalid call order";
+        case NVB_ERR_CAPACITY: return "output buffer too small";
+        case NVB_ERR_DATA: return "malformed data";
+        default: return "unknown status";
+    }
+}
+
+const char* nvb_last_error(nvb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int nvb_create(int device, nvb_ctx** out) {
+    if (!out) return set_err(nullptr, NVB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(nullptr, e, "cudaGetDeviceCount (no CPU fallback exists)"); }
+    if (device < 0 || device >= count) return set_err(nullptr, NVB_ERR_ARG, "device index out of range");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10) return set_err(nullptr, NVB_ERR_CUDA, "device is not sm_100-class: this library carries sm_100a code only");
+    nvb_ctx* ctx = new (std::nothrow) nvb_ctx();
+    if (!ctx) return set_err(nullptr, NVB_ERR_NOMEM, "host allocation failed");
+    ctx->device = device;
+    DeviceGuard g(device);
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    *out = ctx;
+    return NVB_OK;
+}
+
+int nvb_destroy(nvb_ctx* ctx) {
+    if (!ctx) return NVB_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_dbatch(ctx->staging);
+    cudaFree(ctx->d_pcm); cudaFree(ctx->d_blob); cudaFree(ctx->d_carry[0]); cudaFree(ctx->d_carry[1]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return NVB_OK;
+}
+
+int nvb_host_alloc(size_t bytes, void** out) {
+    if (!out) return set_err(nullptr, NVB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return cuda_fail(nullptr, e, "cudaHostAlloc"); }
+    return NVB_OK;
+}
+int nvb_host_free(void* p) {
+    if (!p) return NVB_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFreeHost");
+    return NVB_OK;
+}
+
+int nvb_upload_setup(nvb_ctx* ctx, const nvb_setup* setup) {
+    if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
+    std::vector<unsigned char> blob; std::string err;
+    int rc = build_blob(setup, blob, err);
+    if (rc != NVB_OK) return set_err(ctx, rc, err);
+    return install_blob(ctx, std::move(blob));
+}
+
+int nvb_setup_blob_size(nvb_ctx* ctx, size_t* bytes) {
+    if (!ctx || !bytes) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    if (!ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
+    *bytes = ctx->host_blob.size();
+    return NVB_OK;
+}
+int nvb_setup_blob_export(nvb_ctx* ctx, void* dst, size_t bytes) {
+    if (!ctx || !dst) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    if (!ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
+    if (bytes < ctx->host_blob.size()) return set_err(ctx, NVB_ERR_CAPACITY, "blob buffer too small");
+    std::memcpy(dst, ctx->host_blob.data(), ctx->host_blob.size());
+    return NVB_OK;
+}
+int nvb_setup_blob_import(nvb_ctx* ctx, const void* src, size_t bytes) {
+    if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
+    std::string err;
+    int rc = validate_blob(src, bytes, err);
+    if (rc != NVB_OK) return set_err(ctx, rc, err);
+    std::vector<unsigned char> blob((const unsigned char*)src, (const unsigned char*)src + bytes);
+    return install_blob(ctx, std::move(blob));
+}
+
+int nvb_post_stride(nvb_ctx* ctx) {
+    if (!ctx || !ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
+    return ctx->H.post_stride;
+}
+
+int nvb_reset(nvb_ctx* ctx) {
+    if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
+    ctx->carry = CarryState();
+    return NVB_OK;
+}
+
+int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap, nvb_result* res) {
+    if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
+    if (!ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
+    DeviceGuard g(ctx->device);
+    if (!ctx->staging) { ctx->staging = new (std::nothrow) nvb_dbatch(); if (!ctx->staging) return set_err(ctx, NVB_ERR_NOMEM, "host allocation failed"); }
+    nvb_dbatch* b = ctx->staging;
+    int rc = upload_batch(ctx, b, batch, flags, ctx->stream);
+    if (rc != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+    const size_t n_out = (size_t)b->plan.samples * ctx->H.channels;
+    if (n_out > pcm_cap || (n_out > 0 && !pcm_out)) { cudaStreamSynchronize(ctx->stream); return set_err(ctx, NVB_ERR_CAPACITY, "pcm_out too small for the batch"); }
+    if ((rc = grow(ctx, ctx->d_pcm, ctx->pcm_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+    rc = enqueue(ctx, b, 0, nullptr, ctx->d_pcm, true, ctx->stream);
+    if (rc != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+    if (n_out) NVB_CUDA(ctx, cudaMemcpyAsync(pcm_out, ctx->d_pcm, n_out * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = fetch_result(ctx, b, ctx->stream, res);
+    // the decoder state advances like StreamDecoder's even when an entry was out of range
+    ctx->carry = b->plan.end_state;
+    if (b->plan.last_ok >= 0) ctx->carry_cur ^= 1;
+    return rc;
+}
+
+int nvb_dbatch_create(nvb_ctx* ctx, const nvb_batch* batch, int flags, nvb_dbatch** out) {
+    if (!ctx || !out) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (!ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
+    DeviceGuard g(ctx->device);
+    nvb_dbatch* b = new (std::nothrow) nvb_dbatch();
+    if (!b) return set_err(ctx, NVB_ERR_NOMEM, "host allocation failed");
+    int rc = upload_batch(ctx, b, batch, flags, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == NVB_OK && e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaStreamSynchronize");
+    if (rc != NVB_OK) { free_dbatch(b); return rc; }
+    *out = b;
+    return NVB_OK;
+}
+
+int64_t nvb_dbatch_samples(const nvb_dbatch* b) { return b ? b->plan.samples : -1; }
+int64_t nvb_dbatch_spectrum_floats(const nvb_dbatch* b) { return b ? b->plan.spec_floats : -1; }
+int nvb_dbatch_launches(const nvb_dbatch* b) { return b ? b->launches : -1; }
+
+int nvb_dbatch_run(nvb_ctx* ctx, nvb_dbatch* b, float* d_pcm, void* stream) {
+    if (!ctx || !b || (!d_pcm && b->plan.samples > 0)) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    DeviceGuard g(ctx->device);
+    return enqueue(ctx, b, 0, nullptr, d_pcm, false, (cudaStream_t)stream);
+}
+int nvb_dbatch_run_spectrum(nvb_ctx* ctx, nvb_dbatch* b, float* d_spectrum, void* stream) {
+    if (!ctx || !b || (!d_spectrum && b->plan.spec_floats > 0)) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    DeviceGuard g(ctx->device);
+    return enqueue(ctx, b, 1, d_spectrum, nullptr, false, (cudaStream_t)stream);
+}
+int nvb_dbatch_run_imdct(nvb_ctx* ctx, nvb_dbatch* b, const float* d_spectrum, float* d_pcm, void* stream) {
+    if (!ctx || !b || (!d_spectrum && b->plan.spec_floats > 0) || (!d_pcm && b->plan.samples > 0)) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    DeviceGuard g(ctx->device);
+    return enqueue(ctx, b, 2, const_cast<float*>(d_spectrum), d_pcm, false, (cudaStream_t)stream);
+}
+int nvb_dbatch_result(nvb_ctx* ctx, nvb_dbatch* b, void* stream, nvb_result* res) {
+    if (!ctx || !b) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    DeviceGuard g(ctx->device);
+    return fetch_result(ctx, b, (cudaStream_t)stream, res);
+}
+int nvb_dbatch_destroy(nvb_ctx* ctx, nvb_dbatch* b) {
+    if (!b) return NVB_OK;
+    if (ctx) { DeviceGuard g(ctx->device); cudaDeviceSynchronize(); free_dbatch(b); }
+    else free_dbatch(b);
+    return NVB_OK;
+}
+
+}  // extern "C"

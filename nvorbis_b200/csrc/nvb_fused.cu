@@ -15,14 +15,15 @@
 //   * the first block of a run is recomputed as a halo (its output belongs to the previous CTA);
 //   * output: two samples x two channels per thread as one float4 store, coalesced.
 // No tensor cores: the IMDCT is FFT-structured, not a dense contraction.
+#if !defined(NVB_CPU_SHIM)
 #include <cuda_runtime.h>
+#endif
 #include "nvb_fused_core.h"
 
 namespace nvb {
 
 constexpr int FUSED_THREADS = 256;
 constexpr int FUSED_WARPS = FUSED_THREADS / 32;
-constexpr int FUSED_MAX_G = 8;
 
 struct FusedParams {
     LaunchArgs a;
@@ -43,7 +44,7 @@ __device__ __forceinline__ float slot_z(const DevSetup& S, const DevFrame& f, co
 }
 
 __global__ void __launch_bounds__(FUSED_THREADS, 2) k_imdct_fused(FusedParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NVB_DYN_SMEM(smem_raw);
     const LaunchArgs& a = p.a;
     const DevSetup& S = a.S;
     const int C = S.channels;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_imdct_fused(FusedParams p)
     int first = lo;
     {
         const DevFrame f0 = a.frames[lo];
-        if (f0.kind == 0 && f0.ola_len > 0 && f0.prev >= 0) first = lo - 1;    // halo: previous block's tail is needed
+        if (f0.prev >= 0 && (f0.ola_len > 0 || f0.kind != 0)) first = lo - 1;   // halo: previous block's tail is needed
     }
     int clipped = 0;
 
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_imdct_fused(FusedParams p)
             const int len = f.out_end - f.out_begin;
             const float* slots_f = s_slots + (size_t)r * C * FUSED_SLOT_FLOATS;
             const DevFrame* pf = nullptr; const float* slots_p = nullptr;
-            if (f.ola_len > 0 && f.prev >= 0) {
+            if (f.prev >= 0 && (f.ola_len > 0 || f.kind != 0)) {
                 const int rp = (f.prev - first) % (G + 1);
                 pf = &s_fr[rp]; slots_p = s_slots + (size_t)rp * C * FUSED_SLOT_FLOATS;
             }
@@ -170,18 +171,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_imdct_fused(FusedParams p)
                     const int s = idx / C, c = idx - s * C;
                     const int i = f.out_begin + s;
                     float v;
-                    if (f.kind == 0) v = slot_z(S, f, slots_f + c * FUSED_SLOT_FLOATS, c, i);
-                    else v = a.carry_in[(size_t)c * S.bs[1] + i];
-                    const int o = i - f.start;
-                    if (f.ola_len > 0 && o >= 0 && o < f.ola_len) {
-                        if (pf) v += slot_z(S, *pf, slots_p + c * FUSED_SLOT_FLOATS, c, f.prev_valid + o);
-                        else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)c * S.bs[1] + f.prev_valid + o];
+                    if (f.kind == 0) {
+                        v = slot_z(S, f, slots_f + c * FUSED_SLOT_FLOATS, c, i);
+                        const int o = i - f.start;
+                        if (f.ola_len > 0 && o >= 0 && o < f.ola_len) {                       // StreamDecoder.cs:532-541
+                            if (pf) v += slot_z(S, *pf, slots_p + c * FUSED_SLOT_FLOATS, c, f.prev_valid + o);
+                            else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)c * S.bs[1] + f.prev_valid + o];
+                        }
+                    } else {                                                                  // drain, StreamDecoder.cs:352-356
+                        v = pf ? slot_z(S, *pf, slots_p + c * FUSED_SLOT_FLOATS, c, i) : a.carry_in[(size_t)c * S.bs[1] + i];
                     }
                     if (a.clip) v = clipf(v, clipped);
                     a.pcm[((size_t)f.pcm_off + s) * C + c] = v;
                 }
             }
-            if (x == a.n_frames - 1 && a.carry_out && f.kind == 0) {
+            if (x == a.carry_frame && a.carry_out && f.kind == 0) {
                 // keep the last windowed block for the next batch (StreamDecoder.cs:455-461)
                 for (int idx = tid; idx < f.n * C; idx += FUSED_THREADS) {
                     const int c = idx / f.n, i = idx - c * f.n;
@@ -226,7 +230,7 @@ int launch_imdct_fused(const LaunchArgs& a, const DevFrame*, void* stream) {
     if (fpc < p.G) fpc = p.G;
     p.frames_per_cta = fpc;
     const int grid = (a.n_frames + fpc - 1) / fpc;
-    k_imdct_fused<<<grid, FUSED_THREADS, smem, (cudaStream_t)stream>>>(p);
+    NVB_LAUNCH(k_imdct_fused, grid, FUSED_THREADS, smem, stream, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

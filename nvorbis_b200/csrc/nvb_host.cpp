@@ -1,0 +1,465 @@
+// nvb_host.cpp -- CUDA-free host logic of the C ABI (see nvb_host.h).
+//
+// Table construction follows the reference's expression order and float/double mix exactly
+// (tables are inputs to the GPU arithmetic, so they must be the reference's numbers):
+//   Mdct twiddles  Mdct.cs:30-63      window  Mode.cs:15,69-100      overlap  Mode.cs:102-117
+// Batch planning restates the bookkeeping of StreamDecoder.ReadNextPacket (StreamDecoder.cs:417-463)
+// and the drain rule of StreamDecoder.Read (StreamDecoder.cs:352-356) as a prefix computation.
+#include "nvb_host.h"
+#include "nvb_device_core.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace nvb {
+
+static const uint32_t k_inverse_db_bits[256] = {
+#include "inverse_db_table.inc"
+};
+
+namespace {
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+uint32_t bit_reverse32(uint32_t n) {                                    // Utils.cs:16-28
+    n = ((n & 0xAAAAAAAAu) >> 1) | ((n & 0x55555555u) << 1);
+    n = ((n & 0xCCCCCCCCu) >> 2) | ((n & 0x33333333u) << 2);
+    n = ((n & 0xF0F0F0F0u) >> 4) | ((n & 0x0F0F0F0Fu) << 4);
+    n = ((n & 0xFF00FF00u) >> 8) | ((n & 0x00FF00FFu) << 8);
+    return (n >> 16) | (n << 16);
+}
+
+struct BlobWriter {
+    std::vector<unsigned char>& buf;
+    explicit BlobWriter(std::vector<unsigned char>& b) : buf(b) {}
+    uint64_t reserve(size_t bytes) {
+        size_t off = (buf.size() + 15) & ~size_t(15);
+        buf.resize(off + bytes, 0);
+        return off;
+    }
+    template <class T> T* at(uint64_t off) { return reinterpret_cast<T*>(buf.data() + off); }
+};
+
+// Rising half of the Vorbis window for an overlap of `len` samples (Mode.cs:80-85): the inner sine in
+// double with a float pi/2, squared in float, times the float pi/2 in float, outer sine in double.
+void window_slope(int len, float* out) {
+    const float pi2 = 3.1415926539f / 2;                                 // Mode.cs:15
+    for (int i = 0; i < len; i++) {
+        float x = (float)std::sin((i + .5) / len * (double)pi2);
+        x *= x;
+        out[i] = (float)std::sin((double)(x * pi2));
+    }
+}
+
+// Mode.CalcWindow (Mode.cs:69-100) assembled from the two slopes.
+void assemble_window(const float* slope_l, int left, const float* slope_r, int right, int n, float* out) {
+    const int lb = n / 4 - left / 2, rb = n - n / 4 - right / 2;
+    for (int i = 0; i < n; i++) out[i] = 0.f;
+    for (int i = 0; i < left; i++) out[lb + i] = slope_l[i];
+    for (int i = lb + left; i < rb; i++) out[i] = 1.0f;
+    for (int i = 0; i < right; i++) out[rb + i] = slope_r[right - 1 - i];
+}
+
+void mdct_tables(int n, float* A, float* B, float* C, uint16_t* bitrev) {   // Mdct.cs:30-63
+    const float pi = 3.14159265358979323846264f;                         // Mdct.cs:9 (a float constant)
+    const int n4 = n >> 2, n8 = n >> 3;
+    for (int k = 0; k < n4; k++) {
+        const float aa = (float)(4 * k) * pi / (float)n;                 // int*float/int evaluated in float
+        A[2 * k] = (float)std::cos((double)aa);
+        A[2 * k + 1] = (float)-std::sin((double)aa);
+        const float ab = (float)(2 * k + 1) * pi / (float)n / 2.f;
+        B[2 * k] = (float)std::cos((double)ab) * .5f;
+        B[2 * k + 1] = (float)std::sin((double)ab) * .5f;
+    }
+    for (int k = 0; k < n8; k++) {
+        const float ac = (float)(2 * (2 * k + 1)) * pi / (float)n;
+        C[2 * k] = (float)std::cos((double)ac);
+        C[2 * k + 1] = (float)-std::sin((double)ac);
+    }
+    const int ld = ilog_u(n) - 1;
+    for (int i = 0; i < n8; i++) {
+        const int sh = (32 - (ld - 3)) & 31;                             // C# masks shift counts to 5 bits
+        bitrev[i] = (uint16_t)((bit_reverse32((uint32_t)i) >> sh) << 2);
+    }
+}
+
+void fast_tables(int n, float2* tw, float2* fft) {
+    const int M = n >> 1, Q = n >> 2;
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < Q; k++) {
+        const double a = -pi * (k + 0.125) / M;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        const double b = -2.0 * pi * k / Q;
+        fft[k] = make_float2((float)std::cos(b), (float)std::sin(b));
+    }
+}
+
+int fail(std::string& err, int code, const char* fmt, long long a = 0, long long b = 0) {
+    char tmp[256];
+    std::snprintf(tmp, sizeof tmp, fmt, a, b);
+    err = tmp;
+    return code;
+}
+
+}  // namespace
+
+Overlap nominal_overlap(const BlobHeader& h, int block_flag, int window) {
+    Overlap o;
+    if (!block_flag) { o.start = 0; o.valid = h.bs[0] / 2; o.total = h.bs[0]; return o; }   // Mode.cs:144-147
+    const int n = h.bs[1];
+    const int prev = (window & 1) ? h.bs[1] : h.bs[0], next = (window & 2) ? h.bs[1] : h.bs[0];
+    o.start = n / 4 - prev / 4;                                          // Mode.cs:102-117
+    o.total = n / 4 * 3 + next / 4;
+    o.valid = o.total - next / 4 * 2;
+    return o;
+}
+
+void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) {
+    S.channels = h.channels; S.bs[0] = h.bs[0]; S.bs[1] = h.bs[1];
+    S.post_stride = h.post_stride; S.max_items = h.max_items;
+    S.books = reinterpret_cast<const DevBook*>(base + h.off_books);
+    S.vq = reinterpret_cast<const float*>(base + h.off_vq); S.n_vq = (int64_t)h.n_vq;
+    S.floors = reinterpret_cast<const DevFloor1*>(base + h.off_floors);
+    S.residues = reinterpret_cast<const DevResidue*>(base + h.off_residues);
+    S.mappings = reinterpret_cast<const DevMapping*>(base + h.off_mappings);
+    S.modes = reinterpret_cast<const DevMode*>(base + h.off_modes);
+    S.win_short = reinterpret_cast<const float*>(base + h.off_win_short);
+    S.win_long = reinterpret_cast<const float*>(base + h.off_win_long);
+    for (int i = 0; i < 2; i++) {
+        S.A[i] = reinterpret_cast<const float*>(base + h.off_mdct_a[i]);
+        S.B[i] = reinterpret_cast<const float*>(base + h.off_mdct_b[i]);
+        S.C[i] = reinterpret_cast<const float*>(base + h.off_mdct_c[i]);
+        S.bitrev[i] = reinterpret_cast<const uint16_t*>(base + h.off_bitrev[i]);
+        S.tw[i] = reinterpret_cast<const float2*>(base + h.off_tw[i]);
+        S.fft[i] = reinterpret_cast<const float2*>(base + h.off_fft[i]);
+    }
+    S.db = reinterpret_cast<const float*>(base + h.off_db);
+}
+
+int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string& err) {
+    if (!s) return fail(err, NVB_ERR_ARG, "setup is NULL");
+    if (s->abi_version != NVB_ABI_VERSION) return fail(err, NVB_ERR_ARG, "abi_version %lld, library is %lld", s->abi_version, NVB_ABI_VERSION);
+    if (s->channels < 1) return fail(err, NVB_ERR_DATA, "channels %lld", s->channels);
+    if (s->channels > NVB_MAX_CHANNELS) return fail(err, NVB_ERR_UNSUPPORTED, "channels %lld > %lld", s->channels, NVB_MAX_CHANNELS);
+    for (int i = 0; i < 2; i++)
+        if (!is_pow2(s->block_size[i]) || s->block_size[i] < 64 || s->block_size[i] > 8192)       // StreamDecoder.cs:192-193: 1 << 4 bits
+            return fail(err, NVB_ERR_DATA, "block_size[%lld] = %lld", i, s->block_size[i]);
+    if (s->block_size[0] > s->block_size[1]) return fail(err, NVB_ERR_DATA, "block_size[0] > block_size[1]");
+    if (s->n_books < 1 || s->n_floors < 1 || s->n_residues < 1 || s->n_mappings < 1 || s->n_modes < 1 ||
+        s->n_books > 256 || s->n_floors > 64 || s->n_residues > 64 || s->n_mappings > 64 || s->n_modes > 64)
+        return fail(err, NVB_ERR_DATA, "table counts out of range");
+    if (!s->books || !s->floors || !s->residues || !s->mappings || !s->modes || (s->n_vq_floats > 0 && !s->vq_floats) || s->n_vq_floats < 0)
+        return fail(err, NVB_ERR_ARG, "NULL table pointer");
+    const int C = s->channels;
+
+    for (int i = 0; i < s->n_books; i++) {
+        const nvb_codebook& b = s->books[i];
+        if (b.dims < 0 || b.entries < 0) return fail(err, NVB_ERR_DATA, "book %lld: negative size", i);
+        if (b.map_type != 0 && b.table_off >= 0) {
+            if (b.dims < 1) return fail(err, NVB_ERR_DATA, "book %lld: dims < 1", i);
+            if (b.table_off + (int64_t)b.entries * b.dims > s->n_vq_floats) return fail(err, NVB_ERR_DATA, "book %lld: table outside vq_floats", i);
+        }
+    }
+    int max_posts = 2;
+    for (int i = 0; i < s->n_floors; i++) {
+        const nvb_floor& f = s->floors[i];
+        if (f.type == 0) return fail(err, NVB_ERR_UNSUPPORTED, "floor %lld is type 0 (Floor0.cs): not accepted yet", i);
+        if (f.type != 1) return fail(err, NVB_ERR_DATA, "floor %lld: invalid type %lld", i, f.type);       // Factory.cs:22-31
+        const nvb_floor1& g = f.f1;
+        if (g.n_posts < 2 || g.n_posts > NVB_MAX_POSTS) return fail(err, NVB_ERR_DATA, "floor %lld: n_posts %lld", i, g.n_posts);
+        if (g.multiplier < 1 || g.multiplier > 4 || g.range < 1 || g.range > 256) return fail(err, NVB_ERR_DATA, "floor %lld: multiplier/range", i);
+        if (g.x_list[0] != 0) return fail(err, NVB_ERR_DATA, "floor %lld: x_list[0] != 0", i);
+        for (int k = 2; k < g.n_posts; k++) {
+            const int lo = g.l_neigh[k], hi = g.h_neigh[k];
+            if (lo >= k || hi >= k || !(g.x_list[lo] < g.x_list[k] && g.x_list[k] < g.x_list[hi]))
+                return fail(err, NVB_ERR_DATA, "floor %lld: bad neighbours of post %lld", i, k);
+        }
+        unsigned long long seen = 0;
+        for (int k = 0; k < g.n_posts; k++) {
+            const int sx = g.sort_idx[k];
+            if (sx >= g.n_posts || ((seen >> sx) & 1ull)) return fail(err, NVB_ERR_DATA, "floor %lld: sort_idx is not a permutation", i);
+            seen |= 1ull << sx;
+            if (k > 0 && !(g.x_list[g.sort_idx[k - 1]] < g.x_list[sx])) return fail(err, NVB_ERR_DATA, "floor %lld: sort_idx not ascending in x", i);
+        }
+        if (g.sort_idx[0] != 0) return fail(err, NVB_ERR_DATA, "floor %lld: sort_idx[0] != 0", i);
+        if (g.n_posts > max_posts) max_posts = g.n_posts;
+    }
+    for (int i = 0; i < s->n_residues; i++) {
+        const nvb_residue& r = s->residues[i];
+        if (r.type < 0 || r.type > 2) return fail(err, NVB_ERR_DATA, "residue %lld: invalid type %lld", i, r.type);   // Factory.cs:48-58
+        if (r.begin < 0 || r.end < 0 || r.partition_size < 1 || r.classifications < 1 || r.classifications > NVB_MAX_CLASSES ||
+            r.max_stages < 0 || r.max_stages > NVB_MAX_STAGES)
+            return fail(err, NVB_ERR_DATA, "residue %lld: header fields out of range", i);
+        for (int c = 0; c < r.classifications; c++)
+            for (int st = 0; st < r.max_stages; st++) {
+                if (!((r.cascade[c] >> st) & 1)) continue;
+                const int bk = r.books[c][st];
+                if (bk < 0) continue;
+                if (bk >= s->n_books) return fail(err, NVB_ERR_DATA, "residue %lld: book %lld out of range", i, bk);
+                const nvb_codebook& b = s->books[bk];
+                if (b.map_type == 0 || b.table_off < 0 || b.dims < 1) return fail(err, NVB_ERR_DATA, "residue %lld: book %lld has no lookup table", i, bk);   // Residue0.cs:66-67
+                if (b.entries > 65536) return fail(err, NVB_ERR_UNSUPPORTED, "residue %lld: book %lld has more than 65536 entries", i, bk);
+                if (r.type == 0 && r.partition_size / b.dims < 1) return fail(err, NVB_ERR_DATA, "residue %lld: type 0 book %lld wider than a partition", i, bk);
+            }
+    }
+    for (int i = 0; i < s->n_mappings; i++) {
+        const nvb_mapping& m = s->mappings[i];
+        if (m.n_submaps != 1) return fail(err, NVB_ERR_UNSUPPORTED, "mapping %lld has %lld submaps (Mapping.cs:122-134 mis-decodes those)", i, m.n_submaps);
+        if (m.n_coupling < 0 || m.n_coupling > 256) return fail(err, NVB_ERR_DATA, "mapping %lld: coupling steps", i);
+        if (m.n_coupling > NVB_MAX_COUPLING) return fail(err, NVB_ERR_UNSUPPORTED, "mapping %lld: %lld coupling steps", i, m.n_coupling);
+        for (int k = 0; k < m.n_coupling; k++)
+            if (m.magnitude[k] == m.angle[k] || m.magnitude[k] >= C || m.angle[k] >= C)                  // Mapping.cs:36-41
+                return fail(err, NVB_ERR_DATA, "mapping %lld: invalid coupling step %lld", i, k);
+        if (m.floor < 0 || m.floor >= s->n_floors || m.residue < 0 || m.residue >= s->n_residues)
+            return fail(err, NVB_ERR_DATA, "mapping %lld: floor/residue index", i);
+    }
+    for (int i = 0; i < s->n_modes; i++)
+        if (s->modes[i].mapping < 0 || s->modes[i].mapping >= s->n_mappings) return fail(err, NVB_ERR_DATA, "mode %lld: mapping index", i);   // Mode.cs:35-38
+
+    blob.clear();
+    BlobWriter w(blob);
+    w.reserve(sizeof(BlobHeader));
+    BlobHeader h; std::memset(&h, 0, sizeof h);
+    h.magic = BLOB_MAGIC; h.abi = NVB_ABI_VERSION;
+    h.channels = C; h.sample_rate = s->sample_rate; h.bs[0] = s->block_size[0]; h.bs[1] = s->block_size[1];
+    h.n_books = s->n_books; h.n_floors = s->n_floors; h.n_residues = s->n_residues; h.n_mappings = s->n_mappings; h.n_modes = s->n_modes;
+    h.post_stride = (2 + max_posts + 1) & ~1;
+    h.n_vq = (uint64_t)s->n_vq_floats;
+
+    h.off_books = w.reserve(sizeof(DevBook) * s->n_books);
+    for (int i = 0; i < s->n_books; i++) {
+        DevBook d; d.dims = s->books[i].dims; d.entries = s->books[i].entries;
+        d.off = (s->books[i].map_type != 0) ? s->books[i].table_off : -1;
+        w.at<DevBook>(h.off_books)[i] = d;
+    }
+    h.off_vq = w.reserve(sizeof(float) * (size_t)(s->n_vq_floats > 0 ? s->n_vq_floats : 1));
+    if (s->n_vq_floats > 0) std::memcpy(w.at<float>(h.off_vq), s->vq_floats, sizeof(float) * (size_t)s->n_vq_floats);
+    h.off_floors = w.reserve(sizeof(DevFloor1) * s->n_floors);
+    for (int i = 0; i < s->n_floors; i++) {
+        const nvb_floor1& g = s->floors[i].f1;
+        DevFloor1 d; std::memset(&d, 0, sizeof d);
+        d.n_posts = g.n_posts; d.mult = g.multiplier; d.range = g.range;
+        for (int k = 0; k < g.n_posts; k++) { d.x[k] = g.x_list[k]; d.lo[k] = g.l_neigh[k]; d.hi[k] = g.h_neigh[k]; d.sort[k] = g.sort_idx[k]; }
+        w.at<DevFloor1>(h.off_floors)[i] = d;
+    }
+    h.off_residues = w.reserve(sizeof(DevResidue) * s->n_residues);
+    for (int i = 0; i < s->n_residues; i++) {
+        const nvb_residue& r = s->residues[i];
+        DevResidue d; std::memset(&d, 0, sizeof d);
+        d.type = r.type; d.begin = r.begin; d.end = r.end; d.psize = r.partition_size; d.nclass = r.classifications; d.stages = r.max_stages;
+        for (int c = 0; c < NVB_MAX_CLASSES; c++) {
+            d.cascade[c] = c < r.classifications ? r.cascade[c] : 0;
+            for (int st = 0; st < NVB_MAX_STAGES; st++)
+                d.books[c][st] = (c < r.classifications && st < r.max_stages && ((r.cascade[c] >> st) & 1)) ? r.books[c][st] : (int16_t)-1;
+        }
+        w.at<DevResidue>(h.off_residues)[i] = d;
+    }
+    h.off_mappings = w.reserve(sizeof(DevMapping) * s->n_mappings);
+    for (int i = 0; i < s->n_mappings; i++) {
+        const nvb_mapping& m = s->mappings[i];
+        DevMapping d; std::memset(&d, 0, sizeof d);
+        d.n_coupling = m.n_coupling; d.floor = m.floor; d.residue = m.residue;
+        for (int k = 0; k < m.n_coupling; k++) { d.mag[k] = m.magnitude[k]; d.ang[k] = m.angle[k]; }
+        w.at<DevMapping>(h.off_mappings)[i] = d;
+    }
+    h.off_modes = w.reserve(sizeof(DevMode) * s->n_modes);
+    for (int i = 0; i < s->n_modes; i++) {
+        DevMode d; d.block_flag = s->modes[i].block_flag ? 1 : 0; d.mapping = s->modes[i].mapping;
+        w.at<DevMode>(h.off_modes)[i] = d;
+    }
+
+    // windows (Mode.cs:24-67): one for the short size, four for the long size
+    {
+        std::vector<float> slope[2];
+        for (int i = 0; i < 2; i++) {
+            slope[i].resize((size_t)h.bs[i] / 2);
+            if (s->window_slope[i]) std::memcpy(slope[i].data(), s->window_slope[i], sizeof(float) * slope[i].size());
+            else window_slope(h.bs[i] / 2, slope[i].data());
+        }
+        h.off_win_short = w.reserve(sizeof(float) * h.bs[0]);
+        assemble_window(slope[0].data(), h.bs[0] / 2, slope[0].data(), h.bs[0] / 2, h.bs[0], w.at<float>(h.off_win_short));
+        h.off_win_long = w.reserve(sizeof(float) * 4 * (size_t)h.bs[1]);
+        for (int wi = 0; wi < 4; wi++) {
+            const int l = (wi & 1) ? 1 : 0, r = (wi & 2) ? 1 : 0;            // Mode.cs:44-50
+            assemble_window(slope[l].data(), h.bs[l] / 2, slope[r].data(), h.bs[r] / 2, h.bs[1], w.at<float>(h.off_win_long) + (size_t)wi * h.bs[1]);
+        }
+    }
+    for (int i = 0; i < 2; i++) {
+        const int n = h.bs[i];
+        h.off_mdct_a[i] = w.reserve(sizeof(float) * (n / 2));
+        h.off_mdct_b[i] = w.reserve(sizeof(float) * (n / 2));
+        h.off_mdct_c[i] = w.reserve(sizeof(float) * (n / 4));
+        h.off_bitrev[i] = w.reserve(sizeof(uint16_t) * (n / 8));
+        h.off_tw[i] = w.reserve(sizeof(float2) * (n / 4));
+        h.off_fft[i] = w.reserve(sizeof(float2) * (n / 4));
+        mdct_tables(n, w.at<float>(h.off_mdct_a[i]), w.at<float>(h.off_mdct_b[i]), w.at<float>(h.off_mdct_c[i]), w.at<uint16_t>(h.off_bitrev[i]));
+        if (s->mdct_a[i]) std::memcpy(w.at<float>(h.off_mdct_a[i]), s->mdct_a[i], sizeof(float) * (n / 2));
+        if (s->mdct_b[i]) std::memcpy(w.at<float>(h.off_mdct_b[i]), s->mdct_b[i], sizeof(float) * (n / 2));
+        if (s->mdct_c[i]) std::memcpy(w.at<float>(h.off_mdct_c[i]), s->mdct_c[i], sizeof(float) * (n / 4));
+        if (s->mdct_bitrev[i]) std::memcpy(w.at<uint16_t>(h.off_bitrev[i]), s->mdct_bitrev[i], sizeof(uint16_t) * (n / 8));
+        fast_tables(n, w.at<float2>(h.off_tw[i]), w.at<float2>(h.off_fft[i]));
+    }
+    h.off_db = w.reserve(sizeof(float) * 256);
+    std::memcpy(w.at<float>(h.off_db), k_inverse_db_bits, sizeof k_inverse_db_bits);
+
+    // largest residue item table over the modes (k_spectrum's shared-memory prefix array)
+    {
+        DevSetup S; resolve_setup(blob.data(), h, S);
+        int mx = 1;
+        for (int i = 0; i < h.n_modes; i++) {
+            const DevMode& md = S.modes[i];
+            const DevResidue& R = S.residues[S.mappings[md.mapping].residue];
+            ResGeom g = residue_geom(R, h.bs[md.block_flag], C);
+            if (g.n_items > mx) mx = g.n_items;
+        }
+        if (mx > 40000) return fail(err, NVB_ERR_UNSUPPORTED, "residue layout needs %lld prefix items (> 40000)", mx);
+        h.max_items = mx;
+    }
+    w.reserve(0);
+    h.total_bytes = blob.size();
+    std::memcpy(blob.data(), &h, sizeof h);
+    return NVB_OK;
+}
+
+int validate_blob(const void* data, size_t bytes, std::string& err) {
+    if (!data || bytes < sizeof(BlobHeader)) return fail(err, NVB_ERR_ARG, "blob too small");
+    BlobHeader h; std::memcpy(&h, data, sizeof h);
+    if (h.magic != BLOB_MAGIC || h.abi != NVB_ABI_VERSION) return fail(err, NVB_ERR_DATA, "blob magic/abi mismatch");
+    if (h.total_bytes != bytes) return fail(err, NVB_ERR_DATA, "blob size %lld, header says %lld", (long long)bytes, (long long)h.total_bytes);
+    if (h.channels < 1 || h.channels > NVB_MAX_CHANNELS || !is_pow2(h.bs[0]) || !is_pow2(h.bs[1]) || h.bs[0] < 64 || h.bs[1] > 8192 || h.bs[0] > h.bs[1])
+        return fail(err, NVB_ERR_DATA, "blob header fields out of range");
+    auto in = [&](uint64_t off, uint64_t len) { return off >= sizeof(BlobHeader) && off + len <= bytes && (off & 15) == 0; };
+    bool ok = in(h.off_books, sizeof(DevBook) * (uint64_t)h.n_books) && in(h.off_vq, sizeof(float) * h.n_vq) &&
+              in(h.off_floors, sizeof(DevFloor1) * (uint64_t)h.n_floors) && in(h.off_residues, sizeof(DevResidue) * (uint64_t)h.n_residues) &&
+              in(h.off_mappings, sizeof(DevMapping) * (uint64_t)h.n_mappings) && in(h.off_modes, sizeof(DevMode) * (uint64_t)h.n_modes) &&
+              in(h.off_win_short, 4ull * h.bs[0]) && in(h.off_win_long, 16ull * h.bs[1]) && in(h.off_db, 1024);
+    for (int i = 0; i < 2 && ok; i++)
+        ok = in(h.off_mdct_a[i], 2ull * h.bs[i]) && in(h.off_mdct_b[i], 2ull * h.bs[i]) && in(h.off_mdct_c[i], 1ull * h.bs[i]) &&
+             in(h.off_bitrev[i], h.bs[i] / 4ull) && in(h.off_tw[i], 2ull * h.bs[i]) && in(h.off_fft[i], 2ull * h.bs[i]);
+    if (!ok) return fail(err, NVB_ERR_DATA, "blob section outside the blob");
+    // index ranges the kernels rely on
+    const unsigned char* base = static_cast<const unsigned char*>(data);
+    DevSetup S; resolve_setup(base, h, S);
+    for (int i = 0; i < h.n_modes; i++) if (S.modes[i].mapping < 0 || S.modes[i].mapping >= h.n_mappings) return fail(err, NVB_ERR_DATA, "blob: mode %lld", i);
+    for (int i = 0; i < h.n_mappings; i++) {
+        const DevMapping& m = S.mappings[i];
+        if (m.floor < 0 || m.floor >= h.n_floors || m.residue < 0 || m.residue >= h.n_residues || m.n_coupling < 0 || m.n_coupling > NVB_MAX_COUPLING)
+            return fail(err, NVB_ERR_DATA, "blob: mapping %lld", i);
+        for (int k = 0; k < m.n_coupling; k++) if (m.mag[k] >= h.channels || m.ang[k] >= h.channels) return fail(err, NVB_ERR_DATA, "blob: mapping %lld coupling", i);
+    }
+    for (int i = 0; i < h.n_residues; i++) {
+        const DevResidue& r = S.residues[i];
+        if (r.type < 0 || r.type > 2 || r.psize < 1 || r.nclass < 1 || r.nclass > NVB_MAX_CLASSES || r.stages < 0 || r.stages > NVB_MAX_STAGES || r.begin < 0)
+            return fail(err, NVB_ERR_DATA, "blob: residue %lld", i);
+        for (int c = 0; c < r.nclass; c++) for (int st = 0; st < r.stages; st++) {
+            const int bk = r.books[c][st];
+            if (bk < 0) continue;
+            if (bk >= h.n_books) return fail(err, NVB_ERR_DATA, "blob: residue %lld book", i);
+            const DevBook& b = S.books[bk];
+            if (b.dims < 1 || b.off < 0 || b.off + (int64_t)b.entries * b.dims > (int64_t)h.n_vq) return fail(err, NVB_ERR_DATA, "blob: residue %lld book table", i);
+        }
+    }
+    for (int i = 0; i < h.n_floors; i++) {
+        const DevFloor1& f = S.floors[i];
+        if (f.n_posts < 2 || f.n_posts > NVB_MAX_POSTS) return fail(err, NVB_ERR_DATA, "blob: floor %lld", i);
+        for (int k = 0; k < f.n_posts; k++) {
+            if (f.sort[k] >= f.n_posts) return fail(err, NVB_ERR_DATA, "blob: floor %lld sort", i);
+            if (k >= 2 && (f.lo[k] >= k || f.hi[k] >= k || !(f.x[f.lo[k]] < f.x[k] && f.x[k] < f.x[f.hi[k]]))) return fail(err, NVB_ERR_DATA, "blob: floor %lld neighbours", i);
+            if (k > 0 && !(f.x[f.sort[k - 1]] < f.x[f.sort[k]])) return fail(err, NVB_ERR_DATA, "blob: floor %lld order", i);
+        }
+    }
+    if (h.post_stride < 4 || h.max_items < 1 || h.max_items > 40000) return fail(err, NVB_ERR_DATA, "blob: post_stride/max_items");
+    return NVB_OK;
+}
+
+int plan_batch(const unsigned char* host_blob, const nvb_batch* b, int flags, const CarryState& in, Plan& out, std::string& err) {
+    BlobHeader h; std::memcpy(&h, host_blob, sizeof h);
+    DevSetup S; resolve_setup(host_blob, h, S);
+    if (!b || b->n_frames < 0) return fail(err, NVB_ERR_ARG, "batch is NULL or n_frames < 0");
+    if (b->n_frames > 0 && (!b->frames || !b->posts)) return fail(err, NVB_ERR_ARG, "batch.frames / batch.posts is NULL");
+    if (b->n_classes < 0 || b->n_entries < 0 || (b->n_classes > 0 && !b->classes) || (b->n_entries > 0 && !b->entries))
+        return fail(err, NVB_ERR_ARG, "batch.classes / batch.entries");
+    const int C = h.channels;
+    out = Plan();
+    out.frames.reserve((size_t)b->n_frames);
+    CarryState st = (flags & NVB_RUN_CONTINUE) ? in : CarryState();
+    int last_ok = -1;
+    int64_t pcm = 0, spec = 0;
+
+    for (int i = 0; i < b->n_frames; i++) {
+        const nvb_frame& f = b->frames[i];
+        if (f.status != NVB_FRAME_OK) {
+            // DecodeNextPacket returned null: the rest of the previous block is handed out as it is
+            // (StreamDecoder.cs:352-356: _prevPacketEnd = _prevPacketStop)
+            ++out.n_failed;
+            st.prev_end = st.prev_stop;
+            if (st.have_prev && st.prev_end > st.prev_start) {
+                DevFrame d; std::memset(&d, 0, sizeof d);
+                d.kind = 1; d.n = st.prev_n;
+                d.out_begin = st.prev_start; d.out_end = st.prev_end;
+                d.prev = last_ok >= 0 ? last_ok : PREV_CARRY;
+                if (d.prev == PREV_CARRY) out.uses_carry = true;
+                d.api_index = i; d.pcm_off = pcm;
+                pcm += d.out_end - d.out_begin;
+                out.frames.push_back(d);
+            }
+            st.prev_start = st.prev_end;
+            continue;
+        }
+        if (f.mode >= h.n_modes) return fail(err, NVB_ERR_DATA, "frame %lld: mode %lld out of range", i, f.mode);   // StreamDecoder.cs:497
+        const DevMode& md = S.modes[f.mode];
+        const int n = h.bs[md.block_flag];
+        if (f.window > 3 || (!md.block_flag && f.window != 0)) return fail(err, NVB_ERR_DATA, "frame %lld: window %lld", i, f.window);
+        if (f.start < 0 || f.total > n || f.start > f.total || f.valid > f.total) return fail(err, NVB_ERR_DATA, "frame %lld: start/valid/total outside the block", i);
+        if ((f.exec_mask >> C) != 0) return fail(err, NVB_ERR_DATA, "frame %lld: exec_mask has bits above the channel count", i);
+        const DevMapping& mp = S.mappings[md.mapping];
+        if (f.res_decoded) {
+            const ResGeom g = residue_geom(S.residues[mp.residue], n, C);
+            if ((int64_t)f.classes_off + (int64_t)g.P * g.Sx > b->n_classes) return fail(err, NVB_ERR_DATA, "frame %lld: classes outside the batch", i);
+            if ((int64_t)f.entries_off + (int64_t)f.entry_count > b->n_entries) return fail(err, NVB_ERR_DATA, "frame %lld: entries outside the batch", i);
+        }
+        const Overlap nom = nominal_overlap(h, md.block_flag, f.window);
+
+        DevFrame d; std::memset(&d, 0, sizeof d);
+        d.kind = 0; d.mode = f.mode; d.window = f.window; d.res_decoded = f.res_decoded ? 1 : 0;
+        d.exec_mask = f.exec_mask; d.n = n; d.start = f.start; d.api_index = i;
+        d.classes_off = f.classes_off; d.entries_off = f.entries_off; d.entry_count = f.res_decoded ? f.entry_count : 0;
+        d.prev = PREV_NONE; d.ola_len = 0; d.prev_valid = 0;
+
+        if (st.have_prev && st.prev_end > 0) {                               // StreamDecoder.cs:440-445
+            int ola = st.prev_stop - st.prev_start;
+            if (ola < 0) ola = 0;
+            // The reference adds the whole previous tail at [start, start+ola) even when it reaches past
+            // this block's own overlap region (into its tail, or past the block).  Well-formed streams
+            // never do that; clamp and count.
+            int room = nom.valid - f.start; if (room < 0) room = 0;
+            if (ola > room) { ola = room; ++out.n_inconsistent; }
+            if (ola > 0) {
+                d.ola_len = ola; d.prev_valid = st.prev_start;
+                d.prev = last_ok >= 0 ? last_ok : PREV_CARRY;
+                if (d.prev == PREV_CARRY) out.uses_carry = true;
+            }
+            st.prev_start = f.start;
+        } else if (!st.have_prev) {
+            st.prev_start = f.valid;                                         // StreamDecoder.cs:446-450: first block emits nothing
+        }
+        st.prev_end = f.valid; st.prev_stop = f.total; st.have_prev = true; st.prev_n = n;   // StreamDecoder.cs:455-461
+        if (st.prev_end < st.prev_start) {
+            // EOS trim below the start index (StreamDecoder.cs:429-437 can do that): the reference's Read
+            // loop would never terminate; emit nothing.
+            ++out.n_inconsistent; st.prev_start = st.prev_end;
+        }
+        d.out_begin = st.prev_start; d.out_end = st.prev_end;
+        if (d.out_begin < 0) { d.out_begin = 0; if (d.out_end < 0) d.out_end = 0; }
+        d.pcm_off = pcm; pcm += d.out_end - d.out_begin;
+        st.prev_start = st.prev_end;
+        d.spec_off = (uint32_t)spec; spec += (int64_t)C * (n / 2);
+        if (spec > 0x7fffffffLL / 2) return fail(err, NVB_ERR_CAPACITY, "batch too large: %lld spectrum floats", spec);
+        last_ok = (int)out.frames.size();
+        out.frames.push_back(d);
+    }
+    out.samples = pcm; out.spec_floats = spec; out.last_ok = last_ok; out.end_state = st;
+    return NVB_OK;
+}
+
+}  // namespace nvb

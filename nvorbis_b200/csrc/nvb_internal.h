@@ -5,10 +5,17 @@
 #include <cstddef>
 #include "../../include/nvorbis_b200.h"
 
-#if !defined(__CUDACC__)
-// host-only builds (tests/cpu_shim.cpp): the two CUDA vector types the tables use
+#if !defined(__CUDACC__) && !defined(NVB_HAVE_FLOAT2)
+// host-only compilation of nvb_host.cpp: the CUDA vector type the tables use
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+
+// Kernel launch / dynamic shared memory spelled as macros so that tests/cpu_shim (test-only) can
+// compile the same kernel sources against its thread-per-lane emulation.
+#if !defined(NVB_CPU_SHIM)
+#define NVB_LAUNCH(kernel, grid, block, smem, stream, arg) kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(arg)
+#define NVB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
 namespace nvb {
@@ -54,7 +61,7 @@ struct DevSetup {
 // ---- per-frame plan built on the host from nvb_frame (ok frames only, in order) ----------------
 enum { PREV_NONE = -1, PREV_CARRY = -2 };
 struct DevFrame {
-    uint8_t  mode, window, res_decoded, kind;   // kind 0 = normal, 1 = emit the carried tail only (drain at batch start)
+    uint8_t  mode, window, res_decoded, kind;   // kind 0 = decoded block; 1 = drain: emit [out_begin,out_end) of block `prev` as it is
     uint32_t exec_mask;
     int32_t  n;                 // block size
     int32_t  start;             // packetStartIndex: prev tail is added at [start, start+ola_len)
@@ -78,7 +85,8 @@ struct LaunchArgs {
     float* spectrum;            // [sum C*n/2]
     float* blocks;              // [sum C*n]   (exact path scratch)
     const float* carry_in;      // [C][bs1] previous batch's last block (or nullptr)
-    float* carry_out;           // [C][bs1] receives the batch's last block (or nullptr)
+    float* carry_out;           // [C][bs1] receives the windowed block of frame `carry_frame` (or nullptr)
+    int carry_frame;            // DevFrame index of the batch's last decoded block, -1 = none
     float* pcm;
     Counters* counters;
     int clip;

@@ -8,7 +8,9 @@
 //
 // The fused fast path (IMDCT + window + OLA + clip + interleave in one kernel) lives in
 // nvb_fused.cu.  All arithmetic is in nvb_device_core.h; these are thread-mapping shells.
+#if !defined(NVB_CPU_SHIM)
 #include <cuda_runtime.h>
+#endif
 #include "nvb_device_core.h"
 
 namespace nvb {
@@ -23,7 +25,7 @@ constexpr int OLA_THREADS = 256;
 // (L2-resident) in, C*N/2 floats out, written coalesced per channel row.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    NVB_DYN_SMEM(dyn_smem);
     __shared__ FloorSegs s_segs[NVB_MAX_CHANNELS];
     __shared__ float s_db[256];
     __shared__ uint32_t s_warp[SPEC_THREADS / 32];
@@ -114,7 +116,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
 // Bit-identical to Mdct.cs for every N (including its N = 64/128 behaviour).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MDCT_THREADS) k_imdct_exact(LaunchArgs a) {
-    extern __shared__ __align__(16) float sm[];
+    NVB_DYN_SMEM(sm_raw);
+    float* sm = reinterpret_cast<float*>(sm_raw);
     const DevSetup& S = a.S;
     const int C = S.channels;
     const int fi = blockIdx.x / C, c = blockIdx.x - fi * C;
@@ -157,13 +160,16 @@ __global__ void __launch_bounds__(OLA_THREADS) k_ola(LaunchArgs a) {
     const int len = f.out_end - f.out_begin;
     if (len <= 0) return;
     const float* cur; int cstride;
-    if (f.kind == 0) { cur = a.blocks + 2 * (size_t)f.spec_off; cstride = f.n; }
-    else { cur = a.carry_in; cstride = S.bs[1]; }
     const float* prev = nullptr; int pstride = 0;
-    if (f.ola_len > 0) {
-        if (f.prev >= 0) { const DevFrame pf = a.frames[f.prev]; prev = a.blocks + 2 * (size_t)pf.spec_off; pstride = pf.n; }
-        else if (f.prev == PREV_CARRY) { prev = a.carry_in; pstride = S.bs[1]; }
-    }
+    if (f.kind == 0) {
+        cur = a.blocks + 2 * (size_t)f.spec_off; cstride = f.n;
+        if (f.ola_len > 0) {
+            if (f.prev >= 0) { const DevFrame pf = a.frames[f.prev]; prev = a.blocks + 2 * (size_t)pf.spec_off; pstride = pf.n; }
+            else if (f.prev == PREV_CARRY) { prev = a.carry_in; pstride = S.bs[1]; }
+        }
+    } else if (f.prev >= 0) {                   // drain of a block of this batch (StreamDecoder.cs:352-356)
+        const DevFrame pf = a.frames[f.prev]; cur = a.blocks + 2 * (size_t)pf.spec_off; cstride = pf.n;
+    } else { cur = a.carry_in; cstride = S.bs[1]; }
     int clipped = 0;
     const int total = len * C;
     for (int idx = threadIdx.x; idx < total; idx += OLA_THREADS) {
@@ -191,7 +197,7 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         if (cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = smem;
     }
-    k_spectrum<<<a.n_frames, SPEC_THREADS, smem, (cudaStream_t)stream>>>(a);
+    NVB_LAUNCH(k_spectrum, a.n_frames, SPEC_THREADS, smem, stream, a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -203,13 +209,13 @@ int launch_imdct_exact(const LaunchArgs& a, void* stream) {
         if (cudaFuncSetAttribute(k_imdct_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = smem;
     }
-    k_imdct_exact<<<a.n_frames * a.S.channels, MDCT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    NVB_LAUNCH(k_imdct_exact, a.n_frames * a.S.channels, MDCT_THREADS, smem, stream, a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_ola(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
-    k_ola<<<a.n_frames, OLA_THREADS, 0, (cudaStream_t)stream>>>(a);
+    NVB_LAUNCH(k_ola, a.n_frames, OLA_THREADS, 0, stream, a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

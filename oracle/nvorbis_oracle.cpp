@@ -1316,6 +1316,18 @@ struct Decoder {
         currentPosition = 0; ResetDecoder();
     }
 
+    // Same as Open, but from an already-demuxed packet list (an IPacketProvider in the reference's
+    // terms, Contracts/IPacketProvider.cs): used with the committed tests/golden/*.packets.npz fixtures.
+    void OpenPackets(std::vector<std::unique_ptr<Packet>>&& list) {
+        packets = std::move(list);
+        Packet* p = GetNextPacket();
+        if (!p || !LoadStreamHeader(*p)) throw InvalidData("Could not find Vorbis data to decode.");
+        p = GetNextPacket(); if (!p || !LoadComments(*p)) throw InvalidData("bad comment header");
+        setupPacketIndex = nextPacket;
+        p = GetNextPacket(); if (!p || !LoadBooks(*p)) throw InvalidData("bad setup header");
+        currentPosition = 0; ResetDecoder();
+    }
+
     // Mapping.DecodePacket Mapping.cs:95-198
     void MappingDecodePacket(const Mapping& map, Packet& p, int blockSize, std::vector<std::vector<float>>& buffer, FrameRec* rec) {
         int halfBlockSize = blockSize >> 1;
@@ -1498,7 +1510,64 @@ void* orc_open(const uint8_t* data, size_t len) {
     catch (const std::exception& e) { g_lastError = e.what(); return nullptr; }
     return h.release();
 }
+// packet list: `data` = all packets back to back, sizes[i] bytes each; flags bit0 = hasGranule, bit1 = EOS, bit2 = resync
+void* orc_open_packets(const uint8_t* data, const int64_t* sizes, const int64_t* granules, const uint8_t* flags, int64_t n) {
+    auto h = std::make_unique<OrcHandle>();
+    try {
+        std::vector<std::unique_ptr<Packet>> list; size_t off = 0;
+        for (int64_t i = 0; i < n; i++) {
+            auto p = std::make_unique<Packet>();
+            p->data.assign(data + off, data + off + sizes[i]); off += (size_t)sizes[i];
+            p->hasGranule = flags[i] & 1; p->granule = granules[i]; p->isEndOfStream = (flags[i] & 2) != 0; p->isResync = (flags[i] & 4) != 0;
+            list.push_back(std::move(p));
+        }
+        h->dec.OpenPackets(std::move(list));
+    } catch (const std::exception& e) { g_lastError = e.what(); return nullptr; }
+    return h.release();
+}
 void orc_close(void* h) { delete (OrcHandle*)h; }
+
+// ---- setup introspection for the tables Codebook-level calls do not cover
+void orc_counts(void* hh, int64_t* out) {   // nFloors, nResidues, nMappings, nModes
+    Decoder& d = ((OrcHandle*)hh)->dec;
+    out[0] = (int64_t)d.floors.size(); out[1] = (int64_t)d.residues.size(); out[2] = (int64_t)d.mappings.size(); out[3] = (int64_t)d.modes.size();
+}
+// out[0..3] = type, n_posts, multiplier, range; then xList[64], lNeigh[64], hNeigh[64], sortIdx[64]
+int orc_floor_info(void* hh, int fi, int32_t* out) {
+    Decoder& d = ((OrcHandle*)hh)->dec; if (fi < 0 || fi >= (int)d.floors.size()) return -1;
+    const Floor& f = d.floors[fi];
+    std::memset(out, 0, sizeof(int32_t) * 260);
+    out[0] = f.type; out[1] = (int)f.xList.size(); out[2] = f.multiplier; out[3] = f.range;
+    for (size_t k = 0; k < f.xList.size() && k < 64; k++) { out[4 + k] = f.xList[k]; out[68 + k] = f.lNeigh[k]; out[132 + k] = f.hNeigh[k]; out[196 + k] = f.sortIdx[k]; }
+    return 0;
+}
+// out[0..7] = type, begin, end, partitionSize, classifications, maxStages, classBook, channels; cascade[64]; books[64][8] (-1 = none)
+int orc_residue_info(void* hh, int ri, int32_t* out) {
+    Decoder& d = ((OrcHandle*)hh)->dec; if (ri < 0 || ri >= (int)d.residues.size()) return -1;
+    const Residue& r = d.residues[ri];
+    for (int i = 0; i < 8 + 64 + 512; i++) out[i] = (i >= 72) ? -1 : 0;
+    out[0] = r.type; out[1] = r.begin; out[2] = r.end; out[3] = r.partitionSize; out[4] = r.classifications; out[5] = r.maxStages; out[6] = r.classBook;
+    out[7] = r.type == 2 ? r.r2channels : r.channels;
+    for (int c = 0; c < r.classifications && c < 64; c++) {
+        out[8 + c] = r.cascade[c];
+        for (size_t st = 0; st < r.books[c].size() && st < 8; st++) out[72 + c * 8 + st] = r.books[c][st];
+    }
+    return 0;
+}
+// out[0..3] = couplingSteps, submaps, submapFloor[0], submapResidue[0]; magnitude[256]; angle[256]
+int orc_mapping_info(void* hh, int mi, int32_t* out) {
+    Decoder& d = ((OrcHandle*)hh)->dec; if (mi < 0 || mi >= (int)d.mappings.size()) return -1;
+    const Mapping& m = d.mappings[mi];
+    std::memset(out, 0, sizeof(int32_t) * 516);
+    out[0] = (int)m.couplingAngle.size(); out[1] = (int)m.submapFloor.size(); out[2] = m.submapFloor[0]; out[3] = m.submapResidue[0];
+    for (size_t k = 0; k < m.couplingAngle.size() && k < 256; k++) { out[4 + k] = m.couplingMagnitude[k]; out[260 + k] = m.couplingAngle[k]; }
+    return 0;
+}
+int orc_mode_info(void* hh, int mi, int32_t* out) {   // blockFlag, mapping, blockSize
+    Decoder& d = ((OrcHandle*)hh)->dec; if (mi < 0 || mi >= (int)d.modes.size()) return -1;
+    out[0] = d.modes[mi].blockFlag ? 1 : 0; out[1] = d.modes[mi].mapping; out[2] = d.modes[mi].blockSize;
+    return 0;
+}
 
 // info[0..7] = channels, sampleRate, block0, block1, nPackets(total incl. headers), nModes, nBooks, modeFieldBits
 void orc_info(void* hh, int64_t* info) {

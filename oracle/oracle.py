@@ -53,6 +53,13 @@ def lib():
         L.orc_open.restype = C.c_void_p
         L.orc_open.argtypes = [C.c_char_p, C.c_size_t]
         L.orc_close.argtypes = [C.c_void_p]
+        L.orc_open_packets.restype = C.c_void_p
+        L.orc_open_packets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_counts.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_floor_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_residue_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_mapping_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_mode_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_info.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_read_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -114,13 +121,45 @@ class Boundary:
     block: list = field(default_factory=list)      # per frame [ch, N]
 
 
+@dataclass
+class PacketList:
+    """Demuxed packets of one logical stream (what an IPacketProvider hands out, Contracts/IPacketProvider.cs):
+    data = all packet bytes back to back; flags bit0 = has granule, bit1 = end of stream, bit2 = resync."""
+    data: np.ndarray       # uint8
+    sizes: np.ndarray      # int64
+    granules: np.ndarray   # int64
+    flags: np.ndarray      # uint8
+
+    @staticmethod
+    def from_packets(pk):
+        data = np.frombuffer(b"".join(p[0] for p in pk), dtype=np.uint8).copy() if pk else np.zeros(0, np.uint8)
+        if data.size == 0:
+            data = np.zeros(1, np.uint8)
+        return PacketList(data, np.array([len(p[0]) for p in pk], np.int64), np.array([p[2] for p in pk], np.int64),
+                          np.array([(1 if p[1] else 0) | (2 if p[3] else 0) | (4 if p[4] else 0) for p in pk], np.uint8))
+
+    def save(self, path):
+        np.savez_compressed(path, data=self.data, sizes=self.sizes, granules=self.granules, flags=self.flags)
+
+    @staticmethod
+    def load(path):
+        z = np.load(path)
+        return PacketList(np.ascontiguousarray(z["data"]), np.ascontiguousarray(z["sizes"]), np.ascontiguousarray(z["granules"]),
+                          np.ascontiguousarray(z["flags"]))
+
+
 class OracleReader:
     """Mirror of NVorbis.VorbisReader restricted to what TestApp/Program.cs uses."""
 
-    def __init__(self, data: bytes, clip: bool = True, record: bool = False, record_dense: bool = False):
+    def __init__(self, data, clip: bool = True, record: bool = False, record_dense: bool = False):
+        """data: the bytes of an Ogg file, or a PacketList (already-demuxed packets)."""
         L = lib()
-        self._data = bytes(data)
-        self._h = L.orc_open(self._data, len(self._data))
+        if isinstance(data, PacketList):
+            self._data = data
+            self._h = L.orc_open_packets(_ptr(data.data), _ptr(data.sizes), _ptr(data.granules), _ptr(data.flags), len(data.sizes))
+        else:
+            self._data = bytes(data)
+            self._h = L.orc_open(self._data, len(self._data))
         if not self._h:
             raise OracleError(L.orc_last_error().decode())
         info = np.zeros(8, dtype=np.int64)
@@ -188,6 +227,40 @@ class OracleReader:
         if lengths.size:
             lib().orc_book_lengths(self._h, b, _ptr(lengths))
         return dict(dims=int(info[0]), entries=int(info[1]), map_type=int(info[2]), table=table, lengths=lengths)
+
+    def counts(self):
+        out = np.zeros(4, np.int64)
+        lib().orc_counts(self._h, _ptr(out))
+        return dict(floors=int(out[0]), residues=int(out[1]), mappings=int(out[2]), modes=int(out[3]))
+
+    def floor(self, i: int):
+        o = np.zeros(260, np.int32)
+        if lib().orc_floor_info(self._h, i, _ptr(o)) != 0:
+            raise IndexError(i)
+        n = int(o[1])
+        return dict(type=int(o[0]), n_posts=n, multiplier=int(o[2]), range=int(o[3]), x_list=o[4:4 + n].copy(), l_neigh=o[68:68 + n].copy(),
+                    h_neigh=o[132:132 + n].copy(), sort_idx=o[196:196 + n].copy())
+
+    def residue(self, i: int):
+        o = np.zeros(8 + 64 + 512, np.int32)
+        if lib().orc_residue_info(self._h, i, _ptr(o)) != 0:
+            raise IndexError(i)
+        nc = int(o[4])
+        return dict(type=int(o[0]), begin=int(o[1]), end=int(o[2]), partition_size=int(o[3]), classifications=nc, max_stages=int(o[5]),
+                    class_book=int(o[6]), channels=int(o[7]), cascade=o[8:8 + nc].copy(), books=o[72:72 + 512].reshape(64, 8)[:nc].copy())
+
+    def mapping(self, i: int):
+        o = np.zeros(516, np.int32)
+        if lib().orc_mapping_info(self._h, i, _ptr(o)) != 0:
+            raise IndexError(i)
+        n = int(o[0])
+        return dict(n_coupling=n, n_submaps=int(o[1]), floor=int(o[2]), residue=int(o[3]), magnitude=o[4:4 + n].copy(), angle=o[260:260 + n].copy())
+
+    def mode(self, i: int):
+        o = np.zeros(3, np.int32)
+        if lib().orc_mode_info(self._h, i, _ptr(o)) != 0:
+            raise IndexError(i)
+        return dict(block_flag=int(o[0]), mapping=int(o[1]), block_size=int(o[2]))
 
     def mode_window(self, m: int, w: int) -> np.ndarray:
         n = lib().orc_mode_window(self._h, m, w, None)

@@ -1,0 +1,115 @@
+// cuda_emul.h -- TEST INFRASTRUCTURE ONLY.  A minimal CUDA-on-CPU emulation so that the product's
+// real kernel and C-ABI sources (nvorbis_b200/csrc/*.cu) can be compiled with g++ and single-stepped
+// in the GPU-less build container: one OS thread per CUDA thread, std::barrier for __syncthreads /
+// __syncwarp, shared memory as static storage, CTAs of a launch run one after the other.
+// Nothing in nvorbis_b200/ includes or loads this; the product fails loudly without a GPU.
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define NVB_CPU_SHIM 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define __restrict__
+
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#define NVB_HAVE_FLOAT2 1
+
+namespace cuemu {
+struct Idx { unsigned x = 0, y = 0, z = 0; };
+struct Launch {
+    int nthreads = 0;
+    std::unique_ptr<std::barrier<>> cta;
+    std::vector<std::unique_ptr<std::barrier<>>> warp;
+    std::vector<uint32_t> shfl;           // 32 words per warp
+    std::atomic<int> or_acc{0};
+};
+extern Launch* g_launch;
+extern unsigned char g_dyn_smem[];
+}
+extern thread_local cuemu::Idx threadIdx, blockIdx;
+extern cuemu::Idx blockDim, gridDim;
+
+static inline void __syncthreads() { cuemu::g_launch->cta->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::g_launch->warp[threadIdx.x >> 5]->arrive_and_wait(); }
+static inline int __syncthreads_or(int pred) {
+    cuemu::Launch* L = cuemu::g_launch;
+    if (pred) L->or_acc.fetch_or(1);
+    L->cta->arrive_and_wait();
+    int r = L->or_acc.load();
+    L->cta->arrive_and_wait();
+    if (threadIdx.x == 0) L->or_acc.store(0);
+    L->cta->arrive_and_wait();
+    return r;
+}
+template <class T> static inline T cuemu_shfl(T v, int src_lane_delta, bool is_xor) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    cuemu::Launch* L = cuemu::g_launch;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t bits; std::memcpy(&bits, &v, 4);
+    L->shfl[w * 32 + lane] = bits;
+    L->warp[w]->arrive_and_wait();
+    int src = is_xor ? (lane ^ src_lane_delta) : (lane - src_lane_delta);
+    uint32_t rb = (src >= 0 && src < 32) ? L->shfl[w * 32 + src] : bits;
+    L->warp[w]->arrive_and_wait();
+    T r; std::memcpy(&r, &rb, 4); return r;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return cuemu_shfl(v, m, true); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return cuemu_shfl(v, d, false); }
+static inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+
+// ---- the few runtime calls nvb_api.cu makes -------------------------------------------------------
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcessorCount = 16 };
+struct cudaDeviceProp { int major = 10, minor = 0; };
+static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { const char* e = std::getenv("NVB_SHIM_SMS"); *v = e ? std::atoi(e) : 4; return cudaSuccess; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::aligned_alloc(256, (n + 255) & ~size_t(255)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, int) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < h; r++) std::memcpy((char*)d + r * dp, (const char*)s + r * sp, w);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+
+namespace cuemu {
+void run(int grid, int block, size_t smem, const std::function<void()>& body);
+template <class K, class A> void launch(K kernel, int grid, int block, size_t smem, A arg) { run(grid, block, smem, [=]() { kernel(arg); }); }
+}
+#define NVB_LAUNCH(kernel, grid, block, smem, stream, arg) cuemu::launch(kernel, (int)(grid), (int)(block), (size_t)(smem), arg)
+#define NVB_DYN_SMEM(name) unsigned char* name = cuemu::g_dyn_smem

@@ -1,0 +1,79 @@
+"""Shared test helpers: fixtures, oracle -> C-ABI marshalling.  Test infrastructure only."""
+from __future__ import annotations
+
+import functools
+import os
+import subprocess
+
+import numpy as np
+
+from nvorbis_b200 import capi
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+FIXTURES = ["1test", "2test", "3test", "issue6test"]
+SHIM_DIR = os.path.join(ROOT, "tests", "cpu_shim")
+SHIM_LIB = os.path.join(SHIM_DIR, "libnvb_cpu_shim.so")
+
+
+def packets(name: str) -> O.PacketList:
+    return O.PacketList.load(os.path.join(GOLDEN, name + ".packets.npz"))
+
+
+@functools.lru_cache(maxsize=None)
+def decoded(name: str, dense: bool = False):
+    """(reader, pcm, boundary) of a fixture decoded by the oracle with boundary recording on."""
+    r = O.OracleReader(packets(name), record=True, record_dense=dense)
+    pcm = r.read_all()
+    return r, pcm, r.boundary()
+
+
+def build_shim() -> str:
+    subprocess.check_call(["make", "-C", SHIM_DIR, "-s"])
+    return SHIM_LIB
+
+
+def setup_from_oracle(r: O.OracleReader, **kw) -> capi.Setup:
+    """nvb_setup from the oracle's parsed headers (the tables StreamDecoder.LoadBooks leaves behind)."""
+    cnt = r.counts()
+    books = []
+    for b in range(r.n_books):
+        bk = r.book(b)
+        books.append(dict(dims=bk["dims"], entries=bk["entries"], map_type=bk["map_type"], table=bk["table"]))
+    floors = [r.floor(i) for i in range(cnt["floors"])]
+    residues = [r.residue(i) for i in range(cnt["residues"])]
+    mappings = [r.mapping(i) for i in range(cnt["mappings"])]
+    modes = [r.mode(i) for i in range(cnt["modes"])]
+    return capi.Setup(r.channels, r.sample_rate, (r.block0, r.block1), books, floors, residues, mappings, modes, **kw)
+
+
+def batch_from_boundary(b: O.Boundary, post_stride: int, lo: int = 0, hi: int | None = None) -> capi.HostBatch:
+    """nvb_batch arrays for boundary records [lo, hi)."""
+    hi = len(b.frames) if hi is None else hi
+    n, ch = hi - lo, b.channels
+    fr = np.zeros(n, capi.FRAME_DTYPE)
+    src = b.frames[lo:hi]
+    fr["status"] = np.where(src["ok"] != 0, capi.FRAME_OK, capi.FRAME_FAILED)
+    fr["mode"] = src["mode"]; fr["window"] = src["windowIndex"]; fr["res_decoded"] = src["resDecoded"]
+    fr["exec_mask"] = src["execMask"]; fr["start"] = src["start"]; fr["valid"] = src["valid"]; fr["total"] = src["total"]
+    c0 = int(src["classesOff"][0]) if n else 0
+    e0 = int(src["entriesOff"][0]) if n else 0
+    c1 = int(b.frames["classesOff"][hi]) if hi < len(b.frames) else b.classes.size
+    e1 = int(b.frames["entriesOff"][hi]) if hi < len(b.frames) else b.entries.size
+    fr["classes_off"] = src["classesOff"] - c0; fr["entries_off"] = src["entriesOff"] - e0; fr["entry_count"] = src["entryCount"]
+    posts = np.zeros((n, ch, post_stride), np.int16)
+    p64 = b.posts.reshape(-1, ch, 64)[lo:hi]
+    posts[:, :, 0] = b.post_counts.reshape(-1, ch)[lo:hi]
+    k = min(64, post_stride - 1)
+    posts[:, :, 1:1 + k] = p64[:, :, :k]
+    assert b.entries.size == 0 or b.entries.max() < 65536
+    return capi.HostBatch(fr, posts.reshape(-1), b.classes[c0:c1], b.entries[e0:e1].astype(np.uint16))
+
+
+def oracle_synth(r: O.OracleReader, b: O.Boundary, lo: int = 0, hi: int | None = None, threads: int = 1):
+    """Oracle synthesis of boundary records [lo, hi) from a fresh decoder state."""
+    hi = len(b.frames) if hi is None else hi
+    fr = b.frames[lo:hi].copy()
+    cap = int(fr["total"].astype(np.int64).sum()) + 8192
+    return r.synth_batch(fr, b.posts, b.post_counts, b.classes, b.entries, cap, threads=threads)
