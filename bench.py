@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- audio frames/s of the Vorbis synthesis path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: BASELINE configs[1] = 4096 stereo long-block
+(N=2048) frames per GPU, inputs = the compact boundary records (nvb_frame + posts + classes + entries)
+already resident in HBM, output = interleaved float PCM in HBM.  One process per GPU; the table blob is
+broadcast once over NCCL, the batch shards need no data-path collective (weak scaling).
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio frames/sec (blocksize 2048, stereo)"
+FRAMES_PER_STEP = 4096
+ROTATE = 5                      # batch sets rotated through so that the working set (~70 MB each) exceeds the 126 MB L2
+SEED = 20240002
+POOL = os.path.join(ROOT, "tests", "golden", "3test.boundary.npz")
+PACKETS = os.path.join(ROOT, "tests", "golden", "3test.packets.npz")
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "BASELINE configs[1]: stereo 44.1 kHz long-block N=2048, 4096-frame batch per GPU "
+                        "(long/long frames of the 3test stream drawn with replacement, PCG64 seeds 20240002+)",
+            "frames_per_step_per_gpu": FRAMES_PER_STEP, "channels": 2, "block_size": 2048,
+            "l2_policy": f"{ROTATE} rotating batch sets (inputs + spectrum scratch + PCM, ~70 MB each) > 126 MB L2",
+            "sharding": f"{n_gpus} independent shards, one NCCL broadcast of the table blob, no data-path collective"}
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) >= 8:
+                self.rows.append(p)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = []
+        for j, name in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")):
+            if any(r[j].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, read+write)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def oracle_inputs(hb):
+    """HostBatch (C-ABI layout) -> the oracle's SynthFrame arrays.  cpu_baseline / --impl reference only."""
+    from oracle import oracle as O
+    n = len(hb.frames)
+    fr = np.zeros(n, O.SYNTH_FRAME_DTYPE)
+    f = hb.frames
+    ch = 2
+    stride = hb.posts.size // (n * ch)
+    fr["ok"] = f["status"] == 0; fr["mode"] = f["mode"]; fr["windowIndex"] = f["window"]
+    fr["start"] = f["start"]; fr["valid"] = f["valid"]; fr["total"] = f["total"]; fr["execMask"] = f["exec_mask"]
+    fr["resDecoded"] = f["res_decoded"]; fr["resStreams"] = 1
+    nxt = np.concatenate([f["classes_off"][1:], [hb.classes.size]]).astype(np.int64)
+    fr["resPartitions"] = nxt - f["classes_off"]
+    fr["postsOff"] = np.arange(n, dtype=np.int64) * ch * 64; fr["postCountOff"] = np.arange(n, dtype=np.int64) * ch
+    fr["classesOff"] = f["classes_off"]; fr["entriesOff"] = f["entries_off"]; fr["entryCount"] = f["entry_count"]
+    p = hb.posts.reshape(n, ch, stride)
+    posts = np.zeros((n, ch, 64), np.int32)
+    posts[:, :, :stride - 1] = p[:, :, 1:]
+    return fr, posts.reshape(-1), p[:, :, 0].astype(np.int32).reshape(-1), hb.classes, hb.entries.astype(np.int32)
+
+
+def cpu_reference_rate(hb, threads: int, min_seconds: float, max_reps: int = 50):
+    """frames/s of the CPU oracle (the C++ restatement of the reference's managed path) on the same batch."""
+    from oracle import oracle as O
+    r = O.OracleReader(O.PacketList.load(PACKETS))
+    fr, posts, pc, cls, ent = oracle_inputs(hb)
+    cap = int(hb.frames["total"].astype(np.int64).sum()) + 8192
+    r.synth_batch(fr[:256], posts, pc, cls, ent, cap, threads=min(threads, 8))       # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        r.synth_batch(fr, posts, pc, cls, ent, cap, threads=threads)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or reps >= max_reps:
+            break
+    return len(fr) * reps / dt, reps, dt
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is managed C#
+    and no .NET runtime exists in this image, so this times the oracle (its C++ restatement, kind "port")
+    with every host thread, on the same batch the GPU arm decodes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from nvorbis_b200 import setupio, workloads
+    desc, z = setupio.load(POOL)
+    pool = workloads.FramePool.from_npz(desc, z)
+    hb = workloads.config2(pool, FRAMES_PER_STEP, SEED)
+    from oracle import oracle as O
+    r = O.OracleReader(O.PacketList.load(PACKETS))
+    fr, posts, pc, cls, ent = oracle_inputs(hb)
+    cap = int(hb.frames["total"].astype(np.int64).sum()) + 8192
+    threads = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 1)):
+        r.synth_batch(fr, posts, pc, cls, ent, cap, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.synth_batch(fr, posts, pc, cls, ent, cap, threads=threads)
+    dt = time.perf_counter() - t0
+    value = FRAMES_PER_STEP * args.steps / dt
+    sample = f"{args.steps} x {FRAMES_PER_STEP} frames (the whole step), oracle synthesis from boundary records, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (real 3test frames re-sampled)", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is managed C# (no dotnet/mono in the image): timed its scalar C++ restatement (oracle/), which is expected to be faster than the managed code",
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nvorbis_b200 import capi, setupio, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the synthesis path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    desc, z = setupio.load(POOL)
+    pool = workloads.FramePool.from_npz(desc, z)
+    ctx = capi.Context(local)
+    # one rank parses the headers and uploads; every other rank receives the table blob in ONE broadcast
+    if rank == 0:
+        ctx.upload_setup(setupio.to_setup(desc))
+        blob = ctx.export_blob()
+    if world > 1:
+        n = torch.tensor([len(blob) if rank == 0 else 0], device=dev, dtype=torch.int64)
+        dist.broadcast(n, 0)
+        t = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.from_numpy(blob))
+        dist.broadcast(t, 0)
+        if rank != 0:
+            ctx.import_blob(t.cpu().numpy())
+    C = ctx.channels
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- batches: ROTATE distinct sets per rank, host arrays in pinned memory -------------------------
+    def pinned(a: np.ndarray) -> np.ndarray:
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8).pin_memory()
+        v = t.numpy()[: a.nbytes].view(a.dtype).reshape(a.shape)
+        v[...] = a
+        keep.append(t)
+        return v
+
+    keep, host_batches, dbatches, pcm_bufs, spec_bufs = [], [], [], [], []
+    for s in range(ROTATE):
+        hb = workloads.config2(pool, FRAMES_PER_STEP, SEED + 1000 * rank + s)
+        hb = capi.HostBatch(pinned(hb.frames), pinned(hb.posts), pinned(hb.classes), pinned(hb.entries))
+        host_batches.append(hb)
+        db = ctx.create_dbatch(hb)
+        dbatches.append(db)
+        pcm_bufs.append(torch.empty(db.samples * C + 16, dtype=torch.float32, device=dev))
+        spec_bufs.append(torch.empty(db.spectrum_floats + 16, dtype=torch.float32, device=dev))
+    samples = dbatches[0].samples
+    out_host = torch.empty(samples * C + 16, dtype=torch.float32).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        sync_all()
+        return max_over_ranks(ms)
+
+    # ---- device-resident throughput: boundary records in HBM -> PCM in HBM (spectrum + fused kernels) --
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(lambda i: dbatches[i % ROTATE].run(pcm_bufs[i % ROTATE].data_ptr(), stream), args.steps, args.warmup)
+    launches_per_step = dbatches[0].launches
+    res = dbatches[0].result(stream)
+
+    # ---- the roofline kernel alone: fused IMDCT + window + OLA + clip + interleave, dense spectrum in ----
+    for s in range(ROTATE):
+        dbatches[s].run_spectrum(spec_bufs[s].data_ptr(), stream)
+    ms_imdct = timed(lambda i: dbatches[i % ROTATE].run_imdct(spec_bufs[i % ROTATE].data_ptr(), pcm_bufs[i % ROTATE].data_ptr(), stream),
+                     args.steps, args.warmup)
+    ms_spec = timed(lambda i: dbatches[i % ROTATE].run_spectrum(spec_bufs[i % ROTATE].data_ptr(), stream), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the host-buffer C-ABI call: pinned inputs -> H2D -> kernels -> D2H of PCM ----
+    for i in range(args.warmup):
+        ctx.decode_batch_ptr(host_batches[i % ROTATE], capi.RUN_DEFAULT, out_host.data_ptr(), out_host.numel())
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ctx.decode_batch_ptr(host_batches[i % ROTATE], capi.RUN_DEFAULT, out_host.data_ptr(), out_host.numel())
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    sync_all()
+
+    if rank == 0:
+        frames_total = FRAMES_PER_STEP * world * args.steps
+        ms_step = ms_total / args.steps
+        value = frames_total / (ms_total * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        # algorithmic bytes of the fused kernel per launch: every spectrum float read once, every PCM float written once
+        alg_bytes = int(dbatches[0].spectrum_floats * 4 + samples * C * 4)
+        imdct_ms = ms_imdct / args.steps
+        achieved = alg_bytes / (imdct_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                traffic = json.load(f).get("k_imdct_fused_dram_bytes_per_launch")
+        except Exception:
+            pass
+        threads = os.cpu_count() or 1
+        cpu_val, reps, cpu_dt = cpu_reference_rate(host_batches[0], threads, 3.0)
+        cpu1_val, reps1, cpu1_dt = cpu_reference_rate(host_batches[0], 1, 2.0, max_reps=8)
+        out = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (real 3test frames re-sampled)", "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(host_batches[0].h2d_bytes),
+                    "d2h_bytes_per_step": int(samples * C * 4), "ms_per_step": e2e_ms / args.steps,
+                    "api": "nvb_decode_batch (host buffers, pinned), per GPU"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "kernels": {"k_spectrum_ms": ms_spec / args.steps, "k_imdct_fused_ms": imdct_ms, "step_ms": ms_step},
+            "roofline": {"bound": "hbm", "kernel": "k_imdct_fused", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "frames_per_s_kernel_only": FRAMES_PER_STEP / (imdct_ms * 1e-3)},
+            "cpu_baseline": {"value": cpu_val, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": f"{reps} x {FRAMES_PER_STEP} frames of this workload in {cpu_dt:.1f} s, oracle synthesis (C++ restatement of the managed path), {threads} threads",
+                             "single_thread_value": cpu1_val},
+            "result_check": {"samples_per_channel": res.samples_per_channel, "has_clipped": res.has_clipped},
+        }
+        print(json.dumps(out))
+    for db in dbatches:
+        db.destroy()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

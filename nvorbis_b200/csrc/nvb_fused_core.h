@@ -8,7 +8,7 @@
 //   c[k] = (X[2k] + i X[M-1-2k]) * tw[k],   tw[k] = exp(-i pi (k + 1/8) / M)
 //   Cf   = FFT_Q(c);   D[n] = Cf[n] * tw[n];   u[2n] = Re D[n],  u[M-1-2n] = -Im D[n]
 //   y[i] = u[i+M/2] (i < M/2);  -u[3M/2-1-i] (M/2 <= i < 3M/2);  -u[i-3M/2] (i >= 3M/2)
-// This path may contract to FMA; it is held to <= 1e-5 max-abs against the oracle (the exact
+// This path may contract to FMA; it is held to <= 1e-5 max-abs against the reference arithmetic (the exact
 // path in nvb_kernels.cu is the bit-identical one).
 #pragma once
 #include "nvb_device_core.h"

@@ -71,6 +71,20 @@ def main():
             "survey_probe": SURVEY_PROBE.get(name),
         }
         print(name, json.dumps({k: v for k, v in golden[name].items() if k not in ("spots", "survey_probe")}))
+        if name == "3test":
+            # bench.py's frame pool (BASELINE configs 2/3/5 re-sample real frames of this stream):
+            # the parsed setup and the boundary records in C-ABI layout.  bench.py must not call the oracle on
+            # its product path, so these are stored rather than recomputed.
+            sys.path.insert(0, os.path.join(HERE, ".."))
+            import helpers as H
+            from nvorbis_b200 import setupio
+            desc = H.desc_from_oracle(r)
+            stride = (2 + max(f["n_posts"] for f in desc["floors"]) + 1) & ~1
+            hb = H.batch_from_boundary(b, stride)
+            class_len = np.where(b.frames["resDecoded"] != 0, b.frames["resStreams"].astype(np.int64) * b.frames["resPartitions"], 0)
+            setupio.save(os.path.join(HERE, name + ".boundary.npz"), desc, pool_frames=hb.frames.view(np.uint8), pool_posts=hb.posts,
+                         pool_classes=hb.classes, pool_entries=hb.entries, pool_class_len=class_len,
+                         pool_long=(b.block_size == r.block1))
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(golden, f, indent=1, sort_keys=True)
 

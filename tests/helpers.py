@@ -34,6 +34,18 @@ def build_shim() -> str:
     return SHIM_LIB
 
 
+def desc_from_oracle(r: O.OracleReader) -> dict:
+    """Setup description (nvorbis_b200.setupio format) from the oracle's parsed headers."""
+    cnt = r.counts()
+    books = []
+    for b in range(r.n_books):
+        bk = r.book(b)
+        books.append(dict(dims=bk["dims"], entries=bk["entries"], map_type=bk["map_type"], table=bk["table"] if bk["table"].size else None))
+    return dict(channels=r.channels, sample_rate=r.sample_rate, block_size=(r.block0, r.block1), books=books,
+                floors=[r.floor(i) for i in range(cnt["floors"])], residues=[r.residue(i) for i in range(cnt["residues"])],
+                mappings=[r.mapping(i) for i in range(cnt["mappings"])], modes=[r.mode(i) for i in range(cnt["modes"])])
+
+
 def setup_from_oracle(r: O.OracleReader, **kw) -> capi.Setup:
     """nvb_setup from the oracle's parsed headers (the tables StreamDecoder.LoadBooks leaves behind)."""
     cnt = r.counts()

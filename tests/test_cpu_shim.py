@@ -1,0 +1,152 @@
+"""The product's real kernel and C-ABI sources, compiled against tests/cpu_shim's CUDA-on-CPU emulation
+(one OS thread per CUDA thread) and compared with the oracle.  This is how the kernels are debugged in the
+GPU-less build container; the GPU parity tests proper are in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import helpers as H
+from nvorbis_b200 import capi
+
+
+@pytest.fixture(scope="module")
+def shim():
+    return H.build_shim()
+
+
+def _ctx(shim, name):
+    r, pcm, b = H.decoded(name)
+    ctx = capi.Context(0, lib_path=shim)
+    ctx.upload_setup(H.setup_from_oracle(r))
+    return r, pcm, b, ctx
+
+
+def test_mono_full_stream_exact_and_fused(shim):
+    r, pcm, b, ctx = _ctx(shim, "1test")
+    hb = H.batch_from_boundary(b, ctx.post_stride)
+    out, res = ctx.decode_batch(hb, capi.RUN_EXACT)
+    np.testing.assert_array_equal(out, pcm)                     # stb dataflow, no FMA: bit-identical
+    assert res.samples_per_channel == pcm.size and not res.has_clipped and res.n_failed == 0
+    ctx.reset()
+    out, res = ctx.decode_batch(hb, capi.RUN_DEFAULT)
+    assert out.size == pcm.size and np.abs(out - pcm).max() <= 1e-5
+
+
+def test_stereo_coupled_residue2_with_clipping(shim):
+    r, pcm, b, ctx = _ctx(shim, "3test")
+    lo, hi = 0, 70
+    want, clipped = H.oracle_synth(r, b, lo, hi)
+    hb = H.batch_from_boundary(b, ctx.post_stride, lo, hi)
+    out, res = ctx.decode_batch(hb, capi.RUN_EXACT)
+    np.testing.assert_array_equal(out, want)
+    ctx.reset()
+    out, res = ctx.decode_batch(hb, capi.RUN_DEFAULT)
+    assert out.size == want.size and np.abs(out - want).max() <= 1e-5
+    # a stretch that clips (the oracle reports HasClipped for the full stream)
+    idx = int(np.argmax(np.abs(H.decoded("3test")[1]))) // 2
+    # find the frame run containing the loudest sample: decode frames [a, a+12)
+    lens = np.maximum(b.frames["valid"] - b.frames["start"], 0); lens[0] = 0
+    a = max(int(np.searchsorted(np.cumsum(lens), idx)) - 6, 1)
+    want, clipped = H.oracle_synth(r, b, a, a + 12)
+    assert clipped
+    ctx.reset()
+    out, res = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, a, a + 12), capi.RUN_DEFAULT)
+    assert res.has_clipped and np.abs(out - want).max() <= 1e-5 and np.abs(out).max() <= 0.99999994
+
+
+def test_chained_batches_carry_the_tail(shim):
+    r, pcm, b, ctx = _ctx(shim, "1test")
+    n = len(b.frames)
+    for flags in (capi.RUN_EXACT, capi.RUN_DEFAULT):
+        ctx.reset()
+        parts, pos = [], 0
+        for cut in (3, 4, 11, n):                      # includes a one-frame batch
+            out, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, pos, cut), flags | (capi.RUN_CONTINUE if pos else 0))
+            parts.append(out.copy()); pos = cut
+        got = np.concatenate(parts)
+        if flags == capi.RUN_EXACT:
+            np.testing.assert_array_equal(got, pcm)
+        else:
+            assert got.size == pcm.size and np.abs(got - pcm).max() <= 1e-5
+
+
+def test_failed_packets_drain_the_tail(shim):
+    r, pcm, b, ctx = _ctx(shim, "1test")
+    fr = b.frames.copy()
+    fr["ok"][5] = 0; fr["ok"][6] = 0; fr["ok"][12] = 0
+    b2 = H.O.Boundary(b.channels, fr, b.block_size, b.valid_untrimmed, b.no_exec_mask, b.posts, b.post_counts, b.classes, b.entries)
+    want, _ = H.oracle_synth(r, b2)
+    for flags in (capi.RUN_EXACT, capi.RUN_DEFAULT):
+        ctx.reset()
+        out, res = ctx.decode_batch(H.batch_from_boundary(b2, ctx.post_stride), flags)
+        assert res.n_failed == 3 and out.size == want.size
+        if flags == capi.RUN_EXACT:
+            np.testing.assert_array_equal(out, want)
+        else:
+            assert np.abs(out - want).max() <= 1e-5
+    # drain at the start of a chained batch: the tail comes from the carried block
+    ctx.reset()
+    a, _ = ctx.decode_batch(H.batch_from_boundary(b2, ctx.post_stride, 0, 5), capi.RUN_DEFAULT)
+    c, _ = ctx.decode_batch(H.batch_from_boundary(b2, ctx.post_stride, 5, len(fr)), capi.RUN_DEFAULT | capi.RUN_CONTINUE)
+    got = np.concatenate([a, c])
+    assert got.size == want.size and np.abs(got - want).max() <= 1e-5
+
+
+def test_blob_roundtrip_and_errors(shim):
+    r, pcm, b, ctx = _ctx(shim, "1test")
+    blob = ctx.export_blob()
+    ctx2 = capi.Context(0, lib_path=shim)
+    ctx2.import_blob(blob)
+    hb = H.batch_from_boundary(b, ctx.post_stride)
+    out, _ = ctx2.decode_batch(hb, capi.RUN_EXACT)
+    np.testing.assert_array_equal(out, pcm)
+    bad = blob.copy(); bad[0] ^= 0xFF
+    with pytest.raises(capi.NvbError) as e:
+        ctx2.import_blob(bad)
+    assert e.value.status == capi.ERR_DATA
+    # malformed batches are rejected up front with NVB_ERR_DATA (InvalidDataException in the reference)
+    fr = hb.frames.copy(); fr["mode"][3] = 9
+    with pytest.raises(capi.NvbError) as e:
+        ctx.decode_batch(capi.HostBatch(fr, hb.posts, hb.classes, hb.entries))
+    assert e.value.status == capi.ERR_DATA
+    fr = hb.frames.copy(); fr["entries_off"][4] = 1 << 30
+    with pytest.raises(capi.NvbError) as e:
+        ctx.decode_batch(capi.HostBatch(fr, hb.posts, hb.classes, hb.entries))
+    assert e.value.status == capi.ERR_DATA
+    with pytest.raises(capi.NvbError) as e:
+        ctx.decode_batch(hb, out=np.zeros(16, np.float32))
+    assert e.value.status == capi.ERR_CAPACITY
+    # setups outside the envelope
+    desc = H.desc_from_oracle(r)
+    from nvorbis_b200 import setupio
+    d2 = dict(desc); d2["mappings"] = [dict(m, n_submaps=2) for m in desc["mappings"]]
+    with pytest.raises(capi.NvbError) as e:
+        ctx2.upload_setup(setupio.to_setup(d2))
+    assert e.value.status == capi.ERR_UNSUPPORTED
+    d3 = dict(desc); d3["floors"] = [dict(f, type=0) for f in desc["floors"]]
+    with pytest.raises(capi.NvbError) as e:
+        ctx2.upload_setup(setupio.to_setup(d3))
+    assert e.value.status == capi.ERR_UNSUPPORTED
+
+
+def test_setup_tables_match_oracle(shim):
+    """Windows and MDCT twiddles the library derives itself equal the oracle's (same float/double expression order)."""
+    r, pcm, b, ctx = _ctx(shim, "3test")
+    blob = ctx.export_blob()
+    hdr_off = {}
+    import struct
+    # BlobHeader: magic, abi, total(8), channels, rate, bs0, bs1, 5 counts, post_stride, max_items, pad, then u64 offsets
+    vals = struct.unpack_from("<II Q 4i 5i 3i", blob, 0)
+    offs = struct.unpack_from("<6Q 2Q 8Q 2Q 2Q Q Q", blob, 16 + 16 + 20 + 12)
+    off_win_short, off_win_long = offs[6], offs[7]
+    a0, a1, b0, b1, c0, c1, br0, br1 = offs[8:16]
+    ws = np.frombuffer(blob, np.float32, r.block0, off_win_short)
+    np.testing.assert_array_equal(ws, r.mode_window(0, 0))
+    for w in range(4):
+        wl = np.frombuffer(blob, np.float32, r.block1, off_win_long + 4 * w * r.block1)
+        np.testing.assert_array_equal(wl, r.mode_window(1, w))
+    for n, (oa, ob, oc, obr) in ((r.block0, (a0, b0, c0, br0)), (r.block1, (a1, b1, c1, br1))):
+        A, B, Cc, BR = H.O.mdct_tables(n)
+        np.testing.assert_array_equal(np.frombuffer(blob, np.float32, n // 2, oa), A)
+        np.testing.assert_array_equal(np.frombuffer(blob, np.float32, n // 2, ob), B)
+        np.testing.assert_array_equal(np.frombuffer(blob, np.float32, n // 4, oc), Cc)
+        np.testing.assert_array_equal(np.frombuffer(blob, np.uint16, n // 8, obr), BR)

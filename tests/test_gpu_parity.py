@@ -1,0 +1,192 @@
+"""Parity of the CUDA synthesis path (through the C ABI of libnvorbis_b200.so) with the CPU oracle.
+
+Bar: bit-identical for the exact path (stb dataflow, no FMA contraction); max-abs <= 1e-5 (BASELINE.json
+north_star) for the fused fast path.  Run on a B200: python -m pytest tests -m gpu
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from nvorbis_b200 import capi, setupio, workloads
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5          # north_star: "output floats must match the reference C# path ... to within 1e-5 max-abs"
+
+
+def _ctx(name):
+    r, pcm, b = H.decoded(name)
+    ctx = capi.Context(0)
+    ctx.upload_setup(H.setup_from_oracle(r))
+    return r, pcm, b, ctx
+
+
+def test_library_is_the_real_one():
+    lib = capi.load_library()
+    assert os.path.samefile(lib._name, capi.DEFAULT_LIB)
+
+
+@pytest.mark.parametrize("name", H.FIXTURES)
+def test_fixture_streams(name, golden):
+    r, pcm, b, ctx = _ctx(name)
+    hb = H.batch_from_boundary(b, ctx.post_stride)
+    out, res = ctx.decode_batch(hb, capi.RUN_EXACT)
+    np.testing.assert_array_equal(out, pcm)
+    assert res.samples_per_channel == golden[name]["samples_per_channel"] and res.has_clipped == golden[name]["has_clipped"]
+    ctx.reset()
+    out, res = ctx.decode_batch(hb, capi.RUN_DEFAULT)
+    assert out.size == pcm.size
+    assert float(np.abs(out - pcm).max()) <= TOL
+    assert res.has_clipped == golden[name]["has_clipped"] and res.n_floor_range == 0 and res.n_inconsistent == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["1test", "3test"])
+def test_unclipped_output(name):
+    r, _, b = H.decoded(name)
+    want = H.O.OracleReader(H.packets(name), clip=False).read_all()
+    ctx = capi.Context(0); ctx.upload_setup(H.setup_from_oracle(r))
+    hb = H.batch_from_boundary(b, ctx.post_stride)
+    out, res = ctx.decode_batch(hb, capi.RUN_EXACT | capi.RUN_NO_CLIP)
+    np.testing.assert_array_equal(out, want)
+    ctx.reset()
+    out, res = ctx.decode_batch(hb, capi.RUN_NO_CLIP)
+    assert float(np.abs(out - want).max()) <= TOL and not res.has_clipped
+
+
+@pytest.mark.parametrize("flags", [capi.RUN_EXACT, capi.RUN_DEFAULT])
+def test_chained_batches(flags):
+    """Batches of ragged sizes chained with NVB_RUN_CONTINUE equal one big batch (the tail is carried on the device)."""
+    r, pcm, b, ctx = _ctx("3test")
+    n = len(b.frames)
+    cuts = [1, 2, 9, 10, 64, 65, 200, 333, n]
+    parts, pos = [], 0
+    for cut in cuts:
+        out, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, pos, cut), flags | (capi.RUN_CONTINUE if pos else 0))
+        parts.append(out.copy()); pos = cut
+    got = np.concatenate(parts)
+    assert got.size == pcm.size
+    if flags == capi.RUN_EXACT:
+        np.testing.assert_array_equal(got, pcm)
+    else:
+        assert float(np.abs(got - pcm).max()) <= TOL
+
+
+def test_empty_and_single_frame_batches():
+    r, pcm, b, ctx = _ctx("1test")
+    empty = capi.HostBatch(np.zeros(0, capi.FRAME_DTYPE), np.zeros(0, np.int16), np.zeros(0, np.uint8), np.zeros(0, np.uint16))
+    out, res = ctx.decode_batch(empty)
+    assert out.size == 0 and res.samples_per_channel == 0
+    out, res = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, 0, 1))
+    assert out.size == 0                                    # first block of a stream emits nothing (StreamDecoder.cs:446-450)
+
+
+@pytest.mark.parametrize("flags", [capi.RUN_EXACT, capi.RUN_DEFAULT])
+def test_failed_packets_drain(flags):
+    r, pcm, b, ctx = _ctx("3test")
+    fr = b.frames.copy()
+    for i in (0, 7, 8, 100, 101, 102, 250, len(fr) - 1):
+        fr["ok"][i] = 0
+    b2 = H.O.Boundary(b.channels, fr, b.block_size, b.valid_untrimmed, b.no_exec_mask, b.posts, b.post_counts, b.classes, b.entries)
+    want, _ = H.oracle_synth(r, b2)
+    out, res = ctx.decode_batch(H.batch_from_boundary(b2, ctx.post_stride), flags)
+    assert res.n_failed == 8 and out.size == want.size
+    if flags == capi.RUN_EXACT:
+        np.testing.assert_array_equal(out, want)
+    else:
+        assert float(np.abs(out - want).max()) <= TOL
+
+
+def test_spectrum_stage_matches_oracle():
+    """Residue dequant/scatter + inverse coupling + Floor1 curve (k_spectrum) against the oracle's IMDCT input."""
+    import torch
+    r, pcm, b = H.decoded("3test", dense=True)
+    ctx = capi.Context(0); ctx.upload_setup(H.setup_from_oracle(r))
+    hb = H.batch_from_boundary(b, ctx.post_stride)
+    db = ctx.create_dbatch(hb)
+    spec = torch.zeros(db.spectrum_floats, dtype=torch.float32, device="cuda")
+    db.run_spectrum(spec.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    db.result(torch.cuda.current_stream().cuda_stream)
+    got = spec.cpu().numpy()
+    off = 0
+    for i in range(len(b.frames)):
+        s = b.spectrum[i]
+        if s is None:
+            continue
+        np.testing.assert_array_equal(got[off:off + s.size].reshape(s.shape), s, err_msg=f"frame {i}")     # integer-indexed gathers + exact FP32: bit-identical
+        off += s.size
+    assert off == db.spectrum_floats
+    db.destroy()
+
+
+def _pool():
+    desc, z = setupio.load(os.path.join(H.GOLDEN, "3test.boundary.npz"))
+    return desc, workloads.FramePool.from_npz(desc, z)
+
+
+def _oracle_on_batch(hb):
+    import bench
+    r = H.O.OracleReader(H.packets("3test"))
+    fr, posts, pc, cls, ent = bench.oracle_inputs(hb)
+    cap = int(hb.frames["total"].astype(np.int64).sum()) + 8192
+    return r.synth_batch(fr, posts, pc, cls, ent, cap, threads=os.cpu_count() or 1)
+
+
+def test_config2_full_size():
+    """BASELINE configs[1] at full size: 4096 stereo long-block frames, device-resident API + host API."""
+    import torch
+    desc, pool = _pool()
+    hb = workloads.config2(pool, 4096, 20240002)
+    want, clipped = _oracle_on_batch(hb)
+    ctx = capi.Context(0); ctx.upload_setup(setupio.to_setup(desc))
+    out, res = ctx.decode_batch(hb)
+    assert out.size == want.size == 4095 * 1024 * 2
+    assert float(np.abs(out - want).max()) <= TOL and res.has_clipped == clipped
+    db = ctx.create_dbatch(hb)
+    pcm = torch.zeros(db.samples * 2, dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    db.run(pcm.data_ptr(), st)
+    r2 = db.result(st)
+    np.testing.assert_array_equal(pcm.cpu().numpy(), out)            # same kernels, same result
+    assert db.launches == 2 and r2.samples_per_channel == res.samples_per_channel
+    out_e, _ = ctx.decode_batch(hb, capi.RUN_EXACT)
+    np.testing.assert_array_equal(out_e, want)
+    db.destroy()
+
+
+def test_config3_mixed_windows_full_size():
+    """BASELINE configs[2]: 16k frames with short/long transitions (all window shapes)."""
+    desc, pool = _pool()
+    hb = workloads.config3(pool, 16384, 20240003)
+    assert {0, 1, 2, 3} <= set(np.unique(hb.frames["window"]).tolist())
+    want, clipped = _oracle_on_batch(hb)
+    ctx = capi.Context(0); ctx.upload_setup(setupio.to_setup(desc))
+    out, res = ctx.decode_batch(hb)
+    assert out.size == want.size and res.n_inconsistent == 0
+    assert float(np.abs(out - want).max()) <= TOL
+    out_e, _ = ctx.decode_batch(hb, capi.RUN_EXACT)
+    np.testing.assert_array_equal(out_e, want)
+
+
+def test_blob_roundtrip():
+    r, pcm, b, ctx = _ctx("3test")
+    ctx2 = capi.Context(0)
+    ctx2.import_blob(ctx.export_blob())
+    hb = H.batch_from_boundary(b, ctx.post_stride, 0, 80)
+    a, _ = ctx.decode_batch(hb); c, _ = ctx2.decode_batch(hb)
+    np.testing.assert_array_equal(a, c)
+
+
+def test_bad_entry_is_reported():
+    r, pcm, b, ctx = _ctx("1test")
+    hb = H.batch_from_boundary(b, ctx.post_stride)
+    ent = hb.entries.copy(); ent[:] = 65535
+    with pytest.raises(capi.NvbError) as e:
+        ctx.decode_batch(capi.HostBatch(hb.frames, hb.posts, hb.classes, ent))
+    assert e.value.status == capi.ERR_DATA
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
