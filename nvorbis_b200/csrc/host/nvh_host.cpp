@@ -1,0 +1,797 @@
+// nvh_host.cpp -- libnvorbis_host.so: the host half of the split decoder (include/nvorbis_host.h).
+//
+// Ogg demux, header parsing and the bit-unpacking half of every audio packet, producing the plain arrays of
+// nvb_setup / nvb_batch.  CPU only, multi-threaded over packets.  Written from the behaviour of the reference
+// (citations are NVorbis/ file:line); it shares no code with the test oracle and is never linked with it.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../../include/nvorbis_host.h"
+
+namespace nvh {
+
+struct DataError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+static int ilog(int x) { int n = 0; while (x > 0) { ++n; x >>= 1; } return n; }             // Utils.cs:5-14
+static uint32_t bitrev32(uint32_t n) {
+    n = ((n & 0xAAAAAAAAu) >> 1) | ((n & 0x55555555u) << 1);
+    n = ((n & 0xCCCCCCCCu) >> 2) | ((n & 0x33333333u) << 2);
+    n = ((n & 0xF0F0F0F0u) >> 4) | ((n & 0x0F0F0F0Fu) << 4);
+    n = ((n & 0xFF00FF00u) >> 8) | ((n & 0x00FF00FFu) << 8);
+    return (n >> 16) | (n << 16);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Bit cursor over one packet, LSB first (DataPacket.cs:150-283).  Reading past the end yields zero bits and
+// raises `short_`, as the reference's TryPeekBits/SkipBits pair does (IsShort, DataPacket.cs:255-279).
+// ---------------------------------------------------------------------------------------------------
+struct Bits {
+    const uint8_t* p; size_t nbits; size_t pos = 0; bool short_ = false;
+    Bits(const uint8_t* d, size_t bytes) : p(d), nbits(bytes * 8) {}
+    size_t left() const { return pos < nbits ? nbits - pos : 0; }
+    // up to 32 bits at the cursor, zero-padded beyond the end; does not advance
+    uint32_t peek32() const {
+        const size_t byte = pos >> 3; const unsigned sh = pos & 7;
+        const size_t nbytes = nbits >> 3;
+        uint64_t v = 0;
+        for (size_t i = 0; i < 5 && byte + i < nbytes; i++) v |= (uint64_t)p[byte + i] << (8 * i);
+        v >>= sh;
+        const size_t l = left();
+        if (l < 32) v &= (l == 0) ? 0 : ((1ull << l) - 1);
+        return (uint32_t)v;
+    }
+    void skip(int n) { if ((size_t)n > left()) { pos = nbits; short_ = true; } else pos += (size_t)n; }
+    uint32_t read(int n) {                                                    // n <= 32
+        if (n == 0) return 0;
+        uint32_t v = peek32();
+        if (n < 32) v &= (1u << n) - 1;
+        skip(n);
+        return v;
+    }
+    bool bit() { return read(1) != 0; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Codebooks (Codebook.cs:59-322, Huffman.cs:15-76).  Decoding uses a 10-bit root table plus per-root
+// chains for longer codewords; it returns what Codebook.DecodeScalar returns for the same bits.
+// ---------------------------------------------------------------------------------------------------
+struct Book {
+    int dims = 0, entries = 0, map_type = 0;
+    std::vector<int8_t> len;                       // 0 = unused entry
+    std::vector<float> table;
+    static constexpr int ROOT_BITS = 10;
+    struct Root { int32_t value; uint8_t len; };   // len 0: no short code here; value = head of the chain (-1 none)
+    struct Long { uint32_t code; int32_t value; int32_t next; uint8_t len; };
+    std::vector<Root> root; std::vector<Long> longs;
+    int root_bits = 0; bool decodable = false;
+
+    void parse(Bits& b) {
+        if (b.read(24) != 0x564342u) throw DataError("Book header had invalid signature!");          // Codebook.cs:62-63
+        dims = (int)b.read(16); entries = (int)b.read(24);
+        len.assign((size_t)entries, 0);
+        if (b.bit()) {                                                                                 // ordered lengths, Codebook.cs:83-104
+            int l = (int)b.read(5) + 1;
+            for (int i = 0; i < entries;) {
+                int cnt = (int)b.read(ilog(entries - i));
+                if (i + cnt > entries) throw DataError("ordered codebook overrun");
+                for (int k = 0; k < cnt; k++) len[(size_t)i++] = (int8_t)l;
+                ++l;
+            }
+        } else {
+            const bool sparse = b.bit();                                                               // Codebook.cs:106-127
+            for (int i = 0; i < entries; i++)
+                if (!sparse || b.bit()) len[(size_t)i] = (int8_t)(b.read(5) + 1);
+        }
+        build_decoder();
+        parse_lookup(b);
+    }
+
+    // Codeword assignment of the Vorbis I spec (section 3.2.1), the tree the reference builds in
+    // Codebook.ComputeCodewords (Codebook.cs:172-207): each entry takes the lowest free codeword of its length.
+    void build_decoder() {
+        uint32_t next_free[33] = {0};               // next_free[l]: lowest unused l-bit prefix (MSB first), if any
+        std::vector<uint32_t> code((size_t)entries, 0);
+        int maxlen = 0; bool any = false;
+        for (int i = 0; i < entries; i++) {
+            const int l = len[(size_t)i];
+            if (l <= 0) continue;
+            any = true; if (l > maxlen) maxlen = l;
+            uint32_t c = next_free[l];
+            if (l < 32 && (c >> l)) throw DataError("codebook is over-specified");
+            code[(size_t)i] = c;
+            for (int j = l; j > 0; j--) {           // claim the subtree: bump the markers above ...
+                if (next_free[j] & 1) { if (j == 1) next_free[1]++; else next_free[j] = next_free[j - 1] << 1; break; }
+                next_free[j]++;
+            }
+            for (int j = l + 1; j < 33; j++) {      // ... and re-point the longer lengths that hung below this code
+                if ((next_free[j] >> 1) == c) { c = next_free[j]; next_free[j] = next_free[j - 1] << 1; } else break;
+            }
+        }
+        decodable = any;
+        if (!any) return;
+        root_bits = maxlen < ROOT_BITS ? maxlen : ROOT_BITS;
+        root.assign((size_t)1 << root_bits, Root{-1, 0});
+        for (int i = 0; i < entries; i++) {
+            const int l = len[(size_t)i];
+            if (l <= 0) continue;
+            const uint32_t rev = bitrev32(code[(size_t)i]) >> (32 - l);      // first transmitted bit in bit 0
+            if (l <= root_bits) {
+                for (uint32_t hi = 0; hi < (1u << (root_bits - l)); hi++) root[(hi << l) | rev] = Root{i, (uint8_t)l};
+            } else {
+                Root& r = root[rev & ((1u << root_bits) - 1)];
+                longs.push_back(Long{rev, i, r.value, (uint8_t)l});
+                r.value = (int32_t)longs.size() - 1;
+            }
+        }
+    }
+
+    // Codebook.DecodeScalar (Codebook.cs:294-320): -1 when no bit is left or no codeword matches.
+    int decode(Bits& b) const {
+        if (!decodable || b.left() == 0) return -1;
+        const uint32_t v = b.peek32();
+        const Root& r = root[v & ((1u << root_bits) - 1)];
+        if (r.len) { b.skip(r.len); return r.value; }
+        for (int k = r.value; k >= 0; k = longs[(size_t)k].next) {
+            const Long& L = longs[(size_t)k];
+            const uint32_t mask = L.len >= 32 ? 0xFFFFFFFFu : ((1u << L.len) - 1);
+            if ((v & mask) == L.code) { b.skip(L.len); return L.value; }
+        }
+        return -1;
+    }
+
+    static float unpack_float(uint32_t bits) {                                                        // Utils.cs:45-59
+        const int32_t sign = (int32_t)bits >> 31;
+        const double e = (double)((int)((bits & 0x7fe00000u) >> 21) - 788);
+        const float mant = (float)(int32_t)(((bits & 0x1fffffu) ^ (uint32_t)sign) + (uint32_t)(sign & 1));
+        return mant * (float)std::pow(2.0, e);
+    }
+
+    // VQ lookup table (Codebook.InitLookupTable, Codebook.cs:222-283): float product + float min, then a
+    // double running sum when sequence_p is set, stored as float.
+    void parse_lookup(Bits& b) {
+        map_type = (int)b.read(4);
+        if (map_type == 0) return;
+        if (map_type > 2) throw DataError("invalid codebook lookup type");
+        const float vmin = unpack_float(b.read(32)), vdelta = unpack_float(b.read(32));
+        const int vbits = (int)b.read(4) + 1;
+        const bool seq = b.bit();
+        size_t nq = (size_t)entries * (size_t)dims;
+        table.assign(nq, 0.f);
+        if (map_type == 1) {                                                                          // Codebook.cs:285-292
+            int r = (int)std::floor(std::exp(std::log((double)entries) / dims));
+            if (std::floor(std::pow((double)(r + 1), (double)dims)) <= entries) ++r;
+            nq = (size_t)r;
+        }
+        std::vector<uint32_t> q(nq);
+        for (auto& x : q) x = b.read(vbits);
+        for (int e = 0; e < entries; e++) {
+            double run = 0.0; size_t div = 1;
+            for (int d = 0; d < dims; d++) {
+                const size_t qi = map_type == 1 ? ((size_t)e / div) % nq : (size_t)e * dims + d;
+                float f = (float)q[qi] * vdelta;
+                f = f + vmin;
+                const double v = (double)f + run;
+                table[(size_t)e * dims + d] = (float)v;
+                if (seq) run = v;
+                if (map_type == 1) div *= nq;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Setup tables
+// ---------------------------------------------------------------------------------------------------
+struct Floor1Def {
+    std::vector<int> part_class, class_dims, class_subs, class_master;
+    std::vector<std::vector<int>> sub_books;
+    int mult = 0, range = 0, ybits = 0;
+    std::vector<int> x, lo, hi, order;
+};
+struct ResidueDef {
+    int type = 0, begin = 0, end = 0, psize = 0, nclass = 0, class_book = 0, stages = 0;
+    int streams = 1;                 // Residue0._channels (1 for type 2, Residue2.cs:13)
+    int cascade[64]; int books[64][8];
+    std::vector<std::vector<uint8_t>> class_digits;     // _decodeMap (Residue0.cs:100-114)
+};
+struct MappingDef { std::vector<int> mag, ang; int submaps = 1; int floor0 = 0, residue0 = 0; std::vector<int> ch_floor, ch_residue; };
+struct ModeDef { bool long_block = false; int mapping = 0; };
+
+struct PacketRef { size_t off; size_t size; int64_t granule; uint8_t flags; };       // flags: 1 granule, 2 EOS, 4 resync
+
+struct UnpackedFrame {                 // one packet's result before concatenation
+    nvb_frame f; int n_classes = 0;
+    int64_t granule = 0; bool has_granule = false, eos = false, resync = false;
+};
+
+}  // namespace nvh
+
+using namespace nvh;
+
+struct nvh_stream {
+    std::string err;
+    std::vector<uint8_t> bytes;                  // packet payloads back to back
+    std::vector<PacketRef> packets;
+    bool has_eos = false;
+    // headers
+    int channels = 0, sample_rate = 0, bs[2] = {0, 0}, mode_bits = 0;
+    std::vector<Book> books; std::vector<Floor1Def> floors; std::vector<int> floor_type;
+    std::vector<ResidueDef> residues; std::vector<MappingDef> mappings; std::vector<ModeDef> modes;
+    // C-ABI view of the setup
+    std::vector<nvb_codebook> c_books; std::vector<float> c_vq; std::vector<nvb_floor> c_floors; std::vector<nvb_residue> c_residues;
+    std::vector<nvb_mapping> c_mappings; std::vector<nvb_mode> c_modes; nvb_setup c_setup;
+    int post_stride = 0;
+    // decode cursor (StreamDecoder state that lives on the host)
+    size_t first_audio = 3, next_packet = 3;
+    bool have_prev = false; int prev_start = 0, prev_end = 0, prev_stop = 0;
+    int64_t position = 0; bool has_position = false; bool eos_found = false;
+    // last unpacked batch
+    std::vector<nvb_frame> o_frames; std::vector<int16_t> o_posts; std::vector<uint8_t> o_classes; std::vector<uint16_t> o_entries;
+};
+
+namespace nvh {
+
+static thread_local std::string g_open_error;
+
+// ---- Ogg container: pages -> packets of the first logical stream ----------------------------------------
+// Ogg/PageReaderBase.cs:33-111,227-292 (sync + CRC), Ogg/PageReader.cs:27-93,125-158 (lacing; zero-length packets
+// and packet-less pages are dropped), Ogg/StreamPageReader.cs:44-90 (EOS page, sequence gaps = resync),
+// Ogg/PacketProvider.cs:324-438 (continuations; granule on the last packet completed in a page; EOS flag).
+static void demux_ogg(const uint8_t* d, size_t len, nvh_stream& s) {
+    uint32_t crc_table[256];
+    for (uint32_t i = 0; i < 256; i++) {                                                              // Ogg/Crc.cs:8-21
+        uint32_t r = i << 24;
+        for (int k = 0; k < 8; k++) r = (r << 1) ^ ((r & 0x80000000u) ? 0x04c11db7u : 0u);
+        crc_table[i] = r;
+    }
+    struct Piece { size_t off, size; };
+    struct PageInfo { int64_t granule; bool resync, continued, continuation, eos; std::vector<Piece> pieces; };
+    std::vector<PageInfo> pages;
+    size_t i = 0; bool lost_sync = false, have_serial = false, done = false; uint32_t serial = 0; int32_t last_seq = 0;
+    while (!done && i + 27 <= len) {
+        if (std::memcmp(d + i, "OggS", 4) != 0 || d[i + 4] != 0) { ++i; lost_sync = true; continue; }
+        const int nseg = d[i + 26];
+        if (i + 27 + (size_t)nseg > len) { ++i; lost_sync = true; continue; }
+        size_t body = 0; for (int k = 0; k < nseg; k++) body += d[i + 27 + k];
+        const size_t total = 27 + (size_t)nseg + body;
+        if (i + total > len) { ++i; lost_sync = true; continue; }
+        uint32_t crc = 0;
+        for (size_t k = 0; k < total; k++) {
+            const uint8_t byte = (k >= 22 && k < 26) ? 0 : d[i + k];
+            crc = (crc << 8) ^ crc_table[byte ^ (crc >> 24)];
+        }
+        uint32_t stored; std::memcpy(&stored, d + i + 22, 4);
+        if (crc != stored) { ++i; lost_sync = true; continue; }
+        uint32_t pg_serial; std::memcpy(&pg_serial, d + i + 14, 4);
+        int32_t seq; std::memcpy(&seq, d + i + 18, 4);
+        int64_t granule; std::memcpy(&granule, d + i + 6, 8);
+        const uint8_t flags = d[i + 5];
+        PageInfo pg; pg.granule = granule; pg.continuation = flags & 1; pg.eos = (flags & 4) != 0; pg.continued = false;
+        size_t off = i + 27 + (size_t)nseg, run = 0;
+        for (int k = 0; k < nseg; k++) {
+            const int seg = d[i + 27 + k]; run += (size_t)seg;
+            if (seg < 255) { if (run) { pg.pieces.push_back(Piece{off, run}); off += run; } run = 0; }
+        }
+        if (run) { pg.pieces.push_back(Piece{off, run}); pg.continued = d[i + 26 + nseg] == 255; }
+        i += total;
+        const bool was_lost = lost_sync; lost_sync = false;
+        if (!have_serial) { have_serial = true; serial = pg_serial; }
+        if (pg_serial != serial) continue;                    // other logical streams are not decoded here
+        if (pg.pieces.empty()) continue;                      // Ogg/PageReader.cs:131
+        pg.resync = was_lost || (last_seq != 0 && last_seq + 1 != seq);
+        last_seq = seq;
+        if (pg.eos) { s.has_eos = true; done = true; }
+        pages.push_back(std::move(pg));
+    }
+    // packets: a (page, piece) cursor advanced the way PacketProvider.CreatePacket does (:411-434)
+    size_t pi = 0, k = 0;
+    while (pi < pages.size()) {
+        const PageInfo& pg = pages[pi];
+        PacketRef pr; pr.off = s.bytes.size(); pr.flags = 0; pr.granule = 0;
+        s.bytes.insert(s.bytes.end(), d + pg.pieces[k].off, d + pg.pieces[k].off + pg.pieces[k].size);
+        const bool last_piece = k + 1 == pg.pieces.size();
+        bool resync = pg.resync, last_in_page = last_piece; int64_t granule = pg.granule;
+        size_t final_page = pi, final_pieces = pg.pieces.size();
+        if (last_piece && pg.continued) {
+            bool cont = true; size_t cp = pi;
+            while (cont) {
+                if (++cp >= pages.size()) { s.bytes.resize(pr.off); return; }                    // cannot complete: no packet (:346-350)
+                const PageInfo& nx = pages[cp];
+                granule = nx.granule; resync = nx.resync; cont = nx.continued; final_pieces = nx.pieces.size();
+                if (!nx.continuation || nx.resync) break;                                         // broken chain: keep what we have (:354-357)
+                if (cont && nx.pieces.size() > 1) cont = false;                                   // (:360-363)
+                s.bytes.insert(s.bytes.end(), d + nx.pieces[0].off, d + nx.pieces[0].off + nx.pieces[0].size);
+            }
+            last_in_page = final_pieces == 1;
+            final_page = cp;
+        }
+        pr.size = s.bytes.size() - pr.off;
+        if (resync) pr.flags |= 4;
+        if (last_in_page) {                                                                       // (:399-407)
+            pr.flags |= 1; pr.granule = granule;
+            if (s.has_eos && final_page + 1 == pages.size()) pr.flags |= 2;
+        }
+        s.packets.push_back(pr);
+        if (final_page != pi) { pi = final_page; k = 0; }
+        if (k + 1 == final_pieces) { ++pi; k = 0; } else ++k;
+    }
+}
+
+static void parse_id_header(Bits& b, nvh_stream& s) {                                                 // StreamDecoder.cs:179-204
+    static const uint8_t sig[7] = {0x01, 'v', 'o', 'r', 'b', 'i', 's'};
+    for (int i = 0; i < 7; i++) if (b.read(8) != sig[i]) throw DataError("Could not find Vorbis data to decode.");
+    if (b.read(32) != 0) throw DataError("Could not find Vorbis data to decode.");                  // version
+    s.channels = (int)b.read(8);
+    s.sample_rate = (int)b.read(32);
+    b.read(32); b.read(32); b.read(32);
+    s.bs[0] = 1 << b.read(4); s.bs[1] = 1 << b.read(4);
+    if (s.channels < 1) throw DataError("stream has no channels");
+}
+
+static void parse_floor1(Bits& b, const nvh_stream& s, Floor1Def& f) {                                // Floor1.cs:30-133
+    const int nparts = (int)b.read(5);
+    int max_class = -1;
+    f.part_class.resize((size_t)nparts);
+    for (auto& c : f.part_class) { c = (int)b.read(4); max_class = std::max(max_class, c); }
+    const int nclass = max_class + 1;
+    f.class_dims.assign((size_t)nclass, 0); f.class_subs.assign((size_t)nclass, 0); f.class_master.assign((size_t)nclass, 0);
+    f.sub_books.assign((size_t)nclass, {});
+    for (int c = 0; c < nclass; c++) {
+        f.class_dims[(size_t)c] = (int)b.read(3) + 1;
+        f.class_subs[(size_t)c] = (int)b.read(2);
+        if (f.class_subs[(size_t)c] > 0) {
+            f.class_master[(size_t)c] = (int)b.read(8);
+            if (f.class_master[(size_t)c] >= (int)s.books.size()) throw DataError("floor1: master book out of range");
+        }
+        f.sub_books[(size_t)c].resize((size_t)1 << f.class_subs[(size_t)c]);
+        for (auto& bk : f.sub_books[(size_t)c]) { bk = (int)b.read(8) - 1; if (bk >= (int)s.books.size()) throw DataError("floor1: subclass book out of range"); }
+    }
+    static const int ranges[4] = {256, 128, 86, 64}, ybits[4] = {8, 7, 7, 6};                         // Floor1.cs:27-28
+    const int m = (int)b.read(2);
+    f.mult = m + 1; f.range = ranges[m]; f.ybits = ybits[m];
+    const int rbits = (int)b.read(4);
+    f.x = {0, 1 << rbits};
+    for (int p = 0; p < nparts; p++)
+        for (int k = 0; k < f.class_dims[(size_t)f.part_class[(size_t)p]]; k++) f.x.push_back((int)b.read(rbits));
+    const int n = (int)f.x.size();
+    if (n > 64) throw DataError("floor1: more than 64 posts");                                        // Floor1.Data.Posts is int[64] (Floor1.cs:12)
+    f.lo.assign((size_t)n, 0); f.hi.assign((size_t)n, 0); f.order.resize((size_t)n);
+    for (int i = 0; i < n; i++) f.order[(size_t)i] = i;
+    for (int i = 2; i < n; i++) {                                                                     // nearest neighbours among earlier posts, Floor1.cs:98-115
+        int lo = 0, hi = 1;
+        for (int j = 2; j < i; j++) {
+            if (f.x[(size_t)j] < f.x[(size_t)i]) { if (f.x[(size_t)j] > f.x[(size_t)lo]) lo = j; }
+            else if (f.x[(size_t)j] < f.x[(size_t)hi]) hi = j;
+        }
+        f.lo[(size_t)i] = lo; f.hi[(size_t)i] = hi;
+    }
+    for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (f.x[(size_t)i] == f.x[(size_t)j]) throw DataError("floor1: duplicate x");
+    std::sort(f.order.begin(), f.order.end(), [&](int a, int c) { return f.x[(size_t)a] < f.x[(size_t)c]; });   // Floor1.cs:118-132 (x values are distinct)
+}
+
+static void parse_residue(Bits& b, const nvh_stream& s, int type, ResidueDef& r) {                    // Residue0.cs:35-117, Residue2.cs:10-14
+    r.type = type; r.streams = type == 2 ? 1 : s.channels;
+    r.begin = (int)b.read(24); r.end = (int)b.read(24); r.psize = (int)b.read(24) + 1;
+    r.nclass = (int)b.read(6) + 1; r.class_book = (int)b.read(8);
+    if (r.class_book >= (int)s.books.size()) throw DataError("residue: class book out of range");
+    int nbooks = 0;
+    for (int c = 0; c < 64; c++) { r.cascade[c] = 0; for (int k = 0; k < 8; k++) r.books[c][k] = -1; }
+    for (int c = 0; c < r.nclass; c++) {
+        const int low = (int)b.read(3);
+        r.cascade[c] = b.bit() ? (((int)b.read(5) << 3) | low) : low;
+        nbooks += __builtin_popcount((unsigned)r.cascade[c]);
+    }
+    std::vector<int> list((size_t)nbooks);
+    for (auto& bk : list) {
+        bk = (int)b.read(8);
+        if (bk >= (int)s.books.size()) throw DataError("residue: book out of range");
+        if (s.books[(size_t)bk].map_type == 0) throw DataError("residue: book without a lookup table");     // Residue0.cs:66-67
+    }
+    const Book& cb = s.books[(size_t)r.class_book];
+    long long partvals = 1;
+    for (int k = 0; k < cb.dims; k++) { partvals *= r.nclass; if (partvals > cb.entries) throw DataError("residue: class book too small"); }
+    int at = 0; r.stages = 0;
+    for (int c = 0; c < r.nclass; c++) {
+        const int st = ilog(r.cascade[c]);
+        r.stages = std::max(r.stages, st);
+        for (int k = 0; k < st; k++) if ((r.cascade[c] >> k) & 1) r.books[c][k] = list[(size_t)at++];
+    }
+    r.class_digits.assign((size_t)partvals, std::vector<uint8_t>((size_t)cb.dims));
+    for (long long v = 0; v < partvals; v++) {                                                        // most significant digit first, Residue0.cs:100-114
+        long long rem = v, mult = partvals / r.nclass;
+        for (int k = 0; k < cb.dims; k++) { const long long dgt = rem / mult; rem -= dgt * mult; mult /= r.nclass; r.class_digits[(size_t)v][(size_t)k] = (uint8_t)dgt; }
+    }
+}
+
+static void parse_mapping(Bits& b, const nvh_stream& s, MappingDef& m) {                              // Mapping.cs:16-93
+    m.submaps = b.bit() ? 1 + (int)b.read(4) : 1;
+    const int steps = b.bit() ? 1 + (int)b.read(8) : 0;
+    const int cbits = ilog(s.channels - 1);
+    for (int k = 0; k < steps; k++) {
+        const int mag = (int)b.read(cbits), ang = (int)b.read(cbits);
+        if (mag == ang || mag > s.channels - 1 || ang > s.channels - 1) throw DataError("Invalid magnitude or angle in mapping header!");
+        m.mag.push_back(mag); m.ang.push_back(ang);
+    }
+    if (b.read(2) != 0) throw DataError("Reserved bits not 0 in mapping header.");
+    std::vector<int> mux((size_t)s.channels, 0);
+    if (m.submaps > 1) for (auto& x : mux) { x = (int)b.read(4); if (x >= m.submaps) throw DataError("Invalid channel mux submap index in mapping header!"); }
+    std::vector<int> sf((size_t)m.submaps), sr((size_t)m.submaps);
+    for (int k = 0; k < m.submaps; k++) {
+        b.read(8);
+        sf[(size_t)k] = (int)b.read(8); if (sf[(size_t)k] >= (int)s.floors.size()) throw DataError("Invalid floor number in mapping header!");
+        sr[(size_t)k] = (int)b.read(8); if (sr[(size_t)k] >= (int)s.residues.size()) throw DataError("Invalid residue number in mapping header!");
+    }
+    m.floor0 = sf[0]; m.residue0 = sr[0];
+    for (int c = 0; c < s.channels; c++) { m.ch_floor.push_back(sf[(size_t)mux[(size_t)c]]); m.ch_residue.push_back(sr[(size_t)mux[(size_t)c]]); }
+}
+
+static void parse_setup_header(Bits& b, nvh_stream& s) {                                              // StreamDecoder.cs:226-289
+    static const uint8_t sig[7] = {0x05, 'v', 'o', 'r', 'b', 'i', 's'};
+    for (int i = 0; i < 7; i++) if (b.read(8) != sig[i]) throw DataError("setup header signature");
+    s.books.resize((size_t)b.read(8) + 1);
+    for (auto& bk : s.books) bk.parse(b);
+    const int times = (int)b.read(6) + 1;
+    b.skip(16 * times);
+    const int nfloors = (int)b.read(6) + 1;
+    s.floors.resize((size_t)nfloors); s.floor_type.resize((size_t)nfloors);
+    for (int i = 0; i < nfloors; i++) {
+        const int type = (int)b.read(16);                                                             // Factory.cs:22-31
+        s.floor_type[(size_t)i] = type;
+        if (type == 1) parse_floor1(b, s, s.floors[(size_t)i]);
+        else if (type == 0) throw DataError("floor type 0 streams are not accepted by the synthesis path yet");
+        else throw DataError("Invalid floor type!");
+    }
+    s.residues.resize((size_t)b.read(6) + 1);
+    for (auto& r : s.residues) {
+        const int type = (int)b.read(16);                                                             // Factory.cs:48-58
+        if (type > 2) throw DataError("Invalid residue type!");
+        parse_residue(b, s, type, r);
+    }
+    s.mappings.resize((size_t)b.read(6) + 1);
+    for (auto& m : s.mappings) { if (b.read(16) != 0) throw DataError("Invalid mapping type!"); parse_mapping(b, s, m); }
+    s.modes.resize((size_t)b.read(6) + 1);
+    for (auto& m : s.modes) {                                                                         // Mode.cs:24-41
+        m.long_block = b.bit();
+        if (b.read(32) != 0) throw DataError("Mode header had invalid window or transform type!");
+        m.mapping = (int)b.read(8);
+        if (m.mapping >= (int)s.mappings.size()) throw DataError("Mode header had invalid mapping index!");
+    }
+    if (!b.bit()) throw DataError("Book packet did not end on correct bit!");
+    if (b.short_) throw DataError("setup header is truncated");
+    s.mode_bits = ilog((int)s.modes.size() - 1);
+}
+
+static void export_setup(nvh_stream& s) {
+    int64_t off = 0;
+    for (const Book& b : s.books) {
+        nvb_codebook c; c.dims = b.dims; c.entries = b.entries; c.map_type = b.map_type; c.reserved = 0;
+        c.table_off = b.table.empty() ? -1 : off;
+        s.c_vq.insert(s.c_vq.end(), b.table.begin(), b.table.end()); off += (int64_t)b.table.size();
+        s.c_books.push_back(c);
+    }
+    int max_posts = 2;
+    for (size_t i = 0; i < s.floors.size(); i++) {
+        const Floor1Def& f = s.floors[i];
+        nvb_floor c; std::memset(&c, 0, sizeof c);
+        c.type = s.floor_type[i]; c.f1.n_posts = (int)f.x.size(); c.f1.multiplier = f.mult; c.f1.range = f.range;
+        for (size_t k = 0; k < f.x.size(); k++) { c.f1.x_list[k] = (uint16_t)f.x[k]; c.f1.l_neigh[k] = (uint8_t)f.lo[k]; c.f1.h_neigh[k] = (uint8_t)f.hi[k]; c.f1.sort_idx[k] = (uint8_t)f.order[k]; }
+        max_posts = std::max(max_posts, (int)f.x.size());
+        s.c_floors.push_back(c);
+    }
+    s.post_stride = (2 + max_posts + 1) & ~1;
+    for (const ResidueDef& r : s.residues) {
+        nvb_residue c; std::memset(&c, 0, sizeof c);
+        c.type = r.type; c.begin = r.begin; c.end = r.end; c.partition_size = r.psize; c.classifications = r.nclass; c.max_stages = r.stages;
+        for (int k = 0; k < 64; k++) { c.cascade[k] = r.cascade[k]; for (int st = 0; st < 8; st++) c.books[k][st] = (int16_t)r.books[k][st]; }
+        s.c_residues.push_back(c);
+    }
+    for (const MappingDef& m : s.mappings) {
+        nvb_mapping c; std::memset(&c, 0, sizeof c);
+        c.n_coupling = (int)m.mag.size(); c.n_submaps = m.submaps; c.floor = m.floor0; c.residue = m.residue0;
+        for (size_t k = 0; k < m.mag.size() && k < NVB_MAX_COUPLING; k++) { c.magnitude[k] = (uint8_t)m.mag[k]; c.angle[k] = (uint8_t)m.ang[k]; }
+        s.c_mappings.push_back(c);
+    }
+    for (const ModeDef& m : s.modes) { nvb_mode c; c.block_flag = m.long_block ? 1 : 0; c.mapping = m.mapping; s.c_modes.push_back(c); }
+    nvb_setup& S = s.c_setup; std::memset(&S, 0, sizeof S);
+    S.abi_version = NVB_ABI_VERSION; S.channels = s.channels; S.sample_rate = s.sample_rate; S.block_size[0] = s.bs[0]; S.block_size[1] = s.bs[1];
+    S.n_books = (int)s.c_books.size(); S.n_floors = (int)s.c_floors.size(); S.n_residues = (int)s.c_residues.size();
+    S.n_mappings = (int)s.c_mappings.size(); S.n_modes = (int)s.c_modes.size();
+    S.books = s.c_books.data(); S.vq_floats = s.c_vq.data(); S.n_vq_floats = (int64_t)s.c_vq.size();
+    S.floors = s.c_floors.data(); S.residues = s.c_residues.data(); S.mappings = s.c_mappings.data(); S.modes = s.c_modes.data();
+}
+
+static void open_common(nvh_stream& s) {
+    if (s.packets.size() < 3) throw DataError("Could not find Vorbis data to decode.");
+    { Bits b(s.bytes.data() + s.packets[0].off, s.packets[0].size); parse_id_header(b, s); }
+    {   // comment header: only the signature matters here (StreamDecoder.cs:206-224)
+        Bits b(s.bytes.data() + s.packets[1].off, s.packets[1].size);
+        static const uint8_t sig[7] = {0x03, 'v', 'o', 'r', 'b', 'i', 's'};
+        for (int i = 0; i < 7; i++) if (b.read(8) != sig[i]) throw DataError("comment header signature");
+    }
+    { Bits b(s.bytes.data() + s.packets[2].off, s.packets[2].size); parse_setup_header(b, s); }
+    export_setup(s);
+    s.first_audio = s.next_packet = 3;
+}
+
+// ---- one audio packet -> boundary record ----------------------------------------------------------------
+struct Scratch { std::vector<int16_t> posts; std::vector<uint8_t> classes; std::vector<uint16_t> entries; std::vector<UnpackedFrame> frames; };
+
+static void unpack_packet(const nvh_stream& s, const PacketRef& pr, Scratch& out) {
+    UnpackedFrame uf; std::memset(&uf.f, 0, sizeof uf.f);
+    uf.has_granule = pr.flags & 1; uf.granule = pr.granule; uf.eos = (pr.flags & 2) != 0; uf.resync = (pr.flags & 4) != 0;
+    const int C = s.channels;
+    const size_t posts_at = out.posts.size();
+    out.posts.resize(posts_at + (size_t)C * s.post_stride, 0);
+    uf.f.status = NVB_FRAME_FAILED;
+    uf.f.classes_off = (uint32_t)out.classes.size(); uf.f.entries_off = (uint32_t)out.entries.size();
+    Bits b(s.bytes.data() + pr.off, pr.size);
+    auto done = [&]() { out.frames.push_back(uf); };
+
+    if (b.bit()) return done();                                                                       // not an audio packet, StreamDecoder.cs:490
+    const int mode_idx = (int)b.read(s.mode_bits);
+    if (mode_idx >= (int)s.modes.size()) return done();
+    const ModeDef& mode = s.modes[(size_t)mode_idx];
+    // Mode.GetPacketInfo (Mode.cs:119-151)
+    if (b.short_) return done();
+    int window = 0, start, valid, total;
+    const int N = s.bs[mode.long_block ? 1 : 0];
+    if (mode.long_block) {
+        const bool prev = b.bit(), next = b.bit();
+        window = (prev ? 1 : 0) + (next ? 2 : 0);
+        const int pn = prev ? s.bs[1] : s.bs[0], nn = next ? s.bs[1] : s.bs[0];
+        start = N / 4 - pn / 4; total = N / 4 * 3 + nn / 4; valid = total - nn / 4 * 2;                // Mode.cs:102-117
+    } else { start = 0; valid = N / 2; total = N; }
+    uf.f.status = NVB_FRAME_OK; uf.f.mode = (uint8_t)mode_idx; uf.f.window = (uint8_t)window;
+    uf.f.start = start; uf.f.valid = valid; uf.f.total = total;
+
+    const MappingDef& map = s.mappings[(size_t)mode.mapping];
+    // floors: Floor1.Unpack per channel (Floor1.cs:135-184)
+    uint32_t live = 0;
+    for (int c = 0; c < C; c++) {
+        const Floor1Def& f = s.floors[(size_t)map.ch_floor[(size_t)c]];
+        int16_t* dst = out.posts.data() + posts_at + (size_t)c * s.post_stride;
+        int count = 0;
+        if (b.bit()) {
+            count = 2;
+            dst[1] = (int16_t)b.read(f.ybits); dst[2] = (int16_t)b.read(f.ybits);
+            bool failed = false;
+            for (size_t p = 0; p < f.part_class.size() && !failed; p++) {
+                const int cls = f.part_class[p], cdim = f.class_dims[(size_t)cls], cbits = f.class_subs[(size_t)cls];
+                uint32_t cval = 0;
+                if (cbits > 0) {
+                    const int v = s.books[(size_t)f.class_master[(size_t)cls]].decode(b);
+                    if (v < 0) { failed = true; break; }
+                    cval = (uint32_t)v;
+                }
+                for (int k = 0; k < cdim; k++) {
+                    const int bk = f.sub_books[(size_t)cls][cval & ((1u << cbits) - 1)];
+                    cval >>= cbits;
+                    int y = 0;
+                    if (bk >= 0) { y = s.books[(size_t)bk].decode(b); if (y < 0) { failed = true; break; } }
+                    dst[1 + count] = (int16_t)y;
+                    ++count;
+                }
+            }
+            if (failed) count = 0;                                                                    // "use nothing", Floor1.cs:155-174
+        }
+        dst[0] = (int16_t)count;
+        if (count > 0) live |= 1u << c;
+    }
+    // energy flags (Mapping.cs:105-119): noExecute is taken before the coupling propagation
+    const uint32_t no_exec = ~live & ((1u << C) - 1);
+    uint32_t exec = live;
+    for (size_t k = 0; k < map.mag.size(); k++)
+        if (((exec >> map.ang[k]) | (exec >> map.mag[k])) & 1u) exec |= (1u << map.ang[k]) | (1u << map.mag[k]);
+    uf.f.exec_mask = exec;
+
+    // residue (Residue0.Decode, Residue0.cs:119-178): runs when any channel is live, over all streams
+    const ResidueDef& r = s.residues[(size_t)map.residue0];
+    const int span = (r.type == 2 ? N * C : N) / 2;
+    const int nn = std::min(r.end, span) - r.begin;
+    if (nn > 0 && no_exec != ((1u << C) - 1)) {
+        uf.f.res_decoded = 1;
+        const int P = nn / r.psize, S = r.streams;
+        const Book& cb = s.books[(size_t)r.class_book];
+        const size_t cls_at = out.classes.size();
+        out.classes.resize(cls_at + (size_t)S * P, 0);
+        uf.n_classes = S * P;
+        bool stop = false;
+        std::vector<uint16_t> pending;
+        for (int stage = 0; stage < r.stages && !stop; stage++) {
+            for (int p = 0; p < P && !stop;) {
+                if (stage == 0) {
+                    for (int st = 0; st < S; st++) {
+                        const int w = cb.decode(b);
+                        if (w < 0 || w >= (int)r.class_digits.size()) { stop = true; break; }
+                        for (int k = 0; k < cb.dims && p + k < P; k++) out.classes[cls_at + (size_t)st * P + p + k] = r.class_digits[(size_t)w][(size_t)k];
+                    }
+                    if (stop) break;
+                }
+                for (int k = 0; k < cb.dims && p < P && !stop; k++, p++) {
+                    for (int st = 0; st < S && !stop; st++) {
+                        const int cls = out.classes[cls_at + (size_t)st * P + p];
+                        if (!((r.cascade[cls] >> stage) & 1)) continue;
+                        const int bk = r.books[cls][stage];
+                        if (bk < 0) continue;
+                        const Book& vb = s.books[(size_t)bk];
+                        if (r.type == 0) {
+                            // all of a partition's entries are read before any is used (Residue0.cs:186-192)
+                            const int steps = r.psize / vb.dims;
+                            pending.clear();
+                            for (int q = 0; q < steps; q++) { const int e = vb.decode(b); if (e < 0) { stop = true; break; } pending.push_back((uint16_t)e); }
+                            if (!stop) out.entries.insert(out.entries.end(), pending.begin(), pending.end());
+                        } else {
+                            for (int q = 0; q < r.psize; q += vb.dims) {                              // Residue1.cs:12-23, Residue2.cs:29-44
+                                const int e = vb.decode(b);
+                                if (e < 0) { stop = true; break; }
+                                out.entries.push_back((uint16_t)e);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    uf.f.entry_count = (uint32_t)(out.entries.size() - uf.f.entries_off);
+    done();
+}
+
+}  // namespace nvh
+
+// =====================================================================================================
+extern "C" {
+
+const char* nvh_last_error(nvh_stream* s) { return s ? s->err.c_str() : g_open_error.c_str(); }
+
+static int finish_open(std::unique_ptr<nvh_stream>& s, nvh_stream** out) {
+    try { open_common(*s); }
+    catch (const std::exception& e) { g_open_error = e.what(); return NVB_ERR_DATA; }
+    *out = s.release();
+    return NVB_OK;
+}
+
+int nvh_open_ogg(const uint8_t* data, size_t len, nvh_stream** out) {
+    if (!data || !out) { g_open_error = "NULL argument"; return NVB_ERR_ARG; }
+    *out = nullptr;
+    std::unique_ptr<nvh_stream> s(new nvh_stream());
+    try { demux_ogg(data, len, *s); }
+    catch (const std::exception& e) { g_open_error = e.what(); return NVB_ERR_DATA; }
+    return finish_open(s, out);
+}
+
+int nvh_open_packets(const uint8_t* data, const int64_t* sizes, const int64_t* granules, const uint8_t* flags, int64_t n, nvh_stream** out) {
+    if (!data || !sizes || !granules || !flags || !out || n < 0) { g_open_error = "NULL argument"; return NVB_ERR_ARG; }
+    *out = nullptr;
+    std::unique_ptr<nvh_stream> s(new nvh_stream());
+    size_t off = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (sizes[i] < 0) { g_open_error = "negative packet size"; return NVB_ERR_ARG; }
+        s->packets.push_back(PacketRef{off, (size_t)sizes[i], granules[i], flags[i]});
+        if (flags[i] & 2) s->has_eos = true;
+        off += (size_t)sizes[i];
+    }
+    s->bytes.assign(data, data + off);
+    return finish_open(s, out);
+}
+
+int nvh_close(nvh_stream* s) { delete s; return NVB_OK; }
+
+int nvh_get_info(nvh_stream* s, nvh_info* o) {
+    if (!s || !o) return NVB_ERR_ARG;
+    std::memset(o, 0, sizeof *o);
+    o->channels = s->channels; o->sample_rate = s->sample_rate; o->block_size[0] = s->bs[0]; o->block_size[1] = s->bs[1];
+    o->n_books = (int)s->books.size(); o->n_floors = (int)s->floors.size(); o->n_residues = (int)s->residues.size();
+    o->n_mappings = (int)s->mappings.size(); o->n_modes = (int)s->modes.size(); o->post_stride = s->post_stride;
+    o->n_packets = (int64_t)s->packets.size(); o->n_audio_packets = (int64_t)(s->packets.size() - s->first_audio);
+    o->last_granule = -1;
+    for (const PacketRef& p : s->packets) if (p.flags & 1) o->last_granule = p.granule;
+    o->has_eos = s->has_eos ? 1 : 0;
+    return NVB_OK;
+}
+
+const nvb_setup* nvh_setup(nvh_stream* s) { return s ? &s->c_setup : nullptr; }
+
+int64_t nvh_packet_size(nvh_stream* s, int64_t i) { return (!s || i < 0 || i >= (int64_t)s->packets.size()) ? -1 : (int64_t)s->packets[(size_t)i].size; }
+int nvh_packet_get(nvh_stream* s, int64_t i, uint8_t* dst, int64_t* granule, int32_t* flags) {
+    if (!s || i < 0 || i >= (int64_t)s->packets.size()) return NVB_ERR_ARG;
+    const PacketRef& p = s->packets[(size_t)i];
+    if (dst) std::memcpy(dst, s->bytes.data() + p.off, p.size);
+    if (granule) *granule = p.granule;
+    if (flags) *flags = p.flags;
+    return NVB_OK;
+}
+
+int nvh_rewind(nvh_stream* s) {
+    if (!s) return NVB_ERR_ARG;
+    s->next_packet = s->first_audio;
+    s->have_prev = false; s->prev_start = s->prev_end = s->prev_stop = 0;
+    s->position = 0; s->has_position = false; s->eos_found = false;
+    return NVB_OK;
+}
+
+int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, int32_t* end_of_stream) {
+    if (!s || !out || count < 0) return NVB_ERR_ARG;
+    if (end_of_stream) *end_of_stream = 0;
+    const size_t lo = s->next_packet;
+    const size_t avail = s->packets.size() - lo;
+    const size_t n = std::min<size_t>((size_t)count, avail);
+    int T = std::max(1, threads);
+    if ((size_t)T > n) T = (int)std::max<size_t>(1, n);
+    std::vector<Scratch> parts((size_t)T);
+    auto work = [&](int t) {
+        const size_t a = lo + n * (size_t)t / (size_t)T, b = lo + n * (size_t)(t + 1) / (size_t)T;
+        for (size_t i = a; i < b; i++) unpack_packet(*s, s->packets[i], parts[(size_t)t]);
+    };
+    if (T == 1) work(0);
+    else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+
+    s->o_frames.clear(); s->o_posts.clear(); s->o_classes.clear(); s->o_entries.clear();
+    std::vector<UnpackedFrame> metas;
+    for (Scratch& p : parts) {
+        const uint32_t coff = (uint32_t)s->o_classes.size(), eoff = (uint32_t)s->o_entries.size();
+        for (UnpackedFrame& uf : p.frames) { uf.f.classes_off += coff; uf.f.entries_off += eoff; metas.push_back(uf); }
+        s->o_posts.insert(s->o_posts.end(), p.posts.begin(), p.posts.end());
+        s->o_classes.insert(s->o_classes.end(), p.classes.begin(), p.classes.end());
+        s->o_entries.insert(s->o_entries.end(), p.entries.begin(), p.entries.end());
+    }
+    // Stream-order pass: the bookkeeping of StreamDecoder.ReadNextPacket / Read that lives on the host --
+    // sample position (re-based on the first granule, StreamDecoder.cs:358-363) and the EOS trim (:429-437).
+    for (UnpackedFrame& uf : metas) {
+        nvb_frame& f = uf.f;
+        if (uf.resync) s->has_position = false;                                                       // StreamDecoder.cs:485-488
+        s->eos_found |= uf.eos;
+        int emitted;
+        if (f.status != NVB_FRAME_OK) {
+            s->prev_end = s->prev_stop;                                                               // drain, StreamDecoder.cs:352-356
+            emitted = s->have_prev ? std::max(0, s->prev_end - s->prev_start) : 0;
+            s->prev_start = s->prev_end;
+        } else {
+            if (uf.has_granule && uf.eos) {
+                const int64_t actual_end = s->position + f.valid - f.start;
+                const int diff = (int)(uf.granule - actual_end);
+                if (diff < 0) f.valid += diff;
+            }
+            if (s->prev_end > 0) s->prev_start = f.start;
+            else if (!s->have_prev) s->prev_start = f.valid;
+            s->prev_end = f.valid; s->prev_stop = f.total; s->have_prev = true;
+            emitted = std::max(0, s->prev_end - s->prev_start);
+            if (s->prev_end < s->prev_start) s->prev_start = s->prev_end;
+            s->prev_start = s->prev_end;
+        }
+        s->position += emitted;
+        if (uf.has_granule && !s->has_position && f.status == NVB_FRAME_OK) { s->has_position = true; s->position = uf.granule; }
+        s->o_frames.push_back(f);
+    }
+    s->next_packet = lo + n;
+    if (s->next_packet >= s->packets.size() && (size_t)count > n) {
+        // the provider ran dry: DecodeNextPacket returns null with isEndOfStream = true (StreamDecoder.cs:476-480)
+        if (!s->eos_found) {
+            nvb_frame f; std::memset(&f, 0, sizeof f); f.status = NVB_FRAME_FAILED;
+            f.classes_off = (uint32_t)s->o_classes.size(); f.entries_off = (uint32_t)s->o_entries.size();
+            s->o_frames.push_back(f);
+            s->o_posts.resize(s->o_posts.size() + (size_t)s->channels * s->post_stride, 0);
+            s->prev_end = s->prev_stop;
+            if (s->have_prev) s->position += std::max(0, s->prev_end - s->prev_start);
+            s->prev_start = s->prev_end;
+            s->eos_found = true;
+        }
+        if (end_of_stream) *end_of_stream = 1;
+    } else if (s->eos_found && end_of_stream) {
+        *end_of_stream = 1;
+    }
+    std::memset(out, 0, sizeof *out);
+    out->n_frames = (int32_t)s->o_frames.size();
+    out->frames = s->o_frames.data(); out->posts = s->o_posts.data();
+    out->classes = s->o_classes.data(); out->n_classes = (int64_t)s->o_classes.size();
+    out->entries = s->o_entries.data(); out->n_entries = (int64_t)s->o_entries.size();
+    return (int64_t)s->o_frames.size();
+}
+
+}  // extern "C"

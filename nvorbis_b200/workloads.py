@@ -61,8 +61,12 @@ class FramePool:
     # ---- frame classes ------------------------------------------------------------------------------
     def long_long(self) -> np.ndarray:
         """Indices of long blocks whose both neighbours are long (window index 3, Mode.cs:44-50,135)."""
+        return np.nonzero(self._ll_mask())[0]
+
+    def _ll_mask(self) -> np.ndarray:
         f = self.frames
-        return np.nonzero((f["status"] == capi.FRAME_OK) & self.long_flag & (f["window"] == 3))[0]
+        half = self.block_size[1] // 2           # untrimmed long/long block: start 0, valid N/2 (an EOS-trimmed block is left out)
+        return (f["status"] == capi.FRAME_OK) & self.long_flag & (f["window"] == 3) & (f["start"] == 0) & (f["valid"] == half)
 
 
 def config2(pool: FramePool, n_frames: int = 4096, seed: int = 20240002) -> capi.HostBatch:
@@ -76,7 +80,7 @@ def config3(pool: FramePool, n_frames: int = 16384, seed: int = 20240003, min_ru
     """BASELINE configs[2]: mixed short/long window transitions: contiguous runs of real frames, cut only
     between two long/long blocks so that every block's window flags match its neighbours."""
     f = pool.frames
-    ll = (f["status"] == capi.FRAME_OK) & pool.long_flag & (f["window"] == 3)
+    ll = pool._ll_mask()
     cut = np.nonzero(ll[:-1] & ll[1:])[0] + 1          # a run may start at i if i-1 and i are long/long
     rng = np.random.Generator(np.random.PCG64(seed))
     out, total = [], 0
