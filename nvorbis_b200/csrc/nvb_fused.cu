@@ -5,15 +5,19 @@
 // ClippingCopyBuffer / CopyBuffer (StreamDecoder.cs:391-415).
 //
 // Mapping onto the chip
-//   * one CTA owns a contiguous run of frames and walks it in groups of G frames; one warp
-//     transforms one (frame, channel) block: 512 complex points as 16 per lane, three radix-8
-//     passes in registers, two exchanges through a warp-private 4.5 KB shared-memory slot
-//     (bank-conflict-free strides 72 / 9), twiddles from shared-memory tables;
-//   * the DCT-IV output u of every block stays in shared memory; the previous block's u is still
-//     there (ring of G+1 slots), so the overlap-add never touches HBM: each spectrum float is
-//     read once and each PCM float written once (16 384 B per stereo long frame);
-//   * the first block of a run is recomputed as a halo (its output belongs to the previous CTA);
-//   * output: two samples x two channels per thread as one float4 store, coalesced.
+//   * persistent grid: one CTA per SM owns a contiguous run of frames; its 16 warps take the frames of the
+//     run round-robin.  A warp transforms every channel of its frame (512 complex points as 16 per lane:
+//     three radix-8 passes in registers, two exchanges through the frame's shared-memory slot, twiddles
+//     from per-lane tables that one bulk copy (cp.async.bulk, TMA) stages at kernel start), leaves the
+//     DCT-IV output u in the slot, then writes the frame's PCM from its own u and the previous frame's u;
+//   * no CTA-wide barrier in steady state: slots form a ring guarded by mbarriers -- full[slot] (u of that
+//     frame is complete; awaited by the warp that overlaps onto it) and empty[slot] (both readers of the
+//     slot are done; awaited by the warp that reuses it) -- so transform, overlap and store of different
+//     frames run concurrently on the four schedulers of the SM;
+//   * the previous block's tail never touches HBM: each spectrum float is read once and each PCM float is
+//     written once (16 384 B per stereo long frame); the first block of a run is recomputed as a halo;
+//   * shared memory is bank-conflict free: padded exchange strides (72 / 9 float2), XOR-swizzled u;
+//   * output: two samples x two channels per lane as one float4 store, a warp writes 512 contiguous bytes.
 // No tensor cores: the IMDCT is FFT-structured, not a dense contraction.
 #if !defined(NVB_CPU_SHIM)
 #include <cuda_runtime.h>
@@ -22,19 +26,46 @@
 
 namespace nvb {
 
-constexpr int FUSED_THREADS = 256;
-constexpr int FUSED_WARPS = FUSED_THREADS / 32;
+constexpr int FUSED_WARPS = 16;
+constexpr int FUSED_THREADS = FUSED_WARPS * 32;
+constexpr size_t FUSED_SMEM_LIMIT = 227 * 1024;
 
 struct FusedParams {
     LaunchArgs a;
     int frames_per_cta;
-    int G;
+    int n_slots;
 };
 
-__device__ __forceinline__ float clipf(float v, int& clipped) {
-    float c = fminf(fmaxf(v, -0.99999994f), 0.99999994f);
-    if (c != v) clipped = 1;
-    return c;
+#if !defined(NVB_CPU_SHIM)
+// ---- mbarrier / bulk-copy primitives (PTX) ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// One thread: global -> shared bulk copy (TMA), completion counted in bytes on `bar`.
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+#endif
+
+__device__ __forceinline__ float clipf(float v, float& peak) {
+    peak = fmaxf(peak, fabsf(v));
+    return fminf(fmaxf(v, -0.99999994f), 0.99999994f);                       // Utils.ClipValue, Utils.cs:30-43
 }
 
 // Windowed block value z[i] = y[i] * window[i] of the block held in `slot` (Mode.cs:159-166).
@@ -43,105 +74,116 @@ __device__ __forceinline__ float slot_z(const DevSetup& S, const DevFrame& f, co
     return fused_y(slot, exec, f.n, i) * frame_window(S, f)[i];
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 2) k_imdct_fused(FusedParams p) {
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p) {
     NVB_DYN_SMEM(smem_raw);
     const LaunchArgs& a = p.a;
     const DevSetup& S = a.S;
     const int C = S.channels;
-    const int G = p.G;
+    const int NS = p.n_slots;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    float2* s_tw1  = reinterpret_cast<float2*>(smem_raw);           // 512
-    float2* s_w512 = s_tw1 + 512;                                   // 512
-    float2* s_tw0  = s_w512 + 512;                                  // 64
-    float2* s_w64  = s_tw0 + 64;                                    // 64
-    float*  s_win  = reinterpret_cast<float*>(s_w64 + 64);          // 1024: rising long slope
-    float*  s_slots = s_win + 1024;                                 // (G+1)*C slots
-    DevFrame* s_fr = reinterpret_cast<DevFrame*>(s_slots + (size_t)(G + 1) * C * FUSED_SLOT_FLOATS);
+    float* s_tab = reinterpret_cast<float*>(smem_raw);
+    float* s_slots = s_tab + FusedTables::FLOATS;
+    DevFrame* s_fr = reinterpret_cast<DevFrame*>(s_slots + (size_t)NS * C * FUSED_SLOT_FLOATS);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_fr + NS);
+    uint64_t* s_empty = s_full + NS;
+    uint64_t* s_tabbar = s_empty + NS;
 
     const int lo = blockIdx.x * p.frames_per_cta;
     int hi = lo + p.frames_per_cta; if (hi > a.n_frames) hi = a.n_frames;
     if (lo >= hi) return;
 
-    for (int i = tid; i < 512; i += FUSED_THREADS) { s_tw1[i] = S.tw[1][i]; s_w512[i] = S.fft[1][i]; }
-    if (tid < 64) { s_tw0[tid] = S.tw[0][tid]; s_w64[tid] = S.fft[0][tid]; }
-    for (int i = tid; i < 1024; i += FUSED_THREADS) s_win[i] = S.win_long[3 * (size_t)S.bs[1] + i];
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 2); }
+        mbar_init(s_tabbar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) bulk_load(s_tab, S.fused_tab, FusedTables::FLOATS * sizeof(float), s_tabbar);
 
     int first = lo;
     {
         const DevFrame f0 = a.frames[lo];
         if (f0.prev >= 0 && (f0.ola_len > 0 || f0.kind != 0)) first = lo - 1;   // halo: previous block's tail is needed
     }
-    int clipped = 0;
+    mbar_wait(s_tabbar, 0);
 
-    for (int base = first; base < hi; base += G) {
-        int cnt = hi - base; if (cnt > G) cnt = G;
-        __syncthreads();                                   // previous output phase done with s_fr / slots
-        if (tid < cnt) s_fr[(base + tid - first) % (G + 1)] = a.frames[base + tid];
-        __syncthreads();
+    const float2* s_tw0 = reinterpret_cast<const float2*>(s_tab + FusedTables::TW0);
+    const float2* s_w64 = reinterpret_cast<const float2*>(s_tab + FusedTables::W64);
+    const float* s_win = s_tab + FusedTables::WIN;
+    // swizzled float offsets of this lane's sample pair inside a run of 64 (forward / mirrored), see the fast path
+    const int L2 = 2 * lane;
+    const int A0 = L2 ^ ((lane >> 4) << 2), A8 = A0 ^ 8;
+    const int Bm = 62 - L2;
+    const int B0 = Bm ^ ((Bm >> 5) << 2), B8 = B0 ^ 8;
+    float peak = 0.f;
 
-        // ---------------- transform phase: one warp per (frame, channel) -------------------------
-        for (int x = warp; x < cnt * C; x += FUSED_WARPS) {
-            const int fi = x / C, c = x - fi * C;
-            const int r = (base + fi - first) % (G + 1);
-            const DevFrame& f = s_fr[r];
-            if (f.kind != 0) continue;
-            float* slot = s_slots + (size_t)(r * C + c) * FUSED_SLOT_FLOATS;
-            const int M = f.n >> 1;
-            const float* spec = a.spectrum + (size_t)f.spec_off + (size_t)c * M;
-            if (!((f.exec_mask >> c) & 1u)) {
-                for (int i = lane; i < M; i += 32) slot[i] = spec[i];         // raw residue values (Mapping.cs:192-196)
-            } else if (f.n == FUSED_LONG_N) {
-                float2* ex = reinterpret_cast<float2*>(slot);
-                LongRegs R;
-                long_phase1(lane, reinterpret_cast<const float2*>(spec), s_tw1, s_w512, ex);
-                __syncwarp();
-                long_phase2_load(lane, ex, R);
-                __syncwarp();
-                long_phase2_store(lane, s_w512, ex, R);
-                __syncwarp();
-                long_phase3_load(lane, ex, R);
-                __syncwarp();
-                long_phase3_store(lane, s_tw1, ex, R);
-            } else {
-                ShortRegs R;
-                short_phase1(lane, spec, s_tw0, s_w64, R);
-                #pragma unroll
-                for (int s = 16; s >= 1; s >>= 1) {
-                    cpx pa, pb;
-                    pa.x = __shfl_xor_sync(0xffffffffu, R.a.x, s); pa.y = __shfl_xor_sync(0xffffffffu, R.a.y, s);
-                    pb.x = __shfl_xor_sync(0xffffffffu, R.b.x, s); pb.y = __shfl_xor_sync(0xffffffffu, R.b.y, s);
-                    R.a = short_stage(lane, s, R.a, pa, s_w64);
-                    R.b = short_stage(lane, s, R.b, pb, s_w64);
+    for (int x = first + warp; x < hi; x += FUSED_WARPS) {
+        const int rel = x - first, slot = rel % NS;
+        mbar_wait(&s_empty[slot], ((rel / NS) & 1) ^ 1);                     // both readers of the slot's previous frame are done
+        if (lane == 0) s_fr[slot] = a.frames[x];
+        __syncwarp();
+        const DevFrame f = s_fr[slot];
+        float* slots_f = s_slots + (size_t)slot * C * FUSED_SLOT_FLOATS;
+
+        // ---------------- transform: every channel of frame x -------------------------------------
+        if (f.kind == 0) {
+            for (int c = 0; c < C; c++) {
+                float* slotc = slots_f + (size_t)c * FUSED_SLOT_FLOATS;
+                const int M = f.n >> 1;
+                const float* spec = a.spectrum + (size_t)f.spec_off + (size_t)c * M;
+                if (!((f.exec_mask >> c) & 1u)) {
+                    for (int i = lane; i < M; i += 32) slotc[i] = spec[i];         // raw residue values (Mapping.cs:192-196)
+                } else if (f.n == FUSED_LONG_N) {
+                    float2* ex = reinterpret_cast<float2*>(slotc);
+                    LongRegs R;
+                    long_phase1(lane, reinterpret_cast<const float2*>(spec), s_tab, ex);
+                    __syncwarp();
+                    long_phase2_load(lane, ex, R);
+                    __syncwarp();
+                    long_phase2_store(lane, s_tab, ex, R);
+                    __syncwarp();
+                    long_phase3_load(lane, ex, R);
+                    __syncwarp();
+                    long_phase3_store(lane, s_tab, ex, R);
+                } else {
+                    ShortRegs R;
+                    short_phase1(lane, spec, s_tw0, s_w64, R);
+                    #pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) {
+                        cpx pa, pb;
+                        pa.x = __shfl_xor_sync(0xffffffffu, R.a.x, s); pa.y = __shfl_xor_sync(0xffffffffu, R.a.y, s);
+                        pb.x = __shfl_xor_sync(0xffffffffu, R.b.x, s); pb.y = __shfl_xor_sync(0xffffffffu, R.b.y, s);
+                        R.a = short_stage(lane, s, R.a, pa, s_w64);
+                        R.b = short_stage(lane, s, R.b, pb, s_w64);
+                    }
+                    short_phase3_store(lane, s_tw0, slotc, R);
                 }
-                short_phase3_store(lane, s_tw0, slot, R);
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_full[slot]);                           // u of frame x is complete
 
-        // ---------------- output phase: all threads, frame by frame ------------------------------
-        for (int fi = 0; fi < cnt; fi++) {
-            const int x = base + fi;
-            if (x < lo) continue;                                              // halo block: tail only
-            const int r = (x - first) % (G + 1);
-            const DevFrame& f = s_fr[r];
+        // ---------------- output of frame x (a halo block only leaves its tail) --------------------
+        if (x >= lo) {
             const int len = f.out_end - f.out_begin;
-            const float* slots_f = s_slots + (size_t)r * C * FUSED_SLOT_FLOATS;
             const DevFrame* pf = nullptr; const float* slots_p = nullptr;
             if (f.prev >= 0 && (f.ola_len > 0 || f.kind != 0)) {
-                const int rp = (f.prev - first) % (G + 1);
-                pf = &s_fr[rp]; slots_p = s_slots + (size_t)rp * C * FUSED_SLOT_FLOATS;
+                const int prel = f.prev - first, pslot = prel % NS;
+                mbar_wait(&s_full[pslot], (prel / NS) & 1);
+                pf = &s_fr[pslot]; slots_p = s_slots + (size_t)pslot * C * FUSED_SLOT_FLOATS;
             }
             const bool fast = (C == 2) && f.kind == 0 && pf && f.n == FUSED_LONG_N && pf->n == FUSED_LONG_N && f.window == 3 &&
                               (pf->window & 2) && f.start == 0 && f.out_begin == 0 && f.out_end == 1024 && f.ola_len == 1024 &&
-                              f.prev_valid == 1024 && f.exec_mask == 3u && pf->exec_mask == 3u && a.clip;
+                              f.prev_valid == 1024 && f.exec_mask == 3u && pf->exec_mask == 3u && pf->kind == 0 && ((f.pcm_off & 1) == 0);
             if (fast) {
                 // long block after long block, both channels live (Mode.cs:44-50 window 3):
                 // out[i] = S[i]*yL[i] + S[1023-i]*yR[i],  yL from this block's u, yR from the previous block's u
-                float* out = a.pcm + (size_t)f.pcm_off * 2;
-                const bool al16 = (f.pcm_off & 1) == 0;
-                for (int q = tid; q < 512; q += FUSED_THREADS) {
-                    const int i = 2 * q;
+                float4* out = reinterpret_cast<float4*>(a.pcm + (size_t)f.pcm_off * 2) + lane;
+                const bool clip = a.clip != 0;
+                #pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const int i = L2 + 64 * k;
                     const float2 wl = *reinterpret_cast<const float2*>(s_win + i);
                     const float2 wr = *reinterpret_cast<const float2*>(s_win + 1022 - i);   // (S[1022-i], S[1023-i])
                     float o[4];
@@ -149,25 +191,25 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_imdct_fused(FusedParams p)
                     for (int c = 0; c < 2; c++) {
                         const float* uf = slots_f + c * FUSED_SLOT_FLOATS;
                         const float* up = slots_p + c * FUSED_SLOT_FLOATS;
-                        float yl0, yl1, yr0, yr1;
-                        if (i < 512) {
-                            const float2 l2 = *reinterpret_cast<const float2*>(uf + 512 + i);
-                            const float2 r2 = *reinterpret_cast<const float2*>(up + 510 - i);
-                            yl0 = l2.x; yl1 = l2.y; yr0 = -r2.y; yr1 = -r2.x;
+                        float yl0, yl1, nr0, nr1;                           // nr = -yR
+                        if (k < 8) {
+                            const float2 l2 = *reinterpret_cast<const float2*>(uf + 512 + 64 * k + ((k & 1) ? A8 : A0));    // u[512+i], u[513+i]
+                            const float2 r2 = *reinterpret_cast<const float2*>(up + 448 - 64 * k + ((k & 1) ? B0 : B8));    // u'[510-i], u'[511-i]
+                            yl0 = l2.x; yl1 = l2.y; nr0 = r2.y; nr1 = r2.x;
                         } else {
-                            const float2 l2 = *reinterpret_cast<const float2*>(uf + 1534 - i);
-                            const float2 r2 = *reinterpret_cast<const float2*>(up + i - 512);
-                            yl0 = -l2.y; yl1 = -l2.x; yr0 = -r2.x; yr1 = -r2.y;
+                            const float2 l2 = *reinterpret_cast<const float2*>(uf + 1472 - 64 * k + ((k & 1) ? B0 : B8));   // u[1534-i], u[1535-i]
+                            const float2 r2 = *reinterpret_cast<const float2*>(up + 64 * k - 512 + ((k & 1) ? A8 : A0));    // u'[i-512], u'[i-511]
+                            yl0 = -l2.y; yl1 = -l2.x; nr0 = r2.x; nr1 = r2.y;
                         }
-                        o[c]     = clipf(fmaf(wl.x, yl0, wr.y * yr0), clipped);
-                        o[2 + c] = clipf(fmaf(wl.y, yl1, wr.x * yr1), clipped);
+                        o[c]     = fmaf(wl.x, yl0, -(wr.y * nr0));
+                        o[2 + c] = fmaf(wl.y, yl1, -(wr.x * nr1));
                     }
-                    if (al16) *reinterpret_cast<float4*>(out + 2 * i) = make_float4(o[0], o[1], o[2], o[3]);
-                    else { *reinterpret_cast<float2*>(out + 2 * i) = make_float2(o[0], o[1]); *reinterpret_cast<float2*>(out + 2 * i + 2) = make_float2(o[2], o[3]); }
+                    if (clip) { o[0] = clipf(o[0], peak); o[1] = clipf(o[1], peak); o[2] = clipf(o[2], peak); o[3] = clipf(o[3], peak); }
+                    out[32 * k] = make_float4(o[0], o[1], o[2], o[3]);
                 }
             } else if (len > 0) {
                 const int total = len * C;
-                for (int idx = tid; idx < total; idx += FUSED_THREADS) {
+                for (int idx = lane; idx < total; idx += 32) {
                     const int s = idx / C, c = idx - s * C;
                     const int i = f.out_begin + s;
                     float v;
@@ -181,38 +223,49 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_imdct_fused(FusedParams p)
                     } else {                                                                  // drain, StreamDecoder.cs:352-356
                         v = pf ? slot_z(S, *pf, slots_p + c * FUSED_SLOT_FLOATS, c, i) : a.carry_in[(size_t)c * S.bs[1] + i];
                     }
-                    if (a.clip) v = clipf(v, clipped);
+                    if (a.clip) v = clipf(v, peak);
                     a.pcm[((size_t)f.pcm_off + s) * C + c] = v;
                 }
             }
             if (x == a.carry_frame && a.carry_out && f.kind == 0) {
                 // keep the last windowed block for the next batch (StreamDecoder.cs:455-461)
-                for (int idx = tid; idx < f.n * C; idx += FUSED_THREADS) {
+                for (int idx = lane; idx < f.n * C; idx += 32) {
                     const int c = idx / f.n, i = idx - c * f.n;
                     a.carry_out[(size_t)c * S.bs[1] + i] = slot_z(S, f, slots_f + c * FUSED_SLOT_FLOATS, c, i);
                 }
             }
         }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&s_empty[slot]);                                     // done with frame x as "current"
+            if (rel >= 1) mbar_arrive(&s_empty[(rel - 1) % NS]);             // done with frame x-1 as "previous"
+        }
     }
-    if (__syncthreads_or(clipped) && tid == 0) atomicOr(&a.counters->clipped, 1);
+    if (__any_sync(0xffffffffu, peak > 0.99999994f) && lane == 0) atomicOr(&a.counters->clipped, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
-static int fused_group(int C) { int g = 8 / C; return g < 1 ? 1 : g; }
-static size_t fused_smem(int C, int G) {
-    return (size_t)(512 + 512 + 64 + 64) * sizeof(float2) + 1024 * sizeof(float) +
-           (size_t)(G + 1) * C * FUSED_SLOT_FLOATS * sizeof(float) + (size_t)(G + 1) * sizeof(DevFrame);
+static int fused_slots(int C) {
+    const size_t fixed = FusedTables::FLOATS * sizeof(float) + 64;
+    const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(uint64_t);
+    int ns = (int)((FUSED_SMEM_LIMIT - fixed) / per);
+    if (ns > FUSED_WARPS + 2) ns = FUSED_WARPS + 2;
+    return ns;
+}
+static size_t fused_smem(int C, int NS) {
+    return FusedTables::FLOATS * sizeof(float) + (size_t)NS * ((size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(uint64_t)) + 16;
 }
 
 bool fused_supported(const BlobHeader& h, const DevFrame*, int) {
-    return h.bs[1] == FUSED_LONG_N && h.bs[0] == FUSED_SHORT_N && h.channels >= 1 && h.channels <= NVB_MAX_CHANNELS;
+    return h.bs[1] == FUSED_LONG_N && h.bs[0] == FUSED_SHORT_N && h.off_fused_tab != 0 && h.channels >= 1 && h.channels <= NVB_MAX_CHANNELS &&
+           fused_slots(h.channels) >= 3;
 }
 
 int launch_imdct_fused(const LaunchArgs& a, const DevFrame*, void* stream) {
     if (a.n_frames <= 0) return 0;
     const int C = a.S.channels;
-    FusedParams p; p.a = a; p.G = fused_group(C);
-    const size_t smem = fused_smem(C, p.G);
+    FusedParams p; p.a = a; p.n_slots = fused_slots(C);
+    const size_t smem = fused_smem(C, p.n_slots);
     static size_t configured = 0;
     static int num_sms = 0;
     if (smem > configured) {
@@ -223,11 +276,9 @@ int launch_imdct_fused(const LaunchArgs& a, const DevFrame*, void* stream) {
         int dev = 0; cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
-    // contiguous run of frames per CTA: enough CTAs for ~2 resident per SM, runs a multiple of G
-    const int target_ctas = num_sms * 2;
-    int fpc = (a.n_frames + target_ctas - 1) / target_ctas;
-    fpc = ((fpc + p.G - 1) / p.G) * p.G;
-    if (fpc < p.G) fpc = p.G;
+    // persistent: one CTA per SM, each a contiguous run of frames (at least 8, so that the halo block stays cheap)
+    int fpc = (a.n_frames + num_sms - 1) / num_sms;
+    if (fpc < 8) fpc = 8;
     p.frames_per_cta = fpc;
     const int grid = (a.n_frames + fpc - 1) / fpc;
     NVB_LAUNCH(k_imdct_fused, grid, FUSED_THREADS, smem, stream, p);

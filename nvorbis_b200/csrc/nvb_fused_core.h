@@ -1,7 +1,6 @@
 // nvb_fused_core.h -- lane-level arithmetic of the fused IMDCT + window + OLA + clip + interleave
 // kernel (nvb_fused.cu).  Written as phases of one warp: every phase is a function of
-// (lane, registers, shared memory) with a warp barrier between phases, so tests/cpu_shim.cpp can
-// replay a warp on the host lane by lane.
+// (lane, registers, shared memory) with a warp barrier between phases.
 //
 // IMDCT factorisation (M = N/2 coefficients, Q = N/4 complex points; reproduces what Mdct.Reverse
 // computes for N >= 256, i.e. y[i] = sum_k X[k] cos(2pi/N (i + 1/2 + N/4)(k + 1/2)), Mdct.cs:65-313):
@@ -10,6 +9,11 @@
 //   y[i] = u[i+M/2] (i < M/2);  -u[3M/2-1-i] (M/2 <= i < 3M/2);  -u[i-3M/2] (i >= 3M/2)
 // This path may contract to FMA; it is held to <= 1e-5 max-abs against the reference arithmetic (the exact
 // path in nvb_kernels.cu is the bit-identical one).
+//
+// Long block (N = 2048, Q = 512 = 8*8*8): one warp, 16 points per lane as two radix-8 columns, three
+// passes with two exchanges through shared memory.  Every twiddle a lane needs is the same for every
+// transform, so the host lays the twiddles out per lane ("lane tables", FusedTables below): each load is
+// a conflict-free LDS.128 of consecutive lanes.
 #pragma once
 #include "nvb_device_core.h"
 
@@ -42,41 +46,64 @@ constexpr int FUSED_SLOT_FLOATS = 1152;        // 8 rows * 72 float2 of exchange
 constexpr int FUSED_LONG_N = 2048;
 constexpr int FUSED_SHORT_N = 256;
 
+// Lane tables for N = 2048 / 256, built on the host (nvb_host.cpp: build_fused_tables), one contiguous block
+// so that the kernel stages it with a single bulk copy.  Offsets in floats:
+struct FusedTables {
+    static constexpr int T1 = 0;        // [8][32] float4: pre-twiddles tw[64 k2 + l], tw[64 k2 + 63 - l]
+    static constexpr int T2 = 1024;     // [7][32] float4: W512^(l m2), W512^((63-l) m2), m2 = 1..7
+    static constexpr int T3 = 1920;     // [4][32] float4: W64^(k0 m1) for m1 = 2j+1, 2j+2 (k0 = l & 7)
+    static constexpr int T4 = 2432;     // [8][32] float4: post-twiddles tw[na0 + 64 m0], tw[nb0 + 64 m0]
+    static constexpr int WIN = 3456;    // [1024] rising slope of the long/long window (Mode.cs:80-85)
+    static constexpr int TW0 = 4480;    // [64] float2: short-block twiddles exp(-i pi (k + 1/8) / 128)
+    static constexpr int W64 = 4608;    // [64] float2: exp(-2 pi i k / 64)
+    static constexpr int FLOATS = 4736;
+};
+NVB_HD int fused_na0(int l) { return (l >> 3) + 8 * (l & 7); }
+NVB_HD int fused_nb0(int l) { return (7 - (l >> 3)) + 8 * (7 - (l & 7)); }
+
+// u of an executed long block is stored swizzled: float2 index n -> n ^ (((n >> 4) & 3) << 1).  That makes the
+// phase-3 stores (lanes 8 apart in n) and the output reads (lanes adjacent in n) both bank-conflict free, and
+// keeps aligned groups of four floats contiguous (LDS.128 in the output loop).
+NVB_HD int u_swz2(int n) { return n ^ (((n >> 4) & 3) << 1); }                  // float2 index
+NVB_HD int u_swz(int i) { return i ^ (((i >> 5) & 3) << 2); }                   // float index
+
+NVB_HD cpx ld_cpx(const float4& v, int hi) { cpx r; r.x = hi ? v.z : v.x; r.y = hi ? v.w : v.y; return r; }
+
 // Registers of one lane while it transforms one long block: two radix-8 columns.
 struct LongRegs { cpx a[8]; cpx b[8]; };
 
 // ---- phase 1: load spectrum pairs, pre-twiddle, radix-8 over k2, twiddle W512^(r*m2), store ex1
-// spec2: the channel's spectrum as float2[512]; tw, w512: float2[512] tables; ex: float2[576].
-NVB_HD void long_phase1(int l, const float2* spec2, const float2* tw, const float2* w512, float2* ex) {
+// spec2: the channel's spectrum as float2[512]; tab: FusedTables in shared memory; ex: float2[576].
+NVB_HD void long_phase1(int l, const float2* spec2, const float* tab, float2* ex) {
     const int ra = l, rb = 63 - l;
     float2 pa[8], pb[8];
     #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) { pa[k2] = spec2[64 * k2 + ra]; pb[k2] = spec2[64 * k2 + rb]; }
+    const float4* T1 = reinterpret_cast<const float4*>(tab + FusedTables::T1);
+    const float4* T2 = reinterpret_cast<const float4*>(tab + FusedTables::T2);
     LongRegs R;
     #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) {
-        cpx ca, cb, t;
+        cpx ca, cb;
         ca.x = pa[k2].x; ca.y = pb[7 - k2].y;          // X[2k] + i X[M-1-2k], k = 64 k2 + l
         cb.x = pb[k2].x; cb.y = pa[7 - k2].y;          // k = 64 k2 + 63 - l
-        float2 wa = tw[64 * k2 + ra], wb = tw[64 * k2 + rb];
-        t.x = wa.x; t.y = wa.y; R.a[k2] = cmul(ca, t);
-        t.x = wb.x; t.y = wb.y; R.b[k2] = cmul(cb, t);
+        const float4 w = T1[k2 * 32 + l];
+        R.a[k2] = cmul(ca, ld_cpx(w, 0));
+        R.b[k2] = cmul(cb, ld_cpx(w, 1));
     }
     fft8(R.a); fft8(R.b);
+    ex[ra] = make_float2(R.a[0].x, R.a[0].y);
+    ex[rb] = make_float2(R.b[0].x, R.b[0].y);
     #pragma unroll
-    for (int m2 = 0; m2 < 8; m2++) {
-        cpx va = R.a[m2], vb = R.b[m2];
-        if (m2 > 0) {
-            float2 wa = w512[(ra * m2) & 511], wb = w512[(rb * m2) & 511];
-            cpx t; t.x = wa.x; t.y = wa.y; va = cmul(va, t);
-            t.x = wb.x; t.y = wb.y; vb = cmul(vb, t);
-        }
+    for (int m2 = 1; m2 < 8; m2++) {
+        const float4 w = T2[(m2 - 1) * 32 + l];
+        const cpx va = cmul(R.a[m2], ld_cpx(w, 0)), vb = cmul(R.b[m2], ld_cpx(w, 1));
         ex[m2 * 72 + ra] = make_float2(va.x, va.y);
         ex[m2 * 72 + rb] = make_float2(vb.x, vb.y);
     }
 }
 
-// ---- phase 2: (a) gather the 8 k1 of (m2, k0) for two m2; (b) radix-8 over k1, twiddle W64^(k0*m1), store ex2
+// ---- phase 2: gather the 8 k1 of (m2, k0) for two m2; radix-8 over k1, twiddle W64^(k0*m1), store ex2
 NVB_HD void long_phase2_load(int l, const float2* ex, LongRegs& R) {
     const int m2 = l >> 3, k0 = l & 7;
     #pragma unroll
@@ -85,23 +112,29 @@ NVB_HD void long_phase2_load(int l, const float2* ex, LongRegs& R) {
         R.a[k1].x = va.x; R.a[k1].y = va.y; R.b[k1].x = vb.x; R.b[k1].y = vb.y;
     }
 }
-NVB_HD void long_phase2_store(int l, const float2* w512, float2* ex, LongRegs& R) {
+NVB_HD void long_phase2_store(int l, const float* tab, float2* ex, LongRegs& R) {
     const int m2 = l >> 3, k0 = l & 7;
+    const float4* T3 = reinterpret_cast<const float4*>(tab + FusedTables::T3);
     fft8(R.a); fft8(R.b);
+    ex[m2 * 72 + k0] = make_float2(R.a[0].x, R.a[0].y);
+    ex[(m2 + 4) * 72 + k0] = make_float2(R.b[0].x, R.b[0].y);
     #pragma unroll
-    for (int m1 = 0; m1 < 8; m1++) {
-        cpx va = R.a[m1], vb = R.b[m1];
-        if (m1 > 0) {
-            float2 w = w512[(8 * k0 * m1) & 511];
-            cpx t; t.x = w.x; t.y = w.y; va = cmul(va, t); vb = cmul(vb, t);
+    for (int j = 0; j < 4; j++) {
+        const float4 w = T3[j * 32 + l];
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m1 = 2 * j + 1 + h;
+            if (m1 > 7) break;
+            const cpx t = ld_cpx(w, h);
+            const cpx va = cmul(R.a[m1], t), vb = cmul(R.b[m1], t);
+            ex[m2 * 72 + m1 * 9 + k0] = make_float2(va.x, va.y);
+            ex[(m2 + 4) * 72 + m1 * 9 + k0] = make_float2(vb.x, vb.y);
         }
-        ex[m2 * 72 + m1 * 9 + k0] = make_float2(va.x, va.y);
-        ex[(m2 + 4) * 72 + m1 * 9 + k0] = make_float2(vb.x, vb.y);
     }
 }
 
-// ---- phase 3: (a) gather the 8 k0 of (m2, m1) and of (7-m2, 7-m1); (b) radix-8 over k0, post-twiddle,
-// write u as float2 pairs (u[2n], u[2n+1]) = (Re D[n], -Im D[511-n]).
+// ---- phase 3: gather the 8 k0 of (m2, m1) and of (7-m2, 7-m1); radix-8 over k0, post-twiddle,
+// write u as float2 pairs (u[2n], u[2n+1]) = (Re D[n], -Im D[511-n]), swizzled (u_swz2).
 NVB_HD void long_phase3_load(int l, const float2* ex, LongRegs& R) {
     const int m2 = l >> 3, m1 = l & 7;
     #pragma unroll
@@ -110,21 +143,22 @@ NVB_HD void long_phase3_load(int l, const float2* ex, LongRegs& R) {
         R.a[k0].x = va.x; R.a[k0].y = va.y; R.b[k0].x = vb.x; R.b[k0].y = vb.y;
     }
 }
-NVB_HD void long_phase3_store(int l, const float2* tw, float2* u2, LongRegs& R) {
-    const int m2 = l >> 3, m1 = l & 7;
+NVB_HD void long_phase3_store(int l, const float* tab, float2* u2, LongRegs& R) {
+    const float4* T4 = reinterpret_cast<const float4*>(tab + FusedTables::T4);
     fft8(R.a); fft8(R.b);
-    const int na0 = m2 + 8 * m1, nb0 = (7 - m2) + 8 * (7 - m1);
     #pragma unroll
     for (int m0 = 0; m0 < 8; m0++) {
-        float2 wa = tw[na0 + 64 * m0], wb = tw[nb0 + 64 * m0];
-        cpx t; t.x = wa.x; t.y = wa.y; R.a[m0] = cmul(R.a[m0], t);
-        t.x = wb.x; t.y = wb.y; R.b[m0] = cmul(R.b[m0], t);
+        const float4 w = T4[m0 * 32 + l];
+        R.a[m0] = cmul(R.a[m0], ld_cpx(w, 0));
+        R.b[m0] = cmul(R.b[m0], ld_cpx(w, 1));
     }
+    // n = na0 + 64 m0 and its partner 511 - n = nb0 + 64 (7 - m0), nb0 = 63 - na0; the swizzle only looks at
+    // bits 4-5 of n, which belong to na0 / nb0
+    const int sa = u_swz2(fused_na0(l)), sb = u_swz2(fused_nb0(l));
     #pragma unroll
     for (int m0 = 0; m0 < 8; m0++) {
-        const int n = na0 + 64 * m0;                    // partner 511 - n = nb0 + 64 (7 - m0)
-        u2[n] = make_float2(R.a[m0].x, -R.b[7 - m0].y);
-        u2[511 - n] = make_float2(R.b[7 - m0].x, -R.a[m0].y);
+        u2[sa + 64 * m0] = make_float2(R.a[m0].x, -R.b[7 - m0].y);
+        u2[sb + 64 * (7 - m0)] = make_float2(R.b[7 - m0].x, -R.a[m0].y);
     }
 }
 
@@ -162,12 +196,16 @@ NVB_HD void short_phase3_store(int l, const float2* tw64, float* u, const ShortR
 
 // ---- output side ------------------------------------------------------------------------------------
 // Un-windowed block value y[i] of a slot: u (executed channel) or the raw spectrum (Mapping.cs:192-196).
+// Only the u of an executed long block is swizzled.
 NVB_HD float fused_y(const float* slot, bool exec, int N, int i) {
     const int M = N >> 1, h = M >> 1;
     if (!exec) return i < M ? slot[i] : 0.f;
-    if (i < h) return slot[i + h];
-    if (i < M + h) return -slot[M + h - 1 - i];
-    return -slot[i - M - h];
+    int j; float sgn;
+    if (i < h) { j = i + h; sgn = 1.f; }
+    else if (i < M + h) { j = M + h - 1 - i; sgn = -1.f; }
+    else { j = i - M - h; sgn = -1.f; }
+    if (N == FUSED_LONG_N) j = u_swz(j);
+    return sgn * slot[j];
 }
 
 }  // namespace nvb

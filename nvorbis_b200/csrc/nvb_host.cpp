@@ -6,7 +6,7 @@
 // Batch planning restates the bookkeeping of StreamDecoder.ReadNextPacket (StreamDecoder.cs:417-463)
 // and the drain rule of StreamDecoder.Read (StreamDecoder.cs:352-356) as a prefix computation.
 #include "nvb_host.h"
-#include "nvb_device_core.h"
+#include "nvb_fused_core.h"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -94,6 +94,26 @@ void fast_tables(int n, float2* tw, float2* fft) {
     }
 }
 
+// Lane tables of the fused kernel (FusedTables, nvb_fused_core.h) from the plain twiddle tables.
+void build_fused_tables(const float2* tw1, const float2* w512, const float2* tw0, const float2* w64, const float* slope_long, float* out) {
+    auto put = [&](int base, int row, int lane, float2 a, float2 b) {
+        float* p = out + base + (row * 32 + lane) * 4;
+        p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
+    };
+    for (int l = 0; l < 32; l++) {
+        const int ra = l, rb = 63 - l, k0 = l & 7;
+        for (int k2 = 0; k2 < 8; k2++) put(FusedTables::T1, k2, l, tw1[64 * k2 + ra], tw1[64 * k2 + rb]);
+        for (int m2 = 1; m2 < 8; m2++) put(FusedTables::T2, m2 - 1, l, w512[(ra * m2) & 511], w512[(rb * m2) & 511]);
+        for (int j = 0; j < 4; j++) put(FusedTables::T3, j, l, w512[(8 * k0 * (2 * j + 1)) & 511], w512[(8 * k0 * (2 * j + 2)) & 511]);
+        for (int m0 = 0; m0 < 8; m0++) put(FusedTables::T4, m0, l, tw1[fused_na0(l) + 64 * m0], tw1[fused_nb0(l) + 64 * m0]);
+    }
+    for (int i = 0; i < 1024; i++) out[FusedTables::WIN + i] = slope_long[i];
+    for (int k = 0; k < 64; k++) {
+        out[FusedTables::TW0 + 2 * k] = tw0[k].x; out[FusedTables::TW0 + 2 * k + 1] = tw0[k].y;
+        out[FusedTables::W64 + 2 * k] = w64[k].x; out[FusedTables::W64 + 2 * k + 1] = w64[k].y;
+    }
+}
+
 int fail(std::string& err, int code, const char* fmt, long long a = 0, long long b = 0) {
     char tmp[256];
     std::snprintf(tmp, sizeof tmp, fmt, a, b);
@@ -116,7 +136,7 @@ Overlap nominal_overlap(const BlobHeader& h, int block_flag, int window) {
 
 void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) {
     S.channels = h.channels; S.bs[0] = h.bs[0]; S.bs[1] = h.bs[1];
-    S.post_stride = h.post_stride; S.max_items = h.max_items;
+    S.post_stride = h.post_stride; S.max_items = h.max_items; S.spectrum_fast = h.spectrum_fast;
     S.books = reinterpret_cast<const DevBook*>(base + h.off_books);
     S.vq = reinterpret_cast<const float*>(base + h.off_vq); S.n_vq = (int64_t)h.n_vq;
     S.floors = reinterpret_cast<const DevFloor1*>(base + h.off_floors);
@@ -134,6 +154,7 @@ void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) 
         S.fft[i] = reinterpret_cast<const float2*>(base + h.off_fft[i]);
     }
     S.db = reinterpret_cast<const float*>(base + h.off_db);
+    S.fused_tab = h.off_fused_tab ? reinterpret_cast<const float*>(base + h.off_fused_tab) : nullptr;
 }
 
 int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string& err) {
@@ -228,8 +249,9 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
 
     h.off_books = w.reserve(sizeof(DevBook) * s->n_books);
     for (int i = 0; i < s->n_books; i++) {
-        DevBook d; d.dims = s->books[i].dims; d.entries = s->books[i].entries;
+        DevBook d; d.dims = s->books[i].dims; d.entries = s->books[i].entries; d.pad = 0;
         d.off = (s->books[i].map_type != 0) ? s->books[i].table_off : -1;
+        d.dshift = is_pow2(d.dims) ? ilog_u(d.dims) - 1 : -1;
         w.at<DevBook>(h.off_books)[i] = d;
     }
     h.off_vq = w.reserve(sizeof(float) * (size_t)(s->n_vq_floats > 0 ? s->n_vq_floats : 1));
@@ -240,6 +262,11 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         DevFloor1 d; std::memset(&d, 0, sizeof d);
         d.n_posts = g.n_posts; d.mult = g.multiplier; d.range = g.range;
         for (int k = 0; k < g.n_posts; k++) { d.x[k] = g.x_list[k]; d.lo[k] = g.l_neigh[k]; d.hi[k] = g.h_neigh[k]; d.sort[k] = g.sort_idx[k]; }
+        for (int k = 2; k < g.n_posts; k++) {                           // neighbours always precede the post (validated above)
+            const int lv = 1 + (d.level[d.lo[k]] > d.level[d.hi[k]] ? d.level[d.lo[k]] : d.level[d.hi[k]]);
+            d.level[k] = (uint8_t)lv;
+            if (lv > d.max_level) d.max_level = lv;
+        }
         w.at<DevFloor1>(h.off_floors)[i] = d;
     }
     h.off_residues = w.reserve(sizeof(DevResidue) * s->n_residues);
@@ -247,11 +274,24 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         const nvb_residue& r = s->residues[i];
         DevResidue d; std::memset(&d, 0, sizeof d);
         d.type = r.type; d.begin = r.begin; d.end = r.end; d.psize = r.partition_size; d.nclass = r.classifications; d.stages = r.max_stages;
+        d.pshift = is_pow2(r.partition_size) ? ilog_u(r.partition_size) - 1 : -1;
+        bool fast = d.pshift >= 0 && r.partition_size <= 8192 && r.max_stages >= 1;
+        if (r.type == 2 && (r.begin % C != 0 || r.partition_size % C != 0)) fast = false;    // Residue2.cs:27 truncation case
         for (int c = 0; c < NVB_MAX_CLASSES; c++) {
             d.cascade[c] = c < r.classifications ? r.cascade[c] : 0;
-            for (int st = 0; st < NVB_MAX_STAGES; st++)
-                d.books[c][st] = (c < r.classifications && st < r.max_stages && ((r.cascade[c] >> st) & 1)) ? r.books[c][st] : (int16_t)-1;
+            for (int st = 0; st < NVB_MAX_STAGES; st++) {
+                const bool coded = c < r.classifications && st < r.max_stages && ((r.cascade[c] >> st) & 1) && r.books[c][st] >= 0;
+                d.books[c][st] = coded ? r.books[c][st] : (int16_t)-1;
+                d.cnt[c][st] = 0;
+                if (coded) {
+                    const int dims = s->books[r.books[c][st]].dims;
+                    const int cnt = r.type == 0 ? r.partition_size / dims : (r.partition_size + dims - 1) / dims;   // Residue0.cs:183 / Residue1.cs:12 / Residue2.cs:28
+                    if (cnt > 32767 || !is_pow2(dims) || dims > r.partition_size) fast = false;
+                    d.cnt[c][st] = (int16_t)(cnt > 32767 ? 32767 : cnt);
+                }
+            }
         }
+        d.fast = fast ? 1 : 0;
         w.at<DevResidue>(h.off_residues)[i] = d;
     }
     h.off_mappings = w.reserve(sizeof(DevMapping) * s->n_mappings);
@@ -301,6 +341,12 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
     }
     h.off_db = w.reserve(sizeof(float) * 256);
     std::memcpy(w.at<float>(h.off_db), k_inverse_db_bits, sizeof k_inverse_db_bits);
+    if (h.bs[0] == FUSED_SHORT_N && h.bs[1] == FUSED_LONG_N) {
+        h.off_fused_tab = w.reserve(sizeof(float) * FusedTables::FLOATS);
+        // rising slope of window 3 (long block between long blocks): the first 1024 values of that window
+        build_fused_tables(w.at<float2>(h.off_tw[1]), w.at<float2>(h.off_fft[1]), w.at<float2>(h.off_tw[0]), w.at<float2>(h.off_fft[0]),
+                           w.at<float>(h.off_win_long) + 3 * (size_t)h.bs[1], w.at<float>(h.off_fused_tab));
+    }
 
     // largest residue item table over the modes (k_spectrum's shared-memory prefix array)
     {
@@ -314,6 +360,10 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         }
         if (mx > 40000) return fail(err, NVB_ERR_UNSUPPORTED, "residue layout needs %lld prefix items (> 40000)", mx);
         h.max_items = mx;
+        int fast = 1;
+        for (int i = 0; i < h.n_modes; i++) if (!S.residues[S.mappings[S.modes[i].mapping].residue].fast) fast = 0;
+        if ((size_t)mx * 4 + (size_t)C * (h.bs[1] / 2) * 4 > 160 * 1024) fast = 0;      // prefix table + floor curve rows must fit in shared memory
+        h.spectrum_fast = fast;
     }
     w.reserve(0);
     h.total_bytes = blob.size();
@@ -332,7 +382,8 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
     bool ok = in(h.off_books, sizeof(DevBook) * (uint64_t)h.n_books) && in(h.off_vq, sizeof(float) * h.n_vq) &&
               in(h.off_floors, sizeof(DevFloor1) * (uint64_t)h.n_floors) && in(h.off_residues, sizeof(DevResidue) * (uint64_t)h.n_residues) &&
               in(h.off_mappings, sizeof(DevMapping) * (uint64_t)h.n_mappings) && in(h.off_modes, sizeof(DevMode) * (uint64_t)h.n_modes) &&
-              in(h.off_win_short, 4ull * h.bs[0]) && in(h.off_win_long, 16ull * h.bs[1]) && in(h.off_db, 1024);
+              in(h.off_win_short, 4ull * h.bs[0]) && in(h.off_win_long, 16ull * h.bs[1]) && in(h.off_db, 1024) &&
+              (h.off_fused_tab == 0 || (in(h.off_fused_tab, 4ull * FusedTables::FLOATS) && h.bs[0] == FUSED_SHORT_N && h.bs[1] == FUSED_LONG_N));
     for (int i = 0; i < 2 && ok; i++)
         ok = in(h.off_mdct_a[i], 2ull * h.bs[i]) && in(h.off_mdct_b[i], 2ull * h.bs[i]) && in(h.off_mdct_c[i], 1ull * h.bs[i]) &&
              in(h.off_bitrev[i], h.bs[i] / 4ull) && in(h.off_tw[i], 2ull * h.bs[i]) && in(h.off_fft[i], 2ull * h.bs[i]);
@@ -357,11 +408,14 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
             if (bk >= h.n_books) return fail(err, NVB_ERR_DATA, "blob: residue %lld book", i);
             const DevBook& b = S.books[bk];
             if (b.dims < 1 || b.off < 0 || b.off + (int64_t)b.entries * b.dims > (int64_t)h.n_vq) return fail(err, NVB_ERR_DATA, "blob: residue %lld book table", i);
+            if (r.cnt[c][st] < 0 || (r.fast && (b.dshift < 0 || (1 << b.dshift) != b.dims || r.pshift < 0 || (1 << r.pshift) != r.psize)))
+                return fail(err, NVB_ERR_DATA, "blob: residue %lld fast-path fields", i);
         }
     }
     for (int i = 0; i < h.n_floors; i++) {
         const DevFloor1& f = S.floors[i];
-        if (f.n_posts < 2 || f.n_posts > NVB_MAX_POSTS) return fail(err, NVB_ERR_DATA, "blob: floor %lld", i);
+        if (f.n_posts < 2 || f.n_posts > NVB_MAX_POSTS || f.max_level < 0 || f.max_level > NVB_MAX_POSTS) return fail(err, NVB_ERR_DATA, "blob: floor %lld", i);
+        for (int k = 2; k < f.n_posts; k++) if (f.level[k] < 1 || f.level[k] > f.max_level) return fail(err, NVB_ERR_DATA, "blob: floor %lld levels", i);
         for (int k = 0; k < f.n_posts; k++) {
             if (f.sort[k] >= f.n_posts) return fail(err, NVB_ERR_DATA, "blob: floor %lld sort", i);
             if (k >= 2 && (f.lo[k] >= k || f.hi[k] >= k || !(f.x[f.lo[k]] < f.x[k] && f.x[k] < f.x[f.hi[k]]))) return fail(err, NVB_ERR_DATA, "blob: floor %lld neighbours", i);

@@ -21,9 +21,20 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 namespace nvb {
 
 // ---- immutable per-stream tables, as they sit in ONE contiguous device allocation ("blob") ----
-struct DevBook    { int32_t dims, entries; int64_t off; };           // off: float index into vq, -1 = no table
-struct DevFloor1  { int32_t n_posts, mult, range, pad; uint16_t x[NVB_MAX_POSTS]; uint8_t lo[NVB_MAX_POSTS], hi[NVB_MAX_POSTS], sort[NVB_MAX_POSTS]; };
-struct DevResidue { int32_t type, begin, end, psize, nclass, stages; int32_t cascade[NVB_MAX_CLASSES]; int16_t books[NVB_MAX_CLASSES][NVB_MAX_STAGES]; };
+struct DevBook    { int32_t dims, entries; int64_t off; int32_t dshift, pad; };   // off: float index into vq, -1 = no table; dshift = log2(dims) or -1
+struct DevFloor1  {
+    int32_t n_posts, mult, range, max_level;
+    uint16_t x[NVB_MAX_POSTS]; uint8_t lo[NVB_MAX_POSTS], hi[NVB_MAX_POSTS], sort[NVB_MAX_POSTS];
+    uint8_t level[NVB_MAX_POSTS];   // depth of post i in the neighbour dependency tree: 1 + max(level[lo], level[hi]); posts 0, 1 are level 0
+};
+struct DevResidue {
+    int32_t type, begin, end, psize, nclass, stages;
+    int32_t pshift;                 // log2(psize) or -1
+    int32_t fast;                   // 1: k_spectrum_fast applies (power-of-two partition/book sizes, type 2 partitions aligned to the channel count)
+    int32_t cascade[NVB_MAX_CLASSES];
+    int16_t books[NVB_MAX_CLASSES][NVB_MAX_STAGES];
+    int16_t cnt[NVB_MAX_CLASSES][NVB_MAX_STAGES];   // VQ entries one partition of (class, stage) consumes; 0 = nothing coded
+};
 struct DevMapping { int32_t n_coupling, floor, residue, pad; uint8_t mag[NVB_MAX_COUPLING], ang[NVB_MAX_COUPLING]; };
 struct DevMode    { int32_t block_flag, mapping; };
 
@@ -36,7 +47,7 @@ struct BlobHeader {
     int32_t n_books, n_floors, n_residues, n_mappings, n_modes;
     int32_t post_stride;       // int16 elements per (frame, channel) in nvb_batch.posts
     int32_t max_items;         // max over modes of stages*partitions*streams (residue prefix table)
-    int32_t pad0;
+    int32_t spectrum_fast;     // every residue/floor of the setup fits k_spectrum_fast
     uint64_t off_books, off_vq, off_floors, off_residues, off_mappings, off_modes;
     uint64_t off_win_short;    // bs[0] floats
     uint64_t off_win_long;     // 4 * bs[1] floats (window index = prev?1:0 + next?2:0)
@@ -45,17 +56,19 @@ struct BlobHeader {
     uint64_t off_fft[2];       // fast path: float2[bs/4], exp(-2*pi*i*k/(bs/4))
     uint64_t off_db;           // 256 floats
     uint64_t n_vq;
+    uint64_t off_fused_tab;    // FusedTables block (nvb_fused_core.h) when bs == {256, 2048}, else 0
 };
 
 // Resolved pointers handed to kernels by value.
 struct DevSetup {
-    int32_t channels, bs[2], post_stride, max_items;
+    int32_t channels, bs[2], post_stride, max_items, spectrum_fast;
     const DevBook* books; const float* vq; int64_t n_vq;
     const DevFloor1* floors; const DevResidue* residues; const DevMapping* mappings; const DevMode* modes;
     const float* win_short; const float* win_long;
     const float* A[2]; const float* B[2]; const float* C[2]; const uint16_t* bitrev[2];
     const float2* tw[2]; const float2* fft[2];
     const float* db;
+    const float* fused_tab;    // lane tables of the fused kernel, nullptr when the block sizes are not {256, 2048}
 };
 
 // ---- per-frame plan built on the host from nvb_frame (ok frames only, in order) ----------------
@@ -92,7 +105,8 @@ struct LaunchArgs {
     int clip;
 };
 
-int launch_spectrum(const LaunchArgs& a, void* stream);
+int launch_spectrum(const LaunchArgs& a, void* stream);            // picks k_spectrum_fast when every residue of the setup allows it
+int launch_spectrum_generic(const LaunchArgs& a, void* stream);
 int launch_imdct_exact(const LaunchArgs& a, void* stream);   // spectrum -> windowed blocks
 int launch_ola(const LaunchArgs& a, void* stream);           // blocks (+carry) -> interleaved PCM
 // Fused fast path: spectrum -> PCM for runs of frames; returns <0 if the batch shape is not covered.

@@ -11,6 +11,7 @@
 #if !defined(NVB_CPU_SHIM)
 #include <cuda_runtime.h>
 #endif
+#include <cstdlib>
 #include "nvb_device_core.h"
 
 namespace nvb {
@@ -111,6 +112,258 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1+K2+K3, fast path (DevSetup.spectrum_fast): same results as k_spectrum, organised for the machine.
+//   phase A  warp per channel: Floor1 unwrap with the posts of one dependency level computed in parallel
+//            (lane = post; Floor1.cs:224-297 is serial only along the lo/hi neighbour chains), step flags
+//            by an OR reduction, then the x-sorted walk of Floor1.Apply (Floor1.cs:196-216) as a
+//            ballot/popcount compaction into line-segment records;  one warp builds the entry-stream
+//            prefix (where each (stage, partition, stream) item's VQ entries start).
+//   phase B  (channel, segment) units over all warps, lanes over x: y(x) of RenderLineMulti
+//            (Floor1.cs:316-341) in closed form, floor multiplier inverse_dB[y] -> shared memory.
+//   phase C  thread per spectral bin: gather the VQ values that land on the bin in stage order (the adds of
+//            Residue0/1/2.WriteVectors in the reference's order), inverse coupling, floor multiply, store.
+// No integer division in phases B/C: partition and book sizes are powers of two here (host-checked).
+// ------------------------------------------------------------------------------------------------
+struct SegRec { int16_t x0, x1; int32_t y0, b; int16_t ady, sy; float rcp; };
+
+__device__ __forceinline__ void floor1_segments_warp(const DevFloor1& F, const int16_t* posts, int n, int lane, int* fy, SegRec* segs, int* nseg_out) {
+    int count = posts[0];
+    if (count > F.n_posts) count = F.n_posts;
+    if (count < 2) { if (lane == 0) *nseg_out = 0; return; }             // PostCount == 0: the spectrum is cleared (Floor1.cs:220)
+    int val[2]; unsigned long long contrib = 0ull;
+    #pragma unroll
+    for (int h = 0; h < 2; h++) { const int i = lane + 32 * h; val[h] = i < count ? posts[1 + i] : 0; }
+    if (lane < 2) fy[lane] = val[0];
+    __syncwarp();
+    for (int lvl = 1; lvl <= F.max_level; lvl++) {
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int i = lane + 32 * h;
+            if (i >= 2 && i < count && F.level[i] == lvl) {
+                const int lo = F.lo[i], hi = F.hi[i];
+                const int predicted = render_point(F.x[lo], fy[lo], F.x[hi], fy[hi], F.x[i]);
+                const int v = val[h];
+                const int highroom = F.range - predicted, lowroom = predicted;
+                const int room = (highroom < lowroom ? highroom : lowroom) * 2;
+                int out;
+                if (v != 0) {
+                    contrib |= (1ull << lo) | (1ull << hi) | (1ull << i);
+                    if (v >= room) out = highroom > lowroom ? v - lowroom + predicted : predicted - v + highroom - 1;
+                    else out = (v & 1) ? predicted - ((v + 1) >> 1) : predicted + (v >> 1);       // v > 0 here: (v % 2) == 1 <=> v & 1
+                } else out = predicted;
+                fy[i] = out;
+            }
+        }
+        __syncwarp();
+    }
+    // stepFlags: 0 and 1 always; i when its own value is non-zero or a later post names it as a neighbour (Floor1.cs:253-257,292)
+    unsigned lo32 = (unsigned)contrib, hi32 = (unsigned)(contrib >> 32);
+    #pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { lo32 |= __shfl_xor_sync(0xffffffffu, lo32, d); hi32 |= __shfl_xor_sync(0xffffffffu, hi32, d); }
+    const unsigned long long flags = (((unsigned long long)hi32 << 32) | lo32) | 3ull;
+    // sorted walk: position k (lane, lane + 32) holds post sort[k]
+    int idx[2]; bool act[2];
+    #pragma unroll
+    for (int h = 0; h < 2; h++) { const int k = lane + 32 * h; idx[h] = k < count ? F.sort[k] : 0; act[h] = k < count && idx[h] < count && ((flags >> idx[h]) & 1ull); }
+    const unsigned m0 = __ballot_sync(0xffffffffu, act[0]), m1 = __ballot_sync(0xffffffffu, act[1]);
+    const unsigned long long M = ((unsigned long long)m1 << 32) | m0;      // bit 0 is always set (sort[0] = 0, x = 0)
+    bool emit[2] = {false, false};
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int k = lane + 32 * h;
+        if (act[h] && k >= 1) {
+            const unsigned long long below = M & ((1ull << k) - 1ull);
+            const int pk = 63 - __clzll((long long)below);
+            const int pidx = F.sort[pk];
+            const int lx = F.x[pidx];
+            if (lx < n) {                                                   // Floor1.cs:204 / :211
+                emit[h] = true;
+                const int ly = fy[pidx] * F.mult, hx = F.x[idx[h]], hy = fy[idx[h]] * F.mult;
+                const int x1 = hx < n ? hx : n;                             // x clamped, y NOT re-interpolated (Floor1.cs:206)
+                const int dy = hy - ly, adx = x1 - lx;
+                const int b = dy / adx, ab = b < 0 ? -b : b;
+                SegRec r; r.x0 = (int16_t)lx; r.x1 = (int16_t)x1; r.y0 = ly; r.b = b;
+                r.ady = (int16_t)((dy < 0 ? -dy : dy) - ab * adx); r.sy = (int16_t)(dy < 0 ? -1 : 1); r.rcp = 1.0f / (float)adx;
+                segs[__popcll(below) - 1] = r;
+            }
+        }
+    }
+    const int n_emit = __popc(__ballot_sync(0xffffffffu, emit[0])) + __popc(__ballot_sync(0xffffffffu, emit[1]));
+    if (lane == 0) {
+        int ns = n_emit;
+        const int kl = 63 - __clzll((long long)M);
+        const int lidx = F.sort[kl];
+        const int lx = F.x[lidx];
+        if (lx < n) {                                                       // flat tail, Floor1.cs:213-216
+            SegRec r; r.x0 = (int16_t)lx; r.x1 = (int16_t)n; r.y0 = fy[lidx] * F.mult; r.b = 0; r.ady = 0; r.sy = 1; r.rcp = 1.0f;
+            segs[ns++] = r;
+        }
+        *nseg_out = ns;
+    }
+}
+
+__global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
+    NVB_DYN_SMEM(dyn_smem);
+    __shared__ float s_db[256];
+    __shared__ int s_fy[NVB_MAX_CHANNELS][NVB_MAX_POSTS];
+    __shared__ SegRec s_seg[NVB_MAX_CHANNELS][NVB_MAX_POSTS + 1];
+    __shared__ int s_nseg[NVB_MAX_CHANNELS];
+    __shared__ int s_bad[2];
+
+    const DevFrame f = a.frames[blockIdx.x];
+    if (f.kind != 0) return;
+    const DevSetup& S = a.S;
+    const int C = S.channels;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    constexpr int NW = SPEC_THREADS / 32;
+    const DevMode md = S.modes[f.mode];
+    const DevMapping& mp = S.mappings[md.mapping];
+    const DevResidue& R = S.residues[mp.residue];
+    const DevFloor1& F = S.floors[mp.floor];
+    const int N = f.n, n = N >> 1;
+    float* s_fl = reinterpret_cast<float*>(dyn_smem);                       // [C][n] floor multipliers
+    uint32_t* prefix = reinterpret_cast<uint32_t*>(s_fl + (size_t)C * (S.bs[1] >> 1));
+    const uint8_t* cls = a.classes + f.classes_off;
+    const uint16_t* ent = a.entries + f.entries_off;
+
+    ResGeom g; g.P = 0; g.Sx = 1; g.n_items = 0;
+    if (f.res_decoded) g = residue_geom(R, N, C);
+    if (t < 2) s_bad[t] = 0;
+    s_db[t & 255] = S.db[t & 255];
+
+    // ---- phase A
+    if (warp == NW - 1) {
+        // entry-stream prefix over the items in decode order (stage, partition, stream): warp scan, 32 items a step
+        uint32_t run = 0;
+        const int per_stage = g.P * g.Sx;
+        for (int base = 0; base < g.n_items; base += 32) {
+            const int i = base + lane;
+            uint32_t c = 0;
+            if (i < g.n_items) {
+                const int s = i / per_stage, rem = i - s * per_stage;
+                const int p = rem / g.Sx, st = rem - p * g.Sx;
+                const int cl = cls[st * g.P + p];
+                if (cl < R.nclass) c = (uint32_t)R.cnt[cl][s];
+            }
+            uint32_t incl = c;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+            if (i < g.n_items) prefix[i] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    for (int c = warp; c < C; c += NW) {                                    // the prefix warp also takes a channel only when C == NW
+        if ((f.exec_mask >> c) & 1u)
+            floor1_segments_warp(F, a.posts + ((size_t)f.api_index * C + c) * S.post_stride, n, lane, s_fy[c], s_seg[c], &s_nseg[c]);
+        else if (lane == 0) s_nseg[c] = 0;
+    }
+    __syncthreads();
+
+    // ---- phase B: floor curve rows
+    int bad_floor = 0;
+    {
+        int u = warp;
+        for (int c = 0; c < C; c++) {
+            const int ns = s_nseg[c];
+            for (; u < ns; u += NW) {
+                const SegRec r = s_seg[c][u];
+                const int x0 = r.x0, len = r.x1 - r.x0;
+                for (int k = lane; k < len; k += 32) {
+                    const int num = k * r.ady;                              // < 2^20: exact in float
+                    int q = __float2int_rz(__int2float_rn(num) * r.rcp);
+                    int rem = num - q * len;
+                    if (rem >= len) ++q; else if (rem < 0) --q;
+                    int y = r.y0 + k * r.b + r.sy * q;
+                    if (y < 0 || y > 255) { bad_floor = 1; y = y < 0 ? 0 : 255; }
+                    s_fl[c * n + x0 + k] = s_db[y];
+                }
+            }
+            u -= ns;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: residue gather + coupling + floor multiply
+    int bad_entry = 0;
+    const int pshift = R.pshift, pmask = R.psize - 1;
+    for (int j = t; j < n; j += SPEC_THREADS) {
+        float r[NVB_MAX_CHANNELS];
+        #pragma unroll
+        for (int c = 0; c < NVB_MAX_CHANNELS; c++) r[c] = 0.f;
+        if (g.P > 0) {
+            if (R.type == 2) {
+                // interleaved position of channel 0 of this bin; all C channels sit in one partition (aligned, host-checked)
+                const int q = j * C - R.begin;
+                const int p = q >> pshift;
+                if (q >= 0 && p < g.P) {
+                    const int o = q & pmask;
+                    const int cl = cls[p];
+                    if (cl < R.nclass) {
+                        const int casc = R.cascade[cl];
+                        for (int s = 0; s < R.stages; s++) {
+                            if (!((casc >> s) & 1)) continue;
+                            const int book = R.books[cl][s];
+                            if (book < 0) continue;
+                            const DevBook b = S.books[book];
+                            const uint32_t base = prefix[s * g.P + p];
+                            #pragma unroll
+                            for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
+                                if (c >= C) break;
+                                const int e = o + c;
+                                r[c] = NVB_FADD(r[c], vq_fetch(b, S.vq, ent, base + (uint32_t)(e >> b.dshift), f.entry_count, e & (b.dims - 1), &bad_entry));
+                            }
+                        }
+                    }
+                }
+            } else {
+                const int q = j - R.begin;
+                const int p = q >> pshift;
+                if (q >= 0 && p < g.P) {
+                    const int o = q & pmask;
+                    #pragma unroll
+                    for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
+                        if (c >= C) break;
+                        const int cl = cls[c * g.P + p];
+                        if (cl >= R.nclass) continue;
+                        const int casc = R.cascade[cl];
+                        for (int s = 0; s < R.stages; s++) {
+                            if (!((casc >> s) & 1)) continue;
+                            const int book = R.books[cl][s];
+                            if (book < 0) continue;
+                            const DevBook b = S.books[book];
+                            const uint32_t base = prefix[(s * g.P + p) * g.Sx + c];
+                            if (R.type == 1) r[c] = NVB_FADD(r[c], vq_fetch(b, S.vq, ent, base + (uint32_t)(o >> b.dshift), f.entry_count, o & (b.dims - 1), &bad_entry));
+                            else {                                          // type 0: element (dim, step) at dim*steps + step (Residue0.cs:193-199)
+                                const int sshift = pshift - b.dshift;
+                                r[c] = NVB_FADD(r[c], vq_fetch(b, S.vq, ent, base + (uint32_t)(o & ((1 << sshift) - 1)), f.entry_count, o >> sshift, &bad_entry));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        for (int i = mp.n_coupling - 1; i >= 0; --i) {                      // Mapping.cs:137-182
+            const int m = mp.mag[i], an = mp.ang[i];
+            if (((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u) inverse_couple(r[m], r[an]);
+        }
+        #pragma unroll
+        for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
+            if (c >= C) break;
+            float v = r[c];
+            if ((f.exec_mask >> c) & 1u) v = s_nseg[c] > 0 ? NVB_FMUL(v, s_fl[c * n + j]) : 0.f;      // Floor1.Apply, Floor1.cs:186-222
+            a.spectrum[(size_t)f.spec_off + (size_t)c * n + j] = v;
+        }
+    }
+    if (bad_entry) atomicOr(&s_bad[0], 1);
+    if (bad_floor) atomicOr(&s_bad[1], 1);
+    __syncthreads();
+    if (t == 0) {
+        if (s_bad[0]) atomicAdd(&a.counters->bad_entry, 1);
+        if (s_bad[1]) atomicAdd(&a.counters->floor_range, 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4 exact: one CTA per (frame, channel); the reference's stb_vorbis IMDCT schedule cut into
 // data-parallel steps with a barrier between them, all in shared memory (u[N] + v[N/2]).
 // Bit-identical to Mdct.cs for every N (including its N = 64/128 behaviour).
@@ -190,6 +443,20 @@ __global__ void __launch_bounds__(OLA_THREADS) k_ola(LaunchArgs a) {
 static size_t spectrum_smem(const DevSetup& S) { return (size_t)(S.max_items > 0 ? S.max_items : 1) * sizeof(uint32_t); }
 
 int launch_spectrum(const LaunchArgs& a, void* stream) {
+    if (a.n_frames <= 0) return 0;
+    static const bool force_generic = std::getenv("NVB_SPECTRUM_GENERIC") != nullptr;      // test hook: exercise the general kernel
+    if (!a.S.spectrum_fast || force_generic) return launch_spectrum_generic(a, stream);
+    const size_t smem = spectrum_smem(a.S) + (size_t)a.S.channels * (a.S.bs[1] / 2) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 24 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(k_spectrum_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured = smem;
+    }
+    NVB_LAUNCH(k_spectrum_fast, a.n_frames, SPEC_THREADS, smem, stream, a);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_spectrum_generic(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
     size_t smem = spectrum_smem(a.S);
     static size_t configured = 0;

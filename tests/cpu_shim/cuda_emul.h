@@ -72,6 +72,49 @@ template <class T> static inline T cuemu_shfl(T v, int src_lane_delta, bool is_x
 }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return cuemu_shfl(v, m, true); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return cuemu_shfl(v, d, false); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    cuemu::Launch* L = cuemu::g_launch;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    L->shfl[w * 32 + lane] = pred ? 1u : 0u;
+    L->warp[w]->arrive_and_wait();
+    unsigned m = 0;
+    const int lanes = (L->nthreads - 32 * w) < 32 ? (L->nthreads - 32 * w) : 32;
+    for (int i = 0; i < lanes; i++) m |= L->shfl[w * 32 + i] << i;
+    L->warp[w]->arrive_and_wait();
+    return m;
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    cuemu::Launch* L = cuemu::g_launch;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t bits; std::memcpy(&bits, &v, 4);
+    L->shfl[w * 32 + lane] = bits;
+    L->warp[w]->arrive_and_wait();
+    uint32_t rb = L->shfl[w * 32 + (src & 31)];
+    L->warp[w]->arrive_and_wait();
+    T r; std::memcpy(&r, &rb, 4); return r;
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+// mbarrier emulation: bits 0-15 pending arrivals, 16-31 expected arrivals, 32-63 phase
+static inline void mbar_init(uint64_t* bar, int count) { __atomic_store_n(bar, ((uint64_t)count << 16) | (uint64_t)count, __ATOMIC_SEQ_CST); }
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive(uint64_t* bar) {
+    uint64_t v = __atomic_load_n(bar, __ATOMIC_SEQ_CST), nv;
+    do {
+        uint64_t pending = (v & 0xffff) - 1, expected = (v >> 16) & 0xffff, phase = v >> 32;
+        if (pending == 0) { pending = expected; phase++; }
+        nv = (phase << 32) | (expected << 16) | pending;
+    } while (!__atomic_compare_exchange_n(bar, &v, nv, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+}
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while ((((__atomic_load_n(bar, __ATOMIC_SEQ_CST)) >> 32) & 1u) == parity) std::this_thread::yield();
+}
+static inline void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { std::memcpy(dst, src, bytes); mbar_arrive(bar); }
+static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __float2int_rz(float f) { return (int)f; }
+static inline float __int2float_rn(int v) { return (float)v; }
 static inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
