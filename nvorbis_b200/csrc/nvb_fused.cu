@@ -10,10 +10,12 @@
 //     three radix-8 passes in registers, two exchanges through the frame's shared-memory slot, twiddles
 //     from per-lane tables that one bulk copy (cp.async.bulk, TMA) stages at kernel start), leaves the
 //     DCT-IV output u in the slot, then writes the frame's PCM from its own u and the previous frame's u;
-//   * no CTA-wide barrier in steady state: slots form a ring guarded by mbarriers -- full[slot] (u of that
-//     frame is complete; awaited by the warp that overlaps onto it) and empty[slot] (both readers of the
-//     slot are done; awaited by the warp that reuses it) -- so transform, overlap and store of different
-//     frames run concurrently on the four schedulers of the SM;
+//   * no CTA-wide barrier in steady state: slots form a ring guarded by release/acquire counters in shared
+//     memory -- full[slot] (u of that frame is complete; awaited by the warp that overlaps onto it) and
+//     empty[slot] (both readers of the slot are done; awaited by the warp that reuses it) -- so transform,
+//     overlap and store of different frames run concurrently on the four schedulers of the SM.  Counters
+//     rather than mbarrier phases: nothing bounds the skew between two warps to one ring revolution, and a
+//     parity wait cannot tell "two phases behind" from "done";
 //   * the previous block's tail never touches HBM: each spectrum float is read once and each PCM float is
 //     written once (16 384 B per stereo long frame); the first block of a run is recomputed as a halo;
 //   * shared memory is bank-conflict free: padded exchange strides (72 / 9 float2), XOR-swizzled u;
@@ -54,6 +56,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
 }
+// Monotonic event counters in shared memory: signal = release-add by one lane (after __syncwarp), wait = acquire-poll.
+__device__ __forceinline__ void cnt_signal(int* c) {
+    asm volatile("red.release.cta.shared::cta.add.s32 [%0], 1;" ::"r"(smem_u32(c)) : "memory");
+}
+__device__ __forceinline__ void cnt_wait(const int* c, int need) {
+    const uint32_t addr = smem_u32(c);
+    int v;
+    for (;;) {
+        asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        if (v >= need) break;
+        __nanosleep(32);
+    }
+}
 // One thread: global -> shared bulk copy (TMA), completion counted in bytes on `bar`.
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     const uint32_t b = smem_u32(bar);
@@ -85,16 +100,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
     float* s_tab = reinterpret_cast<float*>(smem_raw);
     float* s_slots = s_tab + FusedTables::FLOATS;
     DevFrame* s_fr = reinterpret_cast<DevFrame*>(s_slots + (size_t)NS * C * FUSED_SLOT_FLOATS);
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_fr + NS);
-    uint64_t* s_empty = s_full + NS;
-    uint64_t* s_tabbar = s_empty + NS;
+    int* s_full = reinterpret_cast<int*>(s_fr + NS);                        // s_full[s]: frames completed in slot s
+    int* s_empty = s_full + NS;                                             // s_empty[s]: reader releases of slot s (two per frame)
+    uint64_t* s_tabbar = reinterpret_cast<uint64_t*>(s_empty + NS);          // 8 NS bytes past s_full: 8-byte aligned
 
     const int lo = blockIdx.x * p.frames_per_cta;
     int hi = lo + p.frames_per_cta; if (hi > a.n_frames) hi = a.n_frames;
     if (lo >= hi) return;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 2); }
+        for (int s = 0; s < NS; s++) { s_full[s] = 0; s_empty[s] = 0; }
         mbar_init(s_tabbar, 1);
         mbar_fence_init();
     }
@@ -119,8 +134,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
     float peak = 0.f;
 
     for (int x = first + warp; x < hi; x += FUSED_WARPS) {
-        const int rel = x - first, slot = rel % NS;
-        mbar_wait(&s_empty[slot], ((rel / NS) & 1) ^ 1);                     // both readers of the slot's previous frame are done
+        const int rel = x - first, slot = rel % NS, it = rel / NS;
+        cnt_wait(&s_empty[slot], 2 * it);                                    // both readers of every earlier frame of the slot are done
         if (lane == 0) s_fr[slot] = a.frames[x];
         __syncwarp();
         const DevFrame f = s_fr[slot];
@@ -162,7 +177,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_full[slot]);                           // u of frame x is complete
+        if (lane == 0) cnt_signal(&s_full[slot]);                            // u of frame x is complete
 
         // ---------------- output of frame x (a halo block only leaves its tail) --------------------
         if (x >= lo) {
@@ -170,7 +185,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
             const DevFrame* pf = nullptr; const float* slots_p = nullptr;
             if (f.prev >= 0 && (f.ola_len > 0 || f.kind != 0)) {
                 const int prel = f.prev - first, pslot = prel % NS;
-                mbar_wait(&s_full[pslot], (prel / NS) & 1);
+                cnt_wait(&s_full[pslot], prel / NS + 1);
                 pf = &s_fr[pslot]; slots_p = s_slots + (size_t)pslot * C * FUSED_SLOT_FLOATS;
             }
             const bool fast = (C == 2) && f.kind == 0 && pf && f.n == FUSED_LONG_N && pf->n == FUSED_LONG_N && f.window == 3 &&
@@ -235,10 +250,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
                 }
             }
         }
+        // Release the slots.  The release of x-1's slot must not overtake frame x-1 itself (it would be counted
+        // against the slot's next user), so frame x-1 has to have claimed and filled its slot by now, needed or not.
+        if (rel >= 1) cnt_wait(&s_full[(rel - 1) % NS], (rel - 1) / NS + 1);
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&s_empty[slot]);                                     // done with frame x as "current"
-            if (rel >= 1) mbar_arrive(&s_empty[(rel - 1) % NS]);             // done with frame x-1 as "previous"
+            cnt_signal(&s_empty[slot]);                                      // done with frame x as "current"
+            if (rel >= 1) cnt_signal(&s_empty[(rel - 1) % NS]);              // done with frame x-1 as "previous"
         }
     }
     if (__any_sync(0xffffffffu, peak > 0.99999994f) && lane == 0) atomicOr(&a.counters->clipped, 1);
@@ -247,13 +265,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
 // ------------------------------------------------------------------------------------------------
 static int fused_slots(int C) {
     const size_t fixed = FusedTables::FLOATS * sizeof(float) + 64;
-    const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(uint64_t);
+    const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
     int ns = (int)((FUSED_SMEM_LIMIT - fixed) / per);
     if (ns > FUSED_WARPS + 2) ns = FUSED_WARPS + 2;
     return ns;
 }
 static size_t fused_smem(int C, int NS) {
-    return FusedTables::FLOATS * sizeof(float) + (size_t)NS * ((size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(uint64_t)) + 16;
+    return FusedTables::FLOATS * sizeof(float) + (size_t)NS * ((size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int)) + 32;
 }
 
 bool fused_supported(const BlobHeader& h, const DevFrame*, int) {

@@ -1,0 +1,118 @@
+"""VorbisReader / StreamDecoder mirror (VorbisReader.cs, StreamDecoder.cs) on top of the split decoder:
+the host library unpacks batches of packets (libnvorbis_host.so), the GPU library synthesises them
+(libnvorbis_b200.so), and ReadSamples is served from the decoded batch, as the batching StreamDecoder of
+INTEGRATION.md does on the C# side.  Same names, argument meaning and end-of-stream behaviour as the
+reference's public API for this path; there is no CPU synthesis fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi, hostlib
+
+
+class VorbisReader:
+    """`new VorbisReader(stream)` ... `ReadSamples(buffer, offset, count)` (VorbisReader.cs:42-64, 336-345)."""
+
+    def __init__(self, source, device: int = 0, batch_packets: int = 4096, clip_samples: bool = True,
+                 unpack_threads: int = 0, lib_path: str | None = None):
+        if isinstance(source, (bytes, bytearray, memoryview)):
+            self._host = hostlib.HostStream(data=bytes(source))
+        elif isinstance(source, str):
+            with open(source, "rb") as f:
+                self._host = hostlib.HostStream(data=f.read())
+        else:                                   # (data, sizes, granules, flags): an IPacketProvider's packets
+            self._host = hostlib.HostStream(packets=tuple(source))
+        self._ctx = capi.Context(device, lib_path=lib_path)
+        self._ctx.upload_setup(self._host.setup())
+        self._batch_packets = int(batch_packets)
+        self._threads = unpack_threads
+        self.clip_samples = bool(clip_samples)          # StreamDecoder.ClipSamples (VorbisReader.cs:77 forces true)
+        self._pcm = np.zeros(0, np.float32)             # decoded, not yet handed out
+        self._pos = 0
+        self._eos = False
+        self._started = False
+        self._has_clipped = False
+        self._samples_read = 0
+
+    # ---- properties of IVorbisReader / IStreamDecoder used by TestApp ---------------------------------
+    @property
+    def channels(self) -> int:
+        return self._host.channels
+
+    @property
+    def sample_rate(self) -> int:
+        return self._host.sample_rate
+
+    @property
+    def has_clipped(self) -> bool:
+        return self._has_clipped
+
+    @has_clipped.setter
+    def has_clipped(self, v: bool):
+        self._has_clipped = bool(v)
+
+    @property
+    def is_end_of_stream(self) -> bool:                 # StreamDecoder.IsEndOfStream
+        return self._eos and self._pos >= self._pcm.size
+
+    @property
+    def sample_position(self) -> int:
+        return self._samples_read
+
+    def _refill(self) -> bool:
+        if self._eos:
+            return False
+        hb, eos = self._host.unpack(self._batch_packets, self._threads, copy=False)
+        flags = capi.RUN_DEFAULT | (capi.RUN_CONTINUE if self._started else 0) | (0 if self.clip_samples else capi.RUN_NO_CLIP)
+        pcm, res = self._ctx.decode_batch(hb, flags)
+        self._started = True
+        self._eos = eos
+        self._has_clipped |= res.has_clipped
+        self._pcm, self._pos = pcm, 0
+        return pcm.size > 0 or not eos
+
+    def read_samples(self, buffer: np.ndarray, offset: int, count: int) -> int:
+        """Fills buffer[offset : offset+count] with interleaved float PCM; returns the number of floats written
+        (a multiple of Channels; 0 at the end of the stream)."""
+        if buffer.dtype != np.float32:
+            raise TypeError("buffer must be float32")
+        if offset < 0 or offset + count > buffer.size:
+            raise IndexError("offset/count outside the buffer")                  # ArgumentOutOfRangeException
+        count -= count % self.channels                                           # VorbisReader.cs:339-340
+        done = 0
+        while done < count:
+            if self._pos >= self._pcm.size and not self._refill():
+                break
+            n = min(count - done, self._pcm.size - self._pos)
+            buffer[offset + done: offset + done + n] = self._pcm[self._pos: self._pos + n]
+            self._pos += n; done += n
+        self._samples_read += done // self.channels
+        return done
+
+    def read_all(self, chunk_seconds: float = 4.0) -> np.ndarray:
+        """TestApp/Program.cs:21-26: 4-second chunks until ReadSamples returns 0."""
+        buf = np.zeros(int(self.sample_rate * chunk_seconds) * self.channels, np.float32)
+        out = []
+        while True:
+            n = self.read_samples(buf, 0, buf.size)
+            if n <= 0:
+                break
+            out.append(buf[:n].copy())
+        return np.concatenate(out) if out else np.zeros(0, np.float32)
+
+    def seek_to_start(self):
+        """SeekTo(0): restart decoding at the first audio packet (StreamDecoder.cs:562-628 with preRoll at the start)."""
+        self._host.rewind()
+        self._ctx.reset()
+        self._pcm, self._pos, self._eos, self._started, self._samples_read = np.zeros(0, np.float32), 0, False, False, 0
+
+    def close(self):
+        self._ctx.close()
+        self._host.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

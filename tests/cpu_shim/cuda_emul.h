@@ -6,6 +6,7 @@
 #pragma once
 #include <atomic>
 #include <barrier>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -107,7 +108,15 @@ static inline void mbar_arrive(uint64_t* bar) {
     } while (!__atomic_compare_exchange_n(bar, &v, nv, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
 }
 static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while ((((__atomic_load_n(bar, __ATOMIC_SEQ_CST)) >> 32) & 1u) == parity) std::this_thread::yield();
+    for (int spins = 0; (((__atomic_load_n(bar, __ATOMIC_SEQ_CST)) >> 32) & 1u) == parity; ++spins) {
+        if (spins < 64) std::this_thread::yield(); else std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+}
+static inline void cnt_signal(int* c) { __atomic_fetch_add(c, 1, __ATOMIC_SEQ_CST); }
+static inline void cnt_wait(const int* c, int need) {
+    for (int spins = 0; __atomic_load_n(c, __ATOMIC_SEQ_CST) < need; ++spins) {
+        if (spins < 64) std::this_thread::yield(); else std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
 }
 static inline void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { std::memcpy(dst, src, bytes); mbar_arrive(bar); }
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }

@@ -89,3 +89,49 @@ def oracle_synth(r: O.OracleReader, b: O.Boundary, lo: int = 0, hi: int | None =
     fr = b.frames[lo:hi].copy()
     cap = int(fr["total"].astype(np.int64).sum()) + 8192
     return r.synth_batch(fr, b.posts, b.post_counts, b.classes, b.entries, cap, threads=threads)
+
+
+def _ogg_crc(data: bytes) -> int:
+    crc = 0
+    for byte in data:
+        crc ^= byte << 24
+        for _ in range(8):
+            crc = ((crc << 1) ^ 0x04c11db7) & 0xFFFFFFFF if crc & 0x80000000 else (crc << 1) & 0xFFFFFFFF
+    return crc
+
+
+def mux_ogg(pk, serial: int = 1, page_payload: int = 4000) -> bytes:
+    """A plain Ogg muxer for tests: packets (bytes, granule, flags) -> pages of at most `page_payload` body bytes,
+    packets continued across pages when they do not fit.  The granule of a page is that of the last packet completed
+    in it (-1 if none); flags bit1 marks the end-of-stream packet."""
+    import struct
+    pages, seq = [], 0
+    segs, body, gran, cont, eos = [], b"", -1, False, False
+    last_g = 0
+
+    def flush(continued_next=False):
+        nonlocal segs, body, gran, cont, eos, seq
+        if not segs:
+            return
+        hdr = struct.pack("<4sBBqIIIB", b"OggS", 0, (1 if cont else 0) | (2 if seq == 0 else 0) | (4 if eos else 0), gran, serial, seq, 0, len(segs))
+        page = bytearray(hdr + bytes(segs) + body)
+        page[22:26] = struct.pack("<I", _ogg_crc(bytes(page)))
+        pages.append(bytes(page)); seq += 1
+        segs, body, gran, cont, eos = [], b"", -1, continued_next, False
+
+    for data, g, fl in pk:
+        if fl & 1:
+            last_g = g
+        pos = 0
+        lacing = [255] * (len(data) // 255) + [len(data) % 255]
+        for lv in lacing:
+            if len(segs) == 255 or len(body) + lv > page_payload:
+                flush(continued_next=True)
+            segs.append(lv); body += data[pos:pos + lv]; pos += lv
+        gran = last_g if (fl & 1) else gran
+        if fl & 2:
+            eos = True
+        if fl & 1:
+            flush()
+    flush()
+    return b"".join(pages)

@@ -150,3 +150,49 @@ def test_setup_tables_match_oracle(shim):
         np.testing.assert_array_equal(np.frombuffer(blob, np.float32, n // 2, ob), B)
         np.testing.assert_array_equal(np.frombuffer(blob, np.float32, n // 4, oc), Cc)
         np.testing.assert_array_equal(np.frombuffer(blob, np.uint16, n // 8, obr), BR)
+
+
+def test_vorbis_reader_end_to_end(shim, golden):
+    """The VorbisReader mirror (host unpacker -> C ABI -> ReadSamples) over the emulated device, with batches much
+    smaller than the stream so that several chained nvb_decode_batch calls are needed."""
+    from nvorbis_b200.reader import VorbisReader
+    pl = H.packets("1test")
+    r, pcm, b = H.decoded("1test")
+    with VorbisReader((pl.data, pl.sizes, pl.granules, pl.flags), batch_packets=7, lib_path=shim) as vr:
+        assert (vr.channels, vr.sample_rate) == (1, 44100)
+        got = vr.read_all(chunk_seconds=0.05)
+        assert got.size == pcm.size == golden["1test"]["samples_per_channel"]
+        assert np.abs(got - pcm).max() <= 1e-5 and not vr.has_clipped
+        assert vr.read_samples(np.zeros(64, np.float32), 0, 64) == 0 and vr.is_end_of_stream
+        vr.seek_to_start()
+        buf = np.zeros(1000, np.float32)
+        assert vr.read_samples(buf, 0, 1000) == 1000 and np.abs(buf - pcm[:1000]).max() <= 1e-5
+
+
+def test_generic_spectrum_kernel(shim):
+    """NVB_SPECTRUM_GENERIC forces the general residue/floor kernel (used for setups outside the fast path's envelope)."""
+    import os, subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, helpers as H\nfrom nvorbis_b200 import capi\n"
+            "r, pcm, b = H.decoded('3test')\nctx = capi.Context(0, lib_path=%r); ctx.upload_setup(H.setup_from_oracle(r))\n"
+            "want, _ = H.oracle_synth(r, b, 0, 40)\nout, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, 0, 40), capi.RUN_EXACT)\n"
+            "assert np.array_equal(out, want)\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"), shim)
+    env = dict(os.environ, NVB_SPECTRUM_GENERIC="1")
+    assert subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().endswith("ok")
+
+
+def test_slot_ring_wraps_with_mixed_windows(shim):
+    """One emulated SM (NVB_SHIM_SMS=1) makes a single CTA walk the whole batch, so the fused kernel's slot ring is
+    reused many times; mixed short/long frames (BASELINE configs[2] generator) exercise every window shape."""
+    import os, subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, helpers as H, bench\nfrom nvorbis_b200 import capi, setupio, workloads\n"
+            "desc, z = setupio.load(%r)\npool = workloads.FramePool.from_npz(desc, z)\n"
+            "hb = workloads.config3(pool, 90, 20240003)\n"
+            "r = H.O.OracleReader(H.packets('3test'))\nfr, posts, pc, cls, ent = bench.oracle_inputs(hb)\n"
+            "want, _ = r.synth_batch(fr, posts, pc, cls, ent, int(hb.frames['total'].astype(np.int64).sum()) + 8192)\n"
+            "ctx = capi.Context(0, lib_path=%r); ctx.upload_setup(setupio.to_setup(desc))\n"
+            "out, res = ctx.decode_batch(hb)\nassert out.size == want.size and np.abs(out - want).max() <= 1e-5\nprint('ok')\n"
+            ) % (H.ROOT, os.path.join(H.ROOT, "tests"), os.path.join(H.GOLDEN, "3test.boundary.npz"), shim)
+    env = dict(os.environ, NVB_SHIM_SMS="1")
+    assert subprocess.check_output([sys.executable, "-c", code], env=env, timeout=600).decode().strip().endswith("ok")

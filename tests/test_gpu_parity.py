@@ -187,6 +187,32 @@ def test_bad_entry_is_reported():
     assert e.value.status == capi.ERR_DATA
 
 
+@pytest.mark.parametrize("name", H.FIXTURES)
+def test_vorbis_reader_read_samples(name, golden):
+    """BASELINE configs[0]: the stream through the VorbisReader.ReadSamples mirror in 4-second chunks (TestApp/Program.cs:21-26):
+    product Ogg/packet unpacker -> C ABI -> GPU, against the oracle's PCM."""
+    from nvorbis_b200.reader import VorbisReader
+    pl = H.packets(name)
+    r, pcm, b = H.decoded(name)
+    with VorbisReader((pl.data, pl.sizes, pl.granules, pl.flags), batch_packets=128) as vr:
+        got = vr.read_all()
+        assert got.size == pcm.size == golden[name]["samples_per_channel"] * vr.channels
+        assert float(np.abs(got - pcm).max()) <= TOL
+        assert vr.has_clipped == golden[name]["has_clipped"]
+
+
+def test_generic_spectrum_kernel_on_gpu():
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, helpers as H\nfrom nvorbis_b200 import capi\n"
+            "for name in ('1test', '3test'):\n"
+            "    r, pcm, b = H.decoded(name)\n    ctx = capi.Context(0); ctx.upload_setup(H.setup_from_oracle(r))\n"
+            "    out, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride), capi.RUN_EXACT)\n"
+            "    assert np.array_equal(out, pcm)\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"))
+    env = dict(os.environ, NVB_SPECTRUM_GENERIC="1")
+    assert subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().endswith("ok")
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

@@ -1,0 +1,107 @@
+"""The host half of the split decoder (libnvorbis_host.so) against the oracle's boundary records: the product's
+own Ogg demux / header parser / Huffman + floor + residue unpacker must hand the GPU exactly the integers the
+reference's bit-reading code produces.  CPU only."""
+import numpy as np
+import pytest
+
+import helpers as H
+from nvorbis_b200 import capi, hostlib
+
+
+def _stream(name):
+    pl = H.packets(name)
+    return hostlib.HostStream(packets=(pl.data, pl.sizes, pl.granules, pl.flags))
+
+
+@pytest.mark.parametrize("name", H.FIXTURES)
+@pytest.mark.parametrize("threads", [1, 5])
+def test_boundary_records_match_oracle(name, threads):
+    r, pcm, b = H.decoded(name)
+    hs = _stream(name)
+    hb, eos = hs.unpack(10 ** 9, threads=threads)
+    ref = H.batch_from_boundary(b, hs.post_stride)
+    assert eos and len(hb.frames) == len(ref.frames)
+    for k in capi.FRAME_DTYPE.names:
+        np.testing.assert_array_equal(hb.frames[k], ref.frames[k], err_msg=k)
+    np.testing.assert_array_equal(hb.posts, ref.posts)
+    np.testing.assert_array_equal(hb.classes, ref.classes)
+    np.testing.assert_array_equal(hb.entries, ref.entries)
+
+
+@pytest.mark.parametrize("name", H.FIXTURES)
+def test_chunked_unpack_keeps_position_bookkeeping(name):
+    """Unpacking in ragged chunks gives the same records (the EOS trim needs the running sample position)."""
+    hs = _stream(name)
+    whole, _ = hs.unpack(10 ** 9, threads=2)
+    hs.rewind()
+    frames = []
+    for n in [1, 2, 7, 64, 100, 10 ** 9]:
+        hb, eos = hs.unpack(n, threads=3)
+        frames.append(hb.frames)
+        if eos:
+            break
+    got = np.concatenate(frames)
+    for k in ("status", "mode", "window", "exec_mask", "start", "valid", "total", "entry_count"):
+        np.testing.assert_array_equal(got[k], whole.frames[k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", H.FIXTURES)
+def test_setup_tables_match_oracle(name):
+    r, _, _ = H.decoded(name)
+    hs = _stream(name)
+    view, owner = hs.setup(), H.setup_from_oracle(r)        # keep the owners of the pointed-to arrays alive
+    s, want = view.struct, owner.struct
+    assert (s.channels, s.sample_rate, s.block_size[0], s.block_size[1]) == (want.channels, want.sample_rate, want.block_size[0], want.block_size[1])
+    assert (s.n_books, s.n_floors, s.n_residues, s.n_mappings, s.n_modes) == (want.n_books, want.n_floors, want.n_residues, want.n_mappings, want.n_modes)
+    assert s.n_vq_floats == want.n_vq_floats
+    np.testing.assert_array_equal(np.ctypeslib.as_array(s.vq_floats, (s.n_vq_floats,)), np.ctypeslib.as_array(want.vq_floats, (want.n_vq_floats,)))
+    import ctypes as C
+    for i in range(s.n_books):
+        a, b = s.books[i], want.books[i]
+        assert (a.dims, a.entries, a.map_type, a.table_off) == (b.dims, b.entries, b.map_type, b.table_off)
+    for i in range(s.n_floors):
+        assert bytes(C.string_at(C.addressof(s.floors[i]), C.sizeof(capi.Floor))) == bytes(C.string_at(C.addressof(want.floors[i]), C.sizeof(capi.Floor)))
+    for i in range(s.n_residues):
+        a, b = s.residues[i], want.residues[i]
+        assert (a.type, a.begin, a.end, a.partition_size, a.classifications, a.max_stages) == (b.type, b.begin, b.end, b.partition_size, b.classifications, b.max_stages)
+        for c in range(a.classifications):
+            assert a.cascade[c] == b.cascade[c]
+            for st in range(a.max_stages):
+                if (a.cascade[c] >> st) & 1:
+                    assert a.books[c][st] == b.books[c][st]
+    for i in range(s.n_mappings):
+        a, b = s.mappings[i], want.mappings[i]
+        assert (a.n_coupling, a.n_submaps, a.floor, a.residue) == (b.n_coupling, b.n_submaps, b.floor, b.residue)
+        assert list(a.magnitude[:a.n_coupling]) == list(b.magnitude[:b.n_coupling]) and list(a.angle[:a.n_coupling]) == list(b.angle[:b.n_coupling])
+    for i in range(s.n_modes):
+        assert (s.modes[i].block_flag, s.modes[i].mapping) == (want.modes[i].block_flag, want.modes[i].mapping)
+
+
+def test_ogg_demux_roundtrip():
+    """Packets re-muxed into Ogg pages (lacing, continued packets across pages, a trailing empty EOS page) demux
+    back to the same packets, granules and end-of-stream flags."""
+    pl = H.packets("1test")
+    pk = []
+    off = 0
+    for sz, g, fl in zip(pl.sizes, pl.granules, pl.flags):
+        pk.append((bytes(pl.data[off:off + sz]), int(g), int(fl))); off += int(sz)
+    ogg = H.mux_ogg(pk, serial=0x1234, page_payload=700)
+    hs = hostlib.HostStream(data=ogg)
+    assert hs.info.n_packets == len(pk)
+    for i, (data, g, fl) in enumerate(pk):
+        d2, g2, f2 = hs.packet(i)
+        assert d2 == data
+    hb, eos = hs.unpack(10 ** 9)
+    ref, _ = _stream("1test").unpack(10 ** 9)
+    np.testing.assert_array_equal(hb.entries, ref.entries)
+    np.testing.assert_array_equal(hb.frames["valid"][:-1], ref.frames["valid"][:-1])
+
+
+def test_malformed_headers_are_rejected():
+    pl = H.packets("1test")
+    data = pl.data.copy()
+    data[int(pl.sizes[0]) + int(pl.sizes[1]) + 3] ^= 0xFF          # corrupt the setup header signature
+    with pytest.raises(hostlib.HostError):
+        hostlib.HostStream(packets=(data, pl.sizes, pl.granules, pl.flags))
+    with pytest.raises(hostlib.HostError):
+        hostlib.HostStream(data=b"not an ogg file at all")
