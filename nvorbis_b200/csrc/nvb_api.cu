@@ -4,6 +4,7 @@
 #if !defined(NVB_CPU_SHIM)
 #include <cuda_runtime.h>
 #endif
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -351,11 +352,13 @@ int nvb_dbatch_run(nvb_ctx* ctx, nvb_dbatch* b, float* d_pcm, void* stream) {
 }
 int nvb_dbatch_run_spectrum(nvb_ctx* ctx, nvb_dbatch* b, float* d_spectrum, void* stream) {
     if (!ctx || !b || (!d_spectrum && b->plan.spec_floats > 0)) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    if (reinterpret_cast<uintptr_t>(d_spectrum) & 15) return set_err(ctx, NVB_ERR_ARG, "d_spectrum must be 16-byte aligned (bulk copies)");
     DeviceGuard g(ctx->device);
     return enqueue(ctx, b, 1, d_spectrum, nullptr, false, (cudaStream_t)stream);
 }
 int nvb_dbatch_run_imdct(nvb_ctx* ctx, nvb_dbatch* b, const float* d_spectrum, float* d_pcm, void* stream) {
     if (!ctx || !b || (!d_spectrum && b->plan.spec_floats > 0) || (!d_pcm && b->plan.samples > 0)) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    if (reinterpret_cast<uintptr_t>(d_spectrum) & 15) return set_err(ctx, NVB_ERR_ARG, "d_spectrum must be 16-byte aligned (bulk copies)");
     DeviceGuard g(ctx->device);
     return enqueue(ctx, b, 2, const_cast<float*>(d_spectrum), d_pcm, false, (cudaStream_t)stream);
 }

@@ -16,6 +16,9 @@
 //     overlap and store of different frames run concurrently on the four schedulers of the SM.  Counters
 //     rather than mbarrier phases: nothing bounds the skew between two warps to one ring revolution, and a
 //     parity wait cannot tell "two phases behind" from "done";
+//   * inputs are TMA-staged: the spectrum rows of a warp's NEXT frame are bulk-copied (cp.async.bulk, completion
+//     on an mbarrier) straight into that frame's slot while the warp still works on the current one, so no
+//     warp waits on a global load in steady state and no load instruction is spent on the input;
 //   * the previous block's tail never touches HBM: each spectrum float is read once and each PCM float is
 //     written once (16 384 B per stereo long frame); the first block of a run is recomputed as a halo;
 //   * shared memory is bank-conflict free: padded exchange strides (72 / 9 float2), XOR-swizzled u;
@@ -69,13 +72,21 @@ __device__ __forceinline__ void cnt_wait(const int* c, int need) {
         __nanosleep(32);
     }
 }
-// One thread: global -> shared bulk copy (TMA), completion counted in bytes on `bar`.
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    const uint32_t b = smem_u32(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+__device__ __forceinline__ bool cnt_ready(const int* c, int need) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(c)) : "memory");
+    return v >= need;
 }
+// One thread: global -> shared bulk copies (TMA), completion counted in bytes on `bar`.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Orders earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
 __device__ __forceinline__ float clipf(float v, float& peak) {
@@ -103,24 +114,48 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
     int* s_full = reinterpret_cast<int*>(s_fr + NS);                        // s_full[s]: frames completed in slot s
     int* s_empty = s_full + NS;                                             // s_empty[s]: reader releases of slot s (two per frame)
     uint64_t* s_tabbar = reinterpret_cast<uint64_t*>(s_empty + NS);          // 8 NS bytes past s_full: 8-byte aligned
+    uint64_t* s_in = s_tabbar + 1;                                          // s_in[s]: the spectrum rows of the slot's frame have landed
 
     const int lo = blockIdx.x * p.frames_per_cta;
     int hi = lo + p.frames_per_cta; if (hi > a.n_frames) hi = a.n_frames;
     if (lo >= hi) return;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { s_full[s] = 0; s_empty[s] = 0; }
+        for (int s = 0; s < NS; s++) { s_full[s] = 0; s_empty[s] = 0; mbar_init(&s_in[s], 1); }
         mbar_init(s_tabbar, 1);
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0) bulk_load(s_tab, S.fused_tab, FusedTables::FLOATS * sizeof(float), s_tabbar);
+    if (tid == 0) {
+        mbar_arrive_expect_tx(s_tabbar, FusedTables::FLOATS * sizeof(float));
+        bulk_g2s(s_tab, S.fused_tab, FusedTables::FLOATS * sizeof(float), s_tabbar);
+    }
 
     int first = lo;
     {
         const DevFrame f0 = a.frames[lo];
         if (f0.prev >= 0 && (f0.ola_len > 0 || f0.kind != 0)) first = lo - 1;   // halo: previous block's tail is needed
     }
+
+    // Claims the slot of frame xx for this warp and starts the bulk copies of its spectrum rows into it.
+    // Every frame completes one phase of s_in[slot], so a slot's phase number equals its revolution count.
+    auto stage_frame = [&](int xx) {
+        const int rel_ = xx - first, slot_ = rel_ % NS;
+        cnt_wait(&s_empty[slot_], 2 * (rel_ / NS));                          // both readers of every earlier frame of the slot are done
+        if (lane == 0) {
+            const DevFrame fr = a.frames[xx];
+            s_fr[slot_] = fr;
+            if (fr.kind == 0) {
+                const uint32_t row = (uint32_t)(fr.n >> 1) * sizeof(float);
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&s_in[slot_], row * C);
+                for (int c = 0; c < C; c++)
+                    bulk_g2s(s_slots + ((size_t)slot_ * C + c) * FUSED_SLOT_FLOATS, a.spectrum + (size_t)fr.spec_off + (size_t)c * (fr.n >> 1), row, &s_in[slot_]);
+            } else mbar_arrive(&s_in[slot_]);
+        }
+        __syncwarp();
+    };
+    if (first + warp < hi) stage_frame(first + warp);
     mbar_wait(s_tabbar, 0);
 
     const float2* s_tw0 = reinterpret_cast<const float2*>(s_tab + FusedTables::TW0);
@@ -135,9 +170,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
 
     for (int x = first + warp; x < hi; x += FUSED_WARPS) {
         const int rel = x - first, slot = rel % NS, it = rel / NS;
-        cnt_wait(&s_empty[slot], 2 * it);                                    // both readers of every earlier frame of the slot are done
-        if (lane == 0) s_fr[slot] = a.frames[x];
-        __syncwarp();
+        // the warp's next frame: stage it as early as its slot is free (three attempts, the last one blocking)
+        const int xn = x + FUSED_WARPS;
+        const int nslot = (xn - first) % NS, nneed = 2 * ((xn - first) / NS);
+        bool staged = xn >= hi;
+        if (!staged && __shfl_sync(0xffffffffu, (int)cnt_ready(&s_empty[nslot], nneed), 0)) { stage_frame(xn); staged = true; }
+        mbar_wait(&s_in[slot], it & 1);                                      // this frame's rows have landed
         const DevFrame f = s_fr[slot];
         float* slots_f = s_slots + (size_t)slot * C * FUSED_SLOT_FLOATS;
 
@@ -145,14 +183,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
         if (f.kind == 0) {
             for (int c = 0; c < C; c++) {
                 float* slotc = slots_f + (size_t)c * FUSED_SLOT_FLOATS;
-                const int M = f.n >> 1;
-                const float* spec = a.spectrum + (size_t)f.spec_off + (size_t)c * M;
                 if (!((f.exec_mask >> c) & 1u)) {
-                    for (int i = lane; i < M; i += 32) slotc[i] = spec[i];         // raw residue values (Mapping.cs:192-196)
+                    // the slot already holds the raw residue values this channel keeps (Mapping.cs:192-196)
                 } else if (f.n == FUSED_LONG_N) {
                     float2* ex = reinterpret_cast<float2*>(slotc);
                     LongRegs R;
-                    long_phase1(lane, reinterpret_cast<const float2*>(spec), s_tab, ex);
+                    {
+                        LongIn in;
+                        long_phase1_load(lane, ex, in);
+                        __syncwarp();                                       // in place: every lane has read its inputs
+                        long_phase1_store(lane, in, s_tab, ex);
+                    }
                     __syncwarp();
                     long_phase2_load(lane, ex, R);
                     __syncwarp();
@@ -163,7 +204,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
                     long_phase3_store(lane, s_tab, ex, R);
                 } else {
                     ShortRegs R;
-                    short_phase1(lane, spec, s_tw0, s_w64, R);
+                    short_phase1(lane, slotc, s_tw0, s_w64, R);            // the shuffles below order these reads before the stores
                     #pragma unroll
                     for (int s = 16; s >= 1; s >>= 1) {
                         cpx pa, pb;
@@ -178,6 +219,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
         }
         __syncwarp();
         if (lane == 0) cnt_signal(&s_full[slot]);                            // u of frame x is complete
+        if (!staged && __shfl_sync(0xffffffffu, (int)cnt_ready(&s_empty[nslot], nneed), 0)) { stage_frame(xn); staged = true; }
 
         // ---------------- output of frame x (a halo block only leaves its tail) --------------------
         if (x >= lo) {
@@ -258,6 +300,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
             cnt_signal(&s_empty[slot]);                                      // done with frame x as "current"
             if (rel >= 1) cnt_signal(&s_empty[(rel - 1) % NS]);              // done with frame x-1 as "previous"
         }
+        if (!staged) stage_frame(xn);
     }
     if (__any_sync(0xffffffffu, peak > 0.99999994f) && lane == 0) atomicOr(&a.counters->clipped, 1);
 }
@@ -265,13 +308,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
 // ------------------------------------------------------------------------------------------------
 static int fused_slots(int C) {
     const size_t fixed = FusedTables::FLOATS * sizeof(float) + 64;
-    const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
+    const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int) + sizeof(uint64_t);
     int ns = (int)((FUSED_SMEM_LIMIT - fixed) / per);
     if (ns > FUSED_WARPS + 2) ns = FUSED_WARPS + 2;
     return ns;
 }
 static size_t fused_smem(int C, int NS) {
-    return FusedTables::FLOATS * sizeof(float) + (size_t)NS * ((size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int)) + 32;
+    return FusedTables::FLOATS * sizeof(float) + (size_t)NS * ((size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int) + sizeof(uint64_t)) + 32;
 }
 
 bool fused_supported(const BlobHeader& h, const DevFrame*, int) {

@@ -73,20 +73,24 @@ NVB_HD cpx ld_cpx(const float4& v, int hi) { cpx r; r.x = hi ? v.z : v.x; r.y = 
 struct LongRegs { cpx a[8]; cpx b[8]; };
 
 // ---- phase 1: load spectrum pairs, pre-twiddle, radix-8 over k2, twiddle W512^(r*m2), store ex1
-// spec2: the channel's spectrum as float2[512]; tab: FusedTables in shared memory; ex: float2[576].
-NVB_HD void long_phase1(int l, const float2* spec2, const float* tab, float2* ex) {
+// spec2: the channel's spectrum as float2[512] -- in the kernel it sits in the slot itself (bulk-copied there),
+// so the loads and the stores are separate calls with a warp barrier between them.
+struct LongIn { float2 pa[8], pb[8]; };
+NVB_HD void long_phase1_load(int l, const float2* spec2, LongIn& in) {
     const int ra = l, rb = 63 - l;
-    float2 pa[8], pb[8];
     #pragma unroll
-    for (int k2 = 0; k2 < 8; k2++) { pa[k2] = spec2[64 * k2 + ra]; pb[k2] = spec2[64 * k2 + rb]; }
+    for (int k2 = 0; k2 < 8; k2++) { in.pa[k2] = spec2[64 * k2 + ra]; in.pb[k2] = spec2[64 * k2 + rb]; }
+}
+NVB_HD void long_phase1_store(int l, const LongIn& in, const float* tab, float2* ex) {
+    const int ra = l, rb = 63 - l;
     const float4* T1 = reinterpret_cast<const float4*>(tab + FusedTables::T1);
     const float4* T2 = reinterpret_cast<const float4*>(tab + FusedTables::T2);
     LongRegs R;
     #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) {
         cpx ca, cb;
-        ca.x = pa[k2].x; ca.y = pb[7 - k2].y;          // X[2k] + i X[M-1-2k], k = 64 k2 + l
-        cb.x = pb[k2].x; cb.y = pa[7 - k2].y;          // k = 64 k2 + 63 - l
+        ca.x = in.pa[k2].x; ca.y = in.pb[7 - k2].y;    // X[2k] + i X[M-1-2k], k = 64 k2 + l
+        cb.x = in.pb[k2].x; cb.y = in.pa[7 - k2].y;    // k = 64 k2 + 63 - l
         const float4 w = T1[k2 * 32 + l];
         R.a[k2] = cmul(ca, ld_cpx(w, 0));
         R.b[k2] = cmul(cb, ld_cpx(w, 1));

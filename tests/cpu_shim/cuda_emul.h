@@ -118,7 +118,18 @@ static inline void cnt_wait(const int* c, int need) {
         if (spins < 64) std::this_thread::yield(); else std::this_thread::sleep_for(std::chrono::microseconds(200));
     }
 }
-static inline void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { std::memcpy(dst, src, bytes); mbar_arrive(bar); }
+static inline bool cnt_ready(const int* c, int need) { return __atomic_load_n(c, __ATOMIC_SEQ_CST) >= need; }
+// bulk copies are emulated synchronously by the issuing thread; the arrival that announces the bytes is deferred
+// until the last announced byte has been copied, as the transaction count of a real mbarrier does
+namespace cuemu { inline thread_local uint64_t* tx_bar = nullptr; inline thread_local uint32_t tx_left = 0; }
+static inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { cuemu::tx_bar = bar; cuemu::tx_left = bytes; if (bytes == 0) mbar_arrive(bar); }
+static inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    std::memcpy(dst, src, bytes);
+    if (bar != cuemu::tx_bar || bytes > cuemu::tx_left) std::abort();
+    cuemu::tx_left -= bytes;
+    if (cuemu::tx_left == 0) mbar_arrive(bar);
+}
+static inline void fence_proxy_async() {}
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
