@@ -266,6 +266,7 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
             const int lv = 1 + (d.level[d.lo[k]] > d.level[d.hi[k]] ? d.level[d.lo[k]] : d.level[d.hi[k]]);
             d.level[k] = (uint8_t)lv;
             if (lv > d.max_level) d.max_level = lv;
+            d.rcp[k] = 1.0f / (float)((int)d.x[d.hi[k]] - (int)d.x[d.lo[k]]);
         }
         w.at<DevFloor1>(h.off_floors)[i] = d;
     }

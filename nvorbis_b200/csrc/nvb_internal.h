@@ -26,6 +26,7 @@ struct DevFloor1  {
     int32_t n_posts, mult, range, max_level;
     uint16_t x[NVB_MAX_POSTS]; uint8_t lo[NVB_MAX_POSTS], hi[NVB_MAX_POSTS], sort[NVB_MAX_POSTS];
     uint8_t level[NVB_MAX_POSTS];   // depth of post i in the neighbour dependency tree: 1 + max(level[lo], level[hi]); posts 0, 1 are level 0
+    float rcp[NVB_MAX_POSTS];       // 1.0f / (x[hi[i]] - x[lo[i]]): RenderPoint's divisor is a setup constant
 };
 struct DevResidue {
     int32_t type, begin, end, psize, nclass, stages;

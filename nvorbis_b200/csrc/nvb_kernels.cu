@@ -126,22 +126,35 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
 // ------------------------------------------------------------------------------------------------
 struct SegRec { int16_t x0, x1; int32_t y0, b; int16_t ady, sy; float rcp; };
 
+// floor(num / den) for 0 <= num < 2^22 with rcp = 1.0f / den: float estimate (exact operands), one-step correction.
+__device__ __forceinline__ int div_small(int num, int den, float rcp) {
+    int q = __float2int_rz(__int2float_rn(num) * rcp);
+    const int rem = num - q * den;
+    if (rem >= den) ++q; else if (rem < 0) --q;
+    return q;
+}
+
 __device__ __forceinline__ void floor1_segments_warp(const DevFloor1& F, const int16_t* posts, int n, int lane, int* fy, SegRec* segs, int* nseg_out) {
     int count = posts[0];
     if (count > F.n_posts) count = F.n_posts;
     if (count < 2) { if (lane == 0) *nseg_out = 0; return; }             // PostCount == 0: the spectrum is cleared (Floor1.cs:220)
+    const int H = count > 32 ? 2 : 1;                                    // posts lane and lane + 32
     int val[2]; unsigned long long contrib = 0ull;
     #pragma unroll
     for (int h = 0; h < 2; h++) { const int i = lane + 32 * h; val[h] = i < count ? posts[1 + i] : 0; }
     if (lane < 2) fy[lane] = val[0];
     __syncwarp();
     for (int lvl = 1; lvl <= F.max_level; lvl++) {
-        #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < H; h++) {
             const int i = lane + 32 * h;
             if (i >= 2 && i < count && F.level[i] == lvl) {
                 const int lo = F.lo[i], hi = F.hi[i];
-                const int predicted = render_point(F.x[lo], fy[lo], F.x[hi], fy[hi], F.x[i]);
+                // RenderPoint (Floor1.cs:299-314): y0 +- |dy| * (X - x0) / adx, the division by the setup constant adx
+                const int x0 = F.x[lo], adx = F.x[hi] - x0, y0 = fy[lo];
+                const int dy = fy[hi] - y0, ady = dy < 0 ? -dy : dy;
+                const int err = ady * (F.x[i] - x0);
+                const int off = (unsigned)err < (1u << 22) ? div_small(err, adx, F.rcp[i]) : err / adx;
+                const int predicted = dy < 0 ? y0 - off : y0 + off;
                 const int v = val[h];
                 const int highroom = F.range - predicted, lowroom = predicted;
                 const int room = (highroom < lowroom ? highroom : lowroom) * 2;
@@ -181,9 +194,11 @@ __device__ __forceinline__ void floor1_segments_warp(const DevFloor1& F, const i
                 const int ly = fy[pidx] * F.mult, hx = F.x[idx[h]], hy = fy[idx[h]] * F.mult;
                 const int x1 = hx < n ? hx : n;                             // x clamped, y NOT re-interpolated (Floor1.cs:206)
                 const int dy = hy - ly, adx = x1 - lx;
-                const int b = dy / adx, ab = b < 0 ? -b : b;
-                SegRec r; r.x0 = (int16_t)lx; r.x1 = (int16_t)x1; r.y0 = ly; r.b = b;
-                r.ady = (int16_t)((dy < 0 ? -dy : dy) - ab * adx); r.sy = (int16_t)(dy < 0 ? -1 : 1); r.rcp = 1.0f / (float)adx;
+                const float rcp = 1.0f / (float)adx;
+                const int ady = dy < 0 ? -dy : dy;
+                const int ab = (unsigned)ady < (1u << 22) ? div_small(ady, adx, rcp) : ady / adx;      // |dy / adx|, truncated like the C# division
+                SegRec r; r.x0 = (int16_t)lx; r.x1 = (int16_t)x1; r.y0 = ly; r.b = dy < 0 ? -ab : ab;
+                r.ady = (int16_t)(ady - ab * adx); r.sy = (int16_t)(dy < 0 ? -1 : 1); r.rcp = rcp;
                 segs[__popcll(below) - 1] = r;
             }
         }
@@ -206,8 +221,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
     NVB_DYN_SMEM(dyn_smem);
     __shared__ float s_db[256];
     __shared__ int s_fy[NVB_MAX_CHANNELS][NVB_MAX_POSTS];
-    __shared__ SegRec s_seg[NVB_MAX_CHANNELS][NVB_MAX_POSTS + 1];
-    __shared__ int s_nseg[NVB_MAX_CHANNELS];
+    __shared__ SegRec s_seg[NVB_MAX_CHANNELS * (NVB_MAX_POSTS + 1)];
+    __shared__ int s_nseg[NVB_MAX_CHANNELS + 1];
     __shared__ int s_bad[2];
 
     const DevFrame f = a.frames[blockIdx.x];
@@ -233,125 +248,150 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
 
     // ---- phase A
     if (warp == NW - 1) {
-        // entry-stream prefix over the items in decode order (stage, partition, stream): warp scan, 32 items a step
+        // entry-stream prefix over the items in decode order (stage, partition, stream): per stage, lanes over
+        // (partition, stream), warp scan of the per-item entry counts
         uint32_t run = 0;
         const int per_stage = g.P * g.Sx;
-        for (int base = 0; base < g.n_items; base += 32) {
-            const int i = base + lane;
-            uint32_t c = 0;
-            if (i < g.n_items) {
-                const int s = i / per_stage, rem = i - s * per_stage;
-                const int p = rem / g.Sx, st = rem - p * g.Sx;
-                const int cl = cls[st * g.P + p];
-                if (cl < R.nclass) c = (uint32_t)R.cnt[cl][s];
+        for (int s = 0; s < R.stages && per_stage > 0; s++) {
+            for (int base = 0; base < per_stage; base += 32) {
+                const int i = base + lane;
+                uint32_t c = 0;
+                if (i < per_stage) {
+                    int p = i, st = 0;
+                    if (g.Sx > 1) { p = i / g.Sx; st = i - p * g.Sx; }
+                    const int cl = cls[st * g.P + p];
+                    if (cl < R.nclass) c = (uint32_t)R.cnt[cl][s];
+                }
+                uint32_t incl = c;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+                if (i < per_stage) prefix[s * per_stage + i] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
             }
-            uint32_t incl = c;
-            #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-            if (i < g.n_items) prefix[i] = run + incl - c;
-            run += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
     for (int c = warp; c < C; c += NW) {                                    // the prefix warp also takes a channel only when C == NW
         if ((f.exec_mask >> c) & 1u)
-            floor1_segments_warp(F, a.posts + ((size_t)f.api_index * C + c) * S.post_stride, n, lane, s_fy[c], s_seg[c], &s_nseg[c]);
+            floor1_segments_warp(F, a.posts + ((size_t)f.api_index * C + c) * S.post_stride, n, lane, s_fy[c], s_seg + c * (NVB_MAX_POSTS + 1), &s_nseg[c]);
         else if (lane == 0) s_nseg[c] = 0;
     }
     __syncthreads();
 
-    // ---- phase B: floor curve rows
+    // ---- phase B: floor curve rows; (channel, segment) units round-robin over the warps, lanes over x
     int bad_floor = 0;
     {
-        int u = warp;
-        for (int c = 0; c < C; c++) {
-            const int ns = s_nseg[c];
-            for (; u < ns; u += NW) {
-                const SegRec r = s_seg[c][u];
-                const int x0 = r.x0, len = r.x1 - r.x0;
-                for (int k = lane; k < len; k += 32) {
-                    const int num = k * r.ady;                              // < 2^20: exact in float
-                    int q = __float2int_rz(__int2float_rn(num) * r.rcp);
-                    int rem = num - q * len;
-                    if (rem >= len) ++q; else if (rem < 0) --q;
-                    int y = r.y0 + k * r.b + r.sy * q;
-                    if (y < 0 || y > 255) { bad_floor = 1; y = y < 0 ? 0 : 255; }
-                    s_fl[c * n + x0 + k] = s_db[y];
-                }
+        int c = 0, first_u = 0, ns = s_nseg[0];
+        int total = 0;
+        for (int k = 0; k < C; k++) total += s_nseg[k];
+        for (int u = warp; u < total; u += NW) {
+            while (u - first_u >= ns) { first_u += ns; ++c; ns = s_nseg[c]; }
+            const SegRec r = s_seg[c * (NVB_MAX_POSTS + 1) + (u - first_u)];
+            const int len = r.x1 - r.x0;
+            float* row = s_fl + c * n + r.x0;
+            for (int k = lane; k < len; k += 32) {
+                const int q = div_small(k * r.ady, len, r.rcp);             // k * ady < 2^20
+                int y = r.y0 + k * r.b + r.sy * q;                          // RenderLineMulti in closed form (Floor1.cs:316-341)
+                if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
+                row[k] = s_db[y];
             }
-            u -= ns;
         }
     }
     __syncthreads();
 
-    // ---- phase C: residue gather + coupling + floor multiply
+    // ---- phase C: residue values in the reference's add order, inverse coupling, floor multiply
     int bad_entry = 0;
     const int pshift = R.pshift, pmask = R.psize - 1;
-    for (int j = t; j < n; j += SPEC_THREADS) {
-        float r[NVB_MAX_CHANNELS];
-        #pragma unroll
-        for (int c = 0; c < NVB_MAX_CHANNELS; c++) r[c] = 0.f;
-        if (g.P > 0) {
-            if (R.type == 2) {
-                // interleaved position of channel 0 of this bin; all C channels sit in one partition (aligned, host-checked)
-                const int q = j * C - R.begin;
-                const int p = q >> pshift;
-                if (q >= 0 && p < g.P) {
-                    const int o = q & pmask;
-                    const int cl = cls[p];
-                    if (cl < R.nclass) {
-                        const int casc = R.cascade[cl];
-                        for (int s = 0; s < R.stages; s++) {
-                            if (!((casc >> s) & 1)) continue;
-                            const int book = R.books[cl][s];
-                            if (book < 0) continue;
-                            const DevBook b = S.books[book];
-                            const uint32_t base = prefix[s * g.P + p];
-                            #pragma unroll
-                            for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
-                                if (c >= C) break;
-                                const int e = o + c;
-                                r[c] = NVB_FADD(r[c], vq_fetch(b, S.vq, ent, base + (uint32_t)(e >> b.dshift), f.entry_count, e & (b.dims - 1), &bad_entry));
-                            }
-                        }
-                    }
+    float* spec_out = a.spectrum + (size_t)f.spec_off;
+    if (R.type == 2 && g.P > 0) {
+        // Residue type 2 (Residue2.cs:23-47): a warp per partition, lane = interleaved element; element j belongs to channel
+        // j % C of bin ob + j / C.  C is a power of two here (it divides the power-of-two partition size), so the
+        // channels of one bin sit in C adjacent lanes and inverse coupling is a lane exchange.
+        const int cshift = ilog_u(C) - 1, cmask = C - 1;
+        const int psize = R.psize, bins_per = psize >> cshift, ob0 = R.begin >> cshift;
+        for (int p = warp; p < g.P; p += NW) {
+            const int cl = cls[p];
+            const int casc = cl < R.nclass ? R.cascade[cl] : 0;
+            for (int j0 = 0; j0 < psize; j0 += 32) {
+                const int j = j0 + lane;
+                const bool live = j < psize;
+                float acc = 0.f;
+                for (int s = 0; s < R.stages; s++) {
+                    if (!((casc >> s) & 1)) continue;
+                    const int book = R.books[cl][s];
+                    if (book < 0) continue;
+                    const DevBook b = S.books[book];
+                    const uint32_t base = prefix[s * g.P + p];
+                    if (live) acc = NVB_FADD(acc, vq_fetch(b, S.vq, ent, base + (uint32_t)(j >> b.dshift), f.entry_count, j & (b.dims - 1), &bad_entry));
                 }
-            } else {
-                const int q = j - R.begin;
-                const int p = q >> pshift;
-                if (q >= 0 && p < g.P) {
-                    const int o = q & pmask;
-                    #pragma unroll
-                    for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
-                        if (c >= C) break;
-                        const int cl = cls[c * g.P + p];
-                        if (cl >= R.nclass) continue;
-                        const int casc = R.cascade[cl];
-                        for (int s = 0; s < R.stages; s++) {
-                            if (!((casc >> s) & 1)) continue;
-                            const int book = R.books[cl][s];
-                            if (book < 0) continue;
-                            const DevBook b = S.books[book];
-                            const uint32_t base = prefix[(s * g.P + p) * g.Sx + c];
-                            if (R.type == 1) r[c] = NVB_FADD(r[c], vq_fetch(b, S.vq, ent, base + (uint32_t)(o >> b.dshift), f.entry_count, o & (b.dims - 1), &bad_entry));
-                            else {                                          // type 0: element (dim, step) at dim*steps + step (Residue0.cs:193-199)
-                                const int sshift = pshift - b.dshift;
-                                r[c] = NVB_FADD(r[c], vq_fetch(b, S.vq, ent, base + (uint32_t)(o & ((1 << sshift) - 1)), f.entry_count, o >> sshift, &bad_entry));
-                            }
-                        }
-                    }
+                const int c = j & cmask, bin = ob0 + p * bins_per + (j >> cshift);
+                const int grp = lane & ~cmask;
+                for (int i = mp.n_coupling - 1; i >= 0; --i) {              // Mapping.cs:137-182
+                    const int m = mp.mag[i], an = mp.ang[i];
+                    if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
+                    float vm = __shfl_sync(0xffffffffu, acc, grp + m), va = __shfl_sync(0xffffffffu, acc, grp + an);
+                    inverse_couple(vm, va);
+                    if (c == m) acc = vm; else if (c == an) acc = va;
+                }
+                if (live) {
+                    float v = acc;
+                    if ((f.exec_mask >> c) & 1u) v = s_nseg[c] > 0 ? NVB_FMUL(v, s_fl[c * n + bin]) : 0.f;      // Floor1.Apply, Floor1.cs:186-222
+                    spec_out[(size_t)c * n + bin] = v;
                 }
             }
         }
-        for (int i = mp.n_coupling - 1; i >= 0; --i) {                      // Mapping.cs:137-182
-            const int m = mp.mag[i], an = mp.ang[i];
-            if (((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u) inverse_couple(r[m], r[an]);
+        // bins no partition reaches keep the cleared value (Mapping.cs:108); coupling and the floor leave zero at zero
+        const int lo_bin = ob0, hi_bin = ob0 + g.P * bins_per;
+        for (int idx = t; idx < C * n; idx += SPEC_THREADS) {
+            const int c = idx / n, bin = idx - c * n;
+            if (bin < lo_bin || bin >= hi_bin) spec_out[(size_t)c * n + bin] = 0.f;
         }
-        #pragma unroll
-        for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
-            if (c >= C) break;
-            float v = r[c];
-            if ((f.exec_mask >> c) & 1u) v = s_nseg[c] > 0 ? NVB_FMUL(v, s_fl[c * n + j]) : 0.f;      // Floor1.Apply, Floor1.cs:186-222
-            a.spectrum[(size_t)f.spec_off + (size_t)c * n + j] = v;
+    } else {
+        for (int j = t; j < n; j += SPEC_THREADS) {
+            float r[NVB_MAX_CHANNELS];
+            #pragma unroll
+            for (int c = 0; c < NVB_MAX_CHANNELS; c++) r[c] = 0.f;
+            const int q = j - R.begin;
+            const int p = q >> pshift;
+            if (g.P > 0 && q >= 0 && p < g.P) {
+                const int o = q & pmask;
+                for (int c = 0; c < C; c++) {
+                    const int cl = cls[c * g.P + p];
+                    if (cl >= R.nclass) continue;
+                    const int casc = R.cascade[cl];
+                    float acc = 0.f;
+                    for (int s = 0; s < R.stages; s++) {
+                        if (!((casc >> s) & 1)) continue;
+                        const int book = R.books[cl][s];
+                        if (book < 0) continue;
+                        const DevBook b = S.books[book];
+                        const uint32_t base = prefix[(s * g.P + p) * g.Sx + c];
+                        if (R.type == 1) acc = NVB_FADD(acc, vq_fetch(b, S.vq, ent, base + (uint32_t)(o >> b.dshift), f.entry_count, o & (b.dims - 1), &bad_entry));
+                        else {                                              // type 0: element (dim, step) at dim*steps + step (Residue0.cs:193-199)
+                            const int sshift = pshift - b.dshift;
+                            acc = NVB_FADD(acc, vq_fetch(b, S.vq, ent, base + (uint32_t)(o & ((1 << sshift) - 1)), f.entry_count, o >> sshift, &bad_entry));
+                        }
+                    }
+                    #pragma unroll
+                    for (int k = 0; k < NVB_MAX_CHANNELS; k++) if (k == c) r[k] = acc;
+                }
+            }
+            for (int i = mp.n_coupling - 1; i >= 0; --i) {                  // Mapping.cs:137-182
+                const int m = mp.mag[i], an = mp.ang[i];
+                if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
+                float vm = 0.f, va = 0.f;
+                #pragma unroll
+                for (int k = 0; k < NVB_MAX_CHANNELS; k++) { if (k == m) vm = r[k]; if (k == an) va = r[k]; }
+                inverse_couple(vm, va);
+                #pragma unroll
+                for (int k = 0; k < NVB_MAX_CHANNELS; k++) { if (k == m) r[k] = vm; if (k == an) r[k] = va; }
+            }
+            #pragma unroll
+            for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
+                if (c >= C) break;
+                float v = r[c];
+                if ((f.exec_mask >> c) & 1u) v = s_nseg[c] > 0 ? NVB_FMUL(v, s_fl[c * n + j]) : 0.f;      // Floor1.Apply, Floor1.cs:186-222
+                spec_out[(size_t)c * n + j] = v;
+            }
         }
     }
     if (bad_entry) atomicOr(&s_bad[0], 1);
