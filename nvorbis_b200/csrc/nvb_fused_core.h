@@ -69,8 +69,12 @@ NVB_HD int u_swz(int i) { return i ^ (((i >> 5) & 3) << 2); }                   
 
 NVB_HD cpx ld_cpx(const float4& v, int hi) { cpx r; r.x = hi ? v.z : v.x; r.y = hi ? v.w : v.y; return r; }
 
-// Registers of one lane while it transforms one long block: two radix-8 columns.
-struct LongRegs { cpx a[8]; cpx b[8]; };
+// One lane owns two radix-8 columns ("a" and "b") of every pass.  They are processed one after the other so that
+// only one column (8 complex values) plus the pass's inputs is live: the kernel runs 32 warps of 64 registers per SM.
+NVB_HD float2 tab2(const float* tab, int base, int row, int l, int col) {
+    return reinterpret_cast<const float2*>(tab + base)[(row * 32 + l) * 2 + col];
+}
+NVB_HD cpx to_cpx(float2 v) { cpx r; r.x = v.x; r.y = v.y; return r; }
 
 // ---- phase 1: load spectrum pairs, pre-twiddle, radix-8 over k2, twiddle W512^(r*m2), store ex1
 // spec2: the channel's spectrum as float2[512] -- in the kernel it sits in the slot itself (bulk-copied there),
@@ -81,88 +85,63 @@ NVB_HD void long_phase1_load(int l, const float2* spec2, LongIn& in) {
     #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) { in.pa[k2] = spec2[64 * k2 + ra]; in.pb[k2] = spec2[64 * k2 + rb]; }
 }
-NVB_HD void long_phase1_store(int l, const LongIn& in, const float* tab, float2* ex) {
-    const int ra = l, rb = 63 - l;
-    const float4* T1 = reinterpret_cast<const float4*>(tab + FusedTables::T1);
-    const float4* T2 = reinterpret_cast<const float4*>(tab + FusedTables::T2);
-    LongRegs R;
+NVB_HD void long_phase1_col(int l, int col, const LongIn& in, const float* tab, float2* ex) {
+    const int r = col ? 63 - l : l;
+    cpx R[8];
     #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) {
-        cpx ca, cb;
-        ca.x = in.pa[k2].x; ca.y = in.pb[7 - k2].y;    // X[2k] + i X[M-1-2k], k = 64 k2 + l
-        cb.x = in.pb[k2].x; cb.y = in.pa[7 - k2].y;    // k = 64 k2 + 63 - l
-        const float4 w = T1[k2 * 32 + l];
-        R.a[k2] = cmul(ca, ld_cpx(w, 0));
-        R.b[k2] = cmul(cb, ld_cpx(w, 1));
+        cpx c;                                              // X[2k] + i X[M-1-2k], k = 64 k2 + r
+        c.x = col ? in.pb[k2].x : in.pa[k2].x;
+        c.y = col ? in.pa[7 - k2].y : in.pb[7 - k2].y;
+        R[k2] = cmul(c, to_cpx(tab2(tab, FusedTables::T1, k2, l, col)));
     }
-    fft8(R.a); fft8(R.b);
-    ex[ra] = make_float2(R.a[0].x, R.a[0].y);
-    ex[rb] = make_float2(R.b[0].x, R.b[0].y);
+    fft8(R);
+    ex[r] = make_float2(R[0].x, R[0].y);
     #pragma unroll
     for (int m2 = 1; m2 < 8; m2++) {
-        const float4 w = T2[(m2 - 1) * 32 + l];
-        const cpx va = cmul(R.a[m2], ld_cpx(w, 0)), vb = cmul(R.b[m2], ld_cpx(w, 1));
-        ex[m2 * 72 + ra] = make_float2(va.x, va.y);
-        ex[m2 * 72 + rb] = make_float2(vb.x, vb.y);
+        const cpx v = cmul(R[m2], to_cpx(tab2(tab, FusedTables::T2, m2 - 1, l, col)));
+        ex[m2 * 72 + r] = make_float2(v.x, v.y);
     }
 }
 
-// ---- phase 2: gather the 8 k1 of (m2, k0) for two m2; radix-8 over k1, twiddle W64^(k0*m1), store ex2
-NVB_HD void long_phase2_load(int l, const float2* ex, LongRegs& R) {
-    const int m2 = l >> 3, k0 = l & 7;
+// ---- phase 2: gather the 8 k1 of (m2, k0); radix-8 over k1, twiddle W64^(k0*m1), store ex2.  Column a works on
+// rows 0-3, column b on rows 4-7; a row is shared by the 8 lanes with the same l >> 3, hence the warp barrier
+// between a column's loads and its stores.
+NVB_HD void long_phase2_load(int l, int col, const float2* ex, cpx* R) {
+    const int m2 = (l >> 3) + 4 * col, k0 = l & 7;
     #pragma unroll
-    for (int k1 = 0; k1 < 8; k1++) {
-        float2 va = ex[m2 * 72 + 8 * k1 + k0], vb = ex[(m2 + 4) * 72 + 8 * k1 + k0];
-        R.a[k1].x = va.x; R.a[k1].y = va.y; R.b[k1].x = vb.x; R.b[k1].y = vb.y;
-    }
+    for (int k1 = 0; k1 < 8; k1++) R[k1] = to_cpx(ex[m2 * 72 + 8 * k1 + k0]);
 }
-NVB_HD void long_phase2_store(int l, const float* tab, float2* ex, LongRegs& R) {
-    const int m2 = l >> 3, k0 = l & 7;
-    const float4* T3 = reinterpret_cast<const float4*>(tab + FusedTables::T3);
-    fft8(R.a); fft8(R.b);
-    ex[m2 * 72 + k0] = make_float2(R.a[0].x, R.a[0].y);
-    ex[(m2 + 4) * 72 + k0] = make_float2(R.b[0].x, R.b[0].y);
+NVB_HD void long_phase2_store(int l, int col, const float* tab, float2* ex, cpx* R) {
+    const int m2 = (l >> 3) + 4 * col, k0 = l & 7;
+    fft8(R);
+    ex[m2 * 72 + k0] = make_float2(R[0].x, R[0].y);
     #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const float4 w = T3[j * 32 + l];
-        #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int m1 = 2 * j + 1 + h;
-            if (m1 > 7) break;
-            const cpx t = ld_cpx(w, h);
-            const cpx va = cmul(R.a[m1], t), vb = cmul(R.b[m1], t);
-            ex[m2 * 72 + m1 * 9 + k0] = make_float2(va.x, va.y);
-            ex[(m2 + 4) * 72 + m1 * 9 + k0] = make_float2(vb.x, vb.y);
-        }
+    for (int m1 = 1; m1 < 8; m1++) {
+        const cpx v = cmul(R[m1], to_cpx(tab2(tab, FusedTables::T3, (m1 - 1) >> 1, l, (m1 - 1) & 1)));
+        ex[m2 * 72 + m1 * 9 + k0] = make_float2(v.x, v.y);
     }
 }
 
-// ---- phase 3: gather the 8 k0 of (m2, m1) and of (7-m2, 7-m1); radix-8 over k0, post-twiddle,
-// write u as float2 pairs (u[2n], u[2n+1]) = (Re D[n], -Im D[511-n]), swizzled (u_swz2).
-NVB_HD void long_phase3_load(int l, const float2* ex, LongRegs& R) {
-    const int m2 = l >> 3, m1 = l & 7;
+// ---- phase 3: gather the 8 k0 of (m2, m1) [column a] and of (7-m2, 7-m1) [column b]; radix-8 over k0, post-twiddle.
+// The results of both columns pair up in the stores (u[2n], u[2n+1]) = (Re D[n], -Im D[511-n]), swizzled (u_swz2);
+// the stores overwrite exchange space, so they follow a warp barrier.
+NVB_HD void long_phase3_col(int l, int col, const float* tab, const float2* ex, cpx* R) {
+    const int m2 = col ? 7 - (l >> 3) : (l >> 3), m1 = col ? 7 - (l & 7) : (l & 7);
     #pragma unroll
-    for (int k0 = 0; k0 < 8; k0++) {
-        float2 va = ex[m2 * 72 + m1 * 9 + k0], vb = ex[(7 - m2) * 72 + (7 - m1) * 9 + k0];
-        R.a[k0].x = va.x; R.a[k0].y = va.y; R.b[k0].x = vb.x; R.b[k0].y = vb.y;
-    }
+    for (int k0 = 0; k0 < 8; k0++) R[k0] = to_cpx(ex[m2 * 72 + m1 * 9 + k0]);
+    fft8(R);
+    #pragma unroll
+    for (int m0 = 0; m0 < 8; m0++) R[m0] = cmul(R[m0], to_cpx(tab2(tab, FusedTables::T4, m0, l, col)));
 }
-NVB_HD void long_phase3_store(int l, const float* tab, float2* u2, LongRegs& R) {
-    const float4* T4 = reinterpret_cast<const float4*>(tab + FusedTables::T4);
-    fft8(R.a); fft8(R.b);
-    #pragma unroll
-    for (int m0 = 0; m0 < 8; m0++) {
-        const float4 w = T4[m0 * 32 + l];
-        R.a[m0] = cmul(R.a[m0], ld_cpx(w, 0));
-        R.b[m0] = cmul(R.b[m0], ld_cpx(w, 1));
-    }
+NVB_HD void long_phase3_store(int l, float2* u2, const cpx* Ra, const cpx* Rb) {
     // n = na0 + 64 m0 and its partner 511 - n = nb0 + 64 (7 - m0), nb0 = 63 - na0; the swizzle only looks at
     // bits 4-5 of n, which belong to na0 / nb0
     const int sa = u_swz2(fused_na0(l)), sb = u_swz2(fused_nb0(l));
     #pragma unroll
     for (int m0 = 0; m0 < 8; m0++) {
-        u2[sa + 64 * m0] = make_float2(R.a[m0].x, -R.b[7 - m0].y);
-        u2[sb + 64 * (7 - m0)] = make_float2(R.b[7 - m0].x, -R.a[m0].y);
+        u2[sa + 64 * m0] = make_float2(Ra[m0].x, -Rb[7 - m0].y);
+        u2[sb + 64 * (7 - m0)] = make_float2(Rb[7 - m0].x, -Ra[m0].y);
     }
 }
 

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
     int bad_entry = 0;
     const int pshift = R.pshift, pmask = R.psize - 1;
     float* spec_out = a.spectrum + (size_t)f.spec_off;
-    if (R.type == 2 && g.P > 0) {
+    if (false && R.type == 2 && g.P > 0) {
         // Residue type 2 (Residue2.cs:23-47): a warp per partition, lane = interleaved element; element j belongs to channel
         // j % C of bin ob + j / C.  C is a power of two here (it divides the power-of-two partition size), so the
         // channels of one bin sit in C adjacent lanes and inverse coupling is a lane exchange.
@@ -350,6 +350,31 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
             float r[NVB_MAX_CHANNELS];
             #pragma unroll
             for (int c = 0; c < NVB_MAX_CHANNELS; c++) r[c] = 0.f;
+            if (R.type == 2) {
+                // interleaved position of channel 0 of this bin; all C channels sit in one partition (aligned, host-checked)
+                const int q = j * C - R.begin;
+                const int p = q >> pshift;
+                if (g.P > 0 && q >= 0 && p < g.P) {
+                    const int o = q & pmask;
+                    const int cl = cls[p];
+                    if (cl < R.nclass) {
+                        const int casc = R.cascade[cl];
+                        for (int s = 0; s < R.stages; s++) {
+                            if (!((casc >> s) & 1)) continue;
+                            const int book = R.books[cl][s];
+                            if (book < 0) continue;
+                            const DevBook b = S.books[book];
+                            const uint32_t base = prefix[s * g.P + p];
+                            #pragma unroll
+                            for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
+                                if (c >= C) break;
+                                const int e = o + c;
+                                r[c] = NVB_FADD(r[c], vq_fetch(b, S.vq, ent, base + (uint32_t)(e >> b.dshift), f.entry_count, e & (b.dims - 1), &bad_entry));
+                            }
+                        }
+                    }
+                }
+            } else {
             const int q = j - R.begin;
             const int p = q >> pshift;
             if (g.P > 0 && q >= 0 && p < g.P) {
@@ -374,6 +399,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
                     #pragma unroll
                     for (int k = 0; k < NVB_MAX_CHANNELS; k++) if (k == c) r[k] = acc;
                 }
+            }
             }
             for (int i = mp.n_coupling - 1; i >= 0; --i) {                  // Mapping.cs:137-182
                 const int m = mp.mag[i], an = mp.ang[i];
