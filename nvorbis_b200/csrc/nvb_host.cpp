@@ -137,6 +137,7 @@ Overlap nominal_overlap(const BlobHeader& h, int block_flag, int window) {
 void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) {
     S.channels = h.channels; S.bs[0] = h.bs[0]; S.bs[1] = h.bs[1];
     S.post_stride = h.post_stride; S.max_items = h.max_items; S.spectrum_fast = h.spectrum_fast;
+    S.max_stages = h.max_stages > 0 ? h.max_stages : 1;
     S.books = reinterpret_cast<const DevBook*>(base + h.off_books);
     S.vq = reinterpret_cast<const float*>(base + h.off_vq); S.n_vq = (int64_t)h.n_vq;
     S.floors = reinterpret_cast<const DevFloor1*>(base + h.off_floors);
@@ -245,17 +246,26 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
     h.channels = C; h.sample_rate = s->sample_rate; h.bs[0] = s->block_size[0]; h.bs[1] = s->block_size[1];
     h.n_books = s->n_books; h.n_floors = s->n_floors; h.n_residues = s->n_residues; h.n_mappings = s->n_mappings; h.n_modes = s->n_modes;
     h.post_stride = (2 + max_posts + 1) & ~1;
-    h.n_vq = (uint64_t)s->n_vq_floats;
 
+    // VQ tables are re-packed so that every table starts on a 16-byte boundary (vector loads of whole VQ vectors)
     h.off_books = w.reserve(sizeof(DevBook) * s->n_books);
+    std::vector<int64_t> new_off((size_t)s->n_books, -1);
+    int64_t vq_total = 0;
+    for (int i = 0; i < s->n_books; i++) {
+        const nvb_codebook& b = s->books[i];
+        if (b.map_type != 0 && b.table_off >= 0) { new_off[(size_t)i] = vq_total; vq_total += ((int64_t)b.entries * b.dims + 3) & ~int64_t(3); }
+    }
+    h.n_vq = (uint64_t)vq_total;
     for (int i = 0; i < s->n_books; i++) {
         DevBook d; d.dims = s->books[i].dims; d.entries = s->books[i].entries; d.pad = 0;
-        d.off = (s->books[i].map_type != 0) ? s->books[i].table_off : -1;
+        d.off = new_off[(size_t)i];
         d.dshift = is_pow2(d.dims) ? ilog_u(d.dims) - 1 : -1;
         w.at<DevBook>(h.off_books)[i] = d;
     }
-    h.off_vq = w.reserve(sizeof(float) * (size_t)(s->n_vq_floats > 0 ? s->n_vq_floats : 1));
-    if (s->n_vq_floats > 0) std::memcpy(w.at<float>(h.off_vq), s->vq_floats, sizeof(float) * (size_t)s->n_vq_floats);
+    h.off_vq = w.reserve(sizeof(float) * (size_t)(vq_total > 0 ? vq_total : 1));
+    for (int i = 0; i < s->n_books; i++)
+        if (new_off[(size_t)i] >= 0)
+            std::memcpy(w.at<float>(h.off_vq) + new_off[(size_t)i], s->vq_floats + s->books[i].table_off, sizeof(float) * (size_t)s->books[i].entries * s->books[i].dims);
     h.off_floors = w.reserve(sizeof(DevFloor1) * s->n_floors);
     for (int i = 0; i < s->n_floors; i++) {
         const nvb_floor1& g = s->floors[i].f1;
@@ -293,6 +303,10 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
             }
         }
         d.fast = fast ? 1 : 0;
+        // level 2: the plane kernel (k_spectrum_planes): one interleaved stream (type 2, or a single channel of type 1) whose
+        // partitions start on multiples of G = max(4, C) floats
+        const int G = C > 4 ? C : 4;
+        if (fast && (r.type == 2 || (r.type == 1 && C == 1)) && r.begin % G == 0 && r.partition_size % G == 0 && is_pow2(C)) d.fast = 2;
         w.at<DevResidue>(h.off_residues)[i] = d;
     }
     h.off_mappings = w.reserve(sizeof(DevMapping) * s->n_mappings);
@@ -361,8 +375,15 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         }
         if (mx > 40000) return fail(err, NVB_ERR_UNSUPPORTED, "residue layout needs %lld prefix items (> 40000)", mx);
         h.max_items = mx;
-        int fast = 1;
-        for (int i = 0; i < h.n_modes; i++) if (!S.residues[S.mappings[S.modes[i].mapping].residue].fast) fast = 0;
+        h.max_stages = 1;
+        for (int i = 0; i < h.n_residues; i++) if (S.residues[i].stages > h.max_stages) h.max_stages = S.residues[i].stages;
+        int fast = 2;
+        for (int i = 0; i < h.n_modes; i++) {
+            const DevResidue& R = S.residues[S.mappings[S.modes[i].mapping].residue];
+            if (R.fast < fast) fast = R.fast;
+            // plane kernel: stages planes + floor rows + item list in shared memory
+            if ((size_t)(h.max_stages + 1) * C * (h.bs[1] / 2) * 4 + (size_t)mx * 9 + 64 > 96 * 1024 && fast > 1) fast = 1;
+        }
         if ((size_t)mx * 4 + (size_t)C * (h.bs[1] / 2) * 4 > 160 * 1024) fast = 0;      // prefix table + floor curve rows must fit in shared memory
         h.spectrum_fast = fast;
     }
@@ -423,7 +444,9 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
             if (k > 0 && !(f.x[f.sort[k - 1]] < f.x[f.sort[k]])) return fail(err, NVB_ERR_DATA, "blob: floor %lld order", i);
         }
     }
-    if (h.post_stride < 4 || h.max_items < 1 || h.max_items > 40000) return fail(err, NVB_ERR_DATA, "blob: post_stride/max_items");
+    if (h.post_stride < 4 || h.max_items < 1 || h.max_items > 40000 || h.max_stages < 1 || h.max_stages > NVB_MAX_STAGES) return fail(err, NVB_ERR_DATA, "blob: post_stride/max_items/max_stages");
+    for (int i = 0; i < h.n_residues; i++) if (S.residues[i].stages > h.max_stages) return fail(err, NVB_ERR_DATA, "blob: max_stages");
+    if (h.spectrum_fast >= 2 && (size_t)(h.max_stages + 1) * h.channels * (h.bs[1] / 2) * 4 + (size_t)h.max_items * 9 + 64 > 96 * 1024) return fail(err, NVB_ERR_DATA, "blob: plane kernel does not fit");
     return NVB_OK;
 }
 

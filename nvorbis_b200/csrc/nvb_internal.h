@@ -31,7 +31,7 @@ struct DevFloor1  {
 struct DevResidue {
     int32_t type, begin, end, psize, nclass, stages;
     int32_t pshift;                 // log2(psize) or -1
-    int32_t fast;                   // 1: k_spectrum_fast applies (power-of-two partition/book sizes, type 2 partitions aligned to the channel count)
+    int32_t fast;                   // 1: k_spectrum_fast applies (power-of-two partition/book sizes, type 2 partitions aligned to the channel count); 2: k_spectrum_planes too
     int32_t cascade[NVB_MAX_CLASSES];
     int16_t books[NVB_MAX_CLASSES][NVB_MAX_STAGES];
     int16_t cnt[NVB_MAX_CLASSES][NVB_MAX_STAGES];   // VQ entries one partition of (class, stage) consumes; 0 = nothing coded
@@ -48,7 +48,7 @@ struct BlobHeader {
     int32_t n_books, n_floors, n_residues, n_mappings, n_modes;
     int32_t post_stride;       // int16 elements per (frame, channel) in nvb_batch.posts
     int32_t max_items;         // max over modes of stages*partitions*streams (residue prefix table)
-    int32_t spectrum_fast;     // every residue/floor of the setup fits k_spectrum_fast
+    int32_t spectrum_fast;     // 2: every mode fits k_spectrum_planes, 1: k_spectrum_fast, 0: only the general k_spectrum
     uint64_t off_books, off_vq, off_floors, off_residues, off_mappings, off_modes;
     uint64_t off_win_short;    // bs[0] floats
     uint64_t off_win_long;     // 4 * bs[1] floats (window index = prev?1:0 + next?2:0)
@@ -58,11 +58,13 @@ struct BlobHeader {
     uint64_t off_db;           // 256 floats
     uint64_t n_vq;
     uint64_t off_fused_tab;    // FusedTables block (nvb_fused_core.h) when bs == {256, 2048}, else 0
+    int32_t max_stages;        // largest residue stage count of the setup
+    int32_t pad1;
 };
 
 // Resolved pointers handed to kernels by value.
 struct DevSetup {
-    int32_t channels, bs[2], post_stride, max_items, spectrum_fast;
+    int32_t channels, bs[2], post_stride, max_items, spectrum_fast, max_stages;
     const DevBook* books; const float* vq; int64_t n_vq;
     const DevFloor1* floors; const DevResidue* residues; const DevMapping* mappings; const DevMode* modes;
     const float* win_short; const float* win_long;

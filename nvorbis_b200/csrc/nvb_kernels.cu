@@ -144,16 +144,28 @@ __device__ __forceinline__ void floor1_segments_warp(const DevFloor1& F, const i
     for (int h = 0; h < 2; h++) { const int i = lane + 32 * h; val[h] = i < count ? posts[1 + i] : 0; }
     if (lane < 2) fy[lane] = val[0];
     __syncwarp();
+    // per-post constants of this lane (setup data): neighbours, RenderPoint's x terms, dependency level
+    int p_lo[2], p_hi[2], p_x0[2], p_adx[2], p_dx[2], p_lvl[2]; float p_rcp[2];
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int i = lane + 32 * h;
+        p_lvl[h] = 0;
+        if (h < H && i >= 2 && i < count) {
+            p_lo[h] = F.lo[i]; p_hi[h] = F.hi[i]; p_x0[h] = F.x[p_lo[h]]; p_adx[h] = F.x[p_hi[h]] - p_x0[h]; p_dx[h] = F.x[i] - p_x0[h];
+            p_rcp[h] = F.rcp[i]; p_lvl[h] = F.level[i];
+        }
+    }
     for (int lvl = 1; lvl <= F.max_level; lvl++) {
-        for (int h = 0; h < H; h++) {
-            const int i = lane + 32 * h;
-            if (i >= 2 && i < count && F.level[i] == lvl) {
-                const int lo = F.lo[i], hi = F.hi[i];
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (p_lvl[h] == lvl) {
+                const int i = lane + 32 * h;
+                const int lo = p_lo[h], hi = p_hi[h];
                 // RenderPoint (Floor1.cs:299-314): y0 +- |dy| * (X - x0) / adx, the division by the setup constant adx
-                const int x0 = F.x[lo], adx = F.x[hi] - x0, y0 = fy[lo];
+                const int adx = p_adx[h], y0 = fy[lo];
                 const int dy = fy[hi] - y0, ady = dy < 0 ? -dy : dy;
-                const int err = ady * (F.x[i] - x0);
-                const int off = (unsigned)err < (1u << 22) ? div_small(err, adx, F.rcp[i]) : err / adx;
+                const int err = ady * p_dx[h];
+                const int off = (unsigned)err < (1u << 22) ? div_small(err, adx, p_rcp[h]) : err / adx;
                 const int predicted = dy < 0 ? y0 - off : y0 + off;
                 const int v = val[h];
                 const int highroom = F.range - predicted, lowroom = predicted;
@@ -430,6 +442,211 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1+K2+K3, plane path (DevSetup.spectrum_fast == 2): residues that code ONE interleaved stream -- type 2, or a
+// single channel of type 1 -- with power-of-two partition and book sizes.  The VQ vectors are copied whole:
+//   phase A  as in k_spectrum_fast (floor unwrap per channel warp); the last warp compacts the coded
+//            (stage, partition) items and the start of each item's entries into a list;
+//   phase B  floor curve rows (channel-interleaved) ...
+//   phase G  ... and, without a barrier in between, the residue: half a warp per item, lane = VQ entry, the entry's
+//            `dims` consecutive values move with one vector load/store into the stage's plane.  A (stage, position)
+//            is written by exactly one entry, so there are no atomics;
+//   phase C  thread per group of G = max(4, C) interleaved values: planes summed in stage order (the float adds of
+//            Residue1/2.WriteVectors in the reference's order, starting from the cleared +0), inverse coupling,
+//            floor multiply, channel rows written with vector stores.
+// ------------------------------------------------------------------------------------------------
+struct ItemRec { uint16_t p; uint8_t s, cl; uint32_t base; };
+
+template <int CT>
+__global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) {
+    constexpr int G = CT > 4 ? CT : 4;
+    constexpr int NW = SPEC_THREADS / 32;
+    NVB_DYN_SMEM(dyn_smem);
+    __shared__ float s_db[256];
+    __shared__ int s_fy[CT][NVB_MAX_POSTS];
+    __shared__ SegRec s_seg[CT * (NVB_MAX_POSTS + 1)];
+    __shared__ int s_nseg[CT + 1];
+    __shared__ int4 s_ci[NVB_MAX_CLASSES * NVB_MAX_STAGES];               // per (class, stage): vq offset, dims, entries, entries per partition
+    __shared__ int s_casc[NVB_MAX_CLASSES];
+    __shared__ int s_nitems;
+    __shared__ int s_bad[2];
+
+    const DevFrame f = a.frames[blockIdx.x];
+    if (f.kind != 0) return;
+    const DevSetup& S = a.S;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const DevMode md = S.modes[f.mode];
+    const DevMapping& mp = S.mappings[md.mapping];
+    const DevResidue& R = S.residues[mp.residue];
+    const DevFloor1& F = S.floors[mp.floor];
+    const int N = f.n, n = N >> 1, span = CT * n;
+    const int max_span = CT * (S.bs[1] >> 1);
+    float* s_fl = reinterpret_cast<float*>(dyn_smem);                       // [n][CT] floor multipliers
+    float* s_pl = s_fl + max_span;                                          // [stages][n][CT] residue planes
+    ItemRec* s_items = reinterpret_cast<ItemRec*>(s_pl + (size_t)S.max_stages * max_span);
+    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_items + S.max_items);
+    const uint8_t* cls = a.classes + f.classes_off;
+    const uint16_t* ent = a.entries + f.entries_off;
+
+    ResGeom g; g.P = 0; g.Sx = 1; g.n_items = 0;
+    if (f.res_decoded) g = residue_geom(R, N, CT);
+    const int P = g.P;
+    if (t < 2) s_bad[t] = 0;
+    s_db[t & 255] = S.db[t & 255];
+    for (int i = t; i < R.nclass * NVB_MAX_STAGES; i += SPEC_THREADS) {
+        const int cl = i >> 3, st = i & 7;
+        const int book = R.books[cl][st];
+        int4 ci = make_int4(0, 1, 0, 0);
+        if (book >= 0) { const DevBook b = S.books[book]; ci = make_int4((int)b.off, b.dims, b.entries, R.cnt[cl][st]); }
+        s_ci[i] = ci;
+        if (st == 0) s_casc[cl] = R.cascade[cl];
+    }
+    for (int p = t; p < P; p += SPEC_THREADS) { const int cl = cls[p]; s_cls[p] = cl < R.nclass ? (uint8_t)cl : (uint8_t)255; }
+
+    // ---- phase A
+    if (warp == NW - 1) {
+        uint32_t run = 0; int nitems = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        for (int st = 0; st < R.stages && P > 0; st++) {
+            for (int base = 0; base < P; base += 32) {
+                const int p = base + lane;
+                uint32_t c = 0; int cl = 0;
+                if (p < P) { cl = cls[p]; if (cl < R.nclass) c = (uint32_t)R.cnt[cl][st]; }
+                uint32_t incl = c;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+                const unsigned m = __ballot_sync(0xffffffffu, c > 0);
+                if (c > 0) { ItemRec r; r.p = (uint16_t)p; r.s = (uint8_t)st; r.cl = (uint8_t)cl; r.base = run + incl - c; s_items[nitems + __popc(m & lt)] = r; }
+                nitems += __popc(m);
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        if (lane == 0) s_nitems = nitems;
+    }
+    for (int c = warp; c < CT; c += NW) {
+        if ((f.exec_mask >> c) & 1u)
+            floor1_segments_warp(F, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, n, lane, s_fy[c], s_seg + c * (NVB_MAX_POSTS + 1), &s_nseg[c]);
+        else if (lane == 0) s_nseg[c] = 0;
+    }
+    __syncthreads();
+
+    // ---- phase B: floor curve rows, channel-interleaved
+    int bad_floor = 0, bad_entry = 0;
+    {
+        int c = 0, first_u = 0, ns = s_nseg[0];
+        int total = 0;
+        for (int k = 0; k < CT; k++) total += s_nseg[k];
+        for (int u = warp; u < total; u += NW) {
+            while (u - first_u >= ns) { first_u += ns; ++c; ns = s_nseg[c]; }
+            const SegRec r = s_seg[c * (NVB_MAX_POSTS + 1) + (u - first_u)];
+            const int len = r.x1 - r.x0;
+            const int dyabs = r.ady + (r.b < 0 ? -r.b : r.b) * len;         // |dy|: y(k) = y0 + sy * floor(k |dy| / adx)  (Floor1.cs:316-341 in closed form)
+            float* row = s_fl + r.x0 * CT + c;
+            for (int k = lane; k < len; k += 32) {
+                const int q = div_small(k * dyabs, len, r.rcp);             // k |dy| < 2^22
+                int y = r.y0 + r.sy * q;
+                if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
+                row[k * CT] = s_db[y];
+            }
+        }
+    }
+    // ---- phase G: VQ vectors into the stage planes; half a warp per item, lane = entry
+    {
+        const int nitems = s_nitems;
+        const int hl = lane & 15;
+        for (int idx = warp * 2 + (lane >> 4); idx < nitems; idx += NW * 2) {
+            const ItemRec r = s_items[idx];
+            const int4 ci = s_ci[r.cl * NVB_MAX_STAGES + r.s];
+            const int dims = ci.y;
+            float* dst = s_pl + (size_t)r.s * max_span + R.begin + (int)r.p * R.psize;
+            const float* tab = S.vq + ci.x;
+            for (int e = hl; e < ci.w; e += 16) {
+                const uint32_t ei = r.base + (uint32_t)e;
+                const float* src = nullptr;
+                if (ei < f.entry_count) {                                   // else never decoded: contributes nothing (Residue0.cs:164-170)
+                    const int en = ent[ei];
+                    if (en < ci.z) src = tab + (size_t)en * dims; else bad_entry = 1;
+                }
+                float* d = dst + e * dims;
+                if (dims == 2) *reinterpret_cast<float2*>(d) = src ? *reinterpret_cast<const float2*>(src) : make_float2(0.f, 0.f);
+                else if (dims == 1) *d = src ? *src : 0.f;
+                else for (int k = 0; k < dims; k += 4) *reinterpret_cast<float4*>(d + k) = src ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: sum the planes in stage order, inverse coupling, floor multiply, store
+    float* spec_out = a.spectrum + (size_t)f.spec_off;
+    const int pshift = R.pshift;
+    constexpr int CSH = CT == 1 ? 0 : CT == 2 ? 1 : CT == 4 ? 2 : 3;
+    bool execc[CT]; bool hasfl[CT];
+    #pragma unroll
+    for (int c = 0; c < CT; c++) { execc[c] = (f.exec_mask >> c) & 1u; hasfl[c] = s_nseg[c] > 0; }
+    for (int gi = t; gi < span / G; gi += SPEC_THREADS) {
+        const int pos = gi * G;
+        float acc[G];
+        #pragma unroll
+        for (int k = 0; k < G; k++) acc[k] = 0.f;
+        const int q = pos - R.begin, p = q >> pshift;
+        if (q >= 0 && p < P) {
+            const int cl = s_cls[p];
+            if (cl != 255) {
+                unsigned casc = (unsigned)s_casc[cl];
+                while (casc) {
+                    const int st = __ffs(casc) - 1; casc &= casc - 1;
+                    if (st >= R.stages || s_ci[cl * NVB_MAX_STAGES + st].w == 0) continue;
+                    const float* pl = s_pl + (size_t)st * max_span + pos;
+                    #pragma unroll
+                    for (int k = 0; k < G; k += 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(pl + k);
+                        acc[k] = NVB_FADD(acc[k], v.x); acc[k + 1] = NVB_FADD(acc[k + 1], v.y); acc[k + 2] = NVB_FADD(acc[k + 2], v.z); acc[k + 3] = NVB_FADD(acc[k + 3], v.w);
+                    }
+                }
+            }
+        }
+        for (int i = mp.n_coupling - 1; i >= 0; --i) {                      // Mapping.cs:137-182
+            const int m = mp.mag[i], an = mp.ang[i];
+            if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
+            #pragma unroll
+            for (int b = 0; b < G / CT; b++) {
+                float vm = 0.f, va = 0.f;
+                #pragma unroll
+                for (int k = 0; k < CT; k++) { if (k == m) vm = acc[b * CT + k]; if (k == an) va = acc[b * CT + k]; }
+                inverse_couple(vm, va);
+                #pragma unroll
+                for (int k = 0; k < CT; k++) { if (k == m) acc[b * CT + k] = vm; if (k == an) acc[b * CT + k] = va; }
+            }
+        }
+        #pragma unroll
+        for (int k = 0; k < G; k += 4) {
+            const float4 fl = *reinterpret_cast<const float4*>(s_fl + pos + k);
+            const float flv[4] = {fl.x, fl.y, fl.z, fl.w};
+            #pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int c = (k + e) & (CT - 1);
+                if (execc[c]) acc[k + e] = hasfl[c] ? NVB_FMUL(acc[k + e], flv[e]) : 0.f;      // Floor1.Apply, Floor1.cs:186-222
+            }
+        }
+        const int bin0 = pos >> CSH;
+        if (CT == 1) *reinterpret_cast<float4*>(spec_out + bin0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else if (CT == 2) {
+            *reinterpret_cast<float2*>(spec_out + bin0) = make_float2(acc[0], acc[2]);
+            *reinterpret_cast<float2*>(spec_out + n + bin0) = make_float2(acc[1], acc[3]);
+        } else {
+            #pragma unroll
+            for (int c = 0; c < CT; c++) spec_out[(size_t)c * n + bin0] = acc[c];
+        }
+    }
+    if (bad_entry) atomicOr(&s_bad[0], 1);
+    if (bad_floor) atomicOr(&s_bad[1], 1);
+    __syncthreads();
+    if (t == 0) {
+        if (s_bad[0]) atomicAdd(&a.counters->bad_entry, 1);
+        if (s_bad[1]) atomicAdd(&a.counters->floor_range, 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4 exact: one CTA per (frame, channel); the reference's stb_vorbis IMDCT schedule cut into
 // data-parallel steps with a barrier between them, all in shared memory (u[N] + v[N/2]).
 // Bit-identical to Mdct.cs for every N (including its N = 64/128 behaviour).
@@ -512,6 +729,27 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
     static const bool force_generic = std::getenv("NVB_SPECTRUM_GENERIC") != nullptr;      // test hook: exercise the general kernel
     if (!a.S.spectrum_fast || force_generic) return launch_spectrum_generic(a, stream);
+    static const bool no_planes = std::getenv("NVB_SPECTRUM_NO_PLANES") != nullptr;           // test hook: exercise k_spectrum_fast
+    if (a.S.spectrum_fast >= 2 && !no_planes) {
+        const int C = a.S.channels;
+        // planes for the deepest residue + floor rows + item list + class bytes (host-checked to fit)
+        const size_t span = (size_t)C * (a.S.bs[1] / 2) * sizeof(float);
+        const size_t smem = span * (size_t)(a.S.max_stages + 1) + (size_t)a.S.max_items * sizeof(ItemRec) + (((size_t)a.S.max_items + 15) & ~size_t(15)) + 16;
+        static size_t configured_pl = 0;
+        if (smem > configured_pl) {
+            cudaError_t e = C == 1 ? cudaFuncSetAttribute(k_spectrum_planes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : C == 2 ? cudaFuncSetAttribute(k_spectrum_planes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : C == 4 ? cudaFuncSetAttribute(k_spectrum_planes<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(k_spectrum_planes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return -1;
+            configured_pl = smem;
+        }
+        if (C == 1) NVB_LAUNCH(k_spectrum_planes<1>, a.n_frames, SPEC_THREADS, smem, stream, a);
+        else if (C == 2) NVB_LAUNCH(k_spectrum_planes<2>, a.n_frames, SPEC_THREADS, smem, stream, a);
+        else if (C == 4) NVB_LAUNCH(k_spectrum_planes<4>, a.n_frames, SPEC_THREADS, smem, stream, a);
+        else NVB_LAUNCH(k_spectrum_planes<8>, a.n_frames, SPEC_THREADS, smem, stream, a);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     const size_t smem = spectrum_smem(a.S) + (size_t)a.S.channels * (a.S.bs[1] / 2) * sizeof(float);
     static size_t configured = 0;
     if (smem > 24 * 1024 && smem > configured) {
