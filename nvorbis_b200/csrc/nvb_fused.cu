@@ -5,25 +5,27 @@
 // ClippingCopyBuffer / CopyBuffer (StreamDecoder.cs:391-415).
 //
 // Mapping onto the chip
-//   * persistent grid: one CTA (32 warps of 64 registers) per SM owns a contiguous run of frames; teams of C
-//     warps take the frames of the run round-robin, warp c of a team = channel c.  A warp transforms its channel
-//     (512 complex points as 16 per lane = two radix-8 columns processed one after the other: three passes in
-//     registers, two exchanges through the frame's shared-memory slot, twiddles from per-lane tables that one
-//     bulk copy (cp.async.bulk, TMA) stages at kernel start), leaves the DCT-IV output u in the slot, then
-//     writes its slice of the frame's PCM from the frame's u and the previous frame's u (all channels);
+//   * persistent grid: one CTA (16 warps) per SM owns a contiguous run of frames; its warps take the frames of the
+//     run round-robin.  A warp transforms every channel of its frame (512 complex points as 16 per lane = two
+//     radix-8 columns: three passes in registers, two exchanges through the frame's shared-memory slot), leaves
+//     the DCT-IV output u in the slot, then writes the frame's PCM from its own u and the previous frame's u;
+//   * the kernel is bound by shared-memory wavefronts and instruction issue, not by HBM or FP32 rate, so both are
+//     minimised: the pre/post twiddles tw[64 j + r] = tw[r] E[j] are folded into compile-time constants E[j] plus
+//     per-lane tables (13 conflict-free LDS.128 of twiddles per transform), the lane tables are staged by one bulk
+//     copy (cp.async.bulk, TMA) per CTA, the TDAC symmetry out[i] / out[1023-i] lets every loaded u / window value
+//     serve two output samples, exchange strides are padded (72 / 9 float2) and u is XOR-swizzled: no bank conflicts;
 //   * no CTA-wide barrier in steady state: slots form a ring guarded by release/acquire counters in shared
 //     memory -- full[slot] (u of that frame is complete; awaited by the warp that overlaps onto it) and
 //     empty[slot] (both readers of the slot are done; awaited by the warp that reuses it) -- so transform,
 //     overlap and store of different frames run concurrently on the four schedulers of the SM.  Counters
 //     rather than mbarrier phases: nothing bounds the skew between two warps to one ring revolution, and a
 //     parity wait cannot tell "two phases behind" from "done";
-//   * inputs are TMA-staged: the spectrum rows of a warp's NEXT frame are bulk-copied (cp.async.bulk, completion
-//     on an mbarrier) straight into that frame's slot while the warp still works on the current one, so no
-//     warp waits on a global load in steady state and no load instruction is spent on the input;
 //   * the previous block's tail never touches HBM: each spectrum float is read once and each PCM float is
 //     written once (16 384 B per stereo long frame); the first block of a run is recomputed as a halo;
-//   * shared memory is bank-conflict free: padded exchange strides (72 / 9 float2), XOR-swizzled u;
 //   * output: two samples x two channels per lane as one float4 store, a warp writes 512 contiguous bytes.
+//   Variants measured and dropped (profiles/r01_d, r01_f): TMA staging of the spectrum rows into the slot (the extra
+//   LDS of the inputs costs more shared-memory bandwidth than the exposed load latency it saves); 32 warps x 64
+//   registers with one warp per channel (more twiddle loads and counter polling, slower).
 // No tensor cores: the IMDCT is FFT-structured, not a dense contraction.
 #if !defined(NVB_CPU_SHIM)
 #include <cuda_runtime.h>
@@ -32,7 +34,7 @@
 
 namespace nvb {
 
-constexpr int FUSED_WARPS = 32;
+constexpr int FUSED_WARPS = 16;
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
 constexpr size_t FUSED_SMEM_LIMIT = 227 * 1024;
 
@@ -108,17 +110,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
     const int C = S.channels;
     const int NS = p.n_slots;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int T = FUSED_WARPS / C;                                          // teams: C warps per frame, warp c of a team = channel c
-    const int team = warp / C, c = warp - team * C;
 
     float* s_tab = reinterpret_cast<float*>(smem_raw);
     float* s_slots = s_tab + FusedTables::FLOATS;
-    DevFrame* s_fr = reinterpret_cast<DevFrame*>(s_slots + (size_t)NS * C * FUSED_SLOT_FLOATS);   // per slot, written by the team's warp 0
-    DevFrame* s_frw = s_fr + NS;                                            // per warp: the descriptor of the frame it works on
-    int* s_full = reinterpret_cast<int*>(s_frw + FUSED_WARPS);              // s_full[s]: channels completed in slot s, over all its frames
-    int* s_empty = s_full + NS;                                             // s_empty[s]: reader releases of slot s (2 C per frame)
+    DevFrame* s_fr = reinterpret_cast<DevFrame*>(s_slots + (size_t)NS * C * FUSED_SLOT_FLOATS);
+    int* s_full = reinterpret_cast<int*>(s_fr + NS);                        // s_full[s]: frames completed in slot s
+    int* s_empty = s_full + NS;                                             // s_empty[s]: reader releases of slot s (two per frame)
     uint64_t* s_tabbar = reinterpret_cast<uint64_t*>(s_empty + NS);          // 8 NS bytes past s_full: 8-byte aligned
-    uint64_t* s_in = s_tabbar + 1;                                          // s_in[s * C + c]: the spectrum row of channel c of the slot's frame has landed
 
     const int lo = blockIdx.x * p.frames_per_cta;
     int hi = lo + p.frames_per_cta; if (hi > a.n_frames) hi = a.n_frames;
@@ -126,107 +124,83 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
 
     if (tid == 0) {
         for (int s = 0; s < NS; s++) { s_full[s] = 0; s_empty[s] = 0; }
-        for (int s = 0; s < NS * C; s++) mbar_init(&s_in[s], 1);
         mbar_init(s_tabbar, 1);
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {                                                         // the lane tables: one bulk copy (TMA) per CTA
         mbar_arrive_expect_tx(s_tabbar, FusedTables::FLOATS * sizeof(float));
         bulk_g2s(s_tab, S.fused_tab, FusedTables::FLOATS * sizeof(float), s_tabbar);
     }
-    if (team >= T) return;                                                  // warps left over when C does not divide the warp count
 
     int first = lo;
     {
         const DevFrame f0 = a.frames[lo];
         if (f0.prev >= 0 && (f0.ola_len > 0 || f0.kind != 0)) first = lo - 1;   // halo: previous block's tail is needed
     }
-
-    // Claims channel c of the slot of frame xx and starts the bulk copy of its spectrum row into it.  Every frame
-    // completes one phase of s_in[slot * C + c], so the phase number equals the slot's revolution count.
-    auto stage_frame = [&](int xx) {
-        const int rel_ = xx - first, slot_ = rel_ % NS;
-        cnt_wait(&s_empty[slot_], 2 * C * (rel_ / NS));                      // every reader of every earlier frame of the slot is done
-        if (lane == 0) {
-            const DevFrame fr = a.frames[xx];
-            s_frw[warp] = fr;
-            if (c == 0) s_fr[slot_] = fr;
-            uint64_t* bar = &s_in[slot_ * C + c];
-            if (fr.kind == 0) {
-                const uint32_t row = (uint32_t)(fr.n >> 1) * sizeof(float);
-                fence_proxy_async();
-                mbar_arrive_expect_tx(bar, row);
-                bulk_g2s(s_slots + ((size_t)slot_ * C + c) * FUSED_SLOT_FLOATS, a.spectrum + (size_t)fr.spec_off + (size_t)c * (fr.n >> 1), row, bar);
-            } else mbar_arrive(bar);
-        }
-        __syncwarp();
-    };
-    if (first + team < hi) stage_frame(first + team);
     mbar_wait(s_tabbar, 0);
 
     const float2* s_tw0 = reinterpret_cast<const float2*>(s_tab + FusedTables::TW0);
     const float2* s_w64 = reinterpret_cast<const float2*>(s_tab + FusedTables::W64);
     const float* s_win = s_tab + FusedTables::WIN;
+    // swizzled float offsets of this lane's sample pair inside a run of 64 (forward / mirrored), see the fast path
+    const int L2 = 2 * lane;
+    const int A0 = L2 ^ ((lane >> 4) << 2), A8 = A0 ^ 8;
+    const int Bm = 62 - L2;
+    const int B0 = Bm ^ ((Bm >> 5) << 2), B8 = B0 ^ 8;
     float peak = 0.f;
 
-    for (int x = first + team; x < hi; x += T) {
+    for (int x = first + warp; x < hi; x += FUSED_WARPS) {
         const int rel = x - first, slot = rel % NS, it = rel / NS;
-        mbar_wait(&s_in[slot * C + c], it & 1);                              // this channel's row has landed
-        const DevFrame f = s_frw[warp];
+        cnt_wait(&s_empty[slot], 2 * it);                                    // both readers of every earlier frame of the slot are done
+        if (lane == 0) s_fr[slot] = a.frames[x];
+        __syncwarp();
+        const DevFrame f = s_fr[slot];
         float* slots_f = s_slots + (size_t)slot * C * FUSED_SLOT_FLOATS;
-        float* slotc = slots_f + (size_t)c * FUSED_SLOT_FLOATS;
 
-        // ---------------- transform: channel c of frame x, in place in the slot ----------------------
-        if (f.kind == 0 && ((f.exec_mask >> c) & 1u)) {                      // else: the slot already holds the raw residue values (Mapping.cs:192-196)
-            if (f.n == FUSED_LONG_N) {
-                float2* ex = reinterpret_cast<float2*>(slotc);
-                {
-                    LongIn in;
-                    long_phase1_load(lane, ex, in);
-                    __syncwarp();                                           // in place: every lane has read its inputs
-                    long_phase1_col(lane, 0, in, s_tab, ex);
-                    long_phase1_col(lane, 1, in, s_tab, ex);
+        // ---------------- transform: every channel of frame x -------------------------------------
+        if (f.kind == 0) {
+            for (int c = 0; c < C; c++) {
+                float* slotc = slots_f + (size_t)c * FUSED_SLOT_FLOATS;
+                const int M = f.n >> 1;
+                const float* spec = a.spectrum + (size_t)f.spec_off + (size_t)c * M;
+                if (!((f.exec_mask >> c) & 1u)) {
+                    for (int i = lane; i < M; i += 32) slotc[i] = spec[i];         // raw residue values (Mapping.cs:192-196)
+                } else if (f.n == FUSED_LONG_N) {
+                    float2* ex = reinterpret_cast<float2*>(slotc);
+                    LongRegs R;
+                    long_phase1(lane, reinterpret_cast<const float2*>(spec), s_tab, ex);
+                    __syncwarp();
+                    long_phase2_load(lane, ex, R);
+                    __syncwarp();
+                    long_phase2_store(lane, s_tab, ex, R);
+                    __syncwarp();
+                    long_phase3_load(lane, ex, R);
+                    __syncwarp();
+                    long_phase3_store(lane, s_tab, ex, R);
+                } else {
+                    ShortRegs R;
+                    short_phase1(lane, spec, s_tw0, s_w64, R);
+                    #pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) {
+                        cpx pa, pb;
+                        pa.x = __shfl_xor_sync(0xffffffffu, R.a.x, s); pa.y = __shfl_xor_sync(0xffffffffu, R.a.y, s);
+                        pb.x = __shfl_xor_sync(0xffffffffu, R.b.x, s); pb.y = __shfl_xor_sync(0xffffffffu, R.b.y, s);
+                        R.a = short_stage(lane, s, R.a, pa, s_w64);
+                        R.b = short_stage(lane, s, R.b, pb, s_w64);
+                    }
+                    short_phase3_store(lane, s_tw0, slotc, R);
                 }
-                __syncwarp();
-                cpx Ra[8], Rb[8];
-                long_phase2_load(lane, 0, ex, Ra);
-                long_phase2_load(lane, 1, ex, Rb);
-                __syncwarp();
-                long_phase2_store(lane, 0, s_tab, ex, Ra);
-                long_phase2_store(lane, 1, s_tab, ex, Rb);
-                __syncwarp();
-                long_phase3_col(lane, 0, s_tab, ex, Ra);
-                long_phase3_col(lane, 1, s_tab, ex, Rb);
-                __syncwarp();
-                long_phase3_store(lane, ex, Ra, Rb);
-            } else {
-                ShortRegs R;
-                short_phase1(lane, slotc, s_tw0, s_w64, R);                // the shuffles below order these reads before the stores
-                #pragma unroll
-                for (int s = 16; s >= 1; s >>= 1) {
-                    cpx pa, pb;
-                    pa.x = __shfl_xor_sync(0xffffffffu, R.a.x, s); pa.y = __shfl_xor_sync(0xffffffffu, R.a.y, s);
-                    pb.x = __shfl_xor_sync(0xffffffffu, R.b.x, s); pb.y = __shfl_xor_sync(0xffffffffu, R.b.y, s);
-                    R.a = short_stage(lane, s, R.a, pa, s_w64);
-                    R.b = short_stage(lane, s, R.b, pb, s_w64);
-                }
-                short_phase3_store(lane, s_tw0, slotc, R);
             }
         }
         __syncwarp();
-        if (lane == 0) cnt_signal(&s_full[slot]);                            // channel c of frame x is complete
+        if (lane == 0) cnt_signal(&s_full[slot]);                            // u of frame x is complete
 
-        // the team's next frame: stage it as soon as its slot is free (checked here, then blocking after the output)
-        const int xn = x + T;
-        bool staged = xn >= hi;
-        if (!staged && __shfl_sync(0xffffffffu, (int)cnt_ready(&s_empty[(xn - first) % NS], 2 * C * ((xn - first) / NS)), 0)) { stage_frame(xn); staged = true; }
-
-        // ---------------- output: slice c of frame x (a halo block only leaves its tail) ---------------
-        cnt_wait(&s_full[slot], C * (it + 1));                               // all channels of this frame
         // Frame x-1 must have claimed and filled its slot before this warp releases it (a release that overtakes the
         // frame itself would be counted against the slot's next user), whether its tail is needed or not.
-        if (rel >= 1) cnt_wait(&s_full[(rel - 1) % NS], C * ((rel - 1) / NS + 1));
+        if (rel >= 1) cnt_wait(&s_full[(rel - 1) % NS], (rel - 1) / NS + 1);
+
+        // ---------------- output of frame x (a halo block only leaves its tail) --------------------
         if (x >= lo) {
             const int len = f.out_end - f.out_begin;
             const DevFrame* pf = nullptr; const float* slots_p = nullptr;
@@ -238,64 +212,60 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
                               (pf->window & 2) && f.start == 0 && f.out_begin == 0 && f.out_end == 1024 && f.ola_len == 1024 &&
                               f.prev_valid == 1024 && f.exec_mask == 3u && pf->exec_mask == 3u && pf->kind == 0 && ((f.pcm_off & 1) == 0);
             if (fast) {
-                // long block after long block, both channels live (Mode.cs:44-50 window 3):
-                // out[i] = S[i]*yL[i] + S[1023-i]*yR[i],  yL from this block's u, yR from the previous block's u.
-                // Warp c writes samples [512 c, 512 c + 512); swizzled float offsets of the lane's sample pair:
-                const int L2 = 2 * lane;
-                const int A0 = L2 ^ ((lane >> 4) << 2), A8 = A0 ^ 8;
-                const int Bm = 62 - L2;
-                const int B0 = Bm ^ ((Bm >> 5) << 2), B8 = B0 ^ 8;
-                float4* out = reinterpret_cast<float4*>(a.pcm + (size_t)f.pcm_off * 2) + lane + 256 * c;
+                // long block after long block, both channels live (Mode.cs:44-50 window 3).  With a = u[512+i] of this
+                // block, b = u'[511-i] of the previous one, s = S[i], s' = S[1023-i] (i < 512):
+                //     out[i] = s a - s' b          out[1023-i] = -s' a - s b
+                // (TDAC: the two samples mirror each other), so every loaded value serves two outputs.
+                float4* out = reinterpret_cast<float4*>(a.pcm + (size_t)f.pcm_off * 2);
                 const bool clip = a.clip != 0;
-                const float* ua = slots_f + (c ? 1472 - 512 : 512);         // this block's u: forward from 512 (c = 0), mirrored from 1534 (c = 1)
-                const float* ub = slots_p + (c ? 0 : 448);                  // previous block's u: mirrored from 510 (c = 0), forward from 0 (c = 1)
                 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const int i = L2 + 64 * k + 512 * c;
-                    const float2 wl = *reinterpret_cast<const float2*>(s_win + i);
+                    const int i = L2 + 64 * k;
+                    const float2 wl = *reinterpret_cast<const float2*>(s_win + i);          // (S[i], S[i+1])
                     const float2 wr = *reinterpret_cast<const float2*>(s_win + 1022 - i);   // (S[1022-i], S[1023-i])
-                    float o[4];
+                    float lo_[4], hi_[4];
                     #pragma unroll
-                    for (int ch = 0; ch < 2; ch++) {
-                        float yl0, yl1, nr0, nr1;                           // nr = -yR
-                        if (c == 0) {
-                            const float2 l2 = *reinterpret_cast<const float2*>(ua + ch * FUSED_SLOT_FLOATS + 64 * k + ((k & 1) ? A8 : A0));    // u[512+i], u[513+i]
-                            const float2 r2 = *reinterpret_cast<const float2*>(ub + ch * FUSED_SLOT_FLOATS - 64 * k + ((k & 1) ? B0 : B8));    // u'[510-i], u'[511-i]
-                            yl0 = l2.x; yl1 = l2.y; nr0 = r2.y; nr1 = r2.x;
-                        } else {
-                            const float2 l2 = *reinterpret_cast<const float2*>(ua + ch * FUSED_SLOT_FLOATS - 64 * k + ((k & 1) ? B0 : B8));    // u[1534-i], u[1535-i]
-                            const float2 r2 = *reinterpret_cast<const float2*>(ub + ch * FUSED_SLOT_FLOATS + 64 * k + ((k & 1) ? A8 : A0));    // u'[i-512], u'[i-511]
-                            yl0 = -l2.y; yl1 = -l2.x; nr0 = r2.x; nr1 = r2.y;
-                        }
-                        o[ch]     = fmaf(wl.x, yl0, -(wr.y * nr0));
-                        o[2 + ch] = fmaf(wl.y, yl1, -(wr.x * nr1));
+                    for (int c = 0; c < 2; c++) {
+                        const float2 a2 = *reinterpret_cast<const float2*>(slots_f + c * FUSED_SLOT_FLOATS + 512 + 64 * k + ((k & 1) ? A8 : A0));   // u[512+i], u[513+i]
+                        const float2 b2 = *reinterpret_cast<const float2*>(slots_p + c * FUSED_SLOT_FLOATS + 448 - 64 * k + ((k & 1) ? B0 : B8));   // u'[510-i], u'[511-i]
+                        lo_[c]     = fmaf(wl.x, a2.x, -(wr.y * b2.y));           // out[i]
+                        lo_[2 + c] = fmaf(wl.y, a2.y, -(wr.x * b2.x));           // out[i+1]
+                        hi_[2 + c] = -fmaf(wr.y, a2.x, wl.x * b2.y);             // out[1023-i]
+                        hi_[c]     = -fmaf(wr.x, a2.y, wl.y * b2.x);             // out[1022-i]
                     }
-                    if (clip) { o[0] = clipf(o[0], peak); o[1] = clipf(o[1], peak); o[2] = clipf(o[2], peak); o[3] = clipf(o[3], peak); }
-                    out[32 * k] = make_float4(o[0], o[1], o[2], o[3]);
+                    if (clip) {
+                        #pragma unroll
+                        for (int e = 0; e < 4; e++) { lo_[e] = clipf(lo_[e], peak); hi_[e] = clipf(hi_[e], peak); }
+                    }
+                    out[lane + 32 * k] = make_float4(lo_[0], lo_[1], lo_[2], lo_[3]);
+                    out[511 - lane - 32 * k] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
                 }
             } else if (len > 0) {
                 const int total = len * C;
-                for (int idx = lane + 32 * c; idx < total; idx += 32 * C) {
-                    const int s = idx / C, ch = idx - s * C;
+                for (int idx = lane; idx < total; idx += 32) {
+                    const int s = idx / C, c = idx - s * C;
                     const int i = f.out_begin + s;
                     float v;
                     if (f.kind == 0) {
-                        v = slot_z(S, f, slots_f + ch * FUSED_SLOT_FLOATS, ch, i);
+                        v = slot_z(S, f, slots_f + c * FUSED_SLOT_FLOATS, c, i);
                         const int o = i - f.start;
                         if (f.ola_len > 0 && o >= 0 && o < f.ola_len) {                       // StreamDecoder.cs:532-541
-                            if (pf) v += slot_z(S, *pf, slots_p + ch * FUSED_SLOT_FLOATS, ch, f.prev_valid + o);
-                            else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)ch * S.bs[1] + f.prev_valid + o];
+                            if (pf) v += slot_z(S, *pf, slots_p + c * FUSED_SLOT_FLOATS, c, f.prev_valid + o);
+                            else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)c * S.bs[1] + f.prev_valid + o];
                         }
                     } else {                                                                  // drain, StreamDecoder.cs:352-356
-                        v = pf ? slot_z(S, *pf, slots_p + ch * FUSED_SLOT_FLOATS, ch, i) : a.carry_in[(size_t)ch * S.bs[1] + i];
+                        v = pf ? slot_z(S, *pf, slots_p + c * FUSED_SLOT_FLOATS, c, i) : a.carry_in[(size_t)c * S.bs[1] + i];
                     }
                     if (a.clip) v = clipf(v, peak);
-                    a.pcm[((size_t)f.pcm_off + s) * C + ch] = v;
+                    a.pcm[((size_t)f.pcm_off + s) * C + c] = v;
                 }
             }
             if (x == a.carry_frame && a.carry_out && f.kind == 0) {
-                // keep the last windowed block for the next batch (StreamDecoder.cs:455-461): warp c saves channel c
-                for (int i = lane; i < f.n; i += 32) a.carry_out[(size_t)c * S.bs[1] + i] = slot_z(S, f, slotc, c, i);
+                // keep the last windowed block for the next batch (StreamDecoder.cs:455-461)
+                for (int idx = lane; idx < f.n * C; idx += 32) {
+                    const int c = idx / f.n, i = idx - c * f.n;
+                    a.carry_out[(size_t)c * S.bs[1] + i] = slot_z(S, f, slots_f + c * FUSED_SLOT_FLOATS, c, i);
+                }
             }
         }
         __syncwarp();
@@ -303,7 +273,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
             cnt_signal(&s_empty[slot]);                                      // done with frame x as "current"
             if (rel >= 1) cnt_signal(&s_empty[(rel - 1) % NS]);              // done with frame x-1 as "previous"
         }
-        if (!staged) stage_frame(xn);
     }
     if (__any_sync(0xffffffffu, peak > 0.99999994f) && lane == 0) atomicOr(&a.counters->clipped, 1);
 }
@@ -311,15 +280,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
 // ------------------------------------------------------------------------------------------------
 static int fused_slots(int C) {
     const size_t fixed = FusedTables::FLOATS * sizeof(float) + 64;
-    const size_t fixed2 = fixed + FUSED_WARPS * sizeof(DevFrame);
-    const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int) + (size_t)C * sizeof(uint64_t);
-    int ns = (int)((FUSED_SMEM_LIMIT - fixed2) / per);
-    if (ns > FUSED_WARPS / C + 2) ns = FUSED_WARPS / C + 2;
+    const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
+    int ns = (int)((FUSED_SMEM_LIMIT - fixed) / per);
+    if (ns > FUSED_WARPS + 2) ns = FUSED_WARPS + 2;
     return ns;
 }
 static size_t fused_smem(int C, int NS) {
-    return FusedTables::FLOATS * sizeof(float) + FUSED_WARPS * sizeof(DevFrame) +
-           (size_t)NS * ((size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int) + (size_t)C * sizeof(uint64_t)) + 32;
+    return FusedTables::FLOATS * sizeof(float) + (size_t)NS * ((size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int)) + 32;
 }
 
 bool fused_supported(const BlobHeader& h, const DevFrame*, int) {

@@ -47,101 +47,128 @@ constexpr int FUSED_LONG_N = 2048;
 constexpr int FUSED_SHORT_N = 256;
 
 // Lane tables for N = 2048 / 256, built on the host (nvb_host.cpp: build_fused_tables), one contiguous block
-// so that the kernel stages it with a single bulk copy.  Offsets in floats:
+// so that the kernel stages it with a single bulk copy.  Offsets in floats.
+// Twiddle folding: tw[64 j + r] = tw[r] * E[j] with the compile-time constants E[j] = exp(-i pi j / 16), so the
+// pre-twiddle of pass 1 becomes 7 constant multiplies on the inputs plus tw[r] merged into the pass-1 output
+// twiddles (T2), and the post-twiddle becomes 7 constant multiplies plus one per-lane value (T4).  That is 13
+// vector loads of twiddles per transform instead of 27: the kernel is bound by shared-memory wavefronts.
 struct FusedTables {
-    static constexpr int T1 = 0;        // [8][32] float4: pre-twiddles tw[64 k2 + l], tw[64 k2 + 63 - l]
-    static constexpr int T2 = 1024;     // [7][32] float4: W512^(l m2), W512^((63-l) m2), m2 = 1..7
-    static constexpr int T3 = 1920;     // [4][32] float4: W64^(k0 m1) for m1 = 2j+1, 2j+2 (k0 = l & 7)
-    static constexpr int T4 = 2432;     // [8][32] float4: post-twiddles tw[na0 + 64 m0], tw[nb0 + 64 m0]
-    static constexpr int WIN = 3456;    // [1024] rising slope of the long/long window (Mode.cs:80-85)
-    static constexpr int TW0 = 4480;    // [64] float2: short-block twiddles exp(-i pi (k + 1/8) / 128)
-    static constexpr int W64 = 4608;    // [64] float2: exp(-2 pi i k / 64)
-    static constexpr int FLOATS = 4736;
+    static constexpr int T2 = 0;        // [8][32] float4: tw[l] W512^(l m2), tw[63-l] W512^((63-l) m2), m2 = 0..7
+    static constexpr int T3 = 1024;     // [4][32] float4: W64^(k0 m1) for m1 = 2j+1, 2j+2 (k0 = l & 7)
+    static constexpr int T4 = 1536;     // [32] float4: tw[na0], tw[nb0]
+    static constexpr int WIN = 1664;    // [1024] rising slope of the long/long window (Mode.cs:80-85)
+    static constexpr int TW0 = 2688;    // [64] float2: short-block twiddles exp(-i pi (k + 1/8) / 128)
+    static constexpr int W64 = 2816;    // [64] float2: exp(-2 pi i k / 64)
+    static constexpr int FLOATS = 2944;
 };
 NVB_HD int fused_na0(int l) { return (l >> 3) + 8 * (l & 7); }
 NVB_HD int fused_nb0(int l) { return (7 - (l >> 3)) + 8 * (7 - (l & 7)); }
 
+// a * E[K], E[K] = exp(-i pi K / 16) = (cos, -sin)(pi K / 16)
+template <int K> NVB_HD cpx cmul_e(cpx a) {
+    constexpr float co[8] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f, 0.70710678118654752440f,
+                             0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+    constexpr float si[8] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f, 0.70710678118654752440f,
+                             0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f};
+    if (K == 0) return a;
+    cpx r; r.x = a.x * co[K] + a.y * si[K]; r.y = a.y * co[K] - a.x * si[K];
+    return r;
+}
+NVB_HD void cmul_e_all(cpx* a) {
+    a[1] = cmul_e<1>(a[1]); a[2] = cmul_e<2>(a[2]); a[3] = cmul_e<3>(a[3]); a[4] = cmul_e<4>(a[4]);
+    a[5] = cmul_e<5>(a[5]); a[6] = cmul_e<6>(a[6]); a[7] = cmul_e<7>(a[7]);
+}
+
 // u of an executed long block is stored swizzled: float2 index n -> n ^ (((n >> 4) & 3) << 1).  That makes the
 // phase-3 stores (lanes 8 apart in n) and the output reads (lanes adjacent in n) both bank-conflict free, and
-// keeps aligned groups of four floats contiguous (LDS.128 in the output loop).
+// keeps aligned groups of four floats contiguous.
 NVB_HD int u_swz2(int n) { return n ^ (((n >> 4) & 3) << 1); }                  // float2 index
 NVB_HD int u_swz(int i) { return i ^ (((i >> 5) & 3) << 2); }                   // float index
 
 NVB_HD cpx ld_cpx(const float4& v, int hi) { cpx r; r.x = hi ? v.z : v.x; r.y = hi ? v.w : v.y; return r; }
 
-// One lane owns two radix-8 columns ("a" and "b") of every pass.  They are processed one after the other so that
-// only one column (8 complex values) plus the pass's inputs is live: the kernel runs 32 warps of 64 registers per SM.
-NVB_HD float2 tab2(const float* tab, int base, int row, int l, int col) {
-    return reinterpret_cast<const float2*>(tab + base)[(row * 32 + l) * 2 + col];
-}
-NVB_HD cpx to_cpx(float2 v) { cpx r; r.x = v.x; r.y = v.y; return r; }
+// Registers of one lane while it transforms one long block: two radix-8 columns.
+struct LongRegs { cpx a[8]; cpx b[8]; };
 
-// ---- phase 1: load spectrum pairs, pre-twiddle, radix-8 over k2, twiddle W512^(r*m2), store ex1
-// spec2: the channel's spectrum as float2[512] -- in the kernel it sits in the slot itself (bulk-copied there),
-// so the loads and the stores are separate calls with a warp barrier between them.
-struct LongIn { float2 pa[8], pb[8]; };
-NVB_HD void long_phase1_load(int l, const float2* spec2, LongIn& in) {
+// ---- phase 1: load spectrum pairs, constant part of the pre-twiddle, radix-8 over k2, twiddle tw[r] W512^(r*m2), store ex1
+// spec2: the channel's spectrum as float2[512] (global memory); tab: FusedTables in shared memory; ex: float2[576].
+NVB_HD void long_phase1(int l, const float2* spec2, const float* tab, float2* ex) {
     const int ra = l, rb = 63 - l;
+    float2 pa[8], pb[8];
     #pragma unroll
-    for (int k2 = 0; k2 < 8; k2++) { in.pa[k2] = spec2[64 * k2 + ra]; in.pb[k2] = spec2[64 * k2 + rb]; }
-}
-NVB_HD void long_phase1_col(int l, int col, const LongIn& in, const float* tab, float2* ex) {
-    const int r = col ? 63 - l : l;
-    cpx R[8];
+    for (int k2 = 0; k2 < 8; k2++) { pa[k2] = spec2[64 * k2 + ra]; pb[k2] = spec2[64 * k2 + rb]; }
+    const float4* T2 = reinterpret_cast<const float4*>(tab + FusedTables::T2);
+    LongRegs R;
     #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) {
-        cpx c;                                              // X[2k] + i X[M-1-2k], k = 64 k2 + r
-        c.x = col ? in.pb[k2].x : in.pa[k2].x;
-        c.y = col ? in.pa[7 - k2].y : in.pb[7 - k2].y;
-        R[k2] = cmul(c, to_cpx(tab2(tab, FusedTables::T1, k2, l, col)));
+        R.a[k2].x = pa[k2].x; R.a[k2].y = pb[7 - k2].y;    // X[2k] + i X[M-1-2k], k = 64 k2 + l
+        R.b[k2].x = pb[k2].x; R.b[k2].y = pa[7 - k2].y;    // k = 64 k2 + 63 - l
     }
-    fft8(R);
-    ex[r] = make_float2(R[0].x, R[0].y);
+    cmul_e_all(R.a); cmul_e_all(R.b);
+    fft8(R.a); fft8(R.b);
     #pragma unroll
-    for (int m2 = 1; m2 < 8; m2++) {
-        const cpx v = cmul(R[m2], to_cpx(tab2(tab, FusedTables::T2, m2 - 1, l, col)));
-        ex[m2 * 72 + r] = make_float2(v.x, v.y);
-    }
-}
-
-// ---- phase 2: gather the 8 k1 of (m2, k0); radix-8 over k1, twiddle W64^(k0*m1), store ex2.  Column a works on
-// rows 0-3, column b on rows 4-7; a row is shared by the 8 lanes with the same l >> 3, hence the warp barrier
-// between a column's loads and its stores.
-NVB_HD void long_phase2_load(int l, int col, const float2* ex, cpx* R) {
-    const int m2 = (l >> 3) + 4 * col, k0 = l & 7;
-    #pragma unroll
-    for (int k1 = 0; k1 < 8; k1++) R[k1] = to_cpx(ex[m2 * 72 + 8 * k1 + k0]);
-}
-NVB_HD void long_phase2_store(int l, int col, const float* tab, float2* ex, cpx* R) {
-    const int m2 = (l >> 3) + 4 * col, k0 = l & 7;
-    fft8(R);
-    ex[m2 * 72 + k0] = make_float2(R[0].x, R[0].y);
-    #pragma unroll
-    for (int m1 = 1; m1 < 8; m1++) {
-        const cpx v = cmul(R[m1], to_cpx(tab2(tab, FusedTables::T3, (m1 - 1) >> 1, l, (m1 - 1) & 1)));
-        ex[m2 * 72 + m1 * 9 + k0] = make_float2(v.x, v.y);
+    for (int m2 = 0; m2 < 8; m2++) {
+        const float4 w = T2[m2 * 32 + l];
+        const cpx va = cmul(R.a[m2], ld_cpx(w, 0)), vb = cmul(R.b[m2], ld_cpx(w, 1));
+        ex[m2 * 72 + ra] = make_float2(va.x, va.y);
+        ex[m2 * 72 + rb] = make_float2(vb.x, vb.y);
     }
 }
 
-// ---- phase 3: gather the 8 k0 of (m2, m1) [column a] and of (7-m2, 7-m1) [column b]; radix-8 over k0, post-twiddle.
-// The results of both columns pair up in the stores (u[2n], u[2n+1]) = (Re D[n], -Im D[511-n]), swizzled (u_swz2);
-// the stores overwrite exchange space, so they follow a warp barrier.
-NVB_HD void long_phase3_col(int l, int col, const float* tab, const float2* ex, cpx* R) {
-    const int m2 = col ? 7 - (l >> 3) : (l >> 3), m1 = col ? 7 - (l & 7) : (l & 7);
+// ---- phase 2: gather the 8 k1 of (m2, k0) for two m2; radix-8 over k1, twiddle W64^(k0*m1), store ex2
+NVB_HD void long_phase2_load(int l, const float2* ex, LongRegs& R) {
+    const int m2 = l >> 3, k0 = l & 7;
     #pragma unroll
-    for (int k0 = 0; k0 < 8; k0++) R[k0] = to_cpx(ex[m2 * 72 + m1 * 9 + k0]);
-    fft8(R);
-    #pragma unroll
-    for (int m0 = 0; m0 < 8; m0++) R[m0] = cmul(R[m0], to_cpx(tab2(tab, FusedTables::T4, m0, l, col)));
+    for (int k1 = 0; k1 < 8; k1++) {
+        float2 va = ex[m2 * 72 + 8 * k1 + k0], vb = ex[(m2 + 4) * 72 + 8 * k1 + k0];
+        R.a[k1].x = va.x; R.a[k1].y = va.y; R.b[k1].x = vb.x; R.b[k1].y = vb.y;
+    }
 }
-NVB_HD void long_phase3_store(int l, float2* u2, const cpx* Ra, const cpx* Rb) {
+NVB_HD void long_phase2_store(int l, const float* tab, float2* ex, LongRegs& R) {
+    const int m2 = l >> 3, k0 = l & 7;
+    const float4* T3 = reinterpret_cast<const float4*>(tab + FusedTables::T3);
+    fft8(R.a); fft8(R.b);
+    ex[m2 * 72 + k0] = make_float2(R.a[0].x, R.a[0].y);
+    ex[(m2 + 4) * 72 + k0] = make_float2(R.b[0].x, R.b[0].y);
+    #pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float4 w = T3[j * 32 + l];
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m1 = 2 * j + 1 + h;
+            if (m1 > 7) break;
+            const cpx t = ld_cpx(w, h);
+            const cpx va = cmul(R.a[m1], t), vb = cmul(R.b[m1], t);
+            ex[m2 * 72 + m1 * 9 + k0] = make_float2(va.x, va.y);
+            ex[(m2 + 4) * 72 + m1 * 9 + k0] = make_float2(vb.x, vb.y);
+        }
+    }
+}
+
+// ---- phase 3: gather the 8 k0 of (m2, m1) and of (7-m2, 7-m1); radix-8 over k0, post-twiddle E[m0] tw[n0],
+// write u as float2 pairs (u[2n], u[2n+1]) = (Re D[n], -Im D[511-n]), swizzled (u_swz2).
+NVB_HD void long_phase3_load(int l, const float2* ex, LongRegs& R) {
+    const int m2 = l >> 3, m1 = l & 7;
+    #pragma unroll
+    for (int k0 = 0; k0 < 8; k0++) {
+        float2 va = ex[m2 * 72 + m1 * 9 + k0], vb = ex[(7 - m2) * 72 + (7 - m1) * 9 + k0];
+        R.a[k0].x = va.x; R.a[k0].y = va.y; R.b[k0].x = vb.x; R.b[k0].y = vb.y;
+    }
+}
+NVB_HD void long_phase3_store(int l, const float* tab, float2* u2, LongRegs& R) {
+    const float4 w = reinterpret_cast<const float4*>(tab + FusedTables::T4)[l];
+    fft8(R.a); fft8(R.b);
+    cmul_e_all(R.a); cmul_e_all(R.b);
+    const cpx wa = ld_cpx(w, 0), wb = ld_cpx(w, 1);
+    #pragma unroll
+    for (int m0 = 0; m0 < 8; m0++) { R.a[m0] = cmul(R.a[m0], wa); R.b[m0] = cmul(R.b[m0], wb); }
     // n = na0 + 64 m0 and its partner 511 - n = nb0 + 64 (7 - m0), nb0 = 63 - na0; the swizzle only looks at
     // bits 4-5 of n, which belong to na0 / nb0
     const int sa = u_swz2(fused_na0(l)), sb = u_swz2(fused_nb0(l));
     #pragma unroll
     for (int m0 = 0; m0 < 8; m0++) {
-        u2[sa + 64 * m0] = make_float2(Ra[m0].x, -Rb[7 - m0].y);
-        u2[sb + 64 * (7 - m0)] = make_float2(Rb[7 - m0].x, -Ra[m0].y);
+        u2[sa + 64 * m0] = make_float2(R.a[m0].x, -R.b[7 - m0].y);
+        u2[sb + 64 * (7 - m0)] = make_float2(R.b[7 - m0].x, -R.a[m0].y);
     }
 }
 

@@ -94,18 +94,25 @@ void fast_tables(int n, float2* tw, float2* fft) {
     }
 }
 
-// Lane tables of the fused kernel (FusedTables, nvb_fused_core.h) from the plain twiddle tables.
-void build_fused_tables(const float2* tw1, const float2* w512, const float2* tw0, const float2* w64, const float* slope_long, float* out) {
-    auto put = [&](int base, int row, int lane, float2 a, float2 b) {
-        float* p = out + base + (row * 32 + lane) * 4;
-        p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
-    };
+// Lane tables of the fused kernel (FusedTables, nvb_fused_core.h), N = 2048 / 256, evaluated in double.
+void build_fused_tables(const float2* tw0, const float2* w64, const float* slope_long, float* out) {
+    const double pi = 3.14159265358979323846;
+    auto tw = [&](int k) { return -pi * (k + 0.125) / 1024.0; };                // angle of tw[k] = exp(-i pi (k + 1/8) / M), M = 1024
+    auto put2 = [&](float* p, double ang) { p[0] = (float)std::cos(ang); p[1] = (float)std::sin(ang); };
     for (int l = 0; l < 32; l++) {
         const int ra = l, rb = 63 - l, k0 = l & 7;
-        for (int k2 = 0; k2 < 8; k2++) put(FusedTables::T1, k2, l, tw1[64 * k2 + ra], tw1[64 * k2 + rb]);
-        for (int m2 = 1; m2 < 8; m2++) put(FusedTables::T2, m2 - 1, l, w512[(ra * m2) & 511], w512[(rb * m2) & 511]);
-        for (int j = 0; j < 4; j++) put(FusedTables::T3, j, l, w512[(8 * k0 * (2 * j + 1)) & 511], w512[(8 * k0 * (2 * j + 2)) & 511]);
-        for (int m0 = 0; m0 < 8; m0++) put(FusedTables::T4, m0, l, tw1[fused_na0(l) + 64 * m0], tw1[fused_nb0(l) + 64 * m0]);
+        for (int m2 = 0; m2 < 8; m2++) {
+            float* p = out + FusedTables::T2 + (m2 * 32 + l) * 4;
+            put2(p, tw(ra) - 2.0 * pi * ((ra * m2) & 511) / 512.0);
+            put2(p + 2, tw(rb) - 2.0 * pi * ((rb * m2) & 511) / 512.0);
+        }
+        for (int j = 0; j < 4; j++) {
+            float* p = out + FusedTables::T3 + (j * 32 + l) * 4;
+            put2(p, -2.0 * pi * ((k0 * (2 * j + 1)) & 63) / 64.0);
+            put2(p + 2, -2.0 * pi * ((k0 * (2 * j + 2)) & 63) / 64.0);
+        }
+        float* p = out + FusedTables::T4 + l * 4;
+        put2(p, tw(fused_na0(l))); put2(p + 2, tw(fused_nb0(l)));
     }
     for (int i = 0; i < 1024; i++) out[FusedTables::WIN + i] = slope_long[i];
     for (int k = 0; k < 64; k++) {
@@ -359,8 +366,7 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
     if (h.bs[0] == FUSED_SHORT_N && h.bs[1] == FUSED_LONG_N) {
         h.off_fused_tab = w.reserve(sizeof(float) * FusedTables::FLOATS);
         // rising slope of window 3 (long block between long blocks): the first 1024 values of that window
-        build_fused_tables(w.at<float2>(h.off_tw[1]), w.at<float2>(h.off_fft[1]), w.at<float2>(h.off_tw[0]), w.at<float2>(h.off_fft[0]),
-                           w.at<float>(h.off_win_long) + 3 * (size_t)h.bs[1], w.at<float>(h.off_fused_tab));
+        build_fused_tables(w.at<float2>(h.off_tw[0]), w.at<float2>(h.off_fft[0]), w.at<float>(h.off_win_long) + 3 * (size_t)h.bs[1], w.at<float>(h.off_fused_tab));
     }
 
     // largest residue item table over the modes (k_spectrum's shared-memory prefix array)
