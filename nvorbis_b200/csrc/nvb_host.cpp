@@ -145,6 +145,7 @@ void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) 
     S.channels = h.channels; S.bs[0] = h.bs[0]; S.bs[1] = h.bs[1];
     S.post_stride = h.post_stride; S.max_items = h.max_items; S.spectrum_fast = h.spectrum_fast;
     S.max_stages = h.max_stages > 0 ? h.max_stages : 1;
+    S.ci_total = h.ci_total; S.n_residues = h.n_residues;
     S.books = reinterpret_cast<const DevBook*>(base + h.off_books);
     S.vq = reinterpret_cast<const float*>(base + h.off_vq); S.n_vq = (int64_t)h.n_vq;
     S.floors = reinterpret_cast<const DevFloor1*>(base + h.off_floors);
@@ -288,6 +289,7 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         w.at<DevFloor1>(h.off_floors)[i] = d;
     }
     h.off_residues = w.reserve(sizeof(DevResidue) * s->n_residues);
+    int ci_total = 0;
     for (int i = 0; i < s->n_residues; i++) {
         const nvb_residue& r = s->residues[i];
         DevResidue d; std::memset(&d, 0, sizeof d);
@@ -306,10 +308,12 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
                     const int cnt = r.type == 0 ? r.partition_size / dims : (r.partition_size + dims - 1) / dims;   // Residue0.cs:183 / Residue1.cs:12 / Residue2.cs:28
                     if (cnt > 32767 || !is_pow2(dims) || dims > r.partition_size) fast = false;
                     d.cnt[c][st] = (int16_t)(cnt > 32767 ? 32767 : cnt);
+                    if (cnt > 0) d.coded[c] |= (uint8_t)(1u << st);
                 }
             }
         }
         d.fast = fast ? 1 : 0;
+        d.ci_off = ci_total; ci_total += r.classifications * (r.max_stages > 0 ? r.max_stages : 1);
         // level 2: the plane kernel (k_spectrum_planes): one interleaved stream (type 2, or a single channel of type 1) whose
         // partitions start on multiples of G = max(4, C) floats
         const int G = C > 4 ? C : 4;
@@ -381,6 +385,7 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         }
         if (mx > 40000) return fail(err, NVB_ERR_UNSUPPORTED, "residue layout needs %lld prefix items (> 40000)", mx);
         h.max_items = mx;
+        h.ci_total = ci_total;
         h.max_stages = 1;
         for (int i = 0; i < h.n_residues; i++) if (S.residues[i].stages > h.max_stages) h.max_stages = S.residues[i].stages;
         int fast = 2;

@@ -35,6 +35,8 @@ struct DevResidue {
     int32_t cascade[NVB_MAX_CLASSES];
     int16_t books[NVB_MAX_CLASSES][NVB_MAX_STAGES];
     int16_t cnt[NVB_MAX_CLASSES][NVB_MAX_STAGES];   // VQ entries one partition of (class, stage) consumes; 0 = nothing coded
+    uint8_t coded[NVB_MAX_CLASSES];                 // per class: bit s set <=> stage s codes entries (cnt > 0)
+    int32_t ci_off, pad2;                           // k_spectrum_warp: start of this residue's (class, stage) records in its shared table
 };
 struct DevMapping { int32_t n_coupling, floor, residue, pad; uint8_t mag[NVB_MAX_COUPLING], ang[NVB_MAX_COUPLING]; };
 struct DevMode    { int32_t block_flag, mapping; };
@@ -59,12 +61,12 @@ struct BlobHeader {
     uint64_t n_vq;
     uint64_t off_fused_tab;    // FusedTables block (nvb_fused_core.h) when bs == {256, 2048}, else 0
     int32_t max_stages;        // largest residue stage count of the setup
-    int32_t pad1;
+    int32_t ci_total;          // sum over residues of nclass * stages: size of k_spectrum_warp's (class, stage) table
 };
 
 // Resolved pointers handed to kernels by value.
 struct DevSetup {
-    int32_t channels, bs[2], post_stride, max_items, spectrum_fast, max_stages;
+    int32_t channels, bs[2], post_stride, max_items, spectrum_fast, max_stages, ci_total, n_residues;
     const DevBook* books; const float* vq; int64_t n_vq;
     const DevFloor1* floors; const DevResidue* residues; const DevMapping* mappings; const DevMode* modes;
     const float* win_short; const float* win_long;

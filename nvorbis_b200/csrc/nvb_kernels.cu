@@ -647,6 +647,215 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1+K2+K3, warp path (the default when DevSetup.spectrum_fast == 2): the same arithmetic as k_spectrum_planes with
+// ONE WARP PER FRAME in a persistent grid -- no block-wide barrier, every warp runs its own frame start to end
+// while the other warps of the SM hide its latencies:
+//   floor unwrap + segment list per channel (lane = post), (stage, partition) item compaction (warp scan),
+//   floor curve as 8-bit table indices (lanes over x), residue: half a warp per item, lane = VQ entry, whole VQ
+//   vectors added into ONE accumulator plane stage after stage (the reference's add order; a (stage, position)
+//   pair has a single writer, so no atomics), then groups of G = max(4, C) interleaved values: inverse coupling,
+//   floor multiply, vector stores of the channel rows.
+// Per-warp shared memory: accumulator plane C*n floats + C*n floor bytes + segment / item lists.
+// ------------------------------------------------------------------------------------------------
+struct WarpSmem { size_t acc, fl8, seg, fy, items, cls, misc, total; };
+__host__ __device__ inline WarpSmem spectrum_warp_layout(int C, int bs1, int max_items) {
+    WarpSmem w; size_t o = 0;
+    const size_t span = (size_t)C * (bs1 / 2);
+    w.acc = o; o += span * sizeof(float);
+    w.fl8 = o; o += (span + 15) & ~size_t(15);
+    w.seg = o; o += (((size_t)C * (NVB_MAX_POSTS + 1) * sizeof(SegRec)) + 15) & ~size_t(15);
+    w.fy = o; o += (size_t)C * NVB_MAX_POSTS * sizeof(int);
+    w.items = o; o += ((size_t)max_items * sizeof(ItemRec) + 15) & ~size_t(15);
+    w.cls = o; o += ((size_t)max_items + 15) & ~size_t(15);
+    w.misc = o; o += 64;
+    w.total = o;
+    return w;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(512) k_spectrum_warp(LaunchArgs a) {
+    constexpr int G = CT > 4 ? CT : 4;
+    constexpr int CSH = CT == 1 ? 0 : CT == 2 ? 1 : CT == 4 ? 2 : 3;
+    NVB_DYN_SMEM(dyn_smem);
+    const DevSetup& S = a.S;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+    // CTA-shared: dB table + the (class, stage) records of every residue
+    float* s_db = reinterpret_cast<float*>(dyn_smem);
+    int4* s_ci = reinterpret_cast<int4*>(s_db + 256);
+    const WarpSmem L = spectrum_warp_layout(CT, S.bs[1], S.max_items);
+    unsigned char* wbase = dyn_smem + 1024 + (((size_t)S.ci_total * sizeof(int4) + 15) & ~size_t(15)) + (size_t)warp * L.total;
+    float* s_acc = reinterpret_cast<float*>(wbase + L.acc);
+    uint8_t* s_fl8 = wbase + L.fl8;
+    SegRec* s_seg = reinterpret_cast<SegRec*>(wbase + L.seg);
+    int* s_fy = reinterpret_cast<int*>(wbase + L.fy);
+    ItemRec* s_items = reinterpret_cast<ItemRec*>(wbase + L.items);
+    uint8_t* s_cls = wbase + L.cls;
+    int* s_nseg = reinterpret_cast<int*>(wbase + L.misc);                   // [CT]
+
+    for (int i = t; i < 256; i += blockDim.x) s_db[i] = S.db[i];
+    for (int r = 0; r < S.n_residues; r++) {
+        const DevResidue& R = S.residues[r];
+        const int st_n = R.stages > 0 ? R.stages : 1;
+        for (int i = t; i < R.nclass * st_n; i += blockDim.x) {
+            const int cl = i / st_n, st = i - cl * st_n;
+            const int book = st < R.stages ? R.books[cl][st] : -1;
+            int4 ci = make_int4(0, 1, 0, 0);
+            if (book >= 0) { const DevBook b = S.books[book]; ci = make_int4((int)b.off, b.dims, b.entries, R.cnt[cl][st]); }
+            s_ci[R.ci_off + i] = ci;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t lt = (1u << lane) - 1u;
+    const int hl = lane & 15, half = lane >> 4;
+    for (int fi = blockIdx.x * nwarps + warp; fi < a.n_frames; fi += gridDim.x * nwarps) {
+        const DevFrame f = a.frames[fi];
+        if (f.kind != 0) continue;
+        const DevMode md = S.modes[f.mode];
+        const DevMapping& mp = S.mappings[md.mapping];
+        const DevResidue& R = S.residues[mp.residue];
+        const DevFloor1& F = S.floors[mp.floor];
+        const int n = f.n >> 1, span = CT * n;
+        const int st_n = R.stages > 0 ? R.stages : 1;
+        const uint8_t* cls = a.classes + f.classes_off;
+        const uint16_t* ent = a.entries + f.entries_off;
+        ResGeom g; g.P = 0; g.Sx = 1; g.n_items = 0;
+        if (f.res_decoded) g = residue_geom(R, f.n, CT);
+        const int P = g.P;
+        int bad_floor = 0, bad_entry = 0;
+        __syncwarp();                                                       // the previous frame's readers of this warp's buffers are done
+
+        // ---- floors: unwrap + segments, one channel after the other
+        for (int c = 0; c < CT; c++) {
+            if ((f.exec_mask >> c) & 1u)
+                floor1_segments_warp(F, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, n, lane, s_fy + c * NVB_MAX_POSTS, s_seg + c * (NVB_MAX_POSTS + 1), &s_nseg[c]);
+            else if (lane == 0) s_nseg[c] = 0;
+        }
+        // ---- residue items: compaction of the coded (stage, partition) pairs, start of each one's entries
+        int nitems = 0; int stage_end[NVB_MAX_STAGES];
+        {
+            uint32_t run = 0;
+            for (int st = 0; st < R.stages; st++) {
+                for (int base = 0; base < P; base += 32) {
+                    const int p = base + lane;
+                    uint32_t c = 0; int cl = 255;
+                    if (p < P) { cl = cls[p]; if (cl < R.nclass) c = (uint32_t)R.cnt[cl][st]; else cl = 255; if (st == 0) s_cls[p] = (uint8_t)cl; }
+                    uint32_t incl = c;
+                    #pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+                    const unsigned m = __ballot_sync(0xffffffffu, c > 0);
+                    if (c > 0) { ItemRec r; r.p = (uint16_t)p; r.s = (uint8_t)st; r.cl = (uint8_t)cl; r.base = run + incl - c; s_items[nitems + __popc(m & lt)] = r; }
+                    nitems += __popc(m);
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                stage_end[st] = nitems;
+            }
+        }
+        // ---- clear the accumulator plane (Mapping.cs:108)
+        for (int i = lane * 4; i < span; i += 128) *reinterpret_cast<float4*>(s_acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+
+        // ---- floor curve as table indices, channel-interleaved (RenderLineMulti in closed form, Floor1.cs:316-341)
+        for (int c = 0; c < CT; c++) {
+            const int ns = s_nseg[c];
+            for (int u = 0; u < ns; u++) {
+                const SegRec r = s_seg[c * (NVB_MAX_POSTS + 1) + u];
+                const int len = r.x1 - r.x0;
+                const int dyabs = r.ady + (r.b < 0 ? -r.b : r.b) * len;     // |dy|: y(k) = y0 + sy * floor(k |dy| / adx)
+                uint8_t* row = s_fl8 + r.x0 * CT + c;
+                for (int k = lane; k < len; k += 32) {
+                    int y = r.y0 + r.sy * div_small(k * dyabs, len, r.rcp);
+                    if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
+                    row[k * CT] = (uint8_t)y;
+                }
+            }
+        }
+        // ---- residue: stage after stage, half a warp per item, lane = entry, whole VQ vectors added into the plane
+        {
+            int it0 = 0;
+            for (int st = 0; st < R.stages; st++) {
+                const int it1 = stage_end[st];
+                for (int idx = it0 + half; idx < it1; idx += 2) {
+                    const ItemRec r = s_items[idx];
+                    const int4 ci = s_ci[R.ci_off + r.cl * st_n + st];
+                    const int dims = ci.y;
+                    float* dst = s_acc + R.begin + (int)r.p * R.psize;
+                    const float* tab = S.vq + ci.x;
+                    for (int e = hl; e < ci.w; e += 16) {
+                        const uint32_t ei = r.base + (uint32_t)e;
+                        if (ei >= f.entry_count) continue;                  // never decoded: contributes nothing (Residue0.cs:164-170)
+                        const int en = ent[ei];
+                        if (en >= ci.z) { bad_entry = 1; continue; }
+                        const float* src = tab + (size_t)en * dims;
+                        float* d = dst + e * dims;
+                        if (dims == 2) {
+                            const float2 v = *reinterpret_cast<const float2*>(src); float2 o = *reinterpret_cast<float2*>(d);
+                            o.x = NVB_FADD(o.x, v.x); o.y = NVB_FADD(o.y, v.y); *reinterpret_cast<float2*>(d) = o;
+                        } else if (dims == 1) *d = NVB_FADD(*d, *src);
+                        else for (int k = 0; k < dims; k += 4) {
+                            const float4 v = *reinterpret_cast<const float4*>(src + k); float4 o = *reinterpret_cast<float4*>(d + k);
+                            o.x = NVB_FADD(o.x, v.x); o.y = NVB_FADD(o.y, v.y); o.z = NVB_FADD(o.z, v.z); o.w = NVB_FADD(o.w, v.w);
+                            *reinterpret_cast<float4*>(d + k) = o;
+                        }
+                    }
+                }
+                it0 = it1;
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+
+        // ---- inverse coupling, floor multiply, store
+        float* spec_out = a.spectrum + (size_t)f.spec_off;
+        bool execc[CT], hasfl[CT];
+        #pragma unroll
+        for (int c = 0; c < CT; c++) { execc[c] = (f.exec_mask >> c) & 1u; hasfl[c] = s_nseg[c] > 0; }
+        for (int pos = lane * G; pos < span; pos += 32 * G) {
+            float acc[G];
+            #pragma unroll
+            for (int k = 0; k < G; k += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(s_acc + pos + k);
+                acc[k] = v.x; acc[k + 1] = v.y; acc[k + 2] = v.z; acc[k + 3] = v.w;
+            }
+            for (int i = mp.n_coupling - 1; i >= 0; --i) {                  // Mapping.cs:137-182
+                const int m = mp.mag[i], an = mp.ang[i];
+                if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
+                #pragma unroll
+                for (int b = 0; b < G / CT; b++) {
+                    float vm = 0.f, va = 0.f;
+                    #pragma unroll
+                    for (int k = 0; k < CT; k++) { if (k == m) vm = acc[b * CT + k]; if (k == an) va = acc[b * CT + k]; }
+                    inverse_couple(vm, va);
+                    #pragma unroll
+                    for (int k = 0; k < CT; k++) { if (k == m) acc[b * CT + k] = vm; if (k == an) acc[b * CT + k] = va; }
+                }
+            }
+            #pragma unroll
+            for (int k = 0; k < G; k += 4) {
+                const uchar4 y4 = *reinterpret_cast<const uchar4*>(s_fl8 + pos + k);
+                const uint8_t yv[4] = {y4.x, y4.y, y4.z, y4.w};
+                #pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int c = (k + e) & (CT - 1);
+                    if (execc[c]) acc[k + e] = hasfl[c] ? NVB_FMUL(acc[k + e], s_db[yv[e]]) : 0.f;      // Floor1.Apply, Floor1.cs:186-222
+                }
+            }
+            const int bin0 = pos >> CSH;
+            if (CT == 1) *reinterpret_cast<float4*>(spec_out + bin0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            else if (CT == 2) {
+                *reinterpret_cast<float2*>(spec_out + bin0) = make_float2(acc[0], acc[2]);
+                *reinterpret_cast<float2*>(spec_out + n + bin0) = make_float2(acc[1], acc[3]);
+            } else {
+                #pragma unroll
+                for (int c = 0; c < CT; c++) spec_out[(size_t)c * n + bin0] = acc[c];
+            }
+        }
+        if (__any_sync(0xffffffffu, bad_entry) && lane == 0) atomicAdd(&a.counters->bad_entry, 1);
+        if (__any_sync(0xffffffffu, bad_floor) && lane == 0) atomicAdd(&a.counters->floor_range, 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4 exact: one CTA per (frame, channel); the reference's stb_vorbis IMDCT schedule cut into
 // data-parallel steps with a barrier between them, all in shared memory (u[N] + v[N/2]).
 // Bit-identical to Mdct.cs for every N (including its N = 64/128 behaviour).
@@ -730,6 +939,38 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
     static const bool force_generic = std::getenv("NVB_SPECTRUM_GENERIC") != nullptr;      // test hook: exercise the general kernel
     if (!a.S.spectrum_fast || force_generic) return launch_spectrum_generic(a, stream);
     static const bool no_planes = std::getenv("NVB_SPECTRUM_NO_PLANES") != nullptr;           // test hook: exercise k_spectrum_fast
+    static const bool no_warp = std::getenv("NVB_SPECTRUM_NO_WARP") != nullptr;               // test hook: exercise k_spectrum_planes
+    if (a.S.spectrum_fast >= 2 && !no_planes && !no_warp) {
+        const int C = a.S.channels;
+        const WarpSmem L = spectrum_warp_layout(C, a.S.bs[1], a.S.max_items);
+        const size_t shared_part = 1024 + (((size_t)a.S.ci_total * sizeof(int4) + 15) & ~size_t(15));
+        int nw = (int)((220 * 1024 - shared_part) / L.total);
+        if (nw > 16) nw = 16;
+        if (nw >= 2) {
+            static int num_sms = 0;
+            if (num_sms == 0) {
+                int dev = 0; cudaGetDevice(&dev);
+                if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+            }
+            const size_t smem = shared_part + (size_t)nw * L.total;
+            static size_t configured_w = 0;
+            if (smem > configured_w) {
+                cudaError_t e = C == 1 ? cudaFuncSetAttribute(k_spectrum_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : C == 2 ? cudaFuncSetAttribute(k_spectrum_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : C == 4 ? cudaFuncSetAttribute(k_spectrum_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                       : cudaFuncSetAttribute(k_spectrum_warp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return -1;
+                configured_w = smem;
+            }
+            int grid = (a.n_frames + nw - 1) / nw;
+            if (grid > num_sms) grid = num_sms;
+            if (C == 1) NVB_LAUNCH(k_spectrum_warp<1>, grid, nw * 32, smem, stream, a);
+            else if (C == 2) NVB_LAUNCH(k_spectrum_warp<2>, grid, nw * 32, smem, stream, a);
+            else if (C == 4) NVB_LAUNCH(k_spectrum_warp<4>, grid, nw * 32, smem, stream, a);
+            else NVB_LAUNCH(k_spectrum_warp<8>, grid, nw * 32, smem, stream, a);
+            return cudaGetLastError() == cudaSuccess ? 1 : -1;
+        }
+    }
     if (a.S.spectrum_fast >= 2 && !no_planes) {
         const int C = a.S.channels;
         // planes for the deepest residue + floor rows + item list + class bytes (host-checked to fit)
