@@ -37,7 +37,8 @@ def workload_config(n_gpus: int) -> dict:
                         "(long/long frames of the 3test stream drawn with replacement, PCG64 seeds 20240002+)",
             "frames_per_step_per_gpu": FRAMES_PER_STEP, "channels": 2, "block_size": 2048,
             "l2_policy": f"{ROTATE} rotating batch sets (inputs + spectrum scratch + PCM, ~70 MB each) > 126 MB L2",
-            "sharding": f"{n_gpus} independent shards, one NCCL broadcast of the table blob, no data-path collective"}
+            "sharding": f"corpus of {n_gpus} x 4096 frames cut into {n_gpus} contiguous shards (+1 halo frame each), one NCCL broadcast "
+                        "of the table blob, no data-path collective"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -162,7 +163,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from nvorbis_b200 import capi, setupio, workloads
+    from nvorbis_b200 import capi, setupio, sharding, workloads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,7 +204,10 @@ def run_ours(args):
 
     keep, host_batches, dbatches, pcm_bufs, spec_bufs = [], [], [], [], []
     for s in range(ROTATE):
-        hb = workloads.config2(pool, FRAMES_PER_STEP, SEED + 1000 * rank + s)
+        # the step's corpus (the same on every rank: seeded) and this rank's shard of it: a contiguous range of
+        # FRAMES_PER_STEP frames plus one halo frame in front (none on rank 0), no data-path communication
+        corpus = workloads.config2(pool, FRAMES_PER_STEP * world, SEED + s)
+        hb = sharding.take_shard(corpus, sharding.shard_cuts(corpus.frames, world), rank, C) if world > 1 else corpus
         hb = capi.HostBatch(pinned(hb.frames), pinned(hb.posts), pinned(hb.classes), pinned(hb.entries))
         host_batches.append(hb)
         db = ctx.create_dbatch(hb)

@@ -149,6 +149,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
     const int Bm = 62 - L2;
     const int B0 = Bm ^ ((Bm >> 5) << 2), B8 = B0 ^ 8;
     float peak = 0.f;
+    // Register-level software pipeline: the spectrum rows of the warp's next long transform are loaded right after
+    // the current transform has consumed its inputs, so the load latency hides behind passes 2-3 and the output.
+    LongIn pre; int pre_x = -1, pre_c = -1;
+    auto can_prefetch = [&](int kind, int n, uint32_t exec_mask, int cc) { return kind == 0 && n == FUSED_LONG_N && ((exec_mask >> cc) & 1u); };
 
     for (int x = first + warp; x < hi; x += FUSED_WARPS) {
         const int rel = x - first, slot = rel % NS, it = rel / NS;
@@ -156,6 +160,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
         if (lane == 0) s_fr[slot] = a.frames[x];
         __syncwarp();
         const DevFrame f = s_fr[slot];
+        const int xn = x + FUSED_WARPS;                                      // the warp's next frame (for the prefetch)
+        int n_kind = 1, n_n = 0; uint32_t n_exec = 0, n_spec = 0;
+        if (xn < hi) { const DevFrame* fn = a.frames + xn; n_kind = fn->kind; n_n = fn->n; n_exec = fn->exec_mask; n_spec = fn->spec_off; }
         float* slots_f = s_slots + (size_t)slot * C * FUSED_SLOT_FLOATS;
 
         // ---------------- transform: every channel of frame x -------------------------------------
@@ -169,7 +176,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
                 } else if (f.n == FUSED_LONG_N) {
                     float2* ex = reinterpret_cast<float2*>(slotc);
                     LongRegs R;
-                    long_phase1(lane, reinterpret_cast<const float2*>(spec), s_tab, ex);
+                    if (!(pre_x == x && pre_c == c)) long_phase1_load(lane, reinterpret_cast<const float2*>(spec), pre);   // cold start
+                    long_phase1_compute(lane, pre, s_tab, ex);
+                    if (c + 1 < C && can_prefetch(0, f.n, f.exec_mask, c + 1)) {
+                        long_phase1_load(lane, reinterpret_cast<const float2*>(spec + M), pre); pre_x = x; pre_c = c + 1;
+                    } else if (c + 1 == C && can_prefetch(n_kind, n_n, n_exec, 0)) {
+                        long_phase1_load(lane, reinterpret_cast<const float2*>(a.spectrum + (size_t)n_spec), pre); pre_x = xn; pre_c = 0;
+                    }
                     __syncwarp();
                     long_phase2_load(lane, ex, R);
                     __syncwarp();

@@ -92,17 +92,20 @@ struct LongRegs { cpx a[8]; cpx b[8]; };
 
 // ---- phase 1: load spectrum pairs, constant part of the pre-twiddle, radix-8 over k2, twiddle tw[r] W512^(r*m2), store ex1
 // spec2: the channel's spectrum as float2[512] (global memory); tab: FusedTables in shared memory; ex: float2[576].
-NVB_HD void long_phase1(int l, const float2* spec2, const float* tab, float2* ex) {
+struct LongIn { float2 pa[8], pb[8]; };
+NVB_HD void long_phase1_load(int l, const float2* spec2, LongIn& in) {
     const int ra = l, rb = 63 - l;
-    float2 pa[8], pb[8];
     #pragma unroll
-    for (int k2 = 0; k2 < 8; k2++) { pa[k2] = spec2[64 * k2 + ra]; pb[k2] = spec2[64 * k2 + rb]; }
+    for (int k2 = 0; k2 < 8; k2++) { in.pa[k2] = spec2[64 * k2 + ra]; in.pb[k2] = spec2[64 * k2 + rb]; }
+}
+NVB_HD void long_phase1_compute(int l, const LongIn& in, const float* tab, float2* ex) {
+    const int ra = l, rb = 63 - l;
     const float4* T2 = reinterpret_cast<const float4*>(tab + FusedTables::T2);
     LongRegs R;
     #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) {
-        R.a[k2].x = pa[k2].x; R.a[k2].y = pb[7 - k2].y;    // X[2k] + i X[M-1-2k], k = 64 k2 + l
-        R.b[k2].x = pb[k2].x; R.b[k2].y = pa[7 - k2].y;    // k = 64 k2 + 63 - l
+        R.a[k2].x = in.pa[k2].x; R.a[k2].y = in.pb[7 - k2].y;    // X[2k] + i X[M-1-2k], k = 64 k2 + l
+        R.b[k2].x = in.pb[k2].x; R.b[k2].y = in.pa[7 - k2].y;    // k = 64 k2 + 63 - l
     }
     cmul_e_all(R.a); cmul_e_all(R.b);
     fft8(R.a); fft8(R.b);
