@@ -6,6 +6,7 @@
 #endif
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -27,6 +28,10 @@ struct nvb_ctx {
     float* d_carry[2] = {nullptr, nullptr};
     int carry_cur = 0;
     cudaStream_t stream = nullptr;
+    // nvb_decode_batch pipelines chunks of a large batch over these: kernels of chunk k+1 run while the PCM of chunk k
+    // crosses PCIe
+    cudaStream_t chunk_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_inputs = nullptr, ev_spec[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // reusable device staging of nvb_decode_batch
     nvb_dbatch* staging = nullptr;
     float* d_pcm = nullptr; size_t pcm_cap = 0;
@@ -135,7 +140,7 @@ int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags,
 LaunchArgs make_args(nvb_ctx* ctx, nvb_dbatch* b, float* spectrum, float* d_pcm, bool save_carry) {
     LaunchArgs a;
     a.S = ctx->S;
-    a.frames = b->d_frames; a.n_frames = (int)b->plan.frames.size();
+    a.frames = b->d_frames; a.frame_lo = 0; a.n_frames = (int)b->plan.frames.size();
     a.posts = b->d_posts; a.classes = b->d_classes; a.entries = b->d_entries;
     a.spectrum = spectrum;
     a.blocks = b->d_blocks;
@@ -150,16 +155,20 @@ LaunchArgs make_args(nvb_ctx* ctx, nvb_dbatch* b, float* spectrum, float* d_pcm,
 
 // Enqueues the synthesis of an uploaded batch.  stage: 0 = all, 1 = spectrum only, 2 = IMDCT.. only.
 // `spectrum` = dense spectrum buffer written by stage 1 and read by stage 2 (nullptr: the batch's own).
-int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pcm, bool save_carry, cudaStream_t st) {
+int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pcm, bool save_carry, cudaStream_t st,
+            int frame_lo = 0, int frame_cnt = -1, bool reset_counters = true, cudaEvent_t after_spectrum = nullptr, cudaEvent_t before_synth = nullptr) {
     if (b->plan.frames.empty()) { b->launches = 0; return NVB_OK; }
     LaunchArgs a = make_args(ctx, b, spectrum ? spectrum : b->d_spectrum, d_pcm, save_carry);
+    if (frame_cnt >= 0) { a.frame_lo = frame_lo; a.n_frames = frame_cnt; }
     int launches = 0, r;
-    NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), st));
+    if (reset_counters) NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), st));
     if (stage != 2) {
         if ((r = launch_spectrum(a, st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_spectrum launch");
         launches += r;
+        if (after_spectrum) NVB_CUDA(ctx, cudaEventRecord(after_spectrum, st));
     }
     if (stage != 1) {
+        if (before_synth) NVB_CUDA(ctx, cudaStreamWaitEvent(st, before_synth, 0));     // the halo block's spectrum comes from the previous chunk
         if (b->fused) {
             if ((r = launch_imdct_fused(a, b->plan.frames.data(), st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_imdct_fused launch");
             launches += r;
@@ -175,7 +184,7 @@ int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pc
             }
         }
     }
-    b->launches = launches;
+    b->launches = (frame_cnt >= 0 && frame_lo > 0) ? b->launches + launches : launches;
     return NVB_OK;
 }
 
@@ -234,7 +243,13 @@ int nvb_create(int device, nvb_ctx** out) {
     ctx->device = device;
     DeviceGuard g(device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&ctx->chunk_stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_spec[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate / cudaEventCreate"); }
     *out = ctx;
     return NVB_OK;
 }
@@ -246,6 +261,8 @@ int nvb_destroy(nvb_ctx* ctx) {
     free_dbatch(ctx->staging);
     cudaFree(ctx->d_pcm); cudaFree(ctx->d_blob); cudaFree(ctx->d_carry[0]); cudaFree(ctx->d_carry[1]);
     cudaStreamDestroy(ctx->stream);
+    for (int i = 0; i < 2; i++) { cudaStreamDestroy(ctx->chunk_stream[i]); cudaEventDestroy(ctx->ev_spec[i]); cudaEventDestroy(ctx->ev_done[i]); }
+    cudaEventDestroy(ctx->ev_inputs);
     delete ctx;
     return NVB_OK;
 }
@@ -316,9 +333,34 @@ int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm
     const size_t n_out = (size_t)b->plan.samples * ctx->H.channels;
     if (n_out > pcm_cap || (n_out > 0 && !pcm_out)) { cudaStreamSynchronize(ctx->stream); return set_err(ctx, NVB_ERR_CAPACITY, "pcm_out too small for the batch"); }
     if ((rc = grow(ctx, ctx->d_pcm, ctx->pcm_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
-    rc = enqueue(ctx, b, 0, nullptr, ctx->d_pcm, true, ctx->stream);
-    if (rc != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
-    if (n_out) NVB_CUDA(ctx, cudaMemcpyAsync(pcm_out, ctx->d_pcm, n_out * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    const int nf = (int)b->plan.frames.size();
+    static const int chunk_min = std::getenv("NVB_CHUNK_MIN") ? std::atoi(std::getenv("NVB_CHUNK_MIN")) : 1024;   // test hook
+    const int n_chunks = (b->fused && nf >= chunk_min && nf >= 8) ? 4 : 1;
+    if (n_chunks == 1) {
+        rc = enqueue(ctx, b, 0, nullptr, ctx->d_pcm, true, ctx->stream);
+        if (rc != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+        if (n_out) NVB_CUDA(ctx, cudaMemcpyAsync(pcm_out, ctx->d_pcm, n_out * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        // Pipeline: inputs up (one copy), then per chunk of frames: spectrum + synthesis kernels and the D2H of that chunk's
+        // PCM range, chunks alternating between two streams so that kernels overlap the previous chunk's PCIe transfer.
+        // A chunk's first block overlaps onto the last block of the previous chunk, whose spectrum the previous chunk's
+        // stream produces: one event per chunk orders exactly that.
+        NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), ctx->stream));
+        NVB_CUDA(ctx, cudaEventRecord(ctx->ev_inputs, ctx->stream));
+        const size_t C = (size_t)ctx->H.channels;
+        for (int k = 0; k < n_chunks; k++) {
+            cudaStream_t st = ctx->chunk_stream[k & 1];
+            const int lo = (int)((long long)nf * k / n_chunks), hi = (int)((long long)nf * (k + 1) / n_chunks);
+            NVB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_inputs, 0));
+            rc = enqueue(ctx, b, 0, nullptr, ctx->d_pcm, true, st, lo, hi - lo, false, ctx->ev_spec[k & 1], k > 0 ? ctx->ev_spec[(k - 1) & 1] : nullptr);
+            if (rc != NVB_OK) { cudaDeviceSynchronize(); return rc; }
+            const size_t s0 = (size_t)b->plan.frames[(size_t)lo].pcm_off * C;
+            const size_t s1 = hi < nf ? (size_t)b->plan.frames[(size_t)hi].pcm_off * C : n_out;
+            if (s1 > s0) NVB_CUDA(ctx, cudaMemcpyAsync(pcm_out + s0, ctx->d_pcm + s0, (s1 - s0) * sizeof(float), cudaMemcpyDeviceToHost, st));
+            NVB_CUDA(ctx, cudaEventRecord(ctx->ev_done[k & 1], st));
+        }
+        for (int i = 0; i < 2; i++) NVB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_done[i], 0));
+    }
     rc = fetch_result(ctx, b, ctx->stream, res);
     // the decoder state advances like StreamDecoder's even when an entry was out of range
     ctx->carry = b->plan.end_state;

@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
     int* s_empty = s_full + NS;                                             // s_empty[s]: reader releases of slot s (two per frame)
     uint64_t* s_tabbar = reinterpret_cast<uint64_t*>(s_empty + NS);          // 8 NS bytes past s_full: 8-byte aligned
 
-    const int lo = blockIdx.x * p.frames_per_cta;
-    int hi = lo + p.frames_per_cta; if (hi > a.n_frames) hi = a.n_frames;
+    const int lo = a.frame_lo + blockIdx.x * p.frames_per_cta;              // plan indices; this launch covers [frame_lo, frame_lo + n_frames)
+    int hi = lo + p.frames_per_cta; if (hi > a.frame_lo + a.n_frames) hi = a.frame_lo + a.n_frames;
     if (lo >= hi) return;
 
     if (tid == 0) {
@@ -138,6 +138,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
         const DevFrame f0 = a.frames[lo];
         if (f0.prev >= 0 && (f0.ola_len > 0 || f0.kind != 0)) first = lo - 1;   // halo: previous block's tail is needed
     }
+    // the first transform's rows are requested before the lane tables have landed: both latencies overlap
+    LongIn pre; int pre_x = -1, pre_c = -1;
+    if (first + warp < hi) {
+        const DevFrame* f0 = a.frames + first + warp;
+        if (f0->kind == 0 && f0->n == FUSED_LONG_N && (f0->exec_mask & 1u)) {
+            long_phase1_load(lane, reinterpret_cast<const float2*>(a.spectrum + (size_t)f0->spec_off), pre); pre_x = first + warp; pre_c = 0;
+        }
+    }
     mbar_wait(s_tabbar, 0);
 
     const float2* s_tw0 = reinterpret_cast<const float2*>(s_tab + FusedTables::TW0);
@@ -151,7 +159,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
     float peak = 0.f;
     // Register-level software pipeline: the spectrum rows of the warp's next long transform are loaded right after
     // the current transform has consumed its inputs, so the load latency hides behind passes 2-3 and the output.
-    LongIn pre; int pre_x = -1, pre_c = -1;
     auto can_prefetch = [&](int kind, int n, uint32_t exec_mask, int cc) { return kind == 0 && n == FUSED_LONG_N && ((exec_mask >> cc) & 1u); };
 
     for (int x = first + warp; x < hi; x += FUSED_WARPS) {
@@ -247,8 +254,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
                         hi_[c]     = -fmaf(wr.x, a2.y, wl.y * b2.x);             // out[1022-i]
                     }
                     if (clip) {
-                        #pragma unroll
-                        for (int e = 0; e < 4; e++) { lo_[e] = clipf(lo_[e], peak); hi_[e] = clipf(hi_[e], peak); }
+                        // Utils.ClipValue (Utils.cs:30-43): clamping is only needed when some sample of the warp's 256 exceeds the
+                        // limit, which is rare: one max reduction + vote instead of three min/max per sample
+                        const float m = fmaxf(fmaxf(fmaxf(fabsf(lo_[0]), fabsf(lo_[1])), fmaxf(fabsf(lo_[2]), fabsf(lo_[3]))),
+                                              fmaxf(fmaxf(fabsf(hi_[0]), fabsf(hi_[1])), fmaxf(fabsf(hi_[2]), fabsf(hi_[3]))));
+                        if (__any_sync(0xffffffffu, m > 0.99999994f)) {
+                            #pragma unroll
+                            for (int e = 0; e < 4; e++) { lo_[e] = clipf(lo_[e], peak); hi_[e] = clipf(hi_[e], peak); }
+                        }
                     }
                     out[lane + 32 * k] = make_float4(lo_[0], lo_[1], lo_[2], lo_[3]);
                     out[511 - lane - 32 * k] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);

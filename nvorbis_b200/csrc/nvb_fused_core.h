@@ -21,8 +21,23 @@ namespace nvb {
 
 struct cpx { float x, y; };
 NVB_HD cpx cmul(cpx a, cpx b) { cpx r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+#if defined(__CUDA_ARCH__)
+// Blackwell packed FP32: one add.rn.f32x2 (SASS FADD2) per complex add -- same IEEE results as two scalar adds, half
+// the issue slots; the butterflies are add-dominated and the kernel is issue-bound.
+__device__ __forceinline__ cpx cadd2_(float ax, float ay, float bx, float by) {
+    unsigned long long ua, ub, ud; cpx r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(ax), "f"(ay));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(bx), "f"(by));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(ud));
+    return r;
+}
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return cadd2_(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return cadd2_(a.x, a.y, -b.x, -b.y); }
+#else
 NVB_HD cpx cadd(cpx a, cpx b) { cpx r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 NVB_HD cpx csub(cpx a, cpx b) { cpx r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+#endif
 NVB_HD cpx cmul_mi(cpx a) { cpx r; r.x = a.y; r.y = -a.x; return r; }          // a * (-i)
 
 // 8-point forward DFT (W8 = exp(-2 pi i / 8)), in place, natural order in and out.

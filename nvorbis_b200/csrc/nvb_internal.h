@@ -98,7 +98,8 @@ struct Counters { int clipped, floor_range, bad_entry, pad; };
 // ---- launchers (nvb_kernels.cu) -----------------------------------------------------------------
 struct LaunchArgs {
     DevSetup S;
-    const DevFrame* frames; int n_frames;      // device array
+    const DevFrame* frames;     // device array of the whole batch plan
+    int frame_lo, n_frames;     // this launch covers plan frames [frame_lo, frame_lo + n_frames)
     const int16_t* posts; const uint8_t* classes; const uint16_t* entries;
     float* spectrum;            // [sum C*n/2]
     float* blocks;              // [sum C*n]   (exact path scratch)

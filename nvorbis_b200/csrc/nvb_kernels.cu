@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
     __shared__ uint32_t s_warp[SPEC_THREADS / 32];
     __shared__ int s_bad[2];
 
-    const DevFrame f = a.frames[blockIdx.x];
+    const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
     if (f.kind != 0) return;
     const DevSetup& S = a.S;
     const int C = S.channels;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
     __shared__ int s_nseg[NVB_MAX_CHANNELS + 1];
     __shared__ int s_bad[2];
 
-    const DevFrame f = a.frames[blockIdx.x];
+    const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
     if (f.kind != 0) return;
     const DevSetup& S = a.S;
     const int C = S.channels;
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
     __shared__ int s_nitems;
     __shared__ int s_bad[2];
 
-    const DevFrame f = a.frames[blockIdx.x];
+    const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
     if (f.kind != 0) return;
     const DevSetup& S = a.S;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(512) k_spectrum_warp(LaunchArgs a) {
     const uint32_t lt = (1u << lane) - 1u;
     const int hl = lane & 15, half = lane >> 4;
     for (int fi = blockIdx.x * nwarps + warp; fi < a.n_frames; fi += gridDim.x * nwarps) {
-        const DevFrame f = a.frames[fi];
+        const DevFrame f = a.frames[a.frame_lo + fi];
         if (f.kind != 0) continue;
         const DevMode md = S.modes[f.mode];
         const DevMapping& mp = S.mappings[md.mapping];
@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(MDCT_THREADS) k_imdct_exact(LaunchArgs a) {
     const DevSetup& S = a.S;
     const int C = S.channels;
     const int fi = blockIdx.x / C, c = blockIdx.x - fi * C;
-    const DevFrame f = a.frames[fi];
+    const DevFrame f = a.frames[a.frame_lo + fi];
     if (f.kind != 0) return;
     const int t = threadIdx.x, nt = MDCT_THREADS;
     const int N = f.n, n2 = N >> 1;
@@ -901,7 +901,7 @@ __global__ void __launch_bounds__(MDCT_THREADS) k_imdct_exact(LaunchArgs a) {
 __global__ void __launch_bounds__(OLA_THREADS) k_ola(LaunchArgs a) {
     const DevSetup& S = a.S;
     const int C = S.channels;
-    const DevFrame f = a.frames[blockIdx.x];
+    const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
     const int len = f.out_end - f.out_begin;
     if (len <= 0) return;
     const float* cur; int cstride;

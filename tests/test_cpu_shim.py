@@ -197,3 +197,6 @@ def test_slot_ring_wraps_with_mixed_windows(shim):
             ) % (H.ROOT, os.path.join(H.ROOT, "tests"), os.path.join(H.GOLDEN, "3test.boundary.npz"), shim)
     env = dict(os.environ, NVB_SHIM_SMS="1")
     assert subprocess.check_output([sys.executable, "-c", code], env=env, timeout=600).decode().strip().endswith("ok")
+    # the same batch through nvb_decode_batch's chunked copy/compute pipeline (four frame ranges, halo across chunk edges)
+    env = dict(os.environ, NVB_SHIM_SMS="2", NVB_CHUNK_MIN="16")
+    assert subprocess.check_output([sys.executable, "-c", code], env=env, timeout=600).decode().strip().endswith("ok")
