@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
 
     const int lo = a.frame_lo + blockIdx.x * p.frames_per_cta;              // plan indices; this launch covers [frame_lo, frame_lo + n_frames)
     int hi = lo + p.frames_per_cta; if (hi > a.frame_lo + a.n_frames) hi = a.frame_lo + a.n_frames;
+    nvb_grid_dep_launch();                                                  // the next kernel of the stream may start scheduling its blocks
     if (lo >= hi) return;
 
     if (tid == 0) {
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
         bulk_g2s(s_tab, S.fused_tab, FusedTables::FLOATS * sizeof(float), s_tabbar);
     }
 
+    nvb_grid_dep_wait();                                                    // everything below reads what earlier work of the stream wrote
     int first = lo;
     {
         const DevFrame f0 = a.frames[lo];

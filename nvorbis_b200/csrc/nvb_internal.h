@@ -14,8 +14,28 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 // Kernel launch / dynamic shared memory spelled as macros so that tests/cpu_shim (test-only) can
 // compile the same kernel sources against its thread-per-lane emulation.
 #if !defined(NVB_CPU_SHIM)
-#define NVB_LAUNCH(kernel, grid, block, smem, stream, arg) kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(arg)
+// Every kernel is launched with programmatic stream serialization (PDL): its blocks may be scheduled, and run their
+// prologue (shared-memory setup, table staging), while the previous kernel of the stream drains; nvb_grid_dep_wait()
+// then blocks until that kernel has completed and its writes are visible, so stream order is preserved for all data.
+#define NVB_LAUNCH(kernel, grid, block, smem, stream, arg)                                                   \
+    do {                                                                                                    \
+        cudaLaunchConfig_t cfg__ = {};                                                                      \
+        cfg__.gridDim = dim3((unsigned)(grid)); cfg__.blockDim = dim3((unsigned)(block));                   \
+        cfg__.dynamicSmemBytes = (size_t)(smem); cfg__.stream = (cudaStream_t)(stream);                     \
+        cudaLaunchAttribute attr__[1];                                                                      \
+        attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                  \
+        attr__[0].val.programmaticStreamSerializationAllowed = 1;                                           \
+        cfg__.attrs = attr__; cfg__.numAttrs = 1;                                                           \
+        cudaLaunchKernelEx(&cfg__, kernel, arg);                                                            \
+    } while (0)
 #define NVB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#if defined(__CUDA_ARCH__)
+#define nvb_grid_dep_wait() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define nvb_grid_dep_launch() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#else
+#define nvb_grid_dep_wait() ((void)0)
+#define nvb_grid_dep_launch() ((void)0)
+#endif
 #endif
 
 namespace nvb {

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
     __shared__ uint32_t s_warp[SPEC_THREADS / 32];
     __shared__ int s_bad[2];
 
+    nvb_grid_dep_launch();
+    nvb_grid_dep_wait();
     const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
     if (f.kind != 0) return;
     const DevSetup& S = a.S;
@@ -237,6 +239,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
     __shared__ int s_nseg[NVB_MAX_CHANNELS + 1];
     __shared__ int s_bad[2];
 
+    nvb_grid_dep_launch();
+    nvb_grid_dep_wait();
     const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
     if (f.kind != 0) return;
     const DevSetup& S = a.S;
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1+K2+K3, plane path (DevSetup.spectrum_fast == 2): residues that code ONE interleaved stream -- type 2, or a
+// K1+K2+K3, plane path (the default when DevSetup.spectrum_fast == 2): residues that code ONE interleaved stream -- type 2, or a
 // single channel of type 1 -- with power-of-two partition and book sizes.  The VQ vectors are copied whole:
 //   phase A  as in k_spectrum_fast (floor unwrap per channel warp); the last warp compacts the coded
 //            (stage, partition) items and the start of each item's entries into a list;
@@ -470,6 +474,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
     __shared__ int s_nitems;
     __shared__ int s_bad[2];
 
+    nvb_grid_dep_launch();
+    nvb_grid_dep_wait();
     const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
     if (f.kind != 0) return;
     const DevSetup& S = a.S;
@@ -647,7 +653,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1+K2+K3, warp path (the default when DevSetup.spectrum_fast == 2): the same arithmetic as k_spectrum_planes with
+// K1+K2+K3, warp path (NVB_SPECTRUM_WARP=1; see launch_spectrum for why it is not the default): the same arithmetic as k_spectrum_planes with
 // ONE WARP PER FRAME in a persistent grid -- no block-wide barrier, every warp runs its own frame start to end
 // while the other warps of the SM hide its latencies:
 //   floor unwrap + segment list per channel (lane = post), (stage, partition) item compaction (warp scan),
@@ -692,6 +698,7 @@ __global__ void __launch_bounds__(512) k_spectrum_warp(LaunchArgs a) {
     uint8_t* s_cls = wbase + L.cls;
     int* s_nseg = reinterpret_cast<int*>(wbase + L.misc);                   // [CT]
 
+    nvb_grid_dep_launch();
     for (int i = t; i < 256; i += blockDim.x) s_db[i] = S.db[i];
     for (int r = 0; r < S.n_residues; r++) {
         const DevResidue& R = S.residues[r];
@@ -705,6 +712,7 @@ __global__ void __launch_bounds__(512) k_spectrum_warp(LaunchArgs a) {
         }
     }
     __syncthreads();
+    nvb_grid_dep_wait();
 
     const uint32_t lt = (1u << lane) - 1u;
     const int hl = lane & 15, half = lane >> 4;
@@ -866,6 +874,8 @@ __global__ void __launch_bounds__(MDCT_THREADS) k_imdct_exact(LaunchArgs a) {
     const DevSetup& S = a.S;
     const int C = S.channels;
     const int fi = blockIdx.x / C, c = blockIdx.x - fi * C;
+    nvb_grid_dep_launch();
+    nvb_grid_dep_wait();
     const DevFrame f = a.frames[a.frame_lo + fi];
     if (f.kind != 0) return;
     const int t = threadIdx.x, nt = MDCT_THREADS;
@@ -901,6 +911,8 @@ __global__ void __launch_bounds__(MDCT_THREADS) k_imdct_exact(LaunchArgs a) {
 __global__ void __launch_bounds__(OLA_THREADS) k_ola(LaunchArgs a) {
     const DevSetup& S = a.S;
     const int C = S.channels;
+    nvb_grid_dep_launch();
+    nvb_grid_dep_wait();
     const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
     const int len = f.out_end - f.out_begin;
     if (len <= 0) return;
@@ -939,8 +951,11 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
     static const bool force_generic = std::getenv("NVB_SPECTRUM_GENERIC") != nullptr;      // test hook: exercise the general kernel
     if (!a.S.spectrum_fast || force_generic) return launch_spectrum_generic(a, stream);
     static const bool no_planes = std::getenv("NVB_SPECTRUM_NO_PLANES") != nullptr;           // test hook: exercise k_spectrum_fast
-    static const bool no_warp = std::getenv("NVB_SPECTRUM_NO_WARP") != nullptr;               // test hook: exercise k_spectrum_planes
-    if (a.S.spectrum_fast >= 2 && !no_planes && !no_warp) {
+    // k_spectrum_warp (one warp per frame, no block barrier) is kept as an option: on B200 it measured slower than
+    // k_spectrum_planes (94.8 vs 80.7 us for 4096 stereo frames, profiles/r01_i): 14 warps per SM cannot hide its
+    // dependent entry -> VQ-vector loads
+    static const bool use_warp = std::getenv("NVB_SPECTRUM_WARP") != nullptr;
+    if (a.S.spectrum_fast >= 2 && !no_planes && use_warp) {
         const int C = a.S.channels;
         const WarpSmem L = spectrum_warp_layout(C, a.S.bs[1], a.S.max_items);
         const size_t shared_part = 1024 + (((size_t)a.S.ci_total * sizeof(int4) + 15) & ~size_t(15));

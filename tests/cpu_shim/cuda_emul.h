@@ -186,3 +186,5 @@ template <class K, class A> void launch(K kernel, int grid, int block, size_t sm
 }
 #define NVB_LAUNCH(kernel, grid, block, smem, stream, arg) cuemu::launch(kernel, (int)(grid), (int)(block), (size_t)(smem), arg)
 #define NVB_DYN_SMEM(name) unsigned char* name = cuemu::g_dyn_smem
+#define nvb_grid_dep_wait() ((void)0)
+#define nvb_grid_dep_launch() ((void)0)

@@ -135,3 +135,33 @@ def mux_ogg(pk, serial: int = 1, page_payload: int = 4000) -> bytes:
             flush()
     flush()
     return b"".join(pages)
+
+
+def oracle_records(hb: capi.HostBatch, desc: dict):
+    """HostBatch (C-ABI layout) -> the oracle's SynthFrame arrays, for any setup description."""
+    n, C = len(hb.frames), desc["channels"]
+    fr = np.zeros(n, O.SYNTH_FRAME_DTYPE)
+    f = hb.frames
+    stride = hb.posts.size // max(n * C, 1)
+    fr["ok"] = f["status"] == 0; fr["mode"] = f["mode"]; fr["windowIndex"] = f["window"]
+    fr["start"] = f["start"]; fr["valid"] = f["valid"]; fr["total"] = f["total"]; fr["execMask"] = f["exec_mask"]
+    fr["resDecoded"] = f["res_decoded"]
+    for i in range(n):
+        m = desc["modes"][int(f["mode"][i])]
+        rs = desc["residues"][desc["mappings"][m["mapping"]]["residue"]]
+        N = desc["block_size"][1 if m["block_flag"] else 0]
+        span = N * C // 2 if rs["type"] == 2 else N // 2
+        fr["resStreams"][i] = 1 if rs["type"] == 2 else C
+        fr["resPartitions"][i] = max(min(rs["end"], span) - rs["begin"], 0) // rs["partition_size"]
+    fr["postsOff"] = np.arange(n, dtype=np.int64) * C * 64; fr["postCountOff"] = np.arange(n, dtype=np.int64) * C
+    fr["classesOff"] = f["classes_off"]; fr["entriesOff"] = f["entries_off"]; fr["entryCount"] = f["entry_count"]
+    p = hb.posts.reshape(n, C, stride)
+    posts = np.zeros((n, C, 64), np.int32)
+    posts[:, :, :stride - 1] = p[:, :, 1:]
+    return fr, posts.reshape(-1), p[:, :, 0].astype(np.int32).reshape(-1), hb.classes, hb.entries.astype(np.int32)
+
+
+def oracle_decode_records(reader: O.OracleReader, hb: capi.HostBatch, desc: dict, threads: int = 1):
+    fr, posts, pc, cls, ent = oracle_records(hb, desc)
+    cap = int(hb.frames["total"].astype(np.int64).sum()) + 8192
+    return reader.synth_batch(fr, posts, pc, cls, ent, cap, threads=threads)
