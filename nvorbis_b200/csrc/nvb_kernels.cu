@@ -469,7 +469,6 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
     __shared__ int s_fy[CT][NVB_MAX_POSTS];
     __shared__ SegRec s_seg[CT * (NVB_MAX_POSTS + 1)];
     __shared__ int s_nseg[CT + 1];
-    __shared__ int4 s_ci[NVB_MAX_CLASSES * NVB_MAX_STAGES];               // per (class, stage): vq offset, dims, entries, entries per partition
     __shared__ int s_casc[NVB_MAX_CLASSES];
     __shared__ int s_nitems;
     __shared__ int s_bad[2];
@@ -489,7 +488,9 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
     float* s_fl = reinterpret_cast<float*>(dyn_smem);                       // [n][CT] floor multipliers
     float* s_pl = s_fl + max_span;                                          // [stages][n][CT] residue planes
     ItemRec* s_items = reinterpret_cast<ItemRec*>(s_pl + (size_t)S.max_stages * max_span);
-    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_items + S.max_items);
+    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_items) + (((size_t)S.max_items * sizeof(ItemRec) + 15) & ~size_t(15));
+    int4* s_ci = reinterpret_cast<int4*>(s_cls + ((S.max_items + 15) & ~15));   // per (class, stage): vq offset, dims, entries, entries per partition (16-byte aligned)
+    const int st_n = R.stages > 0 ? R.stages : 1;
     const uint8_t* cls = a.classes + f.classes_off;
     const uint16_t* ent = a.entries + f.entries_off;
 
@@ -498,9 +499,9 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
     const int P = g.P;
     if (t < 2) s_bad[t] = 0;
     s_db[t & 255] = S.db[t & 255];
-    for (int i = t; i < R.nclass * NVB_MAX_STAGES; i += SPEC_THREADS) {
-        const int cl = i >> 3, st = i & 7;
-        const int book = R.books[cl][st];
+    for (int i = t; i < R.nclass * st_n; i += SPEC_THREADS) {
+        const int cl = i / st_n, st = i - cl * st_n;
+        const int book = st < R.stages ? R.books[cl][st] : -1;
         int4 ci = make_int4(0, 1, 0, 0);
         if (book >= 0) { const DevBook b = S.books[book]; ci = make_int4((int)b.off, b.dims, b.entries, R.cnt[cl][st]); }
         s_ci[i] = ci;
@@ -559,24 +560,27 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
     {
         const int nitems = s_nitems;
         const int hl = lane & 15;
+        auto move_entry = [&](const ItemRec& r, const int4& ci, int e) {
+            const int dims = ci.y;
+            const uint32_t ei = r.base + (uint32_t)e;
+            const float* src = nullptr;
+            if (ei < f.entry_count) {                                       // else never decoded: contributes nothing (Residue0.cs:164-170)
+                const int en = ent[ei];
+                if (en < ci.z) src = S.vq + ci.x + (size_t)en * dims; else bad_entry = 1;
+            }
+            float* d = s_pl + (size_t)r.s * max_span + R.begin + (int)r.p * R.psize + e * dims;
+            if (dims == 2) *reinterpret_cast<float2*>(d) = src ? *reinterpret_cast<const float2*>(src) : make_float2(0.f, 0.f);
+            else if (dims == 1) *d = src ? *src : 0.f;
+            else for (int k = 0; k < dims; k += 4) *reinterpret_cast<float4*>(d + k) = src ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        // items are independent (distinct plane positions): four in flight per half-warp so that the dependent
+        // entry -> VQ-vector loads of different items overlap
+        #pragma unroll 4
         for (int idx = warp * 2 + (lane >> 4); idx < nitems; idx += NW * 2) {
             const ItemRec r = s_items[idx];
-            const int4 ci = s_ci[r.cl * NVB_MAX_STAGES + r.s];
-            const int dims = ci.y;
-            float* dst = s_pl + (size_t)r.s * max_span + R.begin + (int)r.p * R.psize;
-            const float* tab = S.vq + ci.x;
-            for (int e = hl; e < ci.w; e += 16) {
-                const uint32_t ei = r.base + (uint32_t)e;
-                const float* src = nullptr;
-                if (ei < f.entry_count) {                                   // else never decoded: contributes nothing (Residue0.cs:164-170)
-                    const int en = ent[ei];
-                    if (en < ci.z) src = tab + (size_t)en * dims; else bad_entry = 1;
-                }
-                float* d = dst + e * dims;
-                if (dims == 2) *reinterpret_cast<float2*>(d) = src ? *reinterpret_cast<const float2*>(src) : make_float2(0.f, 0.f);
-                else if (dims == 1) *d = src ? *src : 0.f;
-                else for (int k = 0; k < dims; k += 4) *reinterpret_cast<float4*>(d + k) = src ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            const int4 ci = s_ci[r.cl * st_n + r.s];
+            if (hl < ci.w) move_entry(r, ci, hl);
+            for (int e = hl + 16; e < ci.w; e += 16) move_entry(r, ci, e);   // more than 16 entries per partition: rare
         }
     }
     __syncthreads();
@@ -600,7 +604,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
                 unsigned casc = (unsigned)s_casc[cl];
                 while (casc) {
                     const int st = __ffs(casc) - 1; casc &= casc - 1;
-                    if (st >= R.stages || s_ci[cl * NVB_MAX_STAGES + st].w == 0) continue;
+                    if (st >= R.stages || s_ci[cl * st_n + st].w == 0) continue;
                     const float* pl = s_pl + (size_t)st * max_span + pos;
                     #pragma unroll
                     for (int k = 0; k < G; k += 4) {
@@ -968,7 +972,8 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
                 if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
             }
             const size_t smem = shared_part + (size_t)nw * L.total;
-            static size_t configured_w = 0;
+            static size_t configured_w_by_c[NVB_MAX_CHANNELS + 1] = {0};    // per template instantiation
+            size_t& configured_w = configured_w_by_c[C];
             if (smem > configured_w) {
                 cudaError_t e = C == 1 ? cudaFuncSetAttribute(k_spectrum_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                               : C == 2 ? cudaFuncSetAttribute(k_spectrum_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -990,8 +995,10 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         const int C = a.S.channels;
         // planes for the deepest residue + floor rows + item list + class bytes (host-checked to fit)
         const size_t span = (size_t)C * (a.S.bs[1] / 2) * sizeof(float);
-        const size_t smem = span * (size_t)(a.S.max_stages + 1) + (size_t)a.S.max_items * sizeof(ItemRec) + (((size_t)a.S.max_items + 15) & ~size_t(15)) + 16;
-        static size_t configured_pl = 0;
+        const size_t smem = span * (size_t)(a.S.max_stages + 1) + (((size_t)a.S.max_items * sizeof(ItemRec) + 15) & ~size_t(15)) +
+                            (((size_t)a.S.max_items + 15) & ~size_t(15)) + (size_t)a.S.ci_total * sizeof(int4) + 16;
+        static size_t configured_pl_by_c[NVB_MAX_CHANNELS + 1] = {0};       // per template instantiation
+        size_t& configured_pl = configured_pl_by_c[C];
         if (smem > configured_pl) {
             cudaError_t e = C == 1 ? cudaFuncSetAttribute(k_spectrum_planes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                           : C == 2 ? cudaFuncSetAttribute(k_spectrum_planes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
