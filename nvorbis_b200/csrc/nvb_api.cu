@@ -115,7 +115,7 @@ int install_blob(nvb_ctx* ctx, std::vector<unsigned char>&& blob) {
 }
 
 // Uploads a batch into `b` (buffers grow as needed) and plans it.
-int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags, cudaStream_t st) {
+int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags, cudaStream_t st, bool* defer_inputs = nullptr) {
     std::string err;
     int rc = plan_batch(ctx->host_blob.data(), batch, flags, ctx->carry, b->plan, err);
     if (rc != NVB_OK) return set_err(ctx, rc, err);
@@ -131,6 +131,11 @@ int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags,
     if (!b->fused && (rc = grow(ctx, b->d_blocks, b->cap_blocks, 2 * (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
     if (!b->d_counters) { size_t cap = 0; if ((rc = grow(ctx, b->d_counters, cap, 1)) != NVB_OK) return rc; }
     if (nf) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_frames, b->plan.frames.data(), nf * sizeof(DevFrame), cudaMemcpyHostToDevice, st));
+    if (defer_inputs) {
+        // nvb_decode_batch uploads posts / classes / entries chunk by chunk when the batch is laid out sequentially
+        *defer_inputs = *defer_inputs && b->fused && b->plan.sequential;
+        if (*defer_inputs) return NVB_OK;
+    }
     if (n_posts) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts, batch->posts, n_posts * sizeof(int16_t), cudaMemcpyHostToDevice, st));
     if (batch->n_classes) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_classes, batch->classes, (size_t)batch->n_classes, cudaMemcpyHostToDevice, st));
     if (batch->n_entries) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_entries, batch->entries, (size_t)batch->n_entries * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
@@ -328,14 +333,22 @@ int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm
     DeviceGuard g(ctx->device);
     if (!ctx->staging) { ctx->staging = new (std::nothrow) nvb_dbatch(); if (!ctx->staging) return set_err(ctx, NVB_ERR_NOMEM, "host allocation failed"); }
     nvb_dbatch* b = ctx->staging;
-    int rc = upload_batch(ctx, b, batch, flags, ctx->stream);
+    static const int chunk_min = std::getenv("NVB_CHUNK_MIN") ? std::atoi(std::getenv("NVB_CHUNK_MIN")) : 1024;   // test hook
+    bool chunked_inputs = batch && batch->n_frames >= chunk_min && batch->n_frames >= 8;
+    int rc = upload_batch(ctx, b, batch, flags, ctx->stream, &chunked_inputs);
     if (rc != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
     const size_t n_out = (size_t)b->plan.samples * ctx->H.channels;
     if (n_out > pcm_cap || (n_out > 0 && !pcm_out)) { cudaStreamSynchronize(ctx->stream); return set_err(ctx, NVB_ERR_CAPACITY, "pcm_out too small for the batch"); }
     if ((rc = grow(ctx, ctx->d_pcm, ctx->pcm_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
     const int nf = (int)b->plan.frames.size();
-    static const int chunk_min = std::getenv("NVB_CHUNK_MIN") ? std::atoi(std::getenv("NVB_CHUNK_MIN")) : 1024;   // test hook
     const int n_chunks = (b->fused && nf >= chunk_min && nf >= 8) ? 4 : 1;
+    if (n_chunks == 1 && chunked_inputs) {                                  // few decoded frames after all: upload everything now
+        const size_t n_posts = (size_t)batch->n_frames * ctx->H.channels * ctx->H.post_stride;
+        if (n_posts) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts, batch->posts, n_posts * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (batch->n_classes) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_classes, batch->classes, (size_t)batch->n_classes, cudaMemcpyHostToDevice, ctx->stream));
+        if (batch->n_entries) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_entries, batch->entries, (size_t)batch->n_entries * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        chunked_inputs = false;
+    }
     if (n_chunks == 1) {
         rc = enqueue(ctx, b, 0, nullptr, ctx->d_pcm, true, ctx->stream);
         if (rc != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
@@ -352,6 +365,24 @@ int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm
             cudaStream_t st = ctx->chunk_stream[k & 1];
             const int lo = (int)((long long)nf * k / n_chunks), hi = (int)((long long)nf * (k + 1) / n_chunks);
             NVB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_inputs, 0));
+            if (chunked_inputs) {
+                // this chunk's share of the inputs: the api frames from the chunk's first decoded block up to the next chunk's
+                const int a0 = k == 0 ? 0 : b->plan.frames[(size_t)lo].api_index;
+                const int a1 = k + 1 == n_chunks ? batch->n_frames : b->plan.frames[(size_t)hi].api_index;
+                auto first_off = [&](int from, int64_t& c_off, int64_t& e_off) {
+                    c_off = batch->n_classes; e_off = batch->n_entries;
+                    for (int i = from; i < batch->n_frames; i++)
+                        if (batch->frames[i].status == NVB_FRAME_OK && batch->frames[i].res_decoded) { c_off = batch->frames[i].classes_off; e_off = batch->frames[i].entries_off; break; }
+                };
+                int64_t c0, e0, c1, e1;
+                first_off(a0, c0, e0);
+                if (k + 1 == n_chunks) { c1 = batch->n_classes; e1 = batch->n_entries; } else first_off(a1, c1, e1);
+                if (k == 0) { c0 = 0; e0 = 0; }
+                const size_t row = (size_t)ctx->H.channels * ctx->H.post_stride;
+                if (a1 > a0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts + (size_t)a0 * row, batch->posts + (size_t)a0 * row, (size_t)(a1 - a0) * row * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+                if (c1 > c0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_classes + c0, batch->classes + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+                if (e1 > e0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_entries + e0, batch->entries + e0, (size_t)(e1 - e0) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+            }
             rc = enqueue(ctx, b, 0, nullptr, ctx->d_pcm, true, st, lo, hi - lo, false, ctx->ev_spec[k & 1], k > 0 ? ctx->ev_spec[(k - 1) & 1] : nullptr);
             if (rc != NVB_OK) { cudaDeviceSynchronize(); return rc; }
             const size_t s0 = (size_t)b->plan.frames[(size_t)lo].pcm_off * C;

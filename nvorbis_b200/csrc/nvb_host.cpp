@@ -474,6 +474,7 @@ int plan_batch(const unsigned char* host_blob, const nvb_batch* b, int flags, co
     CarryState st = (flags & NVB_RUN_CONTINUE) ? in : CarryState();
     int last_ok = -1;
     int64_t pcm = 0, spec = 0;
+    int64_t end_c = 0, end_e = 0;
 
     for (int i = 0; i < b->n_frames; i++) {
         const nvb_frame& f = b->frames[i];
@@ -506,6 +507,8 @@ int plan_batch(const unsigned char* host_blob, const nvb_batch* b, int flags, co
             const ResGeom g = residue_geom(S.residues[mp.residue], n, C);
             if ((int64_t)f.classes_off + (int64_t)g.P * g.Sx > b->n_classes) return fail(err, NVB_ERR_DATA, "frame %lld: classes outside the batch", i);
             if ((int64_t)f.entries_off + (int64_t)f.entry_count > b->n_entries) return fail(err, NVB_ERR_DATA, "frame %lld: entries outside the batch", i);
+            if ((int64_t)f.classes_off < end_c || (int64_t)f.entries_off < end_e) out.sequential = false;
+            end_c = (int64_t)f.classes_off + (int64_t)g.P * g.Sx; end_e = (int64_t)f.entries_off + (int64_t)f.entry_count;
         }
         const Overlap nom = nominal_overlap(h, md.block_flag, f.window);
 

@@ -16,6 +16,22 @@
 
 namespace nvb {
 
+#if !defined(NVB_CPU_SHIM)
+// Monotonic event counters in shared memory: signal = release-add by one lane (after __syncwarp), wait = acquire-poll.
+__device__ __forceinline__ void cnt_signal(int* c) {
+    asm volatile("red.release.cta.shared::cta.add.s32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(c)) : "memory");
+}
+__device__ __forceinline__ void cnt_wait(const int* c, int need) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(c);
+    int v;
+    for (;;) {
+        asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        if (v >= need) break;
+        __nanosleep(32);
+    }
+}
+#endif
+
 constexpr int SPEC_THREADS = 256;
 constexpr int MDCT_THREADS = 256;
 constexpr int OLA_THREADS = 256;
@@ -472,6 +488,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
     __shared__ int s_casc[NVB_MAX_CLASSES];
     __shared__ int s_nitems;
     __shared__ int s_bad[2];
+    __shared__ int s_ready[2];                                              // [0]: item list complete, [1]: channels whose floor segments are complete
 
     nvb_grid_dep_launch();
     nvb_grid_dep_wait();
@@ -497,7 +514,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
     ResGeom g; g.P = 0; g.Sx = 1; g.n_items = 0;
     if (f.res_decoded) g = residue_geom(R, N, CT);
     const int P = g.P;
-    if (t < 2) s_bad[t] = 0;
+    if (t < 2) { s_bad[t] = 0; s_ready[t] = 0; }
     s_db[t & 255] = S.db[t & 255];
     for (int i = t; i < R.nclass * st_n; i += SPEC_THREADS) {
         const int cl = i / st_n, st = i - cl * st_n;
@@ -509,7 +526,11 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
     }
     for (int p = t; p < P; p += SPEC_THREADS) { const int cl = cls[p]; s_cls[p] = cl < R.nclass ? (uint8_t)cl : (uint8_t)255; }
 
-    // ---- phase A
+    __syncthreads();                                                        // tables staged, flags cleared
+
+    // ---- phase A: the item list (last warp) and the floor segments (one warp per channel) are produced concurrently; the
+    // other warps start on the residue as soon as the item list is there and render floor rows once the segments are
+    // (release/acquire counters instead of a block barrier, so nobody waits for the slowest producer)
     if (warp == NW - 1) {
         uint32_t run = 0; int nitems = 0;
         const uint32_t lt = (1u << lane) - 1u;
@@ -528,16 +549,45 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
             }
         }
         if (lane == 0) s_nitems = nitems;
+        __syncwarp();
+        if (lane == 0) cnt_signal(&s_ready[0]);
     }
     for (int c = warp; c < CT; c += NW) {
         if ((f.exec_mask >> c) & 1u)
             floor1_segments_warp(F, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, n, lane, s_fy[c], s_seg + c * (NVB_MAX_POSTS + 1), &s_nseg[c]);
         else if (lane == 0) s_nseg[c] = 0;
+        __syncwarp();
+        if (lane == 0) cnt_signal(&s_ready[1]);
     }
-    __syncthreads();
-
-    // ---- phase B: floor curve rows, channel-interleaved
     int bad_floor = 0, bad_entry = 0;
+    // ---- phase G: VQ vectors into the stage planes; half a warp per item, lane = entry
+    {
+        cnt_wait(&s_ready[0], 1);
+        const int nitems = s_nitems;
+        const int hl = lane & 15;
+        auto move_entry = [&](const ItemRec& r, const int4& ci, int e) {
+            const int dims = ci.y;
+            const uint32_t ei = r.base + (uint32_t)e;
+            const float* src = nullptr;
+            if (ei < f.entry_count) {                                       // else never decoded: contributes nothing (Residue0.cs:164-170)
+                const int en = ent[ei];
+                if (en < ci.z) src = S.vq + ci.x + (size_t)en * dims; else bad_entry = 1;
+            }
+            float* d = s_pl + (size_t)r.s * max_span + R.begin + (int)r.p * R.psize + e * dims;
+            if (dims == 2) *reinterpret_cast<float2*>(d) = src ? *reinterpret_cast<const float2*>(src) : make_float2(0.f, 0.f);
+            else if (dims == 1) *d = src ? *src : 0.f;
+            else for (int k = 0; k < dims; k += 4) *reinterpret_cast<float4*>(d + k) = src ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        #pragma unroll 1
+        for (int idx = warp * 2 + (lane >> 4); idx < nitems; idx += NW * 2) {
+            const ItemRec r = s_items[idx];
+            const int4 ci = s_ci[r.cl * st_n + r.s];
+            if (hl < ci.w) move_entry(r, ci, hl);
+            for (int e = hl + 16; e < ci.w; e += 16) move_entry(r, ci, e);   // more than 16 entries per partition: rare
+        }
+    }
+    // ---- phase B: floor curve rows, channel-interleaved
+    cnt_wait(&s_ready[1], CT);
     {
         int c = 0, first_u = 0, ns = s_nseg[0];
         int total = 0;
@@ -554,33 +604,6 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
                 if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
                 row[k * CT] = s_db[y];
             }
-        }
-    }
-    // ---- phase G: VQ vectors into the stage planes; half a warp per item, lane = entry
-    {
-        const int nitems = s_nitems;
-        const int hl = lane & 15;
-        auto move_entry = [&](const ItemRec& r, const int4& ci, int e) {
-            const int dims = ci.y;
-            const uint32_t ei = r.base + (uint32_t)e;
-            const float* src = nullptr;
-            if (ei < f.entry_count) {                                       // else never decoded: contributes nothing (Residue0.cs:164-170)
-                const int en = ent[ei];
-                if (en < ci.z) src = S.vq + ci.x + (size_t)en * dims; else bad_entry = 1;
-            }
-            float* d = s_pl + (size_t)r.s * max_span + R.begin + (int)r.p * R.psize + e * dims;
-            if (dims == 2) *reinterpret_cast<float2*>(d) = src ? *reinterpret_cast<const float2*>(src) : make_float2(0.f, 0.f);
-            else if (dims == 1) *d = src ? *src : 0.f;
-            else for (int k = 0; k < dims; k += 4) *reinterpret_cast<float4*>(d + k) = src ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        // items are independent (distinct plane positions): four in flight per half-warp so that the dependent
-        // entry -> VQ-vector loads of different items overlap
-        #pragma unroll 4
-        for (int idx = warp * 2 + (lane >> 4); idx < nitems; idx += NW * 2) {
-            const ItemRec r = s_items[idx];
-            const int4 ci = s_ci[r.cl * st_n + r.s];
-            if (hl < ci.w) move_entry(r, ci, hl);
-            for (int e = hl + 16; e < ci.w; e += 16) move_entry(r, ci, e);   // more than 16 entries per partition: rare
         }
     }
     __syncthreads();
