@@ -173,6 +173,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"                 # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     desc, z = setupio.load(POOL)

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
     const float2* s_tw0 = reinterpret_cast<const float2*>(s_tab + FusedTables::TW0);
     const float2* s_w64 = reinterpret_cast<const float2*>(s_tab + FusedTables::W64);
     const float* s_win = s_tab + FusedTables::WIN;
+    LaneTw ltw; lane_tw_load(lane, s_tab, ltw);
     // swizzled float offsets of this lane's sample pair inside a run of 64 (forward / mirrored), see the fast path
     const int L2 = 2 * lane;
     const int A0 = L2 ^ ((lane >> 4) << 2), A8 = A0 ^ 8;
@@ -195,11 +196,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
                     __syncwarp();
                     long_phase2_load(lane, ex, R);
                     __syncwarp();
-                    long_phase2_store(lane, s_tab, ex, R);
+                    long_phase2_store(lane, ltw, ex, R);
                     __syncwarp();
                     long_phase3_load(lane, ex, R);
                     __syncwarp();
-                    long_phase3_store(lane, s_tab, ex, R);
+                    long_phase3_store(lane, ltw, ex, R);
                 } else {
                     ShortRegs R;
                     short_phase1(lane, spec, s_tw0, s_w64, R);

@@ -142,24 +142,29 @@ NVB_HD void long_phase2_load(int l, const float2* ex, LongRegs& R) {
         R.a[k1].x = va.x; R.a[k1].y = va.y; R.b[k1].x = vb.x; R.b[k1].y = vb.y;
     }
 }
-NVB_HD void long_phase2_store(int l, const float* tab, float2* ex, LongRegs& R) {
-    const int m2 = l >> 3, k0 = l & 7;
+// The pass-2 twiddles W64^(k0 m1) and the post-twiddle pair of a lane never change: they live in registers.
+struct LaneTw { cpx t3[7]; cpx t4a, t4b; };
+NVB_HD void lane_tw_load(int l, const float* tab, LaneTw& w) {
     const float4* T3 = reinterpret_cast<const float4*>(tab + FusedTables::T3);
+    #pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float4 v = T3[j * 32 + l];
+        w.t3[2 * j] = ld_cpx(v, 0);
+        if (2 * j + 1 < 7) w.t3[2 * j + 1] = ld_cpx(v, 1);
+    }
+    const float4 v = reinterpret_cast<const float4*>(tab + FusedTables::T4)[l];
+    w.t4a = ld_cpx(v, 0); w.t4b = ld_cpx(v, 1);
+}
+NVB_HD void long_phase2_store(int l, const LaneTw& w, float2* ex, LongRegs& R) {
+    const int m2 = l >> 3, k0 = l & 7;
     fft8(R.a); fft8(R.b);
     ex[m2 * 72 + k0] = make_float2(R.a[0].x, R.a[0].y);
     ex[(m2 + 4) * 72 + k0] = make_float2(R.b[0].x, R.b[0].y);
     #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const float4 w = T3[j * 32 + l];
-        #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int m1 = 2 * j + 1 + h;
-            if (m1 > 7) break;
-            const cpx t = ld_cpx(w, h);
-            const cpx va = cmul(R.a[m1], t), vb = cmul(R.b[m1], t);
-            ex[m2 * 72 + m1 * 9 + k0] = make_float2(va.x, va.y);
-            ex[(m2 + 4) * 72 + m1 * 9 + k0] = make_float2(vb.x, vb.y);
-        }
+    for (int m1 = 1; m1 < 8; m1++) {
+        const cpx va = cmul(R.a[m1], w.t3[m1 - 1]), vb = cmul(R.b[m1], w.t3[m1 - 1]);
+        ex[m2 * 72 + m1 * 9 + k0] = make_float2(va.x, va.y);
+        ex[(m2 + 4) * 72 + m1 * 9 + k0] = make_float2(vb.x, vb.y);
     }
 }
 
@@ -173,11 +178,10 @@ NVB_HD void long_phase3_load(int l, const float2* ex, LongRegs& R) {
         R.a[k0].x = va.x; R.a[k0].y = va.y; R.b[k0].x = vb.x; R.b[k0].y = vb.y;
     }
 }
-NVB_HD void long_phase3_store(int l, const float* tab, float2* u2, LongRegs& R) {
-    const float4 w = reinterpret_cast<const float4*>(tab + FusedTables::T4)[l];
+NVB_HD void long_phase3_store(int l, const LaneTw& w, float2* u2, LongRegs& R) {
     fft8(R.a); fft8(R.b);
     cmul_e_all(R.a); cmul_e_all(R.b);
-    const cpx wa = ld_cpx(w, 0), wb = ld_cpx(w, 1);
+    const cpx wa = w.t4a, wb = w.t4b;
     #pragma unroll
     for (int m0 = 0; m0 < 8; m0++) { R.a[m0] = cmul(R.a[m0], wa); R.b[m0] = cmul(R.b[m0], wb); }
     // n = na0 + 64 m0 and its partner 511 - n = nb0 + 64 (7 - m0), nb0 = 63 - na0; the swizzle only looks at
