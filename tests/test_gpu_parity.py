@@ -169,6 +169,21 @@ def test_config3_mixed_windows_full_size():
     np.testing.assert_array_equal(out_e, want)
 
 
+def test_large_chained_batches_through_the_chunked_pipeline():
+    """Two chained 6000-frame calls (each runs nvb_decode_batch's four-chunk copy/compute pipeline) equal one decode."""
+    from nvorbis_b200 import sharding
+    desc, pool = _pool()
+    hb = workloads.config3(pool, 12000, 77)
+    want, clipped = _oracle_on_batch(hb)
+    ctx = capi.Context(0); ctx.upload_setup(setupio.to_setup(desc))
+    a, ra = ctx.decode_batch(sharding.slice_batch(hb, 0, 6000, 2))
+    a = a.copy()
+    b, rb = ctx.decode_batch(sharding.slice_batch(hb, 6000, 12000, 2), capi.RUN_CONTINUE)
+    got = np.concatenate([a, b])
+    assert got.size == want.size and float(np.abs(got - want).max()) <= TOL
+    assert (ra.has_clipped or rb.has_clipped) == clipped
+
+
 def test_blob_roundtrip():
     r, pcm, b, ctx = _ctx("3test")
     ctx2 = capi.Context(0)
