@@ -164,6 +164,8 @@ void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) 
     }
     S.db = reinterpret_cast<const float*>(base + h.off_db);
     S.fused_tab = h.off_fused_tab ? reinterpret_cast<const float*>(base + h.off_fused_tab) : nullptr;
+    S.ci = reinterpret_cast<const CiRec*>(base + h.off_ci);
+    S.bin2k = reinterpret_cast<const uint8_t*>(base + h.off_bin2k);
 }
 
 int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string& err) {
@@ -286,7 +288,19 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
             if (lv > d.max_level) d.max_level = lv;
             d.rcp[k] = 1.0f / (float)((int)d.x[d.hi[k]] - (int)d.x[d.lo[k]]);
         }
+        for (int k = 0; k < g.n_posts; k++) d.xs[k] = d.x[d.sort[k]];
         w.at<DevFloor1>(h.off_floors)[i] = d;
+    }
+    // bin -> sorted position of the last post at or below it (posts are strictly ascending in sort order, x[sort[0]] = 0)
+    h.off_bin2k = w.reserve((size_t)s->n_floors * (h.bs[1] / 2));
+    for (int i = 0; i < s->n_floors; i++) {
+        const DevFloor1& d = w.at<DevFloor1>(h.off_floors)[i];
+        uint8_t* tab = w.at<uint8_t>(h.off_bin2k) + (size_t)i * (h.bs[1] / 2);
+        int k = 0;
+        for (int bin = 0; bin < h.bs[1] / 2; bin++) {
+            while (k + 1 < d.n_posts && (int)d.xs[k + 1] <= bin) ++k;
+            tab[bin] = (uint8_t)k;
+        }
     }
     h.off_residues = w.reserve(sizeof(DevResidue) * s->n_residues);
     int ci_total = 0;
@@ -318,7 +332,23 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         // partitions start on multiples of G = max(4, C) floats
         const int G = C > 4 ? C : 4;
         if (fast && (r.type == 2 || (r.type == 1 && C == 1)) && r.begin % G == 0 && r.partition_size % G == 0 && is_pow2(C)) d.fast = 2;
+        // level 3: k_spectrum_run works on groups of 8 consecutive values of the stream
+        if (d.fast == 2 && r.begin % 8 == 0 && r.partition_size % 8 == 0) d.fast = 3;
         w.at<DevResidue>(h.off_residues)[i] = d;
+    }
+    h.off_ci = w.reserve(sizeof(CiRec) * (size_t)(ci_total > 0 ? ci_total : 1));
+    for (int i = 0; i < s->n_residues; i++) {
+        const DevResidue& d = w.at<DevResidue>(h.off_residues)[i];
+        const int st_n = d.stages > 0 ? d.stages : 1;
+        for (int c = 0; c < d.nclass; c++) for (int st = 0; st < st_n; st++) {
+            CiRec ci; ci.off = 0; ci.dshift = 0; ci.entries = 0; ci.cnt = 0;
+            const int bk = st < d.stages ? d.books[c][st] : -1;
+            if (bk >= 0 && new_off[(size_t)bk] >= 0 && new_off[(size_t)bk] < (int64_t(1) << 30)) {
+                const DevBook& b = w.at<DevBook>(h.off_books)[bk];
+                ci.off = (int32_t)b.off; ci.dshift = b.dshift; ci.entries = b.entries; ci.cnt = d.cnt[c][st];
+            }
+            w.at<CiRec>(h.off_ci)[d.ci_off + c * st_n + st] = ci;
+        }
     }
     h.off_mappings = w.reserve(sizeof(DevMapping) * s->n_mappings);
     for (int i = 0; i < s->n_mappings; i++) {
@@ -388,13 +418,14 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         h.ci_total = ci_total;
         h.max_stages = 1;
         for (int i = 0; i < h.n_residues; i++) if (S.residues[i].stages > h.max_stages) h.max_stages = S.residues[i].stages;
-        int fast = 2;
+        int fast = 3;
         for (int i = 0; i < h.n_modes; i++) {
             const DevResidue& R = S.residues[S.mappings[S.modes[i].mapping].residue];
             if (R.fast < fast) fast = R.fast;
-            // plane kernel: stages planes + floor rows + item list in shared memory
-            if ((size_t)(h.max_stages + 1) * C * (h.bs[1] / 2) * 4 + (size_t)mx * 9 + 64 > 96 * 1024 && fast > 1) fast = 1;
         }
+        // plane kernel: stages planes + floor rows + item list in shared memory (k_spectrum_run needs none of those)
+        if (fast == 2 && (size_t)(h.max_stages + 1) * C * (h.bs[1] / 2) * 4 + (size_t)mx * 9 + 64 > 96 * 1024) fast = 1;
+        if (fast == 3 && (size_t)mx * 5 + (size_t)ci_total * sizeof(CiRec) + 64 > 160 * 1024) fast = 1;
         if ((size_t)mx * 4 + (size_t)C * (h.bs[1] / 2) * 4 > 160 * 1024) fast = 0;      // prefix table + floor curve rows must fit in shared memory
         h.spectrum_fast = fast;
     }
@@ -416,6 +447,7 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
               in(h.off_floors, sizeof(DevFloor1) * (uint64_t)h.n_floors) && in(h.off_residues, sizeof(DevResidue) * (uint64_t)h.n_residues) &&
               in(h.off_mappings, sizeof(DevMapping) * (uint64_t)h.n_mappings) && in(h.off_modes, sizeof(DevMode) * (uint64_t)h.n_modes) &&
               in(h.off_win_short, 4ull * h.bs[0]) && in(h.off_win_long, 16ull * h.bs[1]) && in(h.off_db, 1024) &&
+              h.ci_total >= 0 && in(h.off_ci, sizeof(CiRec) * (uint64_t)(h.ci_total > 0 ? h.ci_total : 1)) && in(h.off_bin2k, (uint64_t)h.n_floors * (h.bs[1] / 2)) &&
               (h.off_fused_tab == 0 || (in(h.off_fused_tab, 4ull * FusedTables::FLOATS) && h.bs[0] == FUSED_SHORT_N && h.bs[1] == FUSED_LONG_N));
     for (int i = 0; i < 2 && ok; i++)
         ok = in(h.off_mdct_a[i], 2ull * h.bs[i]) && in(h.off_mdct_b[i], 2ull * h.bs[i]) && in(h.off_mdct_c[i], 1ull * h.bs[i]) &&
@@ -457,7 +489,26 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
     }
     if (h.post_stride < 4 || h.max_items < 1 || h.max_items > 40000 || h.max_stages < 1 || h.max_stages > NVB_MAX_STAGES) return fail(err, NVB_ERR_DATA, "blob: post_stride/max_items/max_stages");
     for (int i = 0; i < h.n_residues; i++) if (S.residues[i].stages > h.max_stages) return fail(err, NVB_ERR_DATA, "blob: max_stages");
-    if (h.spectrum_fast >= 2 && (size_t)(h.max_stages + 1) * h.channels * (h.bs[1] / 2) * 4 + (size_t)h.max_items * 9 + 64 > 96 * 1024) return fail(err, NVB_ERR_DATA, "blob: plane kernel does not fit");
+    if (h.spectrum_fast == 2 && (size_t)(h.max_stages + 1) * h.channels * (h.bs[1] / 2) * 4 + (size_t)h.max_items * 9 + 64 > 96 * 1024) return fail(err, NVB_ERR_DATA, "blob: plane kernel does not fit");
+    if (h.spectrum_fast < 0 || h.spectrum_fast > 3) return fail(err, NVB_ERR_DATA, "blob: spectrum_fast");
+    for (int i = 0; i < h.n_residues; i++) {
+        const DevResidue& r = S.residues[i];
+        const int st_n = r.stages > 0 ? r.stages : 1;
+        if (r.ci_off < 0 || r.ci_off + r.nclass * st_n > h.ci_total) return fail(err, NVB_ERR_DATA, "blob: residue %lld ci table", i);
+        for (int k = 0; k < r.nclass * st_n; k++) {
+            const CiRec& ci = S.ci[r.ci_off + k];
+            if (ci.cnt < 0 || ci.entries < 0 || ci.off < 0 || ci.dshift < -1 || ci.dshift > 16 ||
+                (ci.cnt > 0 && ci.dshift >= 0 && (uint64_t)ci.off + ((uint64_t)ci.entries << ci.dshift) > h.n_vq)) return fail(err, NVB_ERR_DATA, "blob: residue %lld ci record", i);
+        }
+    }
+    for (int i = 0; i < h.n_floors; i++) {
+        const DevFloor1& f = S.floors[i];
+        for (int k = 0; k < f.n_posts; k++) if (f.xs[k] != f.x[f.sort[k]]) return fail(err, NVB_ERR_DATA, "blob: floor %lld sorted x", i);
+        for (int b = 0; b < h.bs[1] / 2; b++) {
+            const int k = S.bin2k[(size_t)i * (h.bs[1] / 2) + b];
+            if (k >= f.n_posts || f.xs[k] > b || (k + 1 < f.n_posts && f.xs[k + 1] <= b)) return fail(err, NVB_ERR_DATA, "blob: floor %lld bin table", i);
+        }
+    }
     return NVB_OK;
 }
 

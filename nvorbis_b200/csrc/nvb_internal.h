@@ -47,11 +47,14 @@ struct DevFloor1  {
     uint16_t x[NVB_MAX_POSTS]; uint8_t lo[NVB_MAX_POSTS], hi[NVB_MAX_POSTS], sort[NVB_MAX_POSTS];
     uint8_t level[NVB_MAX_POSTS];   // depth of post i in the neighbour dependency tree: 1 + max(level[lo], level[hi]); posts 0, 1 are level 0
     float rcp[NVB_MAX_POSTS];       // 1.0f / (x[hi[i]] - x[lo[i]]): RenderPoint's divisor is a setup constant
+    uint16_t xs[NVB_MAX_POSTS];     // x[sort[k]]: the x list in ascending order (k_spectrum_run)
 };
+// k_spectrum_run: one record per (class, stage) of a residue, DevResidue.ci_off + class * stages + stage
+struct alignas(16) CiRec { int32_t off, dshift, entries, cnt; };   // VQ table float offset, log2(dims), book entries, entries per partition (0 = nothing coded)
 struct DevResidue {
     int32_t type, begin, end, psize, nclass, stages;
     int32_t pshift;                 // log2(psize) or -1
-    int32_t fast;                   // 1: k_spectrum_fast applies (power-of-two partition/book sizes, type 2 partitions aligned to the channel count); 2: k_spectrum_planes too
+    int32_t fast;                   // 1: k_spectrum_fast applies (power-of-two partition/book sizes, type 2 partitions aligned to the channel count); 2: k_spectrum_planes too; 3: k_spectrum_run too
     int32_t cascade[NVB_MAX_CLASSES];
     int16_t books[NVB_MAX_CLASSES][NVB_MAX_STAGES];
     int16_t cnt[NVB_MAX_CLASSES][NVB_MAX_STAGES];   // VQ entries one partition of (class, stage) consumes; 0 = nothing coded
@@ -70,7 +73,7 @@ struct BlobHeader {
     int32_t n_books, n_floors, n_residues, n_mappings, n_modes;
     int32_t post_stride;       // int16 elements per (frame, channel) in nvb_batch.posts
     int32_t max_items;         // max over modes of stages*partitions*streams (residue prefix table)
-    int32_t spectrum_fast;     // 2: every mode fits k_spectrum_planes, 1: k_spectrum_fast, 0: only the general k_spectrum
+    int32_t spectrum_fast;     // 3: every mode fits k_spectrum_run, 2: k_spectrum_planes, 1: k_spectrum_fast, 0: only the general k_spectrum
     uint64_t off_books, off_vq, off_floors, off_residues, off_mappings, off_modes;
     uint64_t off_win_short;    // bs[0] floats
     uint64_t off_win_long;     // 4 * bs[1] floats (window index = prev?1:0 + next?2:0)
@@ -81,7 +84,9 @@ struct BlobHeader {
     uint64_t n_vq;
     uint64_t off_fused_tab;    // FusedTables block (nvb_fused_core.h) when bs == {256, 2048}, else 0
     int32_t max_stages;        // largest residue stage count of the setup
-    int32_t ci_total;          // sum over residues of nclass * stages: size of k_spectrum_warp's (class, stage) table
+    int32_t ci_total;          // sum over residues of nclass * stages: size of the (class, stage) table
+    uint64_t off_ci;           // CiRec[ci_total]
+    uint64_t off_bin2k;        // uint8[n_floors][bs[1]/2]: sorted position of the last floor post with x <= bin
 };
 
 // Resolved pointers handed to kernels by value.
@@ -94,6 +99,7 @@ struct DevSetup {
     const float2* tw[2]; const float2* fft[2];
     const float* db;
     const float* fused_tab;    // lane tables of the fused kernel, nullptr when the block sizes are not {256, 2048}
+    const CiRec* ci; const uint8_t* bin2k;
 };
 
 // ---- per-frame plan built on the host from nvb_frame (ok frames only, in order) ----------------

@@ -152,10 +152,12 @@ __device__ __forceinline__ int div_small(int num, int den, float rcp) {
     return q;
 }
 
-__device__ __forceinline__ void floor1_segments_warp(const DevFloor1& F, const int16_t* posts, int n, int lane, int* fy, SegRec* segs, int* nseg_out) {
-    int count = posts[0];
+// UnwrapPosts (Floor1.cs:224-297) by one warp, lane = post (and post + 32): the posts of one dependency level in parallel.
+// Leaves finalY in fy[] and returns the step flags (bit i = stepFlags[i]); `count` is the clamped PostCount (< 2: nothing done).
+__device__ __forceinline__ unsigned long long floor1_unwrap_warp(const DevFloor1& F, const int16_t* posts, int lane, int* fy, int& count) {
+    count = posts[0];
     if (count > F.n_posts) count = F.n_posts;
-    if (count < 2) { if (lane == 0) *nseg_out = 0; return; }             // PostCount == 0: the spectrum is cleared (Floor1.cs:220)
+    if (count < 2) return 0ull;                                           // PostCount == 0: the spectrum is cleared (Floor1.cs:220)
     const int H = count > 32 ? 2 : 1;                                    // posts lane and lane + 32
     int val[2]; unsigned long long contrib = 0ull;
     #pragma unroll
@@ -203,7 +205,13 @@ __device__ __forceinline__ void floor1_segments_warp(const DevFloor1& F, const i
     unsigned lo32 = (unsigned)contrib, hi32 = (unsigned)(contrib >> 32);
     #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { lo32 |= __shfl_xor_sync(0xffffffffu, lo32, d); hi32 |= __shfl_xor_sync(0xffffffffu, hi32, d); }
-    const unsigned long long flags = (((unsigned long long)hi32 << 32) | lo32) | 3ull;
+    return (((unsigned long long)hi32 << 32) | lo32) | 3ull;
+}
+
+__device__ __forceinline__ void floor1_segments_warp(const DevFloor1& F, const int16_t* posts, int n, int lane, int* fy, SegRec* segs, int* nseg_out) {
+    int count;
+    const unsigned long long flags = floor1_unwrap_warp(F, posts, lane, fy, count);
+    if (count < 2) { if (lane == 0) *nseg_out = 0; return; }
     // sorted walk: position k (lane, lane + 32) holds post sort[k]
     int idx[2]; bool act[2];
     #pragma unroll
@@ -680,6 +688,252 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_planes(LaunchArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1+K2+K3, run path (the default when DevSetup.spectrum_fast == 3): the same residues as the plane path whose
+// partitions start on multiples of 8 values.  No planes, no floor rows, no item list: a thread owns a RUN of 8
+// consecutive values of the interleaved stream -- 8 / C consecutive bins of every channel -- start to end:
+//   phase A  a warp per channel unwraps the floor posts (floor1_unwrap_warp) and leaves the active-post mask of the
+//            x-sorted walk of Floor1.Apply (Floor1.cs:196-216) plus the sorted (x, y) lists; the last warp turns the class
+//            bytes into the entry-stream offset of every (stage, partition);
+//   main     per thread: the VQ vectors of its run are whole vector loads (8 values lie inside one partition, and
+//            inside one entry when dims >= 8), summed in stage order from +0 (the float adds of WriteVectors in the
+//            reference's order); inverse coupling pairs sit in the same thread; the floor line is walked along the
+//            run with the bin -> post table of the setup, y(x) of RenderLineMulti (Floor1.cs:316-341) in closed form;
+//            one vector store per channel.
+// ------------------------------------------------------------------------------------------------
+#if !defined(NVB_CPU_SHIM)
+__device__ __forceinline__ float rcp_estimate(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+static inline float rcp_estimate(float x) { return 1.0f / x; }
+static inline void prefetch_l1(const void*) {}
+#endif
+
+template <int CT, int NT>
+__global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
+    constexpr int NW = NT / 32;
+    constexpr int RB = 8 / CT;                                              // bins per channel in one run
+    NVB_DYN_SMEM(dyn_smem);
+    __shared__ float s_db[256];
+    __shared__ int s_fy[CT][NVB_MAX_POSTS];
+    __shared__ int s_ys[CT][NVB_MAX_POSTS];                                 // finalY * multiplier in x-sorted order
+    __shared__ int s_xs[NVB_MAX_POSTS];                                     // x list in ascending order
+    __shared__ unsigned long long s_mask[CT];                               // bit k: sorted position k is a step of the walk; 0 = no floor
+    __shared__ uint8_t s_coded[NVB_MAX_CLASSES];
+
+    nvb_grid_dep_launch();
+    nvb_grid_dep_wait();
+    const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
+    if (f.kind != 0) return;
+    const DevSetup& S = a.S;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const DevMode md = S.modes[f.mode];
+    const DevMapping& mp = S.mappings[md.mapping];
+    const DevResidue& R = S.residues[mp.residue];
+    const DevFloor1& F = S.floors[mp.floor];
+    const int N = f.n, n = N >> 1, span = CT * n;
+    const int st_n = R.stages > 0 ? R.stages : 1;
+    const int rbegin = R.begin, pshift = R.pshift, nclass = R.nclass;
+    int P = 0;
+    if (f.res_decoded) { const int e = R.end < span ? R.end : span; const int nn = e - rbegin; P = nn > 0 ? nn >> pshift : 0; }   // Residue0.cs:122-127
+    CiRec* s_ci = reinterpret_cast<CiRec*>(dyn_smem);
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(s_ci + S.ci_total);      // [stage][partition]: where the item's entries start
+    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_base + S.max_items);
+    const uint8_t* cls = a.classes + f.classes_off;
+    const uint16_t* ent = a.entries + f.entries_off;
+    const uint8_t* bin2k = S.bin2k + (size_t)mp.floor * (S.bs[1] >> 1);
+
+    for (int i = t; i < 256; i += NT) s_db[i] = S.db[i];
+    for (int i = t; i < nclass * st_n; i += NT) s_ci[i] = S.ci[R.ci_off + i];
+    for (int i = t; i < nclass; i += NT) s_coded[i] = R.coded[i];
+    for (int p = t; p < P; p += NT) { const int cl = cls[p]; s_cls[p] = cl < nclass ? (uint8_t)cl : (uint8_t)255; }
+    for (int k = t; k < F.n_posts; k += NT) s_xs[k] = F.xs[k];
+    if (P > 0) for (uint32_t i = (uint32_t)t * 64u; i < f.entry_count; i += NT * 64u) prefetch_l1(ent + i);   // the frame's entries: 128 bytes per thread
+    __syncthreads();
+
+    // ---- phase A
+    if (warp == NW - 1 && P > 0) {
+        uint32_t run = 0;
+        for (int st = 0; st < R.stages; st++) {
+            for (int base = 0; base < P; base += 32) {
+                const int p = base + lane;
+                uint32_t c = 0;
+                if (p < P) { const int cl = s_cls[p]; if (cl != 255) c = (uint32_t)s_ci[cl * st_n + st].cnt; }
+                uint32_t incl = c;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+                if (p < P) s_base[st * P + p] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+    }
+    for (int c = warp; c < CT; c += NW) {
+        unsigned long long mask = 0ull;
+        if ((f.exec_mask >> c) & 1u) {
+            int count;
+            const unsigned long long flags = floor1_unwrap_warp(F, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, lane, s_fy[c], count);
+            if (count >= 2) {
+                // the walk of Floor1.Apply visits sorted positions 1 .. PostCount-1 and steps on flagged posts; position 0 is its start
+                unsigned m[2];
+                #pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int k = lane + 32 * h;
+                    int idx = 0; bool act = false;
+                    if (k < count) { idx = F.sort[k]; act = idx < count && ((flags >> idx) & 1ull); s_ys[c][k] = s_fy[c][idx < count ? idx : 0] * F.mult; }
+                    m[h] = __ballot_sync(0xffffffffu, act);
+                }
+                mask = (((unsigned long long)m[1] << 32) | m[0]) | 1ull;
+            }
+        }
+        if (lane == 0) s_mask[c] = mask;
+    }
+    __syncthreads();
+
+    // ---- main: one run of 8 stream values per thread
+    float* spec_out = a.spectrum + (size_t)f.spec_off;
+    const uint32_t ecount = f.entry_count;
+    const int pmask = (1 << pshift) - 1;
+    int bad_floor = 0, bad_entry = 0;
+    for (int gi = t; gi < (span >> 3); gi += NT) {
+        const int pos0 = gi << 3;
+        float acc[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0.f;
+        const int q = pos0 - rbegin, p = q >> pshift;
+        if (q >= 0 && p < P) {
+            const int cl = s_cls[p];
+            if (cl != 255) {
+                const int o = q & pmask;
+                unsigned casc = s_coded[cl];
+                while (casc) {
+                    const int st = __ffs(casc) - 1; casc &= casc - 1;
+                    const CiRec ci = s_ci[cl * st_n + st];
+                    const uint32_t eb = s_base[st * P + p];
+                    const float* tab = S.vq + ci.off;
+                    if (ci.dshift >= 3) {                                   // the run lies inside one entry
+                        const uint32_t ei = eb + (uint32_t)(o >> ci.dshift);
+                        if (ei < ecount) {                                  // else never decoded: contributes nothing (Residue0.cs:164-170)
+                            const int en = ent[ei];
+                            if (en < ci.entries) {
+                                const float4* src = reinterpret_cast<const float4*>(tab + ((size_t)en << ci.dshift) + (o & ((1 << ci.dshift) - 1)));
+                                const float4 v0 = src[0], v1 = src[1];
+                                acc[0] = NVB_FADD(acc[0], v0.x); acc[1] = NVB_FADD(acc[1], v0.y); acc[2] = NVB_FADD(acc[2], v0.z); acc[3] = NVB_FADD(acc[3], v0.w);
+                                acc[4] = NVB_FADD(acc[4], v1.x); acc[5] = NVB_FADD(acc[5], v1.y); acc[6] = NVB_FADD(acc[6], v1.z); acc[7] = NVB_FADD(acc[7], v1.w);
+                            } else bad_entry = 1;
+                        }
+                    } else if (ci.dshift == 2) {
+                        #pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const uint32_t ei = eb + (uint32_t)(o >> 2) + h;
+                            if (ei < ecount) {
+                                const int en = ent[ei];
+                                if (en < ci.entries) {
+                                    const float4 v = *reinterpret_cast<const float4*>(tab + ((size_t)en << 2));
+                                    acc[4 * h] = NVB_FADD(acc[4 * h], v.x); acc[4 * h + 1] = NVB_FADD(acc[4 * h + 1], v.y);
+                                    acc[4 * h + 2] = NVB_FADD(acc[4 * h + 2], v.z); acc[4 * h + 3] = NVB_FADD(acc[4 * h + 3], v.w);
+                                } else bad_entry = 1;
+                            }
+                        }
+                    } else if (ci.dshift == 1) {
+                        #pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            const uint32_t ei = eb + (uint32_t)(o >> 1) + h;
+                            if (ei < ecount) {
+                                const int en = ent[ei];
+                                if (en < ci.entries) {
+                                    const float2 v = *reinterpret_cast<const float2*>(tab + ((size_t)en << 1));
+                                    acc[2 * h] = NVB_FADD(acc[2 * h], v.x); acc[2 * h + 1] = NVB_FADD(acc[2 * h + 1], v.y);
+                                } else bad_entry = 1;
+                            }
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int h = 0; h < 8; h++) {
+                            const uint32_t ei = eb + (uint32_t)o + h;
+                            if (ei < ecount) {
+                                const int en = ent[ei];
+                                if (en < ci.entries) acc[h] = NVB_FADD(acc[h], tab[en]); else bad_entry = 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        for (int i = mp.n_coupling - 1; i >= 0; --i) {                      // Mapping.cs:137-182
+            const int m = mp.mag[i], an = mp.ang[i];
+            if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
+            #pragma unroll
+            for (int b = 0; b < RB; b++) {
+                float vm = 0.f, va = 0.f;
+                #pragma unroll
+                for (int k = 0; k < CT; k++) { if (k == m) vm = acc[b * CT + k]; if (k == an) va = acc[b * CT + k]; }
+                inverse_couple(vm, va);
+                #pragma unroll
+                for (int k = 0; k < CT; k++) { if (k == m) acc[b * CT + k] = vm; if (k == an) acc[b * CT + k] = va; }
+            }
+        }
+        const int bin0 = pos0 / CT;
+        #pragma unroll
+        for (int c = 0; c < CT; c++) {
+            if ((f.exec_mask >> c) & 1u) {                                  // Floor1.Apply, Floor1.cs:186-222
+                const unsigned long long M = s_mask[c];
+                if (M == 0ull) {
+                    #pragma unroll
+                    for (int b = 0; b < RB; b++) acc[b * CT + c] = 0.f;
+                } else {
+                    const int* ys = s_ys[c];
+                    const int k0 = bin2k[bin0];
+                    int lo = 63 - __clzll((long long)(M & (0xffffffffffffffffull >> (63 - k0))));    // bit 0 is set
+                    unsigned long long above = M & ~(((1ull << lo) << 1) - 1ull);
+                    int x0, y0, hx, adx, dyabs, sy; float rcp;
+                    auto load_segment = [&]() {
+                        x0 = s_xs[lo]; y0 = ys[lo];
+                        if (above) {
+                            const int hi = __ffsll((long long)above) - 1;
+                            hx = s_xs[hi];
+                            const int dy = ys[hi] - y0;
+                            adx = (hx < n ? hx : n) - x0;                   // x clamped, y NOT re-interpolated (Floor1.cs:206)
+                            dyabs = dy < 0 ? -dy : dy; sy = dy < 0 ? -1 : 1;
+                            lo = hi; above &= above - 1ull;                 // the segment after this one
+                        } else { hx = 0x7fffffff; adx = 1; dyabs = 0; sy = 1; }   // flat tail, Floor1.cs:213-216
+                        rcp = rcp_estimate((float)adx);
+                    };
+                    load_segment();
+                    #pragma unroll
+                    for (int b = 0; b < RB; b++) {
+                        const int x = bin0 + b;
+                        while (x >= hx) load_segment();
+                        const int num = (x - x0) * dyabs;                   // y(x) = y0 + sy * floor((x - x0) |dy| / adx)
+                        const int qq = (unsigned)num < (1u << 22) ? div_small(num, adx, rcp) : num / adx;
+                        int y = y0 + sy * qq;
+                        if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
+                        acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], s_db[y]);
+                    }
+                }
+            }
+            float* dst = spec_out + (size_t)c * n + bin0;
+            if (RB == 8) {
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            } else if (RB == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[c], acc[CT + c], acc[2 * CT + c], acc[3 * CT + c]);
+            else if (RB == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[c], acc[CT + c]);
+            else *dst = acc[c];
+        }
+    }
+    if (__syncthreads_or(bad_entry | (bad_floor << 1))) {                   // rare: count the frame once per kind
+        __shared__ int s_bad[2];
+        if (t < 2) s_bad[t] = 0;
+        __syncthreads();
+        if (bad_entry) atomicOr(&s_bad[0], 1);
+        if (bad_floor) atomicOr(&s_bad[1], 1);
+        __syncthreads();
+        if (t == 0) {
+            if (s_bad[0]) atomicAdd(&a.counters->bad_entry, 1);
+            if (s_bad[1]) atomicAdd(&a.counters->floor_range, 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1+K2+K3, warp path (NVB_SPECTRUM_WARP=1; see launch_spectrum for why it is not the default): the same arithmetic as k_spectrum_planes with
 // ONE WARP PER FRAME in a persistent grid -- no block-wide barrier, every warp runs its own frame start to end
 // while the other warps of the SM hide its latencies:
@@ -1013,6 +1267,19 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
             else NVB_LAUNCH(k_spectrum_warp<8>, grid, nw * 32, smem, stream, a);
             return cudaGetLastError() == cudaSuccess ? 1 : -1;
         }
+    }
+    static const bool force_planes = std::getenv("NVB_SPECTRUM_PLANES") != nullptr;           // test hook: exercise k_spectrum_planes
+    if (a.S.spectrum_fast >= 3 && !no_planes && !force_planes) {
+        const int C = a.S.channels;
+        static const int nt = std::getenv("NVB_SPECTRUM_NT") ? std::atoi(std::getenv("NVB_SPECTRUM_NT")) : 256;
+        const size_t smem = (size_t)a.S.ci_total * sizeof(CiRec) + (size_t)a.S.max_items * sizeof(uint32_t) + (((size_t)a.S.max_items + 15) & ~size_t(15)) + 16;
+        auto go = [&](auto kernel, int threads) -> int {
+            if (smem > 40 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            NVB_LAUNCH(kernel, a.n_frames, threads, smem, stream, a);
+            return cudaGetLastError() == cudaSuccess ? 1 : -1;
+        };
+        if (nt == 128) return C == 1 ? go(k_spectrum_run<1, 128>, 128) : C == 2 ? go(k_spectrum_run<2, 128>, 128) : C == 4 ? go(k_spectrum_run<4, 128>, 128) : go(k_spectrum_run<8, 128>, 128);
+        return C == 1 ? go(k_spectrum_run<1, 256>, 256) : C == 2 ? go(k_spectrum_run<2, 256>, 256) : C == 4 ? go(k_spectrum_run<4, 256>, 256) : go(k_spectrum_run<8, 256>, 256);
     }
     if (a.S.spectrum_fast >= 2 && !no_planes) {
         const int C = a.S.channels;
