@@ -708,6 +708,21 @@ static inline float rcp_estimate(float x) { return 1.0f / x; }
 static inline void prefetch_l1(const void*) {}
 #endif
 
+// Segment of the floor line that starts at an active post (x-sorted position k): RenderLineMulti(x0, y0, min(hx, n), hy)
+// (Floor1.cs:206).  y(x) = y0 + sign(dy) * floor((x - x0) |dy| / adx); the division by adx is a multiply-high with
+// m = floor(2^32 / adx) + 1, exact while (x - x0) |dy| adx < 2^32 (checked per segment: adx^2 |dy| < 2^32); m == 0 sends the
+// bin to the plain division.
+struct alignas(16) RunSeg { int32_t x0, y0, dy; uint32_t m; };
+
+// Inverse coupling of one bin (Mapping.cs:145-181), branch-free: same compares, one add or subtract.
+__device__ __forceinline__ void inverse_couple_sel(float& m, float& a) {
+    const float M = m, A = a;
+    const bool mp = M > 0.f, ap = A > 0.f;
+    const float t = (mp == ap) ? NVB_FSUB(M, A) : NVB_FADD(M, A);
+    m = ap ? M : t;
+    a = ap ? t : M;
+}
+
 template <int CT, int NT>
 __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
     constexpr int NW = NT / 32;
@@ -716,9 +731,11 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
     __shared__ float s_db[256];
     __shared__ int s_fy[CT][NVB_MAX_POSTS];
     __shared__ int s_ys[CT][NVB_MAX_POSTS];                                 // finalY * multiplier in x-sorted order
-    __shared__ int s_xs[NVB_MAX_POSTS];                                     // x list in ascending order
-    __shared__ unsigned long long s_mask[CT];                               // bit k: sorted position k is a step of the walk; 0 = no floor
+    __shared__ RunSeg s_seg[CT][NVB_MAX_POSTS];                             // segment that starts at sorted position k
+    __shared__ int s_adx[CT][NVB_MAX_POSTS];
+    __shared__ unsigned long long s_mask[CT];                               // bit k: sorted position k starts a segment; 0 = no floor
     __shared__ uint8_t s_coded[NVB_MAX_CLASSES];
+    __shared__ int s_bad[2];
 
     nvb_grid_dep_launch();
     nvb_grid_dep_wait();
@@ -746,7 +763,7 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
     for (int i = t; i < nclass * st_n; i += NT) s_ci[i] = S.ci[R.ci_off + i];
     for (int i = t; i < nclass; i += NT) s_coded[i] = R.coded[i];
     for (int p = t; p < P; p += NT) { const int cl = cls[p]; s_cls[p] = cl < nclass ? (uint8_t)cl : (uint8_t)255; }
-    for (int k = t; k < F.n_posts; k += NT) s_xs[k] = F.xs[k];
+    if (t < 2) s_bad[t] = 0;
     if (P > 0) for (uint32_t i = (uint32_t)t * 64u; i < f.entry_count; i += NT * 64u) prefetch_l1(ent + i);   // the frame's entries: 128 bytes per thread
     __syncthreads();
 
@@ -782,6 +799,26 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
                     m[h] = __ballot_sync(0xffffffffu, act);
                 }
                 mask = (((unsigned long long)m[1] << 32) | m[0]) | 1ull;
+                __syncwarp();
+                #pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int k = lane + 32 * h;
+                    if ((mask >> k) & 1ull) {
+                        RunSeg r; r.x0 = F.xs[k]; r.y0 = s_ys[c][k]; r.dy = 0; r.m = 1u;
+                        int adx = 1;
+                        const unsigned long long above = mask & ~(((1ull << k) << 1) - 1ull);
+                        if (above) {                                        // else the flat tail, Floor1.cs:213-216
+                            const int hi = __ffsll((long long)above) - 1;
+                            const int hx = F.xs[hi];
+                            adx = (hx < n ? hx : n) - r.x0;                 // x clamped, y NOT re-interpolated (Floor1.cs:206)
+                            r.dy = s_ys[c][hi] - r.y0;
+                            const unsigned long long ady = (unsigned long long)(r.dy < 0 ? -(long long)r.dy : (long long)r.dy);
+                            if (adx <= 1) { adx = 1; r.m = 1u; }            // one bin (or a post at or beyond n): (x - x0) = 0
+                            else r.m = ((unsigned long long)adx * (unsigned long long)adx * ady < (1ull << 32)) ? 0xffffffffu / (unsigned)adx + 1u : 0u;
+                        }
+                        s_seg[c][k] = r; s_adx[c][k] = adx;
+                    }
+                }
             }
         }
         if (lane == 0) s_mask[c] = mask;
@@ -792,9 +829,20 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
     float* spec_out = a.spectrum + (size_t)f.spec_off;
     const uint32_t ecount = f.entry_count;
     const int pmask = (1 << pshift) - 1;
+    const bool posts32 = F.n_posts <= 32;
+    unsigned long long fmask[CT];
+    #pragma unroll
+    for (int c = 0; c < CT; c++) fmask[c] = s_mask[c];
     int bad_floor = 0, bad_entry = 0;
     for (int gi = t; gi < (span >> 3); gi += NT) {
         const int pos0 = gi << 3;
+        const int bin0 = pos0 / CT;
+        // sorted position of the last post at or below each bin of the run (setup table, one load)
+        unsigned long long kword;
+        if (RB == 8) kword = *reinterpret_cast<const unsigned long long*>(bin2k + bin0);
+        else if (RB == 4) kword = *reinterpret_cast<const uint32_t*>(bin2k + bin0);
+        else if (RB == 2) kword = *reinterpret_cast<const uint16_t*>(bin2k + bin0);
+        else kword = bin2k[bin0];
         float acc[8];
         #pragma unroll
         for (int k = 0; k < 8; k++) acc[k] = 0.f;
@@ -861,50 +909,42 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
         for (int i = mp.n_coupling - 1; i >= 0; --i) {                      // Mapping.cs:137-182
             const int m = mp.mag[i], an = mp.ang[i];
             if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
-            #pragma unroll
-            for (int b = 0; b < RB; b++) {
-                float vm = 0.f, va = 0.f;
+            if (CT == 2) {                                                  // (magnitude, angle) is (0, 1) or (1, 0)
                 #pragma unroll
-                for (int k = 0; k < CT; k++) { if (k == m) vm = acc[b * CT + k]; if (k == an) va = acc[b * CT + k]; }
-                inverse_couple(vm, va);
+                for (int b = 0; b < RB; b++) { if (m == 0) inverse_couple_sel(acc[2 * b], acc[2 * b + 1]); else inverse_couple_sel(acc[2 * b + 1], acc[2 * b]); }
+            } else {
                 #pragma unroll
-                for (int k = 0; k < CT; k++) { if (k == m) acc[b * CT + k] = vm; if (k == an) acc[b * CT + k] = va; }
+                for (int b = 0; b < RB; b++) {
+                    float vm = 0.f, va = 0.f;
+                    #pragma unroll
+                    for (int k = 0; k < CT; k++) { if (k == m) vm = acc[b * CT + k]; if (k == an) va = acc[b * CT + k]; }
+                    inverse_couple_sel(vm, va);
+                    #pragma unroll
+                    for (int k = 0; k < CT; k++) { if (k == m) acc[b * CT + k] = vm; if (k == an) acc[b * CT + k] = va; }
+                }
             }
         }
-        const int bin0 = pos0 / CT;
         #pragma unroll
         for (int c = 0; c < CT; c++) {
             if ((f.exec_mask >> c) & 1u) {                                  // Floor1.Apply, Floor1.cs:186-222
-                const unsigned long long M = s_mask[c];
+                const unsigned long long M = fmask[c];
                 if (M == 0ull) {
                     #pragma unroll
                     for (int b = 0; b < RB; b++) acc[b * CT + c] = 0.f;
                 } else {
-                    const int* ys = s_ys[c];
-                    const int k0 = bin2k[bin0];
-                    int lo = 63 - __clzll((long long)(M & (0xffffffffffffffffull >> (63 - k0))));    // bit 0 is set
-                    unsigned long long above = M & ~(((1ull << lo) << 1) - 1ull);
-                    int x0, y0, hx, adx, dyabs, sy; float rcp;
-                    auto load_segment = [&]() {
-                        x0 = s_xs[lo]; y0 = ys[lo];
-                        if (above) {
-                            const int hi = __ffsll((long long)above) - 1;
-                            hx = s_xs[hi];
-                            const int dy = ys[hi] - y0;
-                            adx = (hx < n ? hx : n) - x0;                   // x clamped, y NOT re-interpolated (Floor1.cs:206)
-                            dyabs = dy < 0 ? -dy : dy; sy = dy < 0 ? -1 : 1;
-                            lo = hi; above &= above - 1ull;                 // the segment after this one
-                        } else { hx = 0x7fffffff; adx = 1; dyabs = 0; sy = 1; }   // flat tail, Floor1.cs:213-216
-                        rcp = rcp_estimate((float)adx);
-                    };
-                    load_segment();
                     #pragma unroll
                     for (int b = 0; b < RB; b++) {
                         const int x = bin0 + b;
-                        while (x >= hx) load_segment();
-                        const int num = (x - x0) * dyabs;                   // y(x) = y0 + sy * floor((x - x0) |dy| / adx)
-                        const int qq = (unsigned)num < (1u << 22) ? div_small(num, adx, rcp) : num / adx;
-                        int y = y0 + sy * qq;
+                        const unsigned kk = (unsigned)(kword >> (8 * b)) & 0xffu;
+                        int lo;                                             // the segment's start: last active position at or below kk (bit 0 is set)
+                        if (posts32) lo = 31 - __clz((int)((unsigned)M & (0xffffffffu >> (31 - kk))));
+                        else lo = 63 - __clzll((long long)(M & (0xffffffffffffffffull >> (63 - kk))));
+                        const RunSeg r = s_seg[c][lo];
+                        const int num = (x - r.x0) * (r.dy < 0 ? -r.dy : r.dy);
+                        int qq;
+                        if (r.m != 0u) qq = (int)__umulhi((unsigned)num, r.m);
+                        else qq = num / s_adx[c][lo];
+                        int y = r.dy < 0 ? r.y0 - qq : r.y0 + qq;
                         if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
                         acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], s_db[y]);
                     }
@@ -919,18 +959,9 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
             else *dst = acc[c];
         }
     }
-    if (__syncthreads_or(bad_entry | (bad_floor << 1))) {                   // rare: count the frame once per kind
-        __shared__ int s_bad[2];
-        if (t < 2) s_bad[t] = 0;
-        __syncthreads();
-        if (bad_entry) atomicOr(&s_bad[0], 1);
-        if (bad_floor) atomicOr(&s_bad[1], 1);
-        __syncthreads();
-        if (t == 0) {
-            if (s_bad[0]) atomicAdd(&a.counters->bad_entry, 1);
-            if (s_bad[1]) atomicAdd(&a.counters->floor_range, 1);
-        }
-    }
+    // rare: count the frame once per kind (the first thread to raise a flag reports it)
+    if (bad_entry && atomicOr(&s_bad[0], 1) == 0) atomicAdd(&a.counters->bad_entry, 1);
+    if (bad_floor && atomicOr(&s_bad[1], 1) == 0) atomicAdd(&a.counters->floor_range, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1271,13 +1302,14 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
     static const bool force_planes = std::getenv("NVB_SPECTRUM_PLANES") != nullptr;           // test hook: exercise k_spectrum_planes
     if (a.S.spectrum_fast >= 3 && !no_planes && !force_planes) {
         const int C = a.S.channels;
-        static const int nt = std::getenv("NVB_SPECTRUM_NT") ? std::atoi(std::getenv("NVB_SPECTRUM_NT")) : 256;
+        static const int nt = std::getenv("NVB_SPECTRUM_NT") ? std::atoi(std::getenv("NVB_SPECTRUM_NT")) : 128;
         const size_t smem = (size_t)a.S.ci_total * sizeof(CiRec) + (size_t)a.S.max_items * sizeof(uint32_t) + (((size_t)a.S.max_items + 15) & ~size_t(15)) + 16;
         auto go = [&](auto kernel, int threads) -> int {
             if (smem > 40 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
             NVB_LAUNCH(kernel, a.n_frames, threads, smem, stream, a);
             return cudaGetLastError() == cudaSuccess ? 1 : -1;
         };
+        if (nt == 64) return C == 1 ? go(k_spectrum_run<1, 64>, 64) : C == 2 ? go(k_spectrum_run<2, 64>, 64) : C == 4 ? go(k_spectrum_run<4, 64>, 64) : go(k_spectrum_run<8, 64>, 64);
         if (nt == 128) return C == 1 ? go(k_spectrum_run<1, 128>, 128) : C == 2 ? go(k_spectrum_run<2, 128>, 128) : C == 4 ? go(k_spectrum_run<4, 128>, 128) : go(k_spectrum_run<8, 128>, 128);
         return C == 1 ? go(k_spectrum_run<1, 256>, 256) : C == 2 ? go(k_spectrum_run<2, 256>, 256) : C == 4 ? go(k_spectrum_run<4, 256>, 256) : go(k_spectrum_run<8, 256>, 256);
     }

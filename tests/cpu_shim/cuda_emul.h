@@ -35,6 +35,8 @@ struct alignas(4) uchar4 { unsigned char x, y, z, w; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 #define NVB_HAVE_FLOAT2 1
 
 namespace cuemu {

@@ -178,7 +178,7 @@ def test_generic_spectrum_kernel(shim):
             "want, _ = H.oracle_synth(r, b, 0, 40)\nout, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, 0, 40), capi.RUN_EXACT)\n"
             "assert np.array_equal(out, want)\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"), shim)
     for var in ("NVB_SPECTRUM_GENERIC", "NVB_SPECTRUM_NO_PLANES", "NVB_SPECTRUM_WARP", "NVB_SPECTRUM_PLANES", "NVB_SPECTRUM_NT"):          # the general kernel / the per-bin fast kernel
-        env = dict(os.environ); env[var] = "128" if var == "NVB_SPECTRUM_NT" else "1"
+        env = dict(os.environ); env[var] = "256" if var == "NVB_SPECTRUM_NT" else "1"
         assert subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().endswith("ok")
 
 

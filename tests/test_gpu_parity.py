@@ -225,7 +225,7 @@ def test_generic_spectrum_kernel_on_gpu():
             "    out, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride), capi.RUN_EXACT)\n"
             "    assert np.array_equal(out, pcm)\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"))
     for var in ("NVB_SPECTRUM_GENERIC", "NVB_SPECTRUM_NO_PLANES", "NVB_SPECTRUM_WARP", "NVB_SPECTRUM_PLANES", "NVB_SPECTRUM_NT"):          # the general kernel / the per-bin fast kernel
-        env = dict(os.environ); env[var] = "128" if var == "NVB_SPECTRUM_NT" else "1"
+        env = dict(os.environ); env[var] = "256" if var == "NVB_SPECTRUM_NT" else "1"
         assert subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().endswith("ok")
 
 
