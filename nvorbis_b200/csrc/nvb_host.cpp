@@ -166,6 +166,7 @@ void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) 
     S.fused_tab = h.off_fused_tab ? reinterpret_cast<const float*>(base + h.off_fused_tab) : nullptr;
     S.ci = reinterpret_cast<const CiRec*>(base + h.off_ci);
     S.bin2k = reinterpret_cast<const uint8_t*>(base + h.off_bin2k);
+    S.run_modes = reinterpret_cast<const RunMode*>(base + h.off_run_modes);
 }
 
 int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string& err) {
@@ -364,6 +365,17 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         w.at<DevMode>(h.off_modes)[i] = d;
     }
 
+    h.off_run_modes = w.reserve(sizeof(RunMode) * (size_t)s->n_modes);
+    for (int i = 0; i < s->n_modes; i++) {
+        RunMode rm; std::memset(&rm, 0, sizeof rm);
+        const DevMode md = w.at<DevMode>(h.off_modes)[i];
+        const DevMapping mp = w.at<DevMapping>(h.off_mappings)[md.mapping];
+        const DevResidue& R = w.at<DevResidue>(h.off_residues)[mp.residue];
+        rm.rbegin = R.begin; rm.rend = R.end; rm.pshift = R.pshift; rm.stages = R.stages; rm.nclass = R.nclass; rm.ci_off = R.ci_off;
+        rm.residue = mp.residue; rm.floor = mp.floor; rm.n_coupling = mp.n_coupling; rm.mapping = md.mapping; rm.block_flag = md.block_flag; rm.rtype = R.type;
+        w.at<RunMode>(h.off_run_modes)[i] = rm;
+    }
+
     // windows (Mode.cs:24-67): one for the short size, four for the long size
     {
         std::vector<float> slope[2];
@@ -447,7 +459,7 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
               in(h.off_floors, sizeof(DevFloor1) * (uint64_t)h.n_floors) && in(h.off_residues, sizeof(DevResidue) * (uint64_t)h.n_residues) &&
               in(h.off_mappings, sizeof(DevMapping) * (uint64_t)h.n_mappings) && in(h.off_modes, sizeof(DevMode) * (uint64_t)h.n_modes) &&
               in(h.off_win_short, 4ull * h.bs[0]) && in(h.off_win_long, 16ull * h.bs[1]) && in(h.off_db, 1024) &&
-              h.ci_total >= 0 && in(h.off_ci, sizeof(CiRec) * (uint64_t)(h.ci_total > 0 ? h.ci_total : 1)) && in(h.off_bin2k, (uint64_t)h.n_floors * (h.bs[1] / 2)) &&
+              h.ci_total >= 0 && in(h.off_ci, sizeof(CiRec) * (uint64_t)(h.ci_total > 0 ? h.ci_total : 1)) && in(h.off_bin2k, (uint64_t)h.n_floors * (h.bs[1] / 2)) && in(h.off_run_modes, sizeof(RunMode) * (uint64_t)h.n_modes) &&
               (h.off_fused_tab == 0 || (in(h.off_fused_tab, 4ull * FusedTables::FLOATS) && h.bs[0] == FUSED_SHORT_N && h.bs[1] == FUSED_LONG_N));
     for (int i = 0; i < 2 && ok; i++)
         ok = in(h.off_mdct_a[i], 2ull * h.bs[i]) && in(h.off_mdct_b[i], 2ull * h.bs[i]) && in(h.off_mdct_c[i], 1ull * h.bs[i]) &&
@@ -500,6 +512,13 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
             if (ci.cnt < 0 || ci.entries < 0 || ci.off < 0 || ci.dshift < -1 || ci.dshift > 16 ||
                 (ci.cnt > 0 && ci.dshift >= 0 && (uint64_t)ci.off + ((uint64_t)ci.entries << ci.dshift) > h.n_vq)) return fail(err, NVB_ERR_DATA, "blob: residue %lld ci record", i);
         }
+    }
+    for (int i = 0; i < h.n_modes; i++) {
+        const RunMode& rm = S.run_modes[i];
+        const DevMapping& mp = S.mappings[S.modes[i].mapping];
+        const DevResidue& R = S.residues[mp.residue];
+        if (rm.mapping != S.modes[i].mapping || rm.residue != mp.residue || rm.floor != mp.floor || rm.n_coupling != mp.n_coupling || rm.rbegin != R.begin || rm.rend != R.end ||
+            rm.pshift != R.pshift || rm.stages != R.stages || rm.nclass != R.nclass || rm.ci_off != R.ci_off || rm.rtype != R.type) return fail(err, NVB_ERR_DATA, "blob: run mode %lld", i);
     }
     for (int i = 0; i < h.n_floors; i++) {
         const DevFloor1& f = S.floors[i];

@@ -61,6 +61,14 @@ struct DevResidue {
     uint8_t coded[NVB_MAX_CLASSES];                 // per class: bit s set <=> stage s codes entries (cnt > 0)
     int32_t ci_off, pad2;                           // k_spectrum_warp: start of this residue's (class, stage) records in its shared table
 };
+// k_spectrum_run: everything a frame's CTA needs to know about its mode in one 64-byte record (one load instead of the
+// mode -> mapping -> residue -> floor chain of dependent loads)
+struct alignas(16) RunMode {
+    int32_t rbegin, rend, pshift, stages;
+    int32_t nclass, ci_off, residue, floor;
+    int32_t n_coupling, mapping, block_flag, rtype;
+    int32_t pad[4];
+};
 struct DevMapping { int32_t n_coupling, floor, residue, pad; uint8_t mag[NVB_MAX_COUPLING], ang[NVB_MAX_COUPLING]; };
 struct DevMode    { int32_t block_flag, mapping; };
 
@@ -87,6 +95,7 @@ struct BlobHeader {
     int32_t ci_total;          // sum over residues of nclass * stages: size of the (class, stage) table
     uint64_t off_ci;           // CiRec[ci_total]
     uint64_t off_bin2k;        // uint8[n_floors][bs[1]/2]: sorted position of the last floor post with x <= bin
+    uint64_t off_run_modes;    // RunMode[n_modes]
 };
 
 // Resolved pointers handed to kernels by value.
@@ -99,7 +108,7 @@ struct DevSetup {
     const float2* tw[2]; const float2* fft[2];
     const float* db;
     const float* fused_tab;    // lane tables of the fused kernel, nullptr when the block sizes are not {256, 2048}
-    const CiRec* ci; const uint8_t* bin2k;
+    const CiRec* ci; const uint8_t* bin2k; const RunMode* run_modes;
 };
 
 // ---- per-frame plan built on the host from nvb_frame (ok frames only, in order) ----------------

@@ -723,8 +723,8 @@ __device__ __forceinline__ void inverse_couple_sel(float& m, float& a) {
     a = ap ? t : M;
 }
 
-template <int CT, int NT>
-__global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
+template <int CT, int NT, int MINB = 1536 / NT>
+__global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
     constexpr int NW = NT / 32;
     constexpr int RB = 8 / CT;                                              // bins per channel in one run
     NVB_DYN_SMEM(dyn_smem);
@@ -734,8 +734,8 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
     __shared__ RunSeg s_seg[CT][NVB_MAX_POSTS];                             // segment that starts at sorted position k
     __shared__ int s_adx[CT][NVB_MAX_POSTS];
     __shared__ unsigned long long s_mask[CT];                               // bit k: sorted position k starts a segment; 0 = no floor
-    __shared__ uint8_t s_coded[NVB_MAX_CLASSES];
     __shared__ int s_bad[2];
+    __shared__ int s_careful[CT];                                           // some segment of the channel needs the plain division / range clamp
 
     nvb_grid_dep_launch();
     nvb_grid_dep_wait();
@@ -743,38 +743,33 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
     if (f.kind != 0) return;
     const DevSetup& S = a.S;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const DevMode md = S.modes[f.mode];
-    const DevMapping& mp = S.mappings[md.mapping];
-    const DevResidue& R = S.residues[mp.residue];
-    const DevFloor1& F = S.floors[mp.floor];
+    const RunMode rm = S.run_modes[f.mode];
+    const DevMapping& mp = S.mappings[rm.mapping];
+    const DevFloor1& F = S.floors[rm.floor];
     const int N = f.n, n = N >> 1, span = CT * n;
-    const int st_n = R.stages > 0 ? R.stages : 1;
-    const int rbegin = R.begin, pshift = R.pshift, nclass = R.nclass;
+    const int stages = rm.stages, st_n = stages > 0 ? stages : 1;
+    const int rbegin = rm.rbegin, pshift = rm.pshift, nclass = rm.nclass;
     int P = 0;
-    if (f.res_decoded) { const int e = R.end < span ? R.end : span; const int nn = e - rbegin; P = nn > 0 ? nn >> pshift : 0; }   // Residue0.cs:122-127
-    CiRec* s_ci = reinterpret_cast<CiRec*>(dyn_smem);
-    uint32_t* s_base = reinterpret_cast<uint32_t*>(s_ci + S.ci_total);      // [stage][partition]: where the item's entries start
-    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_base + S.max_items);
+    if (f.res_decoded) { const int e = rm.rend < span ? rm.rend : span; const int nn = e - rbegin; P = nn > 0 ? nn >> pshift : 0; }   // Residue0.cs:122-127
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(dyn_smem);               // [stage][partition]: where the item's entries start
+    const CiRec* ci_tab = S.ci + rm.ci_off;                                 // (class, stage) records and class -> coded stages: setup tables, L1-resident
+    const uint8_t* coded = S.residues[rm.residue].coded;
     const uint8_t* cls = a.classes + f.classes_off;
     const uint16_t* ent = a.entries + f.entries_off;
-    const uint8_t* bin2k = S.bin2k + (size_t)mp.floor * (S.bs[1] >> 1);
+    const uint8_t* bin2k = S.bin2k + (size_t)rm.floor * (S.bs[1] >> 1);
 
     for (int i = t; i < 256; i += NT) s_db[i] = S.db[i];
-    for (int i = t; i < nclass * st_n; i += NT) s_ci[i] = S.ci[R.ci_off + i];
-    for (int i = t; i < nclass; i += NT) s_coded[i] = R.coded[i];
-    for (int p = t; p < P; p += NT) { const int cl = cls[p]; s_cls[p] = cl < nclass ? (uint8_t)cl : (uint8_t)255; }
     if (t < 2) s_bad[t] = 0;
     if (P > 0) for (uint32_t i = (uint32_t)t * 64u; i < f.entry_count; i += NT * 64u) prefetch_l1(ent + i);   // the frame's entries: 128 bytes per thread
-    __syncthreads();
 
     // ---- phase A
     if (warp == NW - 1 && P > 0) {
         uint32_t run = 0;
-        for (int st = 0; st < R.stages; st++) {
+        for (int st = 0; st < stages; st++) {
             for (int base = 0; base < P; base += 32) {
                 const int p = base + lane;
                 uint32_t c = 0;
-                if (p < P) { const int cl = s_cls[p]; if (cl != 255) c = (uint32_t)s_ci[cl * st_n + st].cnt; }
+                if (p < P) { const int cl = cls[p]; if (cl < nclass) c = (uint32_t)ci_tab[cl * st_n + st].cnt; }
                 uint32_t incl = c;
                 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
@@ -784,7 +779,7 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
         }
     }
     for (int c = warp; c < CT; c += NW) {
-        unsigned long long mask = 0ull;
+        unsigned long long mask = 0ull; int careful_any = 0;
         if ((f.exec_mask >> c) & 1u) {
             int count;
             const unsigned long long flags = floor1_unwrap_warp(F, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, lane, s_fy[c], count);
@@ -800,6 +795,7 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
                 }
                 mask = (((unsigned long long)m[1] << 32) | m[0]) | 1ull;
                 __syncwarp();
+                bool careful = false;                                       // some segment needs the plain division or leaves inverse_dB_table's range
                 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int k = lane + 32 * h;
@@ -817,11 +813,14 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
                             else r.m = ((unsigned long long)adx * (unsigned long long)adx * ady < (1ull << 32)) ? 0xffffffffu / (unsigned)adx + 1u : 0u;
                         }
                         s_seg[c][k] = r; s_adx[c][k] = adx;
+                        // y runs monotonically from y0 to y0 + dy: in range at both ends <=> in range everywhere
+                        if (r.x0 < n && (r.m == 0u || (unsigned)r.y0 > 255u || (unsigned)(r.y0 + r.dy) > 255u)) careful = true;
                     }
                 }
+                careful_any = __any_sync(0xffffffffu, careful);
             }
         }
-        if (lane == 0) s_mask[c] = mask;
+        if (lane == 0) { s_mask[c] = mask; s_careful[c] = careful_any; }
     }
     __syncthreads();
 
@@ -830,9 +829,9 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
     const uint32_t ecount = f.entry_count;
     const int pmask = (1 << pshift) - 1;
     const bool posts32 = F.n_posts <= 32;
-    unsigned long long fmask[CT];
+    unsigned long long fmask[CT]; bool careful[CT];
     #pragma unroll
-    for (int c = 0; c < CT; c++) fmask[c] = s_mask[c];
+    for (int c = 0; c < CT; c++) { fmask[c] = s_mask[c]; careful[c] = s_careful[c] != 0; }
     int bad_floor = 0, bad_entry = 0;
     for (int gi = t; gi < (span >> 3); gi += NT) {
         const int pos0 = gi << 3;
@@ -848,13 +847,13 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
         for (int k = 0; k < 8; k++) acc[k] = 0.f;
         const int q = pos0 - rbegin, p = q >> pshift;
         if (q >= 0 && p < P) {
-            const int cl = s_cls[p];
-            if (cl != 255) {
+            const int cl = cls[p];
+            if (cl < nclass) {
                 const int o = q & pmask;
-                unsigned casc = s_coded[cl];
+                unsigned casc = coded[cl];
                 while (casc) {
                     const int st = __ffs(casc) - 1; casc &= casc - 1;
-                    const CiRec ci = s_ci[cl * st_n + st];
+                    const CiRec ci = ci_tab[cl * st_n + st];
                     const uint32_t eb = s_base[st * P + p];
                     const float* tab = S.vq + ci.off;
                     if (ci.dshift >= 3) {                                   // the run lies inside one entry
@@ -906,7 +905,7 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
                 }
             }
         }
-        for (int i = mp.n_coupling - 1; i >= 0; --i) {                      // Mapping.cs:137-182
+        for (int i = rm.n_coupling - 1; i >= 0; --i) {                      // Mapping.cs:137-182
             const int m = mp.mag[i], an = mp.ang[i];
             if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
             if (CT == 2) {                                                  // (magnitude, angle) is (0, 1) or (1, 0)
@@ -924,6 +923,13 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
                 }
             }
         }
+        // per bin: mask of the sorted positions at or below the last post that is not beyond the bin
+        unsigned long long below[RB];
+        #pragma unroll
+        for (int b = 0; b < RB; b++) {
+            const unsigned kk = (unsigned)(kword >> (8 * b)) & 0xffu;
+            below[b] = posts32 ? (unsigned long long)(0xffffffffu >> (31 - kk)) : (0xffffffffffffffffull >> (63 - kk));
+        }
         #pragma unroll
         for (int c = 0; c < CT; c++) {
             if ((f.exec_mask >> c) & 1u) {                                  // Floor1.Apply, Floor1.cs:186-222
@@ -931,19 +937,23 @@ __global__ void __launch_bounds__(NT) k_spectrum_run(LaunchArgs a) {
                 if (M == 0ull) {
                     #pragma unroll
                     for (int b = 0; b < RB; b++) acc[b * CT + c] = 0.f;
+                } else if (!careful[c]) {
+                    #pragma unroll
+                    for (int b = 0; b < RB; b++) {
+                        // the segment's start: last active position at or below the bin's post (bit 0 is set)
+                        const int lo = posts32 ? 31 - __clz((int)((unsigned)M & (unsigned)below[b])) : 63 - __clzll((long long)(M & below[b]));
+                        const RunSeg r = s_seg[c][lo];
+                        const int sg = r.dy >> 31;                          // 0 or -1
+                        const int qq = (int)__umulhi((unsigned)((bin0 + b - r.x0) * ((r.dy ^ sg) - sg)), r.m);
+                        acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], s_db[r.y0 + ((qq ^ sg) - sg)]);
+                    }
                 } else {
                     #pragma unroll
                     for (int b = 0; b < RB; b++) {
-                        const int x = bin0 + b;
-                        const unsigned kk = (unsigned)(kword >> (8 * b)) & 0xffu;
-                        int lo;                                             // the segment's start: last active position at or below kk (bit 0 is set)
-                        if (posts32) lo = 31 - __clz((int)((unsigned)M & (0xffffffffu >> (31 - kk))));
-                        else lo = 63 - __clzll((long long)(M & (0xffffffffffffffffull >> (63 - kk))));
+                        const int lo = posts32 ? 31 - __clz((int)((unsigned)M & (unsigned)below[b])) : 63 - __clzll((long long)(M & below[b]));
                         const RunSeg r = s_seg[c][lo];
-                        const int num = (x - r.x0) * (r.dy < 0 ? -r.dy : r.dy);
-                        int qq;
-                        if (r.m != 0u) qq = (int)__umulhi((unsigned)num, r.m);
-                        else qq = num / s_adx[c][lo];
+                        const int num = (bin0 + b - r.x0) * (r.dy < 0 ? -r.dy : r.dy);
+                        const int qq = r.m != 0u ? (int)__umulhi((unsigned)num, r.m) : num / s_adx[c][lo];
                         int y = r.dy < 0 ? r.y0 - qq : r.y0 + qq;
                         if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
                         acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], s_db[y]);
@@ -1303,12 +1313,14 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
     if (a.S.spectrum_fast >= 3 && !no_planes && !force_planes) {
         const int C = a.S.channels;
         static const int nt = std::getenv("NVB_SPECTRUM_NT") ? std::atoi(std::getenv("NVB_SPECTRUM_NT")) : 128;
-        const size_t smem = (size_t)a.S.ci_total * sizeof(CiRec) + (size_t)a.S.max_items * sizeof(uint32_t) + (((size_t)a.S.max_items + 15) & ~size_t(15)) + 16;
+        const size_t smem = (size_t)a.S.max_items * sizeof(uint32_t) + 16;
         auto go = [&](auto kernel, int threads) -> int {
             if (smem > 40 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
             NVB_LAUNCH(kernel, a.n_frames, threads, smem, stream, a);
             return cudaGetLastError() == cudaSuccess ? 1 : -1;
         };
+        static const bool occ = std::getenv("NVB_SPECTRUM_OCC") != nullptr;                    // experiment: 32 registers, 16 CTAs per SM
+        if (occ && C == 2 && nt == 128) return go(k_spectrum_run<2, 128, 16>, 128);
         if (nt == 64) return C == 1 ? go(k_spectrum_run<1, 64>, 64) : C == 2 ? go(k_spectrum_run<2, 64>, 64) : C == 4 ? go(k_spectrum_run<4, 64>, 64) : go(k_spectrum_run<8, 64>, 64);
         if (nt == 128) return C == 1 ? go(k_spectrum_run<1, 128>, 128) : C == 2 ? go(k_spectrum_run<2, 128>, 128) : C == 4 ? go(k_spectrum_run<4, 128>, 128) : go(k_spectrum_run<8, 128>, 128);
         return C == 1 ? go(k_spectrum_run<1, 256>, 256) : C == 2 ? go(k_spectrum_run<2, 256>, 256) : C == 4 ? go(k_spectrum_run<4, 256>, 256) : go(k_spectrum_run<8, 256>, 256);
