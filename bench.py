@@ -262,7 +262,32 @@ def run_ours(args):
     ms_spec = timed(lambda i: dbatches[i % ROTATE].run_spectrum(spec_bufs[i % ROTATE].data_ptr(), stream), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the host-buffer C-ABI call: pinned inputs -> H2D -> kernels -> D2H of PCM ----
+    # ---- end to end through the host-buffer C-ABI calls: pinned inputs -> H2D -> kernels -> D2H of PCM, every step ----
+    # (a) nvb_decode_batch_begin / _end, two batches in flight (what a batching StreamDecoder does: unpack the next run of
+    #     packets while the previous one is on the GPU); (b) the synchronous nvb_decode_batch, one batch at a time
+    out_host2 = torch.empty(samples * C + 16, dtype=torch.float32).pin_memory()
+    outs = (out_host, out_host2)
+
+    host_begin_s = [0.0]
+
+    def pipelined(n, base):
+        for i in range(n):
+            tb = time.perf_counter()
+            ctx.decode_batch_begin(host_batches[(base + i) % ROTATE], capi.RUN_DEFAULT, outs[i & 1].data_ptr(), outs[i & 1].numel())
+            host_begin_s[0] += time.perf_counter() - tb
+            if i >= 1:
+                ctx.decode_batch_end()
+        if n >= 1:
+            ctx.decode_batch_end()
+
+    pipelined(args.warmup, 0)
+    sync_all()
+    host_begin_s[0] = 0.0
+    t0 = time.perf_counter()
+    pipelined(args.steps, args.warmup)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    sync_all()
     for i in range(args.warmup):
         ctx.decode_batch_ptr(host_batches[i % ROTATE], capi.RUN_DEFAULT, out_host.data_ptr(), out_host.numel())
     sync_all()
@@ -270,8 +295,18 @@ def run_ours(args):
     for i in range(args.steps):
         ctx.decode_batch_ptr(host_batches[i % ROTATE], capi.RUN_DEFAULT, out_host.data_ptr(), out_host.numel())
     torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_sync_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     sync_all()
+    # the PCIe ceiling of this box for the PCM read-back alone (pinned D2H copy of one step's output)
+    d_probe = pcm_bufs[0][: samples * C]
+    for _ in range(3):
+        out_host[: samples * C].copy_(d_probe, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        out_host[: samples * C].copy_(d_probe, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_gbs = 10 * samples * C * 4 / (time.perf_counter() - t0) / 1e9
 
     if rank == 0:
         frames_total = FRAMES_PER_STEP * world * args.steps
@@ -298,7 +333,10 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(host_batches[0].h2d_bytes),
                     "d2h_bytes_per_step": int(samples * C * 4), "ms_per_step": e2e_ms / args.steps,
-                    "api": "nvb_decode_batch (host buffers, pinned), per GPU"},
+                    "api": "nvb_decode_batch_begin/_end (host buffers, pinned, two batches in flight), per GPU",
+                    "sync_value": frames_total / (e2e_sync_ms * 1e-3), "sync_api": "nvb_decode_batch (one batch at a time)",
+                    "host_ms_in_begin_per_step": host_begin_s[0] * 1e3 / args.steps, "pcie_d2h_gbs_measured": d2h_gbs,
+                    "pcie_bound_frames_per_s": world * FRAMES_PER_STEP / (samples * C * 4 / (d2h_gbs * 1e9))},
             "gpu_launches": int(launches_per_step * args.steps),
             "kernels": {"k_spectrum_ms": ms_spec / args.steps, "k_imdct_fused_ms": imdct_ms, "step_ms": ms_step},
             "roofline": {"bound": "hbm", "kernel": "k_imdct_fused", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

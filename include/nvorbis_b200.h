@@ -223,6 +223,15 @@ int nvb_reset(nvb_ctx* ctx);
  * loop leave in the caller's buffer. */
 int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap, nvb_result* res);
 
+/* The same call split in two, so that a host which unpacks the next run of packets while the GPU works (the batching
+ * StreamDecoder.Read loop, StreamDecoder.cs:320-389) keeps PCIe busy in both directions: _begin enqueues the H2D copies,
+ * the kernels and the D2H copy into pcm_out and returns; _end waits for the OLDEST batch begun and reports it.  At most two
+ * batches may be in flight (a third _begin returns NVB_ERR_STATE); batches complete in the order they were begun and chain
+ * their overlap tails exactly like consecutive nvb_decode_batch calls (NVB_RUN_CONTINUE).  The batch arrays and pcm_out of a
+ * batch must stay alive and untouched until its _end; keep them in nvb_host_alloc memory for the copies to be asynchronous. */
+int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap);
+int nvb_decode_batch_end(nvb_ctx* ctx, nvb_result* res);
+
 /* Device-resident variant (pipelining / benchmarking): upload once, run many times.
  * `stream` is a cudaStream_t (NULL = default stream); d_pcm is a device pointer with room for
  * nvb_dbatch_samples()*channels floats.  nvb_dbatch_run only enqueues kernels.  With

@@ -86,7 +86,7 @@ assert FRAME_DTYPE.itemsize == 32
 EXPORTS = [
     "nvb_abi_version", "nvb_strerror", "nvb_last_error", "nvb_create", "nvb_destroy", "nvb_host_alloc", "nvb_host_free",
     "nvb_upload_setup", "nvb_setup_blob_size", "nvb_setup_blob_export", "nvb_setup_blob_import", "nvb_post_stride", "nvb_reset",
-    "nvb_decode_batch", "nvb_dbatch_create", "nvb_dbatch_samples", "nvb_dbatch_run", "nvb_dbatch_result", "nvb_dbatch_destroy",
+    "nvb_decode_batch", "nvb_decode_batch_begin", "nvb_decode_batch_end", "nvb_dbatch_create", "nvb_dbatch_samples", "nvb_dbatch_run", "nvb_dbatch_result", "nvb_dbatch_destroy",
     "nvb_dbatch_run_spectrum", "nvb_dbatch_run_imdct", "nvb_dbatch_spectrum_floats", "nvb_dbatch_launches",
 ]
 
@@ -117,6 +117,8 @@ def load_library(path: str | None = None):
     L.nvb_post_stride.argtypes = [vp]
     L.nvb_reset.argtypes = [vp]
     L.nvb_decode_batch.argtypes = [vp, C.POINTER(BatchStruct), i32, vp, sz, C.POINTER(ResultStruct)]
+    L.nvb_decode_batch_begin.argtypes = [vp, C.POINTER(BatchStruct), i32, vp, sz]
+    L.nvb_decode_batch_end.argtypes = [vp, C.POINTER(ResultStruct)]
     L.nvb_dbatch_create.argtypes = [vp, C.POINTER(BatchStruct), i32, C.POINTER(vp)]
     L.nvb_dbatch_samples.restype = i64; L.nvb_dbatch_samples.argtypes = [vp]
     L.nvb_dbatch_spectrum_floats.restype = i64; L.nvb_dbatch_spectrum_floats.argtypes = [vp]
@@ -350,6 +352,17 @@ class Context:
         rc = self.lib.nvb_decode_batch(self.handle, C.byref(batch.struct), flags, out.ctypes.data, out.size, C.byref(r))
         self._check(rc, "nvb_decode_batch")
         return out[: int(r.samples_per_channel) * self.channels], _result(r)
+
+    def decode_batch_begin(self, batch: HostBatch, flags: int, out_ptr: int, out_floats: int) -> None:
+        """nvb_decode_batch_begin: enqueue H2D + synthesis + D2H and return (up to two batches in flight; the batch's host
+        buffers must stay alive and untouched until its decode_batch_end)."""
+        self._check(self.lib.nvb_decode_batch_begin(self.handle, C.byref(batch.struct), flags, out_ptr, out_floats), "nvb_decode_batch_begin")
+
+    def decode_batch_end(self) -> Result:
+        """nvb_decode_batch_end: wait for the oldest batch in flight."""
+        r = ResultStruct()
+        self._check(self.lib.nvb_decode_batch_end(self.handle, C.byref(r)), "nvb_decode_batch_end")
+        return _result(r)
 
     def decode_batch_ptr(self, batch: HostBatch, flags: int, out_ptr: int, out_floats: int) -> Result:
         r = ResultStruct()

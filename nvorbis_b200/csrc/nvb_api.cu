@@ -15,6 +15,8 @@
 
 using namespace nvb;
 
+constexpr int NVB_CHUNKS = 4;            // frame ranges a large batch is pipelined in
+
 struct nvb_ctx {
     int device = 0;
     std::string err;
@@ -28,13 +30,19 @@ struct nvb_ctx {
     float* d_carry[2] = {nullptr, nullptr};
     int carry_cur = 0;
     cudaStream_t stream = nullptr;
-    // nvb_decode_batch pipelines chunks of a large batch over these: kernels of chunk k+1 run while the PCM of chunk k
-    // crosses PCIe
+    // nvb_decode_batch_begin: ctx->stream carries the uploads, chunk_stream[0] the kernels, chunk_stream[1] the PCM read-back
     cudaStream_t chunk_stream[2] = {nullptr, nullptr};
-    cudaEvent_t ev_inputs = nullptr, ev_spec[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    // reusable device staging of nvb_decode_batch
-    nvb_dbatch* staging = nullptr;
-    float* d_pcm = nullptr; size_t pcm_cap = 0;
+    // nvb_decode_batch_begin/_end: up to two batches in flight, each with its own device staging; a batch's completion
+    // (its last PCM read-back + the counters read-back) is one event on the read-back stream
+    struct Slot {
+        nvb_dbatch* staging = nullptr;
+        float* d_pcm = nullptr; size_t pcm_cap = 0;
+        cudaEvent_t ev_up[NVB_CHUNKS] = {}, ev_k[NVB_CHUNKS] = {}, ev_all = nullptr;
+        Counters* h_counters = nullptr;      // pinned
+        DevFrame* h_frames = nullptr; size_t h_frames_cap = 0;   // pinned copy of the plan: its upload must not block the host
+        int rc = NVB_OK;                     // failure detected while enqueuing (reported by _end)
+    } slot[2];
+    int head = 0, in_flight = 0;
 };
 
 struct nvb_dbatch {
@@ -54,6 +62,37 @@ struct nvb_dbatch {
 namespace {
 
 thread_local std::string g_err;
+
+#if !defined(NVB_CPU_SHIM)
+// NVB_TRACE=1: device-side timeline of nvb_decode_batch_begin/_end (timing events around every copy and kernel group),
+// printed to stderr by _end relative to the first event ever recorded.  Debugging aid for the copy/compute pipeline.
+struct Trace {
+    struct Mark { cudaEvent_t ev; const char* what; int batch, chunk; };
+    std::vector<Mark> marks; cudaEvent_t origin = nullptr; int batch = 0;
+    static bool on() { static const bool v = std::getenv("NVB_TRACE") != nullptr; return v; }
+    void mark(cudaStream_t st, const char* what, int chunk) {
+        if (!on()) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+        if (!origin) origin = e;
+        marks.push_back({e, what, batch, chunk});
+    }
+    void dump(int upto_batch) {
+        if (!on()) return;
+        size_t keep = 0;
+        for (size_t i = 0; i < marks.size(); i++) {
+            if (marks[i].batch > upto_batch) { marks[keep++] = marks[i]; continue; }
+            float ms = 0.f; cudaEventElapsedTime(&ms, origin, marks[i].ev);
+            std::fprintf(stderr, "[nvb trace] batch %d chunk %d %-12s %9.3f ms\n", marks[i].batch, marks[i].chunk, marks[i].what, ms);
+            if (marks[i].ev != origin) cudaEventDestroy(marks[i].ev);
+        }
+        marks.resize(keep);
+    }
+};
+Trace g_trace;
+#define NVB_TRACE_MARK(st, what, chunk) g_trace.mark((st), (what), (chunk))
+#else
+#define NVB_TRACE_MARK(st, what, chunk) ((void)0)
+#endif
 
 int set_err(nvb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg; else g_err = msg;
@@ -115,7 +154,8 @@ int install_blob(nvb_ctx* ctx, std::vector<unsigned char>&& blob) {
 }
 
 // Uploads a batch into `b` (buffers grow as needed) and plans it.
-int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags, cudaStream_t st, bool* defer_inputs = nullptr) {
+int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags, cudaStream_t st, bool* defer_inputs = nullptr,
+                 DevFrame** pinned = nullptr, size_t* pinned_cap = nullptr) {
     std::string err;
     int rc = plan_batch(ctx->host_blob.data(), batch, flags, ctx->carry, b->plan, err);
     if (rc != NVB_OK) return set_err(ctx, rc, err);
@@ -130,7 +170,16 @@ int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags,
     if ((rc = grow(ctx, b->d_spectrum, b->cap_spectrum, (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
     if (!b->fused && (rc = grow(ctx, b->d_blocks, b->cap_blocks, 2 * (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
     if (!b->d_counters) { size_t cap = 0; if ((rc = grow(ctx, b->d_counters, cap, 1)) != NVB_OK) return rc; }
-    if (nf) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_frames, b->plan.frames.data(), nf * sizeof(DevFrame), cudaMemcpyHostToDevice, st));
+    const DevFrame* plan_src = b->plan.frames.data();
+    if (pinned && nf) {                                                     // page-locked staging: the copy is truly asynchronous
+        if (*pinned_cap < nf) {
+            if (*pinned) { cudaFreeHost(*pinned); *pinned = nullptr; *pinned_cap = 0; }
+            if (cudaHostAlloc((void**)pinned, (nf + nf / 4 + 64) * sizeof(DevFrame), cudaHostAllocDefault) == cudaSuccess) *pinned_cap = nf + nf / 4 + 64;
+            else { cudaGetLastError(); *pinned = nullptr; }
+        }
+        if (*pinned) { std::memcpy(*pinned, b->plan.frames.data(), nf * sizeof(DevFrame)); plan_src = *pinned; }
+    }
+    if (nf) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_frames, plan_src, nf * sizeof(DevFrame), cudaMemcpyHostToDevice, st));
     if (defer_inputs) {
         // nvb_decode_batch uploads posts / classes / entries chunk by chunk when the batch is laid out sequentially
         *defer_inputs = *defer_inputs && b->fused && b->plan.sequential;
@@ -248,12 +297,15 @@ int nvb_create(int device, nvb_ctx** out) {
     ctx->device = device;
     DeviceGuard g(device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->chunk_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
-        e = cudaStreamCreateWithFlags(&ctx->chunk_stream[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_spec[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+        e = cudaEventCreateWithFlags(&ctx->slot[i].ev_all, cudaEventDisableTiming);
+        for (int k = 0; k < NVB_CHUNKS && e == cudaSuccess; k++) {
+            e = cudaEventCreateWithFlags(&ctx->slot[i].ev_up[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot[i].ev_k[k], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->slot[i].h_counters, sizeof(Counters), cudaHostAllocDefault);
     }
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate / cudaEventCreate"); }
     *out = ctx;
     return NVB_OK;
@@ -262,12 +314,17 @@ int nvb_create(int device, nvb_ctx** out) {
 int nvb_destroy(nvb_ctx* ctx) {
     if (!ctx) return NVB_OK;
     DeviceGuard g(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    free_dbatch(ctx->staging);
-    cudaFree(ctx->d_pcm); cudaFree(ctx->d_blob); cudaFree(ctx->d_carry[0]); cudaFree(ctx->d_carry[1]);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_blob); cudaFree(ctx->d_carry[0]); cudaFree(ctx->d_carry[1]);
     cudaStreamDestroy(ctx->stream);
-    for (int i = 0; i < 2; i++) { cudaStreamDestroy(ctx->chunk_stream[i]); cudaEventDestroy(ctx->ev_spec[i]); cudaEventDestroy(ctx->ev_done[i]); }
-    cudaEventDestroy(ctx->ev_inputs);
+    for (int i = 0; i < 2; i++) {
+        cudaStreamDestroy(ctx->chunk_stream[i]);
+        free_dbatch(ctx->slot[i].staging); cudaFree(ctx->slot[i].d_pcm);
+        cudaEventDestroy(ctx->slot[i].ev_all);
+        for (int k = 0; k < NVB_CHUNKS; k++) { cudaEventDestroy(ctx->slot[i].ev_up[k]); cudaEventDestroy(ctx->slot[i].ev_k[k]); }
+        if (ctx->slot[i].h_counters) cudaFreeHost(ctx->slot[i].h_counters);
+        if (ctx->slot[i].h_frames) cudaFreeHost(ctx->slot[i].h_frames);
+    }
     delete ctx;
     return NVB_OK;
 }
@@ -323,80 +380,120 @@ int nvb_post_stride(nvb_ctx* ctx) {
 
 int nvb_reset(nvb_ctx* ctx) {
     if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
+    if (ctx->in_flight > 0) return set_err(ctx, NVB_ERR_STATE, "batches in flight");
     ctx->carry = CarryState();
     return NVB_OK;
 }
 
-int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap, nvb_result* res) {
+int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap) {
     if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
     if (!ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
+    if (ctx->in_flight >= 2) return set_err(ctx, NVB_ERR_STATE, "two batches are already in flight: call nvb_decode_batch_end first");
     DeviceGuard g(ctx->device);
-    if (!ctx->staging) { ctx->staging = new (std::nothrow) nvb_dbatch(); if (!ctx->staging) return set_err(ctx, NVB_ERR_NOMEM, "host allocation failed"); }
-    nvb_dbatch* b = ctx->staging;
+    nvb_ctx::Slot& sl = ctx->slot[(ctx->head + ctx->in_flight) & 1];
+    if (!sl.staging) { sl.staging = new (std::nothrow) nvb_dbatch(); if (!sl.staging) return set_err(ctx, NVB_ERR_NOMEM, "host allocation failed"); }
+    nvb_dbatch* b = sl.staging;
     static const int chunk_min = std::getenv("NVB_CHUNK_MIN") ? std::atoi(std::getenv("NVB_CHUNK_MIN")) : 1024;   // test hook
+    // Three in-order streams, one per engine: uploads (ctx->stream), kernels, PCM read-back.  A large batch is cut into
+    // chunks of frames; chunk k's kernels wait for its inputs, its read-back for its kernels, so the PCM of chunk k crosses
+    // PCIe while chunk k+1 computes and the next batch's inputs go up.  Kernels of consecutive chunks and batches run in
+    // stream order, which is all the overlap tail (halo block, carried block) needs.
+    cudaStream_t st_up = ctx->stream, st_k = ctx->chunk_stream[0], st_down = ctx->chunk_stream[1];
+#if !defined(NVB_CPU_SHIM)
+    g_trace.batch++;
+#endif
+    NVB_TRACE_MARK(st_up, "begin", -1);
     bool chunked_inputs = batch && batch->n_frames >= chunk_min && batch->n_frames >= 8;
-    int rc = upload_batch(ctx, b, batch, flags, ctx->stream, &chunked_inputs);
-    if (rc != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+    int rc = upload_batch(ctx, b, batch, flags, st_up, &chunked_inputs, &sl.h_frames, &sl.h_frames_cap);
+    if (rc != NVB_OK) { cudaStreamSynchronize(st_up); return rc; }
     const size_t n_out = (size_t)b->plan.samples * ctx->H.channels;
-    if (n_out > pcm_cap || (n_out > 0 && !pcm_out)) { cudaStreamSynchronize(ctx->stream); return set_err(ctx, NVB_ERR_CAPACITY, "pcm_out too small for the batch"); }
-    if ((rc = grow(ctx, ctx->d_pcm, ctx->pcm_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+    if (n_out > pcm_cap || (n_out > 0 && !pcm_out)) { cudaStreamSynchronize(st_up); return set_err(ctx, NVB_ERR_CAPACITY, "pcm_out too small for the batch"); }
+    if ((rc = grow(ctx, sl.d_pcm, sl.pcm_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(st_up); return rc; }
     const int nf = (int)b->plan.frames.size();
-    const int n_chunks = (b->fused && nf >= chunk_min && nf >= 8) ? 4 : 1;
+    const int n_chunks = (chunked_inputs && nf >= chunk_min && nf >= 8) ? NVB_CHUNKS : 1;
     if (n_chunks == 1 && chunked_inputs) {                                  // few decoded frames after all: upload everything now
         const size_t n_posts = (size_t)batch->n_frames * ctx->H.channels * ctx->H.post_stride;
-        if (n_posts) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts, batch->posts, n_posts * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-        if (batch->n_classes) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_classes, batch->classes, (size_t)batch->n_classes, cudaMemcpyHostToDevice, ctx->stream));
-        if (batch->n_entries) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_entries, batch->entries, (size_t)batch->n_entries * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_posts) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts, batch->posts, n_posts * sizeof(int16_t), cudaMemcpyHostToDevice, st_up));
+        if (batch->n_classes) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_classes, batch->classes, (size_t)batch->n_classes, cudaMemcpyHostToDevice, st_up));
+        if (batch->n_entries) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_entries, batch->entries, (size_t)batch->n_entries * sizeof(uint16_t), cudaMemcpyHostToDevice, st_up));
         chunked_inputs = false;
     }
-    if (n_chunks == 1) {
-        rc = enqueue(ctx, b, 0, nullptr, ctx->d_pcm, true, ctx->stream);
-        if (rc != NVB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
-        if (n_out) NVB_CUDA(ctx, cudaMemcpyAsync(pcm_out, ctx->d_pcm, n_out * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    } else {
-        // Pipeline: inputs up (one copy), then per chunk of frames: spectrum + synthesis kernels and the D2H of that chunk's
-        // PCM range, chunks alternating between two streams so that kernels overlap the previous chunk's PCIe transfer.
-        // A chunk's first block overlaps onto the last block of the previous chunk, whose spectrum the previous chunk's
-        // stream produces: one event per chunk orders exactly that.
-        NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), ctx->stream));
-        NVB_CUDA(ctx, cudaEventRecord(ctx->ev_inputs, ctx->stream));
-        const size_t C = (size_t)ctx->H.channels;
-        for (int k = 0; k < n_chunks; k++) {
-            cudaStream_t st = ctx->chunk_stream[k & 1];
-            const int lo = (int)((long long)nf * k / n_chunks), hi = (int)((long long)nf * (k + 1) / n_chunks);
-            NVB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_inputs, 0));
-            if (chunked_inputs) {
-                // this chunk's share of the inputs: the api frames from the chunk's first decoded block up to the next chunk's
-                const int a0 = k == 0 ? 0 : b->plan.frames[(size_t)lo].api_index;
-                const int a1 = k + 1 == n_chunks ? batch->n_frames : b->plan.frames[(size_t)hi].api_index;
-                auto first_off = [&](int from, int64_t& c_off, int64_t& e_off) {
-                    c_off = batch->n_classes; e_off = batch->n_entries;
-                    for (int i = from; i < batch->n_frames; i++)
-                        if (batch->frames[i].status == NVB_FRAME_OK && batch->frames[i].res_decoded) { c_off = batch->frames[i].classes_off; e_off = batch->frames[i].entries_off; break; }
-                };
-                int64_t c0, e0, c1, e1;
-                first_off(a0, c0, e0);
-                if (k + 1 == n_chunks) { c1 = batch->n_classes; e1 = batch->n_entries; } else first_off(a1, c1, e1);
-                if (k == 0) { c0 = 0; e0 = 0; }
-                const size_t row = (size_t)ctx->H.channels * ctx->H.post_stride;
-                if (a1 > a0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts + (size_t)a0 * row, batch->posts + (size_t)a0 * row, (size_t)(a1 - a0) * row * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-                if (c1 > c0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_classes + c0, batch->classes + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
-                if (e1 > e0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_entries + e0, batch->entries + e0, (size_t)(e1 - e0) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-            }
-            rc = enqueue(ctx, b, 0, nullptr, ctx->d_pcm, true, st, lo, hi - lo, false, ctx->ev_spec[k & 1], k > 0 ? ctx->ev_spec[(k - 1) & 1] : nullptr);
-            if (rc != NVB_OK) { cudaDeviceSynchronize(); return rc; }
-            const size_t s0 = (size_t)b->plan.frames[(size_t)lo].pcm_off * C;
-            const size_t s1 = hi < nf ? (size_t)b->plan.frames[(size_t)hi].pcm_off * C : n_out;
-            if (s1 > s0) NVB_CUDA(ctx, cudaMemcpyAsync(pcm_out + s0, ctx->d_pcm + s0, (s1 - s0) * sizeof(float), cudaMemcpyDeviceToHost, st));
-            NVB_CUDA(ctx, cudaEventRecord(ctx->ev_done[k & 1], st));
+    NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), st_k));
+    const size_t C = (size_t)ctx->H.channels;
+    for (int k = 0; k < n_chunks; k++) {
+        const int lo = (int)((long long)nf * k / n_chunks), hi = (int)((long long)nf * (k + 1) / n_chunks);
+        NVB_TRACE_MARK(st_up, "h2d_begin", k);
+        if (chunked_inputs) {
+            // this chunk's share of the inputs: the api frames from the chunk's first decoded block up to the next chunk's
+            const int a0 = k == 0 ? 0 : b->plan.frames[(size_t)lo].api_index;
+            const int a1 = k + 1 == n_chunks ? batch->n_frames : b->plan.frames[(size_t)hi].api_index;
+            auto first_off = [&](int from, int64_t& c_off, int64_t& e_off) {
+                c_off = batch->n_classes; e_off = batch->n_entries;
+                for (int i = from; i < batch->n_frames; i++)
+                    if (batch->frames[i].status == NVB_FRAME_OK && batch->frames[i].res_decoded) { c_off = batch->frames[i].classes_off; e_off = batch->frames[i].entries_off; break; }
+            };
+            int64_t c0, e0, c1, e1;
+            first_off(a0, c0, e0);
+            if (k + 1 == n_chunks) { c1 = batch->n_classes; e1 = batch->n_entries; } else first_off(a1, c1, e1);
+            if (k == 0) { c0 = 0; e0 = 0; }
+            const size_t row = (size_t)ctx->H.channels * ctx->H.post_stride;
+            if (a1 > a0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts + (size_t)a0 * row, batch->posts + (size_t)a0 * row, (size_t)(a1 - a0) * row * sizeof(int16_t), cudaMemcpyHostToDevice, st_up));
+            if (c1 > c0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_classes + c0, batch->classes + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st_up));
+            if (e1 > e0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_entries + e0, batch->entries + e0, (size_t)(e1 - e0) * sizeof(uint16_t), cudaMemcpyHostToDevice, st_up));
         }
-        for (int i = 0; i < 2; i++) NVB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_done[i], 0));
+        NVB_CUDA(ctx, cudaEventRecord(sl.ev_up[k], st_up));
+        NVB_CUDA(ctx, cudaStreamWaitEvent(st_k, sl.ev_up[k], 0));
+        NVB_TRACE_MARK(st_k, "kernels_begin", k);
+        rc = enqueue(ctx, b, 0, nullptr, sl.d_pcm, true, st_k, n_chunks == 1 ? 0 : lo, n_chunks == 1 ? -1 : hi - lo, false);
+        if (rc != NVB_OK) { cudaDeviceSynchronize(); return rc; }
+        NVB_CUDA(ctx, cudaEventRecord(sl.ev_k[k], st_k));
+        NVB_CUDA(ctx, cudaStreamWaitEvent(st_down, sl.ev_k[k], 0));
+        NVB_TRACE_MARK(st_down, "d2h_begin", k);
+        if (nf > 0) {
+            const size_t s0 = (size_t)b->plan.frames[(size_t)lo].pcm_off * C;
+            const size_t s1 = (n_chunks > 1 && hi < nf) ? (size_t)b->plan.frames[(size_t)hi].pcm_off * C : n_out;
+            if (s1 > s0) NVB_CUDA(ctx, cudaMemcpyAsync(pcm_out + s0, sl.d_pcm + s0, (s1 - s0) * sizeof(float), cudaMemcpyDeviceToHost, st_down));
+        }
+        NVB_TRACE_MARK(st_down, "d2h_end", k);
     }
-    rc = fetch_result(ctx, b, ctx->stream, res);
-    // the decoder state advances like StreamDecoder's even when an entry was out of range
+    std::memset(sl.h_counters, 0, sizeof(Counters));
+    if (!b->plan.frames.empty()) NVB_CUDA(ctx, cudaMemcpyAsync(sl.h_counters, b->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, st_down));
+    NVB_CUDA(ctx, cudaEventRecord(sl.ev_all, st_down));
+    // the decoder state advances like StreamDecoder's (also when an entry turns out to be out of range)
     ctx->carry = b->plan.end_state;
     if (b->plan.last_ok >= 0) ctx->carry_cur ^= 1;
-    return rc;
+    ctx->in_flight++;
+    return NVB_OK;
+}
+
+int nvb_decode_batch_end(nvb_ctx* ctx, nvb_result* res) {
+    if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
+    if (ctx->in_flight <= 0) return set_err(ctx, NVB_ERR_STATE, "no batch in flight");
+    DeviceGuard g(ctx->device);
+    nvb_ctx::Slot& sl = ctx->slot[ctx->head];
+    ctx->head ^= 1; ctx->in_flight--;
+    NVB_CUDA(ctx, cudaEventSynchronize(sl.ev_all));
+#if !defined(NVB_CPU_SHIM)
+    g_trace.dump(g_trace.batch - ctx->in_flight);
+#endif
+    nvb_dbatch* b = sl.staging;
+    const Counters c = *sl.h_counters;
+    if (res) {
+        res->samples_per_channel = b->plan.samples;
+        res->has_clipped = c.clipped ? 1 : 0;
+        res->n_failed = b->plan.n_failed;
+        res->n_floor_range = c.floor_range;
+        res->n_inconsistent = b->plan.n_inconsistent;
+    }
+    if (c.bad_entry) return set_err(ctx, NVB_ERR_DATA, "a VQ entry number is outside its codebook (Codebook.cs:322 would throw)");
+    return NVB_OK;
+}
+
+int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap, nvb_result* res) {
+    if (ctx && ctx->in_flight > 0) return set_err(ctx, NVB_ERR_STATE, "batches begun with nvb_decode_batch_begin are still in flight");
+    const int rc = nvb_decode_batch_begin(ctx, batch, flags, pcm_out, pcm_cap);
+    if (rc != NVB_OK) return rc;
+    return nvb_decode_batch_end(ctx, res);
 }
 
 int nvb_dbatch_create(nvb_ctx* ctx, const nvb_batch* batch, int flags, nvb_dbatch** out) {

@@ -200,3 +200,33 @@ def test_slot_ring_wraps_with_mixed_windows(shim):
     # the same batch through nvb_decode_batch's chunked copy/compute pipeline (four frame ranges, halo across chunk edges)
     env = dict(os.environ, NVB_SHIM_SMS="2", NVB_CHUNK_MIN="16")
     assert subprocess.check_output([sys.executable, "-c", code], env=env, timeout=600).decode().strip().endswith("ok")
+
+
+def test_begin_end_pipeline_matches_sync(shim):
+    """nvb_decode_batch_begin/_end with two batches in flight: the same PCM as consecutive nvb_decode_batch calls,
+    tails chained across the batches; a third begin is refused."""
+    r, pcm, b, ctx = _ctx(shim, "1test")
+    n = len(b.frames)
+    cuts = [0, 5, 9, 16, n]
+    hbs = [H.batch_from_boundary(b, ctx.post_stride, cuts[i], cuts[i + 1]) for i in range(4)]
+    outs = [np.zeros(capi.sum_output_bound(hb.frames) + 64, np.float32) for hb in hbs]
+    got, pending = [], []
+    for i, hb in enumerate(hbs):
+        ctx.decode_batch_begin(hb, capi.RUN_EXACT | (capi.RUN_CONTINUE if i else 0), outs[i].ctypes.data, outs[i].size)
+        pending.append(i)
+        if len(pending) == 2:
+            if i == 1:
+                with pytest.raises(capi.NvbError) as e:
+                    ctx.decode_batch_begin(hbs[2], capi.RUN_EXACT | capi.RUN_CONTINUE, outs[2].ctypes.data, outs[2].size)
+                assert e.value.status == capi.ERR_STATE
+            j = pending.pop(0)
+            res = ctx.decode_batch_end()
+            got.append(outs[j][: res.samples_per_channel].copy())
+    while pending:
+        j = pending.pop(0)
+        res = ctx.decode_batch_end()
+        got.append(outs[j][: res.samples_per_channel].copy())
+    np.testing.assert_array_equal(np.concatenate(got), pcm)
+    with pytest.raises(capi.NvbError) as e:
+        ctx.decode_batch_end()
+    assert e.value.status == capi.ERR_STATE

@@ -232,3 +232,34 @@ def test_generic_spectrum_kernel_on_gpu():
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_begin_end_pipeline_matches_sync_on_gpu():
+    """Two batches in flight through nvb_decode_batch_begin/_end (chunked copy/compute pipeline inside each): bit-identical
+    to the synchronous call, tails chained from batch to batch."""
+    r, pcm, b = H.decoded("3test")
+    ctx = capi.Context(0)
+    ctx.upload_setup(H.setup_from_oracle(r))
+    n = len(b.frames)
+    cuts = [0, 90, 91, 200, 290, n]
+    hbs = [H.batch_from_boundary(b, ctx.post_stride, cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+    want = []
+    for i, hb in enumerate(hbs):
+        out, _ = ctx.decode_batch(hb, capi.RUN_DEFAULT | (capi.RUN_CONTINUE if i else 0))
+        want.append(out.copy())
+    ctx.reset()
+    outs = [np.zeros((capi.sum_output_bound(hb.frames) + 64) * 2, np.float32) for hb in hbs]
+    got, pending, clipped = [], [], False
+    for i, hb in enumerate(hbs):
+        ctx.decode_batch_begin(hb, capi.RUN_DEFAULT | (capi.RUN_CONTINUE if i else 0), outs[i].ctypes.data, outs[i].size)
+        pending.append(i)
+        if len(pending) == 2:
+            j = pending.pop(0); res = ctx.decode_batch_end(); clipped |= res.has_clipped
+            got.append(outs[j][: res.samples_per_channel * 2].copy())
+    while pending:
+        j = pending.pop(0); res = ctx.decode_batch_end(); clipped |= res.has_clipped
+        got.append(outs[j][: res.samples_per_channel * 2].copy())
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+    assert clipped and float(np.abs(np.concatenate(got) - pcm).max()) <= TOL
+    ctx.close()
