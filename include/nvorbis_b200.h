@@ -5,6 +5,7 @@
  *     Residue0/1/2.WriteVectors  `res[o] += book[entry,dim]`   Residue0.cs:180-201, Residue1.cs:8-26, Residue2.cs:23-47
  *     inverse channel coupling                                  Mapping.cs:137-182
  *     Floor1.Apply (UnwrapPosts + RenderLineMulti)              Floor1.cs:186-341
+ *     Floor0.Apply (LSP -> bark-band curve)                     Floor0.cs:152-212
  *     Mdct.Reverse                                              Mdct.cs:13-21,65-535
  *     window multiply                                           Mode.cs:159-166
  *     OverlapBuffers / ClippingCopyBuffer / CopyBuffer          StreamDecoder.cs:391-415,532-541
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVB_ABI_VERSION 1
+#define NVB_ABI_VERSION 2
 
 #define NVB_MAX_CHANNELS   8     /* reference allows 255 (StreamDecoder.cs:186); larger -> NVB_ERR_UNSUPPORTED */
 #define NVB_MAX_POSTS      64    /* Floor1.Data.Posts = new int[64]            (Floor1.cs:12)   */
@@ -75,10 +76,22 @@ typedef struct nvb_floor1 {
     uint8_t  sort_idx[NVB_MAX_POSTS];   /* _sortIdx                  :118-132 */
 } nvb_floor1;
 
+/* Floor type 0 parameters (Floor0.Init, Floor0.cs:28-65).  The library derives the bark map and the 2*cos map per block
+ * size itself (SynthesizeBarkCurve / SynthesizeWDelMap, Floor0.cs:67-96, same float/double expression order). */
+typedef struct nvb_floor0 {
+    int32_t order;                      /* _order (1..255)  */
+    int32_t rate;                       /* _rate            */
+    int32_t bark_map_size;              /* _bark_map_size   */
+    int32_t amp_bits;                   /* _ampBits (used by the host's Unpack only) */
+    int32_t amp_ofs;                    /* _ampOfs          */
+    int32_t reserved[3];
+} nvb_floor0;
+
 typedef struct nvb_floor {
-    int32_t type;                       /* 1 = Floor1.  0 = Floor0: not yet accepted (NVB_ERR_UNSUPPORTED) */
+    int32_t type;                       /* 1 = Floor1 (f1), 0 = Floor0 (f0)  (Factory.cs:22-31) */
     int32_t reserved;
     nvb_floor1 f1;
+    nvb_floor0 f0;
 } nvb_floor;
 
 /* Residue tables (Residue0.Init, Residue0.cs:35-117) */
@@ -159,6 +172,11 @@ typedef struct nvb_frame {
 /* Floor payload: posts[frame][channel][nvb_post_stride()] int16; element 0 = PostCount (0 = floor
  * unused or unpack failed, Floor1.cs:140,155-174), elements 1.. = raw Posts[] as unpacked (before
  * UnwrapPosts).  nvb_post_stride() = 2 + max n_posts over the setup's floors, rounded up to even. */
+/* Floor type 0 payload (only read for packets whose mapping uses a type 0 floor; may be NULL otherwise):
+ * floor0[frame][channel][nvb_floor0_stride()] floats; element 0 = Data.Amp as Floor0.Unpack leaves it (Floor0.cs:107-114:
+ * raw / ampDiv * ampOfs, or 0 when the floor is unused / the unpack failed), elements 1 .. order = Data.Coeff after the
+ * "averaging" pass (Floor0.cs:136-147).  nvb_floor0_stride() = 1 + max order over the setup's type 0 floors, rounded up
+ * to even (0 when the setup has none). */
 typedef struct nvb_batch {
     int32_t          n_frames;
     int32_t          reserved;
@@ -166,6 +184,7 @@ typedef struct nvb_batch {
     const int16_t*   posts;
     const uint8_t*   classes;   int64_t n_classes;
     const uint16_t*  entries;   int64_t n_entries;
+    const float*     floor0;
 } nvb_batch;
 
 typedef struct nvb_result {
@@ -203,8 +222,9 @@ int nvb_host_alloc(size_t bytes, void** out);
 int nvb_host_free(void* p);
 
 /* Uploads the immutable per-stream tables.  Replaces what StreamDecoder.LoadBooks leaves behind
- * (StreamDecoder.cs:226-289).  NVB_ERR_UNSUPPORTED: channels > NVB_MAX_CHANNELS, Floor0,
- * multi-submap mappings, > NVB_MAX_COUPLING steps, residue books with > 65536 entries. */
+ * (StreamDecoder.cs:226-289).  NVB_ERR_UNSUPPORTED: channels > NVB_MAX_CHANNELS, multi-submap mappings,
+ * > NVB_MAX_COUPLING steps, residue books with > 65536 entries, a type 0 floor whose bark map indexes past its cos map
+ * (Floor0.cs:166 would throw IndexOutOfRangeException on every packet). */
 int nvb_upload_setup(nvb_ctx* ctx, const nvb_setup* setup);
 
 /* Serialises the uploaded setup's device tables into one blob / installs such a blob, so that one
@@ -214,6 +234,7 @@ int nvb_setup_blob_export(nvb_ctx* ctx, void* dst, size_t bytes);
 int nvb_setup_blob_import(nvb_ctx* ctx, const void* src, size_t bytes);
 
 int nvb_post_stride(nvb_ctx* ctx);
+int nvb_floor0_stride(nvb_ctx* ctx);
 
 /* ResetDecoder (StreamDecoder.cs:295-305): forget the overlap tail. */
 int nvb_reset(nvb_ctx* ctx);

@@ -8,8 +8,8 @@
  *   container -> packets          Ogg/PageReaderBase.cs, Ogg/PageReader.cs, Ogg/PacketProvider.cs
  *   setup headers -> nvb_setup    StreamDecoder.cs:179-289, Codebook.cs:59-292, Floor1.cs:30-133,
  *                                 Residue0.cs:35-117, Residue2.cs:10-14, Mapping.cs:16-93, Mode.cs:24-67
- *   audio packet -> nvb_frame     StreamDecoder.cs:465-530, Mode.cs:119-151 (GetPacketInfo), Floor1.cs:135-184
- *                                 (Unpack), Mapping.cs:95-134 (ExecuteChannel / ForceEnergy), Residue0.cs:119-178
+ *   audio packet -> nvb_frame     StreamDecoder.cs:465-530, Mode.cs:119-151 (GetPacketInfo), Floor1.cs:135-184 /
+ *                                 Floor0.cs:98-150 (Unpack), Mapping.cs:95-134 (ExecuteChannel / ForceEnergy), Residue0.cs:119-178
  *                                 (class words + VQ entry numbers, Codebook.DecodeScalar Codebook.cs:294-320)
  *   EOS trim of the last block    StreamDecoder.cs:429-437
  *
@@ -37,7 +37,7 @@ typedef struct nvh_info {
     int64_t n_audio_packets;       /* packets after the setup header */
     int64_t last_granule;          /* granule position of the last packet that carries one, -1 if none */
     int32_t has_eos;               /* the container flagged an end-of-stream page that was kept (Ogg/StreamPageReader.cs:72-75) */
-    int32_t reserved;
+    int32_t floor0_stride;         /* floats per (frame, channel) in nvb_batch.floor0 (same rule as nvb_floor0_stride()), 0 = no type 0 floor */
 } nvh_info;
 
 /* nvh_open_ogg: `VorbisReader(Stream)` on an in-memory seekable stream, first logical stream only.

@@ -12,7 +12,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CHANNELS, MAX_POSTS, MAX_CLASSES, MAX_STAGES, MAX_COUPLING = 8, 64, 64, 8, 32
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_STATE, ERR_CAPACITY, ERR_DATA = 0, -1, -2, -3, -4, -5, -6, -7
@@ -39,8 +39,13 @@ class Floor1(C.Structure):
                 ("sort_idx", C.c_uint8 * MAX_POSTS)]
 
 
+class Floor0(C.Structure):
+    _fields_ = [("order", C.c_int32), ("rate", C.c_int32), ("bark_map_size", C.c_int32), ("amp_bits", C.c_int32), ("amp_ofs", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
+
+
 class Floor(C.Structure):
-    _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("f1", Floor1)]
+    _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("f1", Floor1), ("f0", Floor0)]
 
 
 class Residue(C.Structure):
@@ -69,7 +74,7 @@ class SetupStruct(C.Structure):
 
 class BatchStruct(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("reserved", C.c_int32), ("frames", C.c_void_p), ("posts", C.c_void_p),
-                ("classes", C.c_void_p), ("n_classes", C.c_int64), ("entries", C.c_void_p), ("n_entries", C.c_int64)]
+                ("classes", C.c_void_p), ("n_classes", C.c_int64), ("entries", C.c_void_p), ("n_entries", C.c_int64), ("floor0", C.c_void_p)]
 
 
 class ResultStruct(C.Structure):
@@ -85,7 +90,7 @@ assert FRAME_DTYPE.itemsize == 32
 
 EXPORTS = [
     "nvb_abi_version", "nvb_strerror", "nvb_last_error", "nvb_create", "nvb_destroy", "nvb_host_alloc", "nvb_host_free",
-    "nvb_upload_setup", "nvb_setup_blob_size", "nvb_setup_blob_export", "nvb_setup_blob_import", "nvb_post_stride", "nvb_reset",
+    "nvb_upload_setup", "nvb_setup_blob_size", "nvb_setup_blob_export", "nvb_setup_blob_import", "nvb_post_stride", "nvb_floor0_stride", "nvb_reset",
     "nvb_decode_batch", "nvb_decode_batch_begin", "nvb_decode_batch_end", "nvb_dbatch_create", "nvb_dbatch_samples", "nvb_dbatch_run", "nvb_dbatch_result", "nvb_dbatch_destroy",
     "nvb_dbatch_run_spectrum", "nvb_dbatch_run_imdct", "nvb_dbatch_spectrum_floats", "nvb_dbatch_launches",
 ]
@@ -115,6 +120,7 @@ def load_library(path: str | None = None):
     L.nvb_setup_blob_export.argtypes = [vp, vp, sz]
     L.nvb_setup_blob_import.argtypes = [vp, vp, sz]
     L.nvb_post_stride.argtypes = [vp]
+    L.nvb_floor0_stride.argtypes = [vp]
     L.nvb_reset.argtypes = [vp]
     L.nvb_decode_batch.argtypes = [vp, C.POINTER(BatchStruct), i32, vp, sz, C.POINTER(ResultStruct)]
     L.nvb_decode_batch_begin.argtypes = [vp, C.POINTER(BatchStruct), i32, vp, sz]
@@ -164,6 +170,9 @@ class Setup:
                 for k in range(min(n, MAX_POSTS)):
                     fl.f1.x_list[k] = int(f["x_list"][k]); fl.f1.l_neigh[k] = int(f["l_neigh"][k])
                     fl.f1.h_neigh[k] = int(f["h_neigh"][k]); fl.f1.sort_idx[k] = int(f["sort_idx"][k])
+            elif fl.type == 0:
+                fl.f0.order, fl.f0.rate, fl.f0.bark_map_size = int(f["order"]), int(f["rate"]), int(f["bark_map_size"])
+                fl.f0.amp_bits, fl.f0.amp_ofs = int(f["amp_bits"]), int(f["amp_ofs"])
             self._floors[i] = fl
         self._residues = (Residue * max(len(residues), 1))()
         for i, r in enumerate(residues):
@@ -225,7 +234,8 @@ def _result(r: ResultStruct) -> Result:
 class HostBatch:
     """The four host arrays of an nvb_batch (kept alive while the struct is in use)."""
 
-    def __init__(self, frames, posts, classes, entries):
+    def __init__(self, frames, posts, classes, entries, floor0=None):
+        self.floor0 = None if floor0 is None else np.ascontiguousarray(floor0, np.float32)
         self.frames = np.ascontiguousarray(frames, FRAME_DTYPE)
         self.posts = np.ascontiguousarray(posts, np.int16)
         self.classes = np.ascontiguousarray(classes, np.uint8)
@@ -238,11 +248,12 @@ class HostBatch:
         b.n_classes = self.classes.size
         b.entries = self.entries.ctypes.data if self.entries.size else None
         b.n_entries = self.entries.size
+        b.floor0 = self.floor0.ctypes.data if self.floor0 is not None and self.floor0.size else None
         self.struct = b
 
     @property
     def h2d_bytes(self) -> int:
-        return self.frames.nbytes + self.posts.nbytes + self.classes.nbytes + self.entries.nbytes
+        return self.frames.nbytes + self.posts.nbytes + self.classes.nbytes + self.entries.nbytes + (self.floor0.nbytes if self.floor0 is not None else 0)
 
 
 class DeviceBatch:
@@ -332,6 +343,13 @@ class Context:
         blob = np.ascontiguousarray(blob, np.uint8)
         self._check(self.lib.nvb_setup_blob_import(self.handle, blob.ctypes.data, blob.size), "nvb_setup_blob_import")
         self.channels = int(np.frombuffer(blob[16:20].tobytes(), "<i4")[0])
+
+    @property
+    def floor0_stride(self) -> int:
+        r = self.lib.nvb_floor0_stride(self.handle)
+        if r < 0:
+            self._check(r, "nvb_floor0_stride")
+        return int(r)
 
     @property
     def post_stride(self) -> int:

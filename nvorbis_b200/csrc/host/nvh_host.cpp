@@ -195,6 +195,10 @@ struct Floor1Def {
     int mult = 0, range = 0, ybits = 0;
     std::vector<int> x, lo, hi, order;
 };
+struct Floor0Def {                   // Floor0.Init, Floor0.cs:28-51
+    int order = 0, rate = 0, bark_map_size = 0, amp_bits = 0, amp_ofs = 0, amp_div = 0, book_bits = 0;
+    std::vector<int> books;
+};
 struct ResidueDef {
     int type = 0, begin = 0, end = 0, psize = 0, nclass = 0, class_book = 0, stages = 0;
     int streams = 1;                 // Residue0._channels (1 for type 2, Residue2.cs:13)
@@ -222,7 +226,8 @@ struct nvh_stream {
     bool has_eos = false;
     // headers
     int channels = 0, sample_rate = 0, bs[2] = {0, 0}, mode_bits = 0;
-    std::vector<Book> books; std::vector<Floor1Def> floors; std::vector<int> floor_type;
+    std::vector<Book> books; std::vector<Floor1Def> floors; std::vector<int> floor_type; std::vector<Floor0Def> floors0;
+    int f0_stride = 0;                           // floats per (frame, channel) in nvb_batch.floor0, 0 = no type 0 floor
     std::vector<ResidueDef> residues; std::vector<MappingDef> mappings; std::vector<ModeDef> modes;
     // C-ABI view of the setup
     std::vector<nvb_codebook> c_books; std::vector<float> c_vq; std::vector<nvb_floor> c_floors; std::vector<nvb_residue> c_residues;
@@ -234,6 +239,7 @@ struct nvh_stream {
     int64_t position = 0; bool has_position = false; bool eos_found = false;
     // last unpacked batch
     std::vector<nvb_frame> o_frames; std::vector<int16_t> o_posts; std::vector<uint8_t> o_classes; std::vector<uint16_t> o_entries;
+    std::vector<float> o_floor0;
 };
 
 namespace nvh {
@@ -333,6 +339,22 @@ static void parse_id_header(Bits& b, nvh_stream& s) {                           
     b.read(32); b.read(32); b.read(32);
     s.bs[0] = 1 << b.read(4); s.bs[1] = 1 << b.read(4);
     if (s.channels < 1) throw DataError("stream has no channels");
+}
+
+static int ilog_i(int x) { int c = 0; while (x > 0) { ++c; x >>= 1; } return c; }                     // Utils.cs:5-14
+
+static void parse_floor0(Bits& b, const nvh_stream& s, Floor0Def& f) {                                // Floor0.cs:28-51
+    f.order = (int)b.read(8); f.rate = (int)b.read(16); f.bark_map_size = (int)b.read(16);
+    f.amp_bits = (int)b.read(6); f.amp_ofs = (int)b.read(8);
+    f.books.resize((size_t)b.read(4) + 1);
+    if (f.order < 1 || f.rate < 1 || f.bark_map_size < 1) throw DataError("floor0: invalid header");
+    f.amp_div = (int)((1ll << f.amp_bits) - 1);
+    for (auto& bk : f.books) {
+        bk = (int)b.read(8);
+        if (bk >= (int)s.books.size()) throw DataError("floor0: book out of range");
+        if (s.books[(size_t)bk].map_type == 0 || s.books[(size_t)bk].dims < 1) throw DataError("floor0: book without a lookup table");
+    }
+    f.book_bits = ilog_i((int)f.books.size());
 }
 
 static void parse_floor1(Bits& b, const nvh_stream& s, Floor1Def& f) {                                // Floor1.cs:30-133
@@ -440,12 +462,12 @@ static void parse_setup_header(Bits& b, nvh_stream& s) {                        
     const int times = (int)b.read(6) + 1;
     b.skip(16 * times);
     const int nfloors = (int)b.read(6) + 1;
-    s.floors.resize((size_t)nfloors); s.floor_type.resize((size_t)nfloors);
+    s.floors.resize((size_t)nfloors); s.floor_type.resize((size_t)nfloors); s.floors0.resize((size_t)nfloors);
     for (int i = 0; i < nfloors; i++) {
         const int type = (int)b.read(16);                                                             // Factory.cs:22-31
         s.floor_type[(size_t)i] = type;
         if (type == 1) parse_floor1(b, s, s.floors[(size_t)i]);
-        else if (type == 0) throw DataError("floor type 0 streams are not accepted by the synthesis path yet");
+        else if (type == 0) parse_floor0(b, s, s.floors0[(size_t)i]);
         else throw DataError("Invalid floor type!");
     }
     s.residues.resize((size_t)b.read(6) + 1);
@@ -476,16 +498,22 @@ static void export_setup(nvh_stream& s) {
         s.c_vq.insert(s.c_vq.end(), b.table.begin(), b.table.end()); off += (int64_t)b.table.size();
         s.c_books.push_back(c);
     }
-    int max_posts = 2;
+    int max_posts = 2, max_order0 = 0;
     for (size_t i = 0; i < s.floors.size(); i++) {
         const Floor1Def& f = s.floors[i];
         nvb_floor c; std::memset(&c, 0, sizeof c);
         c.type = s.floor_type[i]; c.f1.n_posts = (int)f.x.size(); c.f1.multiplier = f.mult; c.f1.range = f.range;
+        if (c.type == 0) {
+            const Floor0Def& z = s.floors0[i];
+            c.f0.order = z.order; c.f0.rate = z.rate; c.f0.bark_map_size = z.bark_map_size; c.f0.amp_bits = z.amp_bits; c.f0.amp_ofs = z.amp_ofs;
+            max_order0 = std::max(max_order0, z.order);
+        }
         for (size_t k = 0; k < f.x.size(); k++) { c.f1.x_list[k] = (uint16_t)f.x[k]; c.f1.l_neigh[k] = (uint8_t)f.lo[k]; c.f1.h_neigh[k] = (uint8_t)f.hi[k]; c.f1.sort_idx[k] = (uint8_t)f.order[k]; }
         max_posts = std::max(max_posts, (int)f.x.size());
         s.c_floors.push_back(c);
     }
     s.post_stride = (2 + max_posts + 1) & ~1;
+    s.f0_stride = max_order0 > 0 ? (1 + max_order0 + 1) & ~1 : 0;                                       // same rule as nvb_floor0_stride()
     for (const ResidueDef& r : s.residues) {
         nvb_residue c; std::memset(&c, 0, sizeof c);
         c.type = r.type; c.begin = r.begin; c.end = r.end; c.partition_size = r.psize; c.classifications = r.nclass; c.max_stages = r.stages;
@@ -521,7 +549,7 @@ static void open_common(nvh_stream& s) {
 }
 
 // ---- one audio packet -> boundary record ----------------------------------------------------------------
-struct Scratch { std::vector<int16_t> posts; std::vector<uint8_t> classes; std::vector<uint16_t> entries; std::vector<UnpackedFrame> frames; };
+struct Scratch { std::vector<int16_t> posts; std::vector<uint8_t> classes; std::vector<uint16_t> entries; std::vector<float> floor0; std::vector<UnpackedFrame> frames; };
 
 static void unpack_packet(const nvh_stream& s, const PacketRef& pr, Scratch& out) {
     UnpackedFrame uf; std::memset(&uf.f, 0, sizeof uf.f);
@@ -529,6 +557,8 @@ static void unpack_packet(const nvh_stream& s, const PacketRef& pr, Scratch& out
     const int C = s.channels;
     const size_t posts_at = out.posts.size();
     out.posts.resize(posts_at + (size_t)C * s.post_stride, 0);
+    const size_t f0_at = out.floor0.size();
+    out.floor0.resize(f0_at + (size_t)C * s.f0_stride, 0.f);
     uf.f.status = NVB_FRAME_FAILED;
     uf.f.classes_off = (uint32_t)out.classes.size(); uf.f.entries_off = (uint32_t)out.entries.size();
     Bits b(s.bytes.data() + pr.off, pr.size);
@@ -557,6 +587,36 @@ static void unpack_packet(const nvh_stream& s, const PacketRef& pr, Scratch& out
     for (int c = 0; c < C; c++) {
         const Floor1Def& f = s.floors[(size_t)map.ch_floor[(size_t)c]];
         int16_t* dst = out.posts.data() + posts_at + (size_t)c * s.post_stride;
+        if (s.floor_type[(size_t)map.ch_floor[(size_t)c]] == 0) {
+            // Floor0.Unpack (Floor0.cs:98-150): amplitude, book number, LSP coefficients as VQ vectors, then the "averaging"
+            const Floor0Def& z = s.floors0[(size_t)map.ch_floor[(size_t)c]];
+            float* pl = out.floor0.data() + f0_at + (size_t)c * s.f0_stride;
+            float amp = (float)b.read(z.amp_bits);
+            if (amp > 0.f) {
+                amp = amp / (float)z.amp_div * (float)z.amp_ofs;
+                const uint32_t book_num = (uint32_t)b.read(z.book_bits);
+                if (book_num >= z.books.size()) amp = 0.f;
+                else {
+                    const Book& bk = s.books[(size_t)z.books[book_num]];
+                    for (int i = 0; i < z.order && amp > 0.f;) {
+                        const int e = bk.decode(b);
+                        if (e < 0) { amp = 0.f; break; }
+                        for (int j = 0; i < z.order && j < bk.dims; j++, i++) pl[1 + i] = bk.table[(size_t)e * bk.dims + j];
+                    }
+                    if (amp > 0.f) {
+                        float last = 0.f;
+                        for (int j = 0; j < z.order;) {
+                            for (int k = 0; j < z.order && k < bk.dims; j++, k++) pl[1 + j] += last;
+                            last = pl[j];                                                             // Coeff[j - 1]
+                        }
+                    }
+                }
+            }
+            pl[0] = amp;
+            dst[0] = 0;
+            if (amp > 0.f) live |= 1u << c;
+            continue;
+        }
         int count = 0;
         if (b.bit()) {
             count = 2;
@@ -688,7 +748,7 @@ int nvh_get_info(nvh_stream* s, nvh_info* o) {
     std::memset(o, 0, sizeof *o);
     o->channels = s->channels; o->sample_rate = s->sample_rate; o->block_size[0] = s->bs[0]; o->block_size[1] = s->bs[1];
     o->n_books = (int)s->books.size(); o->n_floors = (int)s->floors.size(); o->n_residues = (int)s->residues.size();
-    o->n_mappings = (int)s->mappings.size(); o->n_modes = (int)s->modes.size(); o->post_stride = s->post_stride;
+    o->n_mappings = (int)s->mappings.size(); o->n_modes = (int)s->modes.size(); o->post_stride = s->post_stride; o->floor0_stride = s->f0_stride;
     o->n_packets = (int64_t)s->packets.size(); o->n_audio_packets = (int64_t)(s->packets.size() - s->first_audio);
     o->last_granule = -1;
     for (const PacketRef& p : s->packets) if (p.flags & 1) o->last_granule = p.granule;
@@ -732,7 +792,7 @@ int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, in
     if (T == 1) work(0);
     else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
 
-    s->o_frames.clear(); s->o_posts.clear(); s->o_classes.clear(); s->o_entries.clear();
+    s->o_frames.clear(); s->o_posts.clear(); s->o_classes.clear(); s->o_entries.clear(); s->o_floor0.clear();
     std::vector<UnpackedFrame> metas;
     for (Scratch& p : parts) {
         const uint32_t coff = (uint32_t)s->o_classes.size(), eoff = (uint32_t)s->o_entries.size();
@@ -740,6 +800,7 @@ int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, in
         s->o_posts.insert(s->o_posts.end(), p.posts.begin(), p.posts.end());
         s->o_classes.insert(s->o_classes.end(), p.classes.begin(), p.classes.end());
         s->o_entries.insert(s->o_entries.end(), p.entries.begin(), p.entries.end());
+        s->o_floor0.insert(s->o_floor0.end(), p.floor0.begin(), p.floor0.end());
     }
     // Stream-order pass: the bookkeeping of StreamDecoder.ReadNextPacket / Read that lives on the host --
     // sample position (re-based on the first granule, StreamDecoder.cs:358-363) and the EOS trim (:429-437).
@@ -777,6 +838,7 @@ int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, in
             f.classes_off = (uint32_t)s->o_classes.size(); f.entries_off = (uint32_t)s->o_entries.size();
             s->o_frames.push_back(f);
             s->o_posts.resize(s->o_posts.size() + (size_t)s->channels * s->post_stride, 0);
+            s->o_floor0.resize(s->o_floor0.size() + (size_t)s->channels * s->f0_stride, 0.f);
             s->prev_end = s->prev_stop;
             if (s->have_prev) s->position += std::max(0, s->prev_end - s->prev_start);
             s->prev_start = s->prev_end;
@@ -791,6 +853,7 @@ int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, in
     out->frames = s->o_frames.data(); out->posts = s->o_posts.data();
     out->classes = s->o_classes.data(); out->n_classes = (int64_t)s->o_classes.size();
     out->entries = s->o_entries.data(); out->n_entries = (int64_t)s->o_entries.size();
+    out->floor0 = s->o_floor0.empty() ? nullptr : s->o_floor0.data();
     return (int64_t)s->o_frames.size();
 }
 

@@ -53,6 +53,7 @@ struct nvb_dbatch {
     int16_t* d_posts = nullptr;   size_t cap_posts = 0;
     uint8_t* d_classes = nullptr; size_t cap_classes = 0;
     uint16_t* d_entries = nullptr; size_t cap_entries = 0;
+    float* d_floor0 = nullptr;    size_t cap_floor0 = 0;
     float* d_spectrum = nullptr;  size_t cap_spectrum = 0;
     float* d_blocks = nullptr;    size_t cap_blocks = 0;
     Counters* d_counters = nullptr;
@@ -123,7 +124,7 @@ template <class T> int grow(nvb_ctx* ctx, T*& p, size_t& cap, size_t need) {
 
 void free_dbatch(nvb_dbatch* b) {
     if (!b) return;
-    cudaFree(b->d_frames); cudaFree(b->d_posts); cudaFree(b->d_classes); cudaFree(b->d_entries);
+    cudaFree(b->d_frames); cudaFree(b->d_posts); cudaFree(b->d_classes); cudaFree(b->d_entries); cudaFree(b->d_floor0);
     cudaFree(b->d_spectrum); cudaFree(b->d_blocks); cudaFree(b->d_counters);
     delete b;
 }
@@ -167,6 +168,8 @@ int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags,
     if ((rc = grow(ctx, b->d_posts, b->cap_posts, n_posts)) != NVB_OK) return rc;
     if ((rc = grow(ctx, b->d_classes, b->cap_classes, (size_t)batch->n_classes)) != NVB_OK) return rc;
     if ((rc = grow(ctx, b->d_entries, b->cap_entries, (size_t)batch->n_entries)) != NVB_OK) return rc;
+    const size_t n_floor0 = b->plan.uses_floor0 ? (size_t)batch->n_frames * ctx->H.channels * ctx->H.f0_stride : 0;
+    if (n_floor0 && (rc = grow(ctx, b->d_floor0, b->cap_floor0, n_floor0)) != NVB_OK) return rc;
     if ((rc = grow(ctx, b->d_spectrum, b->cap_spectrum, (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
     if (!b->fused && (rc = grow(ctx, b->d_blocks, b->cap_blocks, 2 * (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
     if (!b->d_counters) { size_t cap = 0; if ((rc = grow(ctx, b->d_counters, cap, 1)) != NVB_OK) return rc; }
@@ -180,6 +183,7 @@ int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags,
         if (*pinned) { std::memcpy(*pinned, b->plan.frames.data(), nf * sizeof(DevFrame)); plan_src = *pinned; }
     }
     if (nf) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_frames, plan_src, nf * sizeof(DevFrame), cudaMemcpyHostToDevice, st));
+    if (n_floor0) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_floor0, batch->floor0, n_floor0 * sizeof(float), cudaMemcpyHostToDevice, st));
     if (defer_inputs) {
         // nvb_decode_batch uploads posts / classes / entries chunk by chunk when the batch is laid out sequentially
         *defer_inputs = *defer_inputs && b->fused && b->plan.sequential;
@@ -196,6 +200,7 @@ LaunchArgs make_args(nvb_ctx* ctx, nvb_dbatch* b, float* spectrum, float* d_pcm,
     a.S = ctx->S;
     a.frames = b->d_frames; a.frame_lo = 0; a.n_frames = (int)b->plan.frames.size();
     a.posts = b->d_posts; a.classes = b->d_classes; a.entries = b->d_entries;
+    a.floor0 = b->plan.uses_floor0 ? b->d_floor0 : nullptr;
     a.spectrum = spectrum;
     a.blocks = b->d_blocks;
     a.carry_in = ctx->d_carry[ctx->carry_cur];
@@ -376,6 +381,11 @@ int nvb_setup_blob_import(nvb_ctx* ctx, const void* src, size_t bytes) {
 int nvb_post_stride(nvb_ctx* ctx) {
     if (!ctx || !ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
     return ctx->H.post_stride;
+}
+
+int nvb_floor0_stride(nvb_ctx* ctx) {
+    if (!ctx || !ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
+    return ctx->H.f0_stride;
 }
 
 int nvb_reset(nvb_ctx* ctx) {

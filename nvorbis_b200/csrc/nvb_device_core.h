@@ -20,11 +20,13 @@
 #define NVB_FMUL(a, b) __fmul_rn((a), (b))
 #define NVB_FADD(a, b) __fadd_rn((a), (b))
 #define NVB_FSUB(a, b) __fsub_rn((a), (b))
+#define NVB_FDIV(a, b) __fdiv_rn((a), (b))
 #else
 // host build of the shim is compiled with -ffp-contract=off
 #define NVB_FMUL(a, b) ((a) * (b))
 #define NVB_FADD(a, b) ((a) + (b))
 #define NVB_FSUB(a, b) ((a) - (b))
+#define NVB_FDIV(a, b) ((a) / (b))
 #endif
 
 namespace nvb {

@@ -40,6 +40,11 @@ struct BlobWriter {
     template <class T> T* at(uint64_t off) { return reinterpret_cast<T*>(buf.data() + off); }
 };
 
+// Floor0.toBARK (Floor0.cs:81-84): double arithmetic, result rounded to float
+float floor0_to_bark(double lsp) {
+    return (float)(13.1 * std::atan(0.00074 * lsp) + 2.24 * std::atan(0.0000000185 * lsp * lsp) + .0001 * lsp);
+}
+
 // Rising half of the Vorbis window for an overlap of `len` samples (Mode.cs:80-85): the inner sine in
 // double with a float pi/2, squared in float, times the float pi/2 in float, outer sine in double.
 void window_slope(int len, float* out) {
@@ -167,6 +172,10 @@ void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) 
     S.ci = reinterpret_cast<const CiRec*>(base + h.off_ci);
     S.bin2k = reinterpret_cast<const uint8_t*>(base + h.off_bin2k);
     S.run_modes = reinterpret_cast<const RunMode*>(base + h.off_run_modes);
+    S.floors0 = reinterpret_cast<const DevFloor0*>(base + h.off_floors0);
+    S.f0_bark = reinterpret_cast<const int32_t*>(base + h.off_f0_bark);
+    S.f0_wmap = reinterpret_cast<const float*>(base + h.off_f0_wmap);
+    S.f0_stride = h.f0_stride; S.f0_max_order = h.f0_max_order;
 }
 
 int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string& err) {
@@ -193,10 +202,16 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
             if (b.table_off + (int64_t)b.entries * b.dims > s->n_vq_floats) return fail(err, NVB_ERR_DATA, "book %lld: table outside vq_floats", i);
         }
     }
-    int max_posts = 2;
+    int max_posts = 2, max_order0 = 0;
     for (int i = 0; i < s->n_floors; i++) {
         const nvb_floor& f = s->floors[i];
-        if (f.type == 0) return fail(err, NVB_ERR_UNSUPPORTED, "floor %lld is type 0 (Floor0.cs): not accepted yet", i);
+        if (f.type == 0) {                                                                              // Floor0.cs:28-39
+            const nvb_floor0& z = f.f0;
+            if (z.order < 1 || z.order > 255 || z.rate < 1 || z.rate > 65535 || z.bark_map_size < 1 || z.bark_map_size > 65535 || z.amp_ofs < 0 || z.amp_ofs > 255)
+                return fail(err, NVB_ERR_DATA, "floor %lld: type 0 header fields out of range", i);
+            if (z.order > max_order0) max_order0 = z.order;
+            continue;
+        }
         if (f.type != 1) return fail(err, NVB_ERR_DATA, "floor %lld: invalid type %lld", i, f.type);       // Factory.cs:22-31
         const nvb_floor1& g = f.f1;
         if (g.n_posts < 2 || g.n_posts > NVB_MAX_POSTS) return fail(err, NVB_ERR_DATA, "floor %lld: n_posts %lld", i, g.n_posts);
@@ -281,6 +296,7 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
     for (int i = 0; i < s->n_floors; i++) {
         const nvb_floor1& g = s->floors[i].f1;
         DevFloor1 d; std::memset(&d, 0, sizeof d);
+        if (s->floors[i].type != 1) { w.at<DevFloor1>(h.off_floors)[i] = d; continue; }    // type 0: see DevFloor0 below
         d.n_posts = g.n_posts; d.mult = g.multiplier; d.range = g.range;
         for (int k = 0; k < g.n_posts; k++) { d.x[k] = g.x_list[k]; d.lo[k] = g.l_neigh[k]; d.hi[k] = g.h_neigh[k]; d.sort[k] = g.sort_idx[k]; }
         for (int k = 2; k < g.n_posts; k++) {                           // neighbours always precede the post (validated above)
@@ -302,6 +318,57 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
             while (k + 1 < d.n_posts && (int)d.xs[k + 1] <= bin) ++k;
             tab[bin] = (uint8_t)k;
         }
+    }
+    // type 0 floors: the bark map and the 2 cos map of Floor0.Init (Floor0.cs:53-96) for both block sizes
+    {
+        h.f0_max_order = max_order0;
+        h.f0_stride = max_order0 > 0 ? (1 + max_order0 + 1) & ~1 : 0;
+        std::vector<int32_t> bark; std::vector<float> wmap;
+        std::vector<DevFloor0> f0((size_t)s->n_floors);
+        for (int i = 0; i < s->n_floors; i++) {
+            DevFloor0& d = f0[(size_t)i]; std::memset(&d, 0, sizeof d);
+            d.type = s->floors[i].type;
+            if (d.type != 0) continue;
+            const nvb_floor0& z = s->floors[i].f0;
+            d.order = z.order; d.amp_ofs = z.amp_ofs; d.bark_map_size = z.bark_map_size;
+            for (int j = 0; j < 2; j++) {
+                const int n = h.bs[j] / 2;
+                d.bark_off[j] = (int32_t)bark.size(); d.wmap_off[j] = (int32_t)wmap.size();
+                // SynthesizeBarkCurve (Floor0.cs:67-79): the loop stops at n - 2, so map[n - 1] keeps its initial 0
+                const float scale = (float)z.bark_map_size / floor0_to_bark((double)(z.rate / 2));
+                int kmax = 0;
+                for (int b = 0; b < n; b++) {
+                    int v = 0;
+                    if (b < n - 1) {
+                        const float fr = (z.rate / 2.f) / n * b;
+                        v = (int)std::floor((double)(floor0_to_bark((double)fr) * scale));
+                        if (v > z.bark_map_size - 1) v = z.bark_map_size - 1;
+                    }
+                    if (v < 0 || v >= n) {
+                        // wMap[k] with k >= n: IndexOutOfRangeException on every packet that applies this floor at this block size
+                        // (Floor0.cs:166); refused if some mode does that, harmless otherwise (the reference builds the map anyway)
+                        bool used = false;
+                        for (int m = 0; m < s->n_modes; m++)
+                            if ((s->modes[m].block_flag ? 1 : 0) == j && s->mappings[s->modes[m].mapping].floor == i) used = true;
+                        if (used) return fail(err, NVB_ERR_UNSUPPORTED, "floor %lld: bark map indexes past the cos map (Floor0.cs:166 would throw)", i);
+                        v = 0;
+                    }
+                    if (v > kmax) kmax = v;
+                    bark.push_back(v);
+                }
+                d.kmax[j] = kmax;
+                // SynthesizeWDelMap (Floor0.cs:86-96)
+                const float wdel = (float)(3.14159265358979323846 / z.bark_map_size);
+                for (int b = 0; b < n; b++) wmap.push_back(2.f * (float)std::cos((double)(wdel * b)));
+            }
+        }
+        h.off_floors0 = w.reserve(sizeof(DevFloor0) * (size_t)s->n_floors);
+        std::memcpy(w.at<DevFloor0>(h.off_floors0), f0.data(), sizeof(DevFloor0) * f0.size());
+        h.n_f0_bark = bark.size(); h.n_f0_wmap = wmap.size();
+        h.off_f0_bark = w.reserve(sizeof(int32_t) * (bark.size() ? bark.size() : 1));
+        if (!bark.empty()) std::memcpy(w.at<int32_t>(h.off_f0_bark), bark.data(), sizeof(int32_t) * bark.size());
+        h.off_f0_wmap = w.reserve(sizeof(float) * (wmap.size() ? wmap.size() : 1));
+        if (!wmap.empty()) std::memcpy(w.at<float>(h.off_f0_wmap), wmap.data(), sizeof(float) * wmap.size());
     }
     h.off_residues = w.reserve(sizeof(DevResidue) * s->n_residues);
     int ci_total = 0;
@@ -438,6 +505,11 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         // plane kernel: stages planes + floor rows + item list in shared memory (k_spectrum_run needs none of those)
         if (fast == 2 && (size_t)(h.max_stages + 1) * C * (h.bs[1] / 2) * 4 + (size_t)mx * 9 + 64 > 96 * 1024) fast = 1;
         if (fast == 3 && (size_t)mx * 5 + (size_t)ci_total * sizeof(CiRec) + 64 > 160 * 1024) fast = 1;
+        for (int i = 0; i < h.n_modes; i++)                                  // Floor0 lives in the general kernel only
+            if (s->floors[S.mappings[S.modes[i].mapping].floor].type == 0) fast = 0;
+        // general kernel: prefix table + (type 0 floors) per-channel curve and coefficient tables in shared memory
+        if (h.f0_stride > 0 && (size_t)mx * 4 + (size_t)C * (h.bs[1] / 2 + 256) * 4 + 64 > 200 * 1024)
+            return fail(err, NVB_ERR_UNSUPPORTED, "type 0 floor tables do not fit in shared memory");
         if ((size_t)mx * 4 + (size_t)C * (h.bs[1] / 2) * 4 > 160 * 1024) fast = 0;      // prefix table + floor curve rows must fit in shared memory
         h.spectrum_fast = fast;
     }
@@ -459,7 +531,8 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
               in(h.off_floors, sizeof(DevFloor1) * (uint64_t)h.n_floors) && in(h.off_residues, sizeof(DevResidue) * (uint64_t)h.n_residues) &&
               in(h.off_mappings, sizeof(DevMapping) * (uint64_t)h.n_mappings) && in(h.off_modes, sizeof(DevMode) * (uint64_t)h.n_modes) &&
               in(h.off_win_short, 4ull * h.bs[0]) && in(h.off_win_long, 16ull * h.bs[1]) && in(h.off_db, 1024) &&
-              h.ci_total >= 0 && in(h.off_ci, sizeof(CiRec) * (uint64_t)(h.ci_total > 0 ? h.ci_total : 1)) && in(h.off_bin2k, (uint64_t)h.n_floors * (h.bs[1] / 2)) && in(h.off_run_modes, sizeof(RunMode) * (uint64_t)h.n_modes) &&
+              h.ci_total >= 0 && in(h.off_ci, sizeof(CiRec) * (uint64_t)(h.ci_total > 0 ? h.ci_total : 1)) && in(h.off_bin2k, (uint64_t)h.n_floors * (h.bs[1] / 2)) && in(h.off_run_modes, sizeof(RunMode) * (uint64_t)h.n_modes) && in(h.off_floors0, sizeof(DevFloor0) * (uint64_t)h.n_floors) &&
+              in(h.off_f0_bark, 4 * (h.n_f0_bark ? h.n_f0_bark : 1)) && in(h.off_f0_wmap, 4 * (h.n_f0_wmap ? h.n_f0_wmap : 1)) && h.f0_stride >= 0 && h.f0_stride <= 258 &&
               (h.off_fused_tab == 0 || (in(h.off_fused_tab, 4ull * FusedTables::FLOATS) && h.bs[0] == FUSED_SHORT_N && h.bs[1] == FUSED_LONG_N));
     for (int i = 0; i < 2 && ok; i++)
         ok = in(h.off_mdct_a[i], 2ull * h.bs[i]) && in(h.off_mdct_b[i], 2ull * h.bs[i]) && in(h.off_mdct_c[i], 1ull * h.bs[i]) &&
@@ -490,6 +563,18 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
         }
     }
     for (int i = 0; i < h.n_floors; i++) {
+        const DevFloor0& z = S.floors0[i];
+        if (z.type == 0) {
+            if (z.order < 1 || z.order > 255 || h.f0_stride < z.order + 1) return fail(err, NVB_ERR_DATA, "blob: floor %lld (type 0)", i);
+            for (int j = 0; j < 2; j++) {
+                const int n = h.bs[j] / 2;
+                if (z.bark_off[j] < 0 || z.wmap_off[j] < 0 || (uint64_t)z.bark_off[j] + n > h.n_f0_bark || (uint64_t)z.wmap_off[j] + n > h.n_f0_wmap || z.kmax[j] < 0 || z.kmax[j] >= n)
+                    return fail(err, NVB_ERR_DATA, "blob: floor %lld (type 0) tables", i);
+                for (int b = 0; b < n; b++) { const int k = S.f0_bark[z.bark_off[j] + b]; if (k < 0 || k > z.kmax[j]) return fail(err, NVB_ERR_DATA, "blob: floor %lld bark map", i); }
+            }
+            continue;
+        }
+        if (z.type != 1) return fail(err, NVB_ERR_DATA, "blob: floor %lld type", i);
         const DevFloor1& f = S.floors[i];
         if (f.n_posts < 2 || f.n_posts > NVB_MAX_POSTS || f.max_level < 0 || f.max_level > NVB_MAX_POSTS) return fail(err, NVB_ERR_DATA, "blob: floor %lld", i);
         for (int k = 2; k < f.n_posts; k++) if (f.level[k] < 1 || f.level[k] > f.max_level) return fail(err, NVB_ERR_DATA, "blob: floor %lld levels", i);
@@ -522,6 +607,7 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
     }
     for (int i = 0; i < h.n_floors; i++) {
         const DevFloor1& f = S.floors[i];
+        if (S.floors0[i].type != 1) continue;
         for (int k = 0; k < f.n_posts; k++) if (f.xs[k] != f.x[f.sort[k]]) return fail(err, NVB_ERR_DATA, "blob: floor %lld sorted x", i);
         for (int b = 0; b < h.bs[1] / 2; b++) {
             const int k = S.bin2k[(size_t)i * (h.bs[1] / 2) + b];
@@ -573,6 +659,10 @@ int plan_batch(const unsigned char* host_blob, const nvb_batch* b, int flags, co
         if (f.start < 0 || f.total > n || f.start > f.total || f.valid > f.total) return fail(err, NVB_ERR_DATA, "frame %lld: start/valid/total outside the block", i);
         if ((f.exec_mask >> C) != 0) return fail(err, NVB_ERR_DATA, "frame %lld: exec_mask has bits above the channel count", i);
         const DevMapping& mp = S.mappings[md.mapping];
+        if (S.floors0[mp.floor].type == 0) {
+            if (!b->floor0) return fail(err, NVB_ERR_ARG, "frame %lld uses a type 0 floor but batch.floor0 is NULL", i);
+            out.uses_floor0 = true;
+        }
         if (f.res_decoded) {
             const ResGeom g = residue_geom(S.residues[mp.residue], n, C);
             if ((int64_t)f.classes_off + (int64_t)g.P * g.Sx > b->n_classes) return fail(err, NVB_ERR_DATA, "frame %lld: classes outside the batch", i);

@@ -37,6 +37,7 @@ struct Plan {
     int n_failed = 0, n_inconsistent = 0;
     int last_ok = -1;             // DevFrame index of the batch's last decoded block, -1 if none
     bool uses_carry = false;      // some DevFrame reads the previous batch's block
+    bool uses_floor0 = false;     // some frame's mapping has a type 0 floor: nvb_batch.floor0 is read
     bool sequential = true;       // class / entry ranges of successive frames do not overlap and ascend (inputs can be uploaded in chunks)
     CarryState end_state;
 };

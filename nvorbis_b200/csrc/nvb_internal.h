@@ -49,6 +49,10 @@ struct DevFloor1  {
     float rcp[NVB_MAX_POSTS];       // 1.0f / (x[hi[i]] - x[lo[i]]): RenderPoint's divisor is a setup constant
     uint16_t xs[NVB_MAX_POSTS];     // x[sort[k]]: the x list in ascending order (k_spectrum_run)
 };
+// Floor type 0 (Floor0.cs): one record per floor of the setup (type 1 floors carry type = 1 and nothing else).
+// bark / wmap: element offsets into DevSetup.f0_bark (int32, n entries: barkMap[0..n)) and DevSetup.f0_wmap (float, n entries)
+// for the short / long block size; kmax = largest bark index that occurs.
+struct DevFloor0 { int32_t type, order, amp_ofs, bark_map_size; int32_t bark_off[2], wmap_off[2], kmax[2]; int32_t pad[2]; };
 // k_spectrum_run: one record per (class, stage) of a residue, DevResidue.ci_off + class * stages + stage
 struct alignas(16) CiRec { int32_t off, dshift, entries, cnt; };   // VQ table float offset, log2(dims), book entries, entries per partition (0 = nothing coded)
 struct DevResidue {
@@ -96,6 +100,11 @@ struct BlobHeader {
     uint64_t off_ci;           // CiRec[ci_total]
     uint64_t off_bin2k;        // uint8[n_floors][bs[1]/2]: sorted position of the last floor post with x <= bin
     uint64_t off_run_modes;    // RunMode[n_modes]
+    uint64_t off_floors0;      // DevFloor0[n_floors]
+    uint64_t off_f0_bark, off_f0_wmap;   // pooled int32 / float tables of the type 0 floors
+    uint64_t n_f0_bark, n_f0_wmap;
+    int32_t f0_stride;         // floats per (frame, channel) in nvb_batch.floor0; 0 = the setup has no type 0 floor
+    int32_t f0_max_order;
 };
 
 // Resolved pointers handed to kernels by value.
@@ -109,6 +118,7 @@ struct DevSetup {
     const float* db;
     const float* fused_tab;    // lane tables of the fused kernel, nullptr when the block sizes are not {256, 2048}
     const CiRec* ci; const uint8_t* bin2k; const RunMode* run_modes;
+    const DevFloor0* floors0; const int32_t* f0_bark; const float* f0_wmap; int32_t f0_stride, f0_max_order;
 };
 
 // ---- per-frame plan built on the host from nvb_frame (ok frames only, in order) ----------------
@@ -136,6 +146,7 @@ struct LaunchArgs {
     const DevFrame* frames;     // device array of the whole batch plan
     int frame_lo, n_frames;     // this launch covers plan frames [frame_lo, frame_lo + n_frames)
     const int16_t* posts; const uint8_t* classes; const uint16_t* entries;
+    const float* floor0;        // [frame][channel][f0_stride] or nullptr
     float* spectrum;            // [sum C*n/2]
     float* blocks;              // [sum C*n]   (exact path scratch)
     const float* carry_in;      // [C][bs1] previous batch's last block (or nullptr)

@@ -87,14 +87,59 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
         uint32_t run = base + incl - sum;
         for (int i = lo; i < hi; i++) { uint32_t c = prefix[i]; prefix[i] = run; run += c; }
     }
-    // ---- floor curves: one lane per channel (serial over <= 64 posts)
-    if (t < C) {
-        if ((f.exec_mask >> t) & 1u)
-            floor1_build(F, a.posts + ((size_t)f.api_index * C + t) * S.post_stride, n, s_segs[t]);
-        else
-            s_segs[t].n = 0;
+    // ---- floor curves
+    const DevFloor0 F0 = S.floors0[mp.floor];
+    float* s_f0q = nullptr;                                                 // type 0: [C][n] curve value per bark index
+    if (F0.type == 1) {
+        // type 1: one lane per channel (serial over <= 64 posts)
+        if (t < C) {
+            if ((f.exec_mask >> t) & 1u)
+                floor1_build(F, a.posts + ((size_t)f.api_index * C + t) * S.post_stride, n, s_segs[t]);
+            else
+                s_segs[t].n = 0;
+        }
+        __syncthreads();
+    } else {
+        // type 0 (Floor0.Apply, Floor0.cs:152-212): the curve only depends on the bark index k = barkMap[bin], so it is
+        // evaluated once per (channel, k) into shared memory; s_segs[c].n doubles as "has a curve" (Amp > 0)
+        const int bi = md.block_flag ? 1 : 0;
+        s_f0q = reinterpret_cast<float*>(prefix + ((S.max_items + 3) & ~3));
+        float* s_f0c = s_f0q + (size_t)C * (S.bs[1] >> 1);                   // [C][256]: 2 cos(coeff)
+        const float* wmap = S.f0_wmap + F0.wmap_off[bi];
+        const int order = F0.order, kmax = F0.kmax[bi];
+        if (t < C) {
+            const float amp = a.floor0[((size_t)f.api_index * C + t) * S.f0_stride];
+            s_segs[t].n = (((f.exec_mask >> t) & 1u) && amp > 0.f) ? 1 : 0;
+        }
+        __syncthreads();
+        for (int i = t; i < C * order; i += nt) {
+            const int c = i / order, j = i - c * order;
+            if (s_segs[c].n) s_f0c[c * 256 + j] = NVB_FMUL(2.f, (float)cos((double)a.floor0[((size_t)f.api_index * C + c) * S.f0_stride + 1 + j]));   // Floor0.cs:166-169
+        }
+        __syncthreads();
+        for (int i = t; i < C * (kmax + 1); i += nt) {
+            const int c = i / (kmax + 1), k = i - c * (kmax + 1);
+            if (!s_segs[c].n) continue;
+            const float* cf = s_f0c + c * 256;
+            const float amp = a.floor0[((size_t)f.api_index * C + c) * S.f0_stride];
+            const float w = wmap[k];
+            float p = .5f, q = .5f;
+            int j;
+            for (j = 1; j < order; j += 2) { q = NVB_FMUL(q, NVB_FSUB(w, cf[j - 1])); p = NVB_FMUL(p, NVB_FSUB(w, cf[j])); }
+            if (j == order) {                                               // odd order filter; slightly asymmetric
+                q = NVB_FMUL(q, NVB_FSUB(w, cf[j - 1]));
+                p = NVB_FMUL(p, NVB_FMUL(p, NVB_FSUB(4.f, NVB_FMUL(w, w))));
+                q = NVB_FMUL(q, q);
+            } else {                                                        // even order filter; still symmetric
+                p = NVB_FMUL(p, NVB_FMUL(p, NVB_FSUB(2.f, w)));
+                q = NVB_FMUL(q, NVB_FMUL(q, NVB_FADD(2.f, w)));
+            }
+            q = NVB_FSUB(NVB_FDIV(amp, (float)sqrt((double)NVB_FADD(p, q))), (float)F0.amp_ofs);      // dB of this bark section
+            s_f0q[c * n + k] = (float)exp((double)NVB_FMUL(q, 0.11512925f));                          // linear sample multiplier
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    const int32_t* f0_bark = S.f0_bark + F0.bark_off[md.block_flag ? 1 : 0];
 
     int bad_entry = 0, bad_floor = 0;
     for (int j = t; j < n; j += nt) {
@@ -110,11 +155,14 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
         for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
             if (c >= C) break;
             float v = r[c];
-            if ((f.exec_mask >> c) & 1u) {                                  // Floor1.Apply, Floor1.cs:186-222
+            if ((f.exec_mask >> c) & 1u) {                                  // Floor1.Apply, Floor1.cs:186-222 / Floor0.Apply, Floor0.cs:152-212
                 if (s_segs[c].n > 0) {
-                    int y = floor1_y(s_segs[c], j);
-                    if (y < 0 || y > 255) { bad_floor = 1; y = y < 0 ? 0 : 255; }
-                    v = NVB_FMUL(v, s_db[y]);
+                    if (s_f0q) v = NVB_FMUL(v, s_f0q[c * n + f0_bark[j]]);
+                    else {
+                        int y = floor1_y(s_segs[c], j);
+                        if (y < 0 || y > 255) { bad_floor = 1; y = y < 0 ? 0 : 255; }
+                        v = NVB_FMUL(v, s_db[y]);
+                    }
                 } else v = 0.f;
             }
             a.spectrum[(size_t)f.spec_off + (size_t)c * n + j] = v;
@@ -1266,7 +1314,11 @@ __global__ void __launch_bounds__(OLA_THREADS) k_ola(LaunchArgs a) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static size_t spectrum_smem(const DevSetup& S) { return (size_t)(S.max_items > 0 ? S.max_items : 1) * sizeof(uint32_t); }
+static size_t spectrum_smem(const DevSetup& S) {
+    size_t b = (size_t)(((S.max_items > 0 ? S.max_items : 1) + 3) & ~3) * sizeof(uint32_t);
+    if (S.f0_stride > 0) b += (size_t)S.channels * ((S.bs[1] >> 1) + 256) * sizeof(float);     // type 0 floors: curve + coefficient tables
+    return b;
+}
 
 int launch_spectrum(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;

@@ -16,7 +16,7 @@ class Info(C.Structure):
     _fields_ = [("channels", C.c_int32), ("sample_rate", C.c_int32), ("block_size", C.c_int32 * 2), ("n_books", C.c_int32),
                 ("n_floors", C.c_int32), ("n_residues", C.c_int32), ("n_mappings", C.c_int32), ("n_modes", C.c_int32),
                 ("post_stride", C.c_int32), ("n_packets", C.c_int64), ("n_audio_packets", C.c_int64), ("last_granule", C.c_int64),
-                ("has_eos", C.c_int32), ("reserved", C.c_int32)]
+                ("has_eos", C.c_int32), ("floor0_stride", C.c_int32)]
 
 
 _lib = None
@@ -80,6 +80,7 @@ class HostStream:
         self.channels, self.sample_rate = info.channels, info.sample_rate
         self.block_size = (info.block_size[0], info.block_size[1])
         self.post_stride = info.post_stride
+        self.floor0_stride = info.floor0_stride
         self.n_audio_packets = int(info.n_audio_packets)
 
     def close(self):
@@ -126,4 +127,5 @@ class HostStream:
         posts = view(b.posts, np.int16, n * self.channels * self.post_stride)
         classes = view(b.classes, np.uint8, b.n_classes)
         entries = view(b.entries, np.uint16, b.n_entries)
-        return capi.HostBatch(frames, posts, classes, entries), bool(eos.value)
+        floor0 = view(b.floor0, np.float32, n * self.channels * self.floor0_stride) if b.floor0 else None
+        return capi.HostBatch(frames, posts, classes, entries, floor0), bool(eos.value)

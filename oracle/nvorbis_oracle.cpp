@@ -1538,6 +1538,11 @@ int orc_floor_info(void* hh, int fi, int32_t* out) {
     const Floor& f = d.floors[fi];
     std::memset(out, 0, sizeof(int32_t) * 260);
     out[0] = f.type; out[1] = (int)f.xList.size(); out[2] = f.multiplier; out[3] = f.range;
+    if (f.type == 0) {   // floor 0: out[4..] = order, rate, bark_map_size, ampBits, ampOfs, number of books, book numbers
+        out[1] = 0; out[4] = f.order; out[5] = f.rate; out[6] = f.bark_map_size; out[7] = f.ampBits; out[8] = f.ampOfs; out[9] = (int)f.f0books.size();
+        for (size_t k = 0; k < f.f0books.size() && k < 16; k++) out[10 + k] = f.f0books[k];
+        return 0;
+    }
     for (size_t k = 0; k < f.xList.size() && k < 64; k++) { out[4 + k] = f.xList[k]; out[68 + k] = f.lNeigh[k]; out[132 + k] = f.hNeigh[k]; out[196 + k] = f.sortIdx[k]; }
     return 0;
 }
@@ -1681,10 +1686,15 @@ float orc_inverse_db(int y) { return inverse_dB(y & 255); }
 // runs, one std::thread each, with a 1-frame halo (frame start-1 recomputed, output dropped).
 int64_t orc_synth_batch(void* hh, const SynthFrame* frames, int64_t nFrames, const int32_t* posts, const int32_t* postCounts,
                         const uint8_t* classes, const int32_t* entries, float* pcm, int64_t pcmCapPerChannel, int* clipped);
+// Floor 0 payload for the next orc_synth_batch calls: [frame][channel][stride] floats, element 0 = Amp, 1.. = Coeff
+// (what Floor0.Unpack leaves behind, Floor0.cs:98-150).  nullptr clears it.
+void orc_set_floor0_payload(const float* payload, int stride);
 
 }  // extern "C"
 
 namespace orc {
+
+static const float* g_f0Payload = nullptr; static int g_f0Stride = 0;
 
 struct SynthState {
     Decoder* d; Mdct mdct;
@@ -1693,7 +1703,7 @@ struct SynthState {
 };
 
 // synthesis half of Mapping.DecodePacket + Mode.Decode for one recorded frame
-static void SynthBlock(SynthState& s, const SynthFrame& f, const int32_t* posts, const int32_t* postCounts, const uint8_t* classes, const int32_t* entries,
+static void SynthBlock(SynthState& s, const SynthFrame& f, int64_t frameIndex, const int32_t* posts, const int32_t* postCounts, const uint8_t* classes, const int32_t* entries,
                        std::vector<std::vector<float>>& buffer) {
     Decoder& d = *s.d; const Mode& mode = d.modes[f.mode]; const Mapping& map = d.mappings[mode.mapping];
     int blockSize = mode.blockSize, half = blockSize >> 1, nch = d.channels;
@@ -1709,7 +1719,12 @@ static void SynthBlock(SynthState& s, const SynthFrame& f, const int32_t* posts,
             FloorData fd;
             for (int k = 0; k < 64; k++) fd.Posts[k] = posts[f.postsOff + c * 64 + k];
             fd.PostCount = postCounts[f.postCountOff + c];
-            if (fl.type != 1) throw InvalidData("orc_synth_batch: floor0 payloads are not carried by SynthFrame");
+            if (fl.type != 1) {
+                if (!g_f0Payload) throw InvalidData("orc_synth_batch: floor 0 stream without orc_set_floor0_payload");
+                const float* pl = g_f0Payload + ((size_t)frameIndex * nch + c) * g_f0Stride;
+                fd.isFloor0 = true; fd.Amp = pl[0]; fd.Coeff.assign(pl + 1, pl + 1 + fl.order); fd.Coeff.push_back(0.f);
+                fl.Apply0(fd, blockSize, buffer[c].data());
+            } else
             fl.Apply1(fd, blockSize, buffer[c].data());
             s.mdct.Reverse(buffer[c].data(), blockSize);
         } else std::fill(buffer[c].begin() + half, buffer[c].begin() + blockSize, 0.f);
@@ -1744,7 +1759,7 @@ static int64_t SynthRun(Decoder& d, const SynthFrame* frames, int64_t lo, int64_
             continue;
         }
         std::vector<std::vector<float>>& cur = (s.prevBuf == &s.bufA) ? s.bufB : s.bufA;
-        SynthBlock(s, f, posts, postCounts, classes, entries, cur);
+        SynthBlock(s, f, fi, posts, postCounts, classes, entries, cur);
         int start = f.start, valid = f.valid, total = f.total;      // valid: after the EOS trim
         if (s.prevEnd > 0) {                           // StreamDecoder.cs:440-445 (prevStart == prevEnd here)
             int ps = s.prevStart, ns = start;
@@ -1769,6 +1784,7 @@ extern "C" {
 
 static int g_synthThreads = 1;
 void orc_set_threads(int n) { g_synthThreads = n < 1 ? 1 : n; }
+void orc_set_floor0_payload(const float* payload, int stride) { orc::g_f0Payload = payload; orc::g_f0Stride = stride; }
 
 // samples per channel each frame contributes (same bookkeeping as SynthRun), for sharding
 static int64_t FrameOutLen(const SynthFrame* frames, int64_t i) {

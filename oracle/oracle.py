@@ -89,6 +89,7 @@ def lib():
         L.orc_inverse_db.restype = C.c_float
         L.orc_inverse_db.argtypes = [C.c_int]
         L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_floor0_payload.argtypes = [C.c_void_p, C.c_int]
         L.orc_synth_batch.restype = C.c_int64
         L.orc_synth_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p]
@@ -238,6 +239,9 @@ class OracleReader:
         if lib().orc_floor_info(self._h, i, _ptr(o)) != 0:
             raise IndexError(i)
         n = int(o[1])
+        if int(o[0]) == 0:
+            return dict(type=0, n_posts=0, order=int(o[4]), rate=int(o[5]), bark_map_size=int(o[6]), amp_bits=int(o[7]), amp_ofs=int(o[8]),
+                        books=o[10:10 + int(o[9])].copy())
         return dict(type=int(o[0]), n_posts=n, multiplier=int(o[2]), range=int(o[3]), x_list=o[4:4 + n].copy(), l_neigh=o[68:68 + n].copy(),
                     h_neigh=o[132:132 + n].copy(), sort_idx=o[196:196 + n].copy())
 
@@ -318,8 +322,13 @@ class OracleReader:
 
     # -- batch synthesis from boundary arrays -----------------------------------------
     def synth_batch(self, frames: np.ndarray, posts: np.ndarray, post_counts: np.ndarray, classes: np.ndarray,
-                    entries: np.ndarray, pcm_cap_per_channel: int, threads: int = 1):
+                    entries: np.ndarray, pcm_cap_per_channel: int, threads: int = 1, floor0: np.ndarray | None = None, floor0_stride: int = 0):
         L = lib()
+        if floor0 is not None:
+            floor0 = np.ascontiguousarray(floor0, dtype=np.float32)
+            L.orc_set_floor0_payload(_ptr(floor0), int(floor0_stride))
+        else:
+            L.orc_set_floor0_payload(None, 0)
         frames = np.ascontiguousarray(frames, dtype=SYNTH_FRAME_DTYPE)
         posts = np.ascontiguousarray(posts, dtype=np.int32)
         post_counts = np.ascontiguousarray(post_counts, dtype=np.int32)
@@ -335,6 +344,7 @@ class OracleReader:
         n = L.orc_synth_batch(self._h, _ptr(frames), len(frames), _ptr(posts), _ptr(post_counts), _ptr(classes),
                               _ptr(entries), _ptr(pcm), pcm_cap_per_channel, C.byref(clipped))
         L.orc_set_threads(1)
+        L.orc_set_floor0_payload(None, 0)
         if n < 0:
             raise OracleError(L.orc_last_error().decode())
         return pcm[: n * self.channels], bool(clipped.value)

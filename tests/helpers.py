@@ -164,4 +164,6 @@ def oracle_records(hb: capi.HostBatch, desc: dict):
 def oracle_decode_records(reader: O.OracleReader, hb: capi.HostBatch, desc: dict, threads: int = 1):
     fr, posts, pc, cls, ent = oracle_records(hb, desc)
     cap = int(hb.frames["total"].astype(np.int64).sum()) + 8192
-    return reader.synth_batch(fr, posts, pc, cls, ent, cap, threads=threads)
+    f0 = getattr(hb, "floor0", None)
+    stride = 0 if f0 is None else f0.size // (len(hb.frames) * desc["channels"])
+    return reader.synth_batch(fr, posts, pc, cls, ent, cap, threads=threads, floor0=f0, floor0_stride=stride)

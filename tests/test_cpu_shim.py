@@ -122,9 +122,16 @@ def test_blob_roundtrip_and_errors(shim):
     with pytest.raises(capi.NvbError) as e:
         ctx2.upload_setup(setupio.to_setup(d2))
     assert e.value.status == capi.ERR_UNSUPPORTED
-    d3 = dict(desc); d3["floors"] = [dict(f, type=0) for f in desc["floors"]]
+    # type 0 floors: a malformed header is InvalidDataException (Floor0.cs:37); a bark map that indexes past the cos map
+    # would throw on every packet (Floor0.cs:166) and is refused
+    f0 = dict(type=0, order=0, rate=44100, bark_map_size=64, amp_bits=6, amp_ofs=100)
+    d3 = dict(desc); d3["floors"] = [dict(f, **f0) for f in desc["floors"]]
     with pytest.raises(capi.NvbError) as e:
         ctx2.upload_setup(setupio.to_setup(d3))
+    assert e.value.status == capi.ERR_DATA
+    d4 = dict(desc); d4["floors"] = [dict(f, **dict(f0, order=8, bark_map_size=8192)) for f in desc["floors"]]
+    with pytest.raises(capi.NvbError) as e:
+        ctx2.upload_setup(setupio.to_setup(d4))
     assert e.value.status == capi.ERR_UNSUPPORTED
 
 
