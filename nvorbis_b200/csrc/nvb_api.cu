@@ -115,8 +115,11 @@ struct DeviceGuard {
 template <class T> int grow(nvb_ctx* ctx, T*& p, size_t& cap, size_t need) {
     if (need <= cap && p) return NVB_OK;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
-    size_t n = need ? need : 1;
+    // headroom: the batches of a stream differ by a few per cent, and a reallocation (cudaFree waits for the device) in the
+    // middle of a pipelined run costs milliseconds
+    size_t n = need + need / 4 + 64;
     cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e != cudaSuccess) { cudaGetLastError(); n = need ? need : 1; e = cudaMalloc((void**)&p, n * sizeof(T)); }
     if (e != cudaSuccess) { p = nullptr; cudaGetLastError(); return set_err(ctx, NVB_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
     cap = n;
     return NVB_OK;

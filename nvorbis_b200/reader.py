@@ -1,7 +1,8 @@
 """VorbisReader / StreamDecoder mirror (VorbisReader.cs, StreamDecoder.cs) on top of the split decoder:
 the host library unpacks batches of packets (libnvorbis_host.so), the GPU library synthesises them
 (libnvorbis_b200.so), and ReadSamples is served from the decoded batch, as the batching StreamDecoder of
-INTEGRATION.md does on the C# side.  Same names, argument meaning and end-of-stream behaviour as the
+INTEGRATION.md does on the C# side.  One batch is always in flight (nvb_decode_batch_begin / _end): while the caller
+consumes batch k, batch k+1 has already been unpacked and is on the GPU.  Same names, argument meaning and end-of-stream behaviour as the
 reference's public API for this path; there is no CPU synthesis fallback.
 """
 from __future__ import annotations
@@ -34,6 +35,8 @@ class VorbisReader:
         self._started = False
         self._has_clipped = False
         self._samples_read = 0
+        self._inflight = None                           # (HostBatch, pcm buffer) of the batch begun and not yet ended
+        self._unpack_done = False                       # the host unpacker reached the end of the stream
 
     # ---- properties of IVorbisReader / IStreamDecoder used by TestApp ---------------------------------
     @property
@@ -60,17 +63,33 @@ class VorbisReader:
     def sample_position(self) -> int:
         return self._samples_read
 
+    def _begin_next(self) -> bool:
+        """Unpacks the next run of packets and puts it on the GPU; False when the stream has no more packets."""
+        if self._unpack_done:
+            return False
+        hb, eos = self._host.unpack(self._batch_packets, self._threads, copy=True)     # the arrays must outlive the call
+        flags = capi.RUN_DEFAULT | (capi.RUN_CONTINUE if self._started else 0) | (0 if self.clip_samples else capi.RUN_NO_CLIP)
+        out = np.empty(max(capi.sum_output_bound(hb.frames) * self.channels, 1), np.float32)
+        self._ctx.decode_batch_begin(hb, flags, out.ctypes.data, out.size)
+        self._inflight = (hb, out)
+        self._started = True
+        self._unpack_done = eos
+        return True
+
     def _refill(self) -> bool:
         if self._eos:
             return False
-        hb, eos = self._host.unpack(self._batch_packets, self._threads, copy=False)
-        flags = capi.RUN_DEFAULT | (capi.RUN_CONTINUE if self._started else 0) | (0 if self.clip_samples else capi.RUN_NO_CLIP)
-        pcm, res = self._ctx.decode_batch(hb, flags)
-        self._started = True
-        self._eos = eos
+        if self._inflight is None and not self._begin_next():
+            self._eos = True
+            return False
+        hb, out = self._inflight
+        res = self._ctx.decode_batch_end()
+        self._inflight = None
         self._has_clipped |= res.has_clipped
-        self._pcm, self._pos = pcm, 0
-        return pcm.size > 0 or not eos
+        self._pcm, self._pos = out[: res.samples_per_channel * self.channels], 0
+        if not self._begin_next():                      # batch k+1 goes up while the caller consumes batch k
+            self._eos = True
+        return self._pcm.size > 0 or not self._eos
 
     def read_samples(self, buffer: np.ndarray, offset: int, count: int) -> int:
         """Fills buffer[offset : offset+count] with interleaved float PCM; returns the number of floats written
@@ -103,11 +122,19 @@ class VorbisReader:
 
     def seek_to_start(self):
         """SeekTo(0): restart decoding at the first audio packet (StreamDecoder.cs:562-628 with preRoll at the start)."""
+        if self._inflight is not None:
+            self._ctx.decode_batch_end(); self._inflight = None
         self._host.rewind()
         self._ctx.reset()
         self._pcm, self._pos, self._eos, self._started, self._samples_read = np.zeros(0, np.float32), 0, False, False, 0
+        self._unpack_done = False
 
     def close(self):
+        if self._inflight is not None:
+            try:
+                self._ctx.decode_batch_end()
+            finally:
+                self._inflight = None
         self._ctx.close()
         self._host.close()
 

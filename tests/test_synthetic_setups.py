@@ -15,6 +15,7 @@ SETUPS = {
     "stereo_r2": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)]),
     "six_ch_r2_coupled": dict(channels=6, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 2), (3, 4), (0, 1)]),
     "quad_r2": dict(channels=4, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1), (2, 3)]),
+    "oct_r2": dict(channels=8, bs0=256, bs1=1024, residue_type=2, coupling=[(0, 1), (2, 3), (6, 7), (0, 4)]),
     "tiny_blocks_r1_lookup2_seq": dict(channels=2, bs0=64, bs1=128, residue_type=1, coupling=[(0, 1)], lookup=2, sequence_p=True),
     "three_ch_r0": dict(channels=3, bs0=512, bs1=4096, residue_type=0, coupling=[(1, 2)]),
     "mono_r1_big": dict(channels=1, bs0=1024, bs1=8192, residue_type=1),
