@@ -270,23 +270,41 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p)
                     out[511 - lane - 32 * k] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
                 }
             } else if (len > 0) {
-                const int total = len * C;
-                for (int idx = lane; idx < total; idx += 32) {
-                    const int s = idx / C, c = idx - s * C;
+                // every other shape (short blocks, window transitions, silent channels, drains, C != 2): lanes over samples,
+                // channels in an inner loop; the index of y[i] inside a slot (fused_y) and the window values are per-sample
+                const float* wf = f.kind == 0 ? frame_window(S, f) : nullptr;
+                const float* wp = pf ? frame_window(S, *pf) : nullptr;
+                const int nf_ = f.n, np_ = pf ? pf->n : 0;
+                const uint32_t ex_f = f.exec_mask, ex_p = pf ? pf->exec_mask : 0u;
+                const bool clip = a.clip != 0;
+                for (int s = lane; s < len; s += 32) {
                     const int i = f.out_begin + s;
-                    float v;
-                    if (f.kind == 0) {
-                        v = slot_z(S, f, slots_f + c * FUSED_SLOT_FLOATS, c, i);
-                        const int o = i - f.start;
-                        if (f.ola_len > 0 && o >= 0 && o < f.ola_len) {                       // StreamDecoder.cs:532-541
-                            if (pf) v += slot_z(S, *pf, slots_p + c * FUSED_SLOT_FLOATS, c, f.prev_valid + o);
-                            else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)c * S.bs[1] + f.prev_valid + o];
+                    const int o = i - f.start;
+                    const bool ola = f.kind == 0 && f.ola_len > 0 && o >= 0 && o < f.ola_len;          // StreamDecoder.cs:532-541
+                    const int ip = f.kind == 0 ? f.prev_valid + o : i;                               // sample of the previous block (overlap or drain)
+                    const bool use_p = ola || f.kind != 0;
+                    float wv = 0.f, wpv = 0.f;
+                    int jf = 0, jp = 0; float sf = 0.f, sp = 0.f;
+                    if (f.kind == 0) { wv = wf[i]; fused_y_index(nf_, i, jf, sf); }
+                    if (use_p && pf) { wpv = wp[ip]; fused_y_index(np_, ip, jp, sp); }
+                    float* dst = a.pcm + ((size_t)f.pcm_off + s) * C;
+                    for (int c = 0; c < C; c++) {
+                        float v = 0.f;
+                        if (f.kind == 0) {
+                            const float* sl = slots_f + c * FUSED_SLOT_FLOATS;
+                            const float y = ((ex_f >> c) & 1u) ? sf * sl[jf] : (i < (nf_ >> 1) ? sl[i] : 0.f);
+                            v = y * wv;
                         }
-                    } else {                                                                  // drain, StreamDecoder.cs:352-356
-                        v = pf ? slot_z(S, *pf, slots_p + c * FUSED_SLOT_FLOATS, c, i) : a.carry_in[(size_t)c * S.bs[1] + i];
+                        if (use_p) {
+                            if (pf) {
+                                const float* sl = slots_p + c * FUSED_SLOT_FLOATS;
+                                const float y = ((ex_p >> c) & 1u) ? sp * sl[jp] : (ip < (np_ >> 1) ? sl[ip] : 0.f);
+                                v += y * wpv;
+                            } else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)c * S.bs[1] + ip];
+                        }
+                        if (clip) v = clipf(v, peak);
+                        dst[c] = v;
                     }
-                    if (a.clip) v = clipf(v, peak);
-                    a.pcm[((size_t)f.pcm_off + s) * C + c] = v;
                 }
             }
             if (x == a.carry_frame && a.carry_out && f.kind == 0) {

@@ -176,6 +176,9 @@ void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) 
     S.f0_bark = reinterpret_cast<const int32_t*>(base + h.off_f0_bark);
     S.f0_wmap = reinterpret_cast<const float*>(base + h.off_f0_wmap);
     S.f0_stride = h.f0_stride; S.f0_max_order = h.f0_max_order;
+    S.r2cand = reinterpret_cast<const uint32_t*>(base + h.off_r2cand);
+    S.r2ob = reinterpret_cast<const uint16_t*>(base + h.off_r2ob);
+    S.spectrum_bins = h.spectrum_bins; S.r2_max_p = h.r2_max_p;
 }
 
 int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string& err) {
@@ -432,6 +435,46 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         w.at<DevMode>(h.off_modes)[i] = d;
     }
 
+    // k_spectrum_bins tables: for a type 2 residue, element e of partition p lands on channel e % C of bin ob(p) + e / C with
+    // ob(p) = (begin + p * psize) / C (Residue2.cs:25-43: chPtr restarts per partition, offset /= channels), so a bin is
+    // reached by the partitions p with ob(p) <= bin and (bin - ob(p)) * C < psize: consecutive p, at most a few
+    std::vector<int> bins_ok((size_t)s->n_residues, 0);
+    {
+        const int nb = h.bs[1] / 2;
+        int max_p = 1;
+        for (int i = 0; i < s->n_residues; i++) {
+            const nvb_residue& r = s->residues[i];
+            if (r.type == 2 && r.partition_size > 0) { const int span = nb * C; const int e = r.end < span ? r.end : span; const int P = e > r.begin ? (e - r.begin) / r.partition_size : 0; if (P > max_p) max_p = P; }
+        }
+        h.r2_max_p = max_p;
+        h.off_r2cand = w.reserve(sizeof(uint32_t) * (size_t)s->n_residues * nb);
+        h.off_r2ob = w.reserve(sizeof(uint16_t) * (size_t)s->n_residues * max_p);
+        for (int i = 0; i < s->n_residues; i++) {
+            const nvb_residue& r = s->residues[i];
+            const DevResidue d = w.at<DevResidue>(h.off_residues)[i];
+            if (r.type != 2 || d.pshift < 0 || r.max_stages < 1) continue;
+            bool ok = true;
+            for (int c = 0; c < d.nclass && ok; c++) for (int st = 0; st < d.stages && ok; st++) {
+                if (d.books[c][st] < 0) continue;
+                const int dims = s->books[d.books[c][st]].dims;
+                if (!is_pow2(dims) || dims > r.partition_size || d.cnt[c][st] > 32767) ok = false;
+            }
+            const int span = nb * C; const int e = r.end < span ? r.end : span; const int P = e > r.begin ? (e - r.begin) / r.partition_size : 0;
+            uint16_t* ob = w.at<uint16_t>(h.off_r2ob) + (size_t)i * max_p;
+            for (int p = 0; p < P; p++) ob[p] = (uint16_t)((r.begin + p * r.partition_size) / C);
+            uint32_t* cand = w.at<uint32_t>(h.off_r2cand) + (size_t)i * nb;
+            for (int bin = 0; bin < nb && ok; bin++) {
+                int first = -1, cnt = 0;
+                for (int p = 0; p < P; p++) {
+                    const int o = (r.begin + p * r.partition_size) / C;
+                    if (o <= bin && (bin - o) * C < r.partition_size) { if (first < 0) first = p; if (p != first + cnt) ok = false; ++cnt; }
+                }
+                if (cnt > 255) ok = false;
+                cand[bin] = first < 0 ? 0u : ((uint32_t)first | ((uint32_t)cnt << 16));
+            }
+            bins_ok[(size_t)i] = ok ? 1 : 0;
+        }
+    }
     h.off_run_modes = w.reserve(sizeof(RunMode) * (size_t)s->n_modes);
     for (int i = 0; i < s->n_modes; i++) {
         RunMode rm; std::memset(&rm, 0, sizeof rm);
@@ -440,8 +483,12 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         const DevResidue& R = w.at<DevResidue>(h.off_residues)[mp.residue];
         rm.rbegin = R.begin; rm.rend = R.end; rm.pshift = R.pshift; rm.stages = R.stages; rm.nclass = R.nclass; rm.ci_off = R.ci_off;
         rm.residue = mp.residue; rm.floor = mp.floor; rm.n_coupling = mp.n_coupling; rm.mapping = md.mapping; rm.block_flag = md.block_flag; rm.rtype = R.type;
+        rm.cand_off = mp.residue * (h.bs[1] / 2); rm.ob_off = mp.residue * h.r2_max_p;
+        rm.bins_ok = bins_ok[(size_t)mp.residue] && s->floors[mp.floor].type == 1;
         w.at<RunMode>(h.off_run_modes)[i] = rm;
     }
+    h.spectrum_bins = 1;
+    for (int i = 0; i < s->n_modes; i++) if (!w.at<RunMode>(h.off_run_modes)[i].bins_ok) h.spectrum_bins = 0;
 
     // windows (Mode.cs:24-67): one for the short size, four for the long size
     {
@@ -532,7 +579,8 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
               in(h.off_mappings, sizeof(DevMapping) * (uint64_t)h.n_mappings) && in(h.off_modes, sizeof(DevMode) * (uint64_t)h.n_modes) &&
               in(h.off_win_short, 4ull * h.bs[0]) && in(h.off_win_long, 16ull * h.bs[1]) && in(h.off_db, 1024) &&
               h.ci_total >= 0 && in(h.off_ci, sizeof(CiRec) * (uint64_t)(h.ci_total > 0 ? h.ci_total : 1)) && in(h.off_bin2k, (uint64_t)h.n_floors * (h.bs[1] / 2)) && in(h.off_run_modes, sizeof(RunMode) * (uint64_t)h.n_modes) && in(h.off_floors0, sizeof(DevFloor0) * (uint64_t)h.n_floors) &&
-              in(h.off_f0_bark, 4 * (h.n_f0_bark ? h.n_f0_bark : 1)) && in(h.off_f0_wmap, 4 * (h.n_f0_wmap ? h.n_f0_wmap : 1)) && h.f0_stride >= 0 && h.f0_stride <= 258 &&
+              in(h.off_f0_bark, 4 * (h.n_f0_bark ? h.n_f0_bark : 1)) && h.r2_max_p >= 1 && h.r2_max_p <= 65536 &&
+              in(h.off_r2cand, 4ull * h.n_residues * (h.bs[1] / 2)) && in(h.off_r2ob, 2ull * h.n_residues * h.r2_max_p) && in(h.off_f0_wmap, 4 * (h.n_f0_wmap ? h.n_f0_wmap : 1)) && h.f0_stride >= 0 && h.f0_stride <= 258 &&
               (h.off_fused_tab == 0 || (in(h.off_fused_tab, 4ull * FusedTables::FLOATS) && h.bs[0] == FUSED_SHORT_N && h.bs[1] == FUSED_LONG_N));
     for (int i = 0; i < 2 && ok; i++)
         ok = in(h.off_mdct_a[i], 2ull * h.bs[i]) && in(h.off_mdct_b[i], 2ull * h.bs[i]) && in(h.off_mdct_c[i], 1ull * h.bs[i]) &&
@@ -603,7 +651,14 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
         const DevMapping& mp = S.mappings[S.modes[i].mapping];
         const DevResidue& R = S.residues[mp.residue];
         if (rm.mapping != S.modes[i].mapping || rm.residue != mp.residue || rm.floor != mp.floor || rm.n_coupling != mp.n_coupling || rm.rbegin != R.begin || rm.rend != R.end ||
-            rm.pshift != R.pshift || rm.stages != R.stages || rm.nclass != R.nclass || rm.ci_off != R.ci_off || rm.rtype != R.type) return fail(err, NVB_ERR_DATA, "blob: run mode %lld", i);
+            rm.pshift != R.pshift || rm.stages != R.stages || rm.nclass != R.nclass || rm.ci_off != R.ci_off || rm.rtype != R.type ||
+            rm.cand_off != mp.residue * (h.bs[1] / 2) || rm.ob_off != mp.residue * h.r2_max_p) return fail(err, NVB_ERR_DATA, "blob: run mode %lld", i);
+        if (rm.bins_ok) {
+            if (R.type != 2 || R.pshift < 0 || S.floors0[mp.floor].type != 1) return fail(err, NVB_ERR_DATA, "blob: run mode %lld bins flag", i);
+            const int nb = h.bs[1] / 2; const int span = nb * h.channels; const int e = R.end < span ? R.end : span; const int P = e > R.begin ? (e - R.begin) >> R.pshift : 0;
+            if (P > h.r2_max_p) return fail(err, NVB_ERR_DATA, "blob: run mode %lld partitions", i);
+            for (int b = 0; b < nb; b++) { const uint32_t cd = S.r2cand[rm.cand_off + b]; if ((int)(cd & 0xffff) + (int)(cd >> 16) > P) return fail(err, NVB_ERR_DATA, "blob: run mode %lld candidate table", i); }
+        }
     }
     for (int i = 0; i < h.n_floors; i++) {
         const DevFloor1& f = S.floors[i];

@@ -71,7 +71,8 @@ struct alignas(16) RunMode {
     int32_t rbegin, rend, pshift, stages;
     int32_t nclass, ci_off, residue, floor;
     int32_t n_coupling, mapping, block_flag, rtype;
-    int32_t pad[4];
+    int32_t cand_off, ob_off;       // k_spectrum_bins: this residue's slices of DevSetup.r2cand / r2ob
+    int32_t bins_ok, pad;           // k_spectrum_bins applies to this mode
 };
 struct DevMapping { int32_t n_coupling, floor, residue, pad; uint8_t mag[NVB_MAX_COUPLING], ang[NVB_MAX_COUPLING]; };
 struct DevMode    { int32_t block_flag, mapping; };
@@ -105,6 +106,11 @@ struct BlobHeader {
     uint64_t n_f0_bark, n_f0_wmap;
     int32_t f0_stride;         // floats per (frame, channel) in nvb_batch.floor0; 0 = the setup has no type 0 floor
     int32_t f0_max_order;
+    // k_spectrum_bins (type 2 residues whose partitions are not aligned to the channel count, Residue2.cs:25-27):
+    uint64_t off_r2cand;       // uint32[n_residues][bs[1]/2]: first partition that reaches the bin | (number of such partitions << 16)
+    uint64_t off_r2ob;         // uint16[n_residues][r2_max_p]: (begin + p * psize) / channels, the bin a partition starts at
+    int32_t r2_max_p;
+    int32_t spectrum_bins;     // 1: every mode can run k_spectrum_bins
 };
 
 // Resolved pointers handed to kernels by value.
@@ -119,6 +125,7 @@ struct DevSetup {
     const float* fused_tab;    // lane tables of the fused kernel, nullptr when the block sizes are not {256, 2048}
     const CiRec* ci; const uint8_t* bin2k; const RunMode* run_modes;
     const DevFloor0* floors0; const int32_t* f0_bark; const float* f0_wmap; int32_t f0_stride, f0_max_order;
+    const uint32_t* r2cand; const uint16_t* r2ob; int32_t spectrum_bins, r2_max_p;
 };
 
 // ---- per-frame plan built on the host from nvb_frame (ok frames only, in order) ----------------

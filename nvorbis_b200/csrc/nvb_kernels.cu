@@ -771,6 +771,51 @@ __device__ __forceinline__ void inverse_couple_sel(float& m, float& a) {
     a = ap ? t : M;
 }
 
+// Floor 1 of one channel by one warp for k_spectrum_run / k_spectrum_bins: UnwrapPosts, the active-post mask of Floor1.Apply's
+// x-sorted walk (bit k: sorted position k starts a segment; 0 = no curve: the channel is cleared, Floor1.cs:220) and one
+// RunSeg per active position.  `careful`: some segment needs the plain division or leaves inverse_dB_table's range.
+__device__ __forceinline__ void floor1_run_segments_warp(const DevFloor1& F, const int16_t* posts, int n, int lane, int* fy, int* ys, RunSeg* seg, int* adx_out,
+                                                         unsigned long long& mask, int& careful_any) {
+    mask = 0ull; careful_any = 0;
+    int count;
+    const unsigned long long flags = floor1_unwrap_warp(F, posts, lane, fy, count);
+    if (count < 2) return;
+    // the walk of Floor1.Apply visits sorted positions 1 .. PostCount-1 and steps on flagged posts; position 0 is its start
+    unsigned m[2];
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int k = lane + 32 * h;
+        int idx = 0; bool act = false;
+        if (k < count) { idx = F.sort[k]; act = idx < count && ((flags >> idx) & 1ull); ys[k] = fy[idx < count ? idx : 0] * F.mult; }
+        m[h] = __ballot_sync(0xffffffffu, act);
+    }
+    mask = (((unsigned long long)m[1] << 32) | m[0]) | 1ull;
+    __syncwarp();
+    bool careful = false;
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int k = lane + 32 * h;
+        if ((mask >> k) & 1ull) {
+            RunSeg r; r.x0 = F.xs[k]; r.y0 = ys[k]; r.dy = 0; r.m = 1u;
+            int adx = 1;
+            const unsigned long long above = mask & ~(((1ull << k) << 1) - 1ull);
+            if (above) {                                                    // else the flat tail, Floor1.cs:213-216
+                const int hi = __ffsll((long long)above) - 1;
+                const int hx = F.xs[hi];
+                adx = (hx < n ? hx : n) - r.x0;                             // x clamped, y NOT re-interpolated (Floor1.cs:206)
+                r.dy = ys[hi] - r.y0;
+                const unsigned long long ady = (unsigned long long)(r.dy < 0 ? -(long long)r.dy : (long long)r.dy);
+                if (adx <= 1) { adx = 1; r.m = 1u; }                        // one bin (or a post at or beyond n): (x - x0) = 0
+                else r.m = ((unsigned long long)adx * (unsigned long long)adx * ady < (1ull << 32)) ? 0xffffffffu / (unsigned)adx + 1u : 0u;
+            }
+            seg[k] = r; adx_out[k] = adx;
+            // y runs monotonically from y0 to y0 + dy: in range at both ends <=> in range everywhere
+            if (r.x0 < n && (r.m == 0u || (unsigned)r.y0 > 255u || (unsigned)(r.y0 + r.dy) > 255u)) careful = true;
+        }
+    }
+    careful_any = __any_sync(0xffffffffu, careful);
+}
+
 template <int CT, int NT, int MINB = 1536 / NT>
 __global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
     constexpr int NW = NT / 32;
@@ -828,46 +873,8 @@ __global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
     }
     for (int c = warp; c < CT; c += NW) {
         unsigned long long mask = 0ull; int careful_any = 0;
-        if ((f.exec_mask >> c) & 1u) {
-            int count;
-            const unsigned long long flags = floor1_unwrap_warp(F, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, lane, s_fy[c], count);
-            if (count >= 2) {
-                // the walk of Floor1.Apply visits sorted positions 1 .. PostCount-1 and steps on flagged posts; position 0 is its start
-                unsigned m[2];
-                #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int k = lane + 32 * h;
-                    int idx = 0; bool act = false;
-                    if (k < count) { idx = F.sort[k]; act = idx < count && ((flags >> idx) & 1ull); s_ys[c][k] = s_fy[c][idx < count ? idx : 0] * F.mult; }
-                    m[h] = __ballot_sync(0xffffffffu, act);
-                }
-                mask = (((unsigned long long)m[1] << 32) | m[0]) | 1ull;
-                __syncwarp();
-                bool careful = false;                                       // some segment needs the plain division or leaves inverse_dB_table's range
-                #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int k = lane + 32 * h;
-                    if ((mask >> k) & 1ull) {
-                        RunSeg r; r.x0 = F.xs[k]; r.y0 = s_ys[c][k]; r.dy = 0; r.m = 1u;
-                        int adx = 1;
-                        const unsigned long long above = mask & ~(((1ull << k) << 1) - 1ull);
-                        if (above) {                                        // else the flat tail, Floor1.cs:213-216
-                            const int hi = __ffsll((long long)above) - 1;
-                            const int hx = F.xs[hi];
-                            adx = (hx < n ? hx : n) - r.x0;                 // x clamped, y NOT re-interpolated (Floor1.cs:206)
-                            r.dy = s_ys[c][hi] - r.y0;
-                            const unsigned long long ady = (unsigned long long)(r.dy < 0 ? -(long long)r.dy : (long long)r.dy);
-                            if (adx <= 1) { adx = 1; r.m = 1u; }            // one bin (or a post at or beyond n): (x - x0) = 0
-                            else r.m = ((unsigned long long)adx * (unsigned long long)adx * ady < (1ull << 32)) ? 0xffffffffu / (unsigned)adx + 1u : 0u;
-                        }
-                        s_seg[c][k] = r; s_adx[c][k] = adx;
-                        // y runs monotonically from y0 to y0 + dy: in range at both ends <=> in range everywhere
-                        if (r.x0 < n && (r.m == 0u || (unsigned)r.y0 > 255u || (unsigned)(r.y0 + r.dy) > 255u)) careful = true;
-                    }
-                }
-                careful_any = __any_sync(0xffffffffu, careful);
-            }
-        }
+        if ((f.exec_mask >> c) & 1u)
+            floor1_run_segments_warp(F, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, n, lane, s_fy[c], s_ys[c], s_seg[c], s_adx[c], mask, careful_any);
         if (lane == 0) { s_mask[c] = mask; s_careful[c] = careful_any; }
     }
     __syncthreads();
@@ -1018,6 +1025,150 @@ __global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
         }
     }
     // rare: count the frame once per kind (the first thread to raise a flag reports it)
+    if (bad_entry && atomicOr(&s_bad[0], 1) == 0) atomicAdd(&a.counters->bad_entry, 1);
+    if (bad_floor && atomicOr(&s_bad[1], 1) == 0) atomicAdd(&a.counters->floor_range, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1+K2+K3, bins path (DevSetup.spectrum_bins; used when the run path does not apply): type 2 residues with ANY channel
+// count and partition alignment -- e.g. 6 channels with 32-wide partitions, where (begin + p * psize) is not a multiple of
+// the channel count and the reference's Residue2.WriteVectors (Residue2.cs:23-47) restarts the channel pointer at every
+// partition and truncates the bin offset: element e of partition p lands on channel e % C of bin ob(p) + e / C, and two
+// neighbouring partitions can reach the same (channel, bin).  A thread owns one BIN with all its channels in registers:
+//   phase A  as in k_spectrum_run (floor segment records per channel warp, entry-stream offsets per (stage, partition));
+//   main     per bin: the partitions that reach it come from a setup table; for every stage, in partition order (the
+//            order of the reference's adds), the C values of the bin are C consecutive elements of the partition;
+//            inverse coupling over the registers, floor multiply, one coalesced store per channel row.
+// ------------------------------------------------------------------------------------------------
+template <int CT, int NT>
+__global__ void __launch_bounds__(NT) k_spectrum_bins(LaunchArgs a) {
+    constexpr int NW = NT / 32;
+    NVB_DYN_SMEM(dyn_smem);
+    __shared__ float s_db[256];
+    __shared__ int s_fy[CT][NVB_MAX_POSTS];
+    __shared__ int s_ys[CT][NVB_MAX_POSTS];
+    __shared__ RunSeg s_seg[CT][NVB_MAX_POSTS];
+    __shared__ int s_adx[CT][NVB_MAX_POSTS];
+    __shared__ unsigned long long s_mask[CT];
+    __shared__ int s_bad[2];
+    __shared__ int s_careful[CT];
+
+    nvb_grid_dep_launch();
+    nvb_grid_dep_wait();
+    const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
+    if (f.kind != 0) return;
+    const DevSetup& S = a.S;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const RunMode rm = S.run_modes[f.mode];
+    const DevMapping& mp = S.mappings[rm.mapping];
+    const DevFloor1& F = S.floors[rm.floor];
+    const int N = f.n, n = N >> 1, span = CT * n;
+    const int stages = rm.stages, st_n = stages > 0 ? stages : 1;
+    const int rbegin = rm.rbegin, pshift = rm.pshift, nclass = rm.nclass, psize = 1 << pshift;
+    int P = 0;
+    if (f.res_decoded) { const int e = rm.rend < span ? rm.rend : span; const int nn = e - rbegin; P = nn > 0 ? nn >> pshift : 0; }   // Residue2.cs:16-21
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(dyn_smem);               // [stage][partition]: where the item's entries start
+    const CiRec* ci_tab = S.ci + rm.ci_off;
+    const uint8_t* cls = a.classes + f.classes_off;
+    const uint16_t* ent = a.entries + f.entries_off;
+    const uint8_t* bin2k = S.bin2k + (size_t)rm.floor * (S.bs[1] >> 1);
+    const uint32_t* cand = S.r2cand + rm.cand_off;
+    const uint16_t* obs = S.r2ob + rm.ob_off;
+
+    for (int i = t; i < 256; i += NT) s_db[i] = S.db[i];
+    if (t < 2) s_bad[t] = 0;
+    if (P > 0) for (uint32_t i = (uint32_t)t * 64u; i < f.entry_count; i += NT * 64u) prefetch_l1(ent + i);
+
+    // ---- phase A
+    if (warp == NW - 1 && P > 0) {
+        uint32_t run = 0;
+        for (int st = 0; st < stages; st++) {
+            for (int base = 0; base < P; base += 32) {
+                const int p = base + lane;
+                uint32_t c = 0;
+                if (p < P) { const int cl = cls[p]; if (cl < nclass) c = (uint32_t)ci_tab[cl * st_n + st].cnt; }
+                uint32_t incl = c;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+                if (p < P) s_base[st * P + p] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+    }
+    for (int c = warp; c < CT; c += NW) {
+        unsigned long long mask = 0ull; int careful_any = 0;
+        if ((f.exec_mask >> c) & 1u)
+            floor1_run_segments_warp(F, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, n, lane, s_fy[c], s_ys[c], s_seg[c], s_adx[c], mask, careful_any);
+        if (lane == 0) { s_mask[c] = mask; s_careful[c] = careful_any; }
+    }
+    __syncthreads();
+
+    // ---- main: one bin per thread
+    float* spec_out = a.spectrum + (size_t)f.spec_off;
+    const uint32_t ecount = f.entry_count;
+    const bool posts32 = F.n_posts <= 32;
+    int bad_floor = 0, bad_entry = 0;
+    for (int j = t; j < n; j += NT) {
+        float acc[CT];
+        #pragma unroll
+        for (int c = 0; c < CT; c++) acc[c] = 0.f;
+        const uint32_t cd = P > 0 ? cand[j] : 0u;
+        const int p0 = (int)(cd & 0xffffu), ncand = (int)(cd >> 16);
+        for (int st = 0; st < stages; st++) {
+            for (int k = 0; k < ncand; k++) {                               // partition order = the order of the reference's adds
+                const int p = p0 + k;
+                if (p >= P) break;
+                const int cl = cls[p];
+                if (cl >= nclass) continue;
+                const CiRec ci = ci_tab[cl * st_n + st];
+                if (ci.cnt == 0) continue;
+                const int e0 = (j - (int)obs[p]) * CT;                      // first element of this bin inside the partition
+                const uint32_t eb = s_base[st * P + p];
+                const float* tab = S.vq + ci.off;
+                const int dmask = (1 << ci.dshift) - 1;
+                #pragma unroll
+                for (int c = 0; c < CT; c++) {
+                    const int e = e0 + c;
+                    if (e < psize) {
+                        const uint32_t ei = eb + (uint32_t)(e >> ci.dshift);
+                        if (ei < ecount) {                                  // else never decoded: contributes nothing (Residue0.cs:164-170)
+                            const int en = ent[ei];
+                            if (en < ci.entries) acc[c] = NVB_FADD(acc[c], tab[((size_t)en << ci.dshift) + (e & dmask)]); else bad_entry = 1;
+                        }
+                    }
+                }
+            }
+        }
+        for (int i = rm.n_coupling - 1; i >= 0; --i) {                      // Mapping.cs:137-182
+            const int m = mp.mag[i], an = mp.ang[i];
+            if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
+            float vm = 0.f, va = 0.f;
+            #pragma unroll
+            for (int k = 0; k < CT; k++) { if (k == m) vm = acc[k]; if (k == an) va = acc[k]; }
+            inverse_couple_sel(vm, va);
+            #pragma unroll
+            for (int k = 0; k < CT; k++) { if (k == m) acc[k] = vm; if (k == an) acc[k] = va; }
+        }
+        const unsigned kk = bin2k[j];
+        const unsigned long long below = posts32 ? (unsigned long long)(0xffffffffu >> (31 - kk)) : (0xffffffffffffffffull >> (63 - kk));
+        #pragma unroll
+        for (int c = 0; c < CT; c++) {
+            if ((f.exec_mask >> c) & 1u) {                                  // Floor1.Apply, Floor1.cs:186-222
+                const unsigned long long M = s_mask[c];
+                if (M == 0ull) acc[c] = 0.f;
+                else {
+                    const int lo = posts32 ? 31 - __clz((int)((unsigned)M & (unsigned)below)) : 63 - __clzll((long long)(M & below));
+                    const RunSeg r = s_seg[c][lo];
+                    const int num = (j - r.x0) * (r.dy < 0 ? -r.dy : r.dy);
+                    const int qq = r.m != 0u ? (int)__umulhi((unsigned)num, r.m) : num / s_adx[c][lo];
+                    int y = r.dy < 0 ? r.y0 - qq : r.y0 + qq;
+                    if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
+                    acc[c] = NVB_FMUL(acc[c], s_db[y]);
+                }
+            }
+            spec_out[(size_t)c * n + j] = acc[c];
+        }
+    }
     if (bad_entry && atomicOr(&s_bad[0], 1) == 0) atomicAdd(&a.counters->bad_entry, 1);
     if (bad_floor && atomicOr(&s_bad[1], 1) == 0) atomicAdd(&a.counters->floor_range, 1);
 }
@@ -1323,6 +1474,21 @@ static size_t spectrum_smem(const DevSetup& S) {
 int launch_spectrum(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
     static const bool force_generic = std::getenv("NVB_SPECTRUM_GENERIC") != nullptr;      // test hook: exercise the general kernel
+    static const bool no_bins = std::getenv("NVB_SPECTRUM_NO_BINS") != nullptr;                // test hook
+    if (!a.S.spectrum_fast && a.S.spectrum_bins && !force_generic && !no_bins) {
+        const int C = a.S.channels;
+        const size_t smem = (size_t)a.S.max_items * sizeof(uint32_t) + 16;
+        auto go = [&](auto kernel) -> int {
+            if (smem > 40 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            NVB_LAUNCH(kernel, a.n_frames, 128, smem, stream, a);
+            return cudaGetLastError() == cudaSuccess ? 1 : -1;
+        };
+        switch (C) {
+            case 1: return go(k_spectrum_bins<1, 128>); case 2: return go(k_spectrum_bins<2, 128>); case 3: return go(k_spectrum_bins<3, 128>);
+            case 4: return go(k_spectrum_bins<4, 128>); case 5: return go(k_spectrum_bins<5, 128>); case 6: return go(k_spectrum_bins<6, 128>);
+            case 7: return go(k_spectrum_bins<7, 128>); default: return go(k_spectrum_bins<8, 128>);
+        }
+    }
     if (!a.S.spectrum_fast || force_generic) return launch_spectrum_generic(a, stream);
     static const bool no_planes = std::getenv("NVB_SPECTRUM_NO_PLANES") != nullptr;           // test hook: exercise k_spectrum_fast
     // k_spectrum_warp (one warp per frame, no block barrier) is kept as an option: on B200 it measured slower than
@@ -1411,6 +1577,8 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
 
 int launch_spectrum_generic(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
+    static const bool forbid = std::getenv("NVB_SPECTRUM_FORBID_GENERIC") != nullptr;           // test hook: prove a faster kernel covers the setup
+    if (forbid) return -1;
     size_t smem = spectrum_smem(a.S);
     static size_t configured = 0;
     if (smem > 48 * 1024 - 8192 && smem > configured) {

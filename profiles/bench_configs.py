@@ -26,6 +26,24 @@ def time_batches(ctx, batches, C, steps=40, warmup=5):
         dbs[i % R].run(pcm[i % R].data_ptr(), stream)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    # the two stages alone (dense spectrum between them)
+    spec = [torch.empty(db.spectrum_floats + 16, dtype=torch.float32, device="cuda") for db in dbs]
+    stage = {}
+    for name in ("spectrum", "imdct"):
+        def go(i):
+            if name == "spectrum":
+                dbs[i % R].run_spectrum(spec[i % R].data_ptr(), stream)
+            else:
+                dbs[i % R].run_imdct(spec[i % R].data_ptr(), pcm[i % R].data_ptr(), stream)
+        for i in range(R):
+            go(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            go(i)
+        e1.record(); torch.cuda.synchronize()
+        stage[name] = e0.elapsed_time(e1) / steps
+    time_batches.stage = stage
     res = dbs[0].result(stream)
     launches = dbs[0].launches
     for db in dbs:
@@ -41,7 +59,7 @@ def main():
     n3 = 16384
     ms, res, L = time_batches(ctx, [workloads.config3(pool, n3, 20240003 + s) for s in range(5)], 2)
     out["configs[2] mixed 256/2048 stereo"] = {"frames": n3, "ms": ms, "frames_per_s": n3 / (ms * 1e-3), "launches": L,
-                                              "samples_per_channel": res.samples_per_channel}
+                                              "samples_per_channel": res.samples_per_channel, "stage_ms": dict(time_batches.stage)}
     ctx.close()
     import vorbis_headers as VH
     import helpers as H
@@ -57,7 +75,8 @@ def main():
         ctx = capi.Context(0); ctx.upload_setup(host.setup())
         hbs = [VH.random_records(np.random.default_rng(20240004 + k), desc2, n, host.post_stride, short_prob=sp, floor0_stride=host.floor0_stride) for k in range(3)]
         ms, res, L = time_batches(ctx, hbs, kw["channels"], steps=20, warmup=3)
-        out[name] = {"frames": n, "ms": ms, "frames_per_s": n / (ms * 1e-3), "launches": L, "samples_per_channel": res.samples_per_channel}
+        out[name] = {"frames": n, "ms": ms, "frames_per_s": n / (ms * 1e-3), "launches": L, "samples_per_channel": res.samples_per_channel,
+                     "stage_ms": dict(time_batches.stage)}
         ctx.close()
     print(json.dumps(out, indent=1))
 

@@ -110,3 +110,16 @@ def test_floor0_packets_on_cpu_shim(name):
 @pytest.mark.parametrize("name", sorted(FLOOR0))
 def test_floor0_packets_on_gpu(name):
     _run_floor0_packets(name, 400, None)
+
+
+def test_unaligned_type2_residues_run_on_the_bins_kernel():
+    """6 channels with 32-wide partitions (BASELINE configs[3]; Residue2.cs:25-27 truncation case) and 3 / 5 channels are
+    covered by k_spectrum_bins: with the general kernel forbidden the decode still works and stays bit-identical."""
+    import os, subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import test_synthetic_setups as T, helpers as H\n"
+            "T.SETUPS['five_ch_r2'] = dict(channels=5, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1), (3, 4)])\n"
+            "T.SETUPS['three_ch_r2'] = dict(channels=3, bs0=128, bs1=512, residue_type=2, coupling=[(2, 0)])\n"
+            "for name in ('six_ch_r2_coupled', 'five_ch_r2', 'three_ch_r2'):\n    T._run(name, 8, H.build_shim())\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"))
+    env = dict(os.environ, NVB_SPECTRUM_FORBID_GENERIC="1")
+    assert subprocess.check_output([sys.executable, "-c", code], env=env, timeout=600).decode().strip().endswith("ok")
