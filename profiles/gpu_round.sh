@@ -9,4 +9,5 @@ timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 6 --warmup 3 > gpurun_out/ncu_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_imdct_fused -s 12 -c 2 -f -o gpurun_out/prof_fused python bench.py --steps 6 --warmup 3 > gpurun_out/ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_spectrum -s 4 -c 1 -f -o gpurun_out/prof_spectrum python bench.py --steps 6 --warmup 3 >> gpurun_out/ncu_full.log 2>&1
+timeout 600 python profiles/bench_configs.py > gpurun_out/configs.json 2> gpurun_out/configs.err
 tail -5 gpurun_out/pytest.log; cat gpurun_out/bench.json; cat gpurun_out/bench_ref.json; tail -3 gpurun_out/bench.err
