@@ -34,7 +34,10 @@
 
 namespace nvb {
 
-constexpr int FUSED_WARPS = 16;
+#ifndef NVB_FUSED_WARPS
+#define NVB_FUSED_WARPS 16
+#endif
+constexpr int FUSED_WARPS = NVB_FUSED_WARPS;
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
 constexpr size_t FUSED_SMEM_LIMIT = 227 * 1024;
 

@@ -816,7 +816,8 @@ __device__ __forceinline__ void floor1_run_segments_warp(const DevFloor1& F, con
     careful_any = __any_sync(0xffffffffu, careful);
 }
 
-template <int CT, int NT, int MINB = 1536 / NT>
+// MINB caps the registers: 32 (16 CTAs of 128 threads per SM) for one or two channels, 40 otherwise -- measured 39.0 vs 41.0 us
+template <int CT, int NT, int MINB = (CT <= 2 ? 2048 : 1536) / NT>
 __global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
     constexpr int NW = NT / 32;
     constexpr int RB = 8 / CT;                                              // bins per channel in one run
@@ -1537,8 +1538,6 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
             NVB_LAUNCH(kernel, a.n_frames, threads, smem, stream, a);
             return cudaGetLastError() == cudaSuccess ? 1 : -1;
         };
-        static const bool occ = std::getenv("NVB_SPECTRUM_OCC") != nullptr;                    // experiment: 32 registers, 16 CTAs per SM
-        if (occ && C == 2 && nt == 128) return go(k_spectrum_run<2, 128, 16>, 128);
         if (nt == 64) return C == 1 ? go(k_spectrum_run<1, 64>, 64) : C == 2 ? go(k_spectrum_run<2, 64>, 64) : C == 4 ? go(k_spectrum_run<4, 64>, 64) : go(k_spectrum_run<8, 64>, 64);
         if (nt == 128) return C == 1 ? go(k_spectrum_run<1, 128>, 128) : C == 2 ? go(k_spectrum_run<2, 128>, 128) : C == 4 ? go(k_spectrum_run<4, 128>, 128) : go(k_spectrum_run<8, 128>, 128);
         return C == 1 ? go(k_spectrum_run<1, 256>, 256) : C == 2 ? go(k_spectrum_run<2, 256>, 256) : C == 4 ? go(k_spectrum_run<4, 256>, 256) : go(k_spectrum_run<8, 256>, 256);

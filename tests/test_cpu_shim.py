@@ -237,3 +237,35 @@ def test_begin_end_pipeline_matches_sync(shim):
     with pytest.raises(capi.NvbError) as e:
         ctx.decode_batch_end()
     assert e.value.status == capi.ERR_STATE
+
+
+def _floor_range_case(lib_path):
+    """Floor posts whose curve leaves inverse_dB_table (the reference throws IndexOutOfRangeException, Floor1.cs:318,338):
+    every spectrum kernel clamps the same way and counts the frame in n_floor_range; in-range channels of the same frames
+    stay on the multiply-high path."""
+    import os, subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, helpers as H\nfrom nvorbis_b200 import capi\n"
+            "r, pcm, b = H.decoded('3test')\nctx = capi.Context(0, lib_path=%s); ctx.upload_setup(H.setup_from_oracle(r))\n"
+            "hb = H.batch_from_boundary(b, ctx.post_stride, 0, 30)\n"
+            "p = hb.posts.reshape(30, 2, ctx.post_stride)\n"
+            "for i in (7, 8, 19):\n    p[i, 0, 1] = 200; p[i, 0, 2] = 255\n"          # y = 200 * mult, 255 * mult: far above 255
+            "out, res = ctx.decode_batch(hb, capi.RUN_EXACT)\n"
+            "np.save(sys.argv[1], out); print(res.n_floor_range)\n") % (H.ROOT, os.path.join(H.ROOT, "tests"), repr(lib_path))
+    import tempfile
+    outs, counts = [], []
+    with tempfile.TemporaryDirectory() as td:
+        for k, var in enumerate((None, "NVB_SPECTRUM_GENERIC", "NVB_SPECTRUM_PLANES", "NVB_SPECTRUM_NO_PLANES")):
+            env = dict(os.environ)
+            if var:
+                env[var] = "1"
+            path = os.path.join(td, "o%d.npy" % k)
+            counts.append(int(subprocess.check_output([sys.executable, "-c", code, path], env=env, timeout=600).decode().split()[-1]))
+            outs.append(np.load(path))
+    assert counts[0] >= 3 and len(set(counts)) == 1, counts
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o, outs[0])
+
+
+def test_floor_curve_outside_the_table_is_clamped_identically(shim):
+    _floor_range_case(shim)

@@ -263,3 +263,8 @@ def test_begin_end_pipeline_matches_sync_on_gpu():
         np.testing.assert_array_equal(g, w)
     assert clipped and float(np.abs(np.concatenate(got) - pcm).max()) <= TOL
     ctx.close()
+
+
+def test_floor_curve_outside_the_table_is_clamped_identically_on_gpu():
+    import test_cpu_shim
+    test_cpu_shim._floor_range_case(None)
