@@ -268,3 +268,20 @@ def test_begin_end_pipeline_matches_sync_on_gpu():
 def test_floor_curve_outside_the_table_is_clamped_identically_on_gpu():
     import test_cpu_shim
     test_cpu_shim._floor_range_case(None)
+
+
+@pytest.mark.parametrize("name", H.FIXTURES)
+def test_gpu_path_matches_independent_ffmpeg_decoder(name):
+    """The product (host unpacker + GPU synthesis behind the VorbisReader mirror) against FFmpeg's native vorbis decoder."""
+    import ffmpeg_vorbis
+    from nvorbis_b200.reader import VorbisReader
+    pl = H.packets(name)
+    offs = np.concatenate([[0], np.cumsum(pl.sizes)]).astype(np.int64)
+    want = ffmpeg_vorbis.decode([bytes(pl.data[offs[i]:offs[i + 1]]) for i in range(len(pl.sizes))])
+    if want is None:
+        pytest.skip("no usable libavcodec in this environment")
+    with VorbisReader((pl.data, pl.sizes, pl.granules, pl.flags), batch_packets=128) as vr:
+        got = vr.read_all().reshape(-1, vr.channels)
+    n = min(len(got), len(want))
+    assert n >= len(got) - 2048
+    assert float(np.abs(got[:n] - np.clip(want[:n], -0.99999994, 0.99999994)).max()) <= TOL

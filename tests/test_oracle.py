@@ -122,3 +122,23 @@ def test_synthesis_from_boundary_records(name, threads):
         out, clipped = H.oracle_synth(r, b)
         np.testing.assert_array_equal(out, pcm)
         assert clipped == r.has_clipped
+
+
+@pytest.mark.parametrize("name", H.FIXTURES)
+def test_independent_ffmpeg_decoder_agrees(name):
+    """Cross-check against a decoder that shares no code with the oracle or with NVorbis: FFmpeg's native vorbis decoder
+    (the libavcodec inside opencv-python-headless, driven through ctypes on the same demuxed packets).  Agreement to float
+    rounding over the common prefix proves the oracle decodes the reference's own test files correctly; the lengths differ
+    only where NVorbis trims / drains the end of the stream (StreamDecoder.cs:429-437, :352-356)."""
+    import ffmpeg_vorbis
+    pl = H.packets(name)
+    offs = np.concatenate([[0], np.cumsum(pl.sizes)]).astype(np.int64)
+    got = ffmpeg_vorbis.decode([bytes(pl.data[offs[i]:offs[i + 1]]) for i in range(len(pl.sizes))])
+    if got is None:
+        pytest.skip("no usable libavcodec in this environment")
+    r, pcm, _ = H.decoded(name)
+    want = pcm.reshape(-1, r.channels)
+    n = min(len(got), len(want))
+    assert got.shape[1] == r.channels and n >= len(want) - 2048 and n >= len(got) - 2048
+    clipped = np.clip(got[:n], -0.99999994, 0.99999994)          # Utils.ClipValue; FFmpeg hands out un-clipped floats
+    assert float(np.abs(clipped - want[:n]).max()) <= 2e-6
