@@ -1538,6 +1538,7 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
             NVB_LAUNCH(kernel, a.n_frames, threads, smem, stream, a);
             return cudaGetLastError() == cudaSuccess ? 1 : -1;
         };
+        if (nt == 96 && C <= 2) return C == 1 ? go(k_spectrum_run<1, 96>, 96) : go(k_spectrum_run<2, 96>, 96);
         if (nt == 64) return C == 1 ? go(k_spectrum_run<1, 64>, 64) : C == 2 ? go(k_spectrum_run<2, 64>, 64) : C == 4 ? go(k_spectrum_run<4, 64>, 64) : go(k_spectrum_run<8, 64>, 64);
         if (nt == 128) return C == 1 ? go(k_spectrum_run<1, 128>, 128) : C == 2 ? go(k_spectrum_run<2, 128>, 128) : C == 4 ? go(k_spectrum_run<4, 128>, 128) : go(k_spectrum_run<8, 128>, 128);
         return C == 1 ? go(k_spectrum_run<1, 256>, 256) : C == 2 ? go(k_spectrum_run<2, 256>, 256) : C == 4 ? go(k_spectrum_run<4, 256>, 256) : go(k_spectrum_run<8, 256>, 256);

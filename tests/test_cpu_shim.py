@@ -269,3 +269,27 @@ def _floor_range_case(lib_path):
 
 def test_floor_curve_outside_the_table_is_clamped_identically(shim):
     _floor_range_case(shim)
+
+
+def _edge_batches(lib_path):
+    """Empty batch, a batch of failed packets only, a single packet: nothing is emitted and nothing hangs (the first block
+    of a stream leaves only its tail, StreamDecoder.cs:446-450)."""
+    r, pcm, b = H.decoded("1test")
+    ctx = capi.Context(0, lib_path=lib_path)
+    ctx.upload_setup(H.setup_from_oracle(r))
+    out, res = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, 0, 0))
+    assert out.size == 0 and res.samples_per_channel == 0 and res.n_failed == 0
+    fr = np.zeros(3, capi.FRAME_DTYPE); fr["status"] = capi.FRAME_FAILED
+    out, res = ctx.decode_batch(capi.HostBatch(fr, np.zeros(3 * ctx.post_stride, np.int16), np.zeros(0, np.uint8), np.zeros(0, np.uint16)))
+    assert out.size == 0 and res.n_failed == 3
+    ctx.decode_batch_begin(H.batch_from_boundary(b, ctx.post_stride, 0, 0), capi.RUN_DEFAULT, 0, 0)
+    assert ctx.decode_batch_end().samples_per_channel == 0
+    out, res = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, 0, 1))
+    assert out.size == 0
+    out, res = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, 1, len(b.frames)), capi.RUN_CONTINUE | capi.RUN_EXACT)
+    np.testing.assert_array_equal(out, pcm)                     # ... and the stream continues from that tail
+    ctx.close()
+
+
+def test_empty_failed_and_single_packet_batches(shim):
+    _edge_batches(shim)

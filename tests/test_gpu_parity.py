@@ -285,3 +285,8 @@ def test_gpu_path_matches_independent_ffmpeg_decoder(name):
     n = min(len(got), len(want))
     assert n >= len(got) - 2048
     assert float(np.abs(got[:n] - np.clip(want[:n], -0.99999994, 0.99999994)).max()) <= TOL
+
+
+def test_empty_failed_and_single_packet_batches_on_gpu():
+    import test_cpu_shim
+    test_cpu_shim._edge_batches(None)
