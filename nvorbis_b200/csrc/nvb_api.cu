@@ -353,6 +353,7 @@ int nvb_host_free(void* p) {
 
 int nvb_upload_setup(nvb_ctx* ctx, const nvb_setup* setup) {
     if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
+    if (ctx->in_flight > 0) return set_err(ctx, NVB_ERR_STATE, "batches in flight");
     std::vector<unsigned char> blob; std::string err;
     int rc = build_blob(setup, blob, err);
     if (rc != NVB_OK) return set_err(ctx, rc, err);
@@ -374,6 +375,7 @@ int nvb_setup_blob_export(nvb_ctx* ctx, void* dst, size_t bytes) {
 }
 int nvb_setup_blob_import(nvb_ctx* ctx, const void* src, size_t bytes) {
     if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
+    if (ctx->in_flight > 0) return set_err(ctx, NVB_ERR_STATE, "batches in flight");
     std::string err;
     int rc = validate_blob(src, bytes, err);
     if (rc != NVB_OK) return set_err(ctx, rc, err);

@@ -38,8 +38,9 @@ namespace nvb {
 #define NVB_FUSED_WARPS 16
 #endif
 constexpr int FUSED_WARPS = NVB_FUSED_WARPS;
+constexpr int FUSED_CTAS_PER_SM = FUSED_WARPS <= 8 ? 2 : 1;      // 8-warp build: two half-size CTAs share an SM
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
-constexpr size_t FUSED_SMEM_LIMIT = 227 * 1024;
+constexpr size_t FUSED_SMEM_LIMIT = (FUSED_WARPS <= 8 ? 112 : 227) * 1024;
 
 struct FusedParams {
     LaunchArgs a;
@@ -106,7 +107,7 @@ __device__ __forceinline__ float slot_z(const DevSetup& S, const DevFrame& f, co
     return fused_y(slot, exec, f.n, i) * frame_window(S, f)[i];
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_fused(FusedParams p) {
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fused(FusedParams p) {
     NVB_DYN_SMEM(smem_raw);
     const LaunchArgs& a = p.a;
     const DevSetup& S = a.S;
@@ -360,7 +361,8 @@ int launch_imdct_fused(const LaunchArgs& a, const DevFrame*, void* stream) {
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
     // persistent: one CTA per SM, each a contiguous run of frames (at least 8, so that the halo block stays cheap)
-    int fpc = (a.n_frames + num_sms - 1) / num_sms;
+    const int ctas = num_sms * FUSED_CTAS_PER_SM;
+    int fpc = (a.n_frames + ctas - 1) / ctas;
     if (fpc < 8) fpc = 8;
     p.frames_per_cta = fpc;
     const int grid = (a.n_frames + fpc - 1) / fpc;
