@@ -20,6 +20,7 @@ SETUPS = {
     "three_ch_r0": dict(channels=3, bs0=512, bs1=4096, residue_type=0, coupling=[(1, 2)]),
     "mono_r1_big": dict(channels=1, bs0=1024, bs1=8192, residue_type=1),
     "stereo_r1": dict(channels=2, bs0=256, bs1=2048, residue_type=1, coupling=[(1, 0)], sequence_p=True),
+    "stereo_r2_48_posts": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], floor_posts=46),
     "stereo_floor0": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], floor_type=0),
     "quad_floor0_r1": dict(channels=4, bs0=128, bs1=1024, residue_type=1, coupling=[(0, 1), (2, 3)], floor_type=0),
 }
@@ -120,6 +121,7 @@ def test_unaligned_type2_residues_run_on_the_bins_kernel():
             "import test_synthetic_setups as T, helpers as H\n"
             "T.SETUPS['five_ch_r2'] = dict(channels=5, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1), (3, 4)])\n"
             "T.SETUPS['three_ch_r2'] = dict(channels=3, bs0=128, bs1=512, residue_type=2, coupling=[(2, 0)])\n"
-            "for name in ('six_ch_r2_coupled', 'five_ch_r2', 'three_ch_r2'):\n    T._run(name, 8, H.build_shim())\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"))
+            "T.SETUPS['six_ch_40_posts'] = dict(channels=6, bs0=256, bs1=1024, residue_type=2, coupling=[(0, 1)], floor_posts=38)\n"
+            "for name in ('six_ch_r2_coupled', 'five_ch_r2', 'three_ch_r2', 'six_ch_40_posts'):\n    T._run(name, 8, H.build_shim())\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"))
     env = dict(os.environ, NVB_SPECTRUM_FORBID_GENERIC="1")
     assert subprocess.check_output([sys.executable, "-c", code], env=env, timeout=600).decode().strip().endswith("ok")

@@ -142,7 +142,7 @@ def write_mapping(w: BitWriter, channels: int, coupling, floor: int, residue: in
 
 
 def build_stream(channels: int, bs0: int, bs1: int, residue_type: int = 2, coupling=(), lookup: int = 1, sequence_p: bool = False,
-                 rate: int = 44100, floor_type: int = 1):
+                 rate: int = 44100, floor_type: int = 1, floor_posts: int = 9):
     """Header packets of a synthetic stream: two floors / residues / mappings / modes (short, long).
     Books: 0 = class book (dims 2, entries 16 -> 4 classes), 1..3 = residue books (dims 2, 4, 8), 4 = floor book (scalar)."""
     w = BitWriter()
@@ -171,8 +171,15 @@ def build_stream(channels: int, bs0: int, bs1: int, residue_type: int = 2, coupl
             continue
         rb = ilog(n) - 1 if (1 << (ilog(n) - 1)) == n else ilog(n)                 # x_list[1] = 1 << rangebits = n
         w.put(1, 16)
-        inner = sorted(set(int(v) for v in np.unique(np.round(np.geomspace(2, n - 1, 9)))))
-        xs = [inner[:3], inner[3:6], inner[6:]]
+        if floor_posts <= 9:
+            inner = sorted(set(int(v) for v in np.unique(np.round(np.geomspace(2, n - 1, 9)))))
+            xs = [inner[:3], inner[3:6], inner[6:]]
+        else:                                                                      # more than 32 posts: the 64-bit mask paths of the kernels
+            cnt = min(floor_posts, n - 3)
+            inner = sorted(set(int(v) for v in np.unique(np.round(np.linspace(2, n - 1, cnt)))))
+            order = list(np.random.default_rng(n).permutation(len(inner)))          # posts are NOT stored in x order
+            inner = [inner[k] for k in order]
+            xs = [inner[k:k + 8] for k in range(0, len(inner), 8)]
         write_floor1(w, xs, 2, rb, None, 0, 4)
     w.put(2 - 1, 6)                                                                # residues
     for bs in (bs0, bs1):
