@@ -20,6 +20,8 @@ SETUPS = {
     "three_ch_r0": dict(channels=3, bs0=512, bs1=4096, residue_type=0, coupling=[(1, 2)]),
     "mono_r1_big": dict(channels=1, bs0=1024, bs1=8192, residue_type=1),
     "stereo_r1": dict(channels=2, bs0=256, bs1=2048, residue_type=1, coupling=[(1, 0)], sequence_p=True),
+    "stereo_r2_dims_1_16": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], lookup=2, res_dims=(1, 16, 8)),
+    "mono_r1_dims_1_16": dict(channels=1, bs0=256, bs1=2048, residue_type=1, lookup=2, res_dims=(16, 1, 4)),
     "stereo_r2_48_posts": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], floor_posts=46),
     "stereo_floor0": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], floor_type=0),
     "quad_floor0_r1": dict(channels=4, bs0=128, bs1=1024, residue_type=1, coupling=[(0, 1), (2, 3)], floor_type=0),

@@ -142,7 +142,7 @@ def write_mapping(w: BitWriter, channels: int, coupling, floor: int, residue: in
 
 
 def build_stream(channels: int, bs0: int, bs1: int, residue_type: int = 2, coupling=(), lookup: int = 1, sequence_p: bool = False,
-                 rate: int = 44100, floor_type: int = 1, floor_posts: int = 9):
+                 rate: int = 44100, floor_type: int = 1, floor_posts: int = 9, res_dims=(2, 4, 8)):
     """Header packets of a synthetic stream: two floors / residues / mappings / modes (short, long).
     Books: 0 = class book (dims 2, entries 16 -> 4 classes), 1..3 = residue books (dims 2, 4, 8), 4 = floor book (scalar)."""
     w = BitWriter()
@@ -155,9 +155,9 @@ def build_stream(channels: int, bs0: int, bs1: int, residue_type: int = 2, coupl
         write_codebook(w, 4, 81, 1, -0.75, 0.75, 2, sequence_p)                    # 2: 3 values per dim
         write_codebook(w, 8, 256, 1, -0.5, 1.0, 1, sequence_p)                     # 3: 2 values per dim
     else:
-        write_codebook(w, 2, 32, 2, -1.0, 0.125, 4, sequence_p)
-        write_codebook(w, 4, 64, 2, -0.5, 0.0625, 4, sequence_p)
-        write_codebook(w, 8, 128, 2, -0.25, 0.03125, 4, sequence_p)
+        write_codebook(w, res_dims[0], 32, 2, -1.0, 0.125, 4, sequence_p)
+        write_codebook(w, res_dims[1], 64, 2, -0.5, 0.0625, 4, sequence_p)
+        write_codebook(w, res_dims[2], 128, 2, -0.25, 0.03125, 4, sequence_p)
     write_codebook(w, 1, 128, 0)                                                   # 4: floor values (scalar, 7 bits)
     if floor_type == 0:
         write_codebook(w, 2, 49, 1, 0.1, 0.1, 3, False)                            # 5: LSP steps for floor 0 (7 values per dim)
