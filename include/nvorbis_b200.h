@@ -261,7 +261,8 @@ int nvb_decode_batch_end(nvb_ctx* ctx, nvb_result* res);
 int     nvb_dbatch_create(nvb_ctx* ctx, const nvb_batch* batch, int flags, nvb_dbatch** out);
 int64_t nvb_dbatch_samples(const nvb_dbatch* b);
 int     nvb_dbatch_run(nvb_ctx* ctx, nvb_dbatch* b, float* d_pcm, void* stream);
-int     nvb_dbatch_result(nvb_ctx* ctx, nvb_dbatch* b, void* stream, nvb_result* res);   /* synchronises `stream` */
+int     nvb_dbatch_result(nvb_ctx* ctx, nvb_dbatch* b, void* stream, nvb_result* res);   /* synchronises `stream`; has_clipped / n_floor_range
+                                                                                            cover the runs since the previous call (then cleared) */
 int     nvb_dbatch_destroy(nvb_ctx* ctx, nvb_dbatch* b);
 
 /* Stage entry points (same kernels, exposed for parity tests and for the roofline measurement):

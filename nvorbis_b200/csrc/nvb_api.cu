@@ -175,7 +175,11 @@ int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags,
     if (n_floor0 && (rc = grow(ctx, b->d_floor0, b->cap_floor0, n_floor0)) != NVB_OK) return rc;
     if ((rc = grow(ctx, b->d_spectrum, b->cap_spectrum, (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
     if (!b->fused && (rc = grow(ctx, b->d_blocks, b->cap_blocks, 2 * (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
-    if (!b->d_counters) { size_t cap = 0; if ((rc = grow(ctx, b->d_counters, cap, 1)) != NVB_OK) return rc; }
+    if (!b->d_counters) {
+        size_t cap = 0;
+        if ((rc = grow(ctx, b->d_counters, cap, 1)) != NVB_OK) return rc;
+        NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), st));
+    }
     const DevFrame* plan_src = b->plan.frames.data();
     if (pinned && nf) {                                                     // page-locked staging: the copy is truly asynchronous
         if (*pinned_cap < nf) {
@@ -223,7 +227,9 @@ int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pc
     LaunchArgs a = make_args(ctx, b, spectrum ? spectrum : b->d_spectrum, d_pcm, save_carry);
     if (frame_cnt >= 0) { a.frame_lo = frame_lo; a.n_frames = frame_cnt; }
     int launches = 0, r;
-    if (reset_counters) NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), st));
+    // the counters are cleared when they are read (fetch_result) or per batch (nvb_decode_batch_begin), not per run: a
+    // memset between the kernels of consecutive runs would serialise what programmatic dependent launch overlaps
+    (void)reset_counters;
     if (stage != 2) {
         if ((r = launch_spectrum(a, st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_spectrum launch");
         launches += r;
@@ -254,6 +260,7 @@ int fetch_result(nvb_ctx* ctx, nvb_dbatch* b, cudaStream_t st, nvb_result* res) 
     Counters c; std::memset(&c, 0, sizeof c);
     if (!b->plan.frames.empty()) {
         NVB_CUDA(ctx, cudaMemcpyAsync(&c, b->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
+        NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), st));
     }
     NVB_CUDA(ctx, cudaStreamSynchronize(st));
     if (res) {

@@ -831,10 +831,12 @@ __global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
     __shared__ int s_bad[2];
     __shared__ int s_careful[CT];                                           // some segment of the channel needs the plain division / range clamp
 
+    // Programmatic dependent launch: everything up to the first store only reads batch inputs and setup tables, none of
+    // which the previous kernel of the stream writes, so it runs while that kernel drains; the wait sits in front of the
+    // main loop, whose stores may overwrite a spectrum buffer the previous kernel still reads.
     nvb_grid_dep_launch();
-    nvb_grid_dep_wait();
     const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
-    if (f.kind != 0) return;
+    if (f.kind != 0) { nvb_grid_dep_wait(); return; }
     const DevSetup& S = a.S;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const RunMode rm = S.run_modes[f.mode];
@@ -879,6 +881,7 @@ __global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
         if (lane == 0) { s_mask[c] = mask; s_careful[c] = careful_any; }
     }
     __syncthreads();
+    nvb_grid_dep_wait();
 
     // ---- main: one run of 8 stream values per thread
     float* spec_out = a.spectrum + (size_t)f.spec_off;
@@ -1054,10 +1057,9 @@ __global__ void __launch_bounds__(NT) k_spectrum_bins(LaunchArgs a) {
     __shared__ int s_bad[2];
     __shared__ int s_careful[CT];
 
-    nvb_grid_dep_launch();
-    nvb_grid_dep_wait();
+    nvb_grid_dep_launch();                                                  // see k_spectrum_run
     const DevFrame f = a.frames[a.frame_lo + blockIdx.x];
-    if (f.kind != 0) return;
+    if (f.kind != 0) { nvb_grid_dep_wait(); return; }
     const DevSetup& S = a.S;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const RunMode rm = S.run_modes[f.mode];
@@ -1103,6 +1105,7 @@ __global__ void __launch_bounds__(NT) k_spectrum_bins(LaunchArgs a) {
         if (lane == 0) { s_mask[c] = mask; s_careful[c] = careful_any; }
     }
     __syncthreads();
+    nvb_grid_dep_wait();
 
     // ---- main: one bin per thread
     float* spec_out = a.spectrum + (size_t)f.spec_off;
