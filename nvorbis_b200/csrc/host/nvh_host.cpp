@@ -40,6 +40,10 @@ struct Bits {
     uint32_t peek32() const {
         const size_t byte = pos >> 3; const unsigned sh = pos & 7;
         const size_t nbytes = nbits >> 3;
+        if (byte + 8 <= nbytes) {                                             // common case: one unaligned 64-bit window, no masking (>= 57 bits left)
+            uint64_t w; std::memcpy(&w, p + byte, 8);
+            return (uint32_t)(w >> sh);
+        }
         uint64_t v = 0;
         for (size_t i = 0; i < 5 && byte + i < nbytes; i++) v |= (uint64_t)p[byte + i] << (8 * i);
         v >>= sh;
