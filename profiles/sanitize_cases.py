@@ -10,3 +10,33 @@ g.smoke()                                                    # 1test + 3test: k_
 for name in ("six_ch_r2_coupled", "stereo_floor0", "three_ch_r0", "tiny_blocks_r1_lookup2_seq"):
     T._run(name, 24, None, seed=5)                           # k_spectrum_bins / general kernel with type 0 floors / k_spectrum_fast / exact kernels
 print("sanitize cases ok")
+
+# malformed records: arbitrary posts / class bytes / entry numbers / truncated entry counts must be clamped, counted or
+# refused with NVB_ERR_DATA -- never read or written out of bounds (compute-sanitizer memcheck watches)
+import numpy as np
+from nvorbis_b200 import capi
+for name in ("3test", "1test"):
+    r, pcm, b = H.decoded(name)
+    nfr = min(40, len(b.frames))
+    for bad_entries in (False, True):
+        ctx = capi.Context(0); ctx.upload_setup(H.setup_from_oracle(r))
+        hb = H.batch_from_boundary(b, ctx.post_stride, 0, nfr)
+        rng = np.random.default_rng(99)
+        posts = hb.posts.copy(); classes = hb.classes.copy(); entries = hb.entries.copy(); frames = hb.frames.copy()
+        posts[rng.random(posts.size) < 0.3] = rng.integers(-32768, 32767, 1, dtype=np.int16)[0]
+        posts.reshape(nfr, -1, ctx.post_stride)[:, :, 0] = rng.integers(-3, 70, (nfr, posts.size // (nfr * ctx.post_stride)))
+        classes[rng.random(classes.size) < 0.2] = 255
+        if bad_entries:
+            entries[rng.random(entries.size) < 0.1] = 65535
+        frames["entry_count"] = (frames["entry_count"] * rng.random(nfr)).astype(np.uint32)
+        bad = capi.HostBatch(frames, posts, classes, entries)
+        for flags in (capi.RUN_DEFAULT, capi.RUN_EXACT):
+            try:
+                out, res = ctx.decode_batch(bad, flags)
+                print("fuzz", name, flags, "ok: floor_range", res.n_floor_range, "finite", bool(np.isfinite(out).all()))
+            except capi.NvbError as e:
+                assert e.status == capi.ERR_DATA, e
+                print("fuzz", name, flags, "refused: ERR_DATA")
+            ctx.reset()
+        ctx.close()
+print("fuzz cases ok")
