@@ -1810,7 +1810,8 @@ int64_t orc_synth_batch(void* hh, const SynthFrame* frames, int64_t nFrames, con
         int T = g_synthThreads; if (T > nFrames) T = (int)std::max<int64_t>(1, nFrames);
         if (T <= 1) {
             bool c = false; int64_t w = SynthRun(d, frames, 0, nFrames, false, posts, postCounts, classes, entries, pcm, pcmCapPerChannel, c);
-            if (clipped) *clipped = c; return w;
+            if (clipped) *clipped = c;
+            return w;
         }
         // multi-threaded: only for batches without drain frames (all ok); offsets by prefix sum
         for (int64_t i = 0; i < nFrames; i++) if (!frames[i].ok) throw InvalidData("threads>1 requires all frames ok");
