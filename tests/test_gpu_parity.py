@@ -290,3 +290,31 @@ def test_gpu_path_matches_independent_ffmpeg_decoder(name):
 def test_empty_failed_and_single_packet_batches_on_gpu():
     import test_cpu_shim
     test_cpu_shim._edge_batches(None)
+
+
+def test_config5_64k_frames_in_eight_shards():
+    """BASELINE configs[4] at full size: a 65 536-frame stereo corpus cut into 8 contiguous shards (+1 halo frame each,
+    nvorbis_b200/sharding.py), each decoded from a fresh decoder state as a rank would (here one after the other on one
+    GPU): the concatenation equals the oracle's decode of the whole corpus, so shards need no data-path exchange."""
+    import bench
+    from nvorbis_b200 import sharding
+    desc, z = setupio.load(bench.POOL)
+    pool = workloads.FramePool.from_npz(desc, z)
+    corpus = workloads.config2(pool, 65536, 20240005)
+    ctx = capi.Context(0)
+    ctx.upload_setup(setupio.to_setup(desc))
+    cuts = sharding.shard_cuts(corpus.frames, 8)
+    assert cuts == [8192 * k for k in range(9)]
+    parts = []
+    for rank in range(8):
+        ctx.reset()
+        out, res = ctx.decode_batch(sharding.take_shard(corpus, cuts, rank, 2))
+        assert res.samples_per_channel == (8192 - (1 if rank == 0 else 0)) * 1024
+        parts.append(out.copy())
+    got = np.concatenate(parts)
+    r = H.O.OracleReader(H.packets("3test"))
+    fr, posts, pc, cls, ent = bench.oracle_inputs(corpus)
+    want, _ = r.synth_batch(fr, posts, pc, cls, ent, 65536 * 1024 + 8192, threads=os.cpu_count() or 1)
+    assert got.size == want.size == 65535 * 1024 * 2
+    assert float(np.abs(got - want).max()) <= TOL
+    ctx.close()
