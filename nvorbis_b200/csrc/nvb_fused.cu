@@ -350,8 +350,11 @@ int launch_imdct_fused(const LaunchArgs& a, const DevFrame*, void* stream) {
     const int C = a.S.channels;
     FusedParams p; p.a = a; p.n_slots = fused_slots(C);
     const size_t smem = fused_smem(C, p.n_slots);
-    static size_t configured = 0;
-    static int num_sms = 0;
+    static size_t configured_by_dev[64] = {0};
+    static int num_sms_by_dev[64] = {0};
+    int dev_slot = 0; cudaGetDevice(&dev_slot); if (dev_slot < 0 || dev_slot >= 64) dev_slot = 0;
+    size_t& configured = configured_by_dev[dev_slot];
+    int& num_sms = num_sms_by_dev[dev_slot];
     if (smem > configured) {
         if (cudaFuncSetAttribute(k_imdct_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = smem;

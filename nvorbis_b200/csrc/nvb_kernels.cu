@@ -1469,6 +1469,12 @@ __global__ void __launch_bounds__(OLA_THREADS) k_ola(LaunchArgs a) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+
+// Launch-configuration caches are per device: cudaFuncSetAttribute applies to the current device's context only, and one
+// process may hold contexts on several GPUs.
+constexpr int NVB_MAX_DEVICES = 64;
+static inline int current_device_slot() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < NVB_MAX_DEVICES) ? d : 0; }
+
 static size_t spectrum_smem(const DevSetup& S) {
     size_t b = (size_t)(((S.max_items > 0 ? S.max_items : 1) + 3) & ~3) * sizeof(uint32_t);
     if (S.f0_stride > 0) b += (size_t)S.channels * ((S.bs[1] >> 1) + 256) * sizeof(float);     // type 0 floors: curve + coefficient tables
@@ -1512,8 +1518,8 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
                 if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
             }
             const size_t smem = shared_part + (size_t)nw * L.total;
-            static size_t configured_w_by_c[NVB_MAX_CHANNELS + 1] = {0};    // per template instantiation
-            size_t& configured_w = configured_w_by_c[C];
+            static size_t configured_w_by_c[NVB_MAX_DEVICES][NVB_MAX_CHANNELS + 1] = {{0}};    // per device and template instantiation
+            size_t& configured_w = configured_w_by_c[current_device_slot()][C];
             if (smem > configured_w) {
                 cudaError_t e = C == 1 ? cudaFuncSetAttribute(k_spectrum_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                               : C == 2 ? cudaFuncSetAttribute(k_spectrum_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -1552,8 +1558,8 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         const size_t span = (size_t)C * (a.S.bs[1] / 2) * sizeof(float);
         const size_t smem = span * (size_t)(a.S.max_stages + 1) + (((size_t)a.S.max_items * sizeof(ItemRec) + 15) & ~size_t(15)) +
                             (((size_t)a.S.max_items + 15) & ~size_t(15)) + (size_t)a.S.ci_total * sizeof(int4) + 16;
-        static size_t configured_pl_by_c[NVB_MAX_CHANNELS + 1] = {0};       // per template instantiation
-        size_t& configured_pl = configured_pl_by_c[C];
+        static size_t configured_pl_by_c[NVB_MAX_DEVICES][NVB_MAX_CHANNELS + 1] = {{0}};       // per device and template instantiation
+        size_t& configured_pl = configured_pl_by_c[current_device_slot()][C];
         if (smem > configured_pl) {
             cudaError_t e = C == 1 ? cudaFuncSetAttribute(k_spectrum_planes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                           : C == 2 ? cudaFuncSetAttribute(k_spectrum_planes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -1569,7 +1575,8 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
     const size_t smem = spectrum_smem(a.S) + (size_t)a.S.channels * (a.S.bs[1] / 2) * sizeof(float);
-    static size_t configured = 0;
+    static size_t configured_by_dev[NVB_MAX_DEVICES] = {0};
+    size_t& configured = configured_by_dev[current_device_slot()];
     if (smem > 24 * 1024 && smem > configured) {
         if (cudaFuncSetAttribute(k_spectrum_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = smem;
@@ -1583,7 +1590,8 @@ int launch_spectrum_generic(const LaunchArgs& a, void* stream) {
     static const bool forbid = std::getenv("NVB_SPECTRUM_FORBID_GENERIC") != nullptr;           // test hook: prove a faster kernel covers the setup
     if (forbid) return -1;
     size_t smem = spectrum_smem(a.S);
-    static size_t configured = 0;
+    static size_t configured_by_dev[NVB_MAX_DEVICES] = {0};
+    size_t& configured = configured_by_dev[current_device_slot()];
     if (smem > 48 * 1024 - 8192 && smem > configured) {
         if (cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = smem;
@@ -1595,7 +1603,8 @@ int launch_spectrum_generic(const LaunchArgs& a, void* stream) {
 int launch_imdct_exact(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
     size_t smem = (size_t)(a.S.bs[1] + a.S.bs[1] / 2) * sizeof(float);
-    static size_t configured = 0;
+    static size_t configured_by_dev[NVB_MAX_DEVICES] = {0};
+    size_t& configured = configured_by_dev[current_device_slot()];
     if (smem > 40 * 1024 && smem > configured) {
         if (cudaFuncSetAttribute(k_imdct_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = smem;

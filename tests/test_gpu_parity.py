@@ -318,3 +318,20 @@ def test_config5_64k_frames_in_eight_shards():
     assert got.size == want.size == 65535 * 1024 * 2
     assert float(np.abs(got - want).max()) <= TOL
     ctx.close()
+
+
+def test_two_contexts_on_two_devices_in_one_process():
+    """One process, two GPUs: the launch configuration of every kernel is set per device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    r, pcm, b = H.decoded("3test")
+    outs = []
+    for dev in (0, 1):
+        ctx = capi.Context(dev)
+        ctx.upload_setup(H.setup_from_oracle(r))
+        out, res = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride))
+        outs.append(out.copy())
+        ctx.close()
+    np.testing.assert_array_equal(outs[0], outs[1])
+    assert float(np.abs(outs[0] - pcm).max()) <= TOL
