@@ -30,6 +30,7 @@
 #if !defined(NVB_CPU_SHIM)
 #include <cuda_runtime.h>
 #endif
+#include <cstdlib>
 #include "nvb_fused_core.h"
 
 namespace nvb {
@@ -102,9 +103,53 @@ __device__ __forceinline__ float clipf(float v, float& peak) {
 }
 
 // Windowed block value z[i] = y[i] * window[i] of the block held in `slot` (Mode.cs:159-166).
-__device__ __forceinline__ float slot_z(const DevSetup& S, const DevFrame& f, const float* slot, int c, int i) {
+__device__ __forceinline__ float slot_z(const DevSetup& S, const DevFrame& f, const float* slot, int c, int i, bool swz = true) {
     const bool exec = (f.exec_mask >> c) & 1u;
-    return fused_y(slot, exec, f.n, i) * frame_window(S, f)[i];
+    return fused_y(slot, exec, f.n, i, swz) * frame_window(S, f)[i];
+}
+
+// Output of one frame for every shape the TDAC fast path of k_imdct_fused does not cover (short blocks, window transitions,
+// silent channels, drains, C != 2) and for all of k_imdct_generic: lanes over samples, channels in an inner loop; the index of
+// y[i] inside a slot (fused_y_index) and the window values are per-sample.  slot stride per channel = slot_floats.
+template <bool SWZ>
+__device__ __forceinline__ void emit_samples(const LaunchArgs& a, const DevSetup& S, const DevFrame& f, const DevFrame* pf, const float* slots_f,
+                                             const float* slots_p, int slot_floats, int lane, float& peak) {
+    const int C = S.channels;
+    const int len = f.out_end - f.out_begin;
+    const float* wf = f.kind == 0 ? frame_window(S, f) : nullptr;
+    const float* wp = pf ? frame_window(S, *pf) : nullptr;
+    const int nf_ = f.n, np_ = pf ? pf->n : 0;
+    const uint32_t ex_f = f.exec_mask, ex_p = pf ? pf->exec_mask : 0u;
+    const bool clip = a.clip != 0;
+    for (int s = lane; s < len; s += 32) {
+        const int i = f.out_begin + s;
+        const int o = i - f.start;
+        const bool ola = f.kind == 0 && f.ola_len > 0 && o >= 0 && o < f.ola_len;          // StreamDecoder.cs:532-541
+        const int ip = f.kind == 0 ? f.prev_valid + o : i;                               // sample of the previous block (overlap or drain)
+        const bool use_p = ola || f.kind != 0;
+        float wv = 0.f, wpv = 0.f;
+        int jf = 0, jp = 0; float sf = 0.f, sp = 0.f;
+        if (f.kind == 0) { wv = wf[i]; fused_y_index(nf_, i, jf, sf, SWZ); }
+        if (use_p && pf) { wpv = wp[ip]; fused_y_index(np_, ip, jp, sp, SWZ); }
+        float* dst = a.pcm + ((size_t)f.pcm_off + s) * C;
+        for (int c = 0; c < C; c++) {
+            float v = 0.f;
+            if (f.kind == 0) {
+                const float* sl = slots_f + (size_t)c * slot_floats;
+                const float y = ((ex_f >> c) & 1u) ? sf * sl[jf] : (i < (nf_ >> 1) ? sl[i] : 0.f);
+                v = y * wv;
+            }
+            if (use_p) {
+                if (pf) {
+                    const float* sl = slots_p + (size_t)c * slot_floats;
+                    const float y = ((ex_p >> c) & 1u) ? sp * sl[jp] : (ip < (np_ >> 1) ? sl[ip] : 0.f);
+                    v += y * wpv;
+                } else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)c * S.bs[1] + ip];
+            }
+            if (clip) v = clipf(v, peak);
+            dst[c] = v;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fused(FusedParams p) {
@@ -274,42 +319,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
                     out[511 - lane - 32 * k] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
                 }
             } else if (len > 0) {
-                // every other shape (short blocks, window transitions, silent channels, drains, C != 2): lanes over samples,
-                // channels in an inner loop; the index of y[i] inside a slot (fused_y) and the window values are per-sample
-                const float* wf = f.kind == 0 ? frame_window(S, f) : nullptr;
-                const float* wp = pf ? frame_window(S, *pf) : nullptr;
-                const int nf_ = f.n, np_ = pf ? pf->n : 0;
-                const uint32_t ex_f = f.exec_mask, ex_p = pf ? pf->exec_mask : 0u;
-                const bool clip = a.clip != 0;
-                for (int s = lane; s < len; s += 32) {
-                    const int i = f.out_begin + s;
-                    const int o = i - f.start;
-                    const bool ola = f.kind == 0 && f.ola_len > 0 && o >= 0 && o < f.ola_len;          // StreamDecoder.cs:532-541
-                    const int ip = f.kind == 0 ? f.prev_valid + o : i;                               // sample of the previous block (overlap or drain)
-                    const bool use_p = ola || f.kind != 0;
-                    float wv = 0.f, wpv = 0.f;
-                    int jf = 0, jp = 0; float sf = 0.f, sp = 0.f;
-                    if (f.kind == 0) { wv = wf[i]; fused_y_index(nf_, i, jf, sf); }
-                    if (use_p && pf) { wpv = wp[ip]; fused_y_index(np_, ip, jp, sp); }
-                    float* dst = a.pcm + ((size_t)f.pcm_off + s) * C;
-                    for (int c = 0; c < C; c++) {
-                        float v = 0.f;
-                        if (f.kind == 0) {
-                            const float* sl = slots_f + c * FUSED_SLOT_FLOATS;
-                            const float y = ((ex_f >> c) & 1u) ? sf * sl[jf] : (i < (nf_ >> 1) ? sl[i] : 0.f);
-                            v = y * wv;
-                        }
-                        if (use_p) {
-                            if (pf) {
-                                const float* sl = slots_p + c * FUSED_SLOT_FLOATS;
-                                const float y = ((ex_p >> c) & 1u) ? sp * sl[jp] : (ip < (np_ >> 1) ? sl[ip] : 0.f);
-                                v += y * wpv;
-                            } else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)c * S.bs[1] + ip];
-                        }
-                        if (clip) v = clipf(v, peak);
-                        dst[c] = v;
-                    }
-                }
+                emit_samples<true>(a, S, f, pf, slots_f, slots_p, FUSED_SLOT_FLOATS, lane, peak);
             }
             if (x == a.carry_frame && a.carry_out && f.kind == 0) {
                 // keep the last windowed block for the next batch (StreamDecoder.cs:455-461)
@@ -329,6 +339,137 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_imdct_generic -- the same fused IMDCT + window + overlap-add + clip + interleave for every other pair of block sizes
+// from 256 up (e.g. 512/1024, 512/4096, 1024/8192; the reference's Mdct does not compute an IMDCT below 256, so those
+// sizes stay on the exact kernels).  Same persistent CTAs, slot ring and release/acquire counters as k_imdct_fused; the
+// transform is the generic form of the same factorisation: pre-twiddle, radix-2 Stockham FFT of N/4 complex points by
+// one warp inside the frame's slot (two ping-pong buffers of N/2 floats), post-twiddle into u[0 .. N/2); twiddles come
+// from the setup's per-block-size tables (L1-resident).  Slot = N_long floats per channel.
+// ------------------------------------------------------------------------------------------------
+struct GenericParams {
+    LaunchArgs a;
+    int frames_per_cta;
+    int n_slots;
+    int slot_floats;
+};
+
+__device__ __forceinline__ void generic_transform(int lane, int N, const float* spec, const float2* tw, const float2* fft, float* slot) {
+    const int M = N >> 1, Q = N >> 2;
+    int S = 0; while ((1 << S) < Q) ++S;                                    // log2 Q stages
+    float2* A = reinterpret_cast<float2*>(slot);
+    float2* B = A + Q;
+    // the last stage must leave the spectrum in B (the post-twiddle writes u over A)
+    float2* x = (S & 1) ? A : B;
+    float2* y = (S & 1) ? B : A;
+    for (int k = lane; k < Q; k += 32) {                                    // c[k] = (X[2k] + i X[M-1-2k]) tw[k]
+        cpx c, t; c.x = spec[2 * k]; c.y = spec[M - 1 - 2 * k];
+        const float2 w = tw[k]; t.x = w.x; t.y = w.y;
+        c = cmul(c, t);
+        x[k] = make_float2(c.x, c.y);
+    }
+    __syncwarp();
+    for (int l = Q >> 1, m = 1, lm = 0; l >= 1; l >>= 1, m <<= 1, ++lm) {    // Stockham autosort, forward DFT
+        for (int b = lane; b < (Q >> 1); b += 32) {
+            const int j = b >> lm, k = b & (m - 1);
+            const float2 w = fft[j << lm];                                  // exp(-2 pi i j / (2 l)) = exp(-2 pi i j m / Q)
+            const float2 v0 = x[k + (j << lm)], v1 = x[k + (j << lm) + l * m];
+            cpx c0, c1, t; c0.x = v0.x; c0.y = v0.y; c1.x = v1.x; c1.y = v1.y; t.x = w.x; t.y = w.y;
+            const cpx s0 = cadd(c0, c1), s1 = cmul(csub(c0, c1), t);
+            y[k + (j << (lm + 1))] = make_float2(s0.x, s0.y);
+            y[k + (j << (lm + 1)) + m] = make_float2(s1.x, s1.y);
+        }
+        __syncwarp();
+        float2* tmp = x; x = y; y = tmp;
+    }
+    for (int n = lane; n < Q; n += 32) {                                    // D[n] = C[n] tw[n]; u[2n] = Re D, u[M-1-2n] = -Im D
+        cpx c, t; const float2 v = x[n], w = tw[n];
+        c.x = v.x; c.y = v.y; t.x = w.x; t.y = w.y;
+        c = cmul(c, t);
+        slot[2 * n] = c.x; slot[M - 1 - 2 * n] = -c.y;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_generic(GenericParams p) {
+    NVB_DYN_SMEM(smem_raw);
+    const LaunchArgs& a = p.a;
+    const DevSetup& S = a.S;
+    const int C = S.channels;
+    const int NS = p.n_slots, SLOT = p.slot_floats;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    float* s_slots = reinterpret_cast<float*>(smem_raw);
+    DevFrame* s_fr = reinterpret_cast<DevFrame*>(s_slots + (size_t)NS * C * SLOT);
+    int* s_full = reinterpret_cast<int*>(s_fr + NS);
+    int* s_empty = s_full + NS;
+
+    const int lo = a.frame_lo + blockIdx.x * p.frames_per_cta;
+    int hi = lo + p.frames_per_cta; if (hi > a.frame_lo + a.n_frames) hi = a.frame_lo + a.n_frames;
+    nvb_grid_dep_launch();
+    if (lo >= hi) return;
+    if (tid == 0) for (int s = 0; s < NS; s++) { s_full[s] = 0; s_empty[s] = 0; }
+    __syncthreads();
+    nvb_grid_dep_wait();
+    int first = lo;
+    {
+        const DevFrame f0 = a.frames[lo];
+        if (f0.prev >= 0 && (f0.ola_len > 0 || f0.kind != 0)) first = lo - 1;   // halo: previous block's tail is needed
+    }
+    float peak = 0.f;
+    for (int x = first + warp; x < hi; x += FUSED_WARPS) {
+        const int rel = x - first, slot = rel % NS, it = rel / NS;
+        cnt_wait(&s_empty[slot], 2 * it);
+        if (lane == 0) s_fr[slot] = a.frames[x];
+        __syncwarp();
+        const DevFrame f = s_fr[slot];
+        float* slots_f = s_slots + (size_t)slot * C * SLOT;
+        if (f.kind == 0) {
+            const int bi = f.n == S.bs[1] ? 1 : 0;
+            const int M = f.n >> 1;
+            for (int c = 0; c < C; c++) {
+                float* slotc = slots_f + (size_t)c * SLOT;
+                const float* spec = a.spectrum + (size_t)f.spec_off + (size_t)c * M;
+                if (!((f.exec_mask >> c) & 1u)) { for (int i = lane; i < M; i += 32) slotc[i] = spec[i]; }   // raw residue values (Mapping.cs:192-196)
+                else generic_transform(lane, f.n, spec, S.tw[bi], S.fft[bi], slotc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) cnt_signal(&s_full[slot]);
+        if (rel >= 1) cnt_wait(&s_full[(rel - 1) % NS], (rel - 1) / NS + 1);
+        if (x >= lo) {
+            const DevFrame* pf = nullptr; const float* slots_p = nullptr;
+            if (f.prev >= 0 && (f.ola_len > 0 || f.kind != 0)) {
+                const int pslot = (f.prev - first) % NS;
+                pf = &s_fr[pslot]; slots_p = s_slots + (size_t)pslot * C * SLOT;
+            }
+            if (f.out_end > f.out_begin) emit_samples<false>(a, S, f, pf, slots_f, slots_p, SLOT, lane, peak);
+            if (x == a.carry_frame && a.carry_out && f.kind == 0) {
+                for (int idx = lane; idx < f.n * C; idx += 32) {            // keep the last windowed block for the next batch (StreamDecoder.cs:455-461)
+                    const int c = idx / f.n, i = idx - c * f.n;
+                    a.carry_out[(size_t)c * S.bs[1] + i] = slot_z(S, f, slots_f + (size_t)c * SLOT, c, i, false);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            cnt_signal(&s_empty[slot]);
+            if (rel >= 1) cnt_signal(&s_empty[(rel - 1) % NS]);
+        }
+    }
+    if (__any_sync(0xffffffffu, peak > 0.99999994f) && lane == 0) atomicOr(&a.counters->clipped, 1);
+}
+
+static int generic_slots(int C, int bs1) {
+    const size_t per = (size_t)C * bs1 * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
+    int ns = (int)((227 * 1024 - 64) / per);
+    if (ns > FUSED_WARPS + 2) ns = FUSED_WARPS + 2;
+    return ns;
+}
+static bool generic_supported(const BlobHeader& h) {
+    return h.bs[0] >= 256 && h.bs[1] <= 8192 && h.channels >= 1 && h.channels <= NVB_MAX_CHANNELS && generic_slots(h.channels, h.bs[1]) >= 3;
+}
+
+// ------------------------------------------------------------------------------------------------
 static int fused_slots(int C) {
     const size_t fixed = FusedTables::FLOATS * sizeof(float) + 64;
     const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
@@ -340,13 +481,38 @@ static size_t fused_smem(int C, int NS) {
     return FusedTables::FLOATS * sizeof(float) + (size_t)NS * ((size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int)) + 32;
 }
 
-bool fused_supported(const BlobHeader& h, const DevFrame*, int) {
+static bool classic_supported(const BlobHeader& h) {
     return h.bs[1] == FUSED_LONG_N && h.bs[0] == FUSED_SHORT_N && h.off_fused_tab != 0 && h.channels >= 1 && h.channels <= NVB_MAX_CHANNELS &&
            fused_slots(h.channels) >= 3;
+}
+bool fused_supported(const BlobHeader& h, const DevFrame*, int) {
+    static const bool no_generic = std::getenv("NVB_NO_GENERIC_IMDCT") != nullptr;        // test hook: other block sizes on the exact kernels
+    return classic_supported(h) || (!no_generic && generic_supported(h));
+}
+
+static int launch_imdct_generic(const LaunchArgs& a, void* stream) {
+    const int C = a.S.channels;
+    GenericParams p; p.a = a; p.n_slots = generic_slots(C, a.S.bs[1]); p.slot_floats = a.S.bs[1];
+    const size_t smem = (size_t)p.n_slots * ((size_t)C * p.slot_floats * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int)) + 32;
+    static size_t configured_by_dev[64] = {0};
+    static int num_sms_by_dev[64] = {0};
+    int dev_slot = 0; cudaGetDevice(&dev_slot); if (dev_slot < 0 || dev_slot >= 64) dev_slot = 0;
+    if (smem > configured_by_dev[dev_slot]) {
+        if (cudaFuncSetAttribute(k_imdct_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured_by_dev[dev_slot] = smem;
+    }
+    int& num_sms = num_sms_by_dev[dev_slot];
+    if (num_sms == 0 && (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev_slot) != cudaSuccess || num_sms <= 0)) num_sms = 148;
+    int fpc = (a.n_frames + num_sms - 1) / num_sms;
+    if (fpc < 8) fpc = 8;
+    p.frames_per_cta = fpc;
+    NVB_LAUNCH(k_imdct_generic, (a.n_frames + fpc - 1) / fpc, FUSED_THREADS, smem, stream, p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_imdct_fused(const LaunchArgs& a, const DevFrame*, void* stream) {
     if (a.n_frames <= 0) return 0;
+    if (!(a.S.bs[0] == FUSED_SHORT_N && a.S.bs[1] == FUSED_LONG_N && a.S.fused_tab)) return launch_imdct_generic(a, stream);
     const int C = a.S.channels;
     FusedParams p; p.a = a; p.n_slots = fused_slots(C);
     const size_t smem = fused_smem(C, p.n_slots);

@@ -230,22 +230,20 @@ NVB_HD void short_phase3_store(int l, const float2* tw64, float* u, const ShortR
 // Un-windowed block value y[i] of a slot: u (executed channel) or the raw spectrum (Mapping.cs:192-196).
 // Only the u of an executed long block is swizzled.
 // Where y[i] of an executed channel sits inside its slot: y[i] = sgn * slot[j].
-NVB_HD void fused_y_index(int N, int i, int& j, float& sgn) {
+// swz: the slot holds the swizzled u of the specialised N = 2048 transform (k_imdct_fused); k_imdct_generic stores u plainly.
+NVB_HD void fused_y_index(int N, int i, int& j, float& sgn, bool swz = true) {
     const int M = N >> 1, h = M >> 1;
     if (i < h) { j = i + h; sgn = 1.f; }
     else if (i < M + h) { j = M + h - 1 - i; sgn = -1.f; }
     else { j = i - M - h; sgn = -1.f; }
-    if (N == FUSED_LONG_N) j = u_swz(j);
+    if (swz && N == FUSED_LONG_N) j = u_swz(j);
 }
 
-NVB_HD float fused_y(const float* slot, bool exec, int N, int i) {
-    const int M = N >> 1, h = M >> 1;
+NVB_HD float fused_y(const float* slot, bool exec, int N, int i, bool swz = true) {
+    const int M = N >> 1;
     if (!exec) return i < M ? slot[i] : 0.f;
     int j; float sgn;
-    if (i < h) { j = i + h; sgn = 1.f; }
-    else if (i < M + h) { j = M + h - 1 - i; sgn = -1.f; }
-    else { j = i - M - h; sgn = -1.f; }
-    if (N == FUSED_LONG_N) j = u_swz(j);
+    fused_y_index(N, i, j, sgn, swz);
     return sgn * slot[j];
 }
 

@@ -65,7 +65,8 @@ def main():
     import helpers as H
     from oracle import oracle as O
     cases = [("configs[3] 6-channel coupled N=2048", dict(channels=6, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 2), (3, 4), (0, 1)]), 8192, 0.0),
-             ("mono N=8192 residue 1 (exact kernels)", dict(channels=1, bs0=1024, bs1=8192, residue_type=1), 2048, 0.0),
+             ("mono N=8192 residue 1 (k_imdct_generic)", dict(channels=1, bs0=1024, bs1=8192, residue_type=1), 2048, 0.0),
+             ("stereo N=512/1024 (k_imdct_generic)", dict(channels=2, bs0=512, bs1=1024, residue_type=2, coupling=[(0, 1)]), 8192, 0.3),
              ("stereo N=128/64 lookup 2 (exact kernels)", dict(channels=2, bs0=64, bs1=128, residue_type=1, coupling=[(0, 1)], lookup=2, sequence_p=True), 16384, 0.3),
              ("stereo floor 0 N=2048", dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], floor_type=0), 4096, 0.0)]
     for name, kw, n, sp in cases:

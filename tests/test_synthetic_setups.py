@@ -20,6 +20,9 @@ SETUPS = {
     "three_ch_r0": dict(channels=3, bs0=512, bs1=4096, residue_type=0, coupling=[(1, 2)]),
     "mono_r1_big": dict(channels=1, bs0=1024, bs1=8192, residue_type=1),
     "stereo_r1": dict(channels=2, bs0=256, bs1=2048, residue_type=1, coupling=[(1, 0)], sequence_p=True),
+    "stereo_512_1024": dict(channels=2, bs0=512, bs1=1024, residue_type=2, coupling=[(0, 1)]),
+    "stereo_1024_2048": dict(channels=2, bs0=1024, bs1=2048, residue_type=2, coupling=[(0, 1)]),
+    "stereo_512_4096": dict(channels=2, bs0=512, bs1=4096, residue_type=2, coupling=[(0, 1)]),
     "stereo_r2_dims_1_16": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], lookup=2, res_dims=(1, 16, 8)),
     "mono_r1_dims_1_16": dict(channels=1, bs0=256, bs1=2048, residue_type=1, lookup=2, res_dims=(16, 1, 4)),
     "stereo_r2_48_posts": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], floor_posts=46),
@@ -127,3 +130,23 @@ def test_unaligned_type2_residues_run_on_the_bins_kernel():
             "for name in ('six_ch_r2_coupled', 'five_ch_r2', 'three_ch_r2', 'six_ch_40_posts'):\n    T._run(name, 8, H.build_shim())\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"))
     env = dict(os.environ, NVB_SPECTRUM_FORBID_GENERIC="1")
     assert subprocess.check_output([sys.executable, "-c", code], env=env, timeout=600).decode().strip().endswith("ok")
+
+
+def test_block_sizes_from_256_up_run_on_the_fused_path():
+    """Every pair of block sizes >= 256 decodes with two kernels (spectrum + fused IMDCT/window/OLA: k_imdct_fused for
+    256/2048, k_imdct_generic otherwise); sizes below 256, where the reference's Mdct is not an IMDCT, take the exact
+    kernels (three launches)."""
+    shim = H.build_shim()
+    for name, want in (("stereo_r2", 2), ("stereo_512_1024", 2), ("stereo_512_4096", 2), ("mono_r1_big", 2), ("three_ch_r0", 2),
+                       ("tiny_blocks_r1_lookup2_seq", 3), ("quad_floor0_r1", 3)):
+        d, s_, g, f = VH.build_stream(**SETUPS[name])
+        host = hostlib.HostStream(packets=(d, s_, g, f))
+        desc = H.desc_from_oracle(O.OracleReader(O.PacketList(d, s_, g, f)))
+        hb = VH.random_records(np.random.default_rng(3), desc, 6, host.post_stride, floor0_stride=host.floor0_stride)
+        ctx = capi.Context(0, lib_path=shim)
+        ctx.upload_setup(host.setup())
+        db = ctx.create_dbatch(hb)
+        pcm = np.zeros(db.samples * desc["channels"] + 16, np.float32)
+        db.run(pcm.ctypes.data, 0)
+        assert db.launches == want, (name, db.launches)
+        db.destroy(); ctx.close()
