@@ -113,8 +113,8 @@ __device__ __forceinline__ float slot_z(const DevSetup& S, const DevFrame& f, co
 // y[i] inside a slot (fused_y_index) and the window values are per-sample.  slot stride per channel = slot_floats.
 template <bool SWZ>
 __device__ __forceinline__ void emit_samples(const LaunchArgs& a, const DevSetup& S, const DevFrame& f, const DevFrame* pf, const float* slots_f,
-                                             const float* slots_p, int slot_floats, int lane, float& peak) {
-    const int C = S.channels;
+                                             const float* slots_p, int slot_floats, int lane, float& peak, int cbase, int G) {
+    const int C = S.channels;                                               // row stride of the interleave; the unit covers channels cbase .. cbase + G - 1
     const int len = f.out_end - f.out_begin;
     const float* wf = f.kind == 0 ? frame_window(S, f) : nullptr;
     const float* wp = pf ? frame_window(S, *pf) : nullptr;
@@ -131,20 +131,20 @@ __device__ __forceinline__ void emit_samples(const LaunchArgs& a, const DevSetup
         int jf = 0, jp = 0; float sf = 0.f, sp = 0.f;
         if (f.kind == 0) { wv = wf[i]; fused_y_index(nf_, i, jf, sf, SWZ); }
         if (use_p && pf) { wpv = wp[ip]; fused_y_index(np_, ip, jp, sp, SWZ); }
-        float* dst = a.pcm + ((size_t)f.pcm_off + s) * C;
-        for (int c = 0; c < C; c++) {
+        float* dst = a.pcm + ((size_t)f.pcm_off + s) * C + cbase;
+        for (int c = 0; c < G; c++) {
             float v = 0.f;
             if (f.kind == 0) {
                 const float* sl = slots_f + (size_t)c * slot_floats;
-                const float y = ((ex_f >> c) & 1u) ? sf * sl[jf] : (i < (nf_ >> 1) ? sl[i] : 0.f);
+                const float y = ((ex_f >> (cbase + c)) & 1u) ? sf * sl[jf] : (i < (nf_ >> 1) ? sl[i] : 0.f);
                 v = y * wv;
             }
             if (use_p) {
                 if (pf) {
                     const float* sl = slots_p + (size_t)c * slot_floats;
-                    const float y = ((ex_p >> c) & 1u) ? sp * sl[jp] : (ip < (np_ >> 1) ? sl[ip] : 0.f);
+                    const float y = ((ex_p >> (cbase + c)) & 1u) ? sp * sl[jp] : (ip < (np_ >> 1) ? sl[ip] : 0.f);
                     v += y * wpv;
-                } else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)c * S.bs[1] + ip];
+                } else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)(cbase + c) * S.bs[1] + ip];
             }
             if (clip) v = clipf(v, peak);
             dst[c] = v;
@@ -152,17 +152,24 @@ __device__ __forceinline__ void emit_samples(const LaunchArgs& a, const DevSetup
     }
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fused(FusedParams p) {
+// GROUPED (even channel counts above two, no drains in the launch): the unit of work is a CHANNEL PAIR of a frame instead
+// of a whole frame -- slots hold two channels (18 of them instead of 7 six-channel slots), every warp stays busy, and the pair
+// takes the stereo TDAC output path with two float2 stores per sample pair into the C-channel interleave.  Units of one
+// frame are consecutive (v = frame * U + pair), the previous block of a unit is unit v - U.
+template <bool GROUPED>
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fused_t(FusedParams p) {
     NVB_DYN_SMEM(smem_raw);
     const LaunchArgs& a = p.a;
     const DevSetup& S = a.S;
     const int C = S.channels;
+    const int G = GROUPED ? 2 : C;                                          // channels per unit (= per slot)
+    const int U = GROUPED ? (C >> 1) : 1;                                   // units per frame
     const int NS = p.n_slots;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     float* s_tab = reinterpret_cast<float*>(smem_raw);
     float* s_slots = s_tab + FusedTables::FLOATS;
-    DevFrame* s_fr = reinterpret_cast<DevFrame*>(s_slots + (size_t)NS * C * FUSED_SLOT_FLOATS);
+    DevFrame* s_fr = reinterpret_cast<DevFrame*>(s_slots + (size_t)NS * G * FUSED_SLOT_FLOATS);
     int* s_full = reinterpret_cast<int*>(s_fr + NS);                        // s_full[s]: frames completed in slot s
     int* s_empty = s_full + NS;                                             // s_empty[s]: reader releases of slot s (two per frame)
     uint64_t* s_tabbar = reinterpret_cast<uint64_t*>(s_empty + NS);          // 8 NS bytes past s_full: 8-byte aligned
@@ -190,11 +197,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
         if (f0.prev >= 0 && (f0.ola_len > 0 || f0.kind != 0)) first = lo - 1;   // halo: previous block's tail is needed
     }
     // the first transform's rows are requested before the lane tables have landed: both latencies overlap
+    const int vfirst = first * U, vhi = hi * U;                             // unit indices (== frame indices when not grouped)
     LongIn pre; int pre_x = -1, pre_c = -1;
-    if (first + warp < hi) {
-        const DevFrame* f0 = a.frames + first + warp;
-        if (f0->kind == 0 && f0->n == FUSED_LONG_N && (f0->exec_mask & 1u)) {
-            long_phase1_load(lane, reinterpret_cast<const float2*>(a.spectrum + (size_t)f0->spec_off), pre); pre_x = first + warp; pre_c = 0;
+    if (vfirst + warp < vhi) {
+        const int v0 = vfirst + warp, x0 = GROUPED ? v0 / U : v0, c0 = GROUPED ? (v0 - x0 * U) * 2 : 0;
+        const DevFrame* f0 = a.frames + x0;
+        if (f0->kind == 0 && f0->n == FUSED_LONG_N && ((f0->exec_mask >> c0) & 1u)) {
+            long_phase1_load(lane, reinterpret_cast<const float2*>(a.spectrum + (size_t)f0->spec_off + (size_t)c0 * (FUSED_LONG_N / 2)), pre); pre_x = v0; pre_c = 0;
         }
     }
     mbar_wait(s_tabbar, 0);
@@ -213,34 +222,39 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
     // the current transform has consumed its inputs, so the load latency hides behind passes 2-3 and the output.
     auto can_prefetch = [&](int kind, int n, uint32_t exec_mask, int cc) { return kind == 0 && n == FUSED_LONG_N && ((exec_mask >> cc) & 1u); };
 
-    for (int x = first + warp; x < hi; x += FUSED_WARPS) {
-        const int rel = x - first, slot = rel % NS, it = rel / NS;
+    for (int v = vfirst + warp; v < vhi; v += FUSED_WARPS) {
+        const int rel = v - vfirst, slot = rel % NS, it = rel / NS;
+        const int x = GROUPED ? v / U : v;                                   // frame and first channel of this unit
+        const int cbase = GROUPED ? (v - x * U) * 2 : 0;
         cnt_wait(&s_empty[slot], 2 * it);                                    // both readers of every earlier frame of the slot are done
         if (lane == 0) s_fr[slot] = a.frames[x];
         __syncwarp();
         const DevFrame f = s_fr[slot];
-        const int xn = x + FUSED_WARPS;                                      // the warp's next frame (for the prefetch)
+        const int vn = v + FUSED_WARPS;                                      // the warp's next unit (for the prefetch)
         int n_kind = 1, n_n = 0; uint32_t n_exec = 0, n_spec = 0;
-        if (xn < hi) { const DevFrame* fn = a.frames + xn; n_kind = fn->kind; n_n = fn->n; n_exec = fn->exec_mask; n_spec = fn->spec_off; }
-        float* slots_f = s_slots + (size_t)slot * C * FUSED_SLOT_FLOATS;
+        if (vn < vhi) {
+            const int xn = GROUPED ? vn / U : vn, cn = GROUPED ? (vn - xn * U) * 2 : 0;
+            const DevFrame* fn = a.frames + xn; n_kind = fn->kind; n_n = fn->n; n_exec = fn->exec_mask >> cn; n_spec = fn->spec_off + (uint32_t)cn * (uint32_t)(fn->n >> 1);
+        }
+        float* slots_f = s_slots + (size_t)slot * G * FUSED_SLOT_FLOATS;
 
         // ---------------- transform: every channel of frame x -------------------------------------
         if (f.kind == 0) {
-            for (int c = 0; c < C; c++) {
+            for (int c = 0; c < G; c++) {
                 float* slotc = slots_f + (size_t)c * FUSED_SLOT_FLOATS;
                 const int M = f.n >> 1;
-                const float* spec = a.spectrum + (size_t)f.spec_off + (size_t)c * M;
-                if (!((f.exec_mask >> c) & 1u)) {
+                const float* spec = a.spectrum + (size_t)f.spec_off + (size_t)(cbase + c) * M;
+                if (!((f.exec_mask >> (cbase + c)) & 1u)) {
                     for (int i = lane; i < M; i += 32) slotc[i] = spec[i];         // raw residue values (Mapping.cs:192-196)
                 } else if (f.n == FUSED_LONG_N) {
                     float2* ex = reinterpret_cast<float2*>(slotc);
                     LongRegs R;
-                    if (!(pre_x == x && pre_c == c)) long_phase1_load(lane, reinterpret_cast<const float2*>(spec), pre);   // cold start
+                    if (!(pre_x == v && pre_c == c)) long_phase1_load(lane, reinterpret_cast<const float2*>(spec), pre);   // cold start
                     long_phase1_compute(lane, pre, s_tab, ex);
-                    if (c + 1 < C && can_prefetch(0, f.n, f.exec_mask, c + 1)) {
-                        long_phase1_load(lane, reinterpret_cast<const float2*>(spec + M), pre); pre_x = x; pre_c = c + 1;
-                    } else if (c + 1 == C && can_prefetch(n_kind, n_n, n_exec, 0)) {
-                        long_phase1_load(lane, reinterpret_cast<const float2*>(a.spectrum + (size_t)n_spec), pre); pre_x = xn; pre_c = 0;
+                    if (c + 1 < G && can_prefetch(0, f.n, f.exec_mask >> cbase, c + 1)) {
+                        long_phase1_load(lane, reinterpret_cast<const float2*>(spec + M), pre); pre_x = v; pre_c = c + 1;
+                    } else if (c + 1 == G && can_prefetch(n_kind, n_n, n_exec, 0)) {
+                        long_phase1_load(lane, reinterpret_cast<const float2*>(a.spectrum + (size_t)n_spec), pre); pre_x = vn; pre_c = 0;
                     }
                     __syncwarp();
                     long_phase2_load(lane, ex, R);
@@ -270,19 +284,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
 
         // Frame x-1 must have claimed and filled its slot before this warp releases it (a release that overtakes the
         // frame itself would be counted against the slot's next user), whether its tail is needed or not.
-        if (rel >= 1) cnt_wait(&s_full[(rel - 1) % NS], (rel - 1) / NS + 1);
+        if (rel >= U) cnt_wait(&s_full[(rel - U) % NS], (rel - U) / NS + 1);
 
         // ---------------- output of frame x (a halo block only leaves its tail) --------------------
         if (x >= lo) {
             const int len = f.out_end - f.out_begin;
             const DevFrame* pf = nullptr; const float* slots_p = nullptr;
             if (f.prev >= 0 && (f.ola_len > 0 || f.kind != 0)) {
-                const int pslot = (f.prev - first) % NS;
-                pf = &s_fr[pslot]; slots_p = s_slots + (size_t)pslot * C * FUSED_SLOT_FLOATS;
+                const int pslot = (GROUPED ? (f.prev * U + (v - x * U)) - vfirst : f.prev - first) % NS;
+                pf = &s_fr[pslot]; slots_p = s_slots + (size_t)pslot * G * FUSED_SLOT_FLOATS;
             }
-            const bool fast = (C == 2) && f.kind == 0 && pf && f.n == FUSED_LONG_N && pf->n == FUSED_LONG_N && f.window == 3 &&
+            const bool fast = (G == 2) && f.kind == 0 && pf && f.n == FUSED_LONG_N && pf->n == FUSED_LONG_N && f.window == 3 &&
                               (pf->window & 2) && f.start == 0 && f.out_begin == 0 && f.out_end == 1024 && f.ola_len == 1024 &&
-                              f.prev_valid == 1024 && f.exec_mask == 3u && pf->exec_mask == 3u && pf->kind == 0 && ((f.pcm_off & 1) == 0);
+                              f.prev_valid == 1024 && ((f.exec_mask >> cbase) & 3u) == 3u && ((pf->exec_mask >> cbase) & 3u) == 3u && pf->kind == 0 &&
+                              (GROUPED || (f.pcm_off & 1) == 0);
             if (fast) {
                 // long block after long block, both channels live (Mode.cs:44-50 window 3).  With a = u[512+i] of this
                 // block, b = u'[511-i] of the previous one, s = S[i], s' = S[1023-i] (i < 512):
@@ -315,24 +330,32 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
                             for (int e = 0; e < 4; e++) { lo_[e] = clipf(lo_[e], peak); hi_[e] = clipf(hi_[e], peak); }
                         }
                     }
-                    out[lane + 32 * k] = make_float4(lo_[0], lo_[1], lo_[2], lo_[3]);
-                    out[511 - lane - 32 * k] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
+                    if (!GROUPED) {
+                        out[lane + 32 * k] = make_float4(lo_[0], lo_[1], lo_[2], lo_[3]);
+                        out[511 - lane - 32 * k] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
+                    } else {                                                 // the pair's two samples inside the C-channel interleave
+                        float* o = a.pcm + (size_t)f.pcm_off * C + cbase;
+                        *reinterpret_cast<float2*>(o + (size_t)i * C) = make_float2(lo_[0], lo_[1]);
+                        *reinterpret_cast<float2*>(o + (size_t)(i + 1) * C) = make_float2(lo_[2], lo_[3]);
+                        *reinterpret_cast<float2*>(o + (size_t)(1022 - i) * C) = make_float2(hi_[0], hi_[1]);
+                        *reinterpret_cast<float2*>(o + (size_t)(1023 - i) * C) = make_float2(hi_[2], hi_[3]);
+                    }
                 }
             } else if (len > 0) {
-                emit_samples<true>(a, S, f, pf, slots_f, slots_p, FUSED_SLOT_FLOATS, lane, peak);
+                emit_samples<true>(a, S, f, pf, slots_f, slots_p, FUSED_SLOT_FLOATS, lane, peak, cbase, G);
             }
             if (x == a.carry_frame && a.carry_out && f.kind == 0) {
                 // keep the last windowed block for the next batch (StreamDecoder.cs:455-461)
-                for (int idx = lane; idx < f.n * C; idx += 32) {
+                for (int idx = lane; idx < f.n * G; idx += 32) {
                     const int c = idx / f.n, i = idx - c * f.n;
-                    a.carry_out[(size_t)c * S.bs[1] + i] = slot_z(S, f, slots_f + c * FUSED_SLOT_FLOATS, c, i);
+                    a.carry_out[(size_t)(cbase + c) * S.bs[1] + i] = slot_z(S, f, slots_f + c * FUSED_SLOT_FLOATS, cbase + c, i);
                 }
             }
         }
         __syncwarp();
         if (lane == 0) {
             cnt_signal(&s_empty[slot]);                                      // done with frame x as "current"
-            if (rel >= 1) cnt_signal(&s_empty[(rel - 1) % NS]);              // done with frame x-1 as "previous"
+            if (rel >= U) cnt_signal(&s_empty[(rel - U) % NS]);              // done with the previous block's unit as "previous"
         }
     }
     if (__any_sync(0xffffffffu, peak > 0.99999994f) && lane == 0) atomicOr(&a.counters->clipped, 1);
@@ -442,7 +465,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_generic(GenericParam
                 const int pslot = (f.prev - first) % NS;
                 pf = &s_fr[pslot]; slots_p = s_slots + (size_t)pslot * C * SLOT;
             }
-            if (f.out_end > f.out_begin) emit_samples<false>(a, S, f, pf, slots_f, slots_p, SLOT, lane, peak);
+            if (f.out_end > f.out_begin) emit_samples<false>(a, S, f, pf, slots_f, slots_p, SLOT, lane, peak, 0, C);
             if (x == a.carry_frame && a.carry_out && f.kind == 0) {
                 for (int idx = lane; idx < f.n * C; idx += 32) {            // keep the last windowed block for the next batch (StreamDecoder.cs:455-461)
                     const int c = idx / f.n, i = idx - c * f.n;
@@ -510,19 +533,26 @@ static int launch_imdct_generic(const LaunchArgs& a, void* stream) {
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_imdct_fused(const LaunchArgs& a, const DevFrame*, void* stream) {
+int launch_imdct_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream) {
     if (a.n_frames <= 0) return 0;
     if (!(a.S.bs[0] == FUSED_SHORT_N && a.S.bs[1] == FUSED_LONG_N && a.S.fused_tab)) return launch_imdct_generic(a, stream);
     const int C = a.S.channels;
-    FusedParams p; p.a = a; p.n_slots = fused_slots(C);
-    const size_t smem = fused_smem(C, p.n_slots);
+    // channel-pair units for even channel counts above two -- unless the launch contains a drain (its successor reaches two
+    // blocks back, which the unit ring only covers frame by frame)
+    static const bool no_grouped = std::getenv("NVB_FUSED_NO_GROUPED") != nullptr;           // test hook
+    bool grouped = C > 2 && (C & 1) == 0 && !no_grouped && host_frames != nullptr;
+    if (grouped) for (int i = a.frame_lo; i < a.frame_lo + a.n_frames; i++) if (host_frames[i].kind != 0 || (host_frames[i].prev >= 0 && host_frames[i].prev != i - 1)) { grouped = false; break; }
+    const int G = grouped ? 2 : C;
+    FusedParams p; p.a = a; p.n_slots = fused_slots(G);
+    const size_t smem = fused_smem(G, p.n_slots);
     static size_t configured_by_dev[64] = {0};
     static int num_sms_by_dev[64] = {0};
     int dev_slot = 0; cudaGetDevice(&dev_slot); if (dev_slot < 0 || dev_slot >= 64) dev_slot = 0;
     size_t& configured = configured_by_dev[dev_slot];
     int& num_sms = num_sms_by_dev[dev_slot];
     if (smem > configured) {
-        if (cudaFuncSetAttribute(k_imdct_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(k_imdct_fused_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(k_imdct_fused_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = smem;
     }
     if (num_sms == 0) {
@@ -535,7 +565,8 @@ int launch_imdct_fused(const LaunchArgs& a, const DevFrame*, void* stream) {
     if (fpc < 8) fpc = 8;
     p.frames_per_cta = fpc;
     const int grid = (a.n_frames + fpc - 1) / fpc;
-    NVB_LAUNCH(k_imdct_fused, grid, FUSED_THREADS, smem, stream, p);
+    if (grouped) NVB_LAUNCH(k_imdct_fused_t<true>, grid, FUSED_THREADS, smem, stream, p);
+    else NVB_LAUNCH(k_imdct_fused_t<false>, grid, FUSED_THREADS, smem, stream, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
