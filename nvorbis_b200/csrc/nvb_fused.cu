@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
 // k_imdct_generic -- the same fused IMDCT + window + overlap-add + clip + interleave for every other pair of block sizes
 // from 256 up (e.g. 512/1024, 512/4096, 1024/8192; the reference's Mdct does not compute an IMDCT below 256, so those
 // sizes stay on the exact kernels).  Same persistent CTAs, slot ring and release/acquire counters as k_imdct_fused; the
-// transform is the generic form of the same factorisation: pre-twiddle, radix-2 Stockham FFT of N/4 complex points by
+// transform is the generic form of the same factorisation: pre-twiddle, radix-4 (+ one radix-2) Stockham FFT of N/4 complex points by
 // one warp inside the frame's slot (two ping-pong buffers of N/2 floats), post-twiddle into u[0 .. N/2); twiddles come
 // from the setup's per-block-size tables (L1-resident).  Slot = N_long floats per channel.
 // ------------------------------------------------------------------------------------------------
@@ -378,12 +378,13 @@ struct GenericParams {
 
 __device__ __forceinline__ void generic_transform(int lane, int N, const float* spec, const float2* tw, const float2* fft, float* slot) {
     const int M = N >> 1, Q = N >> 2;
-    int S = 0; while ((1 << S) < Q) ++S;                                    // log2 Q stages
+    int lq = 0; while ((1 << lq) < Q) ++lq;                                  // log2 Q
+    const int stages = (lq + 1) >> 1;                                       // radix-4 passes plus one radix-2 pass when log2 Q is odd
     float2* A = reinterpret_cast<float2*>(slot);
     float2* B = A + Q;
-    // the last stage must leave the spectrum in B (the post-twiddle writes u over A)
-    float2* x = (S & 1) ? A : B;
-    float2* y = (S & 1) ? B : A;
+    // the last pass must leave the spectrum in B (the post-twiddle writes u over A)
+    float2* x = (stages & 1) ? A : B;
+    float2* y = (stages & 1) ? B : A;
     for (int k = lane; k < Q; k += 32) {                                    // c[k] = (X[2k] + i X[M-1-2k]) tw[k]
         cpx c, t; c.x = spec[2 * k]; c.y = spec[M - 1 - 2 * k];
         const float2 w = tw[k]; t.x = w.x; t.y = w.y;
@@ -391,15 +392,35 @@ __device__ __forceinline__ void generic_transform(int lane, int N, const float* 
         x[k] = make_float2(c.x, c.y);
     }
     __syncwarp();
-    for (int l = Q >> 1, m = 1, lm = 0; l >= 1; l >>= 1, m <<= 1, ++lm) {    // Stockham autosort, forward DFT
-        for (int b = lane; b < (Q >> 1); b += 32) {
-            const int j = b >> lm, k = b & (m - 1);
-            const float2 w = fft[j << lm];                                  // exp(-2 pi i j / (2 l)) = exp(-2 pi i j m / Q)
-            const float2 v0 = x[k + (j << lm)], v1 = x[k + (j << lm) + l * m];
-            cpx c0, c1, t; c0.x = v0.x; c0.y = v0.y; c1.x = v1.x; c1.y = v1.y; t.x = w.x; t.y = w.y;
-            const cpx s0 = cadd(c0, c1), s1 = cmul(csub(c0, c1), t);
-            y[k + (j << (lm + 1))] = make_float2(s0.x, s0.y);
-            y[k + (j << (lm + 1)) + m] = make_float2(s1.x, s1.y);
+    auto ld = [](const float2& v) { cpx r; r.x = v.x; r.y = v.y; return r; };
+    for (int lm = 0; lm < lq;) {                                            // Stockham autosort passes, forward DFT; m = 1 << lm sub-transforms done
+        const int m = 1 << lm;
+        if (lq - lm >= 2) {                                                 // radix 4: l = Q / (4 m)
+            const int lmQ = Q >> (lm + 2);                                  // l
+            for (int b = lane; b < (Q >> 2); b += 32) {
+                const int j = b >> lm, k = b & (m - 1);
+                const int i0 = k + (j << lm), st = lmQ << lm;               // stride l * m
+                const cpx c0 = ld(x[i0]), c1 = ld(x[i0 + st]), c2 = ld(x[i0 + 2 * st]), c3 = ld(x[i0 + 3 * st]);
+                const cpx d0 = cadd(c0, c2), d1 = csub(c0, c2), d2 = cadd(c1, c3), d3 = cmul_mi(csub(c1, c3));
+                const int tj = j << lm;                                     // w1 = exp(-2 pi i j m / Q), w2 = w1^2, w3 = w1^3
+                const cpx w1 = ld(fft[tj]), w2 = ld(fft[2 * tj]), w3 = ld(fft[3 * tj]);
+                const cpx o0 = cadd(d0, d2), o1 = cmul(cadd(d1, d3), w1), o2 = cmul(csub(d0, d2), w2), o3 = cmul(csub(d1, d3), w3);
+                const int o = k + (j << (lm + 2));
+                y[o] = make_float2(o0.x, o0.y); y[o + m] = make_float2(o1.x, o1.y);
+                y[o + 2 * m] = make_float2(o2.x, o2.y); y[o + 3 * m] = make_float2(o3.x, o3.y);
+            }
+            lm += 2;
+        } else {                                                            // radix 2: l = Q / (2 m)
+            const int st = (Q >> (lm + 1)) << lm;
+            for (int b = lane; b < (Q >> 1); b += 32) {
+                const int j = b >> lm, k = b & (m - 1);
+                const int i0 = k + (j << lm);
+                const cpx c0 = ld(x[i0]), c1 = ld(x[i0 + st]);
+                const cpx s0 = cadd(c0, c1), s1 = cmul(csub(c0, c1), ld(fft[j << lm]));
+                const int o = k + (j << (lm + 1));
+                y[o] = make_float2(s0.x, s0.y); y[o + m] = make_float2(s1.x, s1.y);
+            }
+            lm += 1;
         }
         __syncwarp();
         float2* tmp = x; x = y; y = tmp;
