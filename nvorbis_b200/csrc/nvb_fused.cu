@@ -26,6 +26,8 @@
 //   Variants measured and dropped (profiles/r01_d, r01_f): TMA staging of the spectrum rows into the slot (the extra
 //   LDS of the inputs costs more shared-memory bandwidth than the exposed load latency it saves); 32 warps x 64
 //   registers with one warp per channel (more twiddle loads and counter polling, slower).
+//   * even channel counts above two run as channel-pair units (k_imdct_fused_t<true>); every other pair of block sizes from
+//     256 up runs on k_imdct_generic (radix-4 Stockham warp FFT in the slot) -- both further down in this file.
 // No tensor cores: the IMDCT is FFT-structured, not a dense contraction.
 #if !defined(NVB_CPU_SHIM)
 #include <cuda_runtime.h>

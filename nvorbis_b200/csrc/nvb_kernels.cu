@@ -1,13 +1,17 @@
-// nvb_kernels.cu -- sm_100a kernels of the Vorbis synthesis path (generic / exact path).
+// nvb_kernels.cu -- sm_100a kernels of the Vorbis synthesis path: the spectrum stage (K1+K2+K3) and the exact IMDCT path.
 //
-//   k_spectrum     : residue VQ gather (K1) + inverse coupling (K2) + Floor1 curve multiply (K3)
-//                    compact boundary records -> dense spectrum [frame][channel][N/2]
-//   k_imdct_exact  : inverse MDCT in the reference's stb dataflow, no FMA contraction (K4, exact)
-//                    + window multiply -> windowed blocks [frame][channel][N]
-//   k_ola          : overlap-add with the previous block's tail + clip + interleave (K5)
+//   spectrum stage: compact boundary records -> dense spectrum [frame][channel][N/2]
+//     k_spectrum_run    default (type 2 / mono type 1 residues, power-of-two sizes, 8-aligned partitions): a thread owns
+//                       a run of 8 stream values; per-segment floor records with multiply-high division
+//     k_spectrum_bins   type 2 residues with any channel count / partition alignment (Residue2.cs:25-27 truncation case)
+//     k_spectrum_planes / k_spectrum_fast / k_spectrum_warp   earlier designs, kept as cross-checks (NVB_SPECTRUM_* hooks)
+//     k_spectrum        everything else: odd sizes, type 0 floors (Floor0.cs:152-212)
+//   exact path (NVB_RUN_EXACT, block sizes below 256):
+//     k_imdct_exact     inverse MDCT in the reference's stb dataflow, no FMA contraction (K4) + window multiply
+//     k_ola             overlap-add with the previous block's tail + clip + interleave (K5)
 //
-// The fused fast path (IMDCT + window + OLA + clip + interleave in one kernel) lives in
-// nvb_fused.cu.  All arithmetic is in nvb_device_core.h; these are thread-mapping shells.
+// The fused fast path (IMDCT + window + OLA + clip + interleave in one kernel: k_imdct_fused_t / k_imdct_generic) lives in
+// nvb_fused.cu.  Shared arithmetic is in nvb_device_core.h.
 #if !defined(NVB_CPU_SHIM)
 #include <cuda_runtime.h>
 #endif
