@@ -79,11 +79,16 @@ struct Book {
     void parse(Bits& b) {
         if (b.read(24) != 0x564342u) throw DataError("Book header had invalid signature!");          // Codebook.cs:62-63
         dims = (int)b.read(16); entries = (int)b.read(24);
+        if (b.short_) throw DataError("codebook header is truncated");
         len.assign((size_t)entries, 0);
         if (b.bit()) {                                                                                 // ordered lengths, Codebook.cs:83-104
             int l = (int)b.read(5) + 1;
             for (int i = 0; i < entries;) {
+                // a codeword is at most 32 bits (the length field of the unordered form is 5 bits + 1); past the end of the
+                // packet every count reads as 0 and the reference's loop would never end
+                if (l > 32) throw DataError("ordered codebook: codeword length above 32");
                 int cnt = (int)b.read(ilog(entries - i));
+                if (b.short_) throw DataError("ordered codebook: packet is truncated");
                 if (i + cnt > entries) throw DataError("ordered codebook overrun");
                 for (int k = 0; k < cnt; k++) len[(size_t)i++] = (int8_t)l;
                 ++l;
@@ -106,6 +111,7 @@ struct Book {
         for (int i = 0; i < entries; i++) {
             const int l = len[(size_t)i];
             if (l <= 0) continue;
+            if (l > 32) throw DataError("codeword length above 32");
             any = true; if (l > maxlen) maxlen = l;
             uint32_t c = next_free[l];
             if (l < 32 && (c >> l)) throw DataError("codebook is over-specified");
@@ -163,6 +169,9 @@ struct Book {
         map_type = (int)b.read(4);
         if (map_type == 0) return;
         if (map_type > 2) throw DataError("invalid codebook lookup type");
+        // a value table needs at least one dimension (Floor0.cs:48 rejects such books; for residues the reference divides by
+        // Dimensions, Residue0.cs:183): refuse the setup instead of dividing by zero per packet
+        if (dims < 1) throw DataError("codebook with a lookup table has no dimensions");
         const float vmin = unpack_float(b.read(32)), vdelta = unpack_float(b.read(32));
         const int vbits = (int)b.read(4) + 1;
         const bool seq = b.bit();
@@ -419,6 +428,7 @@ static void parse_residue(Bits& b, const nvh_stream& s, int type, ResidueDef& r)
         bk = (int)b.read(8);
         if (bk >= (int)s.books.size()) throw DataError("residue: book out of range");
         if (s.books[(size_t)bk].map_type == 0) throw DataError("residue: book without a lookup table");     // Residue0.cs:66-67
+        if (s.books[(size_t)bk].dims < 1) throw DataError("residue: book without dimensions");
     }
     const Book& cb = s.books[(size_t)r.class_book];
     long long partvals = 1;
@@ -788,13 +798,27 @@ int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, in
     const size_t n = std::min<size_t>((size_t)count, avail);
     int T = std::max(1, threads);
     if ((size_t)T > n) T = (int)std::max<size_t>(1, n);
-    std::vector<Scratch> parts((size_t)T);
+    // nothing may unwind through the C boundary (or out of a worker thread: std::terminate): the first failure is kept
+    // in s->err and reported as a status
+    std::atomic<int> failed{NVB_OK};
+    std::vector<Scratch> parts;
+    try {
+    parts.resize((size_t)T);
     auto work = [&](int t) {
-        const size_t a = lo + n * (size_t)t / (size_t)T, b = lo + n * (size_t)(t + 1) / (size_t)T;
-        for (size_t i = a; i < b; i++) unpack_packet(*s, s->packets[i], parts[(size_t)t]);
+        try {
+            const size_t a = lo + n * (size_t)t / (size_t)T, b = lo + n * (size_t)(t + 1) / (size_t)T;
+            for (size_t i = a; i < b; i++) unpack_packet(*s, s->packets[i], parts[(size_t)t]);
+        } catch (const std::bad_alloc&) { failed = NVB_ERR_NOMEM; }
+        catch (...) { failed = NVB_ERR_DATA; }
     };
     if (T == 1) work(0);
-    else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    else {
+        std::vector<std::thread> th;
+        try { for (int t = 0; t < T; t++) th.emplace_back(work, t); }
+        catch (...) { failed = NVB_ERR_NOMEM; }                                // thread creation failed: join what started
+        for (auto& x : th) x.join();
+    }
+    if (failed != NVB_OK) { s->err = failed == NVB_ERR_NOMEM ? "nvh_unpack: out of memory" : "nvh_unpack: internal error while unpacking"; return failed; }
 
     s->o_frames.clear(); s->o_posts.clear(); s->o_classes.clear(); s->o_entries.clear(); s->o_floor0.clear();
     std::vector<UnpackedFrame> metas;
@@ -859,6 +883,8 @@ int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, in
     out->entries = s->o_entries.data(); out->n_entries = (int64_t)s->o_entries.size();
     out->floor0 = s->o_floor0.empty() ? nullptr : s->o_floor0.data();
     return (int64_t)s->o_frames.size();
+    } catch (const std::bad_alloc&) { s->err = "nvh_unpack: out of memory"; return NVB_ERR_NOMEM; }
+    catch (const std::exception& e) { s->err = std::string("nvh_unpack: ") + e.what(); return NVB_ERR_DATA; }
 }
 
 }  // extern "C"

@@ -126,6 +126,43 @@ void build_fused_tables(const float2* tw0, const float2* w64, const float* slope
     }
 }
 
+// FNV-1a 64 over the blob body (everything behind the header): a damaged blob is rejected before any offset is trusted
+uint64_t blob_body_hash(const unsigned char* blob, size_t bytes) {
+    uint64_t hsh = 1469598103934665603ull;
+    for (size_t i = sizeof(BlobHeader); i < bytes; i++) { hsh ^= blob[i]; hsh *= 1099511628211ull; }
+    return hsh;
+}
+
+// The kernel-selection level of one residue (DevResidue.fast) and its per-(class, stage) entry counts, from the plain
+// residue fields and the book dimensions.  build_blob stores the result; validate_blob recomputes and compares, so that a
+// blob cannot steer a residue onto a kernel whose alignment / power-of-two assumptions it does not meet.
+struct ResidueDerived { int pshift, fast; int16_t cnt[NVB_MAX_CLASSES][NVB_MAX_STAGES]; uint8_t coded[NVB_MAX_CLASSES]; };
+template <class BookDims>
+ResidueDerived derive_residue(int type, int begin, int psize, int nclass, int stages, const int32_t* cascade, const int16_t (*books)[NVB_MAX_STAGES], int C, BookDims dims_of) {
+    ResidueDerived d; std::memset(&d, 0, sizeof d);
+    d.pshift = is_pow2(psize) ? ilog_u(psize) - 1 : -1;
+    bool fast = d.pshift >= 0 && psize <= 8192 && stages >= 1;
+    if (type == 2 && (begin % C != 0 || psize % C != 0)) fast = false;     // Residue2.cs:27 truncation case
+    for (int c = 0; c < NVB_MAX_CLASSES; c++)
+        for (int st = 0; st < NVB_MAX_STAGES; st++) {
+            const bool coded = c < nclass && st < stages && ((cascade[c] >> st) & 1) && books[c][st] >= 0;
+            if (!coded) continue;
+            const int dims = dims_of(books[c][st]);
+            const int cnt = type == 0 ? psize / dims : (psize + dims - 1) / dims;   // Residue0.cs:183 / Residue1.cs:12 / Residue2.cs:28
+            if (cnt > 32767 || !is_pow2(dims) || dims > psize) fast = false;
+            d.cnt[c][st] = (int16_t)(cnt > 32767 ? 32767 : cnt);
+            if (cnt > 0) d.coded[c] |= (uint8_t)(1u << st);
+        }
+    d.fast = fast ? 1 : 0;
+    // level 2: the plane kernel (k_spectrum_planes): one interleaved stream (type 2, or a single channel of type 1) whose
+    // partitions start on multiples of G = max(4, C) floats
+    const int G = C > 4 ? C : 4;
+    if (fast && (type == 2 || (type == 1 && C == 1)) && begin % G == 0 && psize % G == 0 && is_pow2(C)) d.fast = 2;
+    // level 3: k_spectrum_run works on groups of 8 consecutive values of the stream
+    if (d.fast == 2 && begin % 8 == 0 && psize % 8 == 0) d.fast = 3;
+    return d;
+}
+
 int fail(std::string& err, int code, const char* fmt, long long a = 0, long long b = 0) {
     char tmp[256];
     std::snprintf(tmp, sizeof tmp, fmt, a, b);
@@ -179,6 +216,9 @@ void resolve_setup(const unsigned char* base, const BlobHeader& h, DevSetup& S) 
     S.r2cand = reinterpret_cast<const uint32_t*>(base + h.off_r2cand);
     S.r2ob = reinterpret_cast<const uint16_t*>(base + h.off_r2ob);
     S.spectrum_bins = h.spectrum_bins; S.r2_max_p = h.r2_max_p;
+    S.magic = reinterpret_cast<const uint32_t*>(base + h.off_magic);
+    S.cls_cnt = reinterpret_cast<const unsigned long long*>(base + h.off_cls_cnt);
+    S.wf_max_p = h.wf_max_p; S.max_posts = (h.post_stride - 2 > 2) ? h.post_stride - 2 : 2;
 }
 
 int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string& err) {
@@ -307,6 +347,8 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
             d.level[k] = (uint8_t)lv;
             if (lv > d.max_level) d.max_level = lv;
             d.rcp[k] = 1.0f / (float)((int)d.x[d.hi[k]] - (int)d.x[d.lo[k]]);
+            const uint32_t adx = (uint32_t)((int)d.x[d.hi[k]] - (int)d.x[d.lo[k]]);      // >= 2: x[lo] < x[k] < x[hi] (validated above)
+            d.magic[k] = adx >= 2 ? 0xffffffffu / adx + 1u : 0u;
         }
         for (int k = 0; k < g.n_posts; k++) d.xs[k] = d.x[d.sort[k]];
         w.at<DevFloor1>(h.off_floors)[i] = d;
@@ -320,6 +362,18 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         for (int bin = 0; bin < h.bs[1] / 2; bin++) {
             while (k + 1 < d.n_posts && (int)d.xs[k + 1] <= bin) ++k;
             tab[bin] = (uint8_t)k;
+        }
+    }
+    // k_spectrum_wf: floor(q / adx) as umulhi(q, m) with m = floor(2^32 / adx) + 1 is exact while q * adx < 2^32; a segment
+    // evaluates q = (x - x0) |dy| < adx |dy|, so |dy| <= lim = floor((2^32 - 1) / adx^2) suffices
+    {
+        const int nb = h.bs[1] / 2;
+        h.off_magic = w.reserve(sizeof(uint32_t) * 2 * (size_t)(nb + 1));
+        uint32_t* mg = w.at<uint32_t>(h.off_magic);
+        for (int adx = 0; adx <= nb; adx++) {
+            if (adx < 2) { mg[2 * adx] = 1u; mg[2 * adx + 1] = 0xffffffffu; continue; }     // one bin: (x - x0) = 0
+            mg[2 * adx] = 0xffffffffu / (uint32_t)adx + 1u;
+            mg[2 * adx + 1] = (uint32_t)(0xffffffffull / ((uint64_t)adx * (uint64_t)adx));
         }
     }
     // type 0 floors: the bark map and the 2 cos map of Floor0.Init (Floor0.cs:53-96) for both block sizes
@@ -379,32 +433,17 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         const nvb_residue& r = s->residues[i];
         DevResidue d; std::memset(&d, 0, sizeof d);
         d.type = r.type; d.begin = r.begin; d.end = r.end; d.psize = r.partition_size; d.nclass = r.classifications; d.stages = r.max_stages;
-        d.pshift = is_pow2(r.partition_size) ? ilog_u(r.partition_size) - 1 : -1;
-        bool fast = d.pshift >= 0 && r.partition_size <= 8192 && r.max_stages >= 1;
-        if (r.type == 2 && (r.begin % C != 0 || r.partition_size % C != 0)) fast = false;    // Residue2.cs:27 truncation case
         for (int c = 0; c < NVB_MAX_CLASSES; c++) {
             d.cascade[c] = c < r.classifications ? r.cascade[c] : 0;
             for (int st = 0; st < NVB_MAX_STAGES; st++) {
                 const bool coded = c < r.classifications && st < r.max_stages && ((r.cascade[c] >> st) & 1) && r.books[c][st] >= 0;
                 d.books[c][st] = coded ? r.books[c][st] : (int16_t)-1;
-                d.cnt[c][st] = 0;
-                if (coded) {
-                    const int dims = s->books[r.books[c][st]].dims;
-                    const int cnt = r.type == 0 ? r.partition_size / dims : (r.partition_size + dims - 1) / dims;   // Residue0.cs:183 / Residue1.cs:12 / Residue2.cs:28
-                    if (cnt > 32767 || !is_pow2(dims) || dims > r.partition_size) fast = false;
-                    d.cnt[c][st] = (int16_t)(cnt > 32767 ? 32767 : cnt);
-                    if (cnt > 0) d.coded[c] |= (uint8_t)(1u << st);
-                }
             }
         }
-        d.fast = fast ? 1 : 0;
+        const ResidueDerived dv = derive_residue(d.type, d.begin, d.psize, d.nclass, d.stages, d.cascade, d.books, C, [&](int bk) { return s->books[bk].dims; });
+        d.pshift = dv.pshift; d.fast = dv.fast;
+        std::memcpy(d.cnt, dv.cnt, sizeof d.cnt); std::memcpy(d.coded, dv.coded, sizeof d.coded);
         d.ci_off = ci_total; ci_total += r.classifications * (r.max_stages > 0 ? r.max_stages : 1);
-        // level 2: the plane kernel (k_spectrum_planes): one interleaved stream (type 2, or a single channel of type 1) whose
-        // partitions start on multiples of G = max(4, C) floats
-        const int G = C > 4 ? C : 4;
-        if (fast && (r.type == 2 || (r.type == 1 && C == 1)) && r.begin % G == 0 && r.partition_size % G == 0 && is_pow2(C)) d.fast = 2;
-        // level 3: k_spectrum_run works on groups of 8 consecutive values of the stream
-        if (d.fast == 2 && r.begin % 8 == 0 && r.partition_size % 8 == 0) d.fast = 3;
         w.at<DevResidue>(h.off_residues)[i] = d;
     }
     h.off_ci = w.reserve(sizeof(CiRec) * (size_t)(ci_total > 0 ? ci_total : 1));
@@ -419,6 +458,24 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
                 ci.off = (int32_t)b.off; ci.dshift = b.dshift; ci.entries = b.entries; ci.cnt = d.cnt[c][st];
             }
             w.at<CiRec>(h.off_ci)[d.ci_off + c * st_n + st] = ci;
+        }
+    }
+    // k_spectrum_wf: entries per partition of (class, stage) packed 16 bits per stage, four stages per 64-bit word, so that ONE
+    // warp scan yields the entry-stream offsets of four stages (a stage holds at most span <= 32768 entries)
+    std::vector<int> cc_off((size_t)s->n_residues, 0);
+    {
+        int total = 0;
+        for (int i = 0; i < s->n_residues; i++) { const DevResidue& d = w.at<DevResidue>(h.off_residues)[i]; cc_off[(size_t)i] = total; total += ((d.stages + 3) / 4 > 0 ? (d.stages + 3) / 4 : 1) * d.nclass; }
+        h.cls_cnt_total = total;
+        h.off_cls_cnt = w.reserve(sizeof(uint64_t) * (size_t)(total > 0 ? total : 1));
+        for (int i = 0; i < s->n_residues; i++) {
+            const DevResidue& d = w.at<DevResidue>(h.off_residues)[i];
+            const int nw = (d.stages + 3) / 4;
+            for (int wd = 0; wd < nw; wd++) for (int c = 0; c < d.nclass; c++) {
+                uint64_t v = 0;
+                for (int k = 0; k < 4 && 4 * wd + k < d.stages; k++) v |= (uint64_t)(uint16_t)d.cnt[c][4 * wd + k] << (16 * k);
+                w.at<uint64_t>(h.off_cls_cnt)[cc_off[(size_t)i] + wd * d.nclass + c] = v;
+            }
         }
     }
     h.off_mappings = w.reserve(sizeof(DevMapping) * s->n_mappings);
@@ -485,6 +542,13 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         rm.residue = mp.residue; rm.floor = mp.floor; rm.n_coupling = mp.n_coupling; rm.mapping = md.mapping; rm.block_flag = md.block_flag; rm.rtype = R.type;
         rm.cand_off = mp.residue * (h.bs[1] / 2); rm.ob_off = mp.residue * h.r2_max_p;
         rm.bins_ok = bins_ok[(size_t)mp.residue] && s->floors[mp.floor].type == 1;
+        rm.cc_off = cc_off[(size_t)mp.residue]; rm.base_stride = ((R.stages + 3) & ~3) > 0 ? ((R.stages + 3) & ~3) : 4;
+        rm.n_posts = s->floors[mp.floor].type == 1 ? s->floors[mp.floor].f1.n_posts : 0;
+        {   // partitions of this mode's residue over its block size (single-stream residues only matter here)
+            const int span = (R.type == 2 ? C : 1) * (h.bs[md.block_flag] / 2); const int e = R.end < span ? R.end : span;
+            const int P = (e > R.begin && R.psize > 0) ? (e - R.begin) / R.psize : 0;
+            if (P > h.wf_max_p) h.wf_max_p = P;
+        }
         w.at<RunMode>(h.off_run_modes)[i] = rm;
     }
     h.spectrum_bins = 1;
@@ -562,6 +626,7 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
     }
     w.reserve(0);
     h.total_bytes = blob.size();
+    h.body_hash = blob_body_hash(blob.data(), blob.size());
     std::memcpy(blob.data(), &h, sizeof h);
     return NVB_OK;
 }
@@ -573,7 +638,12 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
     if (h.total_bytes != bytes) return fail(err, NVB_ERR_DATA, "blob size %lld, header says %lld", (long long)bytes, (long long)h.total_bytes);
     if (h.channels < 1 || h.channels > NVB_MAX_CHANNELS || !is_pow2(h.bs[0]) || !is_pow2(h.bs[1]) || h.bs[0] < 64 || h.bs[1] > 8192 || h.bs[0] > h.bs[1])
         return fail(err, NVB_ERR_DATA, "blob header fields out of range");
-    auto in = [&](uint64_t off, uint64_t len) { return off >= sizeof(BlobHeader) && off + len <= bytes && (off & 15) == 0; };
+    // len and off are untrusted 64-bit values: compare without forming off + len (which wraps)
+    auto in = [&](uint64_t off, uint64_t len) { return off >= sizeof(BlobHeader) && len <= bytes && off <= bytes - len && (off & 15) == 0; };
+    if (h.n_books < 0 || h.n_floors < 0 || h.n_residues < 0 || h.n_mappings < 0 || h.n_modes < 0 || h.n_books > 65536 || h.n_floors > 256 || h.n_residues > 256 ||
+        h.n_mappings > 256 || h.n_modes > 256 || h.n_vq > bytes / 4 || h.n_f0_bark > bytes / 4 || h.n_f0_wmap > bytes / 4)
+        return fail(err, NVB_ERR_DATA, "blob header counts out of range");
+    if (h.body_hash != blob_body_hash(static_cast<const unsigned char*>(data), bytes)) return fail(err, NVB_ERR_DATA, "blob checksum mismatch");
     bool ok = in(h.off_books, sizeof(DevBook) * (uint64_t)h.n_books) && in(h.off_vq, sizeof(float) * h.n_vq) &&
               in(h.off_floors, sizeof(DevFloor1) * (uint64_t)h.n_floors) && in(h.off_residues, sizeof(DevResidue) * (uint64_t)h.n_residues) &&
               in(h.off_mappings, sizeof(DevMapping) * (uint64_t)h.n_mappings) && in(h.off_modes, sizeof(DevMode) * (uint64_t)h.n_modes) &&
@@ -582,6 +652,8 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
               in(h.off_f0_bark, 4 * (h.n_f0_bark ? h.n_f0_bark : 1)) && h.r2_max_p >= 1 && h.r2_max_p <= 65536 &&
               in(h.off_r2cand, 4ull * h.n_residues * (h.bs[1] / 2)) && in(h.off_r2ob, 2ull * h.n_residues * h.r2_max_p) && in(h.off_f0_wmap, 4 * (h.n_f0_wmap ? h.n_f0_wmap : 1)) && h.f0_stride >= 0 && h.f0_stride <= 258 &&
               (h.off_fused_tab == 0 || (in(h.off_fused_tab, 4ull * FusedTables::FLOATS) && h.bs[0] == FUSED_SHORT_N && h.bs[1] == FUSED_LONG_N));
+    ok = ok && in(h.off_magic, 8ull * (h.bs[1] / 2 + 1)) && h.cls_cnt_total >= 0 && h.cls_cnt_total <= 256 * NVB_MAX_CLASSES * 2 &&
+         in(h.off_cls_cnt, 8ull * (uint64_t)(h.cls_cnt_total > 0 ? h.cls_cnt_total : 1)) && h.wf_max_p >= 0 && h.wf_max_p <= 65536;
     for (int i = 0; i < 2 && ok; i++)
         ok = in(h.off_mdct_a[i], 2ull * h.bs[i]) && in(h.off_mdct_b[i], 2ull * h.bs[i]) && in(h.off_mdct_c[i], 1ull * h.bs[i]) &&
              in(h.off_bitrev[i], h.bs[i] / 4ull) && in(h.off_tw[i], 2ull * h.bs[i]) && in(h.off_fft[i], 2ull * h.bs[i]);
@@ -609,6 +681,16 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
             if (r.cnt[c][st] < 0 || (r.fast && (b.dshift < 0 || (1 << b.dshift) != b.dims || r.pshift < 0 || (1 << r.pshift) != r.psize)))
                 return fail(err, NVB_ERR_DATA, "blob: residue %lld fast-path fields", i);
         }
+        // the derived fields select kernels with alignment / power-of-two assumptions: they must be what build_blob derives
+        for (int c = 0; c < NVB_MAX_CLASSES; c++) for (int st = 0; st < NVB_MAX_STAGES; st++)
+            if (r.books[c][st] >= h.n_books || (r.books[c][st] >= 0 && (c >= r.nclass || st >= r.stages || !((r.cascade[c] >> st) & 1)))) return fail(err, NVB_ERR_DATA, "blob: residue %lld book table", i);
+        const ResidueDerived dv = derive_residue(r.type, r.begin, r.psize, r.nclass, r.stages, r.cascade, r.books, h.channels, [&](int bk) { return S.books[bk].dims; });
+        if (dv.pshift != r.pshift || dv.fast != r.fast || std::memcmp(dv.cnt, r.cnt, sizeof dv.cnt) != 0 || std::memcmp(dv.coded, r.coded, sizeof dv.coded) != 0)
+            return fail(err, NVB_ERR_DATA, "blob: residue %lld derived fields", i);
+    }
+    for (int i = 0; i < h.n_books; i++) {
+        const DevBook& b = S.books[i];
+        if (b.dshift != (is_pow2(b.dims) ? ilog_u(b.dims) - 1 : -1)) return fail(err, NVB_ERR_DATA, "blob: book %lld dshift", i);
     }
     for (int i = 0; i < h.n_floors; i++) {
         const DevFloor0& z = S.floors0[i];
@@ -644,7 +726,25 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
             const CiRec& ci = S.ci[r.ci_off + k];
             if (ci.cnt < 0 || ci.entries < 0 || ci.off < 0 || ci.dshift < -1 || ci.dshift > 16 ||
                 (ci.cnt > 0 && ci.dshift >= 0 && (uint64_t)ci.off + ((uint64_t)ci.entries << ci.dshift) > h.n_vq)) return fail(err, NVB_ERR_DATA, "blob: residue %lld ci record", i);
+            // a record either repeats its book (offset, log2 dims, entries) and the residue's entry count, or codes nothing
+            const int c = k / st_n, st = k - c * st_n;
+            const int bk = st < r.stages ? r.books[c][st] : -1;
+            if (ci.cnt != 0) {
+                if (bk < 0 || ci.cnt != r.cnt[c][st] || ci.off != S.books[bk].off || ci.dshift != S.books[bk].dshift || ci.entries != S.books[bk].entries)
+                    return fail(err, NVB_ERR_DATA, "blob: residue %lld ci record does not match its book", i);
+            } else if (bk >= 0 && r.cnt[c][st] != 0 && S.books[bk].off >= 0 && S.books[bk].off < (int64_t(1) << 30)) return fail(err, NVB_ERR_DATA, "blob: residue %lld ci record missing", i);
         }
+    }
+    {   // the kernel-selection levels of the header: never above what the modes' residues / floors allow
+        int fast = 3; bool bins = true;
+        for (int i = 0; i < h.n_modes; i++) {
+            const DevMapping& mp = S.mappings[S.modes[i].mapping];
+            if (S.residues[mp.residue].fast < fast) fast = S.residues[mp.residue].fast;
+            if (S.floors0[mp.floor].type == 0) fast = 0;
+            if (!S.run_modes[i].bins_ok) bins = false;
+        }
+        if (h.spectrum_fast > fast || (h.spectrum_bins != 0 && !bins) || (h.spectrum_bins != 0 && h.spectrum_bins != 1)) return fail(err, NVB_ERR_DATA, "blob: kernel selection flags");
+        if (h.spectrum_fast == 3 && (size_t)h.max_items * 5 + (size_t)h.ci_total * sizeof(CiRec) + 64 > 160 * 1024) return fail(err, NVB_ERR_DATA, "blob: run kernel does not fit");
     }
     for (int i = 0; i < h.n_modes; i++) {
         const RunMode& rm = S.run_modes[i];
@@ -653,8 +753,26 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
         if (rm.mapping != S.modes[i].mapping || rm.residue != mp.residue || rm.floor != mp.floor || rm.n_coupling != mp.n_coupling || rm.rbegin != R.begin || rm.rend != R.end ||
             rm.pshift != R.pshift || rm.stages != R.stages || rm.nclass != R.nclass || rm.ci_off != R.ci_off || rm.rtype != R.type ||
             rm.cand_off != mp.residue * (h.bs[1] / 2) || rm.ob_off != mp.residue * h.r2_max_p) return fail(err, NVB_ERR_DATA, "blob: run mode %lld", i);
+        {   // k_spectrum_wf's view of the mode
+            const int nw = (R.stages + 3) / 4 > 0 ? (R.stages + 3) / 4 : 1;
+            if (rm.base_stride != (((R.stages + 3) & ~3) > 0 ? ((R.stages + 3) & ~3) : 4) || rm.cc_off < 0 || rm.cc_off + nw * R.nclass > h.cls_cnt_total ||
+                rm.n_posts != (S.floors0[mp.floor].type == 1 ? S.floors[mp.floor].n_posts : 0)) return fail(err, NVB_ERR_DATA, "blob: run mode %lld (wf fields)", i);
+            for (int wd = 0; wd < (R.stages + 3) / 4; wd++) for (int c = 0; c < R.nclass; c++) {
+                uint64_t v = 0;
+                for (int k = 0; k < 4 && 4 * wd + k < R.stages; k++) v |= (uint64_t)(uint16_t)R.cnt[c][4 * wd + k] << (16 * k);
+                if (S.cls_cnt[rm.cc_off + wd * R.nclass + c] != v) return fail(err, NVB_ERR_DATA, "blob: run mode %lld packed entry counts", i);
+            }
+            const int span = (R.type == 2 ? h.channels : 1) * (h.bs[S.modes[i].block_flag] / 2); const int e = R.end < span ? R.end : span;
+            const int P = (e > R.begin && R.psize > 0) ? (e - R.begin) / R.psize : 0;
+            if (P > h.wf_max_p) return fail(err, NVB_ERR_DATA, "blob: run mode %lld partition count", i);
+        }
         if (rm.bins_ok) {
-            if (R.type != 2 || R.pshift < 0 || S.floors0[mp.floor].type != 1) return fail(err, NVB_ERR_DATA, "blob: run mode %lld bins flag", i);
+            if (R.type != 2 || R.pshift < 0 || R.stages < 1 || S.floors0[mp.floor].type != 1) return fail(err, NVB_ERR_DATA, "blob: run mode %lld bins flag", i);
+            for (int c = 0; c < R.nclass; c++) for (int st = 0; st < R.stages; st++) {
+                if (R.books[c][st] < 0) continue;
+                const int dims = S.books[R.books[c][st]].dims;
+                if (!is_pow2(dims) || dims > R.psize) return fail(err, NVB_ERR_DATA, "blob: run mode %lld bins flag (book sizes)", i);
+            }
             const int nb = h.bs[1] / 2; const int span = nb * h.channels; const int e = R.end < span ? R.end : span; const int P = e > R.begin ? (e - R.begin) >> R.pshift : 0;
             if (P > h.r2_max_p) return fail(err, NVB_ERR_DATA, "blob: run mode %lld partitions", i);
             for (int b = 0; b < nb; b++) { const uint32_t cd = S.r2cand[rm.cand_off + b]; if ((int)(cd & 0xffff) + (int)(cd >> 16) > P) return fail(err, NVB_ERR_DATA, "blob: run mode %lld candidate table", i); }
@@ -664,11 +782,16 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
         const DevFloor1& f = S.floors[i];
         if (S.floors0[i].type != 1) continue;
         for (int k = 0; k < f.n_posts; k++) if (f.xs[k] != f.x[f.sort[k]]) return fail(err, NVB_ERR_DATA, "blob: floor %lld sorted x", i);
+        for (int k = 2; k < f.n_posts; k++) if (f.magic[k] != 0xffffffffu / (uint32_t)((int)f.x[f.hi[k]] - (int)f.x[f.lo[k]]) + 1u) return fail(err, NVB_ERR_DATA, "blob: floor %lld multipliers", i);
         for (int b = 0; b < h.bs[1] / 2; b++) {
             const int k = S.bin2k[(size_t)i * (h.bs[1] / 2) + b];
             if (k >= f.n_posts || f.xs[k] > b || (k + 1 < f.n_posts && f.xs[k + 1] <= b)) return fail(err, NVB_ERR_DATA, "blob: floor %lld bin table", i);
         }
     }
+    for (int adx = 2; adx <= h.bs[1] / 2; adx++)
+        if (S.magic[2 * adx] != 0xffffffffu / (uint32_t)adx + 1u || S.magic[2 * adx + 1] != (uint32_t)(0xffffffffull / ((uint64_t)adx * (uint64_t)adx)))
+            return fail(err, NVB_ERR_DATA, "blob: multiplier table");
+    if (S.magic[0] != 1u || S.magic[2] != 1u) return fail(err, NVB_ERR_DATA, "blob: multiplier table");
     return NVB_OK;
 }
 

@@ -28,6 +28,17 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
         cfg__.attrs = attr__; cfg__.numAttrs = 1;                                                           \
         cudaLaunchKernelEx(&cfg__, kernel, arg);                                                            \
     } while (0)
+#define NVB_LAUNCH2(kernel, grid, block, smem, stream, arg0, arg1)                                           \
+    do {                                                                                                    \
+        cudaLaunchConfig_t cfg__ = {};                                                                      \
+        cfg__.gridDim = dim3((unsigned)(grid)); cfg__.blockDim = dim3((unsigned)(block));                   \
+        cfg__.dynamicSmemBytes = (size_t)(smem); cfg__.stream = (cudaStream_t)(stream);                     \
+        cudaLaunchAttribute attr__[1];                                                                      \
+        attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                  \
+        attr__[0].val.programmaticStreamSerializationAllowed = 1;                                           \
+        cfg__.attrs = attr__; cfg__.numAttrs = 1;                                                           \
+        cudaLaunchKernelEx(&cfg__, kernel, arg0, arg1);                                                     \
+    } while (0)
 #define NVB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #if defined(__CUDA_ARCH__)
 #define nvb_grid_dep_wait() asm volatile("griddepcontrol.wait;" ::: "memory")
@@ -48,6 +59,7 @@ struct DevFloor1  {
     uint8_t level[NVB_MAX_POSTS];   // depth of post i in the neighbour dependency tree: 1 + max(level[lo], level[hi]); posts 0, 1 are level 0
     float rcp[NVB_MAX_POSTS];       // 1.0f / (x[hi[i]] - x[lo[i]]): RenderPoint's divisor is a setup constant
     uint16_t xs[NVB_MAX_POSTS];     // x[sort[k]]: the x list in ascending order (k_spectrum_run)
+    uint32_t magic[NVB_MAX_POSTS];  // floor(2^32 / adx) + 1, adx = x[hi[i]] - x[lo[i]] >= 2: RenderPoint's division as one multiply-high (k_spectrum_wf)
 };
 // Floor type 0 (Floor0.cs): one record per floor of the setup (type 1 floors carry type = 1 and nothing else).
 // bark / wmap: element offsets into DevSetup.f0_bark (int32, n entries: barkMap[0..n)) and DevSetup.f0_wmap (float, n entries)
@@ -73,7 +85,14 @@ struct alignas(16) RunMode {
     int32_t n_coupling, mapping, block_flag, rtype;
     int32_t cand_off, ob_off;       // k_spectrum_bins: this residue's slices of DevSetup.r2cand / r2ob
     int32_t bins_ok, pad;           // k_spectrum_bins applies to this mode
+    int32_t cc_off, base_stride;    // k_spectrum_wf: this residue's slice of DevSetup.cls_cnt; stages rounded up to a multiple of 4
+    int32_t n_posts, pad3;          // posts of this mode's floor (type 1)
 };
+// k_spectrum_wf: line segment that starts at an active post (x-sorted position k): RenderLineMulti(x0, y0, x1 = min(hx, n), hy)
+// (Floor1.cs:206); x01 = x0 | x1 << 16 (0xffff: the flat tail, Floor1.cs:213-216); m as in RunSeg.
+struct alignas(16) WfSeg { uint32_t x01; int32_t y0, dy; uint32_t m; };
+// k_spectrum_wf smem bytes per frame group (host-computed, nvb_host.cpp: wf_layout)
+struct WfLayout { int32_t seg_off, fy_off, base_off, cls_off, total, np_pad; };
 struct DevMapping { int32_t n_coupling, floor, residue, pad; uint8_t mag[NVB_MAX_COUPLING], ang[NVB_MAX_COUPLING]; };
 struct DevMode    { int32_t block_flag, mapping; };
 
@@ -111,6 +130,11 @@ struct BlobHeader {
     uint64_t off_r2ob;         // uint16[n_residues][r2_max_p]: (begin + p * psize) / channels, the bin a partition starts at
     int32_t r2_max_p;
     int32_t spectrum_bins;     // 1: every mode can run k_spectrum_bins
+    uint64_t body_hash;        // FNV-1a 64 of everything behind the header: nvb_setup_blob_import rejects a damaged blob
+    uint64_t off_magic;        // uint32[bs[1]/2 + 1][2]: {floor(2^32 / adx) + 1, largest |dy| the multiply-high is exact for} per segment length adx
+    uint64_t off_cls_cnt;      // uint64[sum over residues of ceil(stages / 4) * nclass]: entries per partition of (class, stage), 16 bits per stage
+    int32_t cls_cnt_total;
+    int32_t wf_max_p;          // largest partition count of any mode (k_spectrum_wf's per-frame tables)
 };
 
 // Resolved pointers handed to kernels by value.
@@ -126,6 +150,7 @@ struct DevSetup {
     const CiRec* ci; const uint8_t* bin2k; const RunMode* run_modes;
     const DevFloor0* floors0; const int32_t* f0_bark; const float* f0_wmap; int32_t f0_stride, f0_max_order;
     const uint32_t* r2cand; const uint16_t* r2ob; int32_t spectrum_bins, r2_max_p;
+    const uint32_t* magic; const unsigned long long* cls_cnt; int32_t wf_max_p, max_posts;
 };
 
 // ---- per-frame plan built on the host from nvb_frame (ok frames only, in order) ----------------

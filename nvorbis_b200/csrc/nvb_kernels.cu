@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #endif
 #include <cstdlib>
+#include <type_traits>
 #include "nvb_device_core.h"
 
 namespace nvb {
@@ -1038,6 +1039,404 @@ __global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1+K2+K3, frame-group path (k_spectrum_wf; the default when DevSetup.spectrum_fast == 3): the work of k_spectrum_run with
+// less than half of its instructions.  A frame belongs to a GROUP of WPF warps (1: the whole frame in one warp, nothing but
+// __syncwarp between its phases -- the form a fused K1-K5 kernel wants; 2: one floor per warp in parallel, the better fit
+// for small batches), four warps per CTA.
+//   phase A  per channel: floor1_unwrap_mh (UnwrapPosts with RenderPoint's division as one multiply-high by a setup constant)
+//            and one WfSeg per active post of Floor1.Apply's x-sorted walk; the multiply-high constant of a segment comes from
+//            a table indexed by its length (no division).  Entry-stream offsets: the entries-per-partition of the stages of a
+//            class are packed 16 bits each, so ONE 64-bit warp scan over the partitions yields the offsets of four stages.
+//   main     a thread owns runs of 8 consecutive stream values (as in k_spectrum_run): class + coded-stage mask from shared
+//            memory, ONE code path for every book with dims >= 2 (four float2 loads: lanes of a warp sit in different
+//            partitions with different books, so per-dims paths serialise); the floor line is walked along the run -- segment
+//            found once per (run, channel), y(x) = y0 +- umulhi((x - x0)|dy|, m) with the product advanced by |dy| per bin
+//            and a switch to the next active post when the bin reaches the segment's end.
+// Results are bit-identical to k_spectrum_run / the oracle (same float adds in the same order, same integer floor curve).
+// ------------------------------------------------------------------------------------------------
+constexpr int WF_WARPS = 4;                                               // warps per CTA
+
+// the group's barrier: __syncwarp for one warp per frame, a named barrier for two, __syncthreads for the whole CTA
+template <int WPF> __device__ __forceinline__ void wf_group_sync(int group) {
+    if (WPF == 1) __syncwarp();
+    else if (WPF == WF_WARPS) __syncthreads();
+    else {
+#if !defined(NVB_CPU_SHIM)
+        // ids as immediates: a register id makes ptxas reserve all 16 barriers for the CTA
+        if (group == 0) asm volatile("bar.sync 1, %0;" ::"n"(WPF * 32) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"n"(WPF * 32) : "memory");
+#else
+        cuemu_named_barrier(group + 1, WPF * 32);
+#endif
+    }
+}
+
+#if !defined(NVB_CPU_SHIM)
+__device__ __forceinline__ unsigned wf_reduce_or(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
+#else
+static inline unsigned wf_reduce_or(unsigned v) { for (int d = 16; d >= 1; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d); return v; }
+#endif
+
+// UnwrapPosts (Floor1.cs:224-297) by one warp, lane = post (and post + 32 when H == 2), the posts of one dependency level in
+// parallel; RenderPoint's `err / adx` (Floor1.cs:299-314) is a multiply-high by the setup constant F.magic[i] -- exact for
+// err < 2^20 (adx <= 4096), anything larger (only malformed posts get there) takes the division.  Leaves finalY in fy[].
+template <int H>
+__device__ __forceinline__ unsigned long long floor1_unwrap_mh(const DevFloor1& F, const int16_t* posts, int lane, int* fy, int& count) {
+    count = posts[0];
+    if (count > F.n_posts) count = F.n_posts;
+    if (count < 2) return 0ull;                                           // PostCount == 0: the spectrum is cleared (Floor1.cs:220)
+    int val[H], p_lo[H], p_hi[H], p_x0[H], p_dx[H], p_lvl[H]; unsigned p_m[H];
+    #pragma unroll
+    for (int h = 0; h < H; h++) {
+        const int i = lane + 32 * h;
+        val[h] = i < count ? posts[1 + i] : 0;
+        p_lvl[h] = 0; p_lo[h] = 0; p_hi[h] = 0; p_x0[h] = 0; p_dx[h] = 0; p_m[h] = 0u;
+        if (i >= 2 && i < count) {
+            p_lo[h] = F.lo[i]; p_hi[h] = F.hi[i]; p_x0[h] = F.x[p_lo[h]]; p_dx[h] = F.x[i] - p_x0[h];
+            p_m[h] = F.magic[i]; p_lvl[h] = F.level[i];
+        }
+    }
+    if (lane < 2) fy[lane] = val[0];
+    __syncwarp();
+    unsigned clo = 0u, chi = 0u;                                          // step-flag contributions of this lane's posts
+    const int range = F.range, max_level = F.max_level;
+    for (int lvl = 1; lvl <= max_level; lvl++) {
+        #pragma unroll
+        for (int h = 0; h < H; h++) {
+            if (p_lvl[h] == lvl) {
+                const int i = lane + 32 * h;
+                const int y0 = fy[p_lo[h]];
+                const int dy = fy[p_hi[h]] - y0, ady = dy < 0 ? -dy : dy;
+                const int err = ady * p_dx[h];
+                const int off = (unsigned)err < (1u << 20) ? (int)__umulhi((unsigned)err, p_m[h]) : err / ((int)F.x[p_hi[h]] - p_x0[h]);
+                const int predicted = dy < 0 ? y0 - off : y0 + off;
+                const int v = val[h];
+                const int highroom = range - predicted, lowroom = predicted;
+                const int room = (highroom < lowroom ? highroom : lowroom) * 2;
+                int out = predicted;
+                if (v != 0) {
+                    if (H == 1) clo |= (1u << p_lo[h]) | (1u << p_hi[h]) | (1u << i);
+                    else {
+                        const unsigned long long b = (1ull << p_lo[h]) | (1ull << p_hi[h]) | (1ull << i);
+                        clo |= (unsigned)b; chi |= (unsigned)(b >> 32);
+                    }
+                    if (v >= room) out = highroom > lowroom ? v - lowroom + predicted : predicted - v + highroom - 1;
+                    else out = (v & 1) ? predicted - ((v + 1) >> 1) : predicted + (v >> 1);       // v > 0 here: (v % 2) == 1 <=> v & 1
+                }
+                fy[i] = out;
+            }
+        }
+        __syncwarp();
+    }
+    // stepFlags: 0 and 1 always; i when its own value is non-zero or a later post names it as a neighbour (Floor1.cs:253-257,292)
+    clo = wf_reduce_or(clo);
+    if (H == 2) chi = wf_reduce_or(chi);
+    return (((unsigned long long)chi << 32) | clo) | 3ull;
+}
+
+// Floor 1 of one channel by one warp: unwrap, active-post mask of the x-sorted walk (bit k: sorted position k starts a
+// segment; 0 = no curve, Floor1.cs:220) and one WfSeg per active position.  careful: some segment needs the plain division or
+// leaves inverse_dB_table's range.
+template <int H>
+__device__ __forceinline__ void floor1_wf_segments(const DevFloor1& F, const uint32_t* magic, const int16_t* posts, int n, int lane, int* fy, int* ys, WfSeg* seg,
+                                                   unsigned long long& mask, int& careful_any) {
+    mask = 0ull; careful_any = 0;
+    int count;
+    const unsigned long long flags = floor1_unwrap_mh<H>(F, posts, lane, fy, count);
+    if (count < 2) return;
+    unsigned m[2] = {0u, 0u};
+    const int mult = F.mult;
+    #pragma unroll
+    for (int h = 0; h < H; h++) {
+        const int k = lane + 32 * h;
+        bool act = false;
+        if (k < count) { const int idx = F.sort[k]; act = idx < count && ((flags >> idx) & 1ull); ys[k] = fy[idx < count ? idx : 0] * mult; }
+        m[h] = __ballot_sync(0xffffffffu, act);
+    }
+    mask = (((unsigned long long)m[1] << 32) | m[0]) | 1ull;
+    __syncwarp();
+    bool careful = false;
+    #pragma unroll
+    for (int h = 0; h < H; h++) {
+        const int k = lane + 32 * h;
+        if ((mask >> k) & 1ull) {
+            WfSeg r; const int x0 = F.xs[k]; r.y0 = ys[k]; r.dy = 0; r.m = 1u;
+            int x1 = 0xffff;                                                // the flat tail, Floor1.cs:213-216
+            const unsigned long long above = mask & ~(((1ull << k) << 1) - 1ull);
+            if (above) {
+                const int hi = __ffsll((long long)above) - 1;
+                const int hx = F.xs[hi];
+                x1 = hx < n ? hx : n;                                       // x clamped, y NOT re-interpolated (Floor1.cs:206)
+                const int adx = x1 - x0;
+                r.dy = ys[hi] - r.y0;
+                const unsigned ady = (unsigned)(r.dy < 0 ? -r.dy : r.dy);
+                if (adx >= 2) { const unsigned mm = magic[2 * adx], lim = magic[2 * adx + 1]; r.m = ady <= lim ? mm : 0u; }
+            }
+            r.x01 = (unsigned)x0 | ((unsigned)x1 << 16);
+            seg[k] = r;
+            // y runs monotonically from y0 to y0 + dy: in range at both ends <=> in range everywhere
+            if (x0 < n && (r.m == 0u || (unsigned)r.y0 > 255u || (unsigned)(r.y0 + r.dy) > 255u)) careful = true;
+        }
+    }
+    careful_any = __any_sync(0xffffffffu, careful);
+}
+
+// Entry-stream offsets of every (partition, stage) of the frame by one warp: base[p * ST + st], plus cls[p] = class | coded
+// stage mask << 8 (0 for a class byte outside the residue's range).  Order of the stream: stage-major, partitions ascending.
+__device__ __forceinline__ void wf_entry_offsets(const DevSetup& S, const RunMode& rm, const uint8_t* coded, const uint8_t* cls, int P, int lane,
+                                                 uint32_t* base, uint16_t* scls) {
+    const int stages = rm.stages, ST = rm.base_stride, nclass = rm.nclass;
+    const int nw = (stages + 3) >> 2;
+    uint32_t stage0 = 0;                                                    // entries of all earlier stages
+    for (int w = 0; w < nw; w++) {
+        const unsigned long long* cc = S.cls_cnt + rm.cc_off + w * nclass;
+        unsigned long long run = 0ull;
+        for (int b0 = 0; b0 < P; b0 += 32) {
+            const int p = b0 + lane;
+            unsigned long long pk = 0ull; int cl = 255;
+            if (p < P) { cl = cls[p]; if (cl < nclass) pk = cc[cl]; }
+            unsigned lo = (unsigned)pk, hi = (unsigned)(pk >> 32);          // fields never carry into each other: a stage holds <= 32768 entries
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned ol = __shfl_up_sync(0xffffffffu, lo, d), oh = __shfl_up_sync(0xffffffffu, hi, d);
+                if (lane >= d) { lo += ol; hi += oh; }
+            }
+            const unsigned el = (unsigned)run + lo - (unsigned)pk, eh = (unsigned)(run >> 32) + hi - (unsigned)(pk >> 32);   // exclusive, per field
+            if (p < P) {
+                uint4 v; v.x = el & 0xffffu; v.y = el >> 16; v.z = eh & 0xffffu; v.w = eh >> 16;
+                *reinterpret_cast<uint4*>(base + (size_t)p * ST + 4 * w) = v;
+                if (w == 0) scls[p] = cl < nclass ? (uint16_t)(cl | ((unsigned)coded[cl] << 8)) : (uint16_t)0;
+            }
+            const unsigned tl = __shfl_sync(0xffffffffu, lo, 31), th = __shfl_sync(0xffffffffu, hi, 31);
+            run += ((unsigned long long)th << 32) | tl;
+        }
+        __syncwarp();
+        // the four stages of this word start behind everything earlier: add the stage bases
+        const uint32_t t0 = (unsigned)run & 0xffffu, t1 = (unsigned)run >> 16, t2 = (unsigned)(run >> 32) & 0xffffu, t3 = (unsigned)(run >> 48);
+        const uint32_t s0 = stage0, s1 = s0 + t0, s2 = s1 + t1, s3 = s2 + t2;
+        for (int p = lane; p < P; p += 32) {
+            uint4 v = *reinterpret_cast<uint4*>(base + (size_t)p * ST + 4 * w);
+            v.x += s0; v.y += s1; v.z += s2; v.w += s3;
+            *reinterpret_cast<uint4*>(base + (size_t)p * ST + 4 * w) = v;
+        }
+        stage0 = s3 + t3;
+    }
+}
+
+template <int CT, int WPF, bool P64>
+__global__ void __launch_bounds__(WF_WARPS * 32) k_spectrum_wf(LaunchArgs a, WfLayout L) {
+    constexpr int RB = 8 / CT;                                              // bins per channel in one run
+    constexpr int FPC = WF_WARPS / WPF;                                     // frames per CTA
+    constexpr int GT = WPF * 32;                                            // threads per frame group
+    constexpr int H = P64 ? 2 : 1;
+    typedef typename std::conditional<P64, unsigned long long, unsigned>::type mask_t;
+    NVB_DYN_SMEM(dyn_smem);
+    __shared__ float s_db[256];
+    __shared__ int s_bad[2 * WF_WARPS];                                     // per frame group: bad entry, floor out of range
+
+    nvb_grid_dep_launch();
+    const DevSetup& S = a.S;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int group = warp / WPF, wg = warp - group * WPF, gt = t - group * GT;
+    for (int i = t; i < 256; i += WF_WARPS * 32) s_db[i] = S.db[i];
+    if (t < 2 * WF_WARPS) s_bad[t] = 0;
+    __syncthreads();
+
+    const int fi = blockIdx.x * FPC + group;
+    // warps beyond the batch and drains have nothing to do (a whole group leaves together: its barrier has no other user)
+    if (fi >= a.n_frames) { nvb_grid_dep_wait(); return; }
+    const DevFrame f = a.frames[a.frame_lo + fi];
+    if (f.kind != 0) { nvb_grid_dep_wait(); return; }
+    const RunMode rm = S.run_modes[f.mode];
+    const DevMapping& mp = S.mappings[rm.mapping];
+    const DevFloor1& F = S.floors[rm.floor];
+    const int N = f.n, n = N >> 1, span = CT * n;
+    const int stages = rm.stages, st_n = stages > 0 ? stages : 1, ST = rm.base_stride;
+    const int rbegin = rm.rbegin, pshift = rm.pshift;
+    int P = 0;
+    if (f.res_decoded) { const int e = rm.rend < span ? rm.rend : span; const int nn = e - rbegin; P = nn > 0 ? nn >> pshift : 0; }   // Residue0.cs:122-127
+
+    unsigned char* gsm = dyn_smem + (size_t)group * L.total;
+    WfSeg* s_seg = reinterpret_cast<WfSeg*>(gsm + L.seg_off);               // [CT][np_pad]
+    int* s_fy = reinterpret_cast<int*>(gsm + L.fy_off) + wg * 128;          // per warp: finalY[64], finalY * multiplier in x order [64]
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(gsm + L.base_off);       // [partition][ST]: where the (partition, stage) item's entries start
+    uint16_t* s_cls = reinterpret_cast<uint16_t*>(gsm + L.cls_off);         // [partition]: class | coded stages << 8
+    const int np = L.np_pad;
+    const CiRec* ci_tab = S.ci + rm.ci_off;
+    const uint8_t* cls = a.classes + f.classes_off;
+    const uint16_t* ent = a.entries + f.entries_off;
+    const uint8_t* bin2k = S.bin2k + (size_t)rm.floor * (S.bs[1] >> 1);
+
+    // ---- phase A: floors (warp wg takes channels wg, wg + WPF, ...) and entry offsets (the group's last warp)
+    mask_t fmask[CT]; bool careful[CT];
+    #pragma unroll
+    for (int c = 0; c < CT; c++) { fmask[c] = 0; careful[c] = false; }
+    int* s_flags = reinterpret_cast<int*>(gsm + L.fy_off) + WPF * 128;      // [CT][4]: mask lo, mask hi, careful (groups of more than one warp)
+    #pragma unroll
+    for (int c = 0; c < CT; c++) {
+        if ((c % WPF) == wg && ((f.exec_mask >> c) & 1u)) {
+            unsigned long long mask; int careful_any;
+            floor1_wf_segments<H>(F, S.magic, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, n, lane, s_fy, s_fy + 64, s_seg + c * np, mask, careful_any);
+            fmask[c] = (mask_t)mask; careful[c] = careful_any != 0;
+            if (WPF > 1 && lane == 0) { s_flags[4 * c] = (int)(unsigned)mask; s_flags[4 * c + 1] = (int)(unsigned)(mask >> 32); s_flags[4 * c + 2] = careful_any; }
+            __syncwarp();                                                   // fy / ys are reused by the warp's next channel
+        }
+    }
+    if (wg == WPF - 1 && P > 0) wf_entry_offsets(S, rm, S.residues[rm.residue].coded, cls, P, lane, s_base, s_cls);
+    wf_group_sync<WPF>(group);
+    if (WPF > 1) {
+        #pragma unroll
+        for (int c = 0; c < CT; c++) {
+            if ((f.exec_mask >> c) & 1u) {
+                const unsigned lo = (unsigned)s_flags[4 * c], hi = (unsigned)s_flags[4 * c + 1];
+                fmask[c] = (mask_t)(((unsigned long long)hi << 32) | lo); careful[c] = s_flags[4 * c + 2] != 0;
+            }
+        }
+    }
+    nvb_grid_dep_wait();                                                    // the stores below may overwrite a spectrum an earlier kernel still reads
+
+    // ---- main: runs of 8 stream values
+    float* spec_out = a.spectrum + (size_t)f.spec_off;
+    const uint32_t ecount = f.entry_count;
+    const int pmask = (1 << pshift) - 1;
+    const char* dbp = reinterpret_cast<const char*>(s_db);
+    int bad_floor = 0, bad_entry = 0;
+    const int n_coupling = rm.n_coupling;
+    for (int gi = gt; gi < (span >> 3); gi += GT) {
+        const int pos0 = gi << 3;
+        const int bin0 = pos0 / CT;
+        float acc[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0.f;
+        const int q = pos0 - rbegin, p = q >> pshift;
+        if (q >= 0 && p < P) {
+            const unsigned cw = s_cls[p];
+            unsigned casc = cw >> 8;
+            const int cl = (int)(cw & 0xffu);
+            const int o = q & pmask;
+            while (casc) {
+                const int st = __ffs(casc) - 1; casc &= casc - 1;
+                const CiRec ci = ci_tab[cl * st_n + st];
+                const uint32_t eb = s_base[p * ST + st];
+                const float* tab = S.vq + ci.off;
+                if (ci.dshift >= 1) {                                       // every book with an even number of dimensions: four float2
+                    const int dmask = (1 << ci.dshift) - 1;
+                    #pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const int pos = o + 2 * h;
+                        const uint32_t ei = eb + (uint32_t)(pos >> ci.dshift);
+                        if (ei < ecount) {                                  // else never decoded: contributes nothing (Residue0.cs:164-170)
+                            const int en = ent[ei];
+                            if (en < ci.entries) {
+                                const float2 v = *reinterpret_cast<const float2*>(tab + ((size_t)en << ci.dshift) + (pos & dmask));
+                                acc[2 * h] = NVB_FADD(acc[2 * h], v.x); acc[2 * h + 1] = NVB_FADD(acc[2 * h + 1], v.y);
+                            } else bad_entry = 1;
+                        }
+                    }
+                } else {
+                    #pragma unroll
+                    for (int h = 0; h < 8; h++) {
+                        const uint32_t ei = eb + (uint32_t)o + h;
+                        if (ei < ecount) {
+                            const int en = ent[ei];
+                            if (en < ci.entries) acc[h] = NVB_FADD(acc[h], tab[en]); else bad_entry = 1;
+                        }
+                    }
+                }
+            }
+        }
+        for (int i = n_coupling - 1; i >= 0; --i) {                         // Mapping.cs:137-182
+            const int m = mp.mag[i], an = mp.ang[i];
+            if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
+            if (CT == 2) {                                                  // (magnitude, angle) is (0, 1) or (1, 0)
+                #pragma unroll
+                for (int b = 0; b < RB; b++) { if (m == 0) inverse_couple_sel(acc[2 * b], acc[2 * b + 1]); else inverse_couple_sel(acc[2 * b + 1], acc[2 * b]); }
+            } else {
+                #pragma unroll
+                for (int b = 0; b < RB; b++) {
+                    float vm = 0.f, va = 0.f;
+                    #pragma unroll
+                    for (int k = 0; k < CT; k++) { if (k == m) vm = acc[b * CT + k]; if (k == an) va = acc[b * CT + k]; }
+                    inverse_couple_sel(vm, va);
+                    #pragma unroll
+                    for (int k = 0; k < CT; k++) { if (k == m) acc[b * CT + k] = vm; if (k == an) acc[b * CT + k] = va; }
+                }
+            }
+        }
+        const unsigned kk0 = bin2k[bin0];                                   // sorted position of the last post at or below the run's first bin
+        #pragma unroll
+        for (int c = 0; c < CT; c++) {
+            if ((f.exec_mask >> c) & 1u) {                                  // Floor1.Apply, Floor1.cs:186-222
+                const mask_t M = fmask[c];
+                const WfSeg* segc = s_seg + c * np;
+                if (M == 0) {
+                    #pragma unroll
+                    for (int b = 0; b < RB; b++) acc[b * CT + c] = 0.f;
+                } else if (!careful[c]) {
+                    // the segment of the first bin: last active position at or below its post (bit 0 is set)
+                    int cur = P64 ? 63 - __clzll((long long)(M & (mask_t)(0xffffffffffffffffull >> (63 - kk0)))) : 31 - __clz((int)((unsigned)M & (0xffffffffu >> (31 - kk0))));
+                    WfSeg r = segc[cur];
+                    int x1 = (int)(r.x01 >> 16);
+                    unsigned ady = (unsigned)(r.dy < 0 ? -r.dy : r.dy);
+                    int sgn4 = r.dy < 0 ? -4 : 4;
+                    unsigned tt = (unsigned)(bin0 - (int)(r.x01 & 0xffffu)) * ady;
+                    const char* base = dbp + 4 * r.y0;
+                    #pragma unroll
+                    for (int b = 0; b < RB; b++) {
+                        if (b > 0 && bin0 + b == x1) {                      // the bin reaches the next active post: its segment starts here
+                            const mask_t above = M & ~((((mask_t)1 << cur) << 1) - 1);
+                            cur = P64 ? __ffsll((long long)above) - 1 : __ffs((int)above) - 1;
+                            r = segc[cur];
+                            x1 = (int)(r.x01 >> 16); ady = (unsigned)(r.dy < 0 ? -r.dy : r.dy); sgn4 = r.dy < 0 ? -4 : 4;
+                            tt = 0u; base = dbp + 4 * r.y0;
+                        }
+                        const int qq = (int)__umulhi(tt, r.m);
+                        acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], *reinterpret_cast<const float*>(base + qq * sgn4));
+                        tt += ady;
+                    }
+                } else {
+                    #pragma unroll
+                    for (int b = 0; b < RB; b++) {
+                        const unsigned kk = bin2k[bin0 + b];
+                        const int lo = P64 ? 63 - __clzll((long long)(M & (mask_t)(0xffffffffffffffffull >> (63 - kk)))) : 31 - __clz((int)((unsigned)M & (0xffffffffu >> (31 - kk))));
+                        const WfSeg r = segc[lo];
+                        const int x0 = (int)(r.x01 & 0xffffu), adx = (int)(r.x01 >> 16) - x0;
+                        const int num = (bin0 + b - x0) * (r.dy < 0 ? -r.dy : r.dy);
+                        const int qq = r.m != 0u ? (int)__umulhi((unsigned)num, r.m) : num / adx;
+                        int y = r.dy < 0 ? r.y0 - qq : r.y0 + qq;
+                        if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
+                        acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], s_db[y]);
+                    }
+                }
+            }
+            float* dst = spec_out + (size_t)c * n + bin0;
+            if (RB == 8) {
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            } else if (RB == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[c], acc[CT + c], acc[2 * CT + c], acc[3 * CT + c]);
+            else if (RB == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[c], acc[CT + c]);
+            else *dst = acc[c];
+        }
+    }
+    // rare: count the frame once per kind (the first thread of the frame's group to raise a flag reports it)
+    if (bad_entry && atomicOr(&s_bad[2 * group], 1) == 0) atomicAdd(&a.counters->bad_entry, 1);
+    if (bad_floor && atomicOr(&s_bad[2 * group + 1], 1) == 0) atomicAdd(&a.counters->floor_range, 1);
+}
+
+static WfLayout wf_layout(const DevSetup& S, int CT, int WPF) {
+    WfLayout L;
+    L.np_pad = S.max_posts <= 32 ? 32 : 64;
+    const int st_max = ((S.max_stages + 3) & ~3) > 0 ? ((S.max_stages + 3) & ~3) : 4;
+    const int pmax = S.wf_max_p > 0 ? S.wf_max_p : 1;
+    L.seg_off = 0;
+    L.fy_off = L.seg_off + CT * L.np_pad * (int)sizeof(WfSeg);
+    L.base_off = (L.fy_off + WPF * 128 * (int)sizeof(int) + CT * 4 * (int)sizeof(int) + 15) & ~15;
+    L.cls_off = L.base_off + pmax * st_max * (int)sizeof(uint32_t);
+    L.total = (L.cls_off + pmax * (int)sizeof(uint16_t) + 15) & ~15;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1+K2+K3, bins path (DevSetup.spectrum_bins; used when the run path does not apply): type 2 residues with ANY channel
 // count and partition alignment -- e.g. 6 channels with 32-wide partitions, where (begin + p * psize) is not a multiple of
 // the channel count and the reference's Residue2.WriteVectors (Residue2.cs:23-47) restarts the channel pointer at every
@@ -1542,6 +1941,37 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         }
     }
     static const bool force_planes = std::getenv("NVB_SPECTRUM_PLANES") != nullptr;           // test hook: exercise k_spectrum_planes
+    static const bool force_run = std::getenv("NVB_SPECTRUM_RUN") != nullptr;                 // test hook: exercise k_spectrum_run
+    if (a.S.spectrum_fast >= 3 && !no_planes && !force_planes && !force_run) {
+        const int C = a.S.channels;
+        const int wpf_env = std::getenv("NVB_WF_WPF") ? std::atoi(std::getenv("NVB_WF_WPF")) : 0;   // experiment hook: warps per frame
+        const int WPF = (wpf_env == 1 || wpf_env == 2 || wpf_env == 4) ? wpf_env : 2;
+        const WfLayout L = wf_layout(a.S, C, WPF);
+        const int fpc = WF_WARPS / WPF;
+        const size_t smem = (size_t)L.total * fpc;
+        if (smem <= 200 * 1024) {
+            const bool p64 = L.np_pad > 32;
+            auto go = [&](auto kernel) -> int {
+                static size_t configured[NVB_MAX_DEVICES] = {0};              // one per instantiation (a lambda instantiation has its own statics)
+                size_t& conf = configured[current_device_slot()];
+                if (smem > 40 * 1024 && smem > conf) {
+                    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+                    conf = smem;
+                }
+                NVB_LAUNCH2(kernel, (a.n_frames + fpc - 1) / fpc, WF_WARPS * 32, smem, stream, a, L);
+                return cudaGetLastError() == cudaSuccess ? 1 : -1;
+            };
+#define NVB_WF_CASE(CT_)                                                                                          \
+            if (WPF == 1) return p64 ? go(k_spectrum_wf<CT_, 1, true>) : go(k_spectrum_wf<CT_, 1, false>);          \
+            if (WPF == 2) return p64 ? go(k_spectrum_wf<CT_, 2, true>) : go(k_spectrum_wf<CT_, 2, false>);          \
+            return p64 ? go(k_spectrum_wf<CT_, 4, true>) : go(k_spectrum_wf<CT_, 4, false>);
+            if (C == 1) { NVB_WF_CASE(1) }
+            if (C == 2) { NVB_WF_CASE(2) }
+            if (C == 4) { NVB_WF_CASE(4) }
+            if (C == 8) { NVB_WF_CASE(8) }
+#undef NVB_WF_CASE
+        }
+    }
     if (a.S.spectrum_fast >= 3 && !no_planes && !force_planes) {
         const int C = a.S.channels;
         static const int nt = std::getenv("NVB_SPECTRUM_NT") ? std::atoi(std::getenv("NVB_SPECTRUM_NT")) : 128;

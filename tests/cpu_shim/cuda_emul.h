@@ -13,6 +13,8 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
+#include <type_traits>
 #include <thread>
 #include <vector>
 
@@ -32,6 +34,7 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(4) uchar4 { unsigned char x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
@@ -47,6 +50,8 @@ struct Launch {
     std::vector<std::unique_ptr<std::barrier<>>> warp;
     std::vector<uint32_t> shfl;           // 32 words per warp
     std::atomic<int> or_acc{0};
+    std::mutex named_mu;
+    std::vector<std::unique_ptr<std::barrier<>>> named;
 };
 extern Launch* g_launch;
 extern unsigned char g_dyn_smem[];
@@ -55,6 +60,18 @@ extern thread_local cuemu::Idx threadIdx, blockIdx;
 extern cuemu::Idx blockDim, gridDim;
 
 static inline void __syncthreads() { cuemu::g_launch->cta->arrive_and_wait(); }
+// bar.sync id, nthreads: the barrier object of an id is created by whoever gets there first
+static inline void cuemu_named_barrier(int id, int nthreads) {
+    cuemu::Launch* L = cuemu::g_launch;
+    std::barrier<>* b;
+    {
+        std::lock_guard<std::mutex> g(L->named_mu);
+        if ((int)L->named.size() <= id) L->named.resize((size_t)id + 1);
+        if (!L->named[(size_t)id]) L->named[(size_t)id] = std::make_unique<std::barrier<>>(nthreads);
+        b = L->named[(size_t)id].get();
+    }
+    b->arrive_and_wait();
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::g_launch->warp[threadIdx.x >> 5]->arrive_and_wait(); }
 static inline int __syncthreads_or(int pred) {
     cuemu::Launch* L = cuemu::g_launch;
@@ -189,6 +206,8 @@ void run(int grid, int block, size_t smem, const std::function<void()>& body);
 template <class K, class A> void launch(K kernel, int grid, int block, size_t smem, A arg) { run(grid, block, smem, [=]() { kernel(arg); }); }
 }
 #define NVB_LAUNCH(kernel, grid, block, smem, stream, arg) cuemu::launch(kernel, (int)(grid), (int)(block), (size_t)(smem), arg)
+namespace cuemu { template <class K, class A, class B> void launch2(K kernel, int grid, int block, size_t smem, A a0, B a1) { run(grid, block, smem, [=]() { kernel(a0, a1); }); } }
+#define NVB_LAUNCH2(kernel, grid, block, smem, stream, arg0, arg1) cuemu::launch2(kernel, (int)(grid), (int)(block), (size_t)(smem), arg0, arg1)
 #define NVB_DYN_SMEM(name) unsigned char* name = cuemu::g_dyn_smem
 #define nvb_grid_dep_wait() ((void)0)
 #define nvb_grid_dep_launch() ((void)0)

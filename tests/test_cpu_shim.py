@@ -184,8 +184,12 @@ def test_generic_spectrum_kernel(shim):
             "r, pcm, b = H.decoded('3test')\nctx = capi.Context(0, lib_path=%r); ctx.upload_setup(H.setup_from_oracle(r))\n"
             "want, _ = H.oracle_synth(r, b, 0, 40)\nout, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, 0, 40), capi.RUN_EXACT)\n"
             "assert np.array_equal(out, want)\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"), shim)
-    for var in ("NVB_SPECTRUM_GENERIC", "NVB_SPECTRUM_NO_PLANES", "NVB_SPECTRUM_WARP", "NVB_SPECTRUM_PLANES", "NVB_SPECTRUM_NT"):          # the general kernel / the per-bin fast kernel
-        env = dict(os.environ); env[var] = "256" if var == "NVB_SPECTRUM_NT" else "1"
+    # the general kernel / the per-bin fast kernel / planes / the run kernel / k_spectrum_wf with 1, 2 and 4 warps per frame
+    for var, val in (("NVB_SPECTRUM_GENERIC", "1"), ("NVB_SPECTRUM_NO_PLANES", "1"), ("NVB_SPECTRUM_WARP", "1"), ("NVB_SPECTRUM_PLANES", "1"), ("NVB_SPECTRUM_RUN", "1"),
+                     ("NVB_SPECTRUM_NT", "256"), ("NVB_WF_WPF", "1"), ("NVB_WF_WPF", "2"), ("NVB_WF_WPF", "4")):
+        env = dict(os.environ); env[var] = val
+        if var == "NVB_SPECTRUM_NT":
+            env["NVB_SPECTRUM_RUN"] = "1"
         assert subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().endswith("ok")
 
 
