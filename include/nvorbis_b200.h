@@ -200,8 +200,15 @@ enum {
     NVB_RUN_DEFAULT   = 0,
     NVB_RUN_EXACT     = 1,   /* stb-dataflow IMDCT without FMA contraction: bit-identical to the reference arithmetic */
     NVB_RUN_NO_CLIP   = 2,   /* StreamDecoder.ClipSamples = false (CopyBuffer instead of ClippingCopyBuffer) */
-    NVB_RUN_CONTINUE  = 4    /* chain onto the previous batch of this context (keeps the overlap tail);
+    NVB_RUN_CONTINUE  = 4,   /* chain onto the previous batch of this context (keeps the overlap tail);
                                 without it the batch starts a stream: first block emits nothing (StreamDecoder.cs:446-450) */
+    NVB_RUN_PCM_S16   = 8,   /* nvb_decode_batch[_begin]: pcm_out receives 16-bit PCM (int16_t*, pcm_cap counts int16 elements):
+                                s = round-to-nearest-even(v * 32768) saturated to [-32768, 32767], v = the float sample the call
+                                would otherwise return (after Utils.ClipValue unless NVB_RUN_NO_CLIP).  Halves the read-back;
+                                the reference itself only ever writes 32-bit float WAV (TestApp/WaveWriter.cs:18-62). */
+    NVB_RUN_DEVICE_OUT = 16  /* nvb_decode_batch[_begin]: pcm_out is a DEVICE pointer on the context's GPU (16-byte aligned): the PCM
+                                is left there for an on-device consumer, nothing is copied back (float, or int16 with
+                                NVB_RUN_PCM_S16).  The buffer is ready when the call / the batch's _end returns. */
 };
 
 /* ---- entry points ---------------------------------------------------------------------------- */

@@ -17,10 +17,10 @@ MAX_CHANNELS, MAX_POSTS, MAX_CLASSES, MAX_STAGES, MAX_COUPLING = 8, 64, 64, 8, 3
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_STATE, ERR_CAPACITY, ERR_DATA = 0, -1, -2, -3, -4, -5, -6, -7
 FRAME_OK, FRAME_FAILED = 0, 1
-RUN_DEFAULT, RUN_EXACT, RUN_NO_CLIP, RUN_CONTINUE = 0, 1, 2, 4
+RUN_DEFAULT, RUN_EXACT, RUN_NO_CLIP, RUN_CONTINUE, RUN_PCM_S16, RUN_DEVICE_OUT = 0, 1, 2, 4, 8, 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(_HERE, "libnvorbis_b200.so")
+DEFAULT_LIB = os.environ.get("NVB_LIB_PATH") or os.path.join(_HERE, "libnvorbis_b200.so")      # NVB_LIB_PATH: development hook (kernel build variants)
 
 
 class NvbError(RuntimeError):
@@ -362,10 +362,14 @@ class Context:
         self._check(self.lib.nvb_reset(self.handle), "nvb_reset")
 
     def decode_batch(self, batch: HostBatch, flags: int = RUN_DEFAULT, out: np.ndarray | None = None, cap_samples: int | None = None):
-        """nvb_decode_batch with host buffers.  Returns (interleaved pcm float32 view, Result)."""
+        """nvb_decode_batch with host buffers.  Returns (interleaved pcm view -- float32, or int16 with RUN_PCM_S16 --, Result)."""
+        if flags & RUN_DEVICE_OUT:
+            raise ValueError("RUN_DEVICE_OUT needs a device pointer: use decode_batch_ptr / decode_batch_begin")
         if out is None:
             cap = int(cap_samples) if cap_samples is not None else sum_output_bound(batch.frames)
-            out = np.empty(max(cap * self.channels, 1), np.float32)
+            out = np.empty(max(cap * self.channels, 1), np.int16 if flags & RUN_PCM_S16 else np.float32)
+        elif out.dtype != (np.int16 if flags & RUN_PCM_S16 else np.float32):
+            raise ValueError("out must be int16 with RUN_PCM_S16, float32 otherwise")
         r = ResultStruct()
         rc = self.lib.nvb_decode_batch(self.handle, C.byref(batch.struct), flags, out.ctypes.data, out.size, C.byref(r))
         self._check(rc, "nvb_decode_batch")

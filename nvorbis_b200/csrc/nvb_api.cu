@@ -37,6 +37,7 @@ struct nvb_ctx {
     struct Slot {
         nvb_dbatch* staging = nullptr;
         float* d_pcm = nullptr; size_t pcm_cap = 0;
+        int16_t* d_pcm16 = nullptr; size_t pcm16_cap = 0;     // NVB_RUN_PCM_S16 staging
         cudaEvent_t ev_up[NVB_CHUNKS] = {}, ev_k[NVB_CHUNKS] = {}, ev_all = nullptr;
         Counters* h_counters = nullptr;      // pinned
         DevFrame* h_frames = nullptr; size_t h_frames_cap = 0;   // pinned copy of the plan: its upload must not block the host
@@ -334,7 +335,7 @@ int nvb_destroy(nvb_ctx* ctx) {
     cudaStreamDestroy(ctx->stream);
     for (int i = 0; i < 2; i++) {
         cudaStreamDestroy(ctx->chunk_stream[i]);
-        free_dbatch(ctx->slot[i].staging); cudaFree(ctx->slot[i].d_pcm);
+        free_dbatch(ctx->slot[i].staging); cudaFree(ctx->slot[i].d_pcm); cudaFree(ctx->slot[i].d_pcm16);
         cudaEventDestroy(ctx->slot[i].ev_all);
         for (int k = 0; k < NVB_CHUNKS; k++) { cudaEventDestroy(ctx->slot[i].ev_up[k]); cudaEventDestroy(ctx->slot[i].ev_k[k]); }
         if (ctx->slot[i].h_counters) cudaFreeHost(ctx->slot[i].h_counters);
@@ -430,7 +431,22 @@ int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, floa
     if (rc != NVB_OK) { cudaStreamSynchronize(st_up); return rc; }
     const size_t n_out = (size_t)b->plan.samples * ctx->H.channels;
     if (n_out > pcm_cap || (n_out > 0 && !pcm_out)) { cudaStreamSynchronize(st_up); return set_err(ctx, NVB_ERR_CAPACITY, "pcm_out too small for the batch"); }
-    if ((rc = grow(ctx, sl.d_pcm, sl.pcm_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(st_up); return rc; }
+    // output form: float or 16-bit PCM (NVB_RUN_PCM_S16), copied back to the host or left in the caller's device buffer (NVB_RUN_DEVICE_OUT)
+    const bool s16 = (flags & NVB_RUN_PCM_S16) != 0, dev_out = (flags & NVB_RUN_DEVICE_OUT) != 0;
+    if (dev_out && n_out > 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, pcm_out) != cudaSuccess || pa.type != cudaMemoryTypeDevice || pa.device != ctx->device || (reinterpret_cast<uintptr_t>(pcm_out) & 15)) {
+            cudaGetLastError(); cudaStreamSynchronize(st_up);
+            return set_err(ctx, NVB_ERR_ARG, "NVB_RUN_DEVICE_OUT: pcm_out must be a 16-byte aligned device pointer on the context's GPU");
+        }
+    }
+    float* d_float = (dev_out && !s16) ? pcm_out : nullptr;                 // where the kernels write float PCM
+    if (!d_float) { if ((rc = grow(ctx, sl.d_pcm, sl.pcm_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(st_up); return rc; } d_float = sl.d_pcm; }
+    int16_t* d_s16 = nullptr;
+    if (s16) {
+        if (dev_out) d_s16 = reinterpret_cast<int16_t*>(pcm_out);
+        else { if ((rc = grow(ctx, sl.d_pcm16, sl.pcm16_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(st_up); return rc; } d_s16 = sl.d_pcm16; }
+    }
     const int nf = (int)b->plan.frames.size();
     const int n_chunks = (chunked_inputs && nf >= chunk_min && nf >= 8) ? NVB_CHUNKS : 1;
     if (n_chunks == 1 && chunked_inputs) {                                  // few decoded frames after all: upload everything now
@@ -466,15 +482,23 @@ int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, floa
         NVB_CUDA(ctx, cudaEventRecord(sl.ev_up[k], st_up));
         NVB_CUDA(ctx, cudaStreamWaitEvent(st_k, sl.ev_up[k], 0));
         NVB_TRACE_MARK(st_k, "kernels_begin", k);
-        rc = enqueue(ctx, b, 0, nullptr, sl.d_pcm, true, st_k, n_chunks == 1 ? 0 : lo, n_chunks == 1 ? -1 : hi - lo, false);
+        rc = enqueue(ctx, b, 0, nullptr, d_float, true, st_k, n_chunks == 1 ? 0 : lo, n_chunks == 1 ? -1 : hi - lo, false);
         if (rc != NVB_OK) { cudaDeviceSynchronize(); return rc; }
+        size_t s0 = 0, s1 = 0;                                              // this chunk's elements of the interleaved PCM
+        if (nf > 0) {
+            s0 = (size_t)b->plan.frames[(size_t)lo].pcm_off * C;
+            s1 = (n_chunks > 1 && hi < nf) ? (size_t)b->plan.frames[(size_t)hi].pcm_off * C : n_out;
+        }
+        if (s16 && s1 > s0) {
+            if (launch_pcm_s16(d_float, d_s16, (long long)s0, (long long)s1, st_k) < 0) { cudaDeviceSynchronize(); return cuda_fail(ctx, cudaGetLastError(), "k_pcm_s16 launch"); }
+            b->launches += 1;
+        }
         NVB_CUDA(ctx, cudaEventRecord(sl.ev_k[k], st_k));
         NVB_CUDA(ctx, cudaStreamWaitEvent(st_down, sl.ev_k[k], 0));
         NVB_TRACE_MARK(st_down, "d2h_begin", k);
-        if (nf > 0) {
-            const size_t s0 = (size_t)b->plan.frames[(size_t)lo].pcm_off * C;
-            const size_t s1 = (n_chunks > 1 && hi < nf) ? (size_t)b->plan.frames[(size_t)hi].pcm_off * C : n_out;
-            if (s1 > s0) NVB_CUDA(ctx, cudaMemcpyAsync(pcm_out + s0, sl.d_pcm + s0, (s1 - s0) * sizeof(float), cudaMemcpyDeviceToHost, st_down));
+        if (s1 > s0 && !dev_out) {
+            if (s16) NVB_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<int16_t*>(pcm_out) + s0, d_s16 + s0, (s1 - s0) * sizeof(int16_t), cudaMemcpyDeviceToHost, st_down));
+            else NVB_CUDA(ctx, cudaMemcpyAsync(pcm_out + s0, d_float + s0, (s1 - s0) * sizeof(float), cudaMemcpyDeviceToHost, st_down));
         }
         NVB_TRACE_MARK(st_down, "d2h_end", k);
     }

@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
     // the first transform's rows are requested before the lane tables have landed: both latencies overlap
     const int vfirst = first * U, vhi = hi * U;                             // unit indices (== frame indices when not grouped)
     LongIn pre; int pre_x = -1, pre_c = -1;
+#if !defined(NVB_FUSED_NO_PREFETCH)
     if (vfirst + warp < vhi) {
         const int v0 = vfirst + warp, x0 = GROUPED ? v0 / U : v0, c0 = GROUPED ? (v0 - x0 * U) * 2 : 0;
         const DevFrame* f0 = a.frames + x0;
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
             long_phase1_load(lane, reinterpret_cast<const float2*>(a.spectrum + (size_t)f0->spec_off + (size_t)c0 * (FUSED_LONG_N / 2)), pre); pre_x = v0; pre_c = 0;
         }
     }
+#endif
     mbar_wait(s_tabbar, 0);
 
     const float2* s_tw0 = reinterpret_cast<const float2*>(s_tab + FusedTables::TW0);
@@ -222,7 +224,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
     float peak = 0.f;
     // Register-level software pipeline: the spectrum rows of the warp's next long transform are loaded right after
     // the current transform has consumed its inputs, so the load latency hides behind passes 2-3 and the output.
+#if defined(NVB_FUSED_NO_PREFETCH)
+    // build option: no register prefetch (32 fewer live registers; more warps per SM hide the load latency instead)
+    auto can_prefetch = [&](int, int, uint32_t, int) { return false; };
+#else
     auto can_prefetch = [&](int kind, int n, uint32_t exec_mask, int cc) { return kind == 0 && n == FUSED_LONG_N && ((exec_mask >> cc) & 1u); };
+#endif
 
     for (int v = vfirst + warp; v < vhi; v += FUSED_WARPS) {
         const int rel = v - vfirst, slot = rel % NS, it = rel / NS;

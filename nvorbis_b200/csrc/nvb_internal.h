@@ -28,7 +28,7 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
         cfg__.attrs = attr__; cfg__.numAttrs = 1;                                                           \
         cudaLaunchKernelEx(&cfg__, kernel, arg);                                                            \
     } while (0)
-#define NVB_LAUNCH2(kernel, grid, block, smem, stream, arg0, arg1)                                           \
+#define NVB_LAUNCHV(kernel, grid, block, smem, stream, ...)                                                 \
     do {                                                                                                    \
         cudaLaunchConfig_t cfg__ = {};                                                                      \
         cfg__.gridDim = dim3((unsigned)(grid)); cfg__.blockDim = dim3((unsigned)(block));                   \
@@ -37,7 +37,7 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
         attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                  \
         attr__[0].val.programmaticStreamSerializationAllowed = 1;                                           \
         cfg__.attrs = attr__; cfg__.numAttrs = 1;                                                           \
-        cudaLaunchKernelEx(&cfg__, kernel, arg0, arg1);                                                     \
+        cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                                                    \
     } while (0)
 #define NVB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #if defined(__CUDA_ARCH__)
@@ -193,6 +193,7 @@ int launch_spectrum(const LaunchArgs& a, void* stream);            // picks k_sp
 int launch_spectrum_generic(const LaunchArgs& a, void* stream);
 int launch_imdct_exact(const LaunchArgs& a, void* stream);   // spectrum -> windowed blocks
 int launch_ola(const LaunchArgs& a, void* stream);           // blocks (+carry) -> interleaved PCM
+int launch_pcm_s16(const float* src, int16_t* dst, long long lo, long long hi, void* stream);   // NVB_RUN_PCM_S16: elements [lo, hi)
 // Fused fast path: spectrum -> PCM for runs of frames; returns <0 if the batch shape is not covered.
 int launch_imdct_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream);
 bool fused_supported(const BlobHeader& h, const DevFrame* host_frames, int n_frames);

@@ -1223,13 +1223,194 @@ __device__ __forceinline__ void wf_entry_offsets(const DevSetup& S, const RunMod
     }
 }
 
+// ---- shared memory by 32-bit address (the generic-pointer form costs a window conversion per access)
+#if !defined(NVB_CPU_SHIM)
+typedef uint32_t wf_saddr;
+__device__ __forceinline__ wf_saddr wf_smem(const void* p) { return (wf_saddr)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float wf_lds_f32(wf_saddr a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ WfSeg wf_lds_seg(wf_saddr a) {
+    WfSeg r; asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x01), "=r"(r.y0), "=r"(r.dy), "=r"(r.m) : "r"(a)); return r;
+}
+__device__ __forceinline__ uint32_t wf_lds_u32(wf_saddr a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t wf_lds_u16(wf_saddr a) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+#else
+typedef uintptr_t wf_saddr;
+static inline wf_saddr wf_smem(const void* p) { return (wf_saddr)p; }
+static inline float wf_lds_f32(wf_saddr a) { return *reinterpret_cast<const float*>(a); }
+static inline WfSeg wf_lds_seg(wf_saddr a) { return *reinterpret_cast<const WfSeg*>(a); }
+static inline uint32_t wf_lds_u32(wf_saddr a) { return *reinterpret_cast<const uint32_t*>(a); }
+static inline uint32_t wf_lds_u16(wf_saddr a) { return *reinterpret_cast<const uint16_t*>(a); }
+#endif
+
+// Inverse coupling of one bin (Mapping.cs:145-181): the four sign cases are one add -- new = M + (same sign ? -A : A) -- and
+// two selects (M - A and M + (-A) are the same IEEE operation).
+__device__ __forceinline__ void inverse_couple_fast(float& m, float& a) {
+    const float M = m, A = a;
+    const bool mp = M > 0.f, ap = A > 0.f;
+    const float t = NVB_FADD(M, (mp == ap) ? -A : A);
+    m = ap ? M : t;
+    a = ap ? t : M;
+}
+
+// Per-frame values of k_spectrum_wf's main loop (warp-uniform).
+template <int CT, bool P64> struct WfFrame {
+    typedef typename std::conditional<P64, unsigned long long, unsigned>::type mask_t;
+    // offsets into the launch's arrays instead of pointers (the bases sit in the constant bank): half the registers
+    uint32_t entries_off, spec_off, ci_off, bin2k_off;
+    wf_saddr sdb, sseg, sbase, scls;                                        // inverse_dB_table, segments [CT][np], entry offsets [partition][ST], class words
+    uint32_t ecount, exec_mask;
+    int n, span, np, P, rbegin, pshift, ST, st_n, n_coupling, mapping;
+    mask_t fmask[CT]; bool careful[CT];
+};
+
+// Runs of 16 consecutive stream values (two runs of 8: 16 / CT bins of every channel), stride GT.  PLAIN: every channel is
+// executed with a floor curve on the multiply-high path (the common frame); CM: 0 no coupling step applies, 1 / 2 stereo
+// with (magnitude, angle) = (0, 1) / (1, 0), 3 the general step list.
+template <int CT, int GT, bool P64, bool PLAIN, int CM>
+__device__ __forceinline__ void wf_main(const LaunchArgs& a, const WfFrame<CT, P64>& x, int gt, int& bad_entry, int& bad_floor) {
+    const uint16_t* __restrict__ ent = a.entries; const float* __restrict__ vq = a.S.vq; const CiRec* __restrict__ ci_tab = a.S.ci;
+    const uint8_t* __restrict__ bin2k = a.S.bin2k;
+    typedef typename WfFrame<CT, P64>::mask_t mask_t;
+    constexpr int NB = 16 / CT;                                             // bins per channel in a double run
+    const int pmask = (1 << x.pshift) - 1;
+    for (int d = gt; d < (x.span >> 4); d += GT) {
+        float acc[16];
+        #pragma unroll
+        for (int k = 0; k < 16; k++) acc[k] = 0.f;
+        // ---- residue: the VQ vectors of the two runs, stage by stage from +0 (the float adds of WriteVectors in the reference's order)
+        #pragma unroll
+        for (int r8 = 0; r8 < 2; r8++) {
+            float* ac = acc + 8 * r8;
+            const int q = (d << 4) + 8 * r8 - x.rbegin, p = q >> x.pshift;
+            const bool inr = q >= 0 && p < x.P;
+            const unsigned cw = inr ? wf_lds_u16(x.scls + (wf_saddr)(2 * (inr ? p : 0))) : 0u;
+            unsigned casc = cw >> 8;
+            const int cl = (int)(cw & 0xffu);
+            const int o = q & pmask;
+            while (casc) {                                                  // one iteration for most partitions
+                const int st = __ffs(casc) - 1; casc &= casc - 1;
+                const CiRec ci = ci_tab[x.ci_off + (uint32_t)(cl * x.st_n + st)];
+                const uint32_t eb = wf_lds_u32(x.sbase + (wf_saddr)(4 * (p * x.ST + st)));
+                if (ci.dshift >= 1) {                                       // every book with an even number of dimensions: four float2
+                    const int dmask = (1 << ci.dshift) - 1;
+                    uint32_t en[4]; bool ok[4];
+                    #pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const uint32_t ei = eb + (uint32_t)((o + 2 * h) >> ci.dshift);
+                        ok[h] = ei < x.ecount;                              // else never decoded: contributes nothing (Residue0.cs:164-170)
+                        en[h] = 0u;
+                        if (ok[h]) en[h] = ent[x.entries_off + ei];
+                    }
+                    #pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const bool good = ok[h] && en[h] < (uint32_t)ci.entries;
+                        if (ok[h] && !good) bad_entry = 1;
+                        float2 v = make_float2(0.f, 0.f);
+                        if (good) v = *reinterpret_cast<const float2*>(vq + (uint32_t)(ci.off + (int)(en[h] << ci.dshift) + ((o + 2 * h) & dmask)));
+                        if (good) { ac[2 * h] = NVB_FADD(ac[2 * h], v.x); ac[2 * h + 1] = NVB_FADD(ac[2 * h + 1], v.y); }
+                    }
+                } else {
+                    #pragma unroll
+                    for (int h = 0; h < 8; h++) {
+                        const uint32_t ei = eb + (uint32_t)o + h;
+                        if (ei < x.ecount) {
+                            const uint32_t e1 = ent[x.entries_off + ei];
+                            if (e1 < (uint32_t)ci.entries) ac[h] = NVB_FADD(ac[h], vq[(uint32_t)ci.off + e1]); else bad_entry = 1;
+                        }
+                    }
+                }
+            }
+        }
+        // ---- inverse coupling, last step first (Mapping.cs:137-182); the pairs of a bin sit in the same thread
+        if (CM == 1) {
+            #pragma unroll
+            for (int b = 0; b < 8; b++) inverse_couple_fast(acc[2 * b], acc[2 * b + 1]);
+        } else if (CM == 2) {
+            #pragma unroll
+            for (int b = 0; b < 8; b++) inverse_couple_fast(acc[2 * b + 1], acc[2 * b]);
+        } else if (CM == 3) {
+            for (int i = x.n_coupling - 1; i >= 0; --i) {
+                const int m = a.S.mappings[x.mapping].mag[i], an = a.S.mappings[x.mapping].ang[i];
+                if (!(((x.exec_mask >> m) | (x.exec_mask >> an)) & 1u)) continue;
+                #pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    float vm = 0.f, va = 0.f;
+                    #pragma unroll
+                    for (int k = 0; k < CT; k++) { if (k == m) vm = acc[b * CT + k]; if (k == an) va = acc[b * CT + k]; }
+                    inverse_couple_fast(vm, va);
+                    #pragma unroll
+                    for (int k = 0; k < CT; k++) { if (k == m) acc[b * CT + k] = vm; if (k == an) acc[b * CT + k] = va; }
+                }
+            }
+        }
+        // ---- floor curve (Floor1.Apply, Floor1.cs:186-222) walked along the run, and the store
+        const int bin0 = (d << 4) / CT;
+        const unsigned kk0 = bin2k[x.bin2k_off + (uint32_t)bin0];           // sorted position of the last post at or below the first bin
+        #pragma unroll
+        for (int c = 0; c < CT; c++) {
+            const mask_t M = x.fmask[c];
+            if (PLAIN || (((x.exec_mask >> c) & 1u) && M != 0 && !x.careful[c])) {
+                // the segment of the first bin: last active position at or below its post (bit 0 is set)
+                int cur = P64 ? 63 - __clzll((long long)(M & (mask_t)(0xffffffffffffffffull >> (63 - kk0)))) : 31 - __clz((int)((unsigned)M & (0xffffffffu >> (31 - kk0))));
+                const wf_saddr segc = x.sseg + (wf_saddr)(c * x.np) * (wf_saddr)sizeof(WfSeg);
+                WfSeg r = wf_lds_seg(segc + (wf_saddr)cur * (wf_saddr)sizeof(WfSeg));
+                int xrel = (int)(r.x01 >> 16) - bin0;                       // bins until the next active post
+                unsigned ady = (unsigned)(r.dy < 0 ? -r.dy : r.dy);
+                int sgn4 = r.dy < 0 ? -4 : 4;
+                unsigned tt = (unsigned)(bin0 - (int)(r.x01 & 0xffffu)) * ady;
+                wf_saddr base = x.sdb + (wf_saddr)(4 * r.y0);
+                #pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    if (b > 0 && xrel == b) {                               // the bin reaches the next active post: its segment starts here
+                        const mask_t above = M & ~((((mask_t)1 << cur) << 1) - 1);
+                        cur = P64 ? __ffsll((long long)above) - 1 : __ffs((int)above) - 1;
+                        r = wf_lds_seg(segc + (wf_saddr)cur * (wf_saddr)sizeof(WfSeg));
+                        xrel = (int)(r.x01 >> 16) - bin0; ady = (unsigned)(r.dy < 0 ? -r.dy : r.dy); sgn4 = r.dy < 0 ? -4 : 4;
+                        tt = 0u; base = x.sdb + (wf_saddr)(4 * r.y0);
+                    }
+                    const int qq = (int)__umulhi(tt, r.m);
+                    acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], wf_lds_f32(base + (wf_saddr)(qq * sgn4)));
+                    tt += ady;
+                }
+            } else if ((x.exec_mask >> c) & 1u) {
+                if (M == 0) {                                               // no curve: the channel is cleared (Floor1.cs:220)
+                    #pragma unroll
+                    for (int b = 0; b < NB; b++) acc[b * CT + c] = 0.f;
+                } else {                                                    // some segment needs the plain division or leaves inverse_dB_table's range
+                    const wf_saddr segc = x.sseg + (wf_saddr)(c * x.np) * (wf_saddr)sizeof(WfSeg);
+                    #pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        const unsigned kk = bin2k[x.bin2k_off + (uint32_t)(bin0 + b)];
+                        const int lo = P64 ? 63 - __clzll((long long)(M & (mask_t)(0xffffffffffffffffull >> (63 - kk)))) : 31 - __clz((int)((unsigned)M & (0xffffffffu >> (31 - kk))));
+                        const WfSeg r = wf_lds_seg(segc + (wf_saddr)lo * (wf_saddr)sizeof(WfSeg));
+                        const int x0 = (int)(r.x01 & 0xffffu), adx = (int)(r.x01 >> 16) - x0;
+                        const int num = (bin0 + b - x0) * (r.dy < 0 ? -r.dy : r.dy);
+                        const int qq = r.m != 0u ? (int)__umulhi((unsigned)num, r.m) : num / adx;
+                        int y = r.dy < 0 ? r.y0 - qq : r.y0 + qq;
+                        if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
+                        acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], wf_lds_f32(x.sdb + (wf_saddr)(4 * y)));
+                    }
+                }
+            }
+            float* dst = a.spectrum + (x.spec_off + (uint32_t)(c * x.n + bin0));
+            if (CT == 1) {
+                #pragma unroll
+                for (int v4 = 0; v4 < 4; v4++) reinterpret_cast<float4*>(dst)[v4] = make_float4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2], acc[4 * v4 + 3]);
+            } else if (CT == 2) {
+                reinterpret_cast<float4*>(dst)[0] = make_float4(acc[c], acc[2 + c], acc[4 + c], acc[6 + c]);
+                reinterpret_cast<float4*>(dst)[1] = make_float4(acc[8 + c], acc[10 + c], acc[12 + c], acc[14 + c]);
+            } else if (CT == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[c], acc[4 + c], acc[8 + c], acc[12 + c]);
+            else *reinterpret_cast<float2*>(dst) = make_float2(acc[c], acc[8 + c]);
+        }
+    }
+}
+
 template <int CT, int WPF, bool P64>
-__global__ void __launch_bounds__(WF_WARPS * 32) k_spectrum_wf(LaunchArgs a, WfLayout L) {
-    constexpr int RB = 8 / CT;                                              // bins per channel in one run
+__global__ void __launch_bounds__(WF_WARPS * 32, 8) k_spectrum_wf(LaunchArgs a, WfLayout L) {
     constexpr int FPC = WF_WARPS / WPF;                                     // frames per CTA
     constexpr int GT = WPF * 32;                                            // threads per frame group
     constexpr int H = P64 ? 2 : 1;
-    typedef typename std::conditional<P64, unsigned long long, unsigned>::type mask_t;
+    typedef typename WfFrame<CT, P64>::mask_t mask_t;
     NVB_DYN_SMEM(dyn_smem);
     __shared__ float s_db[256];
     __shared__ int s_bad[2 * WF_WARPS];                                     // per frame group: bad entry, floor out of range
@@ -1248,176 +1429,67 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_spectrum_wf(LaunchArgs a, WfL
     const DevFrame f = a.frames[a.frame_lo + fi];
     if (f.kind != 0) { nvb_grid_dep_wait(); return; }
     const RunMode rm = S.run_modes[f.mode];
-    const DevMapping& mp = S.mappings[rm.mapping];
     const DevFloor1& F = S.floors[rm.floor];
-    const int N = f.n, n = N >> 1, span = CT * n;
-    const int stages = rm.stages, st_n = stages > 0 ? stages : 1, ST = rm.base_stride;
-    const int rbegin = rm.rbegin, pshift = rm.pshift;
-    int P = 0;
-    if (f.res_decoded) { const int e = rm.rend < span ? rm.rend : span; const int nn = e - rbegin; P = nn > 0 ? nn >> pshift : 0; }   // Residue0.cs:122-127
+    const int n = f.n >> 1;
+    WfFrame<CT, P64> x;
+    x.n = n; x.span = CT * n; x.np = L.np_pad; x.rbegin = rm.rbegin; x.pshift = rm.pshift; x.ST = rm.base_stride;
+    x.st_n = rm.stages > 0 ? rm.stages : 1; x.n_coupling = rm.n_coupling; x.mapping = rm.mapping;
+    x.P = 0;
+    if (f.res_decoded) { const int e = rm.rend < x.span ? rm.rend : x.span; const int nn = e - rm.rbegin; x.P = nn > 0 ? nn >> rm.pshift : 0; }   // Residue0.cs:122-127
+    x.entries_off = f.entries_off; x.ci_off = (uint32_t)rm.ci_off; x.bin2k_off = (uint32_t)(rm.floor * (S.bs[1] >> 1));
+    x.ecount = f.entry_count; x.exec_mask = f.exec_mask; x.spec_off = f.spec_off;
+    const uint8_t* cls = a.classes + f.classes_off;
+    if (x.P > 0) for (uint32_t i = (uint32_t)gt * 64u; i < f.entry_count; i += GT * 64u) prefetch_l1(a.entries + f.entries_off + i);   // the frame's entries: 128 bytes per thread
 
     unsigned char* gsm = dyn_smem + (size_t)group * L.total;
     WfSeg* s_seg = reinterpret_cast<WfSeg*>(gsm + L.seg_off);               // [CT][np_pad]
     int* s_fy = reinterpret_cast<int*>(gsm + L.fy_off) + wg * 128;          // per warp: finalY[64], finalY * multiplier in x order [64]
+    int* s_flags = reinterpret_cast<int*>(gsm + L.fy_off) + WPF * 128;      // [CT][4]: mask lo, mask hi, careful (groups of more than one warp)
     uint32_t* s_base = reinterpret_cast<uint32_t*>(gsm + L.base_off);       // [partition][ST]: where the (partition, stage) item's entries start
     uint16_t* s_cls = reinterpret_cast<uint16_t*>(gsm + L.cls_off);         // [partition]: class | coded stages << 8
-    const int np = L.np_pad;
-    const CiRec* ci_tab = S.ci + rm.ci_off;
-    const uint8_t* cls = a.classes + f.classes_off;
-    const uint16_t* ent = a.entries + f.entries_off;
-    const uint8_t* bin2k = S.bin2k + (size_t)rm.floor * (S.bs[1] >> 1);
+    x.sdb = wf_smem(s_db); x.sseg = wf_smem(s_seg); x.sbase = wf_smem(s_base); x.scls = wf_smem(s_cls);
 
     // ---- phase A: floors (warp wg takes channels wg, wg + WPF, ...) and entry offsets (the group's last warp)
-    mask_t fmask[CT]; bool careful[CT];
     #pragma unroll
-    for (int c = 0; c < CT; c++) { fmask[c] = 0; careful[c] = false; }
-    int* s_flags = reinterpret_cast<int*>(gsm + L.fy_off) + WPF * 128;      // [CT][4]: mask lo, mask hi, careful (groups of more than one warp)
+    for (int c = 0; c < CT; c++) { x.fmask[c] = 0; x.careful[c] = false; }
     #pragma unroll
     for (int c = 0; c < CT; c++) {
         if ((c % WPF) == wg && ((f.exec_mask >> c) & 1u)) {
             unsigned long long mask; int careful_any;
-            floor1_wf_segments<H>(F, S.magic, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, n, lane, s_fy, s_fy + 64, s_seg + c * np, mask, careful_any);
-            fmask[c] = (mask_t)mask; careful[c] = careful_any != 0;
+            floor1_wf_segments<H>(F, S.magic, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, n, lane, s_fy, s_fy + 64, s_seg + c * L.np_pad, mask, careful_any);
+            x.fmask[c] = (mask_t)mask; x.careful[c] = careful_any != 0;
             if (WPF > 1 && lane == 0) { s_flags[4 * c] = (int)(unsigned)mask; s_flags[4 * c + 1] = (int)(unsigned)(mask >> 32); s_flags[4 * c + 2] = careful_any; }
             __syncwarp();                                                   // fy / ys are reused by the warp's next channel
         }
     }
-    if (wg == WPF - 1 && P > 0) wf_entry_offsets(S, rm, S.residues[rm.residue].coded, cls, P, lane, s_base, s_cls);
+    if (wg == WPF - 1 && x.P > 0) wf_entry_offsets(S, rm, S.residues[rm.residue].coded, cls, x.P, lane, s_base, s_cls);
     wf_group_sync<WPF>(group);
     if (WPF > 1) {
         #pragma unroll
         for (int c = 0; c < CT; c++) {
             if ((f.exec_mask >> c) & 1u) {
                 const unsigned lo = (unsigned)s_flags[4 * c], hi = (unsigned)s_flags[4 * c + 1];
-                fmask[c] = (mask_t)(((unsigned long long)hi << 32) | lo); careful[c] = s_flags[4 * c + 2] != 0;
+                x.fmask[c] = (mask_t)(((unsigned long long)hi << 32) | lo); x.careful[c] = s_flags[4 * c + 2] != 0;
             }
         }
     }
+    // the common frame: every channel executed, with a curve, all segments on the multiply-high path
+    bool plain = (f.exec_mask & ((1u << CT) - 1u)) == ((1u << CT) - 1u);
+    #pragma unroll
+    for (int c = 0; c < CT; c++) plain = plain && x.fmask[c] != 0 && !x.careful[c];
+    int cm = 0;
+    const DevMapping& mp = S.mappings[rm.mapping];
+    for (int i = 0; i < rm.n_coupling; i++) if (((f.exec_mask >> mp.mag[i]) | (f.exec_mask >> mp.ang[i])) & 1u) cm = 3;
+    if (CT == 2 && cm == 3 && rm.n_coupling == 1) cm = mp.mag[0] == 0 ? 1 : 2;
     nvb_grid_dep_wait();                                                    // the stores below may overwrite a spectrum an earlier kernel still reads
 
-    // ---- main: runs of 8 stream values
-    float* spec_out = a.spectrum + (size_t)f.spec_off;
-    const uint32_t ecount = f.entry_count;
-    const int pmask = (1 << pshift) - 1;
-    const char* dbp = reinterpret_cast<const char*>(s_db);
     int bad_floor = 0, bad_entry = 0;
-    const int n_coupling = rm.n_coupling;
-    for (int gi = gt; gi < (span >> 3); gi += GT) {
-        const int pos0 = gi << 3;
-        const int bin0 = pos0 / CT;
-        float acc[8];
-        #pragma unroll
-        for (int k = 0; k < 8; k++) acc[k] = 0.f;
-        const int q = pos0 - rbegin, p = q >> pshift;
-        if (q >= 0 && p < P) {
-            const unsigned cw = s_cls[p];
-            unsigned casc = cw >> 8;
-            const int cl = (int)(cw & 0xffu);
-            const int o = q & pmask;
-            while (casc) {
-                const int st = __ffs(casc) - 1; casc &= casc - 1;
-                const CiRec ci = ci_tab[cl * st_n + st];
-                const uint32_t eb = s_base[p * ST + st];
-                const float* tab = S.vq + ci.off;
-                if (ci.dshift >= 1) {                                       // every book with an even number of dimensions: four float2
-                    const int dmask = (1 << ci.dshift) - 1;
-                    #pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        const int pos = o + 2 * h;
-                        const uint32_t ei = eb + (uint32_t)(pos >> ci.dshift);
-                        if (ei < ecount) {                                  // else never decoded: contributes nothing (Residue0.cs:164-170)
-                            const int en = ent[ei];
-                            if (en < ci.entries) {
-                                const float2 v = *reinterpret_cast<const float2*>(tab + ((size_t)en << ci.dshift) + (pos & dmask));
-                                acc[2 * h] = NVB_FADD(acc[2 * h], v.x); acc[2 * h + 1] = NVB_FADD(acc[2 * h + 1], v.y);
-                            } else bad_entry = 1;
-                        }
-                    }
-                } else {
-                    #pragma unroll
-                    for (int h = 0; h < 8; h++) {
-                        const uint32_t ei = eb + (uint32_t)o + h;
-                        if (ei < ecount) {
-                            const int en = ent[ei];
-                            if (en < ci.entries) acc[h] = NVB_FADD(acc[h], tab[en]); else bad_entry = 1;
-                        }
-                    }
-                }
-            }
-        }
-        for (int i = n_coupling - 1; i >= 0; --i) {                         // Mapping.cs:137-182
-            const int m = mp.mag[i], an = mp.ang[i];
-            if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
-            if (CT == 2) {                                                  // (magnitude, angle) is (0, 1) or (1, 0)
-                #pragma unroll
-                for (int b = 0; b < RB; b++) { if (m == 0) inverse_couple_sel(acc[2 * b], acc[2 * b + 1]); else inverse_couple_sel(acc[2 * b + 1], acc[2 * b]); }
-            } else {
-                #pragma unroll
-                for (int b = 0; b < RB; b++) {
-                    float vm = 0.f, va = 0.f;
-                    #pragma unroll
-                    for (int k = 0; k < CT; k++) { if (k == m) vm = acc[b * CT + k]; if (k == an) va = acc[b * CT + k]; }
-                    inverse_couple_sel(vm, va);
-                    #pragma unroll
-                    for (int k = 0; k < CT; k++) { if (k == m) acc[b * CT + k] = vm; if (k == an) acc[b * CT + k] = va; }
-                }
-            }
-        }
-        const unsigned kk0 = bin2k[bin0];                                   // sorted position of the last post at or below the run's first bin
-        #pragma unroll
-        for (int c = 0; c < CT; c++) {
-            if ((f.exec_mask >> c) & 1u) {                                  // Floor1.Apply, Floor1.cs:186-222
-                const mask_t M = fmask[c];
-                const WfSeg* segc = s_seg + c * np;
-                if (M == 0) {
-                    #pragma unroll
-                    for (int b = 0; b < RB; b++) acc[b * CT + c] = 0.f;
-                } else if (!careful[c]) {
-                    // the segment of the first bin: last active position at or below its post (bit 0 is set)
-                    int cur = P64 ? 63 - __clzll((long long)(M & (mask_t)(0xffffffffffffffffull >> (63 - kk0)))) : 31 - __clz((int)((unsigned)M & (0xffffffffu >> (31 - kk0))));
-                    WfSeg r = segc[cur];
-                    int x1 = (int)(r.x01 >> 16);
-                    unsigned ady = (unsigned)(r.dy < 0 ? -r.dy : r.dy);
-                    int sgn4 = r.dy < 0 ? -4 : 4;
-                    unsigned tt = (unsigned)(bin0 - (int)(r.x01 & 0xffffu)) * ady;
-                    const char* base = dbp + 4 * r.y0;
-                    #pragma unroll
-                    for (int b = 0; b < RB; b++) {
-                        if (b > 0 && bin0 + b == x1) {                      // the bin reaches the next active post: its segment starts here
-                            const mask_t above = M & ~((((mask_t)1 << cur) << 1) - 1);
-                            cur = P64 ? __ffsll((long long)above) - 1 : __ffs((int)above) - 1;
-                            r = segc[cur];
-                            x1 = (int)(r.x01 >> 16); ady = (unsigned)(r.dy < 0 ? -r.dy : r.dy); sgn4 = r.dy < 0 ? -4 : 4;
-                            tt = 0u; base = dbp + 4 * r.y0;
-                        }
-                        const int qq = (int)__umulhi(tt, r.m);
-                        acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], *reinterpret_cast<const float*>(base + qq * sgn4));
-                        tt += ady;
-                    }
-                } else {
-                    #pragma unroll
-                    for (int b = 0; b < RB; b++) {
-                        const unsigned kk = bin2k[bin0 + b];
-                        const int lo = P64 ? 63 - __clzll((long long)(M & (mask_t)(0xffffffffffffffffull >> (63 - kk)))) : 31 - __clz((int)((unsigned)M & (0xffffffffu >> (31 - kk))));
-                        const WfSeg r = segc[lo];
-                        const int x0 = (int)(r.x01 & 0xffffu), adx = (int)(r.x01 >> 16) - x0;
-                        const int num = (bin0 + b - x0) * (r.dy < 0 ? -r.dy : r.dy);
-                        const int qq = r.m != 0u ? (int)__umulhi((unsigned)num, r.m) : num / adx;
-                        int y = r.dy < 0 ? r.y0 - qq : r.y0 + qq;
-                        if ((unsigned)y > 255u) { bad_floor = 1; y = y < 0 ? 0 : 255; }
-                        acc[b * CT + c] = NVB_FMUL(acc[b * CT + c], s_db[y]);
-                    }
-                }
-            }
-            float* dst = spec_out + (size_t)c * n + bin0;
-            if (RB == 8) {
-                *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            } else if (RB == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[c], acc[CT + c], acc[2 * CT + c], acc[3 * CT + c]);
-            else if (RB == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[c], acc[CT + c]);
-            else *dst = acc[c];
-        }
-    }
+    if (plain) {
+        if (cm == 1) wf_main<CT, GT, P64, true, CT == 2 ? 1 : 3>(a, x, gt, bad_entry, bad_floor);
+        else if (cm == 0) wf_main<CT, GT, P64, true, 0>(a, x, gt, bad_entry, bad_floor);
+        else if (cm == 2) wf_main<CT, GT, P64, true, CT == 2 ? 2 : 3>(a, x, gt, bad_entry, bad_floor);
+        else wf_main<CT, GT, P64, true, 3>(a, x, gt, bad_entry, bad_floor);
+    } else wf_main<CT, GT, P64, false, 3>(a, x, gt, bad_entry, bad_floor);
     // rare: count the frame once per kind (the first thread of the frame's group to raise a flag reports it)
     if (bad_entry && atomicOr(&s_bad[2 * group], 1) == 0) atomicAdd(&a.counters->bad_entry, 1);
     if (bad_floor && atomicOr(&s_bad[2 * group + 1], 1) == 0) atomicAdd(&a.counters->floor_range, 1);
@@ -1870,6 +1942,35 @@ __global__ void __launch_bounds__(OLA_THREADS) k_ola(LaunchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// NVB_RUN_PCM_S16: float PCM -> 16-bit PCM, s = rni(v * 32768) saturated (cvt.rni.sat.s16.f32), elements [lo, hi) of the
+// interleaved buffers.  Memory-bound (6 bytes per sample); halves what crosses PCIe afterwards.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ short pcm_s16(float v) {
+#if !defined(NVB_CPU_SHIM)
+    short r; asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(r) : "f"(v * 32768.0f)); return r;
+#else
+    const float x = std::nearbyintf(v * 32768.0f);                          // round to nearest even (default rounding mode)
+    return (short)(x > 32767.f ? 32767.f : x < -32768.f ? -32768.f : x);
+#endif
+}
+__global__ void __launch_bounds__(256) k_pcm_s16(const float* __restrict__ src, short* __restrict__ dst, long long lo, long long hi) {
+    nvb_grid_dep_launch();
+    nvb_grid_dep_wait();
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+    // groups of four elements whose float4 / 8-byte short4 are both aligned (the buffers are 16- / 8-byte aligned); ragged ends one by one
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+    long long a0 = vec ? ((lo + 3) & ~3ll) : hi, a1 = vec ? (hi & ~3ll) : hi;
+    if (a0 > a1) { a0 = hi; a1 = hi; }
+    for (long long i = lo + tid; i < (a0 < hi ? a0 : hi); i += nt) dst[i] = pcm_s16(src[i]);
+    for (long long g = (a0 >> 2) + tid; g < (a1 >> 2); g += nt) {
+        const float4 v = reinterpret_cast<const float4*>(src)[g];
+        short4 o; o.x = pcm_s16(v.x); o.y = pcm_s16(v.y); o.z = pcm_s16(v.z); o.w = pcm_s16(v.w);
+        reinterpret_cast<short4*>(dst)[g] = o;
+    }
+    for (long long i = (a1 > a0 ? a1 : hi) + tid; i < hi; i += nt) dst[i] = pcm_s16(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 
@@ -1945,7 +2046,7 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
     if (a.S.spectrum_fast >= 3 && !no_planes && !force_planes && !force_run) {
         const int C = a.S.channels;
         const int wpf_env = std::getenv("NVB_WF_WPF") ? std::atoi(std::getenv("NVB_WF_WPF")) : 0;   // experiment hook: warps per frame
-        const int WPF = (wpf_env == 1 || wpf_env == 2 || wpf_env == 4) ? wpf_env : 2;
+        const int WPF = (wpf_env == 1 || wpf_env == 2 || wpf_env == 4) ? wpf_env : 1;
         const WfLayout L = wf_layout(a.S, C, WPF);
         const int fpc = WF_WARPS / WPF;
         const size_t smem = (size_t)L.total * fpc;
@@ -1958,7 +2059,7 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
                     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
                     conf = smem;
                 }
-                NVB_LAUNCH2(kernel, (a.n_frames + fpc - 1) / fpc, WF_WARPS * 32, smem, stream, a, L);
+                NVB_LAUNCHV(kernel, (a.n_frames + fpc - 1) / fpc, WF_WARPS * 32, smem, stream, a, L);
                 return cudaGetLastError() == cudaSuccess ? 1 : -1;
             };
 #define NVB_WF_CASE(CT_)                                                                                          \
@@ -2044,6 +2145,16 @@ int launch_imdct_exact(const LaunchArgs& a, void* stream) {
         configured = smem;
     }
     NVB_LAUNCH(k_imdct_exact, a.n_frames * a.S.channels, MDCT_THREADS, smem, stream, a);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_pcm_s16(const float* src, int16_t* dst, long long lo, long long hi, void* stream) {
+    if (hi <= lo) return 0;
+    const long long groups = (hi - lo + 3) / 4;
+    long long blocks = (groups + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    NVB_LAUNCHV(k_pcm_s16, blocks, 256, 0, stream, src, reinterpret_cast<short*>(dst), lo, hi);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -35,6 +35,7 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(4) uchar4 { unsigned char x, y, z, w; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) short4 { short x, y, z, w; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
@@ -188,6 +189,10 @@ static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, s
     for (size_t r = 0; r < h; r++) std::memcpy((char*)d + r * dp, (const char*)s + r * sp, w);
     return cudaSuccess;
 }
+// every pointer of the emulation is "device memory on device 0"
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; };
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeDevice; a->device = 0; return cudaSuccess; }
 typedef void* cudaEvent_t;
 enum { cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, int) { *e = nullptr; return cudaSuccess; }
@@ -206,8 +211,8 @@ void run(int grid, int block, size_t smem, const std::function<void()>& body);
 template <class K, class A> void launch(K kernel, int grid, int block, size_t smem, A arg) { run(grid, block, smem, [=]() { kernel(arg); }); }
 }
 #define NVB_LAUNCH(kernel, grid, block, smem, stream, arg) cuemu::launch(kernel, (int)(grid), (int)(block), (size_t)(smem), arg)
-namespace cuemu { template <class K, class A, class B> void launch2(K kernel, int grid, int block, size_t smem, A a0, B a1) { run(grid, block, smem, [=]() { kernel(a0, a1); }); } }
-#define NVB_LAUNCH2(kernel, grid, block, smem, stream, arg0, arg1) cuemu::launch2(kernel, (int)(grid), (int)(block), (size_t)(smem), arg0, arg1)
+namespace cuemu { template <class K, class... A> void launchv(K kernel, int grid, int block, size_t smem, A... args) { run(grid, block, smem, [=]() { kernel(args...); }); } }
+#define NVB_LAUNCHV(kernel, grid, block, smem, stream, ...) cuemu::launchv(kernel, (int)(grid), (int)(block), (size_t)(smem), __VA_ARGS__)
 #define NVB_DYN_SMEM(name) unsigned char* name = cuemu::g_dyn_smem
 #define nvb_grid_dep_wait() ((void)0)
 #define nvb_grid_dep_launch() ((void)0)

@@ -297,3 +297,33 @@ def _edge_batches(lib_path):
 
 def test_empty_failed_and_single_packet_batches(shim):
     _edge_batches(shim)
+
+
+def _s16(x):
+    """The 16-bit form NVB_RUN_PCM_S16 defines: round-to-nearest-even(v * 32768), saturated."""
+    return np.clip(np.rint(x.astype(np.float32) * np.float32(32768.0)), -32768, 32767).astype(np.int16)
+
+
+def test_pcm_s16_and_device_out(shim):
+    """NVB_RUN_PCM_S16: the exact path quantised on the device equals the oracle's PCM quantised by the same rule, bit for bit
+    (ragged chunk boundaries included); NVB_RUN_DEVICE_OUT leaves the PCM in the caller's (here: emulated) device buffer."""
+    r, pcm, b, ctx = _ctx(shim, "3test")
+    lo, hi = 0, 48
+    want, _ = H.oracle_synth(r, b, lo, hi)
+    hb = H.batch_from_boundary(b, ctx.post_stride, lo, hi)
+    out, res = ctx.decode_batch(hb, capi.RUN_EXACT | capi.RUN_PCM_S16)
+    assert out.dtype == np.int16 and res.samples_per_channel * 2 == want.size
+    np.testing.assert_array_equal(out, _s16(want))
+    ctx.reset()
+    out, _ = ctx.decode_batch(hb, capi.RUN_DEFAULT | capi.RUN_PCM_S16)
+    assert np.abs(out.astype(np.int32) - _s16(want).astype(np.int32)).max() <= 1      # fused path: within 1e-5 of the oracle => at most one step apart
+    ctx.reset()
+    dev = np.full(want.size + 64, 7.0, np.float32)                  # the emulation's "device memory"
+    res = ctx.decode_batch_ptr(hb, capi.RUN_EXACT | capi.RUN_DEVICE_OUT, dev.ctypes.data, dev.size)
+    np.testing.assert_array_equal(dev[: want.size], want)
+    assert (dev[want.size:] == 7.0).all()
+    ctx.reset()
+    dev16 = np.full(want.size + 64, 7, np.int16)
+    ctx.decode_batch_ptr(hb, capi.RUN_EXACT | capi.RUN_DEVICE_OUT | capi.RUN_PCM_S16, dev16.ctypes.data, dev16.size)
+    np.testing.assert_array_equal(dev16[: want.size], _s16(want))
+    assert (dev16[want.size:] == 7).all()

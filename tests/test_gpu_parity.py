@@ -224,9 +224,63 @@ def test_generic_spectrum_kernel_on_gpu():
             "    r, pcm, b = H.decoded(name)\n    ctx = capi.Context(0); ctx.upload_setup(H.setup_from_oracle(r))\n"
             "    out, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride), capi.RUN_EXACT)\n"
             "    assert np.array_equal(out, pcm)\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"))
-    for var in ("NVB_SPECTRUM_GENERIC", "NVB_SPECTRUM_NO_PLANES", "NVB_SPECTRUM_WARP", "NVB_SPECTRUM_PLANES", "NVB_SPECTRUM_NT"):          # the general kernel / the per-bin fast kernel
-        env = dict(os.environ); env[var] = "256" if var == "NVB_SPECTRUM_NT" else "1"
+    # the general kernel / the per-bin fast kernel / planes / the run kernel / k_spectrum_wf with 1, 2 and 4 warps per frame
+    for var, val in (("NVB_SPECTRUM_GENERIC", "1"), ("NVB_SPECTRUM_NO_PLANES", "1"), ("NVB_SPECTRUM_WARP", "1"), ("NVB_SPECTRUM_PLANES", "1"), ("NVB_SPECTRUM_RUN", "1"),
+                     ("NVB_SPECTRUM_NT", "256"), ("NVB_WF_WPF", "1"), ("NVB_WF_WPF", "2"), ("NVB_WF_WPF", "4")):
+        env = dict(os.environ); env[var] = val
+        if var == "NVB_SPECTRUM_NT":
+            env["NVB_SPECTRUM_RUN"] = "1"
         assert subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().endswith("ok")
+
+
+def _s16(x):
+    """The 16-bit form NVB_RUN_PCM_S16 defines: round-to-nearest-even(v * 32768), saturated."""
+    return np.clip(np.rint(x.astype(np.float32) * np.float32(32768.0)), -32768, 32767).astype(np.int16)
+
+
+def test_pcm_s16_epilogue_and_device_output():
+    """NVB_RUN_PCM_S16 (16-bit PCM, half the read-back): the exact path equals the oracle's PCM quantised by the same rule bit for
+    bit -- 3test clips, so saturation is exercised --, the fused path is at most one step away; through the chunked pipeline at
+    configs[1] size too.  NVB_RUN_DEVICE_OUT leaves float / 16-bit PCM in a device buffer of the caller."""
+    import torch
+    r, pcm, b, ctx = _ctx("3test")
+    hb = H.batch_from_boundary(b, ctx.post_stride)
+    out, res = ctx.decode_batch(hb, capi.RUN_EXACT | capi.RUN_PCM_S16)
+    np.testing.assert_array_equal(out, _s16(pcm))
+    assert res.has_clipped and out.max() == 32767 and out.min() == -32768
+    ctx.reset()
+    out, _ = ctx.decode_batch(hb, capi.RUN_PCM_S16)
+    assert np.abs(out.astype(np.int32) - _s16(pcm).astype(np.int32)).max() <= 1
+    ctx.reset()
+    d = torch.full((pcm.size + 32,), 5.0, dtype=torch.float32, device="cuda")
+    res = ctx.decode_batch_ptr(hb, capi.RUN_EXACT | capi.RUN_DEVICE_OUT, d.data_ptr(), d.numel())
+    got = d.cpu().numpy()
+    np.testing.assert_array_equal(got[: pcm.size], pcm)
+    assert (got[pcm.size:] == 5.0).all() and res.samples_per_channel * 2 == pcm.size
+    ctx.reset()
+    d16 = torch.full((pcm.size + 32,), 5, dtype=torch.int16, device="cuda")
+    ctx.decode_batch_ptr(hb, capi.RUN_EXACT | capi.RUN_DEVICE_OUT | capi.RUN_PCM_S16, d16.data_ptr(), d16.numel())
+    got = d16.cpu().numpy()
+    np.testing.assert_array_equal(got[: pcm.size], _s16(pcm))
+    assert (got[pcm.size:] == 5).all()
+    with pytest.raises(capi.NvbError) as e:                      # a host pointer is refused, not written through
+        ctx.decode_batch_ptr(hb, capi.RUN_DEVICE_OUT, np.zeros(pcm.size, np.float32).ctypes.data, pcm.size)
+    assert e.value.status == capi.ERR_ARG
+    ctx.close()
+    # configs[1] size: four chunks, two batches in flight
+    desc, pool = _pool()
+    hb = workloads.config2(pool, 4096, 20240002)
+    want, _ = _oracle_on_batch(hb)
+    ctx = capi.Context(0); ctx.upload_setup(setupio.to_setup(desc))
+    outs = [np.zeros(want.size, np.int16), np.zeros(want.size, np.int16)]
+    for i in range(3):
+        ctx.decode_batch_begin(hb, capi.RUN_EXACT | capi.RUN_PCM_S16, outs[i & 1].ctypes.data, outs[i & 1].size)
+        if i >= 1:
+            ctx.decode_batch_end()
+    ctx.decode_batch_end()
+    np.testing.assert_array_equal(outs[0], _s16(want))
+    np.testing.assert_array_equal(outs[1], _s16(want))
+    ctx.close()
 
 
 def test_smoke_entry():
