@@ -43,7 +43,7 @@ namespace nvb {
 constexpr int FUSED_WARPS = NVB_FUSED_WARPS;
 constexpr int FUSED_CTAS_PER_SM = FUSED_WARPS <= 8 ? 2 : 1;      // 8-warp build: two half-size CTAs share an SM
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
-constexpr size_t FUSED_SMEM_LIMIT = (FUSED_WARPS <= 8 ? 112 : 227) * 1024;
+constexpr size_t FUSED_SMEM_LIMIT = (FUSED_WARPS <= 8 ? 112 : 227) * 1024 - FUSED_WARPS * 64;   // minus the static per-warp plan records
 
 struct FusedParams {
     LaunchArgs a;
@@ -95,6 +95,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS): no register, no scoreboard; completion via cp_async_wait_all.
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // Orders earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
@@ -172,6 +177,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
     float* s_tab = reinterpret_cast<float*>(smem_raw);
     float* s_slots = s_tab + FusedTables::FLOATS;
     DevFrame* s_fr = reinterpret_cast<DevFrame*>(s_slots + (size_t)NS * G * FUSED_SLOT_FLOATS);
+    __shared__ DevFrame s_pre[FUSED_WARPS];                   // per warp: the plan record of its next unit, requested one unit ahead (cp.async)
     int* s_full = reinterpret_cast<int*>(s_fr + NS);                        // s_full[s]: frames completed in slot s
     int* s_empty = s_full + NS;                                             // s_empty[s]: reader releases of slot s (two per frame)
     uint64_t* s_tabbar = reinterpret_cast<uint64_t*>(s_empty + NS);          // 8 NS bytes past s_full: 8-byte aligned
@@ -200,6 +206,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
     }
     // the first transform's rows are requested before the lane tables have landed: both latencies overlap
     const int vfirst = first * U, vhi = hi * U;                             // unit indices (== frame indices when not grouped)
+    // The plan record of a warp's NEXT unit is requested one unit ahead with cp.async (no register, no scoreboard) into the
+    // warp's staging record: the dependent global load of the record used to stall the start of every unit.
+    if (vfirst + warp < vhi && lane < 4) {
+        const int v0 = vfirst + warp, x0 = GROUPED ? v0 / U : v0;
+        cp_async_16(reinterpret_cast<char*>(&s_pre[warp]) + 16 * lane, reinterpret_cast<const char*>(a.frames + x0) + 16 * lane);
+    }
     LongIn pre; int pre_x = -1, pre_c = -1;
 #if !defined(NVB_FUSED_NO_PREFETCH)
     if (vfirst + warp < vhi) {
@@ -236,15 +248,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
         const int x = GROUPED ? v / U : v;                                   // frame and first channel of this unit
         const int cbase = GROUPED ? (v - x * U) * 2 : 0;
         cnt_wait(&s_empty[slot], 2 * it);                                    // both readers of every earlier frame of the slot are done
-        if (lane == 0) s_fr[slot] = a.frames[x];
+        cp_async_wait_all();                                                 // this unit's plan record (requested one unit ago) has landed
+        __syncwarp();
+        if (lane < 4) reinterpret_cast<int4*>(&s_fr[slot])[lane] = reinterpret_cast<const int4*>(&s_pre[warp])[lane];
         __syncwarp();
         const DevFrame f = s_fr[slot];
-        const int vn = v + FUSED_WARPS;                                      // the warp's next unit (for the prefetch)
-        int n_kind = 1, n_n = 0; uint32_t n_exec = 0, n_spec = 0;
-        if (vn < vhi) {
-            const int xn = GROUPED ? vn / U : vn, cn = GROUPED ? (vn - xn * U) * 2 : 0;
-            const DevFrame* fn = a.frames + xn; n_kind = fn->kind; n_n = fn->n; n_exec = fn->exec_mask >> cn; n_spec = fn->spec_off + (uint32_t)cn * (uint32_t)(fn->n >> 1);
-        }
+        const int vn = v + FUSED_WARPS;                                      // the warp's next unit: its record is requested now, read after phase 1
+        const int xn = GROUPED ? vn / U : vn, cn = GROUPED ? (vn - xn * U) * 2 : 0;
+        if (vn < vhi && lane < 4) cp_async_16(reinterpret_cast<char*>(&s_pre[warp]) + 16 * lane, reinterpret_cast<const char*>(a.frames + xn) + 16 * lane);
+        int n_kind = 1, n_n = 0; uint32_t n_exec = 0, n_spec = 0; bool n_known = false;
         float* slots_f = s_slots + (size_t)slot * G * FUSED_SLOT_FLOATS;
 
         // ---------------- transform: every channel of frame x -------------------------------------
@@ -262,8 +274,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
                     long_phase1_compute(lane, pre, s_tab, ex);
                     if (c + 1 < G && can_prefetch(0, f.n, f.exec_mask >> cbase, c + 1)) {
                         long_phase1_load(lane, reinterpret_cast<const float2*>(spec + M), pre); pre_x = v; pre_c = c + 1;
-                    } else if (c + 1 == G && can_prefetch(n_kind, n_n, n_exec, 0)) {
-                        long_phase1_load(lane, reinterpret_cast<const float2*>(a.spectrum + (size_t)n_spec), pre); pre_x = vn; pre_c = 0;
+                    } else if (c + 1 == G && vn < vhi) {
+                        if (!n_known) {                                      // the next unit's record: long since landed
+                            cp_async_wait_all(); __syncwarp();
+                            const DevFrame* fn = &s_pre[warp];
+                            n_kind = fn->kind; n_n = fn->n; n_exec = fn->exec_mask >> cn; n_spec = fn->spec_off + (uint32_t)cn * (uint32_t)(fn->n >> 1); n_known = true;
+                        }
+                        if (can_prefetch(n_kind, n_n, n_exec, 0)) { long_phase1_load(lane, reinterpret_cast<const float2*>(a.spectrum + (size_t)n_spec), pre); pre_x = vn; pre_c = 0; }
                     }
                     __syncwarp();
                     long_phase2_load(lane, ex, R);

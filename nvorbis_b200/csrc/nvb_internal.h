@@ -155,7 +155,7 @@ struct DevSetup {
 
 // ---- per-frame plan built on the host from nvb_frame (ok frames only, in order) ----------------
 enum { PREV_NONE = -1, PREV_CARRY = -2 };
-struct DevFrame {
+struct alignas(16) DevFrame {
     uint8_t  mode, window, res_decoded, kind;   // kind 0 = decoded block; 1 = drain: emit [out_begin,out_end) of block `prev` as it is
     uint32_t exec_mask;
     int32_t  n;                 // block size

@@ -1077,108 +1077,131 @@ __device__ __forceinline__ unsigned wf_reduce_or(unsigned v) { return __reduce_o
 static inline unsigned wf_reduce_or(unsigned v) { for (int d = 16; d >= 1; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d); return v; }
 #endif
 
-// UnwrapPosts (Floor1.cs:224-297) by one warp, lane = post (and post + 32 when H == 2), the posts of one dependency level in
-// parallel; RenderPoint's `err / adx` (Floor1.cs:299-314) is a multiply-high by the setup constant F.magic[i] -- exact for
-// err < 2^20 (adx <= 4096), anything larger (only malformed posts get there) takes the division.  Leaves finalY in fy[].
-template <int H>
-__device__ __forceinline__ unsigned long long floor1_unwrap_mh(const DevFloor1& F, const int16_t* posts, int lane, int* fy, int& count) {
-    count = posts[0];
-    if (count > F.n_posts) count = F.n_posts;
-    if (count < 2) return 0ull;                                           // PostCount == 0: the spectrum is cleared (Floor1.cs:220)
-    int val[H], p_lo[H], p_hi[H], p_x0[H], p_dx[H], p_lvl[H]; unsigned p_m[H];
+// UnwrapPosts (Floor1.cs:224-297) by one warp for NC channels of one frame at once (they share the floor, so the per-post
+// constants are loaded once and the channels' dependency chains interleave): lane = post (and post + 32 when H == 2), the posts
+// of one dependency level in parallel; RenderPoint's `err / adx` (Floor1.cs:299-314) is a multiply-high by the setup constant
+// F.magic[i] -- exact for err < 2^20 (adx <= 4096), anything larger (only malformed posts get there) takes the division.
+// Leaves finalY of channel j in fy[j][]; flags[j] = step flags (0 when PostCount < 2: the spectrum is cleared, Floor1.cs:220).
+template <int H, int NC>
+__device__ __forceinline__ void floor1_unwrap_mh(const DevFloor1& F, const int16_t* const* posts, int lane, int* const* fy, int* count, unsigned long long* flags) {
+    int p_lo[H], p_hi[H], p_x0[H], p_dx[H], p_lvl[H]; unsigned p_m[H];
+    const int n_posts = F.n_posts;
     #pragma unroll
     for (int h = 0; h < H; h++) {
         const int i = lane + 32 * h;
-        val[h] = i < count ? posts[1 + i] : 0;
         p_lvl[h] = 0; p_lo[h] = 0; p_hi[h] = 0; p_x0[h] = 0; p_dx[h] = 0; p_m[h] = 0u;
-        if (i >= 2 && i < count) {
+        if (i >= 2 && i < n_posts) {
             p_lo[h] = F.lo[i]; p_hi[h] = F.hi[i]; p_x0[h] = F.x[p_lo[h]]; p_dx[h] = F.x[i] - p_x0[h];
             p_m[h] = F.magic[i]; p_lvl[h] = F.level[i];
         }
     }
-    if (lane < 2) fy[lane] = val[0];
+    int val[NC][H]; unsigned clo[NC], chi[NC];
+    #pragma unroll
+    for (int j = 0; j < NC; j++) {
+        int c = posts[j][0];
+        if (c > n_posts) c = n_posts;
+        if (c < 2) c = 0;
+        count[j] = c; clo[j] = 0u; chi[j] = 0u;
+        #pragma unroll
+        for (int h = 0; h < H; h++) { const int i = lane + 32 * h; val[j][h] = i < c ? posts[j][1 + i] : 0; }
+        if (lane < 2) fy[j][lane] = val[j][0];
+    }
     __syncwarp();
-    unsigned clo = 0u, chi = 0u;                                          // step-flag contributions of this lane's posts
     const int range = F.range, max_level = F.max_level;
     for (int lvl = 1; lvl <= max_level; lvl++) {
         #pragma unroll
         for (int h = 0; h < H; h++) {
             if (p_lvl[h] == lvl) {
                 const int i = lane + 32 * h;
-                const int y0 = fy[p_lo[h]];
-                const int dy = fy[p_hi[h]] - y0, ady = dy < 0 ? -dy : dy;
-                const int err = ady * p_dx[h];
-                const int off = (unsigned)err < (1u << 20) ? (int)__umulhi((unsigned)err, p_m[h]) : err / ((int)F.x[p_hi[h]] - p_x0[h]);
-                const int predicted = dy < 0 ? y0 - off : y0 + off;
-                const int v = val[h];
-                const int highroom = range - predicted, lowroom = predicted;
-                const int room = (highroom < lowroom ? highroom : lowroom) * 2;
-                int out = predicted;
-                if (v != 0) {
-                    if (H == 1) clo |= (1u << p_lo[h]) | (1u << p_hi[h]) | (1u << i);
-                    else {
-                        const unsigned long long b = (1ull << p_lo[h]) | (1ull << p_hi[h]) | (1ull << i);
-                        clo |= (unsigned)b; chi |= (unsigned)(b >> 32);
+                #pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    if (i < count[j]) {
+                        const int y0 = fy[j][p_lo[h]];
+                        const int dy = fy[j][p_hi[h]] - y0, ady = dy < 0 ? -dy : dy;
+                        const int err = ady * p_dx[h];
+                        const int off = (unsigned)err < (1u << 20) ? (int)__umulhi((unsigned)err, p_m[h]) : err / ((int)F.x[p_hi[h]] - p_x0[h]);
+                        const int predicted = dy < 0 ? y0 - off : y0 + off;
+                        const int v = val[j][h];
+                        const int highroom = range - predicted, lowroom = predicted;
+                        const int room = (highroom < lowroom ? highroom : lowroom) * 2;
+                        int out = predicted;
+                        if (v != 0) {
+                            if (H == 1) clo[j] |= (1u << p_lo[h]) | (1u << p_hi[h]) | (1u << i);
+                            else {
+                                const unsigned long long b = (1ull << p_lo[h]) | (1ull << p_hi[h]) | (1ull << i);
+                                clo[j] |= (unsigned)b; chi[j] |= (unsigned)(b >> 32);
+                            }
+                            if (v >= room) out = highroom > lowroom ? v - lowroom + predicted : predicted - v + highroom - 1;
+                            else out = (v & 1) ? predicted - ((v + 1) >> 1) : predicted + (v >> 1);       // v > 0 here: (v % 2) == 1 <=> v & 1
+                        }
+                        fy[j][i] = out;
                     }
-                    if (v >= room) out = highroom > lowroom ? v - lowroom + predicted : predicted - v + highroom - 1;
-                    else out = (v & 1) ? predicted - ((v + 1) >> 1) : predicted + (v >> 1);       // v > 0 here: (v % 2) == 1 <=> v & 1
                 }
-                fy[i] = out;
             }
         }
         __syncwarp();
     }
     // stepFlags: 0 and 1 always; i when its own value is non-zero or a later post names it as a neighbour (Floor1.cs:253-257,292)
-    clo = wf_reduce_or(clo);
-    if (H == 2) chi = wf_reduce_or(chi);
-    return (((unsigned long long)chi << 32) | clo) | 3ull;
+    #pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const unsigned lo = wf_reduce_or(clo[j]);
+        const unsigned hi = H == 2 ? wf_reduce_or(chi[j]) : 0u;
+        flags[j] = count[j] >= 2 ? ((((unsigned long long)hi << 32) | lo) | 3ull) : 0ull;
+    }
 }
 
-// Floor 1 of one channel by one warp: unwrap, active-post mask of the x-sorted walk (bit k: sorted position k starts a
+// Floor 1 of NC channels of a frame by one warp: unwrap, active-post mask of the x-sorted walk (bit k: sorted position k starts a
 // segment; 0 = no curve, Floor1.cs:220) and one WfSeg per active position.  careful: some segment needs the plain division or
-// leaves inverse_dB_table's range.
-template <int H>
-__device__ __forceinline__ void floor1_wf_segments(const DevFloor1& F, const uint32_t* magic, const int16_t* posts, int n, int lane, int* fy, int* ys, WfSeg* seg,
-                                                   unsigned long long& mask, int& careful_any) {
-    mask = 0ull; careful_any = 0;
-    int count;
-    const unsigned long long flags = floor1_unwrap_mh<H>(F, posts, lane, fy, count);
-    if (count < 2) return;
-    unsigned m[2] = {0u, 0u};
+// leaves inverse_dB_table's range.  fy[j] / ys[j]: 64 ints of scratch each; seg[j]: the channel's segment records.
+template <int H, int NC>
+__device__ __forceinline__ void floor1_wf_segments(const DevFloor1& F, const uint32_t* magic, const int16_t* const* posts, int n, int lane, int* const* fy, int* const* ys,
+                                                   WfSeg* const* seg, unsigned long long* mask, int* careful_any) {
+    int count[NC]; unsigned long long flags[NC];
+    floor1_unwrap_mh<H, NC>(F, posts, lane, fy, count, flags);
     const int mult = F.mult;
+    int xs_k[H], idx_k[H];
     #pragma unroll
-    for (int h = 0; h < H; h++) {
-        const int k = lane + 32 * h;
-        bool act = false;
-        if (k < count) { const int idx = F.sort[k]; act = idx < count && ((flags >> idx) & 1ull); ys[k] = fy[idx < count ? idx : 0] * mult; }
-        m[h] = __ballot_sync(0xffffffffu, act);
-    }
-    mask = (((unsigned long long)m[1] << 32) | m[0]) | 1ull;
-    __syncwarp();
-    bool careful = false;
+    for (int h = 0; h < H; h++) { const int k = lane + 32 * h; xs_k[h] = 0; idx_k[h] = 0; if (k < F.n_posts) { xs_k[h] = F.xs[k]; idx_k[h] = F.sort[k]; } }
     #pragma unroll
-    for (int h = 0; h < H; h++) {
-        const int k = lane + 32 * h;
-        if ((mask >> k) & 1ull) {
-            WfSeg r; const int x0 = F.xs[k]; r.y0 = ys[k]; r.dy = 0; r.m = 1u;
-            int x1 = 0xffff;                                                // the flat tail, Floor1.cs:213-216
-            const unsigned long long above = mask & ~(((1ull << k) << 1) - 1ull);
-            if (above) {
-                const int hi = __ffsll((long long)above) - 1;
-                const int hx = F.xs[hi];
-                x1 = hx < n ? hx : n;                                       // x clamped, y NOT re-interpolated (Floor1.cs:206)
-                const int adx = x1 - x0;
-                r.dy = ys[hi] - r.y0;
-                const unsigned ady = (unsigned)(r.dy < 0 ? -r.dy : r.dy);
-                if (adx >= 2) { const unsigned mm = magic[2 * adx], lim = magic[2 * adx + 1]; r.m = ady <= lim ? mm : 0u; }
-            }
-            r.x01 = (unsigned)x0 | ((unsigned)x1 << 16);
-            seg[k] = r;
-            // y runs monotonically from y0 to y0 + dy: in range at both ends <=> in range everywhere
-            if (x0 < n && (r.m == 0u || (unsigned)r.y0 > 255u || (unsigned)(r.y0 + r.dy) > 255u)) careful = true;
+    for (int j = 0; j < NC; j++) {
+        unsigned m[2] = {0u, 0u};
+        #pragma unroll
+        for (int h = 0; h < H; h++) {
+            const int k = lane + 32 * h;
+            bool act = false;
+            if (k < count[j]) { const int idx = idx_k[h]; act = idx < count[j] && ((flags[j] >> idx) & 1ull); ys[j][k] = fy[j][idx < count[j] ? idx : 0] * mult; }
+            m[h] = __ballot_sync(0xffffffffu, act);
         }
+        mask[j] = count[j] >= 2 ? ((((unsigned long long)m[1] << 32) | m[0]) | 1ull) : 0ull;
     }
-    careful_any = __any_sync(0xffffffffu, careful);
+    __syncwarp();
+    #pragma unroll
+    for (int j = 0; j < NC; j++) {
+        bool careful = false;
+        #pragma unroll
+        for (int h = 0; h < H; h++) {
+            const int k = lane + 32 * h;
+            if ((mask[j] >> k) & 1ull) {
+                WfSeg r; const int x0 = xs_k[h]; r.y0 = ys[j][k]; r.dy = 0; r.m = 1u;
+                int x1 = 0xffff;                                            // the flat tail, Floor1.cs:213-216
+                const unsigned long long above = mask[j] & ~(((1ull << k) << 1) - 1ull);
+                if (above) {
+                    const int hi = __ffsll((long long)above) - 1;
+                    const int hx = F.xs[hi];
+                    x1 = hx < n ? hx : n;                                   // x clamped, y NOT re-interpolated (Floor1.cs:206)
+                    const int adx = x1 - x0;
+                    r.dy = ys[j][hi] - r.y0;
+                    const unsigned ady = (unsigned)(r.dy < 0 ? -r.dy : r.dy);
+                    if (adx >= 2) { const uint2 mg = *reinterpret_cast<const uint2*>(magic + 2 * adx); r.m = ady <= mg.y ? mg.x : 0u; }
+                }
+                r.x01 = (unsigned)x0 | ((unsigned)x1 << 16);
+                seg[j][k] = r;
+                // y runs monotonically from y0 to y0 + dy: in range at both ends <=> in range everywhere
+                if (x0 < n && (r.m == 0u || (unsigned)r.y0 > 255u || (unsigned)(r.y0 + r.dy) > 255u)) careful = true;
+            }
+        }
+        careful_any[j] = __any_sync(0xffffffffu, careful);
+    }
 }
 
 // Entry-stream offsets of every (partition, stage) of the frame by one warp: base[p * ST + st], plus cls[p] = class | coded
@@ -1443,8 +1466,8 @@ __global__ void __launch_bounds__(WF_WARPS * 32, 8) k_spectrum_wf(LaunchArgs a, 
 
     unsigned char* gsm = dyn_smem + (size_t)group * L.total;
     WfSeg* s_seg = reinterpret_cast<WfSeg*>(gsm + L.seg_off);               // [CT][np_pad]
-    int* s_fy = reinterpret_cast<int*>(gsm + L.fy_off) + wg * 128;          // per warp: finalY[64], finalY * multiplier in x order [64]
-    int* s_flags = reinterpret_cast<int*>(gsm + L.fy_off) + WPF * 128;      // [CT][4]: mask lo, mask hi, careful (groups of more than one warp)
+    int* s_fy = reinterpret_cast<int*>(gsm + L.fy_off) + wg * 256;          // per warp, for two channels at once: finalY[64], finalY * multiplier in x order [64]
+    int* s_flags = reinterpret_cast<int*>(gsm + L.fy_off) + WPF * 256;      // [CT][4]: mask lo, mask hi, careful (groups of more than one warp)
     uint32_t* s_base = reinterpret_cast<uint32_t*>(gsm + L.base_off);       // [partition][ST]: where the (partition, stage) item's entries start
     uint16_t* s_cls = reinterpret_cast<uint16_t*>(gsm + L.cls_off);         // [partition]: class | coded stages << 8
     x.sdb = wf_smem(s_db); x.sseg = wf_smem(s_seg); x.sbase = wf_smem(s_base); x.scls = wf_smem(s_cls);
@@ -1452,15 +1475,28 @@ __global__ void __launch_bounds__(WF_WARPS * 32, 8) k_spectrum_wf(LaunchArgs a, 
     // ---- phase A: floors (warp wg takes channels wg, wg + WPF, ...) and entry offsets (the group's last warp)
     #pragma unroll
     for (int c = 0; c < CT; c++) { x.fmask[c] = 0; x.careful[c] = false; }
+    // channels of this warp in pairs (they interleave in floor1_wf_segments: twice the instruction-level parallelism)
     #pragma unroll
     for (int c = 0; c < CT; c++) {
-        if ((c % WPF) == wg && ((f.exec_mask >> c) & 1u)) {
-            unsigned long long mask; int careful_any;
-            floor1_wf_segments<H>(F, S.magic, a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, n, lane, s_fy, s_fy + 64, s_seg + c * L.np_pad, mask, careful_any);
-            x.fmask[c] = (mask_t)mask; x.careful[c] = careful_any != 0;
-            if (WPF > 1 && lane == 0) { s_flags[4 * c] = (int)(unsigned)mask; s_flags[4 * c + 1] = (int)(unsigned)(mask >> 32); s_flags[4 * c + 2] = careful_any; }
-            __syncwarp();                                                   // fy / ys are reused by the warp's next channel
+        if ((c % WPF) != wg || !((f.exec_mask >> c) & 1u)) continue;
+        const int c2 = c + WPF;                                             // the warp's next channel
+        const bool pair = c2 < CT && ((f.exec_mask >> c2) & 1u);
+        const int16_t* pp[2] = {a.posts + ((size_t)f.api_index * CT + c) * S.post_stride, a.posts + ((size_t)f.api_index * CT + (pair ? c2 : c)) * S.post_stride};
+        int* fyp[2] = {s_fy, s_fy + 128}; int* ysp[2] = {s_fy + 64, s_fy + 192};
+        WfSeg* sg[2] = {s_seg + c * L.np_pad, s_seg + (pair ? c2 : c) * L.np_pad};
+        unsigned long long mask[2] = {0ull, 0ull}; int careful_any[2] = {0, 0};
+        if (pair) floor1_wf_segments<H, 2>(F, S.magic, pp, n, lane, fyp, ysp, sg, mask, careful_any);
+        else floor1_wf_segments<H, 1>(F, S.magic, pp, n, lane, fyp, ysp, sg, mask, careful_any);
+        #pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int cj = j == 0 ? c : c2;
+            if (j == 1 && !pair) break;
+            #pragma unroll
+            for (int cc = 0; cc < CT; cc++) if (cc == cj) { x.fmask[cc] = (mask_t)mask[j]; x.careful[cc] = careful_any[j] != 0; }
+            if (WPF > 1 && lane == 0) { s_flags[4 * cj] = (int)(unsigned)mask[j]; s_flags[4 * cj + 1] = (int)(unsigned)(mask[j] >> 32); s_flags[4 * cj + 2] = careful_any[j]; }
         }
+        __syncwarp();                                                       // fy / ys are reused by the warp's next channels
+        if (pair) c = c2;                                                   // (the loop's own increment moves on from there)
     }
     if (wg == WPF - 1 && x.P > 0) wf_entry_offsets(S, rm, S.residues[rm.residue].coded, cls, x.P, lane, s_base, s_cls);
     wf_group_sync<WPF>(group);
@@ -1502,7 +1538,7 @@ static WfLayout wf_layout(const DevSetup& S, int CT, int WPF) {
     const int pmax = S.wf_max_p > 0 ? S.wf_max_p : 1;
     L.seg_off = 0;
     L.fy_off = L.seg_off + CT * L.np_pad * (int)sizeof(WfSeg);
-    L.base_off = (L.fy_off + WPF * 128 * (int)sizeof(int) + CT * 4 * (int)sizeof(int) + 15) & ~15;
+    L.base_off = (L.fy_off + WPF * 256 * (int)sizeof(int) + CT * 4 * (int)sizeof(int) + 15) & ~15;
     L.cls_off = L.base_off + pmax * st_max * (int)sizeof(uint32_t);
     L.total = (L.cls_off + pmax * (int)sizeof(uint16_t) + 15) & ~15;
     return L;

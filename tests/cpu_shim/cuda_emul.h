@@ -36,6 +36,7 @@ struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(4) uchar4 { unsigned char x, y, z, w; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(8) short4 { short x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
@@ -155,6 +156,8 @@ static inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t
     if (cuemu::tx_left == 0) mbar_arrive(bar);
 }
 static inline void fence_proxy_async() {}
+static inline void cp_async_16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+static inline void cp_async_wait_all() {}
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
