@@ -130,6 +130,60 @@ def cpu_reference_rate(hb, threads: int, min_seconds: float, max_reps: int = 100
     return len(fr) * reps / dt, reps, dt
 
 
+def ogg_to_pcm_rates(ctx, torch, tiles: int = 160, batch_packets: int = 4096):
+    """Packets of a real stream (3test tiled `tiles` times, ~45 k audio packets) to PCM in pinned host memory, two batches in
+    flight: frames/s with the host unpacker and with the GPU-side unpack.  The setup of `ctx` must be 3test's."""
+    from nvorbis_b200 import capi, hostlib
+    z = np.load(PACKETS)
+    data, sizes, gran, flags = z["data"], z["sizes"].astype(np.int64), z["granules"].astype(np.int64), z["flags"].astype(np.uint8)
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    head = data[: off[3]]
+    audio = data[off[3]:]
+    n_audio = len(sizes) - 3
+    t_sizes = np.concatenate([sizes[:3], np.tile(sizes[3:], tiles)])
+    t_data = np.concatenate([head, np.tile(audio, tiles)])
+    t_gran = np.zeros(len(t_sizes), np.int64); t_flags = np.zeros(len(t_sizes), np.uint8)       # no granules / EOS: the tail is drained at the end
+    out = {"workload": f"3test.ogg audio packets tiled {tiles}x ({n_audio * tiles} packets, {int(t_sizes[3:].sum())} bytes), batches of {batch_packets}, two in flight, float PCM into pinned memory",
+           "host_threads": os.cpu_count() or 1}
+    C = ctx.channels
+    for mode in ("host_unpack", "gpu_unpack"):
+        hs = hostlib.HostStream(packets=(t_data, t_sizes, t_gran, t_flags))
+        if mode == "gpu_unpack":
+            ctx.upload_unpack_tables(hs.unpack_tables())
+        ctx.reset()
+        bufs = [torch.empty((batch_packets + 2) * 2048 * C, dtype=torch.float32).pin_memory() for _ in range(2)]
+        keep = [None, None]
+        n_frames = 0; first = True; inflight = 0; i = 0; samples = 0
+        host_s = 0.0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        while True:
+            th = time.perf_counter()
+            if mode == "gpu_unpack":
+                b, eos = hs.packet_batch(batch_packets)
+            else:
+                b, eos = hs.unpack(batch_packets, 0)
+            host_s += time.perf_counter() - th
+            keep[i & 1] = b
+            fl = capi.RUN_DEFAULT | (0 if first else capi.RUN_CONTINUE)
+            if mode == "gpu_unpack":
+                ctx.decode_packets_begin(b, fl, bufs[i & 1].data_ptr(), bufs[i & 1].numel())
+            else:
+                ctx.decode_batch_begin(b, fl, bufs[i & 1].data_ptr(), bufs[i & 1].numel())
+            n_frames += len(b.frames); first = False; inflight += 1; i += 1
+            if inflight == 2:
+                samples += ctx.decode_batch_end().samples_per_channel; inflight -= 1
+            if eos:
+                break
+        while inflight:
+            samples += ctx.decode_batch_end().samples_per_channel; inflight -= 1
+        dt = time.perf_counter() - t0
+        out[mode] = {"frames_per_s": n_frames / dt, "seconds": dt, "frames": n_frames, "samples_per_channel": int(samples),
+                     "host_seconds_in_unpack_or_headers": host_s}
+        hs.close()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is managed C#
@@ -470,6 +524,15 @@ def run_ours(args):
     except Exception as e:                                                   # the headline line must survive a failure of the extra workload
         strong = {"error": repr(e)}
 
+    # ---- real packets end to end: a tiled 3test stream, container packets -> PCM in pinned host memory, (a) host unpacker
+    #      (nvh_unpack on all host threads) + nvb_decode_batch, (b) GPU-side unpack (nvh_packet_batch + nvb_decode_packets) ----
+    ogg = None
+    if rank == 0:
+        try:
+            ogg = ogg_to_pcm_rates(ctx, torch)
+        except Exception as e:
+            ogg = {"error": repr(e)}
+
     if rank == 0:
         frames_total = FRAMES_PER_STEP * world * args.steps
         ms_step = ms_total / args.steps
@@ -505,6 +568,7 @@ def run_ours(args):
                     "device_out_value": frames_total / (t_e2e_dev.ms * 1e-3),
                     "device_out_api": "NVB_RUN_DEVICE_OUT: PCM left in a device buffer of the caller (on-device consumer), d2h 0 bytes"},
             "strong_64k": strong,
+            "ogg_to_pcm": ogg,
             "gpu_launches": int(launches_per_step * args.steps),
             "timing": t_total.stats(),
             "kernels": {"k_spectrum_ms": ms_spec / args.steps, "k_imdct_fused_ms": imdct_ms, "step_ms": ms_step,

@@ -260,6 +260,34 @@ int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm
 int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap);
 int nvb_decode_batch_end(nvb_ctx* ctx, nvb_result* res);
 
+/* ---- GPU-side packet unpack: raw audio packets in, PCM out -------------------------------------
+ * The bit-reading half of Mapping.DecodePacket -- Floor1.Unpack (Floor1.cs:135-184), the class words and VQ entry numbers of
+ * Residue0.Decode (Residue0.cs:119-178) through Codebook.DecodeScalar (Codebook.cs:294-320), the energy flags
+ * (Mapping.cs:105-119) -- runs on the device too, one thread per packet (k_unpack), and writes the same boundary records
+ * the host would have sent.  The host keeps what is sequential across packets: container paging and, per packet, the values
+ * of Mode.GetPacketInfo (Mode.cs:119-151: mode / window flags from the packet's first bits) after the granule bookkeeping
+ * and the end-of-stream trim (StreamDecoder.cs:417-463).  H2D shrinks to the raw packets (about 300 B instead of 1.5 KB per
+ * stereo frame).  Setups with a type 0 floor are not unpacked on the device (NVB_ERR_UNSUPPORTED): use nvb_decode_batch. */
+typedef struct nvb_packet_batch {
+    int32_t          n_packets;
+    int32_t          reserved;
+    const nvb_frame* frames;    /* per packet: status, mode, window, start, valid, total; every other field is ignored (device-produced) */
+    const uint8_t*   data;      /* packet bytes back to back */
+    const uint32_t*  offsets;   /* n_packets + 1 byte offsets into data */
+} nvb_packet_batch;
+
+/* Installs the unpack tables (Huffman decode tables, floor / residue structure) next to the uploaded setup.  The blob is built
+ * by the host half from the same setup header (include/nvorbis_host.h: nvh_unpack_tables); layout: csrc/nvb_unpack_tables.h. */
+int nvb_upload_unpack_tables(nvb_ctx* ctx, const void* blob, size_t bytes);
+/* nvb_decode_batch / _begin for raw packets (same flags, same pipeline, completed by nvb_decode_batch_end). */
+int nvb_decode_packets(nvb_ctx* ctx, const nvb_packet_batch* batch, int flags, float* pcm_out, size_t pcm_cap, nvb_result* res);
+int nvb_decode_packets_begin(nvb_ctx* ctx, const nvb_packet_batch* batch, int flags, float* pcm_out, size_t pcm_cap);
+/* Parity / inspection: unpacks on the device and returns the boundary records in the nvb_batch layout with fixed strides --
+ * frames_out[n_packets] (classes_off = i * cls_stride, entries_off = i * ent_stride), posts_out[n_packets][channels][post_stride],
+ * classes_out[n_packets * cls_stride], entries_out[n_packets * ent_stride]; strides from nvb_unpack_strides. */
+int nvb_unpack_strides(nvb_ctx* ctx, int32_t* cls_stride, int32_t* ent_stride);
+int nvb_unpack_packets(nvb_ctx* ctx, const nvb_packet_batch* batch, nvb_frame* frames_out, int16_t* posts_out, uint8_t* classes_out, uint16_t* entries_out);
+
 /* Device-resident variant (pipelining / benchmarking): upload once, run many times.
  * `stream` is a cudaStream_t (NULL = default stream); d_pcm is a device pointer with room for
  * nvb_dbatch_samples()*channels floats.  nvb_dbatch_run only enqueues kernels.  With

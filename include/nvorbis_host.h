@@ -67,6 +67,25 @@ int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, in
 /* StreamDecoder.SeekTo(0) / ResetDecoder: restart at the first audio packet. */
 int nvh_rewind(nvh_stream* s);
 
+/* StreamDecoder.SeekTo(samplePosition) (StreamDecoder.cs:562-628) on the unpacking half: positions the packet cursor ONE packet
+ * before the packet that holds the sample (the pre-roll packet: decoded for its tail only, as the first block of a stream
+ * is, StreamDecoder.cs:446-450) and returns in *skip_samples how many samples per channel of the following output the caller
+ * drops (the reference's `_prevPacketStart += rollForward`).  The caller resets the synthesis context (nvb_reset) and decodes
+ * on without NVB_RUN_CONTINUE.  Sample positions count the samples a decode from the start of the stream emits (equal to the
+ * granule positions of a well-formed stream).  Packet lengths come from the packets' first bits (GetPacketGranules,
+ * StreamDecoder.cs:630-647): no Huffman decoding.  nvh_total_samples: what a full decode emits (call on a rewound stream). */
+int nvh_seek(nvh_stream* s, int64_t sample_position, int64_t* skip_samples);
+int64_t nvh_total_samples(nvh_stream* s);
+
+/* ---- host half of the GPU-side packet unpack (include/nvorbis_b200.h: nvb_decode_packets) ----
+ * nvh_unpack_tables: the unpack tables of this stream's setup for nvb_upload_unpack_tables (stream-owned, valid until
+ * nvh_close).  NVB_ERR_UNSUPPORTED for setups the device unpacker does not cover (a type 0 floor).
+ * nvh_packet_batch: the next `count` audio packets as an nvb_packet_batch -- raw bytes plus, per packet, what
+ * Mode.GetPacketInfo reads from its first bits (Mode.cs:119-151) after the same stream-order bookkeeping as nvh_unpack
+ * (sample position, end-of-stream trim, the drain record when the provider runs dry).  No Huffman decoding happens here. */
+int nvh_unpack_tables(nvh_stream* s, const void** blob, size_t* bytes);
+int64_t nvh_packet_batch(nvh_stream* s, int64_t count, nvb_packet_batch* out, int32_t* end_of_stream);
+
 #ifdef __cplusplus
 }
 #endif

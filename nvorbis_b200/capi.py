@@ -77,6 +77,10 @@ class BatchStruct(C.Structure):
                 ("classes", C.c_void_p), ("n_classes", C.c_int64), ("entries", C.c_void_p), ("n_entries", C.c_int64), ("floor0", C.c_void_p)]
 
 
+class PacketBatchStruct(C.Structure):
+    _fields_ = [("n_packets", C.c_int32), ("reserved", C.c_int32), ("frames", C.c_void_p), ("data", C.c_void_p), ("offsets", C.c_void_p)]
+
+
 class ResultStruct(C.Structure):
     _fields_ = [("samples_per_channel", C.c_int64), ("has_clipped", C.c_int32), ("n_failed", C.c_int32),
                 ("n_floor_range", C.c_int32), ("n_inconsistent", C.c_int32)]
@@ -93,6 +97,7 @@ EXPORTS = [
     "nvb_upload_setup", "nvb_setup_blob_size", "nvb_setup_blob_export", "nvb_setup_blob_import", "nvb_post_stride", "nvb_floor0_stride", "nvb_reset",
     "nvb_decode_batch", "nvb_decode_batch_begin", "nvb_decode_batch_end", "nvb_dbatch_create", "nvb_dbatch_samples", "nvb_dbatch_run", "nvb_dbatch_result", "nvb_dbatch_destroy",
     "nvb_dbatch_run_spectrum", "nvb_dbatch_run_imdct", "nvb_dbatch_spectrum_floats", "nvb_dbatch_launches",
+    "nvb_upload_unpack_tables", "nvb_decode_packets", "nvb_decode_packets_begin", "nvb_unpack_strides", "nvb_unpack_packets",
 ]
 
 _libs: dict = {}
@@ -134,6 +139,11 @@ def load_library(path: str | None = None):
     L.nvb_dbatch_run_imdct.argtypes = [vp, vp, vp, vp, vp]
     L.nvb_dbatch_result.argtypes = [vp, vp, vp, C.POINTER(ResultStruct)]
     L.nvb_dbatch_destroy.argtypes = [vp, vp]
+    L.nvb_upload_unpack_tables.argtypes = [vp, vp, sz]
+    L.nvb_decode_packets.argtypes = [vp, C.POINTER(PacketBatchStruct), i32, vp, sz, C.POINTER(ResultStruct)]
+    L.nvb_decode_packets_begin.argtypes = [vp, C.POINTER(PacketBatchStruct), i32, vp, sz]
+    L.nvb_unpack_strides.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.nvb_unpack_packets.argtypes = [vp, C.POINTER(PacketBatchStruct), vp, vp, vp, vp]
     _libs[path] = L
     return L
 
@@ -254,6 +264,24 @@ class HostBatch:
     @property
     def h2d_bytes(self) -> int:
         return self.frames.nbytes + self.posts.nbytes + self.classes.nbytes + self.entries.nbytes + (self.floor0.nbytes if self.floor0 is not None else 0)
+
+
+class PacketBatch:
+    """Owns the arrays an nvb_packet_batch points to: raw audio packets + the per-packet header values the host read
+    (Mode.GetPacketInfo, Mode.cs:119-151).  The GPU unpacks them (nvb_decode_packets)."""
+
+    def __init__(self, frames: np.ndarray, data: np.ndarray, offsets: np.ndarray):
+        self.frames = np.ascontiguousarray(frames, FRAME_DTYPE)
+        self.data = np.ascontiguousarray(data, np.uint8)
+        self.offsets = np.ascontiguousarray(offsets, np.uint32)
+        assert self.offsets.size == len(self.frames) + 1
+        if self.data.size == 0:
+            self.data = np.zeros(1, np.uint8)
+        self.struct = PacketBatchStruct(len(self.frames), 0, self.frames.ctypes.data, self.data.ctypes.data, self.offsets.ctypes.data)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(self.offsets[-1]) + self.offsets.nbytes + len(self.frames) * 64
 
 
 class DeviceBatch:
@@ -390,6 +418,37 @@ class Context:
         r = ResultStruct()
         self._check(self.lib.nvb_decode_batch(self.handle, C.byref(batch.struct), flags, out_ptr, out_floats, C.byref(r)), "nvb_decode_batch")
         return _result(r)
+
+    # ---- GPU-side packet unpack -------------------------------------------------------------------------------------
+    def upload_unpack_tables(self, blob: np.ndarray):
+        """nvb_upload_unpack_tables: the blob comes from the host half (hostlib.HostStream.unpack_tables)."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        self._check(self.lib.nvb_upload_unpack_tables(self.handle, blob.ctypes.data, blob.size), "nvb_upload_unpack_tables")
+
+    def unpack_strides(self):
+        c, e = C.c_int32(), C.c_int32()
+        self._check(self.lib.nvb_unpack_strides(self.handle, C.byref(c), C.byref(e)), "nvb_unpack_strides")
+        return int(c.value), int(e.value)
+
+    def decode_packets(self, pb: "PacketBatch", flags: int = RUN_DEFAULT, out: np.ndarray | None = None):
+        """nvb_decode_packets: raw packets in, interleaved PCM out (float32, or int16 with RUN_PCM_S16)."""
+        if out is None:
+            out = np.empty(max(sum_output_bound(pb.frames) * self.channels, 1), np.int16 if flags & RUN_PCM_S16 else np.float32)
+        r = ResultStruct()
+        self._check(self.lib.nvb_decode_packets(self.handle, C.byref(pb.struct), flags, out.ctypes.data, out.size, C.byref(r)), "nvb_decode_packets")
+        return out[: int(r.samples_per_channel) * self.channels], _result(r)
+
+    def decode_packets_begin(self, pb: "PacketBatch", flags: int, out_ptr: int, out_elems: int) -> None:
+        self._check(self.lib.nvb_decode_packets_begin(self.handle, C.byref(pb.struct), flags, out_ptr, out_elems), "nvb_decode_packets_begin")
+
+    def unpack_packets(self, pb: "PacketBatch", post_stride: int) -> HostBatch:
+        """nvb_unpack_packets: the device-produced boundary records, compacted into the layout nvh_unpack uses (for parity tests)."""
+        cs, es = self.unpack_strides()
+        n = len(pb.frames)
+        frames = np.zeros(n, FRAME_DTYPE); posts = np.zeros(max(n * self.channels * post_stride, 1), np.int16)
+        classes = np.zeros(max(n * cs, 1), np.uint8); entries = np.zeros(max(n * es, 1), np.uint16)
+        self._check(self.lib.nvb_unpack_packets(self.handle, C.byref(pb.struct), frames.ctypes.data, posts.ctypes.data, classes.ctypes.data, entries.ctypes.data), "nvb_unpack_packets")
+        return frames, posts[: n * self.channels * post_stride], classes.reshape(n, cs) if n else classes[:0], entries.reshape(n, es) if n else entries[:0]
 
     def create_dbatch(self, batch: HostBatch, flags: int = RUN_DEFAULT) -> DeviceBatch:
         h = C.c_void_p()

@@ -14,6 +14,7 @@
 #include <thread>
 #include <vector>
 #include "../../../include/nvorbis_host.h"
+#include "../nvb_unpack_tables.h"
 
 namespace nvh {
 
@@ -253,6 +254,8 @@ struct nvh_stream {
     // last unpacked batch
     std::vector<nvb_frame> o_frames; std::vector<int16_t> o_posts; std::vector<uint8_t> o_classes; std::vector<uint16_t> o_entries;
     std::vector<float> o_floor0;
+    // GPU-side unpack: the tables blob (built on demand) and the last packet batch
+    std::vector<uint8_t> u_blob; std::vector<uint32_t> o_offsets; std::vector<uint8_t> o_pad;
 };
 
 namespace nvh {
@@ -717,6 +720,187 @@ static void unpack_packet(const nvh_stream& s, const PacketRef& pr, Scratch& out
     done();
 }
 
+
+// Stream-order pass shared by nvh_unpack and nvh_packet_batch: the bookkeeping of StreamDecoder.ReadNextPacket / Read that
+// lives on the host -- sample position (re-based on the first granule, StreamDecoder.cs:358-363), the EOS trim (:429-437) and
+// the drain record when the provider runs dry (:352-356,476-480).  Appends to s->o_frames (and pads o_posts / o_floor0 for
+// the drain record).
+// One packet of the stream-order bookkeeping; returns the samples per channel the packet makes available.
+static int order_step(nvh_stream* s, UnpackedFrame& uf) {
+    nvb_frame& f = uf.f;
+    if (uf.resync) s->has_position = false;                                                       // StreamDecoder.cs:485-488
+    s->eos_found |= uf.eos;
+    int emitted;
+    if (f.status != NVB_FRAME_OK) {
+        s->prev_end = s->prev_stop;                                                               // drain, StreamDecoder.cs:352-356
+        emitted = s->have_prev ? std::max(0, s->prev_end - s->prev_start) : 0;
+        s->prev_start = s->prev_end;
+    } else {
+        if (uf.has_granule && uf.eos) {
+            const int64_t actual_end = s->position + f.valid - f.start;
+            const int diff = (int)(uf.granule - actual_end);
+            if (diff < 0) f.valid += diff;
+        }
+        if (s->prev_end > 0) s->prev_start = f.start;
+        else if (!s->have_prev) s->prev_start = f.valid;
+        s->prev_end = f.valid; s->prev_stop = f.total; s->have_prev = true;
+        emitted = std::max(0, s->prev_end - s->prev_start);
+        if (s->prev_end < s->prev_start) s->prev_start = s->prev_end;
+        s->prev_start = s->prev_end;
+    }
+    s->position += emitted;
+    if (uf.has_granule && !s->has_position && f.status == NVB_FRAME_OK) { s->has_position = true; s->position = uf.granule; }
+    return emitted;
+}
+
+static void stream_order_pass(nvh_stream* s, std::vector<UnpackedFrame>& metas, size_t next_packet, bool wanted_more, int32_t* end_of_stream) {
+    for (UnpackedFrame& uf : metas) { order_step(s, uf); s->o_frames.push_back(uf.f); }
+    s->next_packet = next_packet;
+    if (s->next_packet >= s->packets.size() && wanted_more) {
+        // the provider ran dry: DecodeNextPacket returns null with isEndOfStream = true (StreamDecoder.cs:476-480)
+        if (!s->eos_found) {
+            nvb_frame f; std::memset(&f, 0, sizeof f); f.status = NVB_FRAME_FAILED;
+            f.classes_off = (uint32_t)s->o_classes.size(); f.entries_off = (uint32_t)s->o_entries.size();
+            s->o_frames.push_back(f);
+            s->o_posts.resize(s->o_posts.size() + (size_t)s->channels * s->post_stride, 0);
+            s->o_floor0.resize(s->o_floor0.size() + (size_t)s->channels * s->f0_stride, 0.f);
+            s->prev_end = s->prev_stop;
+            if (s->have_prev) s->position += std::max(0, s->prev_end - s->prev_start);
+            s->prev_start = s->prev_end;
+            s->eos_found = true;
+        }
+        if (end_of_stream) *end_of_stream = 1;
+    } else if (s->eos_found && end_of_stream) {
+        *end_of_stream = 1;
+    }
+}
+
+// What Mode.GetPacketInfo reads from the first bits of an audio packet (Mode.cs:119-151) -- the head of unpack_packet, without
+// any Huffman decoding: status, mode, window flags, nominal start / valid / total.
+static void packet_header(const nvh_stream& s, const PacketRef& pr, UnpackedFrame& uf) {
+    std::memset(&uf.f, 0, sizeof uf.f);
+    uf.has_granule = pr.flags & 1; uf.granule = pr.granule; uf.eos = (pr.flags & 2) != 0; uf.resync = (pr.flags & 4) != 0;
+    uf.f.status = NVB_FRAME_FAILED;
+    Bits b(s.bytes.data() + pr.off, pr.size);
+    if (b.bit()) return;                                                                              // not an audio packet, StreamDecoder.cs:490
+    const int mode_idx = (int)b.read(s.mode_bits);
+    if (mode_idx >= (int)s.modes.size()) return;
+    const ModeDef& mode = s.modes[(size_t)mode_idx];
+    if (b.short_) return;
+    int window = 0, start, valid, total;
+    const int N = s.bs[mode.long_block ? 1 : 0];
+    if (mode.long_block) {
+        const bool prev = b.bit(), next = b.bit();
+        window = (prev ? 1 : 0) + (next ? 2 : 0);
+        const int pn = prev ? s.bs[1] : s.bs[0], nn = next ? s.bs[1] : s.bs[0];
+        start = N / 4 - pn / 4; total = N / 4 * 3 + nn / 4; valid = total - nn / 4 * 2;                // Mode.cs:102-117
+    } else { start = 0; valid = N / 2; total = N; }
+    uf.f.status = NVB_FRAME_OK; uf.f.mode = (uint8_t)mode_idx; uf.f.window = (uint8_t)window;
+    uf.f.start = start; uf.f.valid = valid; uf.f.total = total;
+}
+
+// The unpack tables of the setup (csrc/nvb_unpack_tables.h).
+static int build_unpack_tables(nvh_stream& s) {
+    using namespace nvbu;
+    for (int t : s.floor_type) if (t != 1) { s.err = "a type 0 floor is not unpacked on the device"; return NVB_ERR_UNSUPPORTED; }
+    for (const MappingDef& m : s.mappings) if (m.submaps != 1) { s.err = "multi-submap mappings are not supported"; return NVB_ERR_UNSUPPORTED; }
+    if (s.channels > NVB_MAX_CHANNELS) { s.err = "too many channels"; return NVB_ERR_UNSUPPORTED; }
+    std::vector<UBook> books; std::vector<uint32_t> roots; std::vector<ULong> longs;
+    for (const Book& b : s.books) {
+        UBook u; std::memset(&u, 0, sizeof u);
+        u.dims = b.dims; u.entries = b.entries; u.root_bits = b.root_bits; u.decodable = b.decodable ? 1 : 0;
+        u.root_off = (uint32_t)roots.size(); u.long_off = (uint32_t)longs.size(); u.n_long = (int32_t)b.longs.size();
+        if (b.decodable) {
+            if (b.entries > (1 << 24)) { s.err = "codebook too large for the device tables"; return NVB_ERR_UNSUPPORTED; }
+            for (const Book::Root& r : b.root) {
+                if (r.len) roots.push_back(((uint32_t)r.len << 24) | ((uint32_t)r.value & 0xffffffu));
+                else roots.push_back(r.value >= 0 ? (uint32_t)r.value + 1u : 0u);
+            }
+            for (const Book::Long& l : b.longs) longs.push_back(ULong{l.code, l.value, l.next >= 0 ? l.next + 1 : 0, l.len});
+        }
+        books.push_back(u);
+    }
+    std::vector<UFloor1> floors;
+    for (const Floor1Def& f : s.floors) {
+        UFloor1 u; std::memset(&u, 0, sizeof u);
+        u.type = 1; u.n_parts = (int32_t)f.part_class.size(); u.ybits = f.ybits; u.n_posts = (int32_t)f.x.size();
+        if (u.n_parts > 32 || f.class_dims.size() > 16) { s.err = "floor 1 structure outside the device tables"; return NVB_ERR_UNSUPPORTED; }
+        for (size_t k = 0; k < f.part_class.size(); k++) u.part_class[k] = (uint8_t)f.part_class[k];
+        for (size_t c = 0; c < f.class_dims.size(); c++) {
+            u.class_dims[c] = (uint8_t)f.class_dims[c]; u.class_subs[c] = (uint8_t)f.class_subs[c]; u.class_master[c] = (int16_t)f.class_master[c];
+            for (int k = 0; k < 8; k++) u.sub_books[c][k] = k < (int)f.sub_books[c].size() ? (int16_t)f.sub_books[c][(size_t)k] : (int16_t)-1;
+        }
+        floors.push_back(u);
+    }
+    std::vector<UResidue> residues; std::vector<uint8_t> digits;
+    for (const ResidueDef& r : s.residues) {
+        UResidue u; std::memset(&u, 0, sizeof u);
+        const Book& cb = s.books[(size_t)r.class_book];
+        u.type = r.type; u.begin = r.begin; u.end = r.end; u.psize = r.psize; u.nclass = r.nclass; u.class_book = r.class_book; u.stages = r.stages;
+        u.cdims = cb.dims; u.partvals = (int32_t)r.class_digits.size(); u.digits_off = (uint32_t)digits.size();
+        for (const auto& row : r.class_digits) digits.insert(digits.end(), row.begin(), row.end());
+        for (int c = 0; c < 64; c++) { u.cascade[c] = r.cascade[c]; for (int k = 0; k < 8; k++) u.books[c][k] = (int16_t)r.books[c][k]; }
+        residues.push_back(u);
+    }
+    // per-frame strides of the device-produced records: the largest any mode can need
+    int cls_stride = 1, ent_stride = 1;
+    for (const ModeDef& m : s.modes) {
+        const MappingDef& map = s.mappings[(size_t)m.mapping];
+        const ResidueDef& r = s.residues[(size_t)map.residue0];
+        const int N = s.bs[m.long_block ? 1 : 0];
+        const int span = (r.type == 2 ? N * s.channels : N) / 2;
+        const int nn = std::min(r.end, span) - r.begin;
+        const int P = nn > 0 ? nn / r.psize : 0, S = r.streams;
+        cls_stride = std::max(cls_stride, S * P);
+        long long per_partition = 0;                                       // worst class: entries of all its coded stages
+        for (int c = 0; c < r.nclass; c++) {
+            long long e = 0;
+            for (int st = 0; st < r.stages; st++) {
+                if (!((r.cascade[c] >> st) & 1) || r.books[c][st] < 0) continue;
+                const int d = s.books[(size_t)r.books[c][st]].dims;
+                e += r.type == 0 ? r.psize / d : (r.psize + d - 1) / d;
+            }
+            per_partition = std::max(per_partition, e);
+        }
+        const long long need = per_partition * P * S;
+        if (need > (1 << 22)) { s.err = "a frame can need more VQ entries than the device unpacker provides for"; return NVB_ERR_UNSUPPORTED; }
+        ent_stride = std::max(ent_stride, (int)need);
+    }
+    cls_stride = (cls_stride + 15) & ~15; ent_stride = (ent_stride + 7) & ~7;
+    std::vector<UMapping> mappings;
+    for (const MappingDef& m : s.mappings) {
+        UMapping u; std::memset(&u, 0, sizeof u);
+        if (m.mag.size() > 32) { s.err = "too many coupling steps"; return NVB_ERR_UNSUPPORTED; }
+        u.n_coupling = (int32_t)m.mag.size(); u.floor = m.floor0; u.residue = m.residue0;
+        for (size_t k = 0; k < m.mag.size(); k++) { u.mag[k] = (uint8_t)m.mag[k]; u.ang[k] = (uint8_t)m.ang[k]; }
+        mappings.push_back(u);
+    }
+    std::vector<UMode> modes;
+    for (const ModeDef& m : s.modes) modes.push_back(UMode{m.long_block ? 1 : 0, m.mapping});
+
+    UHeader h; std::memset(&h, 0, sizeof h);
+    h.magic = UNPACK_MAGIC; h.version = 1; h.channels = s.channels; h.bs[0] = s.bs[0]; h.bs[1] = s.bs[1]; h.mode_bits = s.mode_bits;
+    h.n_books = (int32_t)books.size(); h.n_floors = (int32_t)floors.size(); h.n_residues = (int32_t)residues.size();
+    h.n_mappings = (int32_t)mappings.size(); h.n_modes = (int32_t)modes.size();
+    h.post_stride = s.post_stride; h.cls_stride = cls_stride; h.ent_stride = ent_stride;
+    h.n_roots = (uint32_t)roots.size(); h.n_longs = (uint32_t)longs.size(); h.n_digits = (uint32_t)digits.size();
+    std::vector<uint8_t>& blob = s.u_blob;
+    blob.assign(sizeof(UHeader), 0);
+    auto put = [&](const void* src, size_t bytes) { const size_t at = (blob.size() + 15) & ~size_t(15); blob.resize(at + bytes, 0); if (bytes) std::memcpy(blob.data() + at, src, bytes); return (uint64_t)at; };
+    h.off_books = put(books.data(), books.size() * sizeof(UBook));
+    h.off_roots = put(roots.data(), roots.size() * sizeof(uint32_t));
+    h.off_longs = put(longs.data(), longs.size() * sizeof(ULong));
+    h.off_floors = put(floors.data(), floors.size() * sizeof(UFloor1));
+    h.off_residues = put(residues.data(), residues.size() * sizeof(UResidue));
+    h.off_digits = put(digits.data(), digits.size());
+    h.off_mappings = put(mappings.data(), mappings.size() * sizeof(UMapping));
+    h.off_modes = put(modes.data(), modes.size() * sizeof(UMode));
+    blob.resize((blob.size() + 15) & ~size_t(15), 0);
+    h.total_bytes = blob.size();
+    std::memcpy(blob.data(), &h, sizeof h);
+    return NVB_OK;
+}
+
 }  // namespace nvh
 
 // =====================================================================================================
@@ -830,52 +1014,7 @@ int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, in
         s->o_entries.insert(s->o_entries.end(), p.entries.begin(), p.entries.end());
         s->o_floor0.insert(s->o_floor0.end(), p.floor0.begin(), p.floor0.end());
     }
-    // Stream-order pass: the bookkeeping of StreamDecoder.ReadNextPacket / Read that lives on the host --
-    // sample position (re-based on the first granule, StreamDecoder.cs:358-363) and the EOS trim (:429-437).
-    for (UnpackedFrame& uf : metas) {
-        nvb_frame& f = uf.f;
-        if (uf.resync) s->has_position = false;                                                       // StreamDecoder.cs:485-488
-        s->eos_found |= uf.eos;
-        int emitted;
-        if (f.status != NVB_FRAME_OK) {
-            s->prev_end = s->prev_stop;                                                               // drain, StreamDecoder.cs:352-356
-            emitted = s->have_prev ? std::max(0, s->prev_end - s->prev_start) : 0;
-            s->prev_start = s->prev_end;
-        } else {
-            if (uf.has_granule && uf.eos) {
-                const int64_t actual_end = s->position + f.valid - f.start;
-                const int diff = (int)(uf.granule - actual_end);
-                if (diff < 0) f.valid += diff;
-            }
-            if (s->prev_end > 0) s->prev_start = f.start;
-            else if (!s->have_prev) s->prev_start = f.valid;
-            s->prev_end = f.valid; s->prev_stop = f.total; s->have_prev = true;
-            emitted = std::max(0, s->prev_end - s->prev_start);
-            if (s->prev_end < s->prev_start) s->prev_start = s->prev_end;
-            s->prev_start = s->prev_end;
-        }
-        s->position += emitted;
-        if (uf.has_granule && !s->has_position && f.status == NVB_FRAME_OK) { s->has_position = true; s->position = uf.granule; }
-        s->o_frames.push_back(f);
-    }
-    s->next_packet = lo + n;
-    if (s->next_packet >= s->packets.size() && (size_t)count > n) {
-        // the provider ran dry: DecodeNextPacket returns null with isEndOfStream = true (StreamDecoder.cs:476-480)
-        if (!s->eos_found) {
-            nvb_frame f; std::memset(&f, 0, sizeof f); f.status = NVB_FRAME_FAILED;
-            f.classes_off = (uint32_t)s->o_classes.size(); f.entries_off = (uint32_t)s->o_entries.size();
-            s->o_frames.push_back(f);
-            s->o_posts.resize(s->o_posts.size() + (size_t)s->channels * s->post_stride, 0);
-            s->o_floor0.resize(s->o_floor0.size() + (size_t)s->channels * s->f0_stride, 0.f);
-            s->prev_end = s->prev_stop;
-            if (s->have_prev) s->position += std::max(0, s->prev_end - s->prev_start);
-            s->prev_start = s->prev_end;
-            s->eos_found = true;
-        }
-        if (end_of_stream) *end_of_stream = 1;
-    } else if (s->eos_found && end_of_stream) {
-        *end_of_stream = 1;
-    }
+    stream_order_pass(s, metas, lo + n, (size_t)count > n, end_of_stream);
     std::memset(out, 0, sizeof *out);
     out->n_frames = (int32_t)s->o_frames.size();
     out->frames = s->o_frames.data(); out->posts = s->o_posts.data();
@@ -885,6 +1024,102 @@ int64_t nvh_unpack(nvh_stream* s, int64_t count, int threads, nvb_batch* out, in
     return (int64_t)s->o_frames.size();
     } catch (const std::bad_alloc&) { s->err = "nvh_unpack: out of memory"; return NVB_ERR_NOMEM; }
     catch (const std::exception& e) { s->err = std::string("nvh_unpack: ") + e.what(); return NVB_ERR_DATA; }
+}
+
+// Header-only walk of the stream from its start (no Huffman decoding): the samples per channel every audio packet makes
+// available when the stream is decoded from the beginning.  Leaves the stream rewound.
+static void emitted_per_packet(nvh_stream* s, std::vector<int>& emitted, std::vector<int64_t>& pos_before, std::vector<uint8_t>& has_pos_before, int64_t* tail_drain = nullptr) {
+    nvh_rewind(s);
+    const size_t n = s->packets.size() - s->first_audio;
+    emitted.assign(n, 0); pos_before.assign(n, 0); has_pos_before.assign(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        UnpackedFrame uf; packet_header(*s, s->packets[s->first_audio + i], uf);
+        pos_before[i] = s->position; has_pos_before[i] = s->has_position ? 1 : 0;
+        emitted[i] = order_step(s, uf);
+    }
+    // no end-of-stream packet: the provider runs dry and the last tail is drained (StreamDecoder.cs:352-356,476-480)
+    if (tail_drain) *tail_drain = (!s->eos_found && s->have_prev) ? std::max(0, s->prev_stop - s->prev_start) : 0;
+    nvh_rewind(s);
+}
+
+int64_t nvh_total_samples(nvh_stream* s) {
+    if (!s) return NVB_ERR_ARG;
+    if (s->next_packet != s->first_audio) return NVB_ERR_STATE;             // only on a rewound stream: the walk resets the decode cursor
+    try {
+        std::vector<int> e; std::vector<int64_t> p; std::vector<uint8_t> h; int64_t tail = 0;
+        emitted_per_packet(s, e, p, h, &tail);
+        int64_t total = tail; for (int v : e) total += v;
+        return total;
+    } catch (...) { return NVB_ERR_NOMEM; }
+}
+
+int nvh_seek(nvh_stream* s, int64_t sample_position, int64_t* skip_samples) {
+    if (!s || !skip_samples || sample_position < 0) return NVB_ERR_ARG;
+    try {
+        std::vector<int> e; std::vector<int64_t> pos; std::vector<uint8_t> hp;
+        emitted_per_packet(s, e, pos, hp);
+        *skip_samples = 0;
+        if (sample_position == 0 || e.empty()) return NVB_OK;                // the looping case: restart at the first audio packet
+        // packet k: the first one whose samples reach past the target
+        int64_t acc = 0; size_t k = 0;
+        while (k < e.size() && acc + e[k] <= sample_position) { acc += e[k]; ++k; }
+        if (k >= e.size()) {
+            // at or beyond the last packet: only the drained tail (if any) remains -- position the cursor on the last packet
+            k = e.size() - 1; acc -= e[k];
+        }
+        // pre-roll (StreamDecoder.cs:598-617): decoding restarts one packet early; that block only leaves its tail, the next one
+        // overlaps onto it, and `skip` samples of its output are dropped (_prevPacketStart += rollForward)
+        const size_t start = k > 0 ? k - 1 : 0;
+        int64_t lead = 0;                                                    // samples packets start..k-1 would emit after a restart at `start`
+        // (the restart block emits nothing; with start == k-1 nothing lies between it and k)
+        s->next_packet = s->first_audio + start;
+        s->have_prev = false; s->prev_start = s->prev_end = s->prev_stop = 0; s->eos_found = false;
+        // the sample position the continuous decode has when packet k starts to emit: the restart block does not advance it
+        s->position = pos[k]; s->has_position = hp[k] != 0;
+        if (start == k) {                                                    // k == 0: decoding from the very first packet is the continuous decode
+            s->position = 0; s->has_position = false;
+        }
+        *skip_samples = sample_position - acc + lead;
+        return NVB_OK;
+    } catch (const std::bad_alloc&) { s->err = "nvh_seek: out of memory"; return NVB_ERR_NOMEM; }
+    catch (const std::exception& ex) { s->err = std::string("nvh_seek: ") + ex.what(); return NVB_ERR_DATA; }
+}
+
+int nvh_unpack_tables(nvh_stream* s, const void** blob, size_t* bytes) {
+    if (!s || !blob || !bytes) return NVB_ERR_ARG;
+    try {
+        if (s->u_blob.empty()) { const int rc = build_unpack_tables(*s); if (rc != NVB_OK) { s->u_blob.clear(); return rc; } }
+    } catch (const std::bad_alloc&) { s->err = "nvh_unpack_tables: out of memory"; return NVB_ERR_NOMEM; }
+    catch (const std::exception& e) { s->err = std::string("nvh_unpack_tables: ") + e.what(); return NVB_ERR_DATA; }
+    *blob = s->u_blob.data(); *bytes = s->u_blob.size();
+    return NVB_OK;
+}
+
+int64_t nvh_packet_batch(nvh_stream* s, int64_t count, nvb_packet_batch* out, int32_t* end_of_stream) {
+    if (!s || !out || count < 0) return NVB_ERR_ARG;
+    if (end_of_stream) *end_of_stream = 0;
+    try {
+        const size_t lo = s->next_packet;
+        const size_t n = std::min<size_t>((size_t)count, s->packets.size() - lo);
+        std::vector<UnpackedFrame> metas(n);
+        for (size_t i = 0; i < n; i++) packet_header(*s, s->packets[lo + i], metas[i]);
+        s->o_frames.clear(); s->o_posts.clear(); s->o_classes.clear(); s->o_entries.clear(); s->o_floor0.clear();
+        stream_order_pass(s, metas, lo + n, (size_t)count > n, end_of_stream);
+        // packet payloads sit back to back in the stream's byte store: the batch points at them; a drain record (provider ran
+        // dry) is an empty packet.  Offsets are relative to the first packet of the batch.
+        const size_t base = n ? s->packets[lo].off : 0;
+        s->o_offsets.assign(s->o_frames.size() + 1, 0);
+        for (size_t i = 0; i < n; i++) s->o_offsets[i + 1] = (uint32_t)(s->packets[lo + i].off + s->packets[lo + i].size - base);
+        for (size_t i = n; i < s->o_frames.size(); i++) s->o_offsets[i + 1] = s->o_offsets[i];
+        if ((n ? s->packets[lo + n - 1].off + s->packets[lo + n - 1].size - base : 0) > 0xffffffffull) { s->err = "packet batch above 4 GiB"; return NVB_ERR_ARG; }
+        std::memset(out, 0, sizeof *out);
+        out->n_packets = (int32_t)s->o_frames.size();
+        out->frames = s->o_frames.data();
+        out->data = s->bytes.data() + base;
+        out->offsets = s->o_offsets.data();
+        return (int64_t)s->o_frames.size();
+    } catch (const std::bad_alloc&) { s->err = "nvh_packet_batch: out of memory"; return NVB_ERR_NOMEM; }
+    catch (const std::exception& e) { s->err = std::string("nvh_packet_batch: ") + e.what(); return NVB_ERR_DATA; }
 }
 
 }  // extern "C"

@@ -44,6 +44,8 @@ struct nvb_ctx {
         int rc = NVB_OK;                     // failure detected while enqueuing (reported by _end)
     } slot[2];
     int head = 0, in_flight = 0;
+    // GPU-side packet unpack: the unpack tables (nvb_upload_unpack_tables)
+    unsigned char* d_utab = nullptr; bool has_unpack = false; nvbu::UHeader UH; UnpackTables UT;
 };
 
 struct nvb_dbatch {
@@ -59,6 +61,11 @@ struct nvb_dbatch {
     float* d_blocks = nullptr;    size_t cap_blocks = 0;
     Counters* d_counters = nullptr;
     int launches = 0;
+    // raw packets of a packet batch (nvb_decode_packets) and the frames handed to the planner
+    uint8_t* d_pkt = nullptr; size_t cap_pkt = 0;
+    uint32_t* d_pkt_off = nullptr; size_t cap_pkt_off = 0;
+    std::vector<nvb_frame> pkt_frames;
+    bool from_packets = false;
 };
 
 namespace {
@@ -129,7 +136,7 @@ template <class T> int grow(nvb_ctx* ctx, T*& p, size_t& cap, size_t need) {
 void free_dbatch(nvb_dbatch* b) {
     if (!b) return;
     cudaFree(b->d_frames); cudaFree(b->d_posts); cudaFree(b->d_classes); cudaFree(b->d_entries); cudaFree(b->d_floor0);
-    cudaFree(b->d_spectrum); cudaFree(b->d_blocks); cudaFree(b->d_counters);
+    cudaFree(b->d_spectrum); cudaFree(b->d_blocks); cudaFree(b->d_counters); cudaFree(b->d_pkt); cudaFree(b->d_pkt_off);
     delete b;
 }
 
@@ -200,6 +207,73 @@ int upload_batch(nvb_ctx* ctx, nvb_dbatch* b, const nvb_batch* batch, int flags,
     if (n_posts) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts, batch->posts, n_posts * sizeof(int16_t), cudaMemcpyHostToDevice, st));
     if (batch->n_classes) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_classes, batch->classes, (size_t)batch->n_classes, cudaMemcpyHostToDevice, st));
     if (batch->n_entries) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_entries, batch->entries, (size_t)batch->n_entries * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    return NVB_OK;
+}
+
+// A packet batch (nvb_decode_packets): plans it from the host-provided packet headers, uploads the raw packets, sizes the
+// device-side record buffers at the tables' fixed per-frame strides.  k_unpack (enqueue_unpack) fills them.
+int upload_packets(nvb_ctx* ctx, nvb_dbatch* b, const nvb_packet_batch* pb, int flags, cudaStream_t st, DevFrame** pinned, size_t* pinned_cap) {
+    if (!ctx->has_unpack) return set_err(ctx, NVB_ERR_STATE, "no unpack tables uploaded (nvb_upload_unpack_tables)");
+    if (!pb || pb->n_packets < 0 || (pb->n_packets > 0 && (!pb->frames || !pb->offsets || !pb->data))) return set_err(ctx, NVB_ERR_ARG, "packet batch is NULL / has NULL arrays");
+    const size_t n = (size_t)pb->n_packets;
+    const size_t cs = (size_t)ctx->UH.cls_stride, es = (size_t)ctx->UH.ent_stride;
+    if (n * cs > 0xffffffffull || n * es > 0xffffffffull) return set_err(ctx, NVB_ERR_ARG, "packet batch too large for 32-bit record offsets: split it");
+    for (size_t i = 0; i < n; i++) if (pb->offsets[i + 1] < pb->offsets[i]) return set_err(ctx, NVB_ERR_DATA, "packet offsets must ascend");
+    b->pkt_frames.assign(pb->frames, pb->frames + n);
+    for (size_t i = 0; i < n; i++) {                                        // device-produced fields: placeholders with the fixed strides
+        nvb_frame& f = b->pkt_frames[i];
+        f.exec_mask = 0; f.res_decoded = 1; f.entry_count = 0;
+        f.classes_off = (uint32_t)(i * cs); f.entries_off = (uint32_t)(i * es);
+    }
+    static const int16_t dummy_posts = 0;
+    nvb_batch tmp; std::memset(&tmp, 0, sizeof tmp);
+    tmp.n_frames = pb->n_packets; tmp.frames = b->pkt_frames.data(); tmp.posts = &dummy_posts;
+    static const uint8_t dummy_c = 0; static const uint16_t dummy_e = 0;
+    tmp.classes = &dummy_c; tmp.n_classes = (int64_t)(n * cs); tmp.entries = &dummy_e; tmp.n_entries = (int64_t)(n * es);
+    std::string err;
+    int rc = plan_batch(ctx->host_blob.data(), &tmp, flags, ctx->carry, b->plan, err);
+    if (rc != NVB_OK) return set_err(ctx, rc, err);
+    if (b->plan.uses_floor0) return set_err(ctx, NVB_ERR_UNSUPPORTED, "type 0 floors are not unpacked on the device");
+    b->flags = flags; b->from_packets = true;
+    b->fused = !(flags & NVB_RUN_EXACT) && fused_supported(ctx->H, b->plan.frames.data(), (int)b->plan.frames.size());
+    const size_t nf = b->plan.frames.size();
+    const size_t n_posts = n * ctx->H.channels * ctx->H.post_stride;
+    const size_t bytes = n ? pb->offsets[n] : 0;
+    if ((rc = grow(ctx, b->d_frames, b->cap_frames, nf)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_posts, b->cap_posts, n_posts)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_classes, b->cap_classes, n * cs)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_entries, b->cap_entries, n * es)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_pkt, b->cap_pkt, bytes + 16)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_pkt_off, b->cap_pkt_off, n + 1)) != NVB_OK) return rc;
+    if ((rc = grow(ctx, b->d_spectrum, b->cap_spectrum, (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
+    if (!b->fused && (rc = grow(ctx, b->d_blocks, b->cap_blocks, 2 * (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
+    if (!b->d_counters) {
+        size_t cap = 0;
+        if ((rc = grow(ctx, b->d_counters, cap, 1)) != NVB_OK) return rc;
+        NVB_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), st));
+    }
+    const DevFrame* plan_src = b->plan.frames.data();
+    if (pinned && nf) {
+        if (*pinned_cap < nf) {
+            if (*pinned) { cudaFreeHost(*pinned); *pinned = nullptr; *pinned_cap = 0; }
+            if (cudaHostAlloc((void**)pinned, (nf + nf / 4 + 64) * sizeof(DevFrame), cudaHostAllocDefault) == cudaSuccess) *pinned_cap = nf + nf / 4 + 64;
+            else { cudaGetLastError(); *pinned = nullptr; }
+        }
+        if (*pinned) { std::memcpy(*pinned, b->plan.frames.data(), nf * sizeof(DevFrame)); plan_src = *pinned; }
+    }
+    if (nf) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_frames, plan_src, nf * sizeof(DevFrame), cudaMemcpyHostToDevice, st));
+    if (bytes) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_pkt, pb->data, bytes, cudaMemcpyHostToDevice, st));
+    NVB_CUDA(ctx, cudaMemsetAsync(b->d_pkt + bytes, 0, 16, st));             // the bit cursor loads whole aligned words
+    NVB_CUDA(ctx, cudaMemcpyAsync(b->d_pkt_off, pb->offsets, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    return NVB_OK;
+}
+
+int enqueue_unpack(nvb_ctx* ctx, nvb_dbatch* b, cudaStream_t st, int frame_lo, int frame_cnt) {
+    UnpackArgs u;
+    u.T = ctx->UT; u.frames = b->d_frames; u.frame_lo = frame_lo; u.n_frames = frame_cnt;
+    u.data = b->d_pkt; u.offsets = b->d_pkt_off; u.posts = b->d_posts; u.classes = b->d_classes; u.entries = b->d_entries;
+    const int r = launch_unpack(u, st);
+    if (r < 0) return cuda_fail(ctx, cudaGetLastError(), "k_unpack launch");
     return NVB_OK;
 }
 
@@ -331,7 +405,7 @@ int nvb_destroy(nvb_ctx* ctx) {
     if (!ctx) return NVB_OK;
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->d_blob); cudaFree(ctx->d_carry[0]); cudaFree(ctx->d_carry[1]);
+    cudaFree(ctx->d_blob); cudaFree(ctx->d_carry[0]); cudaFree(ctx->d_carry[1]); cudaFree(ctx->d_utab);
     cudaStreamDestroy(ctx->stream);
     for (int i = 0; i < 2; i++) {
         cudaStreamDestroy(ctx->chunk_stream[i]);
@@ -408,7 +482,23 @@ int nvb_reset(nvb_ctx* ctx) {
     return NVB_OK;
 }
 
+static int decode_begin_impl(nvb_ctx* ctx, const nvb_batch* batch, const nvb_packet_batch* pbatch, int flags, float* pcm_out, size_t pcm_cap);
+
 int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap) {
+    return decode_begin_impl(ctx, batch, nullptr, flags, pcm_out, pcm_cap);
+}
+int nvb_decode_packets_begin(nvb_ctx* ctx, const nvb_packet_batch* batch, int flags, float* pcm_out, size_t pcm_cap) {
+    if (!batch) return set_err(ctx, NVB_ERR_ARG, "packet batch is NULL");
+    return decode_begin_impl(ctx, nullptr, batch, flags, pcm_out, pcm_cap);
+}
+int nvb_decode_packets(nvb_ctx* ctx, const nvb_packet_batch* batch, int flags, float* pcm_out, size_t pcm_cap, nvb_result* res) {
+    if (ctx && ctx->in_flight > 0) return set_err(ctx, NVB_ERR_STATE, "batches begun with nvb_decode_batch_begin are still in flight");
+    const int rc = nvb_decode_packets_begin(ctx, batch, flags, pcm_out, pcm_cap);
+    if (rc != NVB_OK) return rc;
+    return nvb_decode_batch_end(ctx, res);
+}
+
+static int decode_begin_impl(nvb_ctx* ctx, const nvb_batch* batch, const nvb_packet_batch* pbatch, int flags, float* pcm_out, size_t pcm_cap) {
     if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
     if (!ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
     if (ctx->in_flight >= 2) return set_err(ctx, NVB_ERR_STATE, "two batches are already in flight: call nvb_decode_batch_end first");
@@ -427,7 +517,9 @@ int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, floa
 #endif
     NVB_TRACE_MARK(st_up, "begin", -1);
     bool chunked_inputs = batch && batch->n_frames >= chunk_min && batch->n_frames >= 8;
-    int rc = upload_batch(ctx, b, batch, flags, st_up, &chunked_inputs, &sl.h_frames, &sl.h_frames_cap);
+    int rc;
+    if (pbatch) { chunked_inputs = false; rc = upload_packets(ctx, b, pbatch, flags, st_up, &sl.h_frames, &sl.h_frames_cap); }
+    else { b->from_packets = false; rc = upload_batch(ctx, b, batch, flags, st_up, &chunked_inputs, &sl.h_frames, &sl.h_frames_cap); }
     if (rc != NVB_OK) { cudaStreamSynchronize(st_up); return rc; }
     const size_t n_out = (size_t)b->plan.samples * ctx->H.channels;
     if (n_out > pcm_cap || (n_out > 0 && !pcm_out)) { cudaStreamSynchronize(st_up); return set_err(ctx, NVB_ERR_CAPACITY, "pcm_out too small for the batch"); }
@@ -448,7 +540,7 @@ int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, floa
         else { if ((rc = grow(ctx, sl.d_pcm16, sl.pcm16_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(st_up); return rc; } d_s16 = sl.d_pcm16; }
     }
     const int nf = (int)b->plan.frames.size();
-    const int n_chunks = (chunked_inputs && nf >= chunk_min && nf >= 8) ? NVB_CHUNKS : 1;
+    const int n_chunks = ((chunked_inputs || pbatch) && nf >= chunk_min && nf >= 8) ? NVB_CHUNKS : 1;
     if (n_chunks == 1 && chunked_inputs) {                                  // few decoded frames after all: upload everything now
         const size_t n_posts = (size_t)batch->n_frames * ctx->H.channels * ctx->H.post_stride;
         if (n_posts) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts, batch->posts, n_posts * sizeof(int16_t), cudaMemcpyHostToDevice, st_up));
@@ -482,6 +574,7 @@ int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, floa
         NVB_CUDA(ctx, cudaEventRecord(sl.ev_up[k], st_up));
         NVB_CUDA(ctx, cudaStreamWaitEvent(st_k, sl.ev_up[k], 0));
         NVB_TRACE_MARK(st_k, "kernels_begin", k);
+        if (pbatch && hi > lo && (rc = enqueue_unpack(ctx, b, st_k, lo, hi - lo)) != NVB_OK) { cudaDeviceSynchronize(); return rc; }
         rc = enqueue(ctx, b, 0, nullptr, d_float, true, st_k, n_chunks == 1 ? 0 : lo, n_chunks == 1 ? -1 : hi - lo, false);
         if (rc != NVB_OK) { cudaDeviceSynchronize(); return rc; }
         size_t s0 = 0, s1 = 0;                                              // this chunk's elements of the interleaved PCM
@@ -540,6 +633,155 @@ int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm
     const int rc = nvb_decode_batch_begin(ctx, batch, flags, pcm_out, pcm_cap);
     if (rc != NVB_OK) return rc;
     return nvb_decode_batch_end(ctx, res);
+}
+
+int nvb_upload_unpack_tables(nvb_ctx* ctx, const void* blob, size_t bytes) {
+    if (!ctx || !blob) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    if (!ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
+    if (ctx->in_flight > 0) return set_err(ctx, NVB_ERR_STATE, "batches in flight");
+    using namespace nvbu;
+    if (bytes < sizeof(UHeader)) return set_err(ctx, NVB_ERR_DATA, "unpack tables: blob too small");
+    UHeader h; std::memcpy(&h, blob, sizeof h);
+    if (h.magic != UNPACK_MAGIC || h.version != 1 || h.total_bytes != bytes) return set_err(ctx, NVB_ERR_DATA, "unpack tables: magic / size mismatch");
+    if (h.channels != ctx->H.channels || h.bs[0] != ctx->H.bs[0] || h.bs[1] != ctx->H.bs[1] || h.post_stride != ctx->H.post_stride ||
+        h.n_books != ctx->H.n_books || h.n_floors != ctx->H.n_floors || h.n_residues != ctx->H.n_residues || h.n_mappings != ctx->H.n_mappings || h.n_modes != ctx->H.n_modes)
+        return set_err(ctx, NVB_ERR_DATA, "unpack tables do not belong to the uploaded setup");
+    auto in = [&](uint64_t off, uint64_t len) { return off >= sizeof(UHeader) && len <= bytes && off <= bytes - len && (off & 15) == 0; };
+    if (h.mode_bits < 0 || h.mode_bits > 8 || h.cls_stride < 1 || h.ent_stride < 1 || h.ent_stride > (1 << 22) + 8 ||
+        !in(h.off_books, sizeof(UBook) * (uint64_t)h.n_books) || !in(h.off_roots, 4ull * h.n_roots) || !in(h.off_longs, sizeof(ULong) * (uint64_t)h.n_longs) ||
+        !in(h.off_floors, sizeof(UFloor1) * (uint64_t)h.n_floors) || !in(h.off_residues, sizeof(UResidue) * (uint64_t)h.n_residues) || !in(h.off_digits, h.n_digits) ||
+        !in(h.off_mappings, sizeof(UMapping) * (uint64_t)h.n_mappings) || !in(h.off_modes, sizeof(UMode) * (uint64_t)h.n_modes))
+        return set_err(ctx, NVB_ERR_DATA, "unpack tables: section outside the blob");
+    // index ranges the kernel relies on
+    const unsigned char* base = static_cast<const unsigned char*>(blob);
+    const UBook* books = reinterpret_cast<const UBook*>(base + h.off_books);
+    const uint32_t* roots = reinterpret_cast<const uint32_t*>(base + h.off_roots);
+    const ULong* longs = reinterpret_cast<const ULong*>(base + h.off_longs);
+    for (int i = 0; i < h.n_books; i++) {
+        const UBook& b = books[i];
+        if (!b.decodable) continue;
+        if (b.root_bits < 1 || b.root_bits > ROOT_BITS || b.n_long < 0 || (uint64_t)b.root_off + (1ull << b.root_bits) > h.n_roots || (uint64_t)b.long_off + (uint64_t)b.n_long > h.n_longs || b.entries < 1 || b.entries > (1 << 24))
+            return set_err(ctx, NVB_ERR_DATA, "unpack tables: codebook table ranges");
+        for (uint32_t k = 0; k < (1u << b.root_bits); k++) {
+            const uint32_t r = roots[b.root_off + k], len = r >> 24;
+            if (len ? (len > (uint32_t)b.root_bits || (r & 0xffffffu) >= (uint32_t)b.entries) : (r > (uint32_t)b.n_long)) return set_err(ctx, NVB_ERR_DATA, "unpack tables: root table entry");
+        }
+        for (int k = 0; k < b.n_long; k++) {
+            const ULong& l = longs[b.long_off + k];
+            // chains run strictly backwards (the builder links each element to an older one): no cycles
+            if (l.len < 1 || l.len > 32 || l.value < 0 || l.value >= b.entries || l.next < 0 || l.next > k) return set_err(ctx, NVB_ERR_DATA, "unpack tables: long codeword");
+        }
+    }
+    const UFloor1* floors = reinterpret_cast<const UFloor1*>(base + h.off_floors);
+    for (int i = 0; i < h.n_floors; i++) {
+        const UFloor1& f = floors[i];
+        if (f.type != 1 || f.n_parts < 0 || f.n_parts > 32 || f.ybits < 1 || f.ybits > 16 || f.n_posts < 2 || f.n_posts > NVB_MAX_POSTS) return set_err(ctx, NVB_ERR_DATA, "unpack tables: floor");
+        int posts = 2;
+        for (int p = 0; p < f.n_parts; p++) {
+            const int c = f.part_class[p];
+            if (c >= 16 || f.class_dims[c] < 1 || f.class_dims[c] > 8 || f.class_subs[c] > 3) return set_err(ctx, NVB_ERR_DATA, "unpack tables: floor class");
+            if (f.class_subs[c] > 0 && (f.class_master[c] < 0 || f.class_master[c] >= h.n_books)) return set_err(ctx, NVB_ERR_DATA, "unpack tables: floor master book");
+            for (int k = 0; k < 8; k++) if (f.sub_books[c][k] >= h.n_books) return set_err(ctx, NVB_ERR_DATA, "unpack tables: floor book");
+            posts += f.class_dims[c];
+        }
+        if (posts != f.n_posts || posts + 1 > h.post_stride) return set_err(ctx, NVB_ERR_DATA, "unpack tables: floor post count");
+    }
+    const UResidue* residues = reinterpret_cast<const UResidue*>(base + h.off_residues);
+    for (int i = 0; i < h.n_residues; i++) {
+        const UResidue& r = residues[i];
+        if (r.type < 0 || r.type > 2 || r.begin < 0 || r.psize < 1 || r.nclass < 1 || r.nclass > 64 || r.stages < 0 || r.stages > 8 || r.class_book < 0 || r.class_book >= h.n_books ||
+            r.cdims < 1 || r.partvals < 1 || (uint64_t)r.digits_off + (uint64_t)r.partvals * (uint64_t)r.cdims > h.n_digits)
+            return set_err(ctx, NVB_ERR_DATA, "unpack tables: residue");
+        const uint8_t* dg = base + h.off_digits + r.digits_off;
+        for (int64_t k = 0; k < (int64_t)r.partvals * r.cdims; k++) if (dg[k] >= r.nclass) return set_err(ctx, NVB_ERR_DATA, "unpack tables: residue class digits");
+        for (int c = 0; c < 64; c++) for (int st = 0; st < 8; st++) {
+            const int bk = r.books[c][st];
+            if (bk >= h.n_books || (bk >= 0 && books[bk].dims < 1)) return set_err(ctx, NVB_ERR_DATA, "unpack tables: residue book");
+        }
+    }
+    const UMapping* mappings = reinterpret_cast<const UMapping*>(base + h.off_mappings);
+    for (int i = 0; i < h.n_mappings; i++) {
+        const UMapping& m = mappings[i];
+        if (m.n_coupling < 0 || m.n_coupling > 32 || m.floor < 0 || m.floor >= h.n_floors || m.residue < 0 || m.residue >= h.n_residues) return set_err(ctx, NVB_ERR_DATA, "unpack tables: mapping");
+        for (int k = 0; k < m.n_coupling; k++) if (m.mag[k] >= h.channels || m.ang[k] >= h.channels) return set_err(ctx, NVB_ERR_DATA, "unpack tables: coupling");
+    }
+    const UMode* modes = reinterpret_cast<const UMode*>(base + h.off_modes);
+    for (int i = 0; i < h.n_modes; i++) if (modes[i].mapping < 0 || modes[i].mapping >= h.n_mappings) return set_err(ctx, NVB_ERR_DATA, "unpack tables: mode");
+    // the strides must cover the largest frame of any mode (k_unpack writes without further checks)
+    for (int i = 0; i < h.n_modes; i++) {
+        const UMapping& m = mappings[modes[i].mapping]; const UResidue& r = residues[m.residue];
+        const int N = h.bs[modes[i].block_flag ? 1 : 0];
+        const int span = (r.type == 2 ? N * h.channels : N) / 2;
+        const int nn = (r.end < span ? r.end : span) - r.begin;
+        const int64_t P = nn > 0 ? nn / r.psize : 0, S = r.type == 2 ? 1 : h.channels;
+        int64_t worst = 0;
+        for (int c = 0; c < r.nclass; c++) {
+            int64_t e = 0;
+            for (int st = 0; st < r.stages; st++) { const int bk = r.books[c][st]; if (((r.cascade[c] >> st) & 1) && bk >= 0) e += r.type == 0 ? r.psize / books[bk].dims : (r.psize + books[bk].dims - 1) / books[bk].dims; }
+            if (e > worst) worst = e;
+        }
+        if (S * P > h.cls_stride || worst * P * S > h.ent_stride) return set_err(ctx, NVB_ERR_DATA, "unpack tables: strides too small for the setup");
+    }
+    DeviceGuard g(ctx->device);
+    unsigned char* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(ctx, NVB_ERR_NOMEM, std::string("cudaMalloc(unpack tables): ") + cudaGetErrorString(e)); }
+    e = cudaMemcpy(d, blob, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(ctx, e, "cudaMemcpy(unpack tables)"); }
+    cudaFree(ctx->d_utab);
+    ctx->d_utab = d; ctx->UH = h; ctx->has_unpack = true;
+    UnpackTables& T = ctx->UT;
+    T.books = reinterpret_cast<const UBook*>(d + h.off_books); T.roots = reinterpret_cast<const uint32_t*>(d + h.off_roots);
+    T.longs = reinterpret_cast<const ULong*>(d + h.off_longs); T.floors = reinterpret_cast<const UFloor1*>(d + h.off_floors);
+    T.residues = reinterpret_cast<const UResidue*>(d + h.off_residues); T.digits = d + h.off_digits;
+    T.mappings = reinterpret_cast<const UMapping*>(d + h.off_mappings); T.modes = reinterpret_cast<const UMode*>(d + h.off_modes);
+    T.channels = h.channels; T.mode_bits = h.mode_bits; T.post_stride = h.post_stride; T.cls_stride = h.cls_stride; T.ent_stride = h.ent_stride;
+    return NVB_OK;
+}
+
+int nvb_unpack_strides(nvb_ctx* ctx, int32_t* cls_stride, int32_t* ent_stride) {
+    if (!ctx || !ctx->has_unpack) return set_err(ctx, NVB_ERR_STATE, "no unpack tables uploaded");
+    if (cls_stride) *cls_stride = ctx->UH.cls_stride;
+    if (ent_stride) *ent_stride = ctx->UH.ent_stride;
+    return NVB_OK;
+}
+
+int nvb_unpack_packets(nvb_ctx* ctx, const nvb_packet_batch* pb, nvb_frame* frames_out, int16_t* posts_out, uint8_t* classes_out, uint16_t* entries_out) {
+    if (!ctx || !pb || !frames_out || !posts_out || !classes_out || !entries_out) return set_err(ctx, NVB_ERR_ARG, "NULL argument");
+    if (!ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
+    if (ctx->in_flight > 0) return set_err(ctx, NVB_ERR_STATE, "batches in flight");
+    DeviceGuard g(ctx->device);
+    nvb_dbatch* b = new (std::nothrow) nvb_dbatch();
+    if (!b) return set_err(ctx, NVB_ERR_NOMEM, "host allocation failed");
+    int rc = upload_packets(ctx, b, pb, NVB_RUN_DEFAULT, ctx->stream, nullptr, nullptr);
+    const size_t n = (size_t)(pb->n_packets > 0 ? pb->n_packets : 0);
+    const size_t nf = b->plan.frames.size();
+    if (rc == NVB_OK && nf) {
+        // records of packets that are not decoded (failed status) stay zero
+        cudaMemsetAsync(b->d_posts, 0, n * ctx->H.channels * ctx->H.post_stride * sizeof(int16_t), ctx->stream);
+        cudaMemsetAsync(b->d_classes, 0, n * (size_t)ctx->UH.cls_stride, ctx->stream);
+        cudaMemsetAsync(b->d_entries, 0, n * (size_t)ctx->UH.ent_stride * sizeof(uint16_t), ctx->stream);
+        rc = enqueue_unpack(ctx, b, ctx->stream, 0, (int)nf);
+    }
+    std::vector<DevFrame> got(nf);
+    if (rc == NVB_OK && nf) {
+        cudaError_t e = cudaMemcpyAsync(got.data(), b->d_frames, nf * sizeof(DevFrame), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && n) e = cudaMemcpyAsync(posts_out, b->d_posts, n * ctx->H.channels * ctx->H.post_stride * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && n) e = cudaMemcpyAsync(classes_out, b->d_classes, n * (size_t)ctx->UH.cls_stride, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && n) e = cudaMemcpyAsync(entries_out, b->d_entries, n * (size_t)ctx->UH.ent_stride * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "nvb_unpack_packets read-back");
+    } else if (rc == NVB_OK) {
+        std::memset(posts_out, 0, n * ctx->H.channels * ctx->H.post_stride * sizeof(int16_t));
+        std::memset(classes_out, 0, n * (size_t)ctx->UH.cls_stride); std::memset(entries_out, 0, n * (size_t)ctx->UH.ent_stride * sizeof(uint16_t));
+    }
+    if (rc == NVB_OK) {
+        for (size_t i = 0; i < n; i++) { frames_out[i] = b->pkt_frames[i]; frames_out[i].res_decoded = 0; frames_out[i].exec_mask = 0; frames_out[i].entry_count = 0; }
+        for (const DevFrame& d : got) if (d.kind == 0) { nvb_frame& f = frames_out[d.api_index]; f.exec_mask = d.exec_mask; f.res_decoded = d.res_decoded; f.entry_count = d.entry_count; }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    free_dbatch(b);
+    return rc;
 }
 
 int nvb_dbatch_create(nvb_ctx* ctx, const nvb_batch* batch, int flags, nvb_dbatch** out) {

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstddef>
 #include "../../include/nvorbis_b200.h"
+#include "nvb_unpack_tables.h"
 
 #if !defined(__CUDACC__) && !defined(NVB_HAVE_FLOAT2)
 // host-only compilation of nvb_host.cpp: the CUDA vector type the tables use
@@ -188,6 +189,20 @@ struct LaunchArgs {
     Counters* counters;
     int clip;
 };
+
+// ---- GPU-side packet unpack (nvb_unpack.cu) ------------------------------------------------------
+struct UnpackTables {           // the unpack-tables blob (nvb_unpack_tables.h) resolved against its device allocation
+    const nvbu::UBook* books; const uint32_t* roots; const nvbu::ULong* longs; const nvbu::UFloor1* floors; const nvbu::UResidue* residues;
+    const uint8_t* digits; const nvbu::UMapping* mappings; const nvbu::UMode* modes;
+    int32_t channels, mode_bits, post_stride, cls_stride, ent_stride;
+};
+struct UnpackArgs {
+    UnpackTables T;
+    DevFrame* frames; int frame_lo, n_frames;      // plan frames [frame_lo, frame_lo + n_frames): exec_mask / res_decoded / entry_count are written
+    const uint8_t* data; const uint32_t* offsets;  // packets of the batch (by api_index), padded by 8 bytes
+    int16_t* posts; uint8_t* classes; uint16_t* entries;
+};
+int launch_unpack(const UnpackArgs& a, void* stream);
 
 int launch_spectrum(const LaunchArgs& a, void* stream);            // picks k_spectrum_fast when every residue of the setup allows it
 int launch_spectrum_generic(const LaunchArgs& a, void* stream);

@@ -41,6 +41,11 @@ def load_library(path: str | None = None):
         L.nvh_unpack.restype = C.c_int64
         L.nvh_unpack.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(capi.BatchStruct), C.POINTER(C.c_int32)]
         L.nvh_rewind.argtypes = [vp]
+        L.nvh_seek.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64)]
+        L.nvh_total_samples.restype = C.c_int64; L.nvh_total_samples.argtypes = [vp]
+        L.nvh_unpack_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.nvh_packet_batch.restype = C.c_int64
+        L.nvh_packet_batch.argtypes = [vp, C.c_int64, C.POINTER(capi.PacketBatchStruct), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
 
@@ -129,3 +134,45 @@ class HostStream:
         entries = view(b.entries, np.uint16, b.n_entries)
         floor0 = view(b.floor0, np.float32, n * self.channels * self.floor0_stride) if b.floor0 else None
         return capi.HostBatch(frames, posts, classes, entries, floor0), bool(eos.value)
+
+    def seek(self, sample_position: int) -> int:
+        """nvh_seek: cursor on the pre-roll packet; returns the samples per channel to drop from the output that follows."""
+        skip = C.c_int64()
+        rc = self.lib.nvh_seek(self.handle, int(sample_position), C.byref(skip))
+        if rc != 0:
+            raise HostError(f"nvh_seek: status {rc} ({self.lib.nvh_last_error(self.handle).decode()})")
+        return int(skip.value)
+
+    def total_samples(self) -> int:
+        n = self.lib.nvh_total_samples(self.handle)
+        if n < 0:
+            raise HostError(f"nvh_total_samples: status {n}")
+        return int(n)
+
+    # ---- host half of the GPU-side packet unpack ------------------------------------------------------------------------
+    def unpack_tables(self) -> np.ndarray:
+        """The unpack tables of this stream's setup (for capi.Context.upload_unpack_tables)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        rc = self.lib.nvh_unpack_tables(self.handle, C.byref(p), C.byref(n))
+        if rc != 0:
+            raise HostError(f"nvh_unpack_tables: status {rc} ({self.lib.nvh_last_error(self.handle).decode()})")
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
+
+    def packet_batch(self, count: int, copy: bool = True):
+        """The next `count` audio packets as raw bytes + per-packet header values.  Returns (capi.PacketBatch, end_of_stream)."""
+        b = capi.PacketBatchStruct()
+        eos = C.c_int32()
+        n = self.lib.nvh_packet_batch(self.handle, count, C.byref(b), C.byref(eos))
+        if n < 0:
+            raise HostError(f"nvh_packet_batch: status {n} ({self.lib.nvh_last_error(self.handle).decode()})")
+
+        def view(ptr, dtype, count_):
+            if not ptr or count_ == 0:
+                return np.zeros(0, dtype)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count_ * np.dtype(dtype).itemsize,)).view(dtype)
+            return a.copy() if copy else a
+
+        offsets = view(b.offsets, np.uint32, n + 1) if n else np.zeros(1, np.uint32)
+        frames = view(b.frames, capi.FRAME_DTYPE, n)
+        data = view(b.data, np.uint8, int(offsets[-1]))
+        return capi.PacketBatch(frames, data, offsets), bool(eos.value)

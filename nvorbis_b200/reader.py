@@ -16,7 +16,7 @@ class VorbisReader:
     """`new VorbisReader(stream)` ... `ReadSamples(buffer, offset, count)` (VorbisReader.cs:42-64, 336-345)."""
 
     def __init__(self, source, device: int = 0, batch_packets: int = 4096, clip_samples: bool = True,
-                 unpack_threads: int = 0, lib_path: str | None = None):
+                 unpack_threads: int = 0, lib_path: str | None = None, gpu_unpack: bool | None = None):
         if isinstance(source, (bytes, bytearray, memoryview)):
             self._host = hostlib.HostStream(data=bytes(source))
         elif isinstance(source, str):
@@ -26,7 +26,19 @@ class VorbisReader:
             self._host = hostlib.HostStream(packets=tuple(source))
         self._ctx = capi.Context(device, lib_path=lib_path)
         self._ctx.upload_setup(self._host.setup())
+        # GPU-side packet unpack (nvb_decode_packets): the host only pages the container and reads each packet's first bits;
+        # None = use it whenever the setup is covered (no type 0 floor), False = host unpacker (nvh_unpack) + nvb_decode_batch
+        self._gpu_unpack = False
+        if gpu_unpack is None or gpu_unpack:
+            try:
+                self._ctx.upload_unpack_tables(self._host.unpack_tables())
+                self._gpu_unpack = True
+            except (hostlib.HostError, capi.NvbError):
+                if gpu_unpack:
+                    raise
         self._batch_packets = int(batch_packets)
+        self._skip = 0                                  # floats to drop after a seek (roll-forward, StreamDecoder.cs:626)
+        self._total = None
         self._threads = unpack_threads
         self.clip_samples = bool(clip_samples)          # StreamDecoder.ClipSamples (VorbisReader.cs:77 forces true)
         self._pcm = np.zeros(0, np.float32)             # decoded, not yet handed out
@@ -67,10 +79,15 @@ class VorbisReader:
         """Unpacks the next run of packets and puts it on the GPU; False when the stream has no more packets."""
         if self._unpack_done:
             return False
-        hb, eos = self._host.unpack(self._batch_packets, self._threads, copy=True)     # the arrays must outlive the call
         flags = capi.RUN_DEFAULT | (capi.RUN_CONTINUE if self._started else 0) | (0 if self.clip_samples else capi.RUN_NO_CLIP)
-        out = np.empty(max(capi.sum_output_bound(hb.frames) * self.channels, 1), np.float32)
-        self._ctx.decode_batch_begin(hb, flags, out.ctypes.data, out.size)
+        if self._gpu_unpack:
+            hb, eos = self._host.packet_batch(self._batch_packets, copy=True)          # the arrays must outlive the call
+            out = np.empty(max(capi.sum_output_bound(hb.frames) * self.channels, 1), np.float32)
+            self._ctx.decode_packets_begin(hb, flags, out.ctypes.data, out.size)
+        else:
+            hb, eos = self._host.unpack(self._batch_packets, self._threads, copy=True)
+            out = np.empty(max(capi.sum_output_bound(hb.frames) * self.channels, 1), np.float32)
+            self._ctx.decode_batch_begin(hb, flags, out.ctypes.data, out.size)
         self._inflight = (hb, out)
         self._started = True
         self._unpack_done = eos
@@ -87,6 +104,9 @@ class VorbisReader:
         self._inflight = None
         self._has_clipped |= res.has_clipped
         self._pcm, self._pos = out[: res.samples_per_channel * self.channels], 0
+        if self._skip:                                  # roll forward to the sample a seek asked for
+            drop = min(self._skip, self._pcm.size)
+            self._pos, self._skip = drop, self._skip - drop
         if not self._begin_next():                      # batch k+1 goes up while the caller consumes batch k
             self._eos = True
         return self._pcm.size > 0 or not self._eos
@@ -120,14 +140,32 @@ class VorbisReader:
             out.append(buf[:n].copy())
         return np.concatenate(out) if out else np.zeros(0, np.float32)
 
-    def seek_to_start(self):
-        """SeekTo(0): restart decoding at the first audio packet (StreamDecoder.cs:562-628 with preRoll at the start)."""
+    @property
+    def total_samples(self) -> int:
+        """TotalSamples: what a decode of the whole stream emits per channel (header-only walk, cached)."""
+        if self._total is None:
+            if self._inflight is not None or self._started:
+                raise RuntimeError("total_samples must be read before decoding starts or after seek_to(0)")
+            self._total = self._host.total_samples()
+        return self._total
+
+    def seek_to(self, sample_position: int):
+        """SeekTo(samplePosition) (StreamDecoder.cs:562-628): the next read_samples starts at that sample.  Decoding restarts
+        one packet early (the pre-roll packet only leaves its overlap tail) and rolls forward inside the next block."""
+        if sample_position < 0:
+            raise IndexError("samplePosition")                                   # ArgumentOutOfRangeException
         if self._inflight is not None:
             self._ctx.decode_batch_end(); self._inflight = None
-        self._host.rewind()
+        skip = self._host.seek(int(sample_position))
         self._ctx.reset()
-        self._pcm, self._pos, self._eos, self._started, self._samples_read = np.zeros(0, np.float32), 0, False, False, 0
+        self._pcm, self._pos, self._eos, self._started = np.zeros(0, np.float32), 0, False, False
+        self._samples_read = int(sample_position)
+        self._skip = skip * self.channels
         self._unpack_done = False
+
+    def seek_to_start(self):
+        """SeekTo(0): restart decoding at the first audio packet (the looping short cut, StreamDecoder.cs:588-592)."""
+        self.seek_to(0)
 
     def close(self):
         if self._inflight is not None:

@@ -38,4 +38,5 @@ void run(int grid, int block, size_t smem, const std::function<void()>& body) {
 #include "../../nvorbis_b200/csrc/nvb_host.cpp"
 #include "../../nvorbis_b200/csrc/nvb_kernels.cu"
 #include "../../nvorbis_b200/csrc/nvb_fused.cu"
+#include "../../nvorbis_b200/csrc/nvb_unpack.cu"
 #include "../../nvorbis_b200/csrc/nvb_api.cu"
