@@ -291,6 +291,7 @@ LaunchArgs make_args(nvb_ctx* ctx, nvb_dbatch* b, float* spectrum, float* d_pcm,
     a.pcm = d_pcm;
     a.counters = b->d_counters;
     a.clip = (b->flags & NVB_RUN_NO_CLIP) ? 0 : 1;
+    a.inputs_from_kernel = b->from_packets ? 1 : 0;
     return a;
 }
 

@@ -49,7 +49,18 @@ struct FusedParams {
     LaunchArgs a;
     int frames_per_cta;
     int n_slots;
+    int skew;                   // stress hook (NVB_FUSED_SKEW): pseudo-random pauses that shuffle the warps' relative progress
 };
+
+// Stress hook of the slot-ring protocol: a pause that depends on (warp, unit, site), so that warps overtake and fall behind
+// each other in ways normal timing never produces.
+__device__ __forceinline__ void fused_skew(int skew, int warp, int v, int site) {
+#if !defined(NVB_CPU_SHIM)
+    if (skew) __nanosleep((unsigned)((warp * 7919 + v * 104729 + site * 1299709) & 2047) * (unsigned)skew);
+#else
+    (void)skew; (void)warp; (void)v; (void)site;
+#endif
+}
 
 #if !defined(NVB_CPU_SHIM)
 // ---- mbarrier / bulk-copy primitives (PTX) ------------------------------------------------------------
@@ -247,6 +258,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
         const int rel = v - vfirst, slot = rel % NS, it = rel / NS;
         const int x = GROUPED ? v / U : v;                                   // frame and first channel of this unit
         const int cbase = GROUPED ? (v - x * U) * 2 : 0;
+        fused_skew(p.skew, warp, v, 0);
         cnt_wait(&s_empty[slot], 2 * it);                                    // both readers of every earlier frame of the slot are done
         cp_async_wait_all();                                                 // this unit's plan record (requested one unit ago) has landed
         __syncwarp();
@@ -310,7 +322,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
 
         // Frame x-1 must have claimed and filled its slot before this warp releases it (a release that overtakes the
         // frame itself would be counted against the slot's next user), whether its tail is needed or not.
+        fused_skew(p.skew, warp, v, 1);
         if (rel >= U) cnt_wait(&s_full[(rel - U) % NS], (rel - U) / NS + 1);
+        fused_skew(p.skew, warp, v, 2);
 
         // ---------------- output of frame x (a halo block only leaves its tail) --------------------
         if (x >= lo) {
@@ -529,6 +543,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_generic(GenericParam
     if (__any_sync(0xffffffffu, peak > 0.99999994f) && lane == 0) atomicOr(&a.counters->clipped, 1);
 }
 
+static int fused_sm_count(int dev_slot) {
+    static std::atomic<int> cache[64];
+    int v = cache[dev_slot].load(std::memory_order_relaxed);
+    if (v == 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev_slot].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 static int generic_slots(int C, int bs1) {
     const size_t per = (size_t)C * bs1 * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
     int ns = (int)((227 * 1024 - 64) / per);
@@ -564,15 +589,10 @@ static int launch_imdct_generic(const LaunchArgs& a, void* stream) {
     const int C = a.S.channels;
     GenericParams p; p.a = a; p.n_slots = generic_slots(C, a.S.bs[1]); p.slot_floats = a.S.bs[1];
     const size_t smem = (size_t)p.n_slots * ((size_t)C * p.slot_floats * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int)) + 32;
-    static size_t configured_by_dev[64] = {0};
-    static int num_sms_by_dev[64] = {0};
+    static std::atomic<size_t> configured_by_dev[64];
     int dev_slot = 0; cudaGetDevice(&dev_slot); if (dev_slot < 0 || dev_slot >= 64) dev_slot = 0;
-    if (smem > configured_by_dev[dev_slot]) {
-        if (cudaFuncSetAttribute(k_imdct_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured_by_dev[dev_slot] = smem;
-    }
-    int& num_sms = num_sms_by_dev[dev_slot];
-    if (num_sms == 0 && (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev_slot) != cudaSuccess || num_sms <= 0)) num_sms = 148;
+    if (!nvb_ensure_smem(configured_by_dev[dev_slot], smem, [&]() { return cudaFuncSetAttribute(k_imdct_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
+    const int num_sms = fused_sm_count(dev_slot);
     int fpc = (a.n_frames + num_sms - 1) / num_sms;
     if (fpc < 8) fpc = 8;
     p.frames_per_cta = fpc;
@@ -591,21 +611,17 @@ int launch_imdct_fused(const LaunchArgs& a, const DevFrame* host_frames, void* s
     if (grouped) for (int i = a.frame_lo; i < a.frame_lo + a.n_frames; i++) if (host_frames[i].kind != 0 || (host_frames[i].prev >= 0 && host_frames[i].prev != i - 1)) { grouped = false; break; }
     const int G = grouped ? 2 : C;
     FusedParams p; p.a = a; p.n_slots = fused_slots(G);
+    // stress hooks (tests): a ring of as few as three slots, pseudo-random pauses between the protocol steps
+    const char* env_slots = std::getenv("NVB_FUSED_SLOTS"); const char* env_skew = std::getenv("NVB_FUSED_SKEW");
+    if (env_slots) { const int ns = std::atoi(env_slots); if (ns >= 3 && ns < p.n_slots) p.n_slots = ns; }
+    p.skew = env_skew ? std::atoi(env_skew) : 0;
     const size_t smem = fused_smem(G, p.n_slots);
-    static size_t configured_by_dev[64] = {0};
-    static int num_sms_by_dev[64] = {0};
+    static std::atomic<size_t> configured_by_dev[64];
     int dev_slot = 0; cudaGetDevice(&dev_slot); if (dev_slot < 0 || dev_slot >= 64) dev_slot = 0;
-    size_t& configured = configured_by_dev[dev_slot];
-    int& num_sms = num_sms_by_dev[dev_slot];
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(k_imdct_fused_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(k_imdct_fused_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
-    if (num_sms == 0) {
-        int dev = 0; cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-    }
+    if (!nvb_ensure_smem(configured_by_dev[dev_slot], smem, [&]() {
+            return cudaFuncSetAttribute(k_imdct_fused_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                   cudaFuncSetAttribute(k_imdct_fused_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
+    const int num_sms = fused_sm_count(dev_slot);
     // persistent: one CTA per SM, each a contiguous run of frames (at least 8, so that the halo block stays cheap)
     const int ctas = num_sms * FUSED_CTAS_PER_SM;
     int fpc = (a.n_frames + ctas - 1) / ctas;

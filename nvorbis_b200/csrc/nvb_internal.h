@@ -3,6 +3,8 @@
 #pragma once
 #include <cstdint>
 #include <cstddef>
+#include <atomic>
+#include <mutex>
 #include "../../include/nvorbis_b200.h"
 #include "nvb_unpack_tables.h"
 
@@ -14,6 +16,12 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 
 // Kernel launch / dynamic shared memory spelled as macros so that tests/cpu_shim (test-only) can
 // compile the same kernel sources against its thread-per-lane emulation.
+// 1: the launch macros allow programmatic dependent launch (the default); 0 inside a NoEarlyStart scope: the kernel starts only
+// after everything before it in the stream has completed -- needed when a kernel's pre-wait prologue reads what the PREVIOUS
+// KERNEL writes (the spectrum kernels read posts / classes / plan records before griddepcontrol.wait, which is fine when
+// those come from host copies and wrong when k_unpack produces them).
+inline thread_local int nvb_launch_pdl = 1;
+struct NvbNoEarlyStart { int prev; explicit NvbNoEarlyStart(bool on) : prev(nvb_launch_pdl) { if (on) nvb_launch_pdl = 0; } ~NvbNoEarlyStart() { nvb_launch_pdl = prev; } };
 #if !defined(NVB_CPU_SHIM)
 // Every kernel is launched with programmatic stream serialization (PDL): its blocks may be scheduled, and run their
 // prologue (shared-memory setup, table staging), while the previous kernel of the stream drains; nvb_grid_dep_wait()
@@ -25,7 +33,7 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
         cfg__.dynamicSmemBytes = (size_t)(smem); cfg__.stream = (cudaStream_t)(stream);                     \
         cudaLaunchAttribute attr__[1];                                                                      \
         attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                  \
-        attr__[0].val.programmaticStreamSerializationAllowed = 1;                                           \
+        attr__[0].val.programmaticStreamSerializationAllowed = nvb_launch_pdl;                                           \
         cfg__.attrs = attr__; cfg__.numAttrs = 1;                                                           \
         cudaLaunchKernelEx(&cfg__, kernel, arg);                                                            \
     } while (0)
@@ -36,7 +44,7 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
         cfg__.dynamicSmemBytes = (size_t)(smem); cfg__.stream = (cudaStream_t)(stream);                     \
         cudaLaunchAttribute attr__[1];                                                                      \
         attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                  \
-        attr__[0].val.programmaticStreamSerializationAllowed = 1;                                           \
+        attr__[0].val.programmaticStreamSerializationAllowed = nvb_launch_pdl;                                           \
         cfg__.attrs = attr__; cfg__.numAttrs = 1;                                                           \
         cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                                                    \
     } while (0)
@@ -51,6 +59,19 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 #endif
 
 namespace nvb {
+
+// Launch-configuration caches, safe for several host threads (a context is single-threaded, but contexts on several
+// threads / devices launch the same kernels): the largest dynamic shared memory a kernel has been opted in to on a device,
+// and the device's SM count.  Zero-initialised statics of these types are valid.
+template <class SetAttr> inline bool nvb_ensure_smem(std::atomic<size_t>& slot, size_t smem, SetAttr set_attr) {
+    if (smem <= slot.load(std::memory_order_acquire)) return true;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    if (smem <= slot.load(std::memory_order_relaxed)) return true;
+    if (!set_attr()) return false;
+    slot.store(smem, std::memory_order_release);
+    return true;
+}
 
 // ---- immutable per-stream tables, as they sit in ONE contiguous device allocation ("blob") ----
 struct DevBook    { int32_t dims, entries; int64_t off; int32_t dshift, pad; };   // off: float index into vq, -1 = no table; dshift = log2(dims) or -1
@@ -188,6 +209,7 @@ struct LaunchArgs {
     float* pcm;
     Counters* counters;
     int clip;
+    int inputs_from_kernel;     // 1: posts / classes / entries / plan records were written by k_unpack just before (no early start of the spectrum kernel)
 };
 
 // ---- GPU-side packet unpack (nvb_unpack.cu) ------------------------------------------------------

@@ -2014,6 +2014,17 @@ __global__ void __launch_bounds__(256) k_pcm_s16(const float* __restrict__ src, 
 // process may hold contexts on several GPUs.
 constexpr int NVB_MAX_DEVICES = 64;
 static inline int current_device_slot() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < NVB_MAX_DEVICES) ? d : 0; }
+static inline int device_sm_count() {
+    static std::atomic<int> cache[NVB_MAX_DEVICES];
+    const int slot = current_device_slot();
+    int v = cache[slot].load(std::memory_order_relaxed);
+    if (v == 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[slot].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 
 static size_t spectrum_smem(const DevSetup& S) {
     size_t b = (size_t)(((S.max_items > 0 ? S.max_items : 1) + 3) & ~3) * sizeof(uint32_t);
@@ -2023,13 +2034,15 @@ static size_t spectrum_smem(const DevSetup& S) {
 
 int launch_spectrum(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
+    NvbNoEarlyStart serialise(a.inputs_from_kernel != 0);
     static const bool force_generic = std::getenv("NVB_SPECTRUM_GENERIC") != nullptr;      // test hook: exercise the general kernel
     static const bool no_bins = std::getenv("NVB_SPECTRUM_NO_BINS") != nullptr;                // test hook
     if (!a.S.spectrum_fast && a.S.spectrum_bins && !force_generic && !no_bins) {
         const int C = a.S.channels;
         const size_t smem = (size_t)a.S.max_items * sizeof(uint32_t) + 16;
         auto go = [&](auto kernel) -> int {
-            if (smem > 40 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            // the run / bins kernels carry up to ~15 KB of static shared memory: static + dynamic above 48 KB needs the opt-in
+            if (smem > 30 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
             NVB_LAUNCH(kernel, a.n_frames, 128, smem, stream, a);
             return cudaGetLastError() == cudaSuccess ? 1 : -1;
         };
@@ -2052,22 +2065,14 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         int nw = (int)((220 * 1024 - shared_part) / L.total);
         if (nw > 16) nw = 16;
         if (nw >= 2) {
-            static int num_sms = 0;
-            if (num_sms == 0) {
-                int dev = 0; cudaGetDevice(&dev);
-                if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-            }
+            const int num_sms = device_sm_count();
             const size_t smem = shared_part + (size_t)nw * L.total;
-            static size_t configured_w_by_c[NVB_MAX_DEVICES][NVB_MAX_CHANNELS + 1] = {{0}};    // per device and template instantiation
-            size_t& configured_w = configured_w_by_c[current_device_slot()][C];
-            if (smem > configured_w) {
-                cudaError_t e = C == 1 ? cudaFuncSetAttribute(k_spectrum_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                              : C == 2 ? cudaFuncSetAttribute(k_spectrum_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                              : C == 4 ? cudaFuncSetAttribute(k_spectrum_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                       : cudaFuncSetAttribute(k_spectrum_warp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return -1;
-                configured_w = smem;
-            }
+            static std::atomic<size_t> configured_w_by_c[NVB_MAX_DEVICES][NVB_MAX_CHANNELS + 1];    // per device and template instantiation
+            if (!nvb_ensure_smem(configured_w_by_c[current_device_slot()][C], smem, [&]() {
+                    return (C == 1 ? cudaFuncSetAttribute(k_spectrum_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : C == 2 ? cudaFuncSetAttribute(k_spectrum_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : C == 4 ? cudaFuncSetAttribute(k_spectrum_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(k_spectrum_warp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) == cudaSuccess; })) return -1;
             int grid = (a.n_frames + nw - 1) / nw;
             if (grid > num_sms) grid = num_sms;
             if (C == 1) NVB_LAUNCH(k_spectrum_warp<1>, grid, nw * 32, smem, stream, a);
@@ -2089,12 +2094,10 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         if (smem <= 200 * 1024) {
             const bool p64 = L.np_pad > 32;
             auto go = [&](auto kernel) -> int {
-                static size_t configured[NVB_MAX_DEVICES] = {0};              // one per instantiation (a lambda instantiation has its own statics)
-                size_t& conf = configured[current_device_slot()];
-                if (smem > 40 * 1024 && smem > conf) {
-                    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-                    conf = smem;
-                }
+                static std::atomic<size_t> configured[NVB_MAX_DEVICES];       // one per instantiation (a lambda instantiation has its own statics)
+                // static + dynamic shared memory above 48 KB needs the opt-in: ask for it whenever the dynamic part is not small
+                if (smem > 32 * 1024 && !nvb_ensure_smem(configured[current_device_slot()], smem, [&]() {
+                        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
                 NVB_LAUNCHV(kernel, (a.n_frames + fpc - 1) / fpc, WF_WARPS * 32, smem, stream, a, L);
                 return cudaGetLastError() == cudaSuccess ? 1 : -1;
             };
@@ -2114,7 +2117,8 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         static const int nt = std::getenv("NVB_SPECTRUM_NT") ? std::atoi(std::getenv("NVB_SPECTRUM_NT")) : 128;
         const size_t smem = (size_t)a.S.max_items * sizeof(uint32_t) + 16;
         auto go = [&](auto kernel, int threads) -> int {
-            if (smem > 40 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            // the run / bins kernels carry up to ~15 KB of static shared memory: static + dynamic above 48 KB needs the opt-in
+            if (smem > 30 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
             NVB_LAUNCH(kernel, a.n_frames, threads, smem, stream, a);
             return cudaGetLastError() == cudaSuccess ? 1 : -1;
         };
@@ -2129,16 +2133,12 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         const size_t span = (size_t)C * (a.S.bs[1] / 2) * sizeof(float);
         const size_t smem = span * (size_t)(a.S.max_stages + 1) + (((size_t)a.S.max_items * sizeof(ItemRec) + 15) & ~size_t(15)) +
                             (((size_t)a.S.max_items + 15) & ~size_t(15)) + (size_t)a.S.ci_total * sizeof(int4) + 16;
-        static size_t configured_pl_by_c[NVB_MAX_DEVICES][NVB_MAX_CHANNELS + 1] = {{0}};       // per device and template instantiation
-        size_t& configured_pl = configured_pl_by_c[current_device_slot()][C];
-        if (smem > configured_pl) {
-            cudaError_t e = C == 1 ? cudaFuncSetAttribute(k_spectrum_planes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : C == 2 ? cudaFuncSetAttribute(k_spectrum_planes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : C == 4 ? cudaFuncSetAttribute(k_spectrum_planes<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                   : cudaFuncSetAttribute(k_spectrum_planes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return -1;
-            configured_pl = smem;
-        }
+        static std::atomic<size_t> configured_pl_by_c[NVB_MAX_DEVICES][NVB_MAX_CHANNELS + 1];   // per device and template instantiation
+        if (!nvb_ensure_smem(configured_pl_by_c[current_device_slot()][C], smem, [&]() {
+                return (C == 1 ? cudaFuncSetAttribute(k_spectrum_planes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : C == 2 ? cudaFuncSetAttribute(k_spectrum_planes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : C == 4 ? cudaFuncSetAttribute(k_spectrum_planes<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                               : cudaFuncSetAttribute(k_spectrum_planes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) == cudaSuccess; })) return -1;
         if (C == 1) NVB_LAUNCH(k_spectrum_planes<1>, a.n_frames, SPEC_THREADS, smem, stream, a);
         else if (C == 2) NVB_LAUNCH(k_spectrum_planes<2>, a.n_frames, SPEC_THREADS, smem, stream, a);
         else if (C == 4) NVB_LAUNCH(k_spectrum_planes<4>, a.n_frames, SPEC_THREADS, smem, stream, a);
@@ -2146,27 +2146,22 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
     const size_t smem = spectrum_smem(a.S) + (size_t)a.S.channels * (a.S.bs[1] / 2) * sizeof(float);
-    static size_t configured_by_dev[NVB_MAX_DEVICES] = {0};
-    size_t& configured = configured_by_dev[current_device_slot()];
-    if (smem > 24 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(k_spectrum_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
+    static std::atomic<size_t> configured_by_dev[NVB_MAX_DEVICES];
+    if (smem > 24 * 1024 && !nvb_ensure_smem(configured_by_dev[current_device_slot()], smem, [&]() {
+            return cudaFuncSetAttribute(k_spectrum_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
     NVB_LAUNCH(k_spectrum_fast, a.n_frames, SPEC_THREADS, smem, stream, a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_spectrum_generic(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
+    NvbNoEarlyStart serialise(a.inputs_from_kernel != 0);
     static const bool forbid = std::getenv("NVB_SPECTRUM_FORBID_GENERIC") != nullptr;           // test hook: prove a faster kernel covers the setup
     if (forbid) return -1;
     size_t smem = spectrum_smem(a.S);
-    static size_t configured_by_dev[NVB_MAX_DEVICES] = {0};
-    size_t& configured = configured_by_dev[current_device_slot()];
-    if (smem > 48 * 1024 - 8192 && smem > configured) {
-        if (cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
+    static std::atomic<size_t> configured_by_dev[NVB_MAX_DEVICES];
+    if (smem > 48 * 1024 - 8192 && !nvb_ensure_smem(configured_by_dev[current_device_slot()], smem, [&]() {
+            return cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
     NVB_LAUNCH(k_spectrum, a.n_frames, SPEC_THREADS, smem, stream, a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -2174,12 +2169,9 @@ int launch_spectrum_generic(const LaunchArgs& a, void* stream) {
 int launch_imdct_exact(const LaunchArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
     size_t smem = (size_t)(a.S.bs[1] + a.S.bs[1] / 2) * sizeof(float);
-    static size_t configured_by_dev[NVB_MAX_DEVICES] = {0};
-    size_t& configured = configured_by_dev[current_device_slot()];
-    if (smem > 40 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(k_imdct_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
+    static std::atomic<size_t> configured_by_dev[NVB_MAX_DEVICES];
+    if (smem > 40 * 1024 && !nvb_ensure_smem(configured_by_dev[current_device_slot()], smem, [&]() {
+            return cudaFuncSetAttribute(k_imdct_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
     NVB_LAUNCH(k_imdct_exact, a.n_frames * a.S.channels, MDCT_THREADS, smem, stream, a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

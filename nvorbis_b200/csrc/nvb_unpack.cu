@@ -1,7 +1,8 @@
 // nvb_unpack.cu -- k_unpack: the bit-reading half of Mapping.DecodePacket on the device.
 //
-// One thread per audio packet: packets are independent given the setup, and inside a packet every field's position depends on
-// the Huffman codewords before it, so a packet is one serial walk -- Floor1.Unpack per channel (Floor1.cs:135-184), the energy
+// One warp per audio packet, its lane 0 walking the bits: packets are independent given the setup, and inside a packet every
+// field's position depends on the Huffman codewords before it, so a packet is one serial walk (32 walks in one warp would
+// serialise on their divergent control flow; with a warp each, thousands of walks hide each other's table-load latency) -- Floor1.Unpack per channel (Floor1.cs:135-184), the energy
 // flags (Mapping.cs:105-119), then the class words and VQ entry numbers of Residue0.Decode (Residue0.cs:119-178) through
 // Codebook.DecodeScalar (Codebook.cs:294-320).  The thread writes the boundary records the host unpacker would have sent
 // (posts / classes / entries at fixed per-frame strides) and patches exec_mask / res_decoded / entry_count into the frame's
@@ -21,6 +22,12 @@ namespace nvb {
 static inline uint32_t nvb_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31)); }
 #else
 __device__ __forceinline__ uint32_t nvb_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+#endif
+
+#if defined(NVB_CPU_SHIM)
+static inline void prefetch_l1_u(const void*) {}
+#else
+__device__ __forceinline__ void prefetch_l1_u(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 
 // Bit cursor over one packet, LSB first (DataPacket.cs:150-283): reading past the end yields zero bits and raises short_.
@@ -64,9 +71,11 @@ __device__ __forceinline__ int book_decode(const UnpackTables& T, int bk, DBits&
     return -1;
 }
 
-__global__ void __launch_bounds__(32) k_unpack(UnpackArgs a) {
+constexpr int UNPACK_WARPS = 4;                                          // packets per CTA: one warp each
+
+__global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a) {
     nvb_grid_dep_launch();
-    const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int fi = blockIdx.x * UNPACK_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     nvb_grid_dep_wait();                                                    // the record buffers may still be read by the previous batch's kernels
     if (fi >= a.n_frames) return;
     DevFrame* df = a.frames + a.frame_lo + fi;
@@ -75,19 +84,33 @@ __global__ void __launch_bounds__(32) k_unpack(UnpackArgs a) {
     const int C = T.channels;
     const int api = df->api_index;
     const uint32_t p0 = a.offsets[api], p1 = a.offsets[api + 1];
-    DBits b; b.base = a.data + p0; b.nbits = (p1 - p0) * 8u; b.pos = 0u; b.short_ = false;
-    // the host already read the packet type bit, the mode number and the window flags (Mode.cs:119-151): skip them
     const nvbu::UMode mode = T.modes[df->mode];
-    b.skip(1u + (uint32_t)T.mode_bits + (mode.block_flag ? 2u : 0u));
     const nvbu::UMapping& map = T.mappings[mode.mapping];
     const int N = df->n;
+    // A packet is one serial walk: lane 0 does it (a warp of 32 walks would serialise on their divergent control flow); the
+    // other lanes pull the packet into L1 and clear the frame's post / class records, then leave.
+    {
+        const nvbu::UResidue& r0 = T.residues[map.residue];
+        const int span0 = (r0.type == 2 ? N * C : N) / 2;
+        const int nn0 = (r0.end < span0 ? r0.end : span0) - r0.begin;
+        const int ncls = nn0 > 0 ? (nn0 / r0.psize) * (r0.type == 2 ? 1 : C) : 0;
+        for (uint32_t o = p0 + 128u * lane; o < p1; o += 128u * 32u) prefetch_l1_u(a.data + o);
+        int16_t* posts = a.posts + (size_t)api * C * T.post_stride;
+        for (int k = lane; k < C * T.post_stride; k += 32) posts[k] = 0;
+        uint8_t* cls0 = a.classes + (size_t)api * T.cls_stride;
+        for (int k = lane; k < ncls; k += 32) cls0[k] = 0;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    DBits b; b.base = a.data + p0; b.nbits = (p1 - p0) * 8u; b.pos = 0u; b.short_ = false;
+    // the host already read the packet type bit, the mode number and the window flags (Mode.cs:119-151): skip them
+    b.skip(1u + (uint32_t)T.mode_bits + (mode.block_flag ? 2u : 0u));
 
     // floors: Floor1.Unpack per channel (Floor1.cs:135-184)
     const nvbu::UFloor1& f = T.floors[map.floor];
     uint32_t live = 0u;
     for (int c = 0; c < C; c++) {
         int16_t* dst = a.posts + ((size_t)api * C + c) * T.post_stride;
-        for (int k = 0; k < T.post_stride; k++) dst[k] = 0;
         int count = 0;
         if (b.read(1u)) {
             count = 2;
@@ -132,7 +155,6 @@ __global__ void __launch_bounds__(32) k_unpack(UnpackArgs a) {
         const int P = nn / r.psize, S = r.type == 2 ? 1 : C;
         uint8_t* cls = a.classes + (size_t)api * T.cls_stride;
         uint16_t* ent = a.entries + (size_t)api * T.ent_stride;
-        for (int k = 0; k < S * P; k++) cls[k] = 0;
         const uint8_t* digits = T.digits + r.digits_off;
         bool stop = false;
         for (int stage = 0; stage < r.stages && !stop; stage++) {
@@ -174,7 +196,7 @@ __global__ void __launch_bounds__(32) k_unpack(UnpackArgs a) {
 
 int launch_unpack(const UnpackArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
-    NVB_LAUNCH(k_unpack, (a.n_frames + 31) / 32, 32, 0, stream, a);
+    NVB_LAUNCH(k_unpack, (a.n_frames + UNPACK_WARPS - 1) / UNPACK_WARPS, UNPACK_WARPS * 32, 0, stream, a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

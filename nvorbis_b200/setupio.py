@@ -83,3 +83,35 @@ def load(path: str):
     desc = dict(channels=int(hdr[0]), sample_rate=int(hdr[1]), block_size=(int(hdr[2]), int(hdr[3])), books=books, floors=floors,
                 residues=residues, mappings=mappings, modes=modes)
     return desc, z
+
+
+def desc_from_setup(view) -> dict:
+    """The description dict of an nvb_setup produced by the host half (hostlib.HostStream.setup()): what the workload
+    generators need (structure only; codebook tables are left out)."""
+    S = view.struct
+    books = [dict(dims=int(S.books[i].dims), entries=int(S.books[i].entries), map_type=int(S.books[i].map_type), table=None) for i in range(S.n_books)]
+    floors = []
+    for i in range(S.n_floors):
+        f = S.floors[i]
+        n = int(f.f1.n_posts)
+        floors.append(dict(type=int(f.type), n_posts=n, multiplier=int(f.f1.multiplier), range=int(f.f1.range),
+                           x_list=np.array(f.f1.x_list[:n], np.int32), l_neigh=np.array(f.f1.l_neigh[:n], np.int32),
+                           h_neigh=np.array(f.f1.h_neigh[:n], np.int32), sort_idx=np.array(f.f1.sort_idx[:n], np.int32),
+                           order=int(f.f0.order), rate=int(f.f0.rate), bark_map_size=int(f.f0.bark_map_size), amp_bits=int(f.f0.amp_bits),
+                           amp_ofs=int(f.f0.amp_ofs)))
+    residues = []
+    for i in range(S.n_residues):
+        r = S.residues[i]
+        nc = int(r.classifications)
+        residues.append(dict(type=int(r.type), begin=int(r.begin), end=int(r.end), partition_size=int(r.partition_size), classifications=nc,
+                             max_stages=int(r.max_stages), cascade=np.array(r.cascade[:nc], np.int32),
+                             books=np.array([[int(r.books[c][k]) for k in range(8)] for c in range(nc)], np.int32)))
+    mappings = []
+    for i in range(S.n_mappings):
+        m = S.mappings[i]
+        n = int(m.n_coupling)
+        mappings.append(dict(n_coupling=n, n_submaps=int(m.n_submaps), floor=int(m.floor), residue=int(m.residue),
+                             magnitude=np.array(m.magnitude[:n], np.int32), angle=np.array(m.angle[:n], np.int32)))
+    modes = [dict(block_flag=int(S.modes[i].block_flag), mapping=int(S.modes[i].mapping)) for i in range(S.n_modes)]
+    return dict(channels=int(S.channels), sample_rate=int(S.sample_rate), block_size=(int(S.block_size[0]), int(S.block_size[1])),
+                books=books, floors=floors, residues=residues, mappings=mappings, modes=modes)

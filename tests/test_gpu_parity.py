@@ -283,6 +283,34 @@ def test_pcm_s16_epilogue_and_device_output():
     ctx.close()
 
 
+def test_slot_ring_under_stress():
+    """The release/acquire counter protocol of k_imdct_fused's slot ring (racecheck cannot model it): a ring of only THREE
+    slots for 16 warps plus pseudo-random pauses between the protocol steps (NVB_FUSED_SLOTS / NVB_FUSED_SKEW) -- warps
+    overtake each other in ways normal timing never shows -- must give bit-identical PCM to the undisturbed run, for the
+    stereo stream with every window shape as one batch and as chained ragged batches."""
+    import subprocess, sys
+    code = ("import sys, os; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, helpers as H\nfrom nvorbis_b200 import capi\n"
+            "r, pcm, b = H.decoded('3test')\nctx = capi.Context(0); ctx.upload_setup(H.setup_from_oracle(r))\n"
+            "hb = H.batch_from_boundary(b, ctx.post_stride)\nout, _ = ctx.decode_batch(hb)\n"
+            "assert float(np.abs(out - pcm).max()) <= 1e-5\n"
+            "parts = []\nctx.reset()\n"
+            "for lo, hi in ((0, 37), (37, 38), (38, 200), (200, len(b.frames))):\n"
+            "    o, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, lo, hi), capi.RUN_CONTINUE if lo else 0)\n    parts.append(o.copy())\n"
+            "np.save(sys.argv[1], np.concatenate([out, np.concatenate(parts)]))\nprint('ok')\n") % (H.ROOT, os.path.join(H.ROOT, "tests"))
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        outs = []
+        for k, extra in enumerate(({}, {"NVB_FUSED_SLOTS": "3", "NVB_FUSED_SKEW": "1"}, {"NVB_FUSED_SLOTS": "4", "NVB_FUSED_SKEW": "5"},
+                                   {"NVB_FUSED_SLOTS": "3", "NVB_FUSED_SKEW": "16"})):
+            env = dict(os.environ); env.update(extra)
+            path = os.path.join(td, f"o{k}.npy")
+            assert subprocess.check_output([sys.executable, "-c", code, path], env=env, timeout=600).decode().strip().endswith("ok")
+            outs.append(np.load(path))
+        for o in outs[1:]:
+            np.testing.assert_array_equal(o, outs[0])
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
