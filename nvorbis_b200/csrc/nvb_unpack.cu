@@ -33,13 +33,19 @@ __device__ __forceinline__ void prefetch_l1_u(const void* p) { asm volatile("pre
 // Bit cursor over one packet, LSB first (DataPacket.cs:150-283): reading past the end yields zero bits and raises short_.
 // The packet store is padded, so the two aligned words around any position inside a packet can always be loaded.
 struct DBits {
-    const uint8_t* base; uint32_t nbits, pos; bool short_;
+    const uint32_t* words; uint32_t bit0;       // aligned word that holds the packet's first byte, bit offset of that byte inside it
+    uint32_t nbits, pos; bool short_;
+    uint32_t lo, hi, cur;                       // the two words around the cursor, cached: reloaded once per 32 bits, not per codeword
+    __device__ __forceinline__ void open(const uint8_t* base, uint32_t bytes) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(base);
+        words = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3)); bit0 = (uint32_t)(addr & 3) * 8u;
+        nbits = bytes * 8u; pos = 0u; short_ = false; cur = 0xffffffffu; lo = hi = 0u;
+    }
     __device__ __forceinline__ uint32_t left() const { return pos < nbits ? nbits - pos : 0u; }
-    __device__ __forceinline__ uint32_t peek32() const {
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(base) + (pos >> 3);
-        const uint32_t* a = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
-        const uint32_t w0 = a[0], w1 = a[1];
-        uint32_t v = nvb_funnel_r(w0, w1, (uint32_t)(addr & 3) * 8u + (pos & 7u));
+    __device__ __forceinline__ uint32_t peek32() {
+        const uint32_t at = bit0 + pos, idx = at >> 5;
+        if (idx != cur) { lo = words[idx]; hi = words[idx + 1]; cur = idx; }
+        uint32_t v = nvb_funnel_r(lo, hi, at & 31u);
         const uint32_t l = left();
         if (l < 32u) v = l ? (v & ((1u << l) - 1u)) : 0u;
         return v;
@@ -54,9 +60,9 @@ struct DBits {
     }
 };
 
-// Codebook.DecodeScalar (Codebook.cs:294-320): -1 when no bit is left or no codeword matches.
-__device__ __forceinline__ int book_decode(const UnpackTables& T, int bk, DBits& b) {
-    const nvbu::UBook B = T.books[bk];
+// Codebook.DecodeScalar (Codebook.cs:294-320): -1 when no bit is left or no codeword matches.  B: the book's record, loaded by
+// the caller once per run of codewords of that book.
+__device__ __forceinline__ int book_decode(const UnpackTables& T, const nvbu::UBook& B, DBits& b) {
     if (!B.decodable || b.left() == 0u) return -1;
     const uint32_t v = b.peek32();
     const uint32_t r = T.roots[B.root_off + (v & ((1u << B.root_bits) - 1u))];
@@ -73,7 +79,8 @@ __device__ __forceinline__ int book_decode(const UnpackTables& T, int bk, DBits&
 
 constexpr int UNPACK_WARPS = 4;                                          // packets per CTA: one warp each
 
-__global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a) {
+__global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a, int smem_cls) {
+    NVB_DYN_SMEM(dyn_smem);
     nvb_grid_dep_launch();
     const int fi = blockIdx.x * UNPACK_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     nvb_grid_dep_wait();                                                    // the record buffers may still be read by the previous batch's kernels
@@ -97,12 +104,15 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a) {
         for (uint32_t o = p0 + 128u * lane; o < p1; o += 128u * 32u) prefetch_l1_u(a.data + o);
         int16_t* posts = a.posts + (size_t)api * C * T.post_stride;
         for (int k = lane; k < C * T.post_stride; k += 32) posts[k] = 0;
-        uint8_t* cls0 = a.classes + (size_t)api * T.cls_stride;
+        // the class bytes are read back partition by partition while the stages are walked: they live in shared memory during
+        // the walk (when the setup's stride fits) and are copied out by the whole warp at the end
+        uint8_t* cls0 = smem_cls ? dyn_smem + (size_t)(threadIdx.x >> 5) * T.cls_stride : a.classes + (size_t)api * T.cls_stride;
         for (int k = lane; k < ncls; k += 32) cls0[k] = 0;
     }
     __syncwarp();
-    if (lane != 0) return;
-    DBits b; b.base = a.data + p0; b.nbits = (p1 - p0) * 8u; b.pos = 0u; b.short_ = false;
+    int n_cls_out = 0;
+    if (lane == 0) {
+    DBits b; b.open(a.data + p0, p1 - p0);
     // the host already read the packet type bit, the mode number and the window flags (Mode.cs:119-151): skip them
     b.skip(1u + (uint32_t)T.mode_bits + (mode.block_flag ? 2u : 0u));
 
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a) {
                 const int cls = f.part_class[p], cdim = f.class_dims[cls], cbits = f.class_subs[cls];
                 uint32_t cval = 0u;
                 if (cbits > 0) {
-                    const int v = book_decode(T, f.class_master[cls], b);
+                    const int v = book_decode(T, T.books[f.class_master[cls]], b);
                     if (v < 0) { failed = true; break; }
                     cval = (uint32_t)v;
                 }
@@ -128,7 +138,7 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a) {
                     const int bk = f.sub_books[cls][cval & ((1u << cbits) - 1u)];
                     cval >>= cbits;
                     int y = 0;
-                    if (bk >= 0) { y = book_decode(T, bk, b); if (y < 0) { failed = true; break; } }
+                    if (bk >= 0) { y = book_decode(T, T.books[bk], b); if (y < 0) { failed = true; break; } }
                     dst[1 + count] = (int16_t)y;
                     ++count;
                 }
@@ -153,15 +163,17 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a) {
     if (nn > 0 && no_exec != all) {
         res_decoded = 1;
         const int P = nn / r.psize, S = r.type == 2 ? 1 : C;
-        uint8_t* cls = a.classes + (size_t)api * T.cls_stride;
+        uint8_t* cls = smem_cls ? dyn_smem + (size_t)(threadIdx.x >> 5) * T.cls_stride : a.classes + (size_t)api * T.cls_stride;
         uint16_t* ent = a.entries + (size_t)api * T.ent_stride;
+        n_cls_out = S * P;
         const uint8_t* digits = T.digits + r.digits_off;
+        const nvbu::UBook cbook = T.books[r.class_book];
         bool stop = false;
         for (int stage = 0; stage < r.stages && !stop; stage++) {
             for (int p = 0; p < P && !stop;) {
                 if (stage == 0) {
                     for (int st = 0; st < S; st++) {
-                        const int w = book_decode(T, r.class_book, b);
+                        const int w = book_decode(T, cbook, b);
                         if (w < 0 || w >= r.partvals) { stop = true; break; }
                         for (int k = 0; k < r.cdims && p + k < P; k++) cls[st * P + p + k] = digits[w * r.cdims + k];
                     }
@@ -173,15 +185,16 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a) {
                         if (!((r.cascade[cl] >> stage) & 1)) continue;
                         const int bk = r.books[cl][stage];
                         if (bk < 0) continue;
-                        const int dims = T.books[bk].dims;
+                        const nvbu::UBook vbook = T.books[bk];
+                        const int dims = vbook.dims;
                         if (r.type == 0) {
                             // all of a partition's entries are read before any is used (Residue0.cs:186-192): they only count once complete
                             const int steps = r.psize / dims;
-                            for (int q = 0; q < steps; q++) { const int e = book_decode(T, bk, b); if (e < 0) { stop = true; break; } ent[n_ent + q] = (uint16_t)e; }
+                            for (int q = 0; q < steps; q++) { const int e = book_decode(T, vbook, b); if (e < 0) { stop = true; break; } ent[n_ent + q] = (uint16_t)e; }
                             if (!stop) n_ent += (uint32_t)steps;
                         } else {
                             for (int q = 0; q < r.psize; q += dims) {              // Residue1.cs:12-23, Residue2.cs:29-44
-                                const int e = book_decode(T, bk, b);
+                                const int e = book_decode(T, vbook, b);
                                 if (e < 0) { stop = true; break; }
                                 ent[n_ent++] = (uint16_t)e;
                             }
@@ -192,11 +205,21 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a) {
         }
     }
     df->exec_mask = exec; df->res_decoded = (uint8_t)res_decoded; df->entry_count = n_ent;
+    }
+    __syncwarp();
+    if (smem_cls) {
+        n_cls_out = __shfl_sync(0xffffffffu, n_cls_out, 0);
+        const uint8_t* src = dyn_smem + (size_t)(threadIdx.x >> 5) * T.cls_stride;
+        uint8_t* dst = a.classes + (size_t)api * T.cls_stride;
+        for (int k = lane; k < n_cls_out; k += 32) dst[k] = src[k];
+    }
 }
 
 int launch_unpack(const UnpackArgs& a, void* stream) {
     if (a.n_frames <= 0) return 0;
-    NVB_LAUNCH(k_unpack, (a.n_frames + UNPACK_WARPS - 1) / UNPACK_WARPS, UNPACK_WARPS * 32, 0, stream, a);
+    const size_t smem = (size_t)UNPACK_WARPS * (size_t)a.T.cls_stride;
+    const int smem_cls = smem <= 40 * 1024 ? 1 : 0;
+    NVB_LAUNCHV(k_unpack, (a.n_frames + UNPACK_WARPS - 1) / UNPACK_WARPS, UNPACK_WARPS * 32, smem_cls ? smem : 0, stream, a, smem_cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Summarise an `ncu --page source --csv --print-source sass` dump: stall reasons, instruction mix, hot instructions."""
+"""Summarise an `ncu --page source --csv --print-source sass` dump: stall reasons, instruction mix, hot instructions.
+A dump can hold several functions (template instantiations of one kernel): only the FIRST function section is summarised --
+round 1 summed them all, which multiplied "total warp inst" by the number of instantiations and listed hot rows twice."""
 import csv, sys
 from collections import Counter
 rows = list(csv.reader(open(sys.argv[1])))
@@ -9,8 +11,12 @@ def num(x):
     try: return int(float(x))
     except Exception: return 0
 tot = Counter(); total = 0; data = []; mix = Counter()
+seen = set()
 for r in rows[2:]:
+    if len(r) >= 1 and r[0] in ('Function Name', 'Address') and data: break          # the next function's section starts
     if len(r) < len(hdr) or r[0] == 'Address' or not r[0].startswith('0x'): continue
+    if r[0] in seen: continue                                                         # an address listed twice
+    seen.add(r[0])
     s = num(r[ix['# Samples']]); total += s
     for k in stalls: tot[k] += num(r[ix[k]])
     n = num(r[ix['Instructions Executed']])
