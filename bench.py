@@ -26,8 +26,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "audio frames/sec (blocksize 2048, stereo)"
 FRAMES_PER_STEP = 4096
-ROTATE = 6                      # batch sets rotated through so that the working set (~70 MB each) exceeds the 126 MB L2 (even: a set stays on one stream)
-STREAMS = 2                     # device-resident loop: consecutive batches alternate between two CUDA streams (the kernels of one batch fill the launch / drain gaps of the other)
+STREAMS = int(os.environ.get("NVB_BENCH_STREAMS", "2"))    # device-resident loop: consecutive batches alternate between CUDA streams (the kernels of one batch fill the launch / drain gaps of the other)
+ROTATE = 6 if STREAMS in (1, 2, 3, 6) else 2 * STREAMS      # batch sets rotated through so that the working set (~70 MB each) exceeds the 126 MB L2 (a multiple of STREAMS: a set stays on one stream)
 SEED = 20240002
 STRONG_FRAMES = 65536           # BASELINE configs[4] / north_star: the corpus of the strong-scaling figure
 MIN_TIMED_S = float(os.environ.get("NVB_BENCH_MIN_S", "0.5"))               # every timed loop is repeated (K steps per repetition, own event pair) until this much device time is measured

@@ -46,6 +46,19 @@ typedef struct nvh_info {
  * NVB_ERR_DATA where the reference throws InvalidDataException. */
 int nvh_open_ogg(const uint8_t* data, size_t len, nvh_stream** out);
 int nvh_open_packets(const uint8_t* data, const int64_t* sizes, const int64_t* granules, const uint8_t* flags, int64_t n, nvh_stream** out);
+/* Containers with several logical streams (multiplexed or chained; VorbisReader.Streams / SwitchStreams, VorbisReader.cs:96-150):
+ * how many there are (by serial number, in order of appearance), and opening the one with a given index.  A stream that is
+ * not Vorbis fails with NVB_ERR_DATA like any other bad header.  nvh_open_ogg = index 0. */
+int nvh_ogg_stream_count(const uint8_t* data, size_t len);
+int nvh_open_ogg_stream(const uint8_t* data, size_t len, int stream_index, nvh_stream** out);
+/* Forward-only input (Ogg/ForwardOnlyPageReader.cs, ForwardOnlyPacketProvider.cs: a stream that cannot seek), in feed form:
+ * nvh_open_forward creates an empty stream, nvh_feed appends the next container bytes (any chunking; end_of_input = 1 with
+ * the last chunk) and returns the number of audio packets demuxed so far (0 until the three header packets are complete;
+ * nvh_get_info / nvh_setup are valid from then on).  Pages and continued packets that are not complete yet wait for more
+ * input; nvh_unpack / nvh_packet_batch hand out what is available and only report the end of the stream (and drain the last
+ * tail) once the input has ended.  nvh_seek / nvh_rewind are not available on such a stream before its input has ended. */
+int nvh_open_forward(nvh_stream** out);
+int64_t nvh_feed(nvh_stream* s, const uint8_t* data, size_t len, int end_of_input);
 int nvh_close(nvh_stream* s);
 const char* nvh_last_error(nvh_stream* s);       /* s may be NULL: error of the last failed open on this thread */
 

@@ -229,6 +229,33 @@ struct UnpackedFrame {                 // one packet's result before concatenati
     int64_t granule = 0; bool has_granule = false, eos = false, resync = false;
 };
 
+// Ogg container: pages -> packets of one logical stream, incrementally (the whole image at once is the one-call case).
+// Ogg/PageReaderBase.cs:33-111,227-292 (sync + CRC), Ogg/PageReader.cs:27-93,125-158 (lacing; zero-length packets
+// and packet-less pages are dropped), Ogg/StreamPageReader.cs:44-90 (EOS page, sequence gaps = resync),
+// Ogg/PacketProvider.cs:324-438 (continuations; granule on the last packet completed in a page; EOS flag).
+// scan() turns the bytes seen so far into page records, emit() turns complete pages into packets; with final == false both
+// stop where more input could still change the answer (a page or a continued packet that is not complete yet) -- the
+// forward-only reader (Ogg/ForwardOnlyPageReader.cs, ForwardOnlyPacketProvider.cs) in feed form.
+struct OggDemux {
+    struct Piece { size_t off, size; };
+    struct PageInfo { int64_t granule; bool resync, continued, continuation, eos; std::vector<Piece> pieces; };
+    uint32_t crc_table[256];
+    std::vector<PageInfo> pages;
+    size_t i = 0; bool lost_sync = false, have_serial = false, done = false; uint32_t serial = 0; int32_t last_seq = 0;
+    size_t pi = 0, k = 0;                                                     // packet cursor: (page, piece)
+    OggDemux() {
+        for (uint32_t n = 0; n < 256; n++) {                                                          // Ogg/Crc.cs:8-21
+            uint32_t r = n << 24;
+            for (int b = 0; b < 8; b++) r = (r << 1) ^ ((r & 0x80000000u) ? 0x04c11db7u : 0u);
+            crc_table[n] = r;
+        }
+    }
+    void want(uint32_t sn) { have_serial = true; serial = sn; }
+
+    void scan(const uint8_t* d, size_t len, bool final, nvh_stream& s);
+    void emit(const uint8_t* d, bool final, nvh_stream& s);
+};
+
 }  // namespace nvh
 
 using namespace nvh;
@@ -256,6 +283,9 @@ struct nvh_stream {
     std::vector<float> o_floor0;
     // GPU-side unpack: the tables blob (built on demand) and the last packet batch
     std::vector<uint8_t> u_blob; std::vector<uint32_t> o_offsets; std::vector<uint8_t> o_pad;
+    // forward-only (feed) mode: the container bytes seen so far, the incremental demuxer, whether the input has ended
+    bool forward = false, input_final = true, headers_done = false;
+    std::vector<uint8_t> raw; OggDemux demux;
 };
 
 namespace nvh {
@@ -266,27 +296,44 @@ static thread_local std::string g_open_error;
 // Ogg/PageReaderBase.cs:33-111,227-292 (sync + CRC), Ogg/PageReader.cs:27-93,125-158 (lacing; zero-length packets
 // and packet-less pages are dropped), Ogg/StreamPageReader.cs:44-90 (EOS page, sequence gaps = resync),
 // Ogg/PacketProvider.cs:324-438 (continuations; granule on the last packet completed in a page; EOS flag).
-static void demux_ogg(const uint8_t* d, size_t len, nvh_stream& s) {
+// Serial numbers of the logical streams of a container, in the order their first pages appear (multiplexed or chained
+// streams: ContainerReader raises NewStreamCallback per serial, Ogg/ContainerReader.cs).  Pages with a bad CRC are skipped as
+// the page reader does.
+static std::vector<uint32_t> ogg_serials(const uint8_t* d, size_t len) {
     uint32_t crc_table[256];
-    for (uint32_t i = 0; i < 256; i++) {                                                              // Ogg/Crc.cs:8-21
-        uint32_t r = i << 24;
-        for (int k = 0; k < 8; k++) r = (r << 1) ^ ((r & 0x80000000u) ? 0x04c11db7u : 0u);
-        crc_table[i] = r;
-    }
-    struct Piece { size_t off, size; };
-    struct PageInfo { int64_t granule; bool resync, continued, continuation, eos; std::vector<Piece> pieces; };
-    std::vector<PageInfo> pages;
-    size_t i = 0; bool lost_sync = false, have_serial = false, done = false; uint32_t serial = 0; int32_t last_seq = 0;
-    while (!done && i + 27 <= len) {
-        if (std::memcmp(d + i, "OggS", 4) != 0 || d[i + 4] != 0) { ++i; lost_sync = true; continue; }
+    for (uint32_t i = 0; i < 256; i++) { uint32_t r = i << 24; for (int k = 0; k < 8; k++) r = (r << 1) ^ ((r & 0x80000000u) ? 0x04c11db7u : 0u); crc_table[i] = r; }
+    std::vector<uint32_t> out;
+    size_t i = 0;
+    while (i + 27 <= len) {
+        if (std::memcmp(d + i, "OggS", 4) != 0 || d[i + 4] != 0) { ++i; continue; }
         const int nseg = d[i + 26];
-        if (i + 27 + (size_t)nseg > len) { ++i; lost_sync = true; continue; }
+        if (i + 27 + (size_t)nseg > len) { ++i; continue; }
         size_t body = 0; for (int k = 0; k < nseg; k++) body += d[i + 27 + k];
         const size_t total = 27 + (size_t)nseg + body;
-        if (i + total > len) { ++i; lost_sync = true; continue; }
+        if (i + total > len) { ++i; continue; }
         uint32_t crc = 0;
-        for (size_t k = 0; k < total; k++) {
-            const uint8_t byte = (k >= 22 && k < 26) ? 0 : d[i + k];
+        for (size_t k = 0; k < total; k++) { const uint8_t byte = (k >= 22 && k < 26) ? 0 : d[i + k]; crc = (crc << 8) ^ crc_table[byte ^ (crc >> 24)]; }
+        uint32_t stored; std::memcpy(&stored, d + i + 22, 4);
+        if (crc != stored) { ++i; continue; }
+        uint32_t serial; std::memcpy(&serial, d + i + 14, 4);
+        if (std::find(out.begin(), out.end(), serial) == out.end()) out.push_back(serial);
+        i += total;
+    }
+    return out;
+}
+
+void OggDemux::scan(const uint8_t* d, size_t len, bool final, nvh_stream& s) {
+    while (!done) {
+        if (i + 27 > len) { if (final) i = len; break; }
+        if (std::memcmp(d + i, "OggS", 4) != 0 || d[i + 4] != 0) { ++i; lost_sync = true; continue; }
+        const int nseg = d[i + 26];
+        if (i + 27 + (size_t)nseg > len) { if (!final) break; ++i; lost_sync = true; continue; }
+        size_t body = 0; for (int n = 0; n < nseg; n++) body += d[i + 27 + n];
+        const size_t total = 27 + (size_t)nseg + body;
+        if (i + total > len) { if (!final) break; ++i; lost_sync = true; continue; }
+        uint32_t crc = 0;
+        for (size_t n = 0; n < total; n++) {
+            const uint8_t byte = (n >= 22 && n < 26) ? 0 : d[i + n];
             crc = (crc << 8) ^ crc_table[byte ^ (crc >> 24)];
         }
         uint32_t stored; std::memcpy(&stored, d + i + 22, 4);
@@ -297,8 +344,8 @@ static void demux_ogg(const uint8_t* d, size_t len, nvh_stream& s) {
         const uint8_t flags = d[i + 5];
         PageInfo pg; pg.granule = granule; pg.continuation = flags & 1; pg.eos = (flags & 4) != 0; pg.continued = false;
         size_t off = i + 27 + (size_t)nseg, run = 0;
-        for (int k = 0; k < nseg; k++) {
-            const int seg = d[i + 27 + k]; run += (size_t)seg;
+        for (int n = 0; n < nseg; n++) {
+            const int seg = d[i + 27 + n]; run += (size_t)seg;
             if (seg < 255) { if (run) { pg.pieces.push_back(Piece{off, run}); off += run; } run = 0; }
         }
         if (run) { pg.pieces.push_back(Piece{off, run}); pg.continued = d[i + 26 + nseg] == 255; }
@@ -312,8 +359,11 @@ static void demux_ogg(const uint8_t* d, size_t len, nvh_stream& s) {
         if (pg.eos) { s.has_eos = true; done = true; }
         pages.push_back(std::move(pg));
     }
-    // packets: a (page, piece) cursor advanced the way PacketProvider.CreatePacket does (:411-434)
-    size_t pi = 0, k = 0;
+}
+
+// packets: a (page, piece) cursor advanced the way PacketProvider.CreatePacket does (:411-434)
+void OggDemux::emit(const uint8_t* d, bool final, nvh_stream& s) {
+    const bool complete = final || done;                      // no further page can arrive
     while (pi < pages.size()) {
         const PageInfo& pg = pages[pi];
         PacketRef pr; pr.off = s.bytes.size(); pr.flags = 0; pr.granule = 0;
@@ -324,7 +374,11 @@ static void demux_ogg(const uint8_t* d, size_t len, nvh_stream& s) {
         if (last_piece && pg.continued) {
             bool cont = true; size_t cp = pi;
             while (cont) {
-                if (++cp >= pages.size()) { s.bytes.resize(pr.off); return; }                    // cannot complete: no packet (:346-350)
+                if (++cp >= pages.size()) {                                                       // the rest has not arrived (or never will: no packet, :346-350)
+                    s.bytes.resize(pr.off);
+                    if (complete) pi = pages.size();
+                    return;
+                }
                 const PageInfo& nx = pages[cp];
                 granule = nx.granule; resync = nx.resync; cont = nx.continued; final_pieces = nx.pieces.size();
                 if (!nx.continuation || nx.resync) break;                                         // broken chain: keep what we have (:354-357)
@@ -344,6 +398,14 @@ static void demux_ogg(const uint8_t* d, size_t len, nvh_stream& s) {
         if (final_page != pi) { pi = final_page; k = 0; }
         if (k + 1 == final_pieces) { ++pi; k = 0; } else ++k;
     }
+}
+
+// The whole container image at once.  want_serial: decode the logical stream with this serial number (has_want) or the first one met.
+static void demux_ogg(const uint8_t* d, size_t len, nvh_stream& s, bool has_want = false, uint32_t want_serial = 0) {
+    OggDemux dm;
+    if (has_want) dm.want(want_serial);
+    dm.scan(d, len, true, s);
+    dm.emit(d, true, s);
 }
 
 static void parse_id_header(Bits& b, nvh_stream& s) {                                                 // StreamDecoder.cs:179-204
@@ -756,7 +818,7 @@ static int order_step(nvh_stream* s, UnpackedFrame& uf) {
 static void stream_order_pass(nvh_stream* s, std::vector<UnpackedFrame>& metas, size_t next_packet, bool wanted_more, int32_t* end_of_stream) {
     for (UnpackedFrame& uf : metas) { order_step(s, uf); s->o_frames.push_back(uf.f); }
     s->next_packet = next_packet;
-    if (s->next_packet >= s->packets.size() && wanted_more) {
+    if (s->next_packet >= s->packets.size() && wanted_more && (!s->forward || s->input_final)) {
         // the provider ran dry: DecodeNextPacket returns null with isEndOfStream = true (StreamDecoder.cs:476-480)
         if (!s->eos_found) {
             nvb_frame f; std::memset(&f, 0, sizeof f); f.status = NVB_FRAME_FAILED;
@@ -924,6 +986,47 @@ int nvh_open_ogg(const uint8_t* data, size_t len, nvh_stream** out) {
     return finish_open(s, out);
 }
 
+int nvh_open_forward(nvh_stream** out) {
+    if (!out) { g_open_error = "NULL argument"; return NVB_ERR_ARG; }
+    nvh_stream* s = new (std::nothrow) nvh_stream();
+    if (!s) return NVB_ERR_NOMEM;
+    s->forward = true; s->input_final = false; s->headers_done = false;
+    *out = s;
+    return NVB_OK;
+}
+
+int64_t nvh_feed(nvh_stream* s, const uint8_t* data, size_t len, int end_of_input) {
+    if (!s || !s->forward || (len > 0 && !data)) return NVB_ERR_ARG;
+    if (s->input_final) { s->err = "nvh_feed after the end of the input"; return NVB_ERR_STATE; }
+    try {
+        s->raw.insert(s->raw.end(), data, data + len);
+        if (end_of_input) s->input_final = true;
+        s->demux.scan(s->raw.data(), s->raw.size(), s->input_final, *s);
+        s->demux.emit(s->raw.data(), s->input_final, *s);
+        if (!s->headers_done && s->packets.size() >= 3) { open_common(*s); s->headers_done = true; }
+        if (!s->headers_done && s->input_final) { s->err = "Could not find Vorbis data to decode."; return NVB_ERR_DATA; }
+        return s->headers_done ? (int64_t)(s->packets.size() - s->first_audio) : 0;
+    } catch (const std::bad_alloc&) { s->err = "nvh_feed: out of memory"; return NVB_ERR_NOMEM; }
+    catch (const std::exception& e) { s->err = e.what(); return NVB_ERR_DATA; }
+}
+
+int nvh_ogg_stream_count(const uint8_t* data, size_t len) {
+    if (!data) return NVB_ERR_ARG;
+    try { return (int)ogg_serials(data, len).size(); } catch (...) { return NVB_ERR_NOMEM; }
+}
+
+int nvh_open_ogg_stream(const uint8_t* data, size_t len, int stream_index, nvh_stream** out) {
+    if (!data || !out || stream_index < 0) { g_open_error = "NULL argument / negative stream index"; return NVB_ERR_ARG; }
+    *out = nullptr;
+    std::unique_ptr<nvh_stream> s(new nvh_stream());
+    try {
+        const std::vector<uint32_t> serials = ogg_serials(data, len);
+        if ((size_t)stream_index >= serials.size()) { g_open_error = "the container has no logical stream with that index"; return NVB_ERR_ARG; }
+        demux_ogg(data, len, *s, true, serials[(size_t)stream_index]);
+    } catch (const std::exception& e) { g_open_error = e.what(); return NVB_ERR_DATA; }
+    return finish_open(s, out);
+}
+
 int nvh_open_packets(const uint8_t* data, const int64_t* sizes, const int64_t* granules, const uint8_t* flags, int64_t n, nvh_stream** out) {
     if (!data || !sizes || !granules || !flags || !out || n < 0) { g_open_error = "NULL argument"; return NVB_ERR_ARG; }
     *out = nullptr;
@@ -1055,6 +1158,7 @@ int64_t nvh_total_samples(nvh_stream* s) {
 
 int nvh_seek(nvh_stream* s, int64_t sample_position, int64_t* skip_samples) {
     if (!s || !skip_samples || sample_position < 0) return NVB_ERR_ARG;
+    if (s->forward && !s->input_final) { s->err = "a forward-only stream cannot seek before its input has ended"; return NVB_ERR_STATE; }
     try {
         std::vector<int> e; std::vector<int64_t> pos; std::vector<uint8_t> hp;
         emitted_per_packet(s, e, pos, hp);

@@ -32,6 +32,10 @@ def load_library(path: str | None = None):
         vp = C.c_void_p
         L.nvh_open_ogg.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
         L.nvh_open_packets.argtypes = [vp, vp, vp, vp, C.c_int64, C.POINTER(vp)]
+        L.nvh_open_forward.argtypes = [C.POINTER(vp)]
+        L.nvh_feed.restype = C.c_int64; L.nvh_feed.argtypes = [vp, vp, C.c_size_t, C.c_int]
+        L.nvh_ogg_stream_count.argtypes = [vp, C.c_size_t]
+        L.nvh_open_ogg_stream.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp)]
         L.nvh_close.argtypes = [vp]
         L.nvh_last_error.restype = C.c_char_p; L.nvh_last_error.argtypes = [vp]
         L.nvh_get_info.argtypes = [vp, C.POINTER(Info)]
@@ -63,30 +67,60 @@ class SetupView:
         self._owner = owner
 
 
+def ogg_stream_count(data) -> int:
+    """Logical streams (serial numbers) of an Ogg container image."""
+    a = np.frombuffer(bytes(data), np.uint8)
+    n = load_library().nvh_ogg_stream_count(a.ctypes.data, a.size)
+    if n < 0:
+        raise HostError(f"nvh_ogg_stream_count: status {n}")
+    return int(n)
+
+
 class HostStream:
     """The unpacking half of a StreamDecoder over an Ogg file image or a packet list."""
 
-    def __init__(self, data=None, packets=None):
+    def __init__(self, data=None, packets=None, stream_index: int = 0, forward: bool = False):
         L = load_library()
         h = C.c_void_p()
+        if forward:                                     # forward-only input: bytes arrive through feed()
+            rc = L.nvh_open_forward(C.byref(h))
+            if rc != 0:
+                raise HostError(f"nvh_open_forward: status {rc}")
+            self.lib, self.handle, self.info = L, h, None
+            self.channels = self.sample_rate = self.post_stride = self.floor0_stride = self.n_audio_packets = 0
+            self.block_size = (0, 0)
+            return
         if packets is not None:
             d, sizes, gran, flags = (np.ascontiguousarray(packets[0], np.uint8), np.ascontiguousarray(packets[1], np.int64),
                                      np.ascontiguousarray(packets[2], np.int64), np.ascontiguousarray(packets[3], np.uint8))
             rc = L.nvh_open_packets(d.ctypes.data, sizes.ctypes.data, gran.ctypes.data, flags.ctypes.data, len(sizes), C.byref(h))
         else:
             self._data = np.frombuffer(bytes(data), np.uint8)
-            rc = L.nvh_open_ogg(self._data.ctypes.data, self._data.size, C.byref(h))
+            rc = L.nvh_open_ogg_stream(self._data.ctypes.data, self._data.size, int(stream_index), C.byref(h))
         if rc != 0:
             raise HostError(f"open failed: status {rc} ({L.nvh_last_error(None).decode()})")
         self.lib, self.handle = L, h
+        self._refresh_info()
+
+    def _refresh_info(self):
         info = Info()
-        L.nvh_get_info(h, C.byref(info))
+        self.lib.nvh_get_info(self.handle, C.byref(info))
         self.info = info
         self.channels, self.sample_rate = info.channels, info.sample_rate
         self.block_size = (info.block_size[0], info.block_size[1])
         self.post_stride = info.post_stride
         self.floor0_stride = info.floor0_stride
         self.n_audio_packets = int(info.n_audio_packets)
+
+    def feed(self, data, end_of_input: bool = False) -> int:
+        """nvh_feed: the next container bytes of a forward-only stream; returns the audio packets demuxed so far."""
+        a = np.frombuffer(bytes(data), np.uint8)
+        n = self.lib.nvh_feed(self.handle, a.ctypes.data if a.size else None, a.size, 1 if end_of_input else 0)
+        if n < 0:
+            raise HostError(f"nvh_feed: status {n} ({self.lib.nvh_last_error(self.handle).decode()})")
+        if n > 0 or self.channels:
+            self._refresh_info()
+        return int(n)
 
     def close(self):
         if self.handle:

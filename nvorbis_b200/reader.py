@@ -16,12 +16,13 @@ class VorbisReader:
     """`new VorbisReader(stream)` ... `ReadSamples(buffer, offset, count)` (VorbisReader.cs:42-64, 336-345)."""
 
     def __init__(self, source, device: int = 0, batch_packets: int = 4096, clip_samples: bool = True,
-                 unpack_threads: int = 0, lib_path: str | None = None, gpu_unpack: bool | None = None):
+                 unpack_threads: int = 0, lib_path: str | None = None, gpu_unpack: bool | None = None, stream_index: int = 0):
+        # stream_index: which logical stream of a multi-stream container (VorbisReader.Streams / SwitchStreams, VorbisReader.cs:96-150)
         if isinstance(source, (bytes, bytearray, memoryview)):
-            self._host = hostlib.HostStream(data=bytes(source))
+            self._host = hostlib.HostStream(data=bytes(source), stream_index=stream_index)
         elif isinstance(source, str):
             with open(source, "rb") as f:
-                self._host = hostlib.HostStream(data=f.read())
+                self._host = hostlib.HostStream(data=f.read(), stream_index=stream_index)
         else:                                   # (data, sizes, granules, flags): an IPacketProvider's packets
             self._host = hostlib.HostStream(packets=tuple(source))
         self._ctx = capi.Context(device, lib_path=lib_path)

@@ -327,3 +327,31 @@ def test_pcm_s16_and_device_out(shim):
     ctx.decode_batch_ptr(hb, capi.RUN_EXACT | capi.RUN_DEVICE_OUT | capi.RUN_PCM_S16, dev16.ctypes.data, dev16.size)
     np.testing.assert_array_equal(dev16[: want.size], _s16(want))
     assert (dev16[want.size:] == 7).all()
+
+
+def test_wave_writer_mirror(shim, tmp_path):
+    """TestApp's pipeline (Program.cs:12-28 + WaveWriter.cs): stream -> ReadSamples -> float WAV; the header fields, the sizes
+    patched on close, the reference's offset-44 quirk when asked for, and the 16-bit form."""
+    import struct, wave as pywave
+    from nvorbis_b200 import wave as W
+    pl = H.packets("1test")
+    r, pcm, b = H.decoded("1test")
+    p = str(tmp_path / "o.wav")
+    n = W.decode_to_wav((pl.data, pl.sizes, pl.granules, pl.flags), p, lib_path=shim, batch_packets=11)
+    raw = open(p, "rb").read()
+    assert n == pcm.size and raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and raw[38:42] == b"data"
+    fmt_size, enc, ch, rate, bps, align, bits, extra = struct.unpack("<ihhiihhh", raw[16:38])
+    assert (fmt_size, enc, ch, rate, bps, align, bits, extra) == (18, 3, 1, 44100, 4 * 44100, 4, 32, 0)
+    assert struct.unpack("<I", raw[4:8])[0] == len(raw) - 8 and struct.unpack("<I", raw[42:46])[0] == len(raw) - 46
+    assert np.abs(np.frombuffer(raw[46:], "<f4") - pcm).max() <= 1e-5
+    q = str(tmp_path / "q.wav")
+    with W.WaveWriter(q, 44100, 1, reference_quirk=True) as ww:
+        ww.write_samples(pcm, 0, pcm.size)
+    rq = open(q, "rb").read()
+    assert struct.unpack("<I", rq[44:48])[0] == len(rq) - 48 and rq[42:44] == b"\0\0"        # WaveWriter.cs:56-57
+    s = str(tmp_path / "s.wav")
+    W.decode_to_wav((pl.data, pl.sizes, pl.granules, pl.flags), s, sample_format="s16", lib_path=shim)
+    with pywave.open(s, "rb") as wf:                                                            # a valid PCM file for any reader
+        assert (wf.getnchannels(), wf.getsampwidth(), wf.getframerate(), wf.getnframes()) == (1, 2, 44100, pcm.size)
+        got = np.frombuffer(wf.readframes(wf.getnframes()), "<i2")
+    assert np.abs(got.astype(np.int32) - _s16(pcm).astype(np.int32)).max() <= 1

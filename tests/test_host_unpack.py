@@ -105,3 +105,68 @@ def test_malformed_headers_are_rejected():
         hostlib.HostStream(packets=(data, pl.sizes, pl.granules, pl.flags))
     with pytest.raises(hostlib.HostError):
         hostlib.HostStream(data=b"not an ogg file at all")
+
+
+def test_multi_stream_container():
+    """Two logical streams in one container (pages of different serial numbers interleaved, as a multiplexed file has
+    them): nvh_ogg_stream_count sees both, nvh_open_ogg_stream(i) demuxes stream i alone -- same packets, same unpacked
+    records as the stream on its own (VorbisReader.Streams / SwitchStreams, VorbisReader.cs:96-150)."""
+    import re
+    from nvorbis_b200 import hostlib
+    blobs = []
+    for name, serial in (("1test", 0x1111), ("3test", 0x2222)):
+        pl = H.packets(name)
+        off = np.concatenate([[0], np.cumsum(pl.sizes)])
+        pk = [(pl.data[off[i]:off[i + 1]].tobytes(), int(pl.granules[i]), int(pl.flags[i])) for i in range(len(pl.sizes))]
+        blobs.append(H.mux_ogg(pk, serial=serial, page_payload=1500))
+    # split both byte streams into pages and interleave them two to one
+    pages = [[m.start() for m in re.finditer(b"OggS", b)] + [len(b)] for b in blobs]
+    cut = [[b[p[i]:p[i + 1]] for i in range(len(p) - 1)] for b, p in zip(blobs, pages)]
+    mixed, ia, ib = [], 0, 0
+    while ia < len(cut[0]) or ib < len(cut[1]):
+        mixed += cut[1][ib:ib + 2]; ib += 2
+        mixed += cut[0][ia:ia + 1]; ia += 1
+    data = b"".join(mixed)
+    assert hostlib.ogg_stream_count(data) == 2
+    for idx, name in ((1, "1test"), (0, "3test")):                 # 3test's first page comes first in the mix
+        alone = hostlib.HostStream(data=blobs[0 if name == "1test" else 1])
+        both = hostlib.HostStream(data=data, stream_index=idx)
+        assert (both.channels, both.n_audio_packets) == (alone.channels, alone.n_audio_packets)
+        a, _ = alone.unpack(alone.n_audio_packets + 1, threads=1)
+        b, _ = both.unpack(both.n_audio_packets + 1, threads=1)
+        for arr_a, arr_b in ((a.frames, b.frames), (a.posts, b.posts), (a.classes, b.classes), (a.entries, b.entries)):
+            np.testing.assert_array_equal(arr_a, arr_b)
+    with pytest.raises(hostlib.HostError):
+        hostlib.HostStream(data=data, stream_index=2)
+
+
+def test_forward_only_feed_equals_whole_file():
+    """nvh_open_forward / nvh_feed: the container arrives in ragged chunks (pages and continued packets cut anywhere);
+    unpacking whatever is available after every chunk yields, concatenated, exactly the records of the whole-file open."""
+    from nvorbis_b200 import hostlib
+    for name, payload in (("1test", 300), ("3test", 1100)):
+        pl = H.packets(name)
+        off = np.concatenate([[0], np.cumsum(pl.sizes)])
+        pk = [(pl.data[off[i]:off[i + 1]].tobytes(), int(pl.granules[i]), int(pl.flags[i])) for i in range(len(pl.sizes))]
+        ogg = H.mux_ogg(pk, serial=77, page_payload=payload)          # small pages: many packets continue across pages
+        whole = hostlib.HostStream(data=ogg)
+        want, _ = whole.unpack(whole.n_audio_packets + 1, threads=1)
+        fwd = hostlib.HostStream(forward=True)
+        rng = np.random.default_rng(5)
+        pos, frames, posts, classes, entries, eos = 0, [], [], [], [], False
+        while pos < len(ogg):
+            n = int(rng.integers(1, 4000))
+            avail = fwd.feed(ogg[pos:pos + n], end_of_input=pos + n >= len(ogg)); pos += n
+            if avail == 0:
+                continue
+            hb, eos = fwd.unpack(1 << 20, threads=1)
+            f = hb.frames.copy()
+            f["classes_off"] += sum(c.size for c in classes); f["entries_off"] += sum(e.size for e in entries)
+            frames.append(f); posts.append(hb.posts); classes.append(hb.classes); entries.append(hb.entries)
+        assert eos and fwd.n_audio_packets == whole.n_audio_packets
+        np.testing.assert_array_equal(np.concatenate(frames), want.frames)
+        np.testing.assert_array_equal(np.concatenate(posts), want.posts)
+        np.testing.assert_array_equal(np.concatenate(classes), want.classes)
+        np.testing.assert_array_equal(np.concatenate(entries), want.entries)
+        with pytest.raises(hostlib.HostError):
+            fwd.feed(b"x")                                              # the input has ended
