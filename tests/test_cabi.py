@@ -66,3 +66,47 @@ def test_product_does_not_touch_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("import oracle", "from oracle", "oracle/", "libnvorbis_oracle", "orc_"):
                     assert needle not in txt, f"{f} references the oracle ({needle})"
+
+
+def _fnv1a64(b: bytes) -> int:
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def test_blob_import_rejects_tampered_blobs():
+    """nvb_setup_blob_import must establish the invariants the kernels rely on -- a damaged body fails the
+    checksum, a section offset near 2^64 does not wrap past the range check, and a blob whose derived kernel-selection
+    fields were edited (checksum fixed up) is refused because the import recomputes them.  Uses the CPU shim build of the
+    library (nvb_setup_blob_import itself is CUDA-free up to the final upload)."""
+    import struct
+    import helpers as H
+    from nvorbis_b200 import capi
+    shim = H.build_shim()
+    r, pcm, b = H.decoded("3test")
+    ctx = capi.Context(0, lib_path=shim)
+    ctx.upload_setup(H.setup_from_oracle(r))
+    blob = ctx.export_blob()
+    HASH_AT, OFF_VQ_AT, OFF_RES_AT, HDR = 352, 72, 88, 384
+    assert struct.unpack_from("<Q", blob, HASH_AT)[0] == _fnv1a64(blob[HDR:].tobytes())      # the layout this test assumes
+
+    def refused(buf):
+        c2 = capi.Context(0, lib_path=shim)
+        with pytest.raises(capi.NvbError) as e:
+            c2.import_blob(buf)
+        assert e.value.status == capi.ERR_DATA
+        c2.close()
+
+    bad = blob.copy(); bad[HDR + 1000] ^= 1                       # body damage
+    refused(bad)
+    bad = blob.copy(); struct.pack_into("<Q", bad, OFF_VQ_AT, 2 ** 64 - 16)      # off + len would wrap
+    refused(bad)
+    off_res = struct.unpack_from("<Q", blob, OFF_RES_AT)[0]
+    bad = blob.copy()
+    assert struct.unpack_from("<i", bad, off_res + 28)[0] == 3   # DevResidue.fast of 3test's first residue
+    struct.pack_into("<i", bad, off_res + 24, -1)                # pshift = -1 with the run kernels still selected
+    struct.pack_into("<Q", bad, HASH_AT, _fnv1a64(bad[HDR:].tobytes()))
+    refused(bad)
+    ok = capi.Context(0, lib_path=shim); ok.import_blob(blob); ok.close()
+    ctx.close()

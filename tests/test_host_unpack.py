@@ -170,3 +170,71 @@ def test_forward_only_feed_equals_whole_file():
         np.testing.assert_array_equal(np.concatenate(entries), want.entries)
         with pytest.raises(hostlib.HostError):
             fwd.feed(b"x")                                              # the input has ended
+
+
+# ---- malformed setup headers: the parser must refuse them, not overflow / hang / divide by zero ----------
+def _setup_with_books(book_writer, n_books=1):
+    import vorbis_headers as VH
+    w = VH.BitWriter()
+    for b in b"\x05vorbis":
+        w.put(b, 8)
+    w.put(n_books - 1, 8)
+    book_writer(w)
+    return w
+
+
+def _open_headers(setup_bytes):
+    import vorbis_headers as VH
+    from nvorbis_b200 import hostlib
+    pk = [VH.id_header(2, 44100, 256, 2048), VH.comment_header(), setup_bytes]
+    data = np.frombuffer(b"".join(pk), np.uint8).copy()
+    return hostlib.HostStream(packets=(data, np.array([len(p) for p in pk], np.int64), np.zeros(3, np.int64), np.zeros(3, np.uint8)))
+
+
+def test_ordered_codebook_with_lengths_above_32_is_rejected():
+    """First length 32, one entry per group: the second group would be 33 bits long (stack overflow in the decoder builder)."""
+    from nvorbis_b200 import hostlib
+
+    def book(w):
+        w.put(0x564342, 24); w.put(1, 16); w.put(4, 24)
+        w.put(1, 1)                                   # ordered
+        w.put(31, 5)                                  # first length 32
+        w.put(1, 3); w.put(1, 2); w.put(1, 2); w.put(1, 1)      # one entry per length: 32, 33, 34, 35
+        w.put(0, 4)
+    with pytest.raises(hostlib.HostError, match="length above 32|status -7"):
+        _open_headers(_setup_with_books(book).done())
+
+
+def test_truncated_ordered_codebook_does_not_hang():
+    """The packet ends inside the ordered-length list: every count reads as 0 and the reference's loop would never advance."""
+    import signal
+    from nvorbis_b200 import hostlib
+
+    def book(w):
+        w.put(0x564342, 24); w.put(1, 16); w.put(1000, 24)
+        w.put(1, 1); w.put(0, 5)                      # ordered, first length 1 ... and nothing more
+
+    def on_alarm(*_):
+        raise AssertionError("the header parser hangs on a truncated ordered codebook")
+    old = signal.signal(signal.SIGALRM, on_alarm); signal.alarm(10)
+    try:
+        with pytest.raises(hostlib.HostError):
+            _open_headers(_setup_with_books(book).done())
+    finally:
+        signal.alarm(0); signal.signal(signal.SIGALRM, old)
+
+
+def test_value_book_without_dimensions_is_rejected():
+    """dims == 0 with a lookup table: Residue0.cs:183 would divide by it per packet."""
+    from nvorbis_b200 import hostlib
+    import vorbis_headers as VH
+
+    def book(w):
+        w.put(0x564342, 24); w.put(0, 16); w.put(4, 24)        # dims 0
+        w.put(0, 1); w.put(0, 1)
+        for _ in range(4):
+            w.put(1, 5)
+        w.put(2, 4)                                             # lookup type 2
+        w.put(VH.float32_pack(-1.0), 32); w.put(VH.float32_pack(0.5), 32); w.put(3, 4); w.put(0, 1)
+    with pytest.raises(hostlib.HostError):
+        _open_headers(_setup_with_books(book).done())
