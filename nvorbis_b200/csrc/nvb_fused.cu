@@ -127,45 +127,118 @@ __device__ __forceinline__ float slot_z(const DevSetup& S, const DevFrame& f, co
 }
 
 // Output of one frame for every shape the TDAC fast path of k_imdct_fused does not cover (short blocks, window transitions,
-// silent channels, drains, C != 2) and for all of k_imdct_generic: lanes over samples, channels in an inner loop; the index of
-// y[i] inside a slot (fused_y_index) and the window values are per-sample.  slot stride per channel = slot_floats.
+// silent channels, drains, C != 2) and for all of k_imdct_generic: lanes over samples; the index of y[i] inside a slot
+// (fused_y_index) and the window values are per-sample, the channels of the unit an inner loop.  slot stride per channel =
+// slot_floats.  SWZ (k_imdct_fused): the windows come from the two slopes in shared memory (s_tab; round 2: the global window
+// loads put ~400 cycles of latency into every iteration, and a batch with window transitions waits for its slowest frame),
+// a lane takes two samples per step, and a two-channel unit stores float2 per sample.
 template <bool SWZ>
 __device__ __forceinline__ void emit_samples(const LaunchArgs& a, const DevSetup& S, const DevFrame& f, const DevFrame* pf, const float* slots_f,
-                                             const float* slots_p, int slot_floats, int lane, float& peak, int cbase, int G) {
+                                             const float* slots_p, int slot_floats, int lane, float& peak, int cbase, int G, const float* s_tab, int s_lo) {
     const int C = S.channels;                                               // row stride of the interleave; the unit covers channels cbase .. cbase + G - 1
     const int len = f.out_end - f.out_begin;
-    const float* wf = f.kind == 0 ? frame_window(S, f) : nullptr;
-    const float* wp = pf ? frame_window(S, *pf) : nullptr;
+    const float* wf = (!SWZ && f.kind == 0) ? frame_window(S, f) : nullptr;
+    const float* wp = (!SWZ && pf) ? frame_window(S, *pf) : nullptr;
+    const float* s_win = SWZ ? s_tab + FusedTables::WIN : nullptr;
+    const float* s_win0 = SWZ ? s_tab + FusedTables::WIN0 : nullptr;
     const int nf_ = f.n, np_ = pf ? pf->n : 0;
-    const uint32_t ex_f = f.exec_mask, ex_p = pf ? pf->exec_mask : 0u;
+    const int wxf = f.window, wxp = pf ? pf->window : 0;
+    const uint32_t ex_f = f.exec_mask >> cbase, ex_p = pf ? (pf->exec_mask >> cbase) : 0u;
     const bool clip = a.clip != 0;
-    for (int s = lane; s < len; s += 32) {
-        const int i = f.out_begin + s;
-        const int o = i - f.start;
-        const bool ola = f.kind == 0 && f.ola_len > 0 && o >= 0 && o < f.ola_len;          // StreamDecoder.cs:532-541
-        const int ip = f.kind == 0 ? f.prev_valid + o : i;                               // sample of the previous block (overlap or drain)
-        const bool use_p = ola || f.kind != 0;
-        float wv = 0.f, wpv = 0.f;
-        int jf = 0, jp = 0; float sf = 0.f, sp = 0.f;
-        if (f.kind == 0) { wv = wf[i]; fused_y_index(nf_, i, jf, sf, SWZ); }
-        if (use_p && pf) { wpv = wp[ip]; fused_y_index(np_, ip, jp, sp, SWZ); }
-        float* dst = a.pcm + ((size_t)f.pcm_off + s) * C + cbase;
-        for (int c = 0; c < G; c++) {
-            float v = 0.f;
-            if (f.kind == 0) {
-                const float* sl = slots_f + (size_t)c * slot_floats;
-                const float y = ((ex_f >> (cbase + c)) & 1u) ? sf * sl[jf] : (i < (nf_ >> 1) ? sl[i] : 0.f);
-                v = y * wv;
+    const bool cur = f.kind == 0;
+    constexpr int SPL = SWZ ? 2 : 1;                                        // samples per lane and step
+    // The flat part of a long block next to a short one (Mode.cs:24-67: window == 1.0 between the slopes, no overlap from the
+    // previous block): out[i] = y[i] = -u[1535 - i] for 512 <= i < 1536, two samples x two channels per lane and step from two
+    // 8-byte loads.  Window shapes 0 / 1 / 2 have 896 / 448 / 448 such samples; the per-sample path below costs ~4x more.
+    int fl_lo = 0, fl_hi = 0;                                               // sample numbers s (relative to out_begin)
+    if (SWZ && G == 2 && C == 2 && cur && nf_ == FUSED_LONG_N && (ex_f & 3u) == 3u && wxf != 3 && (f.out_begin & 1) == 0) {
+        int i_lo = (wxf & 1) ? 1024 : 576, i_hi = (wxf & 2) ? 1024 : 1472;
+        const int ola_end = f.start + (f.ola_len > 0 ? f.ola_len : 0);
+        if (i_lo < ola_end) i_lo = ola_end;
+        if (i_lo < f.out_begin) i_lo = f.out_begin;
+        if (i_hi > f.out_end) i_hi = f.out_end;
+        i_lo = (i_lo + 1) & ~1;                                             // pairs (i even, i + 1) share one aligned float2 of u
+        i_hi &= ~1;
+        if (i_hi - i_lo >= 64 && i_lo - f.out_begin >= s_lo) {
+            fl_lo = i_lo - f.out_begin; fl_hi = i_hi - f.out_begin;
+            const bool a16 = (((size_t)f.pcm_off + fl_lo) & 1) == 0;        // float4 stores need an even sample offset
+            for (int i = i_lo + 2 * lane; i < i_hi; i += 64) {
+                const int j = u_swz(1534 - i);                              // floats (1534 - i, 1535 - i) = (y[i + 1], y[i]) negated; the swizzle keeps the pair together
+                const float2 u0 = *reinterpret_cast<const float2*>(slots_f + j);
+                const float2 u1 = *reinterpret_cast<const float2*>(slots_f + slot_floats + j);
+                float v0 = -u0.y, v1 = -u1.y, v2 = -u0.x, v3 = -u1.x;       // sample i: (ch0, ch1), sample i + 1: (ch0, ch1)
+                if (clip) { v0 = clipf(v0, peak); v1 = clipf(v1, peak); v2 = clipf(v2, peak); v3 = clipf(v3, peak); }
+                float* dst = a.pcm + ((size_t)f.pcm_off + (i - f.out_begin)) * 2;
+                if (a16) *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
+                else { *reinterpret_cast<float2*>(dst) = make_float2(v0, v1); *reinterpret_cast<float2*>(dst + 2) = make_float2(v2, v3); }
             }
-            if (use_p) {
-                if (pf) {
-                    const float* sl = slots_p + (size_t)c * slot_floats;
-                    const float y = ((ex_p >> (cbase + c)) & 1u) ? sp * sl[jp] : (ip < (np_ >> 1) ? sl[ip] : 0.f);
-                    v += y * wpv;
-                } else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)(cbase + c) * S.bs[1] + ip];
+        }
+    }
+    for (int s0 = s_lo + lane * SPL; s0 < len; s0 += 32 * SPL) {                // s_lo: the samples before it were written by the caller
+        if (s0 >= fl_lo && s0 < fl_hi) continue;                            // written above (fl_lo, fl_hi and s0 are even)
+        float wv[SPL], wpv[SPL], sf[SPL], sp[SPL]; int jf[SPL], jp[SPL], ii[SPL], ipp[SPL]; bool use_p[SPL], in[SPL];
+        #pragma unroll
+        for (int q = 0; q < SPL; q++) {
+            const int s = s0 + q;
+            in[q] = s < len;
+            const int i = f.out_begin + (in[q] ? s : 0);
+            const int o = i - f.start;
+            const bool ola = cur && f.ola_len > 0 && o >= 0 && o < f.ola_len;              // StreamDecoder.cs:532-541
+            const int ip = cur ? f.prev_valid + o : i;                                   // sample of the previous block (overlap or drain)
+            use_p[q] = ola || !cur;
+            ii[q] = i; ipp[q] = ip;
+            wv[q] = 0.f; wpv[q] = 0.f; jf[q] = 0; jp[q] = 0; sf[q] = 0.f; sp[q] = 0.f;
+            if (cur) { wv[q] = SWZ ? fused_window_at(s_win, s_win0, nf_, wxf, i) : wf[i]; fused_y_index(nf_, i, jf[q], sf[q], SWZ); }
+            if (use_p[q] && pf) { wpv[q] = SWZ ? fused_window_at(s_win, s_win0, np_, wxp, ip) : wp[ip]; fused_y_index(np_, ip, jp[q], sp[q], SWZ); }
+        }
+        if (SWZ && G == 2) {                                                // a stereo unit: both channels of a sample in one float2
+            #pragma unroll
+            for (int q = 0; q < SPL; q++) {
+                if (!in[q]) continue;
+                float v[2];
+                #pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    float acc = 0.f;
+                    if (cur) {
+                        const float* sl = slots_f + (size_t)c * slot_floats;
+                        const float y = ((ex_f >> c) & 1u) ? sf[q] * sl[jf[q]] : (ii[q] < (nf_ >> 1) ? sl[ii[q]] : 0.f);
+                        acc = y * wv[q];
+                    }
+                    if (use_p[q]) {
+                        if (pf) {
+                            const float* sl = slots_p + (size_t)c * slot_floats;
+                            const float y = ((ex_p >> c) & 1u) ? sp[q] * sl[jp[q]] : (ipp[q] < (np_ >> 1) ? sl[ipp[q]] : 0.f);
+                            acc += y * wpv[q];
+                        } else if (f.prev == PREV_CARRY) acc += a.carry_in[(size_t)(cbase + c) * S.bs[1] + ipp[q]];
+                    }
+                    if (clip) acc = clipf(acc, peak);
+                    v[c] = acc;
+                }
+                *reinterpret_cast<float2*>(a.pcm + ((size_t)f.pcm_off + s0 + q) * C + cbase) = make_float2(v[0], v[1]);
             }
-            if (clip) v = clipf(v, peak);
-            dst[c] = v;
+        } else {
+            #pragma unroll
+            for (int q = 0; q < SPL; q++) {
+                if (!in[q]) continue;
+                float* dst = a.pcm + ((size_t)f.pcm_off + s0 + q) * C + cbase;
+                for (int c = 0; c < G; c++) {
+                    float v = 0.f;
+                    if (cur) {
+                        const float* sl = slots_f + (size_t)c * slot_floats;
+                        const float y = ((ex_f >> c) & 1u) ? sf[q] * sl[jf[q]] : (ii[q] < (nf_ >> 1) ? sl[ii[q]] : 0.f);
+                        v = y * wv[q];
+                    }
+                    if (use_p[q]) {
+                        if (pf) {
+                            const float* sl = slots_p + (size_t)c * slot_floats;
+                            const float y = ((ex_p >> c) & 1u) ? sp[q] * sl[jp[q]] : (ipp[q] < (np_ >> 1) ? sl[ipp[q]] : 0.f);
+                            v += y * wpv[q];
+                        } else if (f.prev == PREV_CARRY) v += a.carry_in[(size_t)(cbase + c) * S.bs[1] + ipp[q]];
+                    }
+                    if (clip) v = clipf(v, peak);
+                    dst[c] = v;
+                }
+            }
         }
     }
 }
@@ -337,8 +410,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
                 const int pslot = (GROUPED ? (f.prev * U + (v - x * U)) - vfirst : f.prev - first) % NS;
                 pf = &s_fr[pslot]; slots_p = s_slots + (size_t)pslot * G * FUSED_SLOT_FLOATS;
             }
-            const bool fast = (G == 2) && f.kind == 0 && pf && f.n == FUSED_LONG_N && pf->n == FUSED_LONG_N && f.window == 3 &&
-                              (pf->window & 2) && f.start == 0 && f.out_begin == 0 && f.out_end == 1024 && f.ola_len == 1024 &&
+            // (window 1 = the next block is short: the first 1024 samples are the same TDAC pairs, 448 flat samples follow)
+            const bool fast = (G == 2) && f.kind == 0 && pf && f.n == FUSED_LONG_N && pf->n == FUSED_LONG_N && (f.window & 1) &&
+                              (pf->window & 2) && f.start == 0 && f.out_begin == 0 && f.out_end >= 1024 && f.ola_len == 1024 &&
                               f.prev_valid == 1024 && ((f.exec_mask >> cbase) & 3u) == 3u && ((pf->exec_mask >> cbase) & 3u) == 3u && pf->kind == 0 &&
                               (GROUPED || (f.pcm_off & 1) == 0);
             if (fast) {
@@ -384,8 +458,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
                         *reinterpret_cast<float2*>(o + (size_t)(1023 - i) * C) = make_float2(hi_[2], hi_[3]);
                     }
                 }
+                if (f.out_end > 1024) emit_samples<true>(a, S, f, pf, slots_f, slots_p, FUSED_SLOT_FLOATS, lane, peak, cbase, G, s_tab, 1024);
             } else if (len > 0) {
-                emit_samples<true>(a, S, f, pf, slots_f, slots_p, FUSED_SLOT_FLOATS, lane, peak, cbase, G);
+                emit_samples<true>(a, S, f, pf, slots_f, slots_p, FUSED_SLOT_FLOATS, lane, peak, cbase, G, s_tab, 0);
             }
             if (x == a.carry_frame && a.carry_out && f.kind == 0) {
                 // keep the last windowed block for the next batch (StreamDecoder.cs:455-461)
@@ -529,7 +604,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_imdct_generic(GenericParam
                 const int pslot = (f.prev - first) % NS;
                 pf = &s_fr[pslot]; slots_p = s_slots + (size_t)pslot * C * SLOT;
             }
-            if (f.out_end > f.out_begin) emit_samples<false>(a, S, f, pf, slots_f, slots_p, SLOT, lane, peak, 0, C);
+            if (f.out_end > f.out_begin) emit_samples<false>(a, S, f, pf, slots_f, slots_p, SLOT, lane, peak, 0, C, nullptr, 0);
             if (x == a.carry_frame && a.carry_out && f.kind == 0) {
                 for (int idx = lane; idx < f.n * C; idx += 32) {            // keep the last windowed block for the next batch (StreamDecoder.cs:455-461)
                     const int c = idx / f.n, i = idx - c * f.n;

@@ -74,8 +74,22 @@ struct FusedTables {
     static constexpr int WIN = 1664;    // [1024] rising slope of the long/long window (Mode.cs:80-85)
     static constexpr int TW0 = 2688;    // [64] float2: short-block twiddles exp(-i pi (k + 1/8) / 128)
     static constexpr int W64 = 2816;    // [64] float2: exp(-2 pi i k / 64)
-    static constexpr int FLOATS = 2944;
+    static constexpr int WIN0 = 2944;   // [128] rising slope of the short window: with WIN, every window shape of Mode.cs:24-67
+    static constexpr int FLOATS = 3072;
 };
+
+// Window value of sample i of a block (N = 2048 with window index widx = prev?1:0 + next?2:0, Mode.cs:44-50, or N = 256) from
+// the two slopes in shared memory: the shapes assemble_window() (nvb_host.cpp) builds -- zeros, a rising slope, ones, the
+// mirrored slope, zeros -- value for value.
+NVB_HD float fused_window_at(const float* s_win, const float* s_win0, int n, int widx, int i) {
+    if (n == FUSED_SHORT_N) return i < 128 ? s_win0[i] : s_win0[255 - i];
+    if (i < 1024) {
+        if (widx & 1) return s_win[i];
+        return i < 448 ? 0.f : (i < 576 ? s_win0[i - 448] : 1.f);
+    }
+    if (widx & 2) return s_win[2047 - i];
+    return i < 1472 ? 1.f : (i < 1600 ? s_win0[1599 - i] : 0.f);
+}
 NVB_HD int fused_na0(int l) { return (l >> 3) + 8 * (l & 7); }
 NVB_HD int fused_nb0(int l) { return (7 - (l >> 3)) + 8 * (7 - (l & 7)); }
 

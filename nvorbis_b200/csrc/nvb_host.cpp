@@ -100,7 +100,7 @@ void fast_tables(int n, float2* tw, float2* fft) {
 }
 
 // Lane tables of the fused kernel (FusedTables, nvb_fused_core.h), N = 2048 / 256, evaluated in double.
-void build_fused_tables(const float2* tw0, const float2* w64, const float* slope_long, float* out) {
+void build_fused_tables(const float2* tw0, const float2* w64, const float* slope_long, const float* slope_short, float* out) {
     const double pi = 3.14159265358979323846;
     auto tw = [&](int k) { return -pi * (k + 0.125) / 1024.0; };                // angle of tw[k] = exp(-i pi (k + 1/8) / M), M = 1024
     auto put2 = [&](float* p, double ang) { p[0] = (float)std::cos(ang); p[1] = (float)std::sin(ang); };
@@ -120,6 +120,7 @@ void build_fused_tables(const float2* tw0, const float2* w64, const float* slope
         put2(p, tw(fused_na0(l))); put2(p + 2, tw(fused_nb0(l)));
     }
     for (int i = 0; i < 1024; i++) out[FusedTables::WIN + i] = slope_long[i];
+    for (int i = 0; i < 128; i++) out[FusedTables::WIN0 + i] = slope_short[i];
     for (int k = 0; k < 64; k++) {
         out[FusedTables::TW0 + 2 * k] = tw0[k].x; out[FusedTables::TW0 + 2 * k + 1] = tw0[k].y;
         out[FusedTables::W64 + 2 * k] = w64[k].x; out[FusedTables::W64 + 2 * k + 1] = w64[k].y;
@@ -590,7 +591,8 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
     if (h.bs[0] == FUSED_SHORT_N && h.bs[1] == FUSED_LONG_N) {
         h.off_fused_tab = w.reserve(sizeof(float) * FusedTables::FLOATS);
         // rising slope of window 3 (long block between long blocks): the first 1024 values of that window
-        build_fused_tables(w.at<float2>(h.off_tw[0]), w.at<float2>(h.off_fft[0]), w.at<float>(h.off_win_long) + 3 * (size_t)h.bs[1], w.at<float>(h.off_fused_tab));
+        build_fused_tables(w.at<float2>(h.off_tw[0]), w.at<float2>(h.off_fft[0]), w.at<float>(h.off_win_long) + 3 * (size_t)h.bs[1], w.at<float>(h.off_win_short),
+                           w.at<float>(h.off_fused_tab));
     }
 
     // largest residue item table over the modes (k_spectrum's shared-memory prefix array)
