@@ -206,9 +206,16 @@ enum {
                                 s = round-to-nearest-even(v * 32768) saturated to [-32768, 32767], v = the float sample the call
                                 would otherwise return (after Utils.ClipValue unless NVB_RUN_NO_CLIP).  Halves the read-back;
                                 the reference itself only ever writes 32-bit float WAV (TestApp/WaveWriter.cs:18-62). */
-    NVB_RUN_DEVICE_OUT = 16  /* nvb_decode_batch[_begin]: pcm_out is a DEVICE pointer on the context's GPU (16-byte aligned): the PCM
+    NVB_RUN_DEVICE_OUT = 16, /* nvb_decode_batch[_begin]: pcm_out is a DEVICE pointer on the context's GPU (16-byte aligned): the PCM
                                 is left there for an on-device consumer, nothing is copied back (float, or int16 with
                                 NVB_RUN_PCM_S16).  The buffer is ready when the call / the batch's _end returns. */
+    NVB_RUN_ONE_KERNEL = 32, /* whole synthesis (Mapping.DecodePacket's float half .. OverlapBuffers, Mapping.cs:95-198 -> Mdct.cs:65-313
+                                -> Mode.cs:159-166 -> StreamDecoder.cs:532-541) in ONE kernel launch per batch: each warp computes its
+                                frame's spectrum into shared memory and transforms it there; no dense spectrum in device memory.
+                                Same results as the two-kernel path.  Applies to mono / stereo streams with 256/2048 blocks and
+                                residues the run-per-lane spectrum stage covers; other streams silently take the default path
+                                (nvb_dbatch_launches tells).  NVB_ONE_KERNEL=1 / 0 in the environment forces it on / off. */
+    NVB_RUN_TWO_KERNELS = 64 /* the opposite request: spectrum kernel + IMDCT kernel even where one kernel is the default */
 };
 
 /* ---- entry points ---------------------------------------------------------------------------- */

@@ -17,7 +17,7 @@ MAX_CHANNELS, MAX_POSTS, MAX_CLASSES, MAX_STAGES, MAX_COUPLING = 8, 64, 64, 8, 3
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_STATE, ERR_CAPACITY, ERR_DATA = 0, -1, -2, -3, -4, -5, -6, -7
 FRAME_OK, FRAME_FAILED = 0, 1
-RUN_DEFAULT, RUN_EXACT, RUN_NO_CLIP, RUN_CONTINUE, RUN_PCM_S16, RUN_DEVICE_OUT = 0, 1, 2, 4, 8, 16
+RUN_DEFAULT, RUN_EXACT, RUN_NO_CLIP, RUN_CONTINUE, RUN_PCM_S16, RUN_DEVICE_OUT, RUN_ONE_KERNEL, RUN_TWO_KERNELS = 0, 1, 2, 4, 8, 16, 32, 64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.environ.get("NVB_LIB_PATH") or os.path.join(_HERE, "libnvorbis_b200.so")      # NVB_LIB_PATH: development hook (kernel build variants)

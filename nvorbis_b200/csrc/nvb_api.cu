@@ -306,6 +306,18 @@ int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pc
     // the counters are cleared when they are read (fetch_result) or per batch (nvb_decode_batch_begin), not per run: a
     // memset between the kernels of consecutive runs would serialise what programmatic dependent launch overlaps
     (void)reset_counters;
+    // one-kernel synthesis (NVB_RUN_ONE_KERNEL / NVB_ONE_KERNEL=1): records -> PCM in one launch where the setup is covered
+    static const char* ok_env = std::getenv("NVB_ONE_KERNEL");
+    const bool one_kernel = ok_env ? std::atoi(ok_env) != 0 : ((b->flags & NVB_RUN_ONE_KERNEL) != 0 && !(b->flags & NVB_RUN_TWO_KERNELS));
+    if (stage == 0 && b->fused && one_kernel) {
+        r = launch_synth_fused(a, b->plan.frames.data(), st);
+        if (r == -1) return cuda_fail(ctx, cudaGetLastError(), "k_imdct_fused<SYN> launch");
+        if (r >= 0) {
+            if (after_spectrum) NVB_CUDA(ctx, cudaEventRecord(after_spectrum, st));
+            b->launches = (frame_cnt >= 0 && frame_lo > 0) ? b->launches + r : r;
+            return NVB_OK;
+        }
+    }
     if (stage != 2) {
         if ((r = launch_spectrum(a, st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_spectrum launch");
         launches += r;

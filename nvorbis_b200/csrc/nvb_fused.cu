@@ -34,6 +34,7 @@
 #endif
 #include <cstdlib>
 #include "nvb_fused_core.h"
+#include "nvb_wf_core.h"
 
 namespace nvb {
 
@@ -50,6 +51,8 @@ struct FusedParams {
     int frames_per_cta;
     int n_slots;
     int skew;                   // stress hook (NVB_FUSED_SKEW): pseudo-random pauses that shuffle the warps' relative progress
+    WfLayout wfl;               // one-kernel synthesis (SYN): per-warp scratch of the spectrum stage ...
+    int wf_off;                 // ... which starts wf_off bytes into the dynamic shared memory (inverse_dB_table first, then the warps)
 };
 
 // Stress hook of the slot-ring protocol: a pause that depends on (warp, unit, site), so that warps overtake and fall behind
@@ -247,7 +250,11 @@ __device__ __forceinline__ void emit_samples(const LaunchArgs& a, const DevSetup
 // of a whole frame -- slots hold two channels (18 of them instead of 7 six-channel slots), every warp stays busy, and the pair
 // takes the stereo TDAC output path with two float2 stores per sample pair into the C-channel interleave.  Units of one
 // frame are consecutive (v = frame * U + pair), the previous block of a unit is unit v - U.
-template <bool GROUPED>
+// SYN (one-kernel synthesis, K1-K5; 0 = off, else the channel count): the warp first computes its frame's spectrum from the boundary
+// records -- k_spectrum_wf's frame function (nvb_wf_core.h): residue gather, inverse coupling, floor curve -- straight into the
+// frame's slot, and the transforms read their inputs from there: one launch per batch, no dense spectrum in HBM (9.7 KB instead
+// of 25.7 KB of algorithmic traffic per stereo long frame).  The halo block's spectrum is recomputed like its transform.
+template <bool GROUPED, int SYN = 0>
 __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fused_t(FusedParams p) {
     NVB_DYN_SMEM(smem_raw);
     const LaunchArgs& a = p.a;
@@ -265,6 +272,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
     int* s_full = reinterpret_cast<int*>(s_fr + NS);                        // s_full[s]: frames completed in slot s
     int* s_empty = s_full + NS;                                             // s_empty[s]: reader releases of slot s (two per frame)
     uint64_t* s_tabbar = reinterpret_cast<uint64_t*>(s_empty + NS);          // 8 NS bytes past s_full: 8-byte aligned
+    float* s_db = reinterpret_cast<float*>(smem_raw + p.wf_off);            // SYN: inverse_dB_table, then one spectrum-stage scratch area per warp
+    unsigned char* s_wf = smem_raw + p.wf_off + 1024 + (size_t)warp * p.wfl.total;
 
     const int lo = a.frame_lo + blockIdx.x * p.frames_per_cta;              // plan indices; this launch covers [frame_lo, frame_lo + n_frames)
     int hi = lo + p.frames_per_cta; if (hi > a.frame_lo + a.n_frames) hi = a.frame_lo + a.n_frames;
@@ -276,6 +285,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
         mbar_init(s_tabbar, 1);
         mbar_fence_init();
     }
+    if (SYN) for (int i = tid; i < 256; i += FUSED_THREADS) s_db[i] = S.db[i];
     __syncthreads();
     if (tid == 0) {                                                         // the lane tables: one bulk copy (TMA) per CTA
         mbar_arrive_expect_tx(s_tabbar, FusedTables::FLOATS * sizeof(float));
@@ -298,7 +308,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
     }
     LongIn pre; int pre_x = -1, pre_c = -1;
 #if !defined(NVB_FUSED_NO_PREFETCH)
-    if (vfirst + warp < vhi) {
+    if (!SYN && vfirst + warp < vhi) {
         const int v0 = vfirst + warp, x0 = GROUPED ? v0 / U : v0, c0 = GROUPED ? (v0 - x0 * U) * 2 : 0;
         const DevFrame* f0 = a.frames + x0;
         if (f0->kind == 0 && f0->n == FUSED_LONG_N && ((f0->exec_mask >> c0) & 1u)) {
@@ -324,7 +334,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
     // build option: no register prefetch (32 fewer live registers; more warps per SM hide the load latency instead)
     auto can_prefetch = [&](int, int, uint32_t, int) { return false; };
 #else
-    auto can_prefetch = [&](int kind, int n, uint32_t exec_mask, int cc) { return kind == 0 && n == FUSED_LONG_N && ((exec_mask >> cc) & 1u); };
+    auto can_prefetch = [&](int kind, int n, uint32_t exec_mask, int cc) { return !SYN && kind == 0 && n == FUSED_LONG_N && ((exec_mask >> cc) & 1u); };
 #endif
 
     // Units go to the warps round-robin.  (Claiming them dynamically -- a warp that finishes a short block takes the next unit at
@@ -347,18 +357,36 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
         int n_kind = 1, n_n = 0; uint32_t n_exec = 0, n_spec = 0; bool n_known = false;
         float* slots_f = s_slots + (size_t)slot * G * FUSED_SLOT_FLOATS;
 
+        // ---------------- SYN: the frame's spectrum, from its boundary records into the slot ----------
+        if constexpr (SYN != 0) if (f.kind == 0) {
+            int bad_entry = 0, bad_floor = 0;
+            wf_frame_to_slot<SYN, false>(a, f, p.wfl, s_wf, s_db, wf_smem(slots_f), (uint32_t)(FUSED_SLOT_FLOATS * sizeof(float)), lane, bad_entry, bad_floor);
+            // a frame is counted once per kind, by the CTA that emits it (not by the one that recomputes it as a halo)
+            const bool be = __any_sync(0xffffffffu, bad_entry != 0), bf = __any_sync(0xffffffffu, bad_floor != 0);
+            if (x >= lo && lane == 0) { if (be) atomicAdd(&a.counters->bad_entry, 1); if (bf) atomicAdd(&a.counters->floor_range, 1); }
+            __syncwarp();
+        }
         // ---------------- transform: every channel of frame x -------------------------------------
         if (f.kind == 0) {
             for (int c = 0; c < G; c++) {
                 float* slotc = slots_f + (size_t)c * FUSED_SLOT_FLOATS;
                 const int M = f.n >> 1;
-                const float* spec = a.spectrum + (size_t)f.spec_off + (size_t)(cbase + c) * M;
+                const float* spec = SYN ? slotc : a.spectrum + (size_t)f.spec_off + (size_t)(cbase + c) * M;
                 if (!((f.exec_mask >> (cbase + c)) & 1u)) {
-                    for (int i = lane; i < M; i += 32) slotc[i] = spec[i];         // raw residue values (Mapping.cs:192-196)
+                    if (!SYN) { for (int i = lane; i < M; i += 32) slotc[i] = spec[i]; }      // raw residue values (Mapping.cs:192-196)
+                    else if (f.n == FUSED_LONG_N) {                          // already there; a long block's 16-byte chunks are permuted: undo
+                        float4 t[8];
+                        #pragma unroll
+                        for (int k = 0; k < 8; k++) { const int j = lane + 32 * k; t[k] = reinterpret_cast<const float4*>(slotc)[j ^ ((j >> 3) & 1)]; }
+                        __syncwarp();
+                        #pragma unroll
+                        for (int k = 0; k < 8; k++) reinterpret_cast<float4*>(slotc)[lane + 32 * k] = t[k];
+                    }
                 } else if (f.n == FUSED_LONG_N) {
                     float2* ex = reinterpret_cast<float2*>(slotc);
                     LongRegs R;
-                    if (!(pre_x == v && pre_c == c)) long_phase1_load(lane, reinterpret_cast<const float2*>(spec), pre);   // cold start
+                    if (SYN) { long_phase1_load_slot(lane, reinterpret_cast<const float2*>(slotc), pre); __syncwarp(); }   // inputs out of the slot before ex overwrites it
+                    else if (!(pre_x == v && pre_c == c)) long_phase1_load(lane, reinterpret_cast<const float2*>(spec), pre);   // cold start
                     long_phase1_compute(lane, pre, s_tab, ex);
                     if (c + 1 < G && can_prefetch(0, f.n, f.exec_mask >> cbase, c + 1)) {
                         long_phase1_load(lane, reinterpret_cast<const float2*>(spec + M), pre); pre_x = v; pre_c = c + 1;
@@ -693,6 +721,7 @@ int launch_imdct_fused(const LaunchArgs& a, const DevFrame* host_frames, void* s
     const char* env_slots = std::getenv("NVB_FUSED_SLOTS"); const char* env_skew = std::getenv("NVB_FUSED_SKEW");
     if (env_slots) { const int ns = std::atoi(env_slots); if (ns >= 3 && ns < p.n_slots) p.n_slots = ns; }
     p.skew = env_skew ? std::atoi(env_skew) : 0;
+    p.wfl = WfLayout(); p.wf_off = 0;
     const size_t smem = fused_smem(G, p.n_slots);
     static std::atomic<size_t> configured_by_dev[64];
     int dev_slot = 0; cudaGetDevice(&dev_slot); if (dev_slot < 0 || dev_slot >= 64) dev_slot = 0;
@@ -708,6 +737,47 @@ int launch_imdct_fused(const LaunchArgs& a, const DevFrame* host_frames, void* s
     const int grid = (a.n_frames + fpc - 1) / fpc;
     if (grouped) NVB_LAUNCH(k_imdct_fused_t<true>, grid, FUSED_THREADS, smem, stream, p);
     else NVB_LAUNCH(k_imdct_fused_t<false>, grid, FUSED_THREADS, smem, stream, p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-kernel synthesis: k_imdct_fused_t<false, C> -- boundary records in, PCM out, one launch per batch.
+static bool synth_supported(const DevSetup& S) {
+    return S.bs[0] == FUSED_SHORT_N && S.bs[1] == FUSED_LONG_N && S.fused_tab && (S.channels == 1 || S.channels == 2) && S.spectrum_fast >= 3 &&
+           S.f0_stride == 0 && S.max_posts <= 32 && S.magic && S.cls_cnt && S.run_modes;
+}
+int launch_synth_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream) {
+    (void)host_frames;
+    if (a.n_frames <= 0) return 0;
+    if (!synth_supported(a.S) || a.floor0) return -2;
+    const int C = a.S.channels;
+    FusedParams p; p.a = a;
+    p.wfl = wf_layout(a.S, C, 1);
+    const size_t scratch = 1024 + (size_t)FUSED_WARPS * p.wfl.total + 16;
+    const size_t fixed = FusedTables::FLOATS * sizeof(float) + 64 + scratch;
+    const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
+    if (fixed + 6 * per > FUSED_SMEM_LIMIT) return -2;                       // fewer than six slots: the ring would serialise the warps
+    int ns = (int)((FUSED_SMEM_LIMIT - fixed) / per);
+    if (ns > FUSED_WARPS + 2) ns = FUSED_WARPS + 2;
+    p.n_slots = ns;
+    const char* env_slots = std::getenv("NVB_FUSED_SLOTS"); const char* env_skew = std::getenv("NVB_FUSED_SKEW");
+    if (env_slots) { const int v = std::atoi(env_slots); if (v >= 3 && v < p.n_slots) p.n_slots = v; }
+    p.skew = env_skew ? std::atoi(env_skew) : 0;
+    p.wf_off = (int)((fused_smem(C, p.n_slots) + 15) & ~size_t(15));
+    const size_t smem = (size_t)p.wf_off + 1024 + (size_t)FUSED_WARPS * p.wfl.total;
+    static std::atomic<size_t> configured_by_dev[64];
+    int dev_slot = 0; cudaGetDevice(&dev_slot); if (dev_slot < 0 || dev_slot >= 64) dev_slot = 0;
+    if (!nvb_ensure_smem(configured_by_dev[dev_slot], smem, [&]() {
+            return cudaFuncSetAttribute(k_imdct_fused_t<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                   cudaFuncSetAttribute(k_imdct_fused_t<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
+    const int num_sms = fused_sm_count(dev_slot);
+    const int ctas = num_sms * FUSED_CTAS_PER_SM;
+    int fpc = (a.n_frames + ctas - 1) / ctas;
+    if (fpc < 8) fpc = 8;
+    p.frames_per_cta = fpc;
+    const int grid = (a.n_frames + fpc - 1) / fpc;
+    if (C == 1) NVB_LAUNCH((k_imdct_fused_t<false, 1>), grid, FUSED_THREADS, smem, stream, p);
+    else NVB_LAUNCH((k_imdct_fused_t<false, 2>), grid, FUSED_THREADS, smem, stream, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

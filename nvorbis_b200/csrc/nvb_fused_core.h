@@ -127,6 +127,13 @@ NVB_HD void long_phase1_load(int l, const float2* spec2, LongIn& in) {
     #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) { in.pa[k2] = spec2[64 * k2 + ra]; in.pb[k2] = spec2[64 * k2 + rb]; }
 }
+// The same rows out of the frame's slot (one-kernel synthesis): the spectrum stage stores 16-byte chunk j of a long block at
+// j ^ ((j >> 3) & 1), i.e. float2 m at m ^ (((m >> 4) & 1) << 1) -- bit 4 of 64 k2 + l is bit 4 of l, of 64 k2 + 63 - l its complement.
+NVB_HD void long_phase1_load_slot(int l, const float2* slot2, LongIn& in) {
+    const int ra = l ^ (((l >> 4) & 1) << 1), rb = (63 - l) ^ ((((63 - l) >> 4) & 1) << 1);
+    #pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) { in.pa[k2] = slot2[64 * k2 + ra]; in.pb[k2] = slot2[64 * k2 + rb]; }
+}
 NVB_HD void long_phase1_compute(int l, const LongIn& in, const float* tab, float2* ex) {
     const int ra = l, rb = 63 - l;
     const float4* T2 = reinterpret_cast<const float4*>(tab + FusedTables::T2);

@@ -234,5 +234,8 @@ int launch_pcm_s16(const float* src, int16_t* dst, long long lo, long long hi, v
 // Fused fast path: spectrum -> PCM for runs of frames; returns <0 if the batch shape is not covered.
 int launch_imdct_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream);
 bool fused_supported(const BlobHeader& h, const DevFrame* host_frames, int n_frames);
+// One-kernel synthesis (records -> PCM, k_imdct_fused_t<false, C>): 1 = launched, -2 = the setup / batch is not covered (take the
+// two-kernel path), -1 = launch error.
+int launch_synth_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream);
 
 }  // namespace nvb

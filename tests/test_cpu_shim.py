@@ -355,3 +355,36 @@ def test_wave_writer_mirror(shim, tmp_path):
         assert (wf.getnchannels(), wf.getsampwidth(), wf.getframerate(), wf.getnframes()) == (1, 2, 44100, pcm.size)
         got = np.frombuffer(wf.readframes(wf.getnframes()), "<i2")
     assert np.abs(got.astype(np.int32) - _s16(pcm).astype(np.int32)).max() <= 1
+
+
+def test_one_kernel_synthesis_equals_two_kernels(shim):
+    """NVB_RUN_ONE_KERNEL (k_imdct_fused_t<false, C>: spectrum stage inside the fused kernel, no dense spectrum) against the
+    two-kernel path and the oracle: mono with short + long blocks, stereo with coupling, chained ragged batches."""
+    for name, hi in (("1test", None), ("3test", 40)):
+        r, pcm, b, ctx = _ctx(shim, name)
+        want, _ = H.oracle_synth(r, b, 0, hi)
+        hb = H.batch_from_boundary(b, ctx.post_stride, 0, hi)
+        two, _ = ctx.decode_batch(hb, capi.RUN_DEFAULT)
+        two = two.copy()
+        ctx.reset()
+        one, res = ctx.decode_batch(hb, capi.RUN_ONE_KERNEL)
+        assert one.size == want.size and np.abs(one - want).max() <= 1e-5
+        np.testing.assert_array_equal(one, two)
+        ctx.reset()
+        n = len(b.frames) if hi is None else hi
+        chained = {}
+        for mode in (capi.RUN_ONE_KERNEL, capi.RUN_TWO_KERNELS):               # (a carried tail is a windowed block: not the fused TDAC arithmetic)
+            ctx.reset()
+            parts, pos = [], 0
+            for cut in (3, 4, 11, n):
+                out, _ = ctx.decode_batch(H.batch_from_boundary(b, ctx.post_stride, pos, cut), mode | (capi.RUN_CONTINUE if pos else 0))
+                parts.append(out.copy()); pos = cut
+            chained[mode] = np.concatenate(parts)
+        np.testing.assert_array_equal(chained[capi.RUN_ONE_KERNEL], chained[capi.RUN_TWO_KERNELS])
+        assert np.abs(chained[capi.RUN_ONE_KERNEL] - want).max() <= 1e-5
+        ctx.close()
+
+
+def test_one_kernel_bad_inputs(shim):
+    import test_gpu_one_kernel
+    test_gpu_one_kernel._bad_inputs_case(shim)
