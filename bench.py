@@ -441,12 +441,34 @@ def run_ours(args):
     ms_imdct = t_imdct.ms
     t_spec = timed(lambda i: dbatches[i % ROTATE].run_spectrum(spec_bufs[i % ROTATE].data_ptr(), stream), args.steps, args.warmup)
     ms_spec = t_spec.ms
+    # ---- the one-kernel form of the path (NVB_RUN_ONE_KERNEL: spectrum stage inside the fused kernel, no dense spectrum in HBM) ----
+    one_kernel = None
+    try:
+        dbs1 = [ctx.create_dbatch(hb, capi.RUN_ONE_KERNEL) for hb in host_batches]
+        t_one = timed(lambda i: dbs1[i % ROTATE].run(pcm_bufs[i % ROTATE].data_ptr(), stream), args.steps, args.warmup)
+        dbatches[0].run(pcm_bufs[0].data_ptr(), stream); torch.cuda.synchronize()
+        ref_pcm = pcm_bufs[0][: samples * C].clone()
+        dbs1[0].run(pcm_bufs[0].data_ptr(), stream); torch.cuda.synchronize()
+        same = bool(torch.equal(ref_pcm, pcm_bufs[0][: samples * C]))
+        del ref_pcm
+        alg1 = int(host_batches[0].h2d_bytes + samples * C * 4)
+        one_ms = t_one.per_step()
+        one_kernel = {"api": "NVB_RUN_ONE_KERNEL: k_imdct_fused_t<false, C> -- each warp computes its frame's spectrum into shared memory, transforms it there and writes PCM",
+                      "launches_per_step": dbs1[0].launches, "ms_per_step_single_stream": one_ms, "frames_per_s": FRAMES_PER_STEP * world / (one_ms * 1e-3),
+                      "two_kernels_ms_per_step_single_stream": ms_single / args.steps, "pcm_identical_to_two_kernels": same, "timing": t_one.stats(),
+                      "roofline_compact_inputs": {"algorithmic_bytes_per_launch": alg1, "achieved": alg1 / (one_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                                  "frac": alg1 / (one_ms * 1e-3) / 1e9 / measured_peak_gbs()[0],
+                                                  "note": "boundary records read + PCM written (SURVEY.md section 8d: ~9.7 KB per stereo long frame); issue- and latency-bound, not HBM-bound"}}
+        for db in dbs1:
+            db.destroy()
+    except Exception as e:
+        one_kernel = {"error": repr(e)}
     clocks = sampler.stop() if rank == 0 else None
     if KERNELS_ONLY:
         if rank == 0:
             print(json.dumps({"kernels_only": True, "value": FRAMES_PER_STEP * world * args.steps / (ms_total * 1e-3), "step_ms": ms_total / args.steps,
                               "step_ms_single_stream": ms_single / args.steps, "k_spectrum_ms": ms_spec / args.steps, "k_imdct_fused_ms": ms_imdct / args.steps,
-                              "timing": t_total.stats(), "clocks": clocks, "env": {k: v for k, v in os.environ.items() if k.startswith("NVB_")}}))
+                              "one_kernel_ms": one_kernel.get("ms_per_step_single_stream") if one_kernel else None, "timing": t_total.stats(), "clocks": clocks, "env": {k: v for k, v in os.environ.items() if k.startswith("NVB_")}}))
         for db in dbatches:
             db.destroy()
         ctx.close()
@@ -549,6 +571,10 @@ def run_ours(args):
         t_strong_spec = timed(lambda i: db64.run_spectrum(spec64.data_ptr(), stream), 4, 3)
         alg64 = int(db64.spectrum_floats * 4 + db64.samples * C * 4)
         del spec64
+        db64_1 = ctx.create_dbatch(hb64, capi.RUN_ONE_KERNEL)
+        t_strong_one = timed(lambda i: db64_1.run(pcm64.data_ptr(), stream), 4, 3)
+        strong_one_launches = db64_1.launches
+        db64_1.destroy()
         out64 = [torch.empty(db64.samples * C + 16, dtype=torch.float32).pin_memory() for _ in range(2)]
 
         def strong_e2e():
@@ -567,6 +593,7 @@ def run_ours(args):
                   "value": STRONG_FRAMES / (t_strong.per_step() * 1e-3), "unit": "frames/s", "ms_per_pass": t_strong.per_step(), "timing": t_strong.stats(),
                   "e2e_value": STRONG_FRAMES / (t_strong_e2e.per_step() * 1e-3), "e2e_ms_per_pass": t_strong_e2e.per_step(),
                   "k_imdct_fused_ms": t_strong_imdct.per_step(), "k_spectrum_ms": t_strong_spec.per_step(),
+                  "one_kernel_ms_per_pass": t_strong_one.per_step(), "one_kernel_launches": strong_one_launches,
                   "roofline_k_imdct_fused": {"achieved": alg64 / (t_strong_imdct.per_step() * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes_per_launch": alg64,
                                              "frac": alg64 / (t_strong_imdct.per_step() * 1e-3) / 1e9 / measured_peak_gbs()[0],
                                              "note": "this rank's shard in ONE launch (max over ranks): launch ramp, tail and the halo block amortised"},
@@ -626,6 +653,7 @@ def run_ours(args):
                     "s16_api": "NVB_RUN_PCM_S16: 16-bit PCM quantised on the device, half the read-back",
                     "device_out_value": frames_total / (t_e2e_dev.ms * 1e-3),
                     "device_out_api": "NVB_RUN_DEVICE_OUT: PCM left in a device buffer of the caller (on-device consumer), d2h 0 bytes"},
+            "one_kernel": one_kernel,
             "strong_64k": strong,
             "ogg_to_pcm": ogg,
             "other_configs": configs,

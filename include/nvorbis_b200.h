@@ -212,10 +212,12 @@ enum {
     NVB_RUN_ONE_KERNEL = 32, /* whole synthesis (Mapping.DecodePacket's float half .. OverlapBuffers, Mapping.cs:95-198 -> Mdct.cs:65-313
                                 -> Mode.cs:159-166 -> StreamDecoder.cs:532-541) in ONE kernel launch per batch: each warp computes its
                                 frame's spectrum into shared memory and transforms it there; no dense spectrum in device memory.
-                                Same results as the two-kernel path.  Applies to mono / stereo streams with 256/2048 blocks and
-                                residues the run-per-lane spectrum stage covers; other streams silently take the default path
-                                (nvb_dbatch_launches tells).  NVB_ONE_KERNEL=1 / 0 in the environment forces it on / off. */
-    NVB_RUN_TWO_KERNELS = 64 /* the opposite request: spectrum kernel + IMDCT kernel even where one kernel is the default */
+                                Same results as the two-kernel path, bit for bit.  Applies to mono / stereo streams with 256/2048
+                                blocks and residues the run-per-lane spectrum stage covers; other streams silently take the two-kernel
+                                path (nvb_dbatch_launches tells).  Without this flag the library picks per launch: one kernel for
+                                launches of up to 15 frames per SM (one round of its warps: lower latency), two kernels above.
+                                NVB_ONE_KERNEL=1 / 0 in the environment forces it on / off. */
+    NVB_RUN_TWO_KERNELS = 64 /* the opposite request: spectrum kernel + IMDCT kernel for every launch */
 };
 
 /* ---- entry points ---------------------------------------------------------------------------- */

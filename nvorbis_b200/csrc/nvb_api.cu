@@ -307,10 +307,12 @@ int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pc
     // memset between the kernels of consecutive runs would serialise what programmatic dependent launch overlaps
     (void)reset_counters;
     // one-kernel synthesis (NVB_RUN_ONE_KERNEL / NVB_ONE_KERNEL=1): records -> PCM in one launch where the setup is covered
+    // (default: the library chooses per launch -- one kernel where the launch fits one round of the CTAs' warps, see launch_synth_fused)
     static const char* ok_env = std::getenv("NVB_ONE_KERNEL");
-    const bool one_kernel = ok_env ? std::atoi(ok_env) != 0 : ((b->flags & NVB_RUN_ONE_KERNEL) != 0 && !(b->flags & NVB_RUN_TWO_KERNELS));
-    if (stage == 0 && b->fused && one_kernel) {
-        r = launch_synth_fused(a, b->plan.frames.data(), st);
+    const bool forced = ok_env ? std::atoi(ok_env) != 0 : (b->flags & NVB_RUN_ONE_KERNEL) != 0;
+    const bool never = ok_env ? std::atoi(ok_env) == 0 : (b->flags & NVB_RUN_TWO_KERNELS) != 0;
+    if (stage == 0 && b->fused && !never) {
+        r = launch_synth_fused(a, b->plan.frames.data(), st, forced);
         if (r == -1) return cuda_fail(ctx, cudaGetLastError(), "k_imdct_fused<SYN> launch");
         if (r >= 0) {
             if (after_spectrum) NVB_CUDA(ctx, cudaEventRecord(after_spectrum, st));

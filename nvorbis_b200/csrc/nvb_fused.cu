@@ -44,6 +44,9 @@ namespace nvb {
 constexpr int FUSED_WARPS = NVB_FUSED_WARPS;
 constexpr int FUSED_CTAS_PER_SM = FUSED_WARPS <= 8 ? 2 : 1;      // 8-warp build: two half-size CTAs share an SM
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
+#ifndef NVB_FUSED_LB_THREADS
+#define NVB_FUSED_LB_THREADS FUSED_THREADS                                  // experiment hook: a larger bound caps the registers of builds with fewer warps
+#endif
 constexpr size_t FUSED_SMEM_LIMIT = (FUSED_WARPS <= 8 ? 112 : 227) * 1024 - FUSED_WARPS * 64;   // minus the static per-warp plan records
 
 struct FusedParams {
@@ -255,7 +258,7 @@ __device__ __forceinline__ void emit_samples(const LaunchArgs& a, const DevSetup
 // frame's slot, and the transforms read their inputs from there: one launch per batch, no dense spectrum in HBM (9.7 KB instead
 // of 25.7 KB of algorithmic traffic per stereo long frame).  The halo block's spectrum is recomputed like its transform.
 template <bool GROUPED, int SYN = 0>
-__global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fused_t(FusedParams p) {
+__global__ void __launch_bounds__(NVB_FUSED_LB_THREADS, FUSED_CTAS_PER_SM) k_imdct_fused_t(FusedParams p) {
     NVB_DYN_SMEM(smem_raw);
     const LaunchArgs& a = p.a;
     const DevSetup& S = a.S;
@@ -273,7 +276,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
     int* s_empty = s_full + NS;                                             // s_empty[s]: reader releases of slot s (two per frame)
     uint64_t* s_tabbar = reinterpret_cast<uint64_t*>(s_empty + NS);          // 8 NS bytes past s_full: 8-byte aligned
     float* s_db = reinterpret_cast<float*>(smem_raw + p.wf_off);            // SYN: inverse_dB_table, then one spectrum-stage scratch area per warp
-    unsigned char* s_wf = smem_raw + p.wf_off + 1024 + (size_t)warp * p.wfl.total;
+    const CiRec* s_ci = reinterpret_cast<const CiRec*>(smem_raw + p.wf_off + 1024);      // SYN: the setup's (class, stage) records
+    unsigned char* s_wf = smem_raw + p.wf_off + 1024 + p.wfl.cta_bytes + (size_t)warp * p.wfl.total;
 
     const int lo = a.frame_lo + blockIdx.x * p.frames_per_cta;              // plan indices; this launch covers [frame_lo, frame_lo + n_frames)
     int hi = lo + p.frames_per_cta; if (hi > a.frame_lo + a.n_frames) hi = a.frame_lo + a.n_frames;
@@ -285,7 +289,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
         mbar_init(s_tabbar, 1);
         mbar_fence_init();
     }
-    if (SYN) for (int i = tid; i < 256; i += FUSED_THREADS) s_db[i] = S.db[i];
+    if (SYN) {
+        for (int i = tid; i < 256; i += FUSED_THREADS) s_db[i] = S.db[i];
+        for (int i = tid; i < S.ci_total; i += FUSED_THREADS) reinterpret_cast<int4*>(smem_raw + p.wf_off + 1024)[i] = reinterpret_cast<const int4*>(S.ci)[i];
+    }
     __syncthreads();
     if (tid == 0) {                                                         // the lane tables: one bulk copy (TMA) per CTA
         mbar_arrive_expect_tx(s_tabbar, FusedTables::FLOATS * sizeof(float));
@@ -360,7 +367,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_imdct_fuse
         // ---------------- SYN: the frame's spectrum, from its boundary records into the slot ----------
         if constexpr (SYN != 0) if (f.kind == 0) {
             int bad_entry = 0, bad_floor = 0;
-            wf_frame_to_slot<SYN, false>(a, f, p.wfl, s_wf, s_db, wf_smem(slots_f), (uint32_t)(FUSED_SLOT_FLOATS * sizeof(float)), lane, bad_entry, bad_floor);
+            wf_frame_to_slot<SYN, false>(a, f, p.wfl, s_wf, reinterpret_cast<int*>(slots_f), s_db, s_ci, wf_smem(slots_f), (uint32_t)(FUSED_SLOT_FLOATS * sizeof(float)), lane, bad_entry, bad_floor);
             // a frame is counted once per kind, by the CTA that emits it (not by the one that recomputes it as a halo)
             const bool be = __any_sync(0xffffffffu, bad_entry != 0), bf = __any_sync(0xffffffffu, bad_floor != 0);
             if (x >= lo && lane == 0) { if (be) atomicAdd(&a.counters->bad_entry, 1); if (bf) atomicAdd(&a.counters->floor_range, 1); }
@@ -746,14 +753,23 @@ static bool synth_supported(const DevSetup& S) {
     return S.bs[0] == FUSED_SHORT_N && S.bs[1] == FUSED_LONG_N && S.fused_tab && (S.channels == 1 || S.channels == 2) && S.spectrum_fast >= 3 &&
            S.f0_stride == 0 && S.max_posts <= 32 && S.magic && S.cls_cnt && S.run_modes;
 }
-int launch_synth_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream) {
+int launch_synth_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream, bool forced) {
     (void)host_frames;
     if (a.n_frames <= 0) return 0;
     if (!synth_supported(a.S) || a.floor0) return -2;
     const int C = a.S.channels;
+    {
+        // Unforced, one kernel takes the launches it wins: those that fit ONE round of the CTA's warps (at most FUSED_WARPS units per
+        // CTA including the halo block).  There a warp's frame is a single dependent chain -- spectrum, transforms, output -- and
+        // one launch beats two (1024 frames: 22.7 vs 34.2 us, profiles/r02_b_one_kernel_ab.json); a second round costs the one-kernel
+        // path more than the two-kernel path (4096 frames: 48.1 vs 44.5 us; 65 536 frames: 0.64 vs 0.52 ms).
+        int dev = 0; cudaGetDevice(&dev); if (dev < 0 || dev >= 64) dev = 0;
+        if (!forced && a.n_frames > (FUSED_WARPS - 1) * fused_sm_count(dev) * FUSED_CTAS_PER_SM) return -2;
+    }
     FusedParams p; p.a = a;
-    p.wfl = wf_layout(a.S, C, 1);
-    const size_t scratch = 1024 + (size_t)FUSED_WARPS * p.wfl.total + 16;
+    p.wfl = wf_layout_slot(a.S, C);
+    if (p.wfl.cta_bytes > 16 * 1024) return -2;
+    const size_t scratch = 1024 + (size_t)p.wfl.cta_bytes + (size_t)FUSED_WARPS * p.wfl.total + 16;
     const size_t fixed = FusedTables::FLOATS * sizeof(float) + 64 + scratch;
     const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
     if (fixed + 6 * per > FUSED_SMEM_LIMIT) return -2;                       // fewer than six slots: the ring would serialise the warps
@@ -764,7 +780,7 @@ int launch_synth_fused(const LaunchArgs& a, const DevFrame* host_frames, void* s
     if (env_slots) { const int v = std::atoi(env_slots); if (v >= 3 && v < p.n_slots) p.n_slots = v; }
     p.skew = env_skew ? std::atoi(env_skew) : 0;
     p.wf_off = (int)((fused_smem(C, p.n_slots) + 15) & ~size_t(15));
-    const size_t smem = (size_t)p.wf_off + 1024 + (size_t)FUSED_WARPS * p.wfl.total;
+    const size_t smem = (size_t)p.wf_off + 1024 + (size_t)p.wfl.cta_bytes + (size_t)FUSED_WARPS * p.wfl.total;
     static std::atomic<size_t> configured_by_dev[64];
     int dev_slot = 0; cudaGetDevice(&dev_slot); if (dev_slot < 0 || dev_slot >= 64) dev_slot = 0;
     if (!nvb_ensure_smem(configured_by_dev[dev_slot], smem, [&]() {

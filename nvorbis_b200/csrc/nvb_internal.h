@@ -114,7 +114,7 @@ struct alignas(16) RunMode {
 // (Floor1.cs:206); x01 = x0 | x1 << 16 (0xffff: the flat tail, Floor1.cs:213-216); m as in RunSeg.
 struct alignas(16) WfSeg { uint32_t x01; int32_t y0, dy; uint32_t m; };
 // k_spectrum_wf smem bytes per frame group (host-computed, nvb_host.cpp: wf_layout)
-struct WfLayout { int32_t seg_off, fy_off, base_off, cls_off, total, np_pad; };
+struct WfLayout { int32_t seg_off, fy_off, base_off, cls_off, total, np_pad, cta_bytes, pad; };   // cta_bytes: the CTA-wide part in front of the groups (CiRec table)
 struct DevMapping { int32_t n_coupling, floor, residue, pad; uint8_t mag[NVB_MAX_COUPLING], ang[NVB_MAX_COUPLING]; };
 struct DevMode    { int32_t block_flag, mapping; };
 
@@ -234,8 +234,8 @@ int launch_pcm_s16(const float* src, int16_t* dst, long long lo, long long hi, v
 // Fused fast path: spectrum -> PCM for runs of frames; returns <0 if the batch shape is not covered.
 int launch_imdct_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream);
 bool fused_supported(const BlobHeader& h, const DevFrame* host_frames, int n_frames);
-// One-kernel synthesis (records -> PCM, k_imdct_fused_t<false, C>): 1 = launched, -2 = the setup / batch is not covered (take the
-// two-kernel path), -1 = launch error.
-int launch_synth_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream);
+// One-kernel synthesis (records -> PCM, k_imdct_fused_t<false, C>): 1 = launched, -2 = the setup / batch is not covered or -- unless
+// forced -- the launch is larger than one round of the CTAs' warps (take the two-kernel path), -1 = launch error.
+int launch_synth_fused(const LaunchArgs& a, const DevFrame* host_frames, void* stream, bool forced);
 
 }  // namespace nvb

@@ -1089,13 +1089,13 @@ __global__ void __launch_bounds__(WF_WARPS * 32, 8) k_spectrum_wf(LaunchArgs a, 
     const uint8_t* cls = a.classes + f.classes_off;
     if (x.P > 0) for (uint32_t i = (uint32_t)gt * 64u; i < f.entry_count; i += GT * 64u) prefetch_l1(a.entries + f.entries_off + i);   // the frame's entries: 128 bytes per thread
 
-    unsigned char* gsm = dyn_smem + (size_t)group * L.total;
+    unsigned char* gsm = dyn_smem + L.cta_bytes + (size_t)group * L.total;
     WfSeg* s_seg = reinterpret_cast<WfSeg*>(gsm + L.seg_off);               // [CT][np_pad]
     int* s_fy = reinterpret_cast<int*>(gsm + L.fy_off) + wg * 256;          // per warp, for two channels at once: finalY[64], finalY * multiplier in x order [64]
     int* s_flags = reinterpret_cast<int*>(gsm + L.fy_off) + WPF * 256;      // [CT][4]: mask lo, mask hi, careful (groups of more than one warp)
     uint32_t* s_base = reinterpret_cast<uint32_t*>(gsm + L.base_off);       // [partition][ST]: where the (partition, stage) item's entries start
     uint16_t* s_cls = reinterpret_cast<uint16_t*>(gsm + L.cls_off);         // [partition]: class | coded stages << 8
-    x.sdb = wf_smem(s_db); x.sseg = wf_smem(s_seg); x.sbase = wf_smem(s_base); x.scls = wf_smem(s_cls);
+    x.sdb = wf_smem(s_db); x.sseg = wf_smem(s_seg); x.sbase = wf_smem(s_base); x.scls = wf_smem(s_cls); x.sci = 0;
 
     // ---- phase A: floors (warp wg takes channels wg, wg + WPF, ...) and entry offsets (the group's last warp)
     #pragma unroll
@@ -1703,8 +1703,8 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         const int WPF = (wpf_env == 1 || wpf_env == 2 || wpf_env == 4) ? wpf_env : 1;
         const WfLayout L = wf_layout(a.S, C, WPF);
         const int fpc = WF_WARPS / WPF;
-        const size_t smem = (size_t)L.total * fpc;
-        if (smem <= 200 * 1024) {
+        const size_t smem = (size_t)L.cta_bytes + (size_t)L.total * fpc;
+        if (smem <= 200 * 1024 && L.cta_bytes <= 16 * 1024) {
             const bool p64 = L.np_pad > 32;
             auto go = [&](auto kernel) -> int {
                 static std::atomic<size_t> configured[NVB_MAX_DEVICES];       // one per instantiation (a lambda instantiation has its own statics)

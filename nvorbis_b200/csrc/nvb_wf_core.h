@@ -216,6 +216,9 @@ __device__ __forceinline__ WfSeg wf_lds_seg(wf_saddr a) {
     WfSeg r; asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x01), "=r"(r.y0), "=r"(r.dy), "=r"(r.m) : "r"(a)); return r;
 }
 __device__ __forceinline__ uint32_t wf_lds_u32(wf_saddr a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ CiRec wf_lds_ci(wf_saddr a) {
+    CiRec r; asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.off), "=r"(r.dshift), "=r"(r.entries), "=r"(r.cnt) : "r"(a)); return r;
+}
 __device__ __forceinline__ uint32_t wf_lds_u16(wf_saddr a) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void wf_sts_v4(wf_saddr a, float x, float y, float z, float w) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
@@ -227,6 +230,7 @@ static inline wf_saddr wf_smem(const void* p) { return (wf_saddr)p; }
 static inline float wf_lds_f32(wf_saddr a) { return *reinterpret_cast<const float*>(a); }
 static inline WfSeg wf_lds_seg(wf_saddr a) { return *reinterpret_cast<const WfSeg*>(a); }
 static inline uint32_t wf_lds_u32(wf_saddr a) { return *reinterpret_cast<const uint32_t*>(a); }
+static inline CiRec wf_lds_ci(wf_saddr a) { return *reinterpret_cast<const CiRec*>(a); }
 static inline uint32_t wf_lds_u16(wf_saddr a) { return *reinterpret_cast<const uint16_t*>(a); }
 static inline void wf_sts_v4(wf_saddr a, float x, float y, float z, float w) { float* p = reinterpret_cast<float*>(a); p[0] = x; p[1] = y; p[2] = z; p[3] = w; }
 static inline void wf_sts_v2(wf_saddr a, float x, float y) { float* p = reinterpret_cast<float*>(a); p[0] = x; p[1] = y; }
@@ -248,6 +252,7 @@ template <int CT, bool P64> struct WfFrame {
     // offsets into the launch's arrays instead of pointers (the bases sit in the constant bank): half the registers
     uint32_t entries_off, spec_off, ci_off, bin2k_off;
     wf_saddr sdb, sseg, sbase, scls;                                        // inverse_dB_table, segments [CT][np], entry offsets [partition][ST], class words
+    wf_saddr sci;                                                           // the setup's (class, stage) records, staged once per CTA
     uint32_t ecount, exec_mask;
     wf_saddr sout; uint32_t sout_stride, sout_swz;                           // SLOT: the frame's shared-memory slot, bytes between its channels, 1 = long block (chunks swizzled)
     int n, span, np, P, rbegin, pshift, ST, st_n, n_coupling, mapping;
@@ -271,19 +276,23 @@ __device__ __forceinline__ void wf_main(const LaunchArgs& a, const WfFrame<CT, P
         float acc[16];
         #pragma unroll
         for (int k = 0; k < 16; k++) acc[k] = 0.f;
-        // ---- residue: the VQ vectors of the two runs, stage by stage from +0 (the float adds of WriteVectors in the reference's order)
+        // ---- residue: the VQ vectors of the two runs, stage by stage from +0 (the float adds of WriteVectors in the reference's order).
+        // (Issuing both runs' entry loads, then both runs' vector loads, before any add -- so that the two dependent load chains
+        // overlap -- measured no different in round 2: 22.1 vs 22.0 us, more spills at 64 registers.)
         #pragma unroll
         for (int r8 = 0; r8 < 2; r8++) {
             float* ac = acc + 8 * r8;
             const int q = (d << 4) + 8 * r8 - x.rbegin, p = q >> x.pshift;
             const bool inr = q >= 0 && p < x.P;
             const unsigned cw = inr ? wf_lds_u16(x.scls + (wf_saddr)(2 * (inr ? p : 0))) : 0u;
-            unsigned casc = cw >> 8;
+            unsigned rest = cw >> 8;
             const int cl = (int)(cw & 0xffu);
             const int o = q & pmask;
-            while (casc) {                                                  // one iteration for most partitions
-                const int st = __ffs(casc) - 1; casc &= casc - 1;
-                const CiRec ci = ci_tab[x.ci_off + (uint32_t)(cl * x.st_n + st)];
+            while (rest) {                                                  // one iteration for most partitions
+                const int st = __ffs(rest) - 1; rest &= rest - 1;
+                // the (class, stage) record: from the CTA's shared-memory copy in the one-kernel path (its L1 is a few KB: 220 KB of the
+                // SM's 256 are shared memory), through L1 in k_spectrum_wf (staging the table per 4-frame CTA cost more than it saved)
+                const CiRec ci = SLOT ? wf_lds_ci(x.sci + (wf_saddr)(16 * (x.ci_off + (uint32_t)(cl * x.st_n + st)))) : ci_tab[x.ci_off + (uint32_t)(cl * x.st_n + st)];
                 const uint32_t eb = wf_lds_u32(x.sbase + (wf_saddr)(4 * (p * x.ST + st)));
                 if (ci.dshift >= 1) {                                       // every book with an even number of dimensions: four float2
                     const int dmask = (1 << ci.dshift) - 1;
@@ -291,7 +300,7 @@ __device__ __forceinline__ void wf_main(const LaunchArgs& a, const WfFrame<CT, P
                     #pragma unroll
                     for (int h = 0; h < 4; h++) {
                         const uint32_t ei = eb + (uint32_t)((o + 2 * h) >> ci.dshift);
-                        ok[h] = ei < x.ecount;                              // else never decoded: contributes nothing (Residue0.cs:164-170)
+                        ok[h] = ei < x.ecount;
                         en[h] = 0u;
                         if (ok[h]) en[h] = ent[x.entries_off + ei];
                     }
@@ -416,7 +425,7 @@ __device__ __forceinline__ void wf_main(const LaunchArgs& a, const WfFrame<CT, P
 // in shared memory, sout / sout_stride: the slot and the bytes between its channels.  The caller provides the warp barrier that
 // makes the slot visible to the transform.
 template <int CT, bool P64>
-__device__ __forceinline__ void wf_frame_to_slot(const LaunchArgs& a, const DevFrame& f, const WfLayout& L, unsigned char* gsm, const float* s_db,
+__device__ __forceinline__ void wf_frame_to_slot(const LaunchArgs& a, const DevFrame& f, const WfLayout& L, unsigned char* gsm, int* s_fy, const float* s_db, const CiRec* s_ci,
                                                  wf_saddr sout, uint32_t sout_stride, int lane, int& bad_entry, int& bad_floor) {
     constexpr int H = P64 ? 2 : 1;
     typedef typename WfFrame<CT, P64>::mask_t mask_t;
@@ -435,11 +444,10 @@ __device__ __forceinline__ void wf_frame_to_slot(const LaunchArgs& a, const DevF
     const uint8_t* cls = a.classes + f.classes_off;
     if (x.P > 0) for (uint32_t i = (uint32_t)lane * 64u; i < f.entry_count; i += 32 * 64u) prefetch_l1(a.entries + f.entries_off + i);
 
-    WfSeg* s_seg = reinterpret_cast<WfSeg*>(gsm + L.seg_off);
-    int* s_fy = reinterpret_cast<int*>(gsm + L.fy_off);
+    WfSeg* s_seg = reinterpret_cast<WfSeg*>(gsm + L.seg_off);          // s_fy (256 ints of unwrap scratch) is only live in phase A: the caller lends the slot
     uint32_t* s_base = reinterpret_cast<uint32_t*>(gsm + L.base_off);
     uint16_t* s_cls = reinterpret_cast<uint16_t*>(gsm + L.cls_off);
-    x.sdb = wf_smem(s_db); x.sseg = wf_smem(s_seg); x.sbase = wf_smem(s_base); x.scls = wf_smem(s_cls);
+    x.sdb = wf_smem(s_db); x.sseg = wf_smem(s_seg); x.sbase = wf_smem(s_base); x.scls = wf_smem(s_cls); x.sci = wf_smem(s_ci);
 
     #pragma unroll
     for (int c = 0; c < CT; c++) { x.fmask[c] = 0; x.careful[c] = false; }
@@ -480,6 +488,21 @@ __device__ __forceinline__ void wf_frame_to_slot(const LaunchArgs& a, const DevF
     } else wf_main<CT, 32, P64, false, 3, true>(a, x, lane, bad_entry, bad_floor);
 }
 
+// The one-kernel path's per-warp scratch: segment records, entry offsets, class words (the unwrap scratch lives in the frame's slot).
+static WfLayout wf_layout_slot(const DevSetup& S, int CT) {
+    WfLayout L;
+    L.np_pad = S.max_posts <= 32 ? 32 : 64;
+    const int st_max = ((S.max_stages + 3) & ~3) > 0 ? ((S.max_stages + 3) & ~3) : 4;
+    const int pmax = S.wf_max_p > 0 ? S.wf_max_p : 1;
+    L.seg_off = 0;
+    L.fy_off = 0;
+    L.base_off = CT * L.np_pad * (int)sizeof(WfSeg);
+    L.cls_off = L.base_off + pmax * st_max * (int)sizeof(uint32_t);
+    L.total = (L.cls_off + pmax * (int)sizeof(uint16_t) + 15) & ~15;
+    L.cta_bytes = (S.ci_total > 0 ? S.ci_total : 1) * (int)sizeof(CiRec);
+    return L;
+}
+
 static WfLayout wf_layout(const DevSetup& S, int CT, int WPF) {
     WfLayout L;
     L.np_pad = S.max_posts <= 32 ? 32 : 64;
@@ -490,6 +513,7 @@ static WfLayout wf_layout(const DevSetup& S, int CT, int WPF) {
     L.base_off = (L.fy_off + WPF * 256 * (int)sizeof(int) + CT * 4 * (int)sizeof(int) + 15) & ~15;
     L.cls_off = L.base_off + pmax * st_max * (int)sizeof(uint32_t);
     L.total = (L.cls_off + pmax * (int)sizeof(uint16_t) + 15) & ~15;
+    L.cta_bytes = 0;
     return L;
 }
 

@@ -9,7 +9,7 @@ export NVB_BENCH_KERNELS_ONLY=1
 for spec in ${VARIANTS:-base:X=1}; do
   v=${spec%%:*}; envs=${spec#*:}
   env $envs timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/k_$v.json 2> gpurun_out/k_$v.err
-  echo "$v $(cat gpurun_out/k_$v.json | python -c 'import json,sys; d=json.loads(sys.stdin.read()); print(round(d["value"]/1e6,1), "M f/s step", round(d["step_ms"]*1e3,1), "us single", round(d["step_ms_single_stream"]*1e3,1), "spec", round(d["k_spectrum_ms"]*1e3,1), "imdct", round(d["k_imdct_fused_ms"]*1e3,1), d["timing"]["repeats"], d["clocks"]["sm_mhz"])' 2>&1 | tail -1)"
+  echo "$v $(cat gpurun_out/k_$v.json | python -c 'import json,sys; d=json.loads(sys.stdin.read()); print(round(d["value"]/1e6,1), "M f/s step", round(d["step_ms"]*1e3,1), "us single", round(d["step_ms_single_stream"]*1e3,1), "spec", round(d["k_spectrum_ms"]*1e3,1), "imdct", round(d["k_imdct_fused_ms"]*1e3,1), "one_kernel", round((d.get("one_kernel_ms") or 0)*1e3,1), d["timing"]["repeats"], d["clocks"]["sm_mhz"])' 2>&1 | tail -1)"
 done
 if [ -z "$SKIP_NCU" ]; then
 M=gpu__time_duration.sum,smsp__inst_executed.sum,sm__cycles_active.avg,sm__cycles_elapsed.max,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__warps_eligible.avg.per_cycle_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__t_sector_hit_rate.pct,dram__bytes_read.sum,dram__bytes_write.sum

@@ -145,7 +145,7 @@ def test_block_sizes_from_256_up_run_on_the_fused_path():
         hb = VH.random_records(np.random.default_rng(3), desc, 6, host.post_stride, floor0_stride=host.floor0_stride)
         ctx = capi.Context(0, lib_path=shim)
         ctx.upload_setup(host.setup())
-        db = ctx.create_dbatch(hb)
+        db = ctx.create_dbatch(hb, capi.RUN_TWO_KERNELS)                      # (small mono / stereo 256/2048 batches default to ONE kernel: test_gpu_one_kernel.py)
         pcm = np.zeros(db.samples * desc["channels"] + 16, np.float32)
         db.run(pcm.ctypes.data, 0)
         assert db.launches == want, (name, db.launches)
