@@ -1054,7 +1054,7 @@ __global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
 // Results are bit-identical to k_spectrum_run / the oracle (same float adds in the same order, same integer floor curve).
 // ------------------------------------------------------------------------------------------------
 template <int CT, int WPF, bool P64>
-__global__ void __launch_bounds__(WF_WARPS * 32, 8) k_spectrum_wf(LaunchArgs a, WfLayout L) {
+__global__ void __launch_bounds__(WF_WARPS * 32, NVB_WF_MINB) k_spectrum_wf(LaunchArgs a, WfLayout L) {
     constexpr int FPC = WF_WARPS / WPF;                                     // frames per CTA
     constexpr int GT = WPF * 32;                                            // threads per frame group
     constexpr int H = P64 ? 2 : 1;

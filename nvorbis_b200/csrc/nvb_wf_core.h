@@ -15,7 +15,13 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 static inline void prefetch_l1(const void*) {}
 #endif
 
-constexpr int WF_WARPS = 4;                                               // warps per CTA
+#ifndef NVB_WF_WARPS
+#define NVB_WF_WARPS 4                                                    // warps per CTA.  (2 / 8 warps per CTA and 7 instead of 8 CTAs per SM
+#endif                                                                    //  -- 72 registers -- all measured 21.7-21.9 us on configs[1], round 2)
+#ifndef NVB_WF_MINB
+#define NVB_WF_MINB 8
+#endif
+constexpr int WF_WARPS = NVB_WF_WARPS;
 
 // the group's barrier: __syncwarp for one warp per frame, a named barrier for two, __syncthreads for the whole CTA
 template <int WPF> __device__ __forceinline__ void wf_group_sync(int group) {
