@@ -678,11 +678,16 @@ static bool generic_supported(const BlobHeader& h) {
 }
 
 // ------------------------------------------------------------------------------------------------
-static int fused_slots(int C) {
+// Slots of the ring.  A slot is free again when its unit and the unit that overlaps onto it are done: unit v + 1 for whole frames, unit
+// v + U for channel-pair units (U pairs per frame) -- so FUSED_WARPS + U + 1 slots let every warp start its next unit without waiting
+// for a unit that is still in flight (round 2: with 18 slots for six channels, 40 % of the instructions k_imdct_fused_t<true> executed
+// were polling for a slot, profiles/r02_b_config3_ncu.txt).
+static int fused_slots(int C, int units_per_frame = 1) {
     const size_t fixed = FusedTables::FLOATS * sizeof(float) + 64;
     const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
     int ns = (int)((FUSED_SMEM_LIMIT - fixed) / per);
-    if (ns > FUSED_WARPS + 2) ns = FUSED_WARPS + 2;
+    const int want = FUSED_WARPS + units_per_frame + 1;
+    if (ns > want) ns = want;
     return ns;
 }
 static size_t fused_smem(int C, int NS) {
@@ -723,7 +728,7 @@ int launch_imdct_fused(const LaunchArgs& a, const DevFrame* host_frames, void* s
     bool grouped = C > 2 && (C & 1) == 0 && !no_grouped && host_frames != nullptr;
     if (grouped) for (int i = a.frame_lo; i < a.frame_lo + a.n_frames; i++) if (host_frames[i].kind != 0 || (host_frames[i].prev >= 0 && host_frames[i].prev != i - 1)) { grouped = false; break; }
     const int G = grouped ? 2 : C;
-    FusedParams p; p.a = a; p.n_slots = fused_slots(G);
+    FusedParams p; p.a = a; p.n_slots = fused_slots(G, grouped ? C / 2 : 1);
     // stress hooks (tests): a ring of as few as three slots, pseudo-random pauses between the protocol steps
     const char* env_slots = std::getenv("NVB_FUSED_SLOTS"); const char* env_skew = std::getenv("NVB_FUSED_SKEW");
     if (env_slots) { const int ns = std::atoi(env_slots); if (ns >= 3 && ns < p.n_slots) p.n_slots = ns; }
