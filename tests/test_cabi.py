@@ -47,6 +47,23 @@ int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(nvb_
     assert sizes == want
 
 
+def test_run_flags_match_header():
+    # the nvb_run flag values of the header against the Python binding's constants (NVB_RUN_ONE_KERNEL / _TWO_KERNELS are round 2's)
+    import subprocess, tempfile
+    src = r'''
+#include <stdio.h>
+#include "nvorbis_b200.h"
+int main(void) { printf("%d %d %d %d %d %d %d %d\n", NVB_RUN_DEFAULT, NVB_RUN_EXACT, NVB_RUN_NO_CLIP, NVB_RUN_CONTINUE, NVB_RUN_PCM_S16, NVB_RUN_DEVICE_OUT,
+  NVB_RUN_ONE_KERNEL, NVB_RUN_TWO_KERNELS); return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        vals = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert vals == [capi.RUN_DEFAULT, capi.RUN_EXACT, capi.RUN_NO_CLIP, capi.RUN_CONTINUE, capi.RUN_PCM_S16, capi.RUN_DEVICE_OUT, capi.RUN_ONE_KERNEL,
+                    capi.RUN_TWO_KERNELS]
+
+
 def test_no_cpu_fallback():
     """Without a GPU the product refuses to run; it never falls back to a CPU path."""
     import torch
