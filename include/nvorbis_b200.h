@@ -30,13 +30,14 @@
 extern "C" {
 #endif
 
-#define NVB_ABI_VERSION 2
+#define NVB_ABI_VERSION 3
 
-#define NVB_MAX_CHANNELS   8     /* reference allows 255 (StreamDecoder.cs:186); larger -> NVB_ERR_UNSUPPORTED */
+#define NVB_MAX_CHANNELS   32    /* reference allows 255 (StreamDecoder.cs:186); nvb_frame.exec_mask has 32 bits; larger -> NVB_ERR_UNSUPPORTED.
+                                    Up to 8 channels run on the specialised spectrum kernels, 9..32 on the general one. */
 #define NVB_MAX_POSTS      64    /* Floor1.Data.Posts = new int[64]            (Floor1.cs:12)   */
 #define NVB_MAX_CLASSES    64    /* residue classifications: 6 bits + 1         (Residue0.cs:41) */
 #define NVB_MAX_STAGES     8     /* cascade: 3 + 5 bits                          (Residue0.cs:48-56) */
-#define NVB_MAX_COUPLING   32    /* reference allows 256 steps (Mapping.cs:28); larger -> unsupported */
+#define NVB_MAX_COUPLING   256   /* 8 bits + 1 (Mapping.cs:28): every step count the reference accepts */
 
 typedef enum nvb_status {
     NVB_OK = 0,

@@ -12,8 +12,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-ABI_VERSION = 2
-MAX_CHANNELS, MAX_POSTS, MAX_CLASSES, MAX_STAGES, MAX_COUPLING = 8, 64, 64, 8, 32
+ABI_VERSION = 3
+MAX_CHANNELS, MAX_POSTS, MAX_CLASSES, MAX_STAGES, MAX_COUPLING = 32, 64, 64, 8, 256
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_STATE, ERR_CAPACITY, ERR_DATA = 0, -1, -2, -3, -4, -5, -6, -7
 FRAME_OK, FRAME_FAILED = 0, 1

@@ -724,7 +724,8 @@ static void unpack_packet(const nvh_stream& s, const PacketRef& pr, Scratch& out
         if (count > 0) live |= 1u << c;
     }
     // energy flags (Mapping.cs:105-119): noExecute is taken before the coupling propagation
-    const uint32_t no_exec = ~live & ((1u << C) - 1);
+    const uint32_t all_ch = C >= 32 ? 0xffffffffu : (1u << C) - 1u;
+    const uint32_t no_exec = ~live & all_ch;
     uint32_t exec = live;
     for (size_t k = 0; k < map.mag.size(); k++)
         if (((exec >> map.ang[k]) | (exec >> map.mag[k])) & 1u) exec |= (1u << map.ang[k]) | (1u << map.mag[k]);
@@ -734,7 +735,7 @@ static void unpack_packet(const nvh_stream& s, const PacketRef& pr, Scratch& out
     const ResidueDef& r = s.residues[(size_t)map.residue0];
     const int span = (r.type == 2 ? N * C : N) / 2;
     const int nn = std::min(r.end, span) - r.begin;
-    if (nn > 0 && no_exec != ((1u << C) - 1)) {
+    if (nn > 0 && no_exec != all_ch) {
         uf.f.res_decoded = 1;
         const int P = nn / r.psize, S = r.streams;
         const Book& cb = s.books[(size_t)r.class_book];

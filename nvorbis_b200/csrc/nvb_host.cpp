@@ -143,6 +143,7 @@ ResidueDerived derive_residue(int type, int begin, int psize, int nclass, int st
     ResidueDerived d; std::memset(&d, 0, sizeof d);
     d.pshift = is_pow2(psize) ? ilog_u(psize) - 1 : -1;
     bool fast = d.pshift >= 0 && psize <= 8192 && stages >= 1;
+    if (C > NVB_FAST_CHANNELS) fast = false;                                // the specialised kernels keep a bin's channels in registers: general kernel beyond 8
     if (type == 2 && (begin % C != 0 || psize % C != 0)) fast = false;     // Residue2.cs:27 truncation case
     for (int c = 0; c < NVB_MAX_CLASSES; c++)
         for (int st = 0; st < NVB_MAX_STAGES; st++) {
@@ -510,7 +511,7 @@ int build_blob(const nvb_setup* s, std::vector<unsigned char>& blob, std::string
         for (int i = 0; i < s->n_residues; i++) {
             const nvb_residue& r = s->residues[i];
             const DevResidue d = w.at<DevResidue>(h.off_residues)[i];
-            if (r.type != 2 || d.pshift < 0 || r.max_stages < 1) continue;
+            if (r.type != 2 || d.pshift < 0 || r.max_stages < 1 || C > NVB_FAST_CHANNELS) continue;
             bool ok = true;
             for (int c = 0; c < d.nclass && ok; c++) for (int st = 0; st < d.stages && ok; st++) {
                 if (d.books[c][st] < 0) continue;
@@ -769,7 +770,7 @@ int validate_blob(const void* data, size_t bytes, std::string& err) {
             if (P > h.wf_max_p) return fail(err, NVB_ERR_DATA, "blob: run mode %lld partition count", i);
         }
         if (rm.bins_ok) {
-            if (R.type != 2 || R.pshift < 0 || R.stages < 1 || S.floors0[mp.floor].type != 1) return fail(err, NVB_ERR_DATA, "blob: run mode %lld bins flag", i);
+            if (R.type != 2 || R.pshift < 0 || R.stages < 1 || S.floors0[mp.floor].type != 1 || h.channels > NVB_FAST_CHANNELS) return fail(err, NVB_ERR_DATA, "blob: run mode %lld bins flag", i);
             for (int c = 0; c < R.nclass; c++) for (int st = 0; st < R.stages; st++) {
                 if (R.books[c][st] < 0) continue;
                 const int dims = S.books[R.books[c][st]].dims;
@@ -837,7 +838,7 @@ int plan_batch(const unsigned char* host_blob, const nvb_batch* b, int flags, co
         const int n = h.bs[md.block_flag];
         if (f.window > 3 || (!md.block_flag && f.window != 0)) return fail(err, NVB_ERR_DATA, "frame %lld: window %lld", i, f.window);
         if (f.start < 0 || f.total > n || f.start > f.total || f.valid > f.total) return fail(err, NVB_ERR_DATA, "frame %lld: start/valid/total outside the block", i);
-        if ((f.exec_mask >> C) != 0) return fail(err, NVB_ERR_DATA, "frame %lld: exec_mask has bits above the channel count", i);
+        if (((uint64_t)f.exec_mask >> C) != 0) return fail(err, NVB_ERR_DATA, "frame %lld: exec_mask has bits above the channel count", i);
         const DevMapping& mp = S.mappings[md.mapping];
         if (S.floors0[mp.floor].type == 0) {
             if (!b->floor0) return fail(err, NVB_ERR_ARG, "frame %lld uses a type 0 floor but batch.floor0 is NULL", i);

@@ -58,6 +58,10 @@ struct NvbNoEarlyStart { int prev; explicit NvbNoEarlyStart(bool on) : prev(nvb_
 #endif
 #endif
 
+// Channel counts up to this run on the specialised spectrum kernels (channels of a bin in registers, per-channel tables in static shared
+// memory); setups with more channels (up to NVB_MAX_CHANNELS) take the general kernel's many-channel instantiation.
+#define NVB_FAST_CHANNELS 8
+
 namespace nvb {
 
 // Launch-configuration caches, safe for several host threads (a context is single-threaded, but contexts on several

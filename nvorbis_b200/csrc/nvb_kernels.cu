@@ -47,9 +47,11 @@ constexpr int OLA_THREADS = 256;
 // HBM traffic per frame: compact inputs (classes + entries + posts, ~1-2 KB) + VQ table gathers
 // (L2-resident) in, C*N/2 floats out, written coalesced per channel row.
 // ------------------------------------------------------------------------------------------------
+// MAXC: NVB_FAST_CHANNELS for up to 8 channels, NVB_MAX_CHANNELS (the bin's channels then live in local memory) beyond.
+template <int MAXC>
 __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
     NVB_DYN_SMEM(dyn_smem);
-    __shared__ FloorSegs s_segs[NVB_MAX_CHANNELS];
+    __shared__ FloorSegs s_segs[MAXC];
     __shared__ float s_db[256];
     __shared__ uint32_t s_warp[SPEC_THREADS / 32];
     __shared__ int s_bad[2];
@@ -149,16 +151,16 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum(LaunchArgs a) {
 
     int bad_entry = 0, bad_floor = 0;
     for (int j = t; j < n; j += nt) {
-        float r[NVB_MAX_CHANNELS];
+        float r[MAXC];
         #pragma unroll
-        for (int c = 0; c < NVB_MAX_CHANNELS; c++)
+        for (int c = 0; c < MAXC; c++)
             r[c] = (c < C) ? residue_value(R, S.books, S.vq, cls, ent, f.entry_count, prefix, g, C, c, j, &bad_entry) : 0.f;
         for (int i = mp.n_coupling - 1; i >= 0; --i) {                      // Mapping.cs:137-182
             int m = mp.mag[i], an = mp.ang[i];
             if (((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u) inverse_couple(r[m], r[an]);
         }
         #pragma unroll
-        for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
+        for (int c = 0; c < MAXC; c++) {
             if (c >= C) break;
             float v = r[c];
             if ((f.exec_mask >> c) & 1u) {                                  // Floor1.Apply, Floor1.cs:186-222 / Floor0.Apply, Floor0.cs:152-212
@@ -312,9 +314,9 @@ __device__ __forceinline__ void floor1_segments_warp(const DevFloor1& F, const i
 __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
     NVB_DYN_SMEM(dyn_smem);
     __shared__ float s_db[256];
-    __shared__ int s_fy[NVB_MAX_CHANNELS][NVB_MAX_POSTS];
-    __shared__ SegRec s_seg[NVB_MAX_CHANNELS * (NVB_MAX_POSTS + 1)];
-    __shared__ int s_nseg[NVB_MAX_CHANNELS + 1];
+    __shared__ int s_fy[NVB_FAST_CHANNELS][NVB_MAX_POSTS];
+    __shared__ SegRec s_seg[NVB_FAST_CHANNELS * (NVB_MAX_POSTS + 1)];
+    __shared__ int s_nseg[NVB_FAST_CHANNELS + 1];
     __shared__ int s_bad[2];
 
     nvb_grid_dep_launch();
@@ -441,9 +443,9 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
         }
     } else {
         for (int j = t; j < n; j += SPEC_THREADS) {
-            float r[NVB_MAX_CHANNELS];
+            float r[NVB_FAST_CHANNELS];
             #pragma unroll
-            for (int c = 0; c < NVB_MAX_CHANNELS; c++) r[c] = 0.f;
+            for (int c = 0; c < NVB_FAST_CHANNELS; c++) r[c] = 0.f;
             if (R.type == 2) {
                 // interleaved position of channel 0 of this bin; all C channels sit in one partition (aligned, host-checked)
                 const int q = j * C - R.begin;
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
                             const DevBook b = S.books[book];
                             const uint32_t base = prefix[s * g.P + p];
                             #pragma unroll
-                            for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
+                            for (int c = 0; c < NVB_FAST_CHANNELS; c++) {
                                 if (c >= C) break;
                                 const int e = o + c;
                                 r[c] = NVB_FADD(r[c], vq_fetch(b, S.vq, ent, base + (uint32_t)(e >> b.dshift), f.entry_count, e & (b.dims - 1), &bad_entry));
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
                         }
                     }
                     #pragma unroll
-                    for (int k = 0; k < NVB_MAX_CHANNELS; k++) if (k == c) r[k] = acc;
+                    for (int k = 0; k < NVB_FAST_CHANNELS; k++) if (k == c) r[k] = acc;
                 }
             }
             }
@@ -500,13 +502,13 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spectrum_fast(LaunchArgs a) {
                 if (!(((f.exec_mask >> m) | (f.exec_mask >> an)) & 1u)) continue;
                 float vm = 0.f, va = 0.f;
                 #pragma unroll
-                for (int k = 0; k < NVB_MAX_CHANNELS; k++) { if (k == m) vm = r[k]; if (k == an) va = r[k]; }
+                for (int k = 0; k < NVB_FAST_CHANNELS; k++) { if (k == m) vm = r[k]; if (k == an) va = r[k]; }
                 inverse_couple(vm, va);
                 #pragma unroll
-                for (int k = 0; k < NVB_MAX_CHANNELS; k++) { if (k == m) r[k] = vm; if (k == an) r[k] = va; }
+                for (int k = 0; k < NVB_FAST_CHANNELS; k++) { if (k == m) r[k] = vm; if (k == an) r[k] = va; }
             }
             #pragma unroll
-            for (int c = 0; c < NVB_MAX_CHANNELS; c++) {
+            for (int c = 0; c < NVB_FAST_CHANNELS; c++) {
                 if (c >= C) break;
                 float v = r[c];
                 if ((f.exec_mask >> c) & 1u) v = s_nseg[c] > 0 ? NVB_FMUL(v, s_fl[c * n + j]) : 0.f;      // Floor1.Apply, Floor1.cs:186-222
@@ -1680,7 +1682,7 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         if (nw >= 2) {
             const int num_sms = device_sm_count();
             const size_t smem = shared_part + (size_t)nw * L.total;
-            static std::atomic<size_t> configured_w_by_c[NVB_MAX_DEVICES][NVB_MAX_CHANNELS + 1];    // per device and template instantiation
+            static std::atomic<size_t> configured_w_by_c[NVB_MAX_DEVICES][NVB_FAST_CHANNELS + 1];    // per device and template instantiation
             if (!nvb_ensure_smem(configured_w_by_c[current_device_slot()][C], smem, [&]() {
                     return (C == 1 ? cudaFuncSetAttribute(k_spectrum_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                           : C == 2 ? cudaFuncSetAttribute(k_spectrum_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -1746,7 +1748,7 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         const size_t span = (size_t)C * (a.S.bs[1] / 2) * sizeof(float);
         const size_t smem = span * (size_t)(a.S.max_stages + 1) + (((size_t)a.S.max_items * sizeof(ItemRec) + 15) & ~size_t(15)) +
                             (((size_t)a.S.max_items + 15) & ~size_t(15)) + (size_t)a.S.ci_total * sizeof(int4) + 16;
-        static std::atomic<size_t> configured_pl_by_c[NVB_MAX_DEVICES][NVB_MAX_CHANNELS + 1];   // per device and template instantiation
+        static std::atomic<size_t> configured_pl_by_c[NVB_MAX_DEVICES][NVB_FAST_CHANNELS + 1];   // per device and template instantiation
         if (!nvb_ensure_smem(configured_pl_by_c[current_device_slot()][C], smem, [&]() {
                 return (C == 1 ? cudaFuncSetAttribute(k_spectrum_planes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                       : C == 2 ? cudaFuncSetAttribute(k_spectrum_planes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -1773,9 +1775,12 @@ int launch_spectrum_generic(const LaunchArgs& a, void* stream) {
     if (forbid) return -1;
     size_t smem = spectrum_smem(a.S);
     static std::atomic<size_t> configured_by_dev[NVB_MAX_DEVICES];
-    if (smem > 48 * 1024 - 8192 && !nvb_ensure_smem(configured_by_dev[current_device_slot()], smem, [&]() {
-            return cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
-    NVB_LAUNCH(k_spectrum, a.n_frames, SPEC_THREADS, smem, stream, a);
+    // (static shared memory: 5 KB for up to 8 channels, 18 KB for up to 32 -- ask for the opt-in early)
+    if (smem > 48 * 1024 - 20 * 1024 && !nvb_ensure_smem(configured_by_dev[current_device_slot()], smem, [&]() {
+            return cudaFuncSetAttribute(k_spectrum<NVB_FAST_CHANNELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                   cudaFuncSetAttribute(k_spectrum<NVB_MAX_CHANNELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
+    if (a.S.channels <= NVB_FAST_CHANNELS) NVB_LAUNCH(k_spectrum<NVB_FAST_CHANNELS>, a.n_frames, SPEC_THREADS, smem, stream, a);
+    else NVB_LAUNCH(k_spectrum<NVB_MAX_CHANNELS>, a.n_frames, SPEC_THREADS, smem, stream, a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

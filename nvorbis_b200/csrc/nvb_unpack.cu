@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a, int 
         if (count > 0) live |= 1u << c;
     }
     // energy flags (Mapping.cs:105-119): noExecute is taken before the coupling propagation
-    const uint32_t all = (1u << C) - 1u;
+    const uint32_t all = C >= 32 ? 0xffffffffu : (1u << C) - 1u;
     const uint32_t no_exec = ~live & all;
     uint32_t exec = live;
     for (int k = 0; k < map.n_coupling; k++)

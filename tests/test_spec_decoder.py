@@ -15,7 +15,7 @@ from test_synthetic_setups import SETUPS
 
 # setups with block sizes >= 256 (the reference's transform is not an IMDCT below that)
 SPEC_SETUPS = ["stereo_r2", "six_ch_r2_coupled", "three_ch_r0", "stereo_r1", "stereo_512_1024", "mono_r1_dims_1_16",
-               "stereo_r2_dims_1_16", "stereo_r2_48_posts", "stereo_floor0"]
+               "stereo_r2_dims_1_16", "stereo_r2_48_posts", "stereo_floor0", "twelve_ch_r2_40_steps", "nine_ch_r1"]
 
 
 def spec_case(name, n_frames=10, seed=99):

@@ -28,11 +28,19 @@ SETUPS = {
     "stereo_r2_48_posts": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], floor_posts=46),
     "stereo_floor0": dict(channels=2, bs0=256, bs1=2048, residue_type=2, coupling=[(0, 1)], floor_type=0),
     "quad_floor0_r1": dict(channels=4, bs0=128, bs1=1024, residue_type=1, coupling=[(0, 1), (2, 3)], floor_type=0),
+    # more than 8 channels (round 2: NVB_MAX_CHANNELS 32, NVB_MAX_COUPLING 256; the reference takes up to 255 channels, StreamDecoder.cs:186,
+    # and 256 coupling steps, Mapping.cs:28): the general spectrum kernel's many-channel instantiation; even counts take the fused
+    # kernel's channel-pair units, odd ones whole-frame units while three slots fit, the rest the exact kernels
+    "twelve_ch_r2_40_steps": dict(channels=12, bs0=256, bs1=2048, residue_type=2,
+                                  coupling=[(i % 12, (i * 5 + 1 + (i // 12)) % 12) for i in range(40) if i % 12 != (i * 5 + 1 + (i // 12)) % 12]),
+    "nine_ch_r1": dict(channels=9, bs0=256, bs1=2048, residue_type=1, coupling=[(0, 1), (8, 2), (3, 7)]),
+    "thirty_two_ch_r1": dict(channels=32, bs0=256, bs1=1024, residue_type=1, coupling=[(2 * i, 2 * i + 1) for i in range(16)]),
+    "twelve_ch_floor0_r1": dict(channels=12, bs0=128, bs1=1024, residue_type=1, coupling=[(0, 1), (2, 3), (11, 4)], floor_type=0),
 }
 # type 0 floors end in exp(), sqrt() and cos() of the platform's math library (System.Math in the reference, libm in the
 # oracle, CUDA's double-precision functions on the GPU): results agree to the last float bit almost everywhere, not
 # everywhere -- the "exact" path is held to a relative 1e-6 there instead of bit equality
-FLOOR0 = {"stereo_floor0", "quad_floor0_r1"}
+FLOOR0 = {"stereo_floor0", "quad_floor0_r1", "twelve_ch_floor0_r1"}
 
 
 def _run(name, n_frames, lib_path, seed=1234):
@@ -153,7 +161,8 @@ def test_block_sizes_from_256_up_run_on_the_fused_path():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["stereo_r2", "six_ch_r2_coupled", "three_ch_r0", "stereo_r1", "stereo_r2_dims_1_16", "stereo_floor0"])
+@pytest.mark.parametrize("name", ["stereo_r2", "six_ch_r2_coupled", "three_ch_r0", "stereo_r1", "stereo_r2_dims_1_16", "stereo_floor0", "twelve_ch_r2_40_steps",
+                                  "nine_ch_r1"])
 def test_gpu_matches_the_spec_decoder(name):
     """The GPU path against the second independent witness (tests/spec_decoder.py: float64, from the Vorbis I specification's
     formulas) -- for floor 0, residue 0, lookup type 2, sequence_p and six channels the oracle is not the only reference."""

@@ -272,6 +272,7 @@ def random_records(rng: np.random.Generator, desc: dict, n_frames: int, post_str
             live |= 1 << c
         execm = live
         for mg, an in zip(mp["magnitude"], mp["angle"]):
+            mg, an = int(mg), int(an)                                       # (Python ints: 32 channels fill a 32-bit mask)
             if ((execm >> mg) | (execm >> an)) & 1:
                 execm |= (1 << mg) | (1 << an)
         f = frames[i]
