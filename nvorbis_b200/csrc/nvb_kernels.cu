@@ -1170,6 +1170,11 @@ __global__ void __launch_bounds__(WF_WARPS * 32, NVB_WF_MINB) k_spectrum_wf(Laun
 //            order of the reference's adds), the C values of the bin are C consecutive elements of the partition;
 //            inverse coupling over the registers, floor multiply, one coalesced store per channel row.
 // ------------------------------------------------------------------------------------------------
+// (Round 2 tried the opposite mapping for BASELINE configs[3] -- residue accumulated partition by partition into per-channel planes in
+// shared memory, warp-uniform class / book per partition, stages separated by block barriers and the elements a partition shares with
+// its predecessor's last bin added in a second pass so that the reference's order of adds per cell is kept; then a thread per bin for
+// coupling + floor.  Bit-identical, and slower: 0.66-0.73 ms against 0.51 ms per 8192 six-channel frames, 466 M against 445 M warp
+// instructions -- the per-element index arithmetic and the read-modify-write of the planes cost what the divergence of this gather costs.)
 template <int CT, int NT>
 __global__ void __launch_bounds__(NT) k_spectrum_bins(LaunchArgs a) {
     constexpr int NW = NT / 32;
