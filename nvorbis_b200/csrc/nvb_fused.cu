@@ -686,7 +686,8 @@ static int fused_slots(int C, int units_per_frame = 1) {
     const size_t fixed = FusedTables::FLOATS * sizeof(float) + 64;
     const size_t per = (size_t)C * FUSED_SLOT_FLOATS * sizeof(float) + sizeof(DevFrame) + 2 * sizeof(int);
     int ns = (int)((FUSED_SMEM_LIMIT - fixed) / per);
-    const int want = FUSED_WARPS + units_per_frame + 1;
+    static const int extra = std::getenv("NVB_FUSED_EXTRA_SLOTS") ? std::atoi(std::getenv("NVB_FUSED_EXTRA_SLOTS")) : 0;   // experiment hook
+    const int want = FUSED_WARPS + units_per_frame + 1 + (extra > 0 ? extra : 0);
     if (ns > want) ns = want;
     return ns;
 }

@@ -294,6 +294,8 @@ __device__ __forceinline__ void wf_main(const LaunchArgs& a, const WfFrame<CT, P
             unsigned rest = cw >> 8;
             const int cl = (int)(cw & 0xffu);
             const int o = q & pmask;
+            // (L1 policy hints on these loads -- evict_last for the VQ tables, evict_first for the entries -- measured slower in round 2:
+            //  23.7 vs 21.8 us)
             while (rest) {                                                  // one iteration for most partitions
                 const int st = __ffs(rest) - 1; rest &= rest - 1;
                 // the (class, stage) record: from the CTA's shared-memory copy in the one-kernel path (its L1 is a few KB: 220 KB of the
