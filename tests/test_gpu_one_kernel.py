@@ -137,3 +137,24 @@ def test_slot_ring_under_stress_one_kernel():
             outs.append(np.load(path))
         for o in outs[1:]:
             np.testing.assert_array_equal(o, outs[0])
+
+
+def test_output_forms_one_kernel():
+    """NVB_RUN_PCM_S16 and NVB_RUN_DEVICE_OUT with the one-kernel launch shape: the same bytes as with two kernels."""
+    import torch
+    r, pcm, b = H.decoded("3test")
+    ctx = capi.Context(0); ctx.upload_setup(H.setup_from_oracle(r))
+    hb = H.batch_from_boundary(b, ctx.post_stride)
+    res = {}
+    for mode in (capi.RUN_ONE_KERNEL, capi.RUN_TWO_KERNELS):
+        ctx.reset()
+        s16, _ = ctx.decode_batch(hb, mode | capi.RUN_PCM_S16)
+        ctx.reset()
+        dev = torch.zeros(pcm.size + 64, dtype=torch.float32, device="cuda")
+        ctx.decode_batch_begin(hb, mode | capi.RUN_DEVICE_OUT, dev.data_ptr(), dev.numel())
+        rr = ctx.decode_batch_end()
+        res[mode] = (s16.copy(), dev.cpu().numpy()[: rr.samples_per_channel * 2].copy())
+    np.testing.assert_array_equal(res[capi.RUN_ONE_KERNEL][0], res[capi.RUN_TWO_KERNELS][0])
+    np.testing.assert_array_equal(res[capi.RUN_ONE_KERNEL][1], res[capi.RUN_TWO_KERNELS][1])
+    assert float(np.abs(res[capi.RUN_ONE_KERNEL][1] - pcm).max()) <= TOL
+    ctx.close()

@@ -104,7 +104,7 @@ def test_device_records_equal_host_records(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", H.FIXTURES)
-@pytest.mark.parametrize("flags", [capi.RUN_EXACT, capi.RUN_DEFAULT])
+@pytest.mark.parametrize("flags", [capi.RUN_EXACT, capi.RUN_DEFAULT, capi.RUN_ONE_KERNEL, capi.RUN_TWO_KERNELS])
 def test_packets_to_pcm(name, flags):
     _compare_pcm(name, None, 97, flags)
 
