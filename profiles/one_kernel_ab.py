@@ -38,8 +38,10 @@ def main():
     C = ctx.channels
     stream = torch.cuda.current_stream().cuda_stream
     out = {}
-    for label, frames, rotate, steps in (("64 frames", 64, 6, 50), ("256 frames", 256, 6, 50), ("1024 frames", 1024, 6, 40), ("configs[1] 4096 frames", 4096, 6, 20),
-                                         ("configs[4] 65536 frames", 65536, 2, 4)):
+    sizes = [int(x) for x in sys.argv[1:]] if len(sys.argv) > 1 else None
+    cases = [(f"{n} frames", n, 6, 40) for n in sizes] if sizes else [("64 frames", 64, 6, 50), ("256 frames", 256, 6, 50), ("1024 frames", 1024, 6, 40),
+                                                                      ("configs[1] 4096 frames", 4096, 6, 20), ("configs[4] 65536 frames", 65536, 2, 4)]
+    for label, frames, rotate, steps in cases:
         hbs = [workloads.config2(pool, frames, 20240002 + s) for s in range(rotate)]
         row = {}
         ref = None
