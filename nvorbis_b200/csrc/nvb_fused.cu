@@ -23,6 +23,9 @@
 //   * the previous block's tail never touches HBM: each spectrum float is read once and each PCM float is
 //     written once (16 384 B per stereo long frame); the first block of a run is recomputed as a halo;
 //   * output: two samples x two channels per lane as one float4 store, a warp writes 512 contiguous bytes.
+//   Round 2: both transforms of a stereo unit interleaved phase by phase (two independent instruction streams between the warp barriers,
+//   no register prefetch: 2 x 32 data registers) -- 20.8 vs 17.8 us per 4096 frames and 7.7 vs 7.0 us for the single-frame chain (512
+//   frames): at 128 registers ptxas serialises and spills instead of overlapping the streams.
 //   Variants measured and dropped (profiles/r01_d, r01_f): TMA staging of the spectrum rows into the slot (the extra
 //   LDS of the inputs costs more shared-memory bandwidth than the exposed load latency it saves); 32 warps x 64
 //   registers with one warp per channel (more twiddle loads and counter polling, slower).
