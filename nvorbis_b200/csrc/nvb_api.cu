@@ -300,6 +300,8 @@ LaunchArgs make_args(nvb_ctx* ctx, nvb_dbatch* b, float* spectrum, float* d_pcm,
 int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pcm, bool save_carry, cudaStream_t st,
             int frame_lo = 0, int frame_cnt = -1, bool reset_counters = true, cudaEvent_t after_spectrum = nullptr, cudaEvent_t before_synth = nullptr) {
     if (b->plan.frames.empty()) { b->launches = 0; return NVB_OK; }
+    static const int no_pdl = std::getenv("NVB_NO_PDL") ? std::atoi(std::getenv("NVB_NO_PDL")) : 0;      // experiment hook: 1 = no programmatic early start at all
+    NvbNoEarlyStart no_early(no_pdl == 1);
     LaunchArgs a = make_args(ctx, b, spectrum ? spectrum : b->d_spectrum, d_pcm, save_carry);
     if (frame_cnt >= 0) { a.frame_lo = frame_lo; a.n_frames = frame_cnt; }
     int launches = 0, r;
@@ -321,6 +323,7 @@ int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pc
         }
     }
     if (stage != 2) {
+        NvbNoEarlyStart spec_no_early(no_pdl == 2);                           // 2: the spectrum kernel waits for everything before it
         if ((r = launch_spectrum(a, st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_spectrum launch");
         launches += r;
         if (after_spectrum) NVB_CUDA(ctx, cudaEventRecord(after_spectrum, st));
@@ -328,6 +331,7 @@ int enqueue(nvb_ctx* ctx, nvb_dbatch* b, int stage, float* spectrum, float* d_pc
     if (stage != 1) {
         if (before_synth) NVB_CUDA(ctx, cudaStreamWaitEvent(st, before_synth, 0));     // the halo block's spectrum comes from the previous chunk
         if (b->fused) {
+            NvbNoEarlyStart imdct_no_early(no_pdl == 3);                      // 3: the IMDCT kernel starts only after the spectrum kernel has ended
             if ((r = launch_imdct_fused(a, b->plan.frames.data(), st)) < 0) return cuda_fail(ctx, cudaGetLastError(), "k_imdct_fused launch");
             launches += r;
         } else {

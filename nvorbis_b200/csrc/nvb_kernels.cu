@@ -1055,8 +1055,12 @@ __global__ void __launch_bounds__(NT, MINB) k_spectrum_run(LaunchArgs a) {
 //            and a switch to the next active post when the bin reaches the segment's end.
 // Results are bit-identical to k_spectrum_run / the oracle (same float adds in the same order, same integer floor curve).
 // ------------------------------------------------------------------------------------------------
-template <int CT, int WPF, bool P64>
-__global__ void __launch_bounds__(WF_WARPS * 32, NVB_WF_MINB) k_spectrum_wf(LaunchArgs a, WfLayout L) {
+// MINB: CTAs per SM the registers are capped for -- 8 (64 registers; the throughput form: 3 % faster on the 65 536-frame launch) or 7 (72
+// registers, fewer spills; the form for launches of up to 16 384 frames: the kernel is then a single wave of dependent chains, and under
+// programmatic dependent launch the CTAs of the next launch pile up on the SMs that drain first -- a cap of 7 spreads 1024 CTAs over 147
+// SMs: 14.3 vs 18.4 us on 1024 frames, 15.1 vs 19.9 us on 2048, a 4096-frame spectrum + IMDCT step on one stream 41.7 vs 44.4 us).
+template <int CT, int WPF, bool P64, int MINB = NVB_WF_MINB>
+__global__ void __launch_bounds__(WF_WARPS * 32, MINB) k_spectrum_wf(LaunchArgs a, WfLayout L) {
     constexpr int FPC = WF_WARPS / WPF;                                     // frames per CTA
     constexpr int GT = WPF * 32;                                            // threads per frame group
     constexpr int H = P64 ? 2 : 1;
@@ -1713,6 +1717,8 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
         const size_t smem = (size_t)L.cta_bytes + (size_t)L.total * fpc;
         if (smem <= 200 * 1024 && L.cta_bytes <= 16 * 1024) {
             const bool p64 = L.np_pad > 32;
+            static const bool no_small = std::getenv("NVB_WF_NO_SMALL") != nullptr;              // experiment hook: always the 8-CTA form
+            const bool small = a.n_frames <= 16384 && !no_small;
             auto go = [&](auto kernel) -> int {
                 static std::atomic<size_t> configured[NVB_MAX_DEVICES];       // one per instantiation (a lambda instantiation has its own statics)
                 // static + dynamic shared memory above 48 KB needs the opt-in: ask for it whenever the dynamic part is not small
@@ -1722,6 +1728,7 @@ int launch_spectrum(const LaunchArgs& a, void* stream) {
                 return cudaGetLastError() == cudaSuccess ? 1 : -1;
             };
 #define NVB_WF_CASE(CT_)                                                                                          \
+            if (WPF == 1 && small) return p64 ? go(k_spectrum_wf<CT_, 1, true, 7>) : go(k_spectrum_wf<CT_, 1, false, 7>); \
             if (WPF == 1) return p64 ? go(k_spectrum_wf<CT_, 1, true>) : go(k_spectrum_wf<CT_, 1, false>);          \
             if (WPF == 2) return p64 ? go(k_spectrum_wf<CT_, 2, true>) : go(k_spectrum_wf<CT_, 2, false>);          \
             return p64 ? go(k_spectrum_wf<CT_, 4, true>) : go(k_spectrum_wf<CT_, 4, false>);
