@@ -7,7 +7,8 @@ import __graft_entry__ as g
 import helpers as H
 import test_synthetic_setups as T
 g.smoke()                                                    # 1test + 3test: k_spectrum_run, exact + fused paths
-for name in ("six_ch_r2_coupled", "stereo_floor0", "three_ch_r0", "tiny_blocks_r1_lookup2_seq", "stereo_512_1024", "mono_r1_big"):
+for name in ("six_ch_r2_coupled", "stereo_floor0", "three_ch_r0", "tiny_blocks_r1_lookup2_seq", "stereo_512_1024", "mono_r1_big",
+             "twelve_ch_r2_40_steps", "nine_ch_r1", "thirty_two_ch_r1", "twelve_ch_floor0_r1"):
     T._run(name, 24, None, seed=5)                           # k_spectrum_bins / general kernel with type 0 floors / k_spectrum_fast / exact kernels
 # both launch shapes explicitly (small batches default to the one-kernel path: k_imdct_fused_t<false, C> with the spectrum stage inside)
 import numpy as np
