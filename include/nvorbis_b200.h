@@ -277,7 +277,7 @@ int nvb_decode_batch_end(nvb_ctx* ctx, nvb_result* res);
  * the host would have sent.  The host keeps what is sequential across packets: container paging and, per packet, the values
  * of Mode.GetPacketInfo (Mode.cs:119-151: mode / window flags from the packet's first bits) after the granule bookkeeping
  * and the end-of-stream trim (StreamDecoder.cs:417-463).  H2D shrinks to the raw packets (about 300 B instead of 1.5 KB per
- * stereo frame).  Setups with a type 0 floor are not unpacked on the device (NVB_ERR_UNSUPPORTED): use nvb_decode_batch. */
+ * stereo frame).  Type 0 floors (Floor0.Unpack, Floor0.cs:98-150) are unpacked on the device as well. */
 typedef struct nvb_packet_batch {
     int32_t          n_packets;
     int32_t          reserved;

@@ -865,7 +865,6 @@ static void packet_header(const nvh_stream& s, const PacketRef& pr, UnpackedFram
 // The unpack tables of the setup (csrc/nvb_unpack_tables.h).
 static int build_unpack_tables(nvh_stream& s) {
     using namespace nvbu;
-    for (int t : s.floor_type) if (t != 1) { s.err = "a type 0 floor is not unpacked on the device"; return NVB_ERR_UNSUPPORTED; }
     for (const MappingDef& m : s.mappings) if (m.submaps != 1) { s.err = "multi-submap mappings are not supported"; return NVB_ERR_UNSUPPORTED; }
     if (s.channels > NVB_MAX_CHANNELS) { s.err = "too many channels"; return NVB_ERR_UNSUPPORTED; }
     std::vector<UBook> books; std::vector<uint32_t> roots; std::vector<ULong> longs;
@@ -884,8 +883,18 @@ static int build_unpack_tables(nvh_stream& s) {
         books.push_back(u);
     }
     std::vector<UFloor1> floors;
-    for (const Floor1Def& f : s.floors) {
+    for (size_t fi = 0; fi < s.floors.size(); fi++) {
+        const Floor1Def& f = s.floors[fi];
         UFloor1 u; std::memset(&u, 0, sizeof u);
+        if (s.floor_type[fi] == 0) {                                        // Floor0.Init (Floor0.cs:28-51): what Floor0.Unpack reads
+            const Floor0Def& z = s.floors0[fi];
+            if (z.books.size() > 16) { s.err = "floor 0 book list outside the device tables"; return NVB_ERR_UNSUPPORTED; }
+            u.type = 0; u.f0.order = z.order; u.f0.amp_bits = z.amp_bits; u.f0.amp_div = z.amp_div; u.f0.amp_ofs = z.amp_ofs; u.f0.book_bits = z.book_bits;
+            u.f0.n_books = (int32_t)z.books.size();
+            for (size_t k = 0; k < z.books.size(); k++) u.f0.books[k] = (int16_t)z.books[k];
+            floors.push_back(u);
+            continue;
+        }
         u.type = 1; u.n_parts = (int32_t)f.part_class.size(); u.ybits = f.ybits; u.n_posts = (int32_t)f.x.size();
         if (u.n_parts > 32 || f.class_dims.size() > 16) { s.err = "floor 1 structure outside the device tables"; return NVB_ERR_UNSUPPORTED; }
         for (size_t k = 0; k < f.part_class.size(); k++) u.part_class[k] = (uint8_t)f.part_class[k];
@@ -933,7 +942,7 @@ static int build_unpack_tables(nvh_stream& s) {
     std::vector<UMapping> mappings;
     for (const MappingDef& m : s.mappings) {
         UMapping u; std::memset(&u, 0, sizeof u);
-        if (m.mag.size() > 32) { s.err = "too many coupling steps"; return NVB_ERR_UNSUPPORTED; }
+        if (m.mag.size() > (size_t)UNPACK_MAX_COUPLING) { s.err = "too many coupling steps"; return NVB_ERR_UNSUPPORTED; }
         u.n_coupling = (int32_t)m.mag.size(); u.floor = m.floor0; u.residue = m.residue0;
         for (size_t k = 0; k < m.mag.size(); k++) { u.mag[k] = (uint8_t)m.mag[k]; u.ang[k] = (uint8_t)m.ang[k]; }
         mappings.push_back(u);
@@ -942,7 +951,7 @@ static int build_unpack_tables(nvh_stream& s) {
     for (const ModeDef& m : s.modes) modes.push_back(UMode{m.long_block ? 1 : 0, m.mapping});
 
     UHeader h; std::memset(&h, 0, sizeof h);
-    h.magic = UNPACK_MAGIC; h.version = 1; h.channels = s.channels; h.bs[0] = s.bs[0]; h.bs[1] = s.bs[1]; h.mode_bits = s.mode_bits;
+    h.magic = UNPACK_MAGIC; h.version = 2; h.f0_stride = s.f0_stride; h.channels = s.channels; h.bs[0] = s.bs[0]; h.bs[1] = s.bs[1]; h.mode_bits = s.mode_bits;
     h.n_books = (int32_t)books.size(); h.n_floors = (int32_t)floors.size(); h.n_residues = (int32_t)residues.size();
     h.n_mappings = (int32_t)mappings.size(); h.n_modes = (int32_t)modes.size();
     h.post_stride = s.post_stride; h.cls_stride = cls_stride; h.ent_stride = ent_stride;

@@ -228,12 +228,12 @@ int upload_packets(nvb_ctx* ctx, nvb_dbatch* b, const nvb_packet_batch* pb, int 
     static const int16_t dummy_posts = 0;
     nvb_batch tmp; std::memset(&tmp, 0, sizeof tmp);
     tmp.n_frames = pb->n_packets; tmp.frames = b->pkt_frames.data(); tmp.posts = &dummy_posts;
-    static const uint8_t dummy_c = 0; static const uint16_t dummy_e = 0;
+    static const uint8_t dummy_c = 0; static const uint16_t dummy_e = 0; static const float dummy_f = 0.f;
+    tmp.floor0 = &dummy_f;                                                  // (type 0 floor records are produced on the device: plan_batch only asks for a pointer)
     tmp.classes = &dummy_c; tmp.n_classes = (int64_t)(n * cs); tmp.entries = &dummy_e; tmp.n_entries = (int64_t)(n * es);
     std::string err;
     int rc = plan_batch(ctx->host_blob.data(), &tmp, flags, ctx->carry, b->plan, err);
     if (rc != NVB_OK) return set_err(ctx, rc, err);
-    if (b->plan.uses_floor0) return set_err(ctx, NVB_ERR_UNSUPPORTED, "type 0 floors are not unpacked on the device");
     b->flags = flags; b->from_packets = true;
     b->fused = !(flags & NVB_RUN_EXACT) && fused_supported(ctx->H, b->plan.frames.data(), (int)b->plan.frames.size());
     const size_t nf = b->plan.frames.size();
@@ -243,6 +243,7 @@ int upload_packets(nvb_ctx* ctx, nvb_dbatch* b, const nvb_packet_batch* pb, int 
     if ((rc = grow(ctx, b->d_posts, b->cap_posts, n_posts)) != NVB_OK) return rc;
     if ((rc = grow(ctx, b->d_classes, b->cap_classes, n * cs)) != NVB_OK) return rc;
     if ((rc = grow(ctx, b->d_entries, b->cap_entries, n * es)) != NVB_OK) return rc;
+    if (ctx->H.f0_stride > 0 && (rc = grow(ctx, b->d_floor0, b->cap_floor0, n * ctx->H.channels * ctx->H.f0_stride)) != NVB_OK) return rc;   // type 0 floor records, written by k_unpack
     if ((rc = grow(ctx, b->d_pkt, b->cap_pkt, bytes + 16)) != NVB_OK) return rc;
     if ((rc = grow(ctx, b->d_pkt_off, b->cap_pkt_off, n + 1)) != NVB_OK) return rc;
     if ((rc = grow(ctx, b->d_spectrum, b->cap_spectrum, (size_t)b->plan.spec_floats)) != NVB_OK) return rc;
@@ -272,6 +273,7 @@ int enqueue_unpack(nvb_ctx* ctx, nvb_dbatch* b, cudaStream_t st, int frame_lo, i
     UnpackArgs u;
     u.T = ctx->UT; u.frames = b->d_frames; u.frame_lo = frame_lo; u.n_frames = frame_cnt;
     u.data = b->d_pkt; u.offsets = b->d_pkt_off; u.posts = b->d_posts; u.classes = b->d_classes; u.entries = b->d_entries;
+    u.floor0 = ctx->H.f0_stride > 0 ? b->d_floor0 : nullptr; u.f0_stride = ctx->H.f0_stride; u.dbooks = ctx->S.books; u.vq = ctx->S.vq;
     const int r = launch_unpack(u, st);
     if (r < 0) return cuda_fail(ctx, cudaGetLastError(), "k_unpack launch");
     return NVB_OK;
@@ -663,7 +665,7 @@ int nvb_upload_unpack_tables(nvb_ctx* ctx, const void* blob, size_t bytes) {
     using namespace nvbu;
     if (bytes < sizeof(UHeader)) return set_err(ctx, NVB_ERR_DATA, "unpack tables: blob too small");
     UHeader h; std::memcpy(&h, blob, sizeof h);
-    if (h.magic != UNPACK_MAGIC || h.version != 1 || h.total_bytes != bytes) return set_err(ctx, NVB_ERR_DATA, "unpack tables: magic / size mismatch");
+    if (h.magic != UNPACK_MAGIC || h.version != 2 || h.total_bytes != bytes) return set_err(ctx, NVB_ERR_DATA, "unpack tables: magic / size mismatch");
     if (h.channels != ctx->H.channels || h.bs[0] != ctx->H.bs[0] || h.bs[1] != ctx->H.bs[1] || h.post_stride != ctx->H.post_stride ||
         h.n_books != ctx->H.n_books || h.n_floors != ctx->H.n_floors || h.n_residues != ctx->H.n_residues || h.n_mappings != ctx->H.n_mappings || h.n_modes != ctx->H.n_modes)
         return set_err(ctx, NVB_ERR_DATA, "unpack tables do not belong to the uploaded setup");
@@ -696,6 +698,14 @@ int nvb_upload_unpack_tables(nvb_ctx* ctx, const void* blob, size_t bytes) {
     const UFloor1* floors = reinterpret_cast<const UFloor1*>(base + h.off_floors);
     for (int i = 0; i < h.n_floors; i++) {
         const UFloor1& f = floors[i];
+        if (f.type == 0) {                                                  // type 0: the fields Floor0.Unpack reads; the records must fit the setup's stride
+            const UFloor0& z = f.f0;
+            if (z.order < 1 || z.order + 1 > h.f0_stride || h.f0_stride != ctx->H.f0_stride || z.amp_bits < 0 || z.amp_bits > 32 || z.amp_div < 1 || z.book_bits < 0 ||
+                z.book_bits > 5 || z.n_books < 1 || z.n_books > 16) return set_err(ctx, NVB_ERR_DATA, "unpack tables: type 0 floor");
+            for (int k = 0; k < z.n_books; k++)
+                if (z.books[k] < 0 || z.books[k] >= h.n_books || ctx->S.n_vq <= 0) return set_err(ctx, NVB_ERR_DATA, "unpack tables: type 0 floor book");
+            continue;
+        }
         if (f.type != 1 || f.n_parts < 0 || f.n_parts > 32 || f.ybits < 1 || f.ybits > 16 || f.n_posts < 2 || f.n_posts > NVB_MAX_POSTS) return set_err(ctx, NVB_ERR_DATA, "unpack tables: floor");
         int posts = 2;
         for (int p = 0; p < f.n_parts; p++) {
@@ -723,7 +733,7 @@ int nvb_upload_unpack_tables(nvb_ctx* ctx, const void* blob, size_t bytes) {
     const UMapping* mappings = reinterpret_cast<const UMapping*>(base + h.off_mappings);
     for (int i = 0; i < h.n_mappings; i++) {
         const UMapping& m = mappings[i];
-        if (m.n_coupling < 0 || m.n_coupling > 32 || m.floor < 0 || m.floor >= h.n_floors || m.residue < 0 || m.residue >= h.n_residues) return set_err(ctx, NVB_ERR_DATA, "unpack tables: mapping");
+        if (m.n_coupling < 0 || m.n_coupling > UNPACK_MAX_COUPLING || m.floor < 0 || m.floor >= h.n_floors || m.residue < 0 || m.residue >= h.n_residues) return set_err(ctx, NVB_ERR_DATA, "unpack tables: mapping");
         for (int k = 0; k < m.n_coupling; k++) if (m.mag[k] >= h.channels || m.ang[k] >= h.channels) return set_err(ctx, NVB_ERR_DATA, "unpack tables: coupling");
     }
     const UMode* modes = reinterpret_cast<const UMode*>(base + h.off_modes);

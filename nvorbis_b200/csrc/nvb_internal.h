@@ -227,6 +227,8 @@ struct UnpackArgs {
     DevFrame* frames; int frame_lo, n_frames;      // plan frames [frame_lo, frame_lo + n_frames): exec_mask / res_decoded / entry_count are written
     const uint8_t* data; const uint32_t* offsets;  // packets of the batch (by api_index), padded by 8 bytes
     int16_t* posts; uint8_t* classes; uint16_t* entries;
+    float* floor0; int f0_stride;                  // type 0 floor records [packet][channel][f0_stride] (nullptr: the setup has none)
+    const DevBook* dbooks; const float* vq;        // the synthesis setup's VQ tables: Floor0.Unpack reads its coefficients out of them
 };
 int launch_unpack(const UnpackArgs& a, void* stream);
 

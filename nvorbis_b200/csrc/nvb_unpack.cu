@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #endif
 #include "nvb_internal.h"
+#include "nvb_device_core.h"
 #include "nvb_unpack_tables.h"
 
 namespace nvb {
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a, int 
         for (uint32_t o = p0 + 128u * lane; o < p1; o += 128u * 32u) prefetch_l1_u(a.data + o);
         int16_t* posts = a.posts + (size_t)api * C * T.post_stride;
         for (int k = lane; k < C * T.post_stride; k += 32) posts[k] = 0;
+        if (a.floor0) for (int k = lane; k < C * a.f0_stride; k += 32) a.floor0[(size_t)api * C * a.f0_stride + k] = 0.f;
         // the class bytes are read back partition by partition while the stages are walked: they live in shared memory during
         // the walk (when the setup's stride fits) and are copied out by the whole warp at the end
         uint8_t* cls0 = smem_cls ? dyn_smem + (size_t)(threadIdx.x >> 5) * T.cls_stride : a.classes + (size_t)api * T.cls_stride;
@@ -121,6 +123,39 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) k_unpack(UnpackArgs a, int 
     uint32_t live = 0u;
     for (int c = 0; c < C; c++) {
         int16_t* dst = a.posts + ((size_t)api * C + c) * T.post_stride;
+        if (f.type == 0) {
+            // Floor0.Unpack (Floor0.cs:98-150): amplitude, book number, the LSP coefficients as VQ vectors, then the running sum
+            const nvbu::UFloor0& z = f.f0;
+            float* pl = a.floor0 + ((size_t)api * C + c) * a.f0_stride;
+            float amp = (float)b.read((uint32_t)z.amp_bits);
+            if (amp > 0.f) {
+                amp = NVB_FMUL(NVB_FDIV(amp, (float)z.amp_div), (float)z.amp_ofs);
+                const uint32_t book_num = b.read((uint32_t)z.book_bits);
+                if (book_num >= (uint32_t)z.n_books) amp = 0.f;
+                else {
+                    const int bk = z.books[book_num];
+                    const nvbu::UBook vb = T.books[bk];
+                    const float* tab = a.vq + a.dbooks[bk].off;
+                    const int dims = vb.dims;
+                    for (int i = 0; i < z.order && amp > 0.f;) {
+                        const int e = book_decode(T, vb, b);
+                        if (e < 0) { amp = 0.f; break; }
+                        for (int j = 0; i < z.order && j < dims; j++, i++) pl[1 + i] = tab[(size_t)e * dims + j];
+                    }
+                    if (amp > 0.f) {
+                        float last = 0.f;
+                        for (int j = 0; j < z.order;) {
+                            for (int k = 0; j < z.order && k < dims; j++, k++) pl[1 + j] = NVB_FADD(pl[1 + j], last);
+                            last = pl[j];                                   // Coeff[j - 1]
+                        }
+                    }
+                }
+            }
+            pl[0] = amp;
+            dst[0] = 0;
+            if (amp > 0.f) live |= 1u << c;
+            continue;
+        }
         int count = 0;
         if (b.read(1u)) {
             count = 2;

@@ -18,10 +18,12 @@ constexpr int ROOT_BITS = 10;                     // codewords up to this length
 struct UBook { int32_t dims, entries, root_bits, decodable; uint32_t root_off, long_off; int32_t n_long, pad; };
 struct ULong { uint32_t code; int32_t value; int32_t next; uint32_t len; };            // next: 1 + index (0 = end of chain), relative to the book's long_off
 
-struct UFloor1 {                                                                       // Floor1.cs:30-133 (type 1), or type = 0: not unpacked on the GPU
+struct UFloor0 { int32_t order, amp_bits, amp_div, amp_ofs, book_bits, n_books; int16_t books[16]; int32_t pad[2]; };   // Floor0.Init, Floor0.cs:28-51
+struct UFloor1 {                                                                       // Floor1.cs:30-133 (type 1); type 0: only f0 is meaningful
     int32_t type, n_parts, ybits, n_posts;
     uint8_t part_class[32]; uint8_t class_dims[16]; uint8_t class_subs[16];
     int16_t class_master[16]; int16_t sub_books[16][8];
+    UFloor0 f0;
 };
 struct UResidue {                                                                      // Residue0.cs:35-117
     int32_t type, begin, end, psize, nclass, class_book, stages, cdims;               // cdims = dimensions of the class book (partitions per class word)
@@ -30,7 +32,8 @@ struct UResidue {                                                               
     int32_t cascade[64]; int16_t books[64][8];
     int32_t pad[2];
 };
-struct UMapping { int32_t n_coupling, floor, residue, pad; uint8_t mag[32], ang[32]; };
+constexpr int UNPACK_MAX_COUPLING = 256;          // = NVB_MAX_COUPLING (Mapping.cs:28: 8 bits + 1)
+struct UMapping { int32_t n_coupling, floor, residue, pad; uint8_t mag[UNPACK_MAX_COUPLING], ang[UNPACK_MAX_COUPLING]; };
 struct UMode { int32_t block_flag, mapping; };
 
 struct UHeader {
@@ -41,7 +44,8 @@ struct UHeader {
     int32_t post_stride;          // int16 per (frame, channel), the same rule as nvb_post_stride()
     int32_t cls_stride;           // class bytes a frame can need (largest streams * partitions of any mode)
     int32_t ent_stride;           // VQ entries a frame can need (largest sum over stages of partitions * entries per partition)
-    uint32_t n_roots, n_longs, n_digits, pad;
+    uint32_t n_roots, n_longs, n_digits;
+    int32_t f0_stride;            // floats per (frame, channel) of the type 0 floor records (amplitude + coefficients), 0 = no type 0 floor
     uint64_t off_books, off_roots, off_longs, off_floors, off_residues, off_digits, off_mappings, off_modes;
 };
 

@@ -103,14 +103,14 @@ def _floor0_stream(name, n_frames, seed):
     return data, sizes, np.zeros(len(sizes), np.int64), np.zeros(len(sizes), np.uint8)
 
 
-def _run_floor0_packets(name, n_frames, lib_path, seed=7):
+def _run_floor0_packets(name, n_frames, lib_path, seed=7, gpu_unpack=False):
     """Floor 0 end to end from PACKETS: the oracle's full decode (Floor0.Unpack + Apply restated) against the product's
     host unpacker + synthesis behind the VorbisReader mirror."""
     from nvorbis_b200.reader import VorbisReader
     d, s, g, f = _floor0_stream(name, n_frames, seed)
     want = O.OracleReader(O.PacketList(d, s, g, f)).read_all()
     assert want.size > 0 and np.isfinite(want).all() and float(np.abs(want).max()) > 1e-3
-    with VorbisReader((d, s, g, f), batch_packets=11, lib_path=lib_path) as vr:
+    with VorbisReader((d, s, g, f), batch_packets=11, lib_path=lib_path, gpu_unpack=gpu_unpack) as vr:
         got = vr.read_all(chunk_seconds=0.25)
     assert got.size == want.size and float(np.abs(got - want).max()) <= 1e-5
 
@@ -120,10 +120,22 @@ def test_floor0_packets_on_cpu_shim(name):
     _run_floor0_packets(name, 14, H.build_shim())
 
 
+@pytest.mark.parametrize("name", sorted(FLOOR0))
+def test_floor0_packets_device_unpack_on_cpu_shim(name):
+    """Floor0.Unpack on the device (k_unpack, round 2): amplitude, book number, LSP coefficients out of the VQ tables, running sum."""
+    _run_floor0_packets(name, 14, H.build_shim(), gpu_unpack=True)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(FLOOR0))
 def test_floor0_packets_on_gpu(name):
     _run_floor0_packets(name, 400, None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FLOOR0))
+def test_floor0_packets_device_unpack_on_gpu(name):
+    _run_floor0_packets(name, 400, None, gpu_unpack=True)
 
 
 def test_unaligned_type2_residues_run_on_the_bins_kernel():
