@@ -12,6 +12,9 @@ import numpy as np
 from . import capi, hostlib
 
 
+SEEK_BEGIN, SEEK_CURRENT, SEEK_END = 0, 1, 2          # System.IO.SeekOrigin
+
+
 class VorbisReader:
     """`new VorbisReader(stream)` ... `ReadSamples(buffer, offset, count)` (VorbisReader.cs:42-64, 336-345)."""
 
@@ -28,7 +31,7 @@ class VorbisReader:
         self._ctx = capi.Context(device, lib_path=lib_path)
         self._ctx.upload_setup(self._host.setup())
         # GPU-side packet unpack (nvb_decode_packets): the host only pages the container and reads each packet's first bits;
-        # None = use it whenever the setup is covered (no type 0 floor), False = host unpacker (nvh_unpack) + nvb_decode_batch
+        # None = use it whenever the setup is covered by the device tables, False = host unpacker (nvh_unpack) + nvb_decode_batch
         self._gpu_unpack = False
         if gpu_unpack is None or gpu_unpack:
             try:
@@ -73,8 +76,24 @@ class VorbisReader:
         return self._eos and self._pos >= self._pcm.size
 
     @property
-    def sample_position(self) -> int:
+    def sample_position(self) -> int:                   # VorbisReader.SamplePosition (VorbisReader.cs:237-244): get, or set = SeekTo(value)
         return self._samples_read
+
+    @sample_position.setter
+    def sample_position(self, value: int):
+        self.seek_to(value)
+
+    @property
+    def time_position(self) -> float:                   # TimePosition in seconds (StreamDecoder.cs: currentPosition / sampleRate); set = SeekTo(TimeSpan)
+        return self._samples_read / self.sample_rate
+
+    @time_position.setter
+    def time_position(self, seconds: float):
+        self.seek_to_time(seconds)
+
+    @property
+    def total_time(self) -> float:                      # TotalTime in seconds (TotalSamples / SampleRate)
+        return self.total_samples / self.sample_rate
 
     def _begin_next(self) -> bool:
         """Unpacks the next run of packets and puts it on the GPU; False when the stream has no more packets."""
@@ -150,9 +169,21 @@ class VorbisReader:
             self._total = self._host.total_samples()
         return self._total
 
-    def seek_to(self, sample_position: int):
-        """SeekTo(samplePosition) (StreamDecoder.cs:562-628): the next read_samples starts at that sample.  Decoding restarts
-        one packet early (the pre-roll packet only leaves its overlap tail) and rolls forward inside the next block."""
+    def seek_to_time(self, seconds: float, origin: int = SEEK_BEGIN):
+        """SeekTo(TimeSpan, SeekOrigin) (StreamDecoder.cs:551-554): (long)(SampleRate * TotalSeconds), then the sample form."""
+        self.seek_to(int(self.sample_rate * float(seconds)), origin)
+
+    def seek_to(self, sample_position: int, origin: int = SEEK_BEGIN):
+        """SeekTo(samplePosition, seekOrigin) (StreamDecoder.cs:562-628): the next read_samples starts at that sample.  Decoding restarts
+        one packet early (the pre-roll packet only leaves its overlap tail) and rolls forward inside the next block.  The origins
+        follow the reference to the letter: Current means SamplePosition - samplePosition (StreamDecoder.cs:572), End means
+        TotalSamples - samplePosition (:575)."""
+        if origin == SEEK_CURRENT:
+            sample_position = self.sample_position - sample_position
+        elif origin == SEEK_END:
+            sample_position = self.total_samples - sample_position
+        elif origin != SEEK_BEGIN:
+            raise IndexError("seekOrigin")                                       # ArgumentOutOfRangeException
         if sample_position < 0:
             raise IndexError("samplePosition")                                   # ArgumentOutOfRangeException
         if self._inflight is not None:

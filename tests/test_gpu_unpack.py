@@ -126,6 +126,20 @@ def _seek_case(name, lib_path, positions, gpu_unpack):
             assert n == want.size and float(np.abs(buf[:n] - want).max()) <= 1e-5, (name, pos)
         vr.seek_to(pcm.size // C)                          # the very end: nothing left
         assert vr.read_samples(np.zeros(64 * C, np.float32), 0, 64 * C) == 0
+        # SeekOrigin forms and the time properties (VorbisReader.cs:215-244, StreamDecoder.cs:562-579): Current SUBTRACTS, like the reference
+        from nvorbis_b200.reader import SEEK_CURRENT, SEEK_END
+        total = pcm.size // C
+        assert abs(vr.total_time - total / vr.sample_rate) < 1e-12
+        vr.seek_to(1000, SEEK_END)
+        assert vr.sample_position == total - 1000 and abs(vr.time_position - (total - 1000) / vr.sample_rate) < 1e-12
+        buf = np.zeros(500 * C, np.float32)
+        assert vr.read_samples(buf, 0, buf.size) == buf.size and float(np.abs(buf - pcm[(total - 1000) * C: (total - 500) * C]).max()) <= 1e-5
+        vr.seek_to(300, SEEK_CURRENT)                      # SamplePosition - 300
+        assert vr.sample_position == total - 500 - 300
+        vr.time_position = 0.01
+        assert vr.sample_position == int(vr.sample_rate * 0.01)
+        vr.sample_position = 77
+        assert vr.sample_position == 77 and vr.read_samples(buf, 0, 2 * C) == 2 * C and float(np.abs(buf[: 2 * C] - pcm[77 * C: 79 * C]).max()) <= 1e-5
 
 
 def test_seek_on_cpu_shim():
