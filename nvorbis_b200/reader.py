@@ -21,25 +21,20 @@ class VorbisReader:
     def __init__(self, source, device: int = 0, batch_packets: int = 4096, clip_samples: bool = True,
                  unpack_threads: int = 0, lib_path: str | None = None, gpu_unpack: bool | None = None, stream_index: int = 0):
         # stream_index: which logical stream of a multi-stream container (VorbisReader.Streams / SwitchStreams, VorbisReader.cs:96-150)
+        self._container = None                  # the container's bytes (kept for SwitchStreams)
         if isinstance(source, (bytes, bytearray, memoryview)):
-            self._host = hostlib.HostStream(data=bytes(source), stream_index=stream_index)
+            self._container = bytes(source)
         elif isinstance(source, str):
             with open(source, "rb") as f:
-                self._host = hostlib.HostStream(data=f.read(), stream_index=stream_index)
+                self._container = f.read()
+        if self._container is not None:
+            self._host = hostlib.HostStream(data=self._container, stream_index=stream_index)
         else:                                   # (data, sizes, granules, flags): an IPacketProvider's packets
             self._host = hostlib.HostStream(packets=tuple(source))
+        self._stream_index = int(stream_index) if self._container is not None else 0
         self._ctx = capi.Context(device, lib_path=lib_path)
-        self._ctx.upload_setup(self._host.setup())
-        # GPU-side packet unpack (nvb_decode_packets): the host only pages the container and reads each packet's first bits;
-        # None = use it whenever the setup is covered by the device tables, False = host unpacker (nvh_unpack) + nvb_decode_batch
-        self._gpu_unpack = False
-        if gpu_unpack is None or gpu_unpack:
-            try:
-                self._ctx.upload_unpack_tables(self._host.unpack_tables())
-                self._gpu_unpack = True
-            except (hostlib.HostError, capi.NvbError):
-                if gpu_unpack:
-                    raise
+        self._want_gpu_unpack = gpu_unpack
+        self._install_setup()
         self._batch_packets = int(batch_packets)
         self._skip = 0                                  # floats to drop after a seek (roll-forward, StreamDecoder.cs:626)
         self._total = None
@@ -53,6 +48,48 @@ class VorbisReader:
         self._samples_read = 0
         self._inflight = None                           # (HostBatch, pcm buffer) of the batch begun and not yet ended
         self._unpack_done = False                       # the host unpacker reached the end of the stream
+
+    def _install_setup(self):
+        """Uploads the current logical stream's setup (and, where wanted and covered, its unpack tables) to the GPU context."""
+        self._ctx.upload_setup(self._host.setup())
+        # GPU-side packet unpack (nvb_decode_packets): the host only pages the container and reads each packet's first bits;
+        # None = use it whenever the setup is covered by the device tables, False = host unpacker (nvh_unpack) + nvb_decode_batch
+        self._gpu_unpack = False
+        if self._want_gpu_unpack is None or self._want_gpu_unpack:
+            try:
+                self._ctx.upload_unpack_tables(self._host.unpack_tables())
+                self._gpu_unpack = True
+            except (hostlib.HostError, capi.NvbError):
+                if self._want_gpu_unpack:
+                    raise
+
+    # ---- logical streams of a multiplexed / chained container (VorbisReader.Streams, StreamIndex, SwitchStreams: VorbisReader.cs:116,184-190,291-305)
+    @property
+    def stream_count(self) -> int:
+        return hostlib.ogg_stream_count(self._container) if self._container is not None else 1
+
+    @property
+    def stream_index(self) -> int:
+        return self._stream_index
+
+    def switch_streams(self, index: int) -> bool:
+        """SwitchStreams(index): decode another logical stream from its start; True when its channel count or sample rate differs from
+        the stream decoded before.  The clipping setting carries over (VorbisReader.cs:299-300)."""
+        if index < 0 or index >= self.stream_count:
+            raise IndexError("index")                                            # ArgumentOutOfRangeException
+        if index == self._stream_index:
+            return False
+        old = (self.channels, self.sample_rate)
+        if self._inflight is not None:
+            self._ctx.decode_batch_end(); self._inflight = None
+        self._host.close()
+        self._host = hostlib.HostStream(data=self._container, stream_index=index)
+        self._stream_index = index
+        self._ctx.reset()
+        self._install_setup()
+        self._pcm, self._pos, self._eos, self._started = np.zeros(0, np.float32), 0, False, False
+        self._samples_read, self._skip, self._unpack_done, self._total, self._has_clipped = 0, 0, False, None, False
+        return (self.channels, self.sample_rate) != old
 
     # ---- properties of IVorbisReader / IStreamDecoder used by TestApp ---------------------------------
     @property

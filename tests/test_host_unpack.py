@@ -138,6 +138,23 @@ def test_multi_stream_container():
             np.testing.assert_array_equal(arr_a, arr_b)
     with pytest.raises(hostlib.HostError):
         hostlib.HostStream(data=data, stream_index=2)
+    # the reader mirror on the multiplexed container: StreamCount / StreamIndex / SwitchStreams (on the CUDA-on-CPU shim here)
+    from nvorbis_b200.reader import VorbisReader
+    alone = []
+    for blob in blobs:                                              # each remuxed stream on its own (the remux moves the end-of-stream granule: not the original file's trim)
+        with VorbisReader(blob, batch_packets=64, lib_path=H.build_shim(), gpu_unpack=False) as one:
+            alone.append(one.read_all(chunk_seconds=0.5))
+    with VorbisReader(data, batch_packets=64, lib_path=H.build_shim(), gpu_unpack=False) as vr:
+        assert vr.stream_count == 2 and vr.stream_index == 0 and vr.channels == 2
+        first = vr.read_all(chunk_seconds=0.5)
+        np.testing.assert_array_equal(first, alone[1])
+        assert float(np.abs(first[:100000] - H.decoded("3test")[1][:100000]).max()) <= 1e-5
+        assert vr.switch_streams(1) is True and vr.stream_index == 1 and vr.channels == 1       # stereo 3test -> mono 1test: the properties differ
+        second = vr.read_all(chunk_seconds=0.5)
+        np.testing.assert_array_equal(second, alone[0])
+        assert vr.switch_streams(1) is False
+        with pytest.raises(IndexError):
+            vr.switch_streams(2)
 
 
 def test_forward_only_feed_equals_whole_file():
