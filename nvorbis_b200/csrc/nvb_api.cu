@@ -561,7 +561,16 @@ static int decode_begin_impl(nvb_ctx* ctx, const nvb_batch* batch, const nvb_pac
         else { if ((rc = grow(ctx, sl.d_pcm16, sl.pcm16_cap, n_out)) != NVB_OK) { cudaStreamSynchronize(st_up); return rc; } d_s16 = sl.d_pcm16; }
     }
     const int nf = (int)b->plan.frames.size();
-    const int n_chunks = ((chunked_inputs || pbatch) && nf >= chunk_min && nf >= 8) ? NVB_CHUNKS : 1;
+    // How many chunks: four when this is the only batch in flight (the synchronous nvb_decode_batch: chunk k's PCM crosses PCIe while
+    // chunk k + 1 computes).  When the caller keeps a batch in flight, the read-back of the batch before this one already covers this
+    // batch's upload and kernels, and every extra copy costs: one chunk for float PCM to the host (4096 stereo frames: 0.609 vs
+    // 0.646 ms per step, 6.73 vs 6.34 M frames/s), two for 16-bit PCM (its read-back is short enough to need the finer overlap: 11.3 vs
+    // 10.0 M), four when nothing is read back.  NVB_N_CHUNKS overrides (profiles/e2e_quick.py).
+    static const int chunks_cfg = std::getenv("NVB_N_CHUNKS") ? std::atoi(std::getenv("NVB_N_CHUNKS")) : 0;
+    int chunks_max = NVB_CHUNKS;
+    if (ctx->in_flight >= 1 && !dev_out) chunks_max = s16 ? 2 : 1;
+    if (chunks_cfg >= 1) chunks_max = chunks_cfg > NVB_CHUNKS ? NVB_CHUNKS : chunks_cfg;
+    const int n_chunks = ((chunked_inputs || pbatch) && nf >= chunk_min && nf >= 8) ? chunks_max : 1;
     if (n_chunks == 1 && chunked_inputs) {                                  // few decoded frames after all: upload everything now
         const size_t n_posts = (size_t)batch->n_frames * ctx->H.channels * ctx->H.post_stride;
         if (n_posts) NVB_CUDA(ctx, cudaMemcpyAsync(b->d_posts, batch->posts, n_posts * sizeof(int16_t), cudaMemcpyHostToDevice, st_up));
