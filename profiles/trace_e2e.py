@@ -17,10 +17,11 @@ for s in range(3):
     hbs.append(capi.HostBatch(pinned(hb.frames), pinned(hb.posts), pinned(hb.classes), pinned(hb.entries)))
 outs = [torch.empty(4096 * 1024 * 2 + 64, dtype=torch.float32).pin_memory() for _ in range(2)]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+FLAGS = capi.RUN_PCM_S16 if len(sys.argv) > 2 and sys.argv[2] == "s16" else capi.RUN_DEFAULT
 t0 = time.perf_counter()
 for i in range(n):
     tb = time.perf_counter()
-    ctx.decode_batch_begin(hbs[i % 3], capi.RUN_DEFAULT, outs[i & 1].data_ptr(), outs[i & 1].numel())
+    ctx.decode_batch_begin(hbs[i % 3], FLAGS, outs[i & 1].data_ptr(), outs[i & 1].numel() * (2 if FLAGS & capi.RUN_PCM_S16 else 1))
     print(f"host: begin {i} at {1e3*(tb-t0):.3f} ms took {1e3*(time.perf_counter()-tb):.3f} ms", file=sys.stderr)
     if i >= 1:
         ctx.decode_batch_end(); print(f"host: end {i-1} returned at {1e3*(time.perf_counter()-t0):.3f} ms", file=sys.stderr)
