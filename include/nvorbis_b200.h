@@ -38,6 +38,7 @@ extern "C" {
 #define NVB_MAX_CLASSES    64    /* residue classifications: 6 bits + 1         (Residue0.cs:41) */
 #define NVB_MAX_STAGES     8     /* cascade: 3 + 5 bits                          (Residue0.cs:48-56) */
 #define NVB_MAX_COUPLING   256   /* 8 bits + 1 (Mapping.cs:28): every step count the reference accepts */
+#define NVB_MAX_IN_FLIGHT  3     /* batches between nvb_decode_batch_begin and _end */
 
 typedef enum nvb_status {
     NVB_OK = 0,
@@ -263,8 +264,9 @@ int nvb_decode_batch(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm
 
 /* The same call split in two, so that a host which unpacks the next run of packets while the GPU works (the batching
  * StreamDecoder.Read loop, StreamDecoder.cs:320-389) keeps PCIe busy in both directions: _begin enqueues the H2D copies,
- * the kernels and the D2H copy into pcm_out and returns; _end waits for the OLDEST batch begun and reports it.  At most two
- * batches may be in flight (a third _begin returns NVB_ERR_STATE); batches complete in the order they were begun and chain
+ * the kernels and the D2H copy into pcm_out and returns; _end waits for the OLDEST batch begun and reports it.  At most
+ * NVB_MAX_IN_FLIGHT batches may be in flight (one more _begin returns NVB_ERR_STATE; two keep the float read-back busy, a third
+ * pays when the read-back is short: 16-bit PCM, device output); batches complete in the order they were begun and chain
  * their overlap tails exactly like consecutive nvb_decode_batch calls (NVB_RUN_CONTINUE).  The batch arrays and pcm_out of a
  * batch must stay alive and untouched until its _end; keep them in nvb_host_alloc memory for the copies to be asynchronous. */
 int nvb_decode_batch_begin(nvb_ctx* ctx, const nvb_batch* batch, int flags, float* pcm_out, size_t pcm_cap);

@@ -14,6 +14,7 @@ import numpy as np
 
 ABI_VERSION = 3
 MAX_CHANNELS, MAX_POSTS, MAX_CLASSES, MAX_STAGES, MAX_COUPLING = 32, 64, 64, 8, 256
+MAX_IN_FLIGHT = 3                                   # NVB_MAX_IN_FLIGHT: batches between decode_batch_begin and decode_batch_end
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_STATE, ERR_CAPACITY, ERR_DATA = 0, -1, -2, -3, -4, -5, -6, -7
 FRAME_OK, FRAME_FAILED = 0, 1

@@ -42,7 +42,7 @@ struct nvb_ctx {
         Counters* h_counters = nullptr;      // pinned
         DevFrame* h_frames = nullptr; size_t h_frames_cap = 0;   // pinned copy of the plan: its upload must not block the host
         int rc = NVB_OK;                     // failure detected while enqueuing (reported by _end)
-    } slot[2];
+    } slot[NVB_MAX_IN_FLIGHT];
     int head = 0, in_flight = 0;
     // GPU-side packet unpack: the unpack tables (nvb_upload_unpack_tables)
     unsigned char* d_utab = nullptr; bool has_unpack = false; nvbu::UHeader UH; UnpackTables UT;
@@ -409,7 +409,7 @@ int nvb_create(int device, nvb_ctx** out) {
     DeviceGuard g(device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->chunk_stream[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    for (int i = 0; i < NVB_MAX_IN_FLIGHT && e == cudaSuccess; i++) {
         e = cudaEventCreateWithFlags(&ctx->slot[i].ev_all, cudaEventDisableTiming);
         for (int k = 0; k < NVB_CHUNKS && e == cudaSuccess; k++) {
             e = cudaEventCreateWithFlags(&ctx->slot[i].ev_up[k], cudaEventDisableTiming);
@@ -428,8 +428,8 @@ int nvb_destroy(nvb_ctx* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->d_blob); cudaFree(ctx->d_carry[0]); cudaFree(ctx->d_carry[1]); cudaFree(ctx->d_utab);
     cudaStreamDestroy(ctx->stream);
-    for (int i = 0; i < 2; i++) {
-        cudaStreamDestroy(ctx->chunk_stream[i]);
+    for (int i = 0; i < 2; i++) cudaStreamDestroy(ctx->chunk_stream[i]);
+    for (int i = 0; i < NVB_MAX_IN_FLIGHT; i++) {
         free_dbatch(ctx->slot[i].staging); cudaFree(ctx->slot[i].d_pcm); cudaFree(ctx->slot[i].d_pcm16);
         cudaEventDestroy(ctx->slot[i].ev_all);
         for (int k = 0; k < NVB_CHUNKS; k++) { cudaEventDestroy(ctx->slot[i].ev_up[k]); cudaEventDestroy(ctx->slot[i].ev_k[k]); }
@@ -522,9 +522,9 @@ int nvb_decode_packets(nvb_ctx* ctx, const nvb_packet_batch* batch, int flags, f
 static int decode_begin_impl(nvb_ctx* ctx, const nvb_batch* batch, const nvb_packet_batch* pbatch, int flags, float* pcm_out, size_t pcm_cap) {
     if (!ctx) return set_err(nullptr, NVB_ERR_ARG, "ctx is NULL");
     if (!ctx->has_setup) return set_err(ctx, NVB_ERR_STATE, "no setup uploaded");
-    if (ctx->in_flight >= 2) return set_err(ctx, NVB_ERR_STATE, "two batches are already in flight: call nvb_decode_batch_end first");
+    if (ctx->in_flight >= NVB_MAX_IN_FLIGHT) return set_err(ctx, NVB_ERR_STATE, "NVB_MAX_IN_FLIGHT batches are already in flight: call nvb_decode_batch_end first");
     DeviceGuard g(ctx->device);
-    nvb_ctx::Slot& sl = ctx->slot[(ctx->head + ctx->in_flight) & 1];
+    nvb_ctx::Slot& sl = ctx->slot[(ctx->head + ctx->in_flight) % NVB_MAX_IN_FLIGHT];
     if (!sl.staging) { sl.staging = new (std::nothrow) nvb_dbatch(); if (!sl.staging) return set_err(ctx, NVB_ERR_NOMEM, "host allocation failed"); }
     nvb_dbatch* b = sl.staging;
     static const int chunk_min = std::getenv("NVB_CHUNK_MIN") ? std::atoi(std::getenv("NVB_CHUNK_MIN")) : 1024;   // test hook
@@ -642,7 +642,7 @@ int nvb_decode_batch_end(nvb_ctx* ctx, nvb_result* res) {
     if (ctx->in_flight <= 0) return set_err(ctx, NVB_ERR_STATE, "no batch in flight");
     DeviceGuard g(ctx->device);
     nvb_ctx::Slot& sl = ctx->slot[ctx->head];
-    ctx->head ^= 1; ctx->in_flight--;
+    ctx->head = (ctx->head + 1) % NVB_MAX_IN_FLIGHT; ctx->in_flight--;
     NVB_CUDA(ctx, cudaEventSynchronize(sl.ev_all));
 #if !defined(NVB_CPU_SHIM)
     g_trace.dump(g_trace.batch - ctx->in_flight);

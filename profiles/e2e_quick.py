@@ -17,18 +17,19 @@ for s in range(6):
     hbs.append(capi.HostBatch(pinned(hb.frames), pinned(hb.posts), pinned(hb.classes), pinned(hb.entries)))
 n = 4095 * 1024 * 2 + 16
 for flags, dt, name in ((capi.RUN_DEFAULT, torch.float32, "float"), (capi.RUN_PCM_S16, torch.int16, "s16"), (capi.RUN_DEVICE_OUT, torch.float32, "device_out")):
-    outs = [torch.empty(n, dtype=dt, device="cuda") if flags & capi.RUN_DEVICE_OUT else torch.empty(n, dtype=dt).pin_memory() for _ in range(2)]
+  for depth in (2, 3):
+    outs = [torch.empty(n, dtype=dt, device="cuda") if flags & capi.RUN_DEVICE_OUT else torch.empty(n, dtype=dt).pin_memory() for _ in range(depth)]
     def loop(steps):
         for i in range(steps):
-            ctx.decode_batch_begin(hbs[i % 6], flags, outs[i & 1].data_ptr(), outs[i & 1].numel())
-            if i >= 1: ctx.decode_batch_end()
-        ctx.decode_batch_end()
+            ctx.decode_batch_begin(hbs[i % 6], flags, outs[i % depth].data_ptr(), outs[i % depth].numel())
+            if i >= depth - 1: ctx.decode_batch_end()
+        for _ in range(depth - 1): ctx.decode_batch_end()
     loop(12); torch.cuda.synchronize()
     reps = []
     for _ in range(5):
         t0 = time.perf_counter(); loop(200); torch.cuda.synchronize(); reps.append((time.perf_counter() - t0) / 200)
     ms = float(np.median(reps)) * 1e3
-    print(name, "ms/step", round(ms, 4), "M frames/s", round(4096 / ms / 1e3, 3), "env", {k: v for k, v in os.environ.items() if k.startswith("NVB_")})
+    print(name, "in flight", depth, "ms/step", round(ms, 4), "M frames/s", round(4096 / ms / 1e3, 3), "env", {k: v for k, v in os.environ.items() if k.startswith("NVB_")})
 
 # the synchronous call (one batch at a time)
 out = torch.empty(n, dtype=torch.float32).pin_memory()

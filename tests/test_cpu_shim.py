@@ -214,30 +214,32 @@ def test_slot_ring_wraps_with_mixed_windows(shim):
 
 
 def test_begin_end_pipeline_matches_sync(shim):
-    """nvb_decode_batch_begin/_end with two batches in flight: the same PCM as consecutive nvb_decode_batch calls,
-    tails chained across the batches; a third begin is refused."""
+    """nvb_decode_batch_begin/_end with two and with NVB_MAX_IN_FLIGHT (three) batches in flight: the same PCM as consecutive
+    nvb_decode_batch calls, tails chained across the batches; one begin more is refused."""
     r, pcm, b, ctx = _ctx(shim, "1test")
     n = len(b.frames)
     cuts = [0, 5, 9, 16, n]
     hbs = [H.batch_from_boundary(b, ctx.post_stride, cuts[i], cuts[i + 1]) for i in range(4)]
     outs = [np.zeros(capi.sum_output_bound(hb.frames) + 64, np.float32) for hb in hbs]
-    got, pending = [], []
-    for i, hb in enumerate(hbs):
-        ctx.decode_batch_begin(hb, capi.RUN_EXACT | (capi.RUN_CONTINUE if i else 0), outs[i].ctypes.data, outs[i].size)
-        pending.append(i)
-        if len(pending) == 2:
-            if i == 1:
-                with pytest.raises(capi.NvbError) as e:
-                    ctx.decode_batch_begin(hbs[2], capi.RUN_EXACT | capi.RUN_CONTINUE, outs[2].ctypes.data, outs[2].size)
-                assert e.value.status == capi.ERR_STATE
+    for depth in (2, capi.MAX_IN_FLIGHT):
+        ctx.reset()
+        got, pending = [], []
+        for i, hb in enumerate(hbs):
+            ctx.decode_batch_begin(hb, capi.RUN_EXACT | (capi.RUN_CONTINUE if i else 0), outs[i].ctypes.data, outs[i].size)
+            pending.append(i)
+            if len(pending) == depth:
+                if depth == capi.MAX_IN_FLIGHT and i == depth - 1:
+                    with pytest.raises(capi.NvbError) as e:
+                        ctx.decode_batch_begin(hbs[depth], capi.RUN_EXACT | capi.RUN_CONTINUE, outs[depth].ctypes.data, outs[depth].size)
+                    assert e.value.status == capi.ERR_STATE
+                j = pending.pop(0)
+                res = ctx.decode_batch_end()
+                got.append(outs[j][: res.samples_per_channel].copy())
+        while pending:
             j = pending.pop(0)
             res = ctx.decode_batch_end()
             got.append(outs[j][: res.samples_per_channel].copy())
-    while pending:
-        j = pending.pop(0)
-        res = ctx.decode_batch_end()
-        got.append(outs[j][: res.samples_per_channel].copy())
-    np.testing.assert_array_equal(np.concatenate(got), pcm)
+        np.testing.assert_array_equal(np.concatenate(got), pcm)
     with pytest.raises(capi.NvbError) as e:
         ctx.decode_batch_end()
     assert e.value.status == capi.ERR_STATE

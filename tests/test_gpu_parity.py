@@ -331,19 +331,21 @@ def test_begin_end_pipeline_matches_sync_on_gpu():
         want.append(out.copy())
     ctx.reset()
     outs = [np.zeros((capi.sum_output_bound(hb.frames) + 64) * 2, np.float32) for hb in hbs]
-    got, pending, clipped = [], [], False
-    for i, hb in enumerate(hbs):
-        ctx.decode_batch_begin(hb, capi.RUN_DEFAULT | (capi.RUN_CONTINUE if i else 0), outs[i].ctypes.data, outs[i].size)
-        pending.append(i)
-        if len(pending) == 2:
+    for depth in (2, capi.MAX_IN_FLIGHT):
+        ctx.reset()
+        got, pending, clipped = [], [], False
+        for i, hb in enumerate(hbs):
+            ctx.decode_batch_begin(hb, capi.RUN_DEFAULT | (capi.RUN_CONTINUE if i else 0), outs[i].ctypes.data, outs[i].size)
+            pending.append(i)
+            if len(pending) == depth:
+                j = pending.pop(0); res = ctx.decode_batch_end(); clipped |= res.has_clipped
+                got.append(outs[j][: res.samples_per_channel * 2].copy())
+        while pending:
             j = pending.pop(0); res = ctx.decode_batch_end(); clipped |= res.has_clipped
             got.append(outs[j][: res.samples_per_channel * 2].copy())
-    while pending:
-        j = pending.pop(0); res = ctx.decode_batch_end(); clipped |= res.has_clipped
-        got.append(outs[j][: res.samples_per_channel * 2].copy())
-    for g, w in zip(got, want):
-        np.testing.assert_array_equal(g, w)
-    assert clipped and float(np.abs(np.concatenate(got) - pcm).max()) <= TOL
+        for g, w in zip(got, want):
+            np.testing.assert_array_equal(g, w)
+        assert clipped and float(np.abs(np.concatenate(got) - pcm).max()) <= TOL
     ctx.close()
 
 
