@@ -405,7 +405,7 @@ class Context:
         return out[: int(r.samples_per_channel) * self.channels], _result(r)
 
     def decode_batch_begin(self, batch: HostBatch, flags: int, out_ptr: int, out_floats: int) -> None:
-        """nvb_decode_batch_begin: enqueue H2D + synthesis + D2H and return (up to two batches in flight; the batch's host
+        """nvb_decode_batch_begin: enqueue H2D + synthesis + D2H and return (up to MAX_IN_FLIGHT = 3 batches in flight; the batch's host
         buffers must stay alive and untouched until its decode_batch_end)."""
         self._check(self.lib.nvb_decode_batch_begin(self.handle, C.byref(batch.struct), flags, out_ptr, out_floats), "nvb_decode_batch_begin")
 
