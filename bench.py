@@ -536,15 +536,16 @@ def run_ours(args):
 
     # ---- the same end-to-end pipeline with 16-bit PCM out (NVB_RUN_PCM_S16: half the read-back) and with the PCM left on the
     #      device (NVB_RUN_DEVICE_OUT: an on-device consumer; only the inputs cross PCIe) ----
-    out16 = [torch.empty(samples * C + 16, dtype=torch.int16).pin_memory() for _ in range(2)]
-    dev_out = [torch.empty(samples * C + 16, dtype=torch.float32, device=dev) for _ in range(2)]
+    DEPTH = capi.MAX_IN_FLIGHT                          # these two legs keep three batches in flight: their read-back is short or absent
+    out16 = [torch.empty(samples * C + 16, dtype=torch.int16).pin_memory() for _ in range(DEPTH)]
+    dev_out = [torch.empty(samples * C + 16, dtype=torch.float32, device=dev) for _ in range(DEPTH)]
 
     def pipelined_flags(n, flags, bufs):
         for i in range(n):
-            ctx.decode_batch_begin(host_batches[i % ROTATE], flags, bufs[i & 1].data_ptr(), bufs[i & 1].numel())
-            if i >= 1:
+            ctx.decode_batch_begin(host_batches[i % ROTATE], flags, bufs[i % DEPTH].data_ptr(), bufs[i % DEPTH].numel())
+            if i >= DEPTH - 1:
                 ctx.decode_batch_end()
-        if n >= 1:
+        for _ in range(min(n, DEPTH - 1)):
             ctx.decode_batch_end()
 
     pipelined_flags(2 * ROTATE, capi.RUN_PCM_S16, out16)
@@ -650,9 +651,9 @@ def run_ours(args):
                     "host_ms_in_begin_per_step": host_begin_per_step, "timing": t_e2e.stats(), "pcie_d2h_gbs_measured": d2h_gbs,
                     "pcie_bound_frames_per_s": world * FRAMES_PER_STEP / (samples * C * 4 / (d2h_gbs * 1e9)),
                     "s16_value": frames_total / (t_e2e_s16.ms * 1e-3), "s16_d2h_bytes_per_step": int(samples * C * 2),
-                    "s16_api": "NVB_RUN_PCM_S16: 16-bit PCM quantised on the device, half the read-back",
+                    "s16_api": "NVB_RUN_PCM_S16: 16-bit PCM quantised on the device, half the read-back (three batches in flight)",
                     "device_out_value": frames_total / (t_e2e_dev.ms * 1e-3),
-                    "device_out_api": "NVB_RUN_DEVICE_OUT: PCM left in a device buffer of the caller (on-device consumer), d2h 0 bytes"},
+                    "device_out_api": "NVB_RUN_DEVICE_OUT: PCM left in a device buffer of the caller (on-device consumer), d2h 0 bytes (three batches in flight)"},
             "one_kernel": one_kernel,
             "strong_64k": strong,
             "ogg_to_pcm": ogg,

@@ -565,10 +565,11 @@ static int decode_begin_impl(nvb_ctx* ctx, const nvb_batch* batch, const nvb_pac
     // chunk k + 1 computes).  When the caller keeps a batch in flight, the read-back of the batch before this one already covers this
     // batch's upload and kernels, and every extra copy costs: one chunk for float PCM to the host (4096 stereo frames: 0.609 vs
     // 0.646 ms per step, 6.73 vs 6.34 M frames/s), two for 16-bit PCM (its read-back is short enough to need the finer overlap: 11.3 vs
-    // 10.0 M), four when nothing is read back.  NVB_N_CHUNKS overrides (profiles/e2e_quick.py).
+    // 10.0 M), one when the PCM stays on the device (then the host side of _begin is the bound, and every chunk is a handful of driver
+    // calls: 24.1 vs 23.3 M with two batches in flight, 29.7 M with three).  NVB_N_CHUNKS overrides (profiles/e2e_quick.py).
     static const int chunks_cfg = std::getenv("NVB_N_CHUNKS") ? std::atoi(std::getenv("NVB_N_CHUNKS")) : 0;
     int chunks_max = NVB_CHUNKS;
-    if (ctx->in_flight >= 1 && !dev_out) chunks_max = s16 ? 2 : 1;
+    if (ctx->in_flight >= 1) chunks_max = (s16 && !dev_out) ? 2 : 1;
     if (chunks_cfg >= 1) chunks_max = chunks_cfg > NVB_CHUNKS ? NVB_CHUNKS : chunks_cfg;
     const int n_chunks = ((chunked_inputs || pbatch) && nf >= chunk_min && nf >= 8) ? chunks_max : 1;
     if (n_chunks == 1 && chunked_inputs) {                                  // few decoded frames after all: upload everything now
